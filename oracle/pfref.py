@@ -1,0 +1,211 @@
+"""ctypes binding of oracle/_ref/libpfref.so -- the UNMODIFIED reference compiled by
+oracle/Makefile (`make ref`).  TEST INFRASTRUCTURE: imported only by tests/, the golden-vector
+generator, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpfref.so")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH)
+        L = _lib
+        L.pfref_map_new.restype = C.c_void_p
+        L.pfref_map_new.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float]
+        L.pfref_map_free.argtypes = [C.c_void_p]
+        L.pfref_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pfref_get_portals.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.pfref_get_portal_edges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.pfref_flow_field_tile.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+        L.pfref_flow_field_portal.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+        L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pfref_request_path.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
+        L.pfref_dest_id.restype = C.c_uint32
+        L.pfref_dest_id.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.pfref_fc_get_flow.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.pfref_fc_get_los.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+        L.pfref_fc_clear.argtypes = [C.c_void_p]
+        L.pfref_desired_velocity.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.pfref_blockers.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
+        L.pfref_update.argtypes = [C.c_void_p]
+        L.pfref_clearpath.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.pfref_agents_set.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.pfref_ents_in_circle.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int]
+        L.pfref_work_set.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfref_velocity_work.argtypes = [C.c_int, C.c_int]
+        L.pfref_velocity_work_mt.restype = C.c_double
+        L.pfref_velocity_work_mt.argtypes = [C.c_int]
+        L.pfref_work_get.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_vpref.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_fields_mt.restype = C.c_double
+        L.pfref_fields_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RefMap:
+    """One reference nav context (N_NewCtxForMapData) over a synthetic pathable-tile grid."""
+
+    def __init__(self, chunk_w, chunk_h, pathable, map_x=0.0, map_z=0.0):
+        pathable = np.ascontiguousarray(pathable, dtype=np.uint8)
+        assert pathable.shape == (chunk_h * 32, chunk_w * 32)
+        self.cw, self.ch = chunk_w, chunk_h
+        self.map_x, self.map_z = float(map_x), float(map_z)
+        self.h = lib().pfref_map_new(chunk_w, chunk_h, _p(pathable), map_x, map_z)
+        if not self.h:
+            raise RuntimeError("pfref_map_new failed")
+
+    def close(self):
+        if self.h:
+            lib().pfref_map_free(self.h)
+            self.h = None
+
+    def field(self, layer, kind):
+        dt = np.uint8 if kind == 0 else np.uint16
+        out = np.zeros((self.ch * self.cw, 64, 64), dtype=dt)
+        lib().pfref_get_field(self.h, layer, kind, _p(out))
+        return out
+
+    def cost_base(self, layer=0): return self.field(layer, 0)
+    def blockers(self, layer=0): return self.field(layer, 1)
+    def islands(self, layer=0): return self.field(layer, 2)
+    def local_islands(self, layer=0): return self.field(layer, 3)
+
+    def portals(self, layer=0):
+        n = lib().pfref_get_portals(self.h, layer, None, 0)
+        out = np.zeros((n, 10), dtype=np.int32)
+        lib().pfref_get_portals(self.h, layer, _p(out), n)
+        return out
+
+    def portal_edges(self, layer, chunk_idx, portal_idx):
+        out = np.zeros((64, 3), dtype=np.uint32)
+        n = lib().pfref_get_portal_edges(self.h, layer, chunk_idx, portal_idx, _p(out), 64)
+        return out[:n]
+
+    def flow_tile(self, chunk, tile, layer=0, faction=0xF, inout=None):
+        init = inout is None
+        buf = np.zeros(4096, dtype=np.uint8) if init else np.ascontiguousarray(inout, dtype=np.uint8).reshape(-1).copy()
+        lib().pfref_flow_field_tile(self.h, layer, chunk[0], chunk[1], tile[0], tile[1], faction, int(init), _p(buf))
+        return buf.reshape(64, 64)
+
+    def flow_portal(self, chunk, portal_idx, port_iid, next_iid, layer=0, faction=0xF, inout=None):
+        init = inout is None
+        buf = np.zeros(4096, dtype=np.uint8) if init else np.ascontiguousarray(inout, dtype=np.uint8).reshape(-1).copy()
+        lib().pfref_flow_field_portal(self.h, layer, chunk[0], chunk[1], portal_idx, port_iid, next_iid,
+                                      faction, int(init), _p(buf))
+        return buf.reshape(64, 64)
+
+    def los(self, chunk, target_td, layer=0, prev=None, prev_chunk=(0, 0)):
+        out = np.zeros(4096, dtype=np.uint8)
+        pv = None if prev is None else np.ascontiguousarray(prev, dtype=np.uint8).reshape(-1)
+        lib().pfref_los_field(self.h, layer, chunk[0], chunk[1], target_td[0], target_td[1], target_td[2],
+                              target_td[3], _p(pv), prev_chunk[0], prev_chunk[1], _p(out))
+        return out.reshape(64, 64)
+
+    def request_path(self, src, dst, layer=0):
+        did = C.c_uint32(0)
+        ok = lib().pfref_request_path(self.h, layer, src[0], src[1], dst[0], dst[1], C.byref(did))
+        return bool(ok), did.value
+
+    def dest_id(self, dst, layer=0):
+        return lib().pfref_dest_id(self.h, layer, dst[0], dst[1])
+
+    def fc_flow(self, dest_id, chunk):
+        out = np.zeros(4096, dtype=np.uint8)
+        ffid = C.c_uint64(0)
+        ok = lib().pfref_fc_get_flow(self.h, dest_id, chunk[0], chunk[1], _p(out), C.byref(ffid))
+        return (out.reshape(64, 64), ffid.value) if ok else (None, None)
+
+    def fc_los(self, dest_id, chunk):
+        out = np.zeros(4096, dtype=np.uint8)
+        ok = lib().pfref_fc_get_los(self.h, dest_id, chunk[0], chunk[1], _p(out))
+        return out.reshape(64, 64) if ok else None
+
+    def fc_clear(self):
+        lib().pfref_fc_clear(self.h)
+
+    def desired_velocity(self, dest_id, pos, los_pos, dest_xz):
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        los_pos = np.ascontiguousarray(los_pos, dtype=np.float32)
+        n = pos.shape[0]
+        vdes = np.zeros((n, 2), dtype=np.float32)
+        los = np.zeros(n, dtype=np.uint8)
+        lib().pfref_desired_velocity(self.h, dest_id, n, _p(pos), _p(los_pos), dest_xz[0], dest_xz[1],
+                                     _p(vdes), _p(los))
+        return vdes, los
+
+    def blockers_incref(self, x, z, radius, faction=0, flags=0):
+        lib().pfref_blockers(self.h, 1, x, z, radius, faction, flags)
+
+    def blockers_decref(self, x, z, radius, faction=0, flags=0):
+        lib().pfref_blockers(self.h, 0, x, z, radius, faction, flags)
+
+    def update(self):
+        lib().pfref_update(self.h)
+
+    def agents_set(self, pos, prev_pos, vel, radius, max_speed, state, flags, flock_of,
+                   flock_target, flock_dest, hz=20):
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        n = len(radius)
+        self._keep = [f32(pos), f32(prev_pos), f32(vel), f32(radius), f32(max_speed),
+                      np.ascontiguousarray(state, dtype=np.int32), np.ascontiguousarray(flags, dtype=np.uint32),
+                      np.ascontiguousarray(flock_of, dtype=np.int32), f32(flock_target),
+                      np.ascontiguousarray(flock_dest, dtype=np.uint32)]
+        k = self._keep
+        lib().pfref_agents_set(self.h, n, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]),
+                               _p(k[7]), len(k[9]), _p(k[8]), _p(k[9]), hz)
+
+    def ents_in_circle(self, x, z, r, maxout=512):
+        out = np.zeros(maxout, dtype=np.uint32)
+        n = lib().pfref_ents_in_circle(x, z, r, _p(out), maxout)
+        return out[:n].copy()
+
+    def work_set(self, uids, vdes, has_los, speed):
+        uids = np.ascontiguousarray(uids, dtype=np.uint32)
+        vdes = np.ascontiguousarray(vdes, dtype=np.float32)
+        has_los = np.ascontiguousarray(has_los, dtype=np.uint8)
+        speed = np.ascontiguousarray(speed, dtype=np.float32)
+        self._nwork = len(uids)
+        lib().pfref_work_set(self._nwork, _p(uids), _p(vdes), _p(has_los), _p(speed))
+
+    def velocity_work(self, nthreads=1):
+        secs = lib().pfref_velocity_work_mt(nthreads)
+        out = np.zeros((self._nwork, 2), dtype=np.float32)
+        lib().pfref_work_get(self._nwork, _p(out))
+        return out, secs
+
+    def vpref(self):
+        out = np.zeros((self._nwork, 2), dtype=np.float32)
+        lib().pfref_vpref(self._nwork, _p(out))
+        return out
+
+    def fields_mt(self, what, reqs, nthreads=1, layer=0, want_out=False):
+        reqs = np.ascontiguousarray(reqs, dtype=np.int32)
+        n = reqs.shape[0]
+        out = np.zeros((n, 64, 64), dtype=np.uint8) if want_out else None
+        secs = lib().pfref_fields_mt(self.h, layer, what, _p(reqs), n, nthreads, _p(out))
+        return secs, out
+
+
+def clearpath(self5, vpref, dyn, stat):
+    self5 = np.ascontiguousarray(self5, dtype=np.float32)
+    vpref = np.ascontiguousarray(vpref, dtype=np.float32)
+    dyn = np.ascontiguousarray(dyn, dtype=np.float32).reshape(-1, 5)
+    stat = np.ascontiguousarray(stat, dtype=np.float32).reshape(-1, 5)
+    out = np.zeros(2, dtype=np.float32)
+    lib().pfref_clearpath(_p(self5), _p(vpref), _p(dyn), dyn.shape[0], _p(stat), stat.shape[0], _p(out))
+    return out

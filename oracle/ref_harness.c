@@ -1,0 +1,735 @@
+/*
+ * oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY (never part of the product path).
+ *
+ * Thin C entry points (prefix pfref_) around the UNMODIFIED reference sources under
+ * /root/reference/src, compiled where they lie by oracle/Makefile into oracle/_ref/libpfref.so.
+ * This file #include's the reference's src/game/movement.c so that its `static` hot-path
+ * functions (move_velocity_work, point_seek_vpref, find_neighbours ... movement.c:1524-2023,
+ * 2768-2828, 3395-3466) are callable, and supplies the handful of engine services those
+ * translation units link against (gamestate getters backed by plain arrays, the M_Nav*
+ * one-line wrappers of src/map/map.c:555-1320, SDL atomics, scheduler no-ops).
+ *
+ * No reference source is copied into this repository: the include below resolves to the
+ * read-only checkout at build time (-I/root/reference/src).
+ *
+ * Used by: tests/ (golden-vector generation + parity), bench.py --impl reference and the
+ * cpu_baseline leg.  See oracle/README.md.
+ */
+#define _GNU_SOURCE
+#include <sched.h>
+#include <unistd.h>
+#include <pthread.h>
+#include "game/movement.c"
+
+#include "navigation/nav_private.h"
+#include "navigation/field.h"
+#include "navigation/fieldcache.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------
+ * A minimal `struct map`: the reference only ever reaches it through M_* accessors, all of
+ * which are provided below (map.c itself is not compiled: it drags in the renderer).
+ * ---------------------------------------------------------------------------------------- */
+struct map{
+    void   *nav_private;
+    vec3_t  pos;
+    size_t  width, height;          /* in chunks */
+    struct tile **chunk_tiles;      /* [height*width] -> tile[32*32] */
+};
+
+#define PFREF_EXPORT __attribute__((visibility("default")))
+
+/* khash instantiations that live in game.c / entity.c in the engine */
+__KHASH_IMPL(id,     extern, khint32_t, int,    1, kh_int_hash_func, kh_int_hash_equal)
+__KHASH_IMPL(range,  extern, khint32_t, float,  1, kh_int_hash_func, kh_int_hash_equal)
+__KHASH_IMPL(entity, extern, khint32_t, char,   0, kh_int_hash_func, kh_int_hash_equal)
+
+unsigned long g_frame_idx = 0;
+
+/* ------------------------------------------------------------------------------------------
+ * Engine services with real bodies
+ * ---------------------------------------------------------------------------------------- */
+
+void M_GetResolution(const struct map *map, struct map_resolution *out)
+{
+    /* map.c:946 */
+    out->chunk_w = map->width;
+    out->chunk_h = map->height;
+    out->tile_w = TILES_PER_CHUNK_WIDTH;
+    out->tile_h = TILES_PER_CHUNK_HEIGHT;
+    out->field_w = TILES_PER_CHUNK_WIDTH * X_COORDS_PER_TILE;
+    out->field_h = TILES_PER_CHUNK_HEIGHT * Z_COORDS_PER_TILE;
+}
+
+vec3_t M_GetCenterPos(const struct map *map)
+{
+    /* map.c:956 */
+    return (vec3_t){
+        map->pos.x - (map->width * TILES_PER_CHUNK_WIDTH * X_COORDS_PER_TILE)/2.0f,
+        map->pos.y,
+        map->pos.z + (map->height * TILES_PER_CHUNK_HEIGHT * Z_COORDS_PER_TILE)/2.0f,
+    };
+}
+
+vec3_t M_GetPos(const struct map *map) { return map->pos; }
+
+static struct box pfref_map_box(const struct map *map)
+{
+    return (struct box){
+        map->pos.x, map->pos.z,
+        map->width * TILES_PER_CHUNK_WIDTH * X_COORDS_PER_TILE,
+        map->height * TILES_PER_CHUNK_HEIGHT * Z_COORDS_PER_TILE,
+    };
+}
+
+bool M_NavPositionPathable(const struct map *map, enum nav_layer layer, vec2_t xz_pos)
+{
+    /* map.c:817 */
+    if(!C_BoxPointIntersection(xz_pos.x, xz_pos.z, pfref_map_box(map)))
+        return false;
+    return N_PositionPathable(xz_pos, layer, map->nav_private, map->pos);
+}
+
+bool M_NavPositionBlocked(const struct map *map, enum nav_layer layer, vec2_t xz_pos)
+{
+    /* map.c:831 */
+    if(!C_BoxPointIntersection(xz_pos.x, xz_pos.z, pfref_map_box(map)))
+        return false;
+    return N_PositionBlocked(xz_pos, layer, map->nav_private, map->pos);
+}
+
+vec2_t M_NavDesiredPointSeekVelocity(const struct map *map, dest_id_t id, vec2_t curr_pos, vec2_t xz_dest)
+{
+    return N_DesiredPointSeekVelocity(id, curr_pos, xz_dest, map->nav_private, map->pos);
+}
+
+bool M_NavHasDestLOS(const struct map *map, dest_id_t id, vec2_t curr_pos, vec2_t xz_dest)
+{
+    return N_HasDestLOS(id, curr_pos, map->nav_private, map->pos, xz_dest);
+}
+
+uint32_t G_FlagsGetFrom(khash_t(id) *table, uint32_t uid)
+{
+    khiter_t k = kh_get(id, table, uid);
+    assert(k != kh_end(table));
+    return kh_value(table, k);
+}
+
+int G_GetFactionIDFrom(khash_t(id) *table, uint32_t uid)
+{
+    khiter_t k = kh_get(id, table, uid);
+    assert(k != kh_end(table));
+    return kh_value(table, k);
+}
+
+float G_GetSelectionRadiusFrom(khash_t(range) *table, uint32_t uid)
+{
+    khiter_t k = kh_get(range, table, uid);
+    assert(k != kh_end(table));
+    return kh_value(table, k);
+}
+
+int Entity_NavLayerWithRadius(uint32_t flags, float radius)
+{
+    /* entity.c:554 */
+    bool water = !!(flags & ENTITY_FLAG_WATER);
+    bool air = !!(flags & ENTITY_FLAG_AIR);
+    if(radius >= 15.0f)
+        return water ? NAV_LAYER_WATER_7X7 : air ? NAV_LAYER_AIR_7X7 : NAV_LAYER_GROUND_7X7;
+    else if(radius >= 10.0f)
+        return water ? NAV_LAYER_WATER_5X5 : air ? NAV_LAYER_AIR_5X5 : NAV_LAYER_GROUND_5X5;
+    else if(radius >= 5.0f)
+        return water ? NAV_LAYER_WATER_3X3 : air ? NAV_LAYER_AIR_3X3 : NAV_LAYER_GROUND_3X3;
+    else
+        return water ? NAV_LAYER_WATER_1X1 : air ? NAV_LAYER_AIR_1X1 : NAV_LAYER_GROUND_1X1;
+}
+
+/* Arrival / formation are inactive in every oracle scenario: the reference
+ * then falls through to the plain point-seek branch (movement.c:1516, 1752, 1888). */
+struct arrival_state *G_ArrivalGroup_ForLayer(const struct arrival_group *g, enum nav_layer layer) { return NULL; }
+bool G_Arrival_NeighbourSettling(const struct arrival_unit_state *us, vec2_t pos, float radius) { return false; }
+
+/* Scheduler / SDL / misc no-ops */
+bool     Sched_UsingBigStack(void) { return true; }
+void     Sched_TryYield(void) {}
+uint32_t Sched_ActiveTID(void) { return 0; }
+int  SDL_AtomicSet(SDL_atomic_t *a, int v) { int old = a->value; a->value = v; return old; }
+int  SDL_AtomicGet(SDL_atomic_t *a) { return a->value; }
+SDL_bool SDL_AtomicCAS(SDL_atomic_t *a, int oldval, int newval)
+{ return __sync_bool_compare_and_swap(&a->value, oldval, newval) ? SDL_TRUE : SDL_FALSE; }
+int  SDL_GetCPUCount(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+Uint32 SDL_GetTicks(void) { return 0; }
+void *mi_malloc(size_t n) { return malloc(n); }
+void *mi_calloc(size_t c, size_t n) { return calloc(c, n); }
+void *mi_realloc(void *p, size_t n) { return realloc(p, n); }
+void  mi_free(void *p) { free(p); }
+bool E_Global_Register(enum eventtype event, handler_t handler, void *user, int simmask) { return true; }
+bool E_Global_Unregister(enum eventtype event, handler_t handler) { return true; }
+
+void pfref_stub_abort(const char *name)
+{
+    fprintf(stderr, "[pfref] FATAL: unimplemented engine stub '%s' was called\n", name);
+    abort();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Exported oracle API
+ * ---------------------------------------------------------------------------------------- */
+
+static bool s_inited = false;
+
+PFREF_EXPORT int pfref_init(void)
+{
+    if(s_inited)
+        return 1;
+    if(!N_Init())
+        return 0;
+    s_inited = true;
+    return 1;
+}
+
+/* pathable: [chunk_h*32][chunk_w*32] map-tile flags (1 = flat pathable tile, 0 = not pathable).
+ * Every tile is TILETYPE_FLAT, base_height 0 (SURVEY.md 8a "Tile cost"). */
+PFREF_EXPORT void *pfref_map_new(int chunk_w, int chunk_h, const uint8_t *pathable,
+                                 float map_x, float map_z)
+{
+    pfref_init();
+    struct map *map = calloc(1, sizeof(struct map));
+    map->width = chunk_w;
+    map->height = chunk_h;
+    map->pos = (vec3_t){map_x, 0.0f, map_z};
+    map->chunk_tiles = calloc(chunk_w * chunk_h, sizeof(struct tile*));
+
+    const int TW = TILES_PER_CHUNK_WIDTH, TH = TILES_PER_CHUNK_HEIGHT;
+    for(int cr = 0; cr < chunk_h; cr++) {
+    for(int cc = 0; cc < chunk_w; cc++) {
+        struct tile *tiles = calloc(TW * TH, sizeof(struct tile));
+        for(int r = 0; r < TH; r++) {
+        for(int c = 0; c < TW; c++) {
+            size_t gr = cr * TH + r, gc = cc * TW + c;
+            struct tile *t = &tiles[r * TW + c];
+            t->pathable = pathable[gr * (chunk_w * TW) + gc] != 0;
+            t->type = TILETYPE_FLAT;
+            t->base_height = 0;
+            t->ramp_height = 0;
+        }}
+        map->chunk_tiles[cr * chunk_w + cc] = tiles;
+    }}
+    map->nav_private = N_NewCtxForMapData(chunk_w, chunk_h, TW, TH,
+        (const struct tile**)map->chunk_tiles, true);
+    if(!map->nav_private) {
+        free(map);
+        return NULL;
+    }
+    return map;
+}
+
+PFREF_EXPORT void pfref_map_free(void *m)
+{
+    struct map *map = m;
+    if(!map) return;
+    N_FC_ClearAll(((struct nav_private*)map->nav_private)->fieldcache);
+    N_FreeCtx(map->nav_private);
+    for(size_t i = 0; i < map->width * map->height; i++)
+        free(map->chunk_tiles[i]);
+    free(map->chunk_tiles);
+    free(map);
+}
+
+static struct nav_private *pfref_priv(void *m) { return ((struct map*)m)->nav_private; }
+
+/* kind: 0 cost_base(u8) 1 blockers(u16) 2 islands(u16) 3 local_islands(u16). out is
+ * [chunks][64][64] in chunk-row-major order. */
+PFREF_EXPORT void pfref_get_field(void *m, int layer, int kind, void *out)
+{
+    struct nav_private *priv = pfref_priv(m);
+    size_t n = priv->width * priv->height;
+    for(size_t i = 0; i < n; i++) {
+        const struct nav_chunk *ch = &priv->chunks[layer][i];
+        switch(kind) {
+        case 0: memcpy((uint8_t*)out  + i * 4096, ch->cost_base, 4096); break;
+        case 1: memcpy((uint16_t*)out + i * 4096, ch->blockers, 8192); break;
+        case 2: memcpy((uint16_t*)out + i * 4096, ch->islands, 8192); break;
+        case 3: memcpy((uint16_t*)out + i * 4096, ch->local_islands, 8192); break;
+        }
+    }
+}
+
+/* Portal table: 10 ints per portal {chunk_r, chunk_c, idx, ep0.r, ep0.c, ep1.r, ep1.c,
+ * conn_chunk_idx, conn_portal_idx, num_neighbours}. Returns the number of portals. */
+PFREF_EXPORT int pfref_get_portals(void *m, int layer, int32_t *out, int maxout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    int n = 0;
+    for(size_t i = 0; i < priv->width * priv->height; i++) {
+        const struct nav_chunk *ch = &priv->chunks[layer][i];
+        for(size_t p = 0; p < ch->num_portals; p++) {
+            const struct portal *port = &ch->portals[p];
+            if(n < maxout) {
+                int32_t *o = out + n * 10;
+                o[0] = port->chunk.r; o[1] = port->chunk.c; o[2] = (int)p;
+                o[3] = port->endpoints[0].r; o[4] = port->endpoints[0].c;
+                o[5] = port->endpoints[1].r; o[6] = port->endpoints[1].c;
+                o[7] = (int)(port->connected >> PORTAL_REF_PORTAL_BITS);
+                o[8] = (int)(port->connected & PORTAL_REF_PORTAL_MASK);
+                o[9] = (int)port->num_neighbours;
+            }
+            n++;
+        }
+    }
+    return n;
+}
+
+/* Edge table of one portal: 3 values per edge {neighbour_ref, state, cost(float bits)} */
+PFREF_EXPORT int pfref_get_portal_edges(void *m, int layer, int chunk_idx, int portal_idx,
+                                        uint32_t *out, int maxout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    const struct portal *port = &priv->chunks[layer][chunk_idx].portals[portal_idx];
+    int n = 0;
+    for(size_t e = 0; e < port->num_neighbours && n < maxout; e++, n++) {
+        out[n*3 + 0] = port->edges[e].neighbour;
+        out[n*3 + 1] = port->edges[e].es;
+        memcpy(&out[n*3 + 2], &port->edges[e].cost, 4);
+    }
+    return n;
+}
+
+static void pfref_flow_pack(const struct flow_field *ff, uint8_t *out)
+{
+    for(int r = 0; r < FIELD_RES_R; r++)
+    for(int c = 0; c < FIELD_RES_C; c++)
+        out[r * FIELD_RES_C + c] = ff->field[r][c].dir_idx;
+}
+
+static void pfref_flow_unpack(const uint8_t *in, struct flow_field *ff)
+{
+    for(int r = 0; r < FIELD_RES_R; r++)
+    for(int c = 0; c < FIELD_RES_C; c++)
+        ff->field[r][c].dir_idx = in[r * FIELD_RES_C + c];
+}
+
+static void pfref_los_pack(const struct LOS_field *lf, uint8_t *out)
+{
+    for(int r = 0; r < FIELD_RES_R; r++)
+    for(int c = 0; c < FIELD_RES_C; c++)
+        out[r * FIELD_RES_C + c] = (uint8_t)(lf->field[r][c].visible | (lf->field[r][c].wavefront_blocked << 1));
+}
+
+static void pfref_los_unpack(const uint8_t *in, struct LOS_field *lf)
+{
+    for(int r = 0; r < FIELD_RES_R; r++)
+    for(int c = 0; c < FIELD_RES_C; c++) {
+        lf->field[r][c].visible = in[r * FIELD_RES_C + c] & 1;
+        lf->field[r][c].wavefront_blocked = (in[r * FIELD_RES_C + c] >> 1) & 1;
+    }
+}
+
+/* N_FlowFieldInit (optional) + N_FlowFieldUpdate(TARGET_TILE); field.c:2020-2083.
+ * inout: 4096 bytes, one dir_idx per tile. */
+PFREF_EXPORT void pfref_flow_field_tile(void *m, int layer, int chunk_r, int chunk_c,
+                                        int tile_r, int tile_c, int faction_id, int init, uint8_t *inout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    struct coord chunk = {chunk_r, chunk_c};
+    struct flow_field ff;
+    if(init) N_FlowFieldInit(chunk, &ff);
+    else { ff.chunk = chunk; pfref_flow_unpack(inout, &ff); }
+    struct field_target target = { .type = TARGET_TILE, .tile = (struct coord){tile_r, tile_c} };
+    N_FlowFieldUpdate(chunk, priv, faction_id, layer, target, priv->unit_query_ctx, &ff);
+    pfref_flow_pack(&ff, inout);
+}
+
+/* N_FlowFieldUpdate(TARGET_PORTAL) towards portal `portal_idx` of the chunk. */
+PFREF_EXPORT void pfref_flow_field_portal(void *m, int layer, int chunk_r, int chunk_c,
+                                          int portal_idx, int port_iid, int next_iid,
+                                          int faction_id, int init, uint8_t *inout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    struct coord chunk = {chunk_r, chunk_c};
+    const struct nav_chunk *ch = &priv->chunks[layer][chunk_r * priv->width + chunk_c];
+    const struct portal *port = &ch->portals[portal_idx];
+    struct flow_field ff;
+    if(init) N_FlowFieldInit(chunk, &ff);
+    else { ff.chunk = chunk; pfref_flow_unpack(inout, &ff); }
+    struct field_target target = { .type = TARGET_PORTAL, .pd = (struct portal_desc){
+        port, (uint16_t)port_iid, n_portal(priv, layer, port->connected), (uint16_t)next_iid } };
+    N_FlowFieldUpdate(chunk, priv, faction_id, layer, target, priv->unit_query_ctx, &ff);
+    pfref_flow_pack(&ff, inout);
+}
+
+/* N_LOSFieldCreate; field.c:2085. prev may be NULL (destination chunk). */
+PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
+                                  int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,
+                                  const uint8_t *prev, int prev_chunk_r, int prev_chunk_c,
+                                  uint8_t *out)
+{
+    struct map *map = m;
+    struct nav_private *priv = pfref_priv(m);
+    struct tile_desc target = {tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c};
+    /* n_dest_id bit packing, nav.c:839-854 */
+    dest_id_t id = (((uint32_t)target.chunk_r & 0x3f) << 26) | (((uint32_t)target.chunk_c & 0x3f) << 20)
+                 | (((uint32_t)target.tile_r  & 0x3f) << 14) | (((uint32_t)target.tile_c  & 0x3f) <<  8)
+                 | (((uint32_t)layer & 0x0f) << 4) | (uint32_t)FACTION_ID_NONE;
+    struct LOS_field lf, prev_lf;
+    if(prev) {
+        prev_lf.chunk = (struct coord){prev_chunk_r, prev_chunk_c};
+        pfref_los_unpack(prev, &prev_lf);
+    }
+    N_LOSFieldCreate(id, (struct coord){chunk_r, chunk_c}, target, priv, map->pos,
+        priv->unit_query_ctx, &lf, prev ? &prev_lf : NULL);
+    pfref_los_pack(&lf, out);
+}
+
+PFREF_EXPORT int pfref_request_path(void *m, int layer, float sx, float sz, float dx, float dz,
+                                    uint32_t *out_dest_id)
+{
+    struct map *map = m;
+    dest_id_t id = DEST_ID_INVALID;
+    bool ok = N_RequestPath(map->nav_private, (vec2_t){sx, sz}, (vec2_t){dx, dz}, map->pos, layer, &id);
+    *out_dest_id = id;
+    return ok;
+}
+
+PFREF_EXPORT uint32_t pfref_dest_id(void *m, int layer, float dx, float dz)
+{
+    struct map *map = m;
+    return N_DestIDForPos(map->nav_private, map->pos, (vec2_t){dx, dz}, layer);
+}
+
+/* Field-cache readback: returns 1 if (dest,chunk) has a flow field; writes dirs + ffid */
+PFREF_EXPORT int pfref_fc_get_flow(void *m, uint32_t dest_id, int chunk_r, int chunk_c,
+                                   uint8_t *out, uint64_t *out_ffid)
+{
+    struct nav_private *priv = pfref_priv(m);
+    ff_id_t ffid;
+    if(!N_FC_GetDestFFMapping(priv->fieldcache, dest_id, (struct coord){chunk_r, chunk_c}, &ffid))
+        return 0;
+    const struct flow_field *ff = N_FC_FlowFieldAt(priv->fieldcache, ffid);
+    if(!ff)
+        return 0;
+    pfref_flow_pack(ff, out);
+    if(out_ffid) *out_ffid = ffid;
+    return 1;
+}
+
+PFREF_EXPORT int pfref_fc_get_los(void *m, uint32_t dest_id, int chunk_r, int chunk_c, uint8_t *out)
+{
+    struct nav_private *priv = pfref_priv(m);
+    if(!N_FC_ContainsLOSField(priv->fieldcache, dest_id, (struct coord){chunk_r, chunk_c}))
+        return 0;
+    const struct LOS_field *lf = N_FC_LOSFieldAt(priv->fieldcache, dest_id, (struct coord){chunk_r, chunk_c});
+    pfref_los_pack(lf, out);
+    return 1;
+}
+
+PFREF_EXPORT void pfref_fc_clear(void *m) { N_FC_ClearAll(pfref_priv(m)->fieldcache); }
+
+/* compute_desired_velocity + compute_los_state for n positions of one flock
+ * (movement.c:4129-4180 -> N_DesiredPointSeekVelocity nav.c:3468, N_HasDestLOS nav.c:4026).
+ * vdes is sampled at pos, LOS at los_pos (the reference samples LOS at prev_pos). */
+PFREF_EXPORT void pfref_desired_velocity(void *m, uint32_t dest_id, int n, const float *pos_xz,
+                                         const float *los_pos_xz, float dest_x, float dest_z,
+                                         float *out_vdes, uint8_t *out_los)
+{
+    struct map *map = m;
+    vec2_t dest = {dest_x, dest_z};
+    for(int i = 0; i < n; i++) {
+        vec2_t p = {pos_xz[2*i], pos_xz[2*i+1]};
+        vec2_t lp = {los_pos_xz[2*i], los_pos_xz[2*i+1]};
+        if(out_los)
+            out_los[i] = N_HasDestLOS(dest_id, lp, map->nav_private, map->pos, dest);
+        if(out_vdes) {
+            vec2_t v = N_DesiredPointSeekVelocity(dest_id, p, dest, map->nav_private, map->pos);
+            out_vdes[2*i] = v.x; out_vdes[2*i+1] = v.z;
+        }
+    }
+}
+
+PFREF_EXPORT void pfref_blockers(void *m, int incref, float x, float z, float radius,
+                                 int faction_id, uint32_t flags)
+{
+    struct map *map = m;
+    if(incref) N_BlockersIncref((vec2_t){x, z}, radius, faction_id, flags, map->pos, map->nav_private);
+    else       N_BlockersDecref((vec2_t){x, z}, radius, faction_id, flags, map->pos, map->nav_private);
+}
+
+PFREF_EXPORT void pfref_update(void *m)
+{
+    struct map *map = m;
+    N_Update(map->nav_private);
+    N_ApplyDeferredInvalidations();
+}
+
+/* G_ClearPath_NewVelocity (clearpath.c:694). dyn/stat: 5 floats each {px,pz,vx,vz,radius} */
+PFREF_EXPORT void pfref_clearpath(const float *self5, const float *vpref2,
+                                  const float *dyn, int ndyn, const float *stat, int nstat,
+                                  float *out2)
+{
+    struct cp_ent self = { {self5[0], self5[1]}, {self5[2], self5[3]}, self5[4] };
+    vec_cp_ent_t vd, vs;
+    vec_cp_ent_init(&vd); vec_cp_ent_init(&vs);
+    vec_cp_ent_resize(&vd, MAX_NEIGHBOURS > ndyn ? MAX_NEIGHBOURS : ndyn);
+    vec_cp_ent_resize(&vs, MAX_NEIGHBOURS > nstat ? MAX_NEIGHBOURS : nstat);
+    for(int i = 0; i < ndyn; i++)
+        vec_cp_ent_push(&vd, (struct cp_ent){ {dyn[5*i], dyn[5*i+1]}, {dyn[5*i+2], dyn[5*i+3]}, dyn[5*i+4] });
+    for(int i = 0; i < nstat; i++)
+        vec_cp_ent_push(&vs, (struct cp_ent){ {stat[5*i], stat[5*i+1]}, {stat[5*i+2], stat[5*i+3]}, stat[5*i+4] });
+    vec2_t v = G_ClearPath_NewVelocity(self, 0, (vec2_t){vpref2[0], vpref2[1]}, vd, vs, false);
+    out2[0] = v.x; out2[1] = v.z;
+    vec_cp_ent_destroy(&vd); vec_cp_ent_destroy(&vs);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Agent population: fills the movement module's own statics the way move_copy_gamestate
+ * (movement.c:3607) + move_do_tick (movement.c:4333-4408) would.
+ * ---------------------------------------------------------------------------------------- */
+
+static int        s_nagents = 0;
+static bg_ent_t   s_pfref_tree;
+static bool       s_tree_valid = false;
+
+static void pfref_agents_clear(void)
+{
+    struct move_gamestate *gs = &s_move_work.gamestate;
+    if(gs->flags)        { kh_destroy(id, gs->flags); gs->flags = NULL; }
+    if(gs->positions)    { kh_destroy(pos, gs->positions); gs->positions = NULL; }
+    if(gs->sel_radiuses) { kh_destroy(range, gs->sel_radiuses); gs->sel_radiuses = NULL; }
+    if(gs->faction_ids)  { kh_destroy(id, gs->faction_ids); gs->faction_ids = NULL; }
+    if(s_tree_valid)     { bg_ent_destroy(&s_pfref_tree); s_tree_valid = false; }
+    if(s_entity_state_table) { kh_destroy(state, s_entity_state_table); s_entity_state_table = NULL; }
+    for(int i = 0; i < vec_size(&s_flocks); i++)
+        kh_destroy(entity, vec_AT(&s_flocks, i).ents);
+    vec_flock_reset(&s_flocks);
+    for(size_t i = 0; i < s_move_work.nwork; i++) {
+        vec_cp_ent_destroy(s_move_work.in[i].dyn_neighbs);  free(s_move_work.in[i].dyn_neighbs);
+        vec_cp_ent_destroy(s_move_work.in[i].stat_neighbs); free(s_move_work.in[i].stat_neighbs);
+    }
+    free(s_move_work.in);  s_move_work.in = NULL;
+    free(s_move_work.out); s_move_work.out = NULL;
+    s_move_work.nwork = 0;
+    s_nagents = 0;
+}
+
+static bool pfref_uids_equal(const uint32_t *a, const uint32_t *b) { return *a == *b; }
+
+/* uid == agent index. Position index: insert in uid order then cleanup (== G_Pos_Set per
+ * entity followed by G_Pos_CopyBitmapGrid, position.c:359), so in-cell order is descending uid.
+ * flock_of[i] = flock index (>= 0) ; flock_target: 2 floats per flock ; flock_dest: dest_id */
+PFREF_EXPORT void pfref_agents_set(void *m, int n, const float *pos_xz, const float *prev_pos_xz,
+                                   const float *vel_xz, const float *radius, const float *max_speed,
+                                   const int32_t *state, const uint32_t *flags, const int32_t *flock_of,
+                                   int nflocks, const float *flock_target, const uint32_t *flock_dest,
+                                   int hz)
+{
+    struct map *map = m;
+    pfref_agents_clear();
+    struct move_gamestate *gs = &s_move_work.gamestate;
+    gs->flags = kh_init(id);
+    gs->positions = kh_init(pos);
+    gs->sel_radiuses = kh_init(range);
+    gs->faction_ids = kh_init(id);
+    gs->map = map;
+    s_map = map;
+    s_entity_state_table = kh_init(state);
+    kh_resize(id, gs->flags, n); kh_resize(pos, gs->positions, n);
+    kh_resize(range, gs->sel_radiuses, n); kh_resize(id, gs->faction_ids, n);
+    kh_resize(state, s_entity_state_table, n);
+    s_move_work.hz = (hz == 20) ? MOVE_HZ_20 : (hz == 10) ? MOVE_HZ_10 : (hz == 5) ? MOVE_HZ_5 : MOVE_HZ_1;
+
+    vec3_t center = M_GetCenterPos(map);
+    float hw = (map->width  * TILES_PER_CHUNK_WIDTH  * X_COORDS_PER_TILE) / 2.0f;
+    float hh = (map->height * TILES_PER_CHUNK_HEIGHT * Z_COORDS_PER_TILE) / 2.0f;
+    bg_ent_init(&s_pfref_tree, center.x - hw, center.x + hw, center.z - hh, center.z + hh, pfref_uids_equal);
+    bg_ent_reserve(&s_pfref_tree, n);
+    s_tree_valid = true;
+
+    vec_flock_init(&s_flocks);
+    for(int f = 0; f < nflocks; f++) {
+        struct flock fl;
+        memset(&fl, 0, sizeof(fl));
+        fl.ents = kh_init(entity);
+        fl.target_xz = (vec2_t){flock_target[2*f], flock_target[2*f+1]};
+        fl.dest_id = flock_dest[f];
+        vec_flock_push(&s_flocks, fl);
+    }
+
+    int ret;
+    for(int i = 0; i < n; i++) {
+        uint32_t uid = i;
+        khiter_t k;
+        k = kh_put(id, gs->flags, uid, &ret);          kh_value(gs->flags, k) = flags[i];
+        k = kh_put(id, gs->faction_ids, uid, &ret);    kh_value(gs->faction_ids, k) = 0;
+        k = kh_put(range, gs->sel_radiuses, uid, &ret); kh_value(gs->sel_radiuses, k) = radius[i];
+        k = kh_put(pos, gs->positions, uid, &ret);
+        kh_value(gs->positions, k) = (vec3_t){pos_xz[2*i], 0.0f, pos_xz[2*i+1]};
+        bg_ent_insert(&s_pfref_tree, pos_xz[2*i], pos_xz[2*i+1], uid);
+
+        struct movestate ms;
+        memset(&ms, 0, sizeof(ms));
+        ms.state = state[i];
+        ms.max_speed = max_speed[i];
+        ms.velocity = (vec2_t){vel_xz[2*i], vel_xz[2*i+1]};
+        ms.prev_pos = (vec3_t){prev_pos_xz[2*i], 0.0f, prev_pos_xz[2*i+1]};
+        k = kh_put(state, s_entity_state_table, uid, &ret);
+        kh_value(s_entity_state_table, k) = ms;
+
+        if(flock_of[i] >= 0)
+            kh_put(entity, vec_AT(&s_flocks, flock_of[i]).ents, uid, &ret);
+    }
+    bg_ent_cleanup(&s_pfref_tree);
+    gs->postree = &s_pfref_tree;
+    s_nagents = n;
+}
+
+/* Query order probe: G_Pos_EntsInCircleFrom (position.c:379) */
+PFREF_EXPORT int pfref_ents_in_circle(float x, float z, float range, uint32_t *out, int maxout)
+{
+    return G_Pos_EntsInCircleFrom(s_move_work.gamestate.postree, s_move_work.gamestate.flags,
+        (vec2_t){x, z}, range, out, maxout);
+}
+
+/* Build the work list for the given uids the way move_do_tick does (movement.c:4333-4408);
+ * vdes/has_los per work item come from pfref_desired_velocity or are supplied directly. */
+PFREF_EXPORT void pfref_work_set(int nwork, const uint32_t *uids, const float *vdes,
+                                 const uint8_t *has_los, const float *speed)
+{
+    for(size_t i = 0; i < s_move_work.nwork; i++) {
+        vec_cp_ent_destroy(s_move_work.in[i].dyn_neighbs);  free(s_move_work.in[i].dyn_neighbs);
+        vec_cp_ent_destroy(s_move_work.in[i].stat_neighbs); free(s_move_work.in[i].stat_neighbs);
+    }
+    free(s_move_work.in); free(s_move_work.out);
+    s_move_work.in = calloc(nwork, sizeof(struct move_work_in));
+    s_move_work.out = calloc(nwork, sizeof(struct move_work_out));
+    s_move_work.nwork = nwork;
+    for(int i = 0; i < nwork; i++) {
+        uint32_t uid = uids[i];
+        const struct movestate *ms = movestate_get(uid);
+        struct move_work_in *in = &s_move_work.in[i];
+        in->ent_uid = uid;
+        in->ent_des_v = (vec2_t){vdes[2*i], vdes[2*i+1]};
+        in->speed = speed[i];
+        in->has_dest_los = has_los[i];
+        in->cp_ent = (struct cp_ent){
+            .xz_pos = (vec2_t){ms->prev_pos.x, ms->prev_pos.z},
+            .xz_vel = ms->velocity,
+            .radius = G_GetSelectionRadiusFrom(s_move_work.gamestate.sel_radiuses, uid)
+        };
+        in->dyn_neighbs = malloc(sizeof(vec_cp_ent_t));
+        in->stat_neighbs = malloc(sizeof(vec_cp_ent_t));
+        vec_cp_ent_init(in->dyn_neighbs);  vec_cp_ent_resize(in->dyn_neighbs, MAX_NEIGHBOURS);
+        vec_cp_ent_init(in->stat_neighbs); vec_cp_ent_resize(in->stat_neighbs, MAX_NEIGHBOURS);
+    }
+}
+
+/* move_velocity_work over [begin, end] (inclusive), re-entrant over disjoint ranges. */
+PFREF_EXPORT void pfref_velocity_work(int begin, int end)
+{
+    for(int i = begin; i <= end; i++) {
+        vec_cp_ent_reset(s_move_work.in[i].dyn_neighbs);
+        vec_cp_ent_reset(s_move_work.in[i].stat_neighbs);
+    }
+    move_velocity_work(begin, end);
+}
+
+struct pfref_range { int begin, end; };
+static void *pfref_vel_thread(void *arg)
+{
+    struct pfref_range *r = arg;
+    pfref_velocity_work(r->begin, r->end);
+    return NULL;
+}
+
+/* The reference's static equal-range fork-join (movement.c:3746-3774) on pthreads.
+ * Returns elapsed seconds. */
+PFREF_EXPORT double pfref_velocity_work_mt(int nthreads)
+{
+    int nwork = (int)s_move_work.nwork;
+    if(nwork == 0) return 0.0;
+    if(nthreads > MAX_MOVE_TASKS) nthreads = MAX_MOVE_TASKS;
+    if(nwork < 64 || nthreads < 1) nthreads = 1;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_t th[MAX_MOVE_TASKS];
+    struct pfref_range rg[MAX_MOVE_TASKS];
+    size_t nitems = ceil((float)nwork / nthreads);
+    int nt = 0;
+    for(int i = 0; i < nthreads; i++) {
+        int b = nitems * i, e = MIN(nitems * (i + 1) - 1, (size_t)nwork - 1);
+        if(b > e) break;
+        rg[nt] = (struct pfref_range){b, e};
+        pthread_create(&th[nt], NULL, pfref_vel_thread, &rg[nt]);
+        nt++;
+    }
+    for(int i = 0; i < nt; i++) pthread_join(th[i], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
+}
+
+PFREF_EXPORT void pfref_work_get(int nwork, float *out_vel)
+{
+    for(int i = 0; i < nwork; i++) {
+        out_vel[2*i] = s_move_work.out[i].ent_vel.x;
+        out_vel[2*i+1] = s_move_work.out[i].ent_vel.z;
+    }
+}
+
+/* vpref only (point_seek_vpref, movement.c:1870) for diagnostics */
+PFREF_EXPORT void pfref_vpref(int nwork, float *out_vpref)
+{
+    for(int i = 0; i < nwork; i++) {
+        struct move_work_in *in = &s_move_work.in[i];
+        const struct flock *flock = flock_for_ent(in->ent_uid);
+        vec2_t v = point_seek_vpref(in->ent_uid, flock, in->ent_des_v, in->has_dest_los, in->speed);
+        out_vpref[2*i] = v.x; out_vpref[2*i+1] = v.z;
+    }
+}
+
+/* Timed field batches for the CPU baseline: reqs = 4 ints {chunk_r, chunk_c, tile_r, tile_c}.
+ * what: 0 = N_FlowFieldInit+Update(TARGET_TILE), 1 = N_LOSFieldCreate (destination chunk). */
+struct pfref_field_job { void *m; int layer; int what; const int32_t *reqs; int begin, end; uint8_t *out; };
+static void *pfref_field_thread(void *arg)
+{
+    struct pfref_field_job *j = arg;
+    for(int i = j->begin; i < j->end; i++) {
+        const int32_t *q = j->reqs + 4*i;
+        uint8_t *o = j->out ? j->out + (size_t)i * 4096 : NULL;
+        uint8_t tmp[4096];
+        if(j->what == 0)
+            pfref_flow_field_tile(j->m, j->layer, q[0], q[1], q[2], q[3], FACTION_ID_NONE, 1, o ? o : tmp);
+        else
+            pfref_los_field(j->m, j->layer, q[0], q[1], q[0], q[1], q[2], q[3], NULL, 0, 0, o ? o : tmp);
+    }
+    return NULL;
+}
+
+PFREF_EXPORT double pfref_fields_mt(void *m, int layer, int what, const int32_t *reqs, int n,
+                                    int nthreads, uint8_t *out)
+{
+    if(nthreads < 1) nthreads = 1;
+    if(nthreads > 256) nthreads = 256;
+    struct nav_private *priv = pfref_priv(m);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_t th[256];
+    struct pfref_field_job jobs[256];
+    int per = (n + nthreads - 1) / nthreads, nt = 0;
+    for(int i = 0; i < nthreads; i++) {
+        int b = per * i, e = MIN(per * (i + 1), n);
+        if(b >= e) break;
+        jobs[nt] = (struct pfref_field_job){m, layer, what, reqs, b, e, out};
+        pthread_attr_t attr;
+        pthread_attr_init(&attr);
+        pthread_attr_setstacksize(&attr, 8u << 20);   /* TASK_BIG_STACK, sched.c:186 */
+        pthread_create(&th[nt], &attr, pfref_field_thread, &jobs[nt]);
+        pthread_attr_destroy(&attr);
+        nt++;
+    }
+    for(int i = 0; i < nt; i++) pthread_join(th[i], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
+}
