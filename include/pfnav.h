@@ -1,0 +1,245 @@
+/*
+ * pfnav.h -- C ABI of libpfnav.so: the B200 (sm_100a) implementation of permafrost-engine's
+ * per-tick navigation + crowd-movement hot path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in any signature (streams are passed
+ * as an opaque `void*` that is a cudaStream_t / CUstream, NULL = the legacy default stream).
+ * All functions return 0 on success and a negative pfnav_status on failure;
+ * pfnav_last_error() returns a thread-local human-readable message.  There is NO CPU fallback:
+ * if no sm_100-class device is usable, pfnav_create() fails.
+ *
+ * Each entry point cites the reference interface (file:line under the reference checkout) that
+ * it replaces; INTEGRATION.md shows the binding a maintainer adds on the engine side.
+ *
+ * Conventions (identical to the reference):
+ *   - a map is chunk_w x chunk_h chunks; a chunk is 64x64 nav tiles (FIELD_RES_R/C,
+ *     src/navigation/nav_data.h:45-46); a nav tile is 4x4 world units; chunk = 256x256 wu.
+ *   - world X DEcreases with the column index, Z increases with the row index
+ *     (src/map/tile.c:547-592); map_pos is the (x,z) of the top-left corner.
+ *   - chunk-blocked grids are [chunk_r][chunk_c][64][64], the order of N_CopyCostBasePacked
+ *     (src/navigation/nav.c:2432).
+ *   - a flow field is 4096 bytes, one `dir_idx` (enum flow_dir 0..8, nav.h:94-104) per tile,
+ *     byte-identical to `struct flow_field::field` (src/navigation/field.h:103-109).
+ *   - a LOS field is 4096 bytes, bit0 = visible, bit1 = wavefront_blocked, byte-identical to
+ *     `struct LOS_field::field` (field.h:48-54).
+ */
+#ifndef PFNAV_H
+#define PFNAV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFNAV_FIELD_RES        64
+#define PFNAV_FIELD_TILES      4096
+#define PFNAV_COST_IMPASSABLE  0xff     /* nav_data.h:47 */
+#define PFNAV_ISLAND_NONE      0xffff   /* nav_data.h:48 */
+#define PFNAV_FACTION_ID_NONE  0xf      /* nav_data.h:49 */
+#define PFNAV_NAV_LAYER_MAX    12       /* nav.h:78-92 */
+#define PFNAV_MAX_NEIGHBOURS   32       /* movement.c:437 */
+
+typedef enum pfnav_status {
+    PFNAV_OK            =  0,
+    PFNAV_ERR_ARG       = -1,
+    PFNAV_ERR_CUDA      = -2,
+    PFNAV_ERR_NO_DEVICE = -3,
+    PFNAV_ERR_STATE     = -4,
+    PFNAV_ERR_NOMEM     = -5
+} pfnav_status;
+
+/* enum flow_dir, src/navigation/public/nav.h:94-104 */
+enum pfnav_flow_dir { PFNAV_FD_NONE = 0, PFNAV_FD_NW, PFNAV_FD_N, PFNAV_FD_NE, PFNAV_FD_W,
+                      PFNAV_FD_E, PFNAV_FD_SW, PFNAV_FD_S, PFNAV_FD_SE };
+
+/* field_target.type, src/navigation/field.h:78-91 (only the chunk-local kinds) */
+enum pfnav_target_type { PFNAV_TARGET_PORTAL = 0, PFNAV_TARGET_TILE = 1 };
+
+typedef struct pfnav_ctx pfnav_ctx;
+
+/* ---------------------------------------------------------------------------------------- */
+/* Context + map state (replaces struct nav_private / nav_chunk, nav_private.h:52, nav_data.h:118)
+ * ---------------------------------------------------------------------------------------- */
+
+const char *pfnav_last_error(void);
+int  pfnav_version(void);
+
+/* device: CUDA ordinal. Fails (PFNAV_ERR_NO_DEVICE) without a usable GPU. */
+int  pfnav_create(int device, pfnav_ctx **out);
+void pfnav_destroy(pfnav_ctx *ctx);
+
+/* N_NewCtxForMapData (nav.c:2284): allocate device grids for chunk_w x chunk_h chunks and
+ * `nlayers` navigation layers (cost_base u8, blockers u16, local_islands u16 per layer). */
+int  pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nlayers,
+                      float map_x, float map_z);
+
+/* Upload one layer from HOST chunk-blocked arrays ([chunk_r][chunk_c][64][64]).
+ * blockers / local_islands may be NULL (treated as all 0 / left unchanged).
+ * Same packed layout as N_CopyCostBasePacked / N_CopyBlockersPacked (nav.c:2432, 2462). */
+int  pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *cost_base,
+                            const uint16_t *blockers, const uint16_t *local_islands);
+
+/* Sparse update of one chunk (what N_BlockersIncref/Decref + N_Update change, nav.c:4663-4705,
+ * 2119): any pointer may be NULL to keep that grid. HOST pointers, [64][64] each. */
+int  pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c,
+                            const uint8_t *cost_base, const uint16_t *blockers,
+                            const uint16_t *local_islands);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Flow fields + LOS fields (seam B2: src/navigation/field.h:115-202)
+ * ---------------------------------------------------------------------------------------- */
+
+/* One N_FlowFieldUpdate call (field.c:2030). 64 bytes. Mirrors struct field_work_in
+ * (nav.c:126-131) with the portal_desc pointers resolved to plain coordinates. */
+typedef struct pfnav_field_req {
+    int32_t  chunk_r, chunk_c;      /* struct coord chunk_coord */
+    int32_t  layer;                 /* enum nav_layer */
+    int32_t  faction_id;            /* PFNAV_FACTION_ID_NONE for non-attacking paths */
+    int32_t  target_type;           /* enum pfnav_target_type */
+    int32_t  init;                  /* !=0: N_FlowFieldInit first (field.c:2020); 0: update the
+                                     * existing `inout` field in place (nav.c:1998-2008) */
+    /* TARGET_TILE: struct coord tile */
+    int32_t  tile_r, tile_c;
+    /* TARGET_PORTAL: struct portal_desc (field.h:68-73) */
+    int16_t  port_r0, port_c0, port_r1, port_c1;   /* pd.port->endpoints[0..1] */
+    int16_t  next_r0, next_c0, next_r1, next_c1;   /* pd.next->endpoints[0..1] */
+    int32_t  next_chunk_r, next_chunk_c;           /* pd.next->chunk (== port->connected chunk) */
+    uint16_t port_iid, next_iid;                   /* pd.port_iid, pd.next_iid */
+    int32_t  _pad;
+} pfnav_field_req;
+
+/* Batch of N_FlowFieldUpdate (+ optional N_FlowFieldInit). reqs and inout_fields are HOST
+ * buffers (inout_fields: n x 4096 bytes). Synchronous: results are in inout_fields on return. */
+int  pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *reqs, size_t n,
+                              uint8_t *inout_fields);
+
+/* Same, DEVICE-resident reqs / fields, asynchronous on `stream`. */
+int  pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n,
+                                  uint8_t *d_inout_fields, void *stream);
+
+/* One N_LOSFieldCreate call (field.c:2085). 48 bytes. */
+typedef struct pfnav_los_req {
+    int32_t  chunk_r, chunk_c;          /* chunk the field is for */
+    int32_t  layer;
+    int32_t  faction_id;
+    int32_t  tgt_chunk_r, tgt_chunk_c;  /* struct tile_desc target */
+    int32_t  tgt_tile_r, tgt_tile_c;
+    int32_t  prev_index;                /* -1: destination chunk (prev_los == NULL); else index,
+                                         * within the same batch, of the request whose output is
+                                         * prev_los. Must be < this request's own index.        */
+    int32_t  prev_chunk_r, prev_chunk_c;/* prev_los->chunk */
+    int32_t  _pad;
+} pfnav_los_req;
+
+/* Batch of N_LOSFieldCreate. Requests are processed in dependency order (a request may name an
+ * earlier one as its prev_los). HOST buffers; out_fields: n x 4096 bytes. */
+int  pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs, size_t n,
+                             uint8_t *out_fields);
+int  pfnav_los_fields_create_dev(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n,
+                                 uint8_t *d_out_fields, int n_waves, const int32_t *h_wave_offsets,
+                                 void *stream);
+
+/* Selects how the 64x64 tiles are staged into shared memory: 1 = TMA tensor maps
+ * (cp.async.bulk.tensor), 0 = plain coalesced loads. Default 1. */
+int  pfnav_set_tma(pfnav_ctx *ctx, int enable);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Field pool: device-resident (dest_id, chunk) -> {flow field, LOS field}
+ * (replaces the fieldcache lookups done per agent: fieldcache.c N_FC_GetDestFFMapping /
+ *  N_FC_FlowFieldAt / N_FC_LOSFieldAt, called from nav.c:3483-3506, 4044-4052)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Size the pool for `ndests` destinations (flocks). Slot table is ndests x chunks. */
+int  pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields);
+/* Store field bytes (HOST, 4096 each; either may be NULL) for (dest, chunk). */
+int  pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c,
+                    const uint8_t *flow_field, const uint8_t *los_field);
+int  pfnav_pool_clear(pfnav_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls
+ * R_GL_MoveUploadData / R_GL_MoveDispatchWork / R_GL_MoveReadNewVelocities,
+ * src/render/public/render.h:619-691, computing what move_velocity_work computes on the CPU,
+ * src/game/movement.c:3395-3466)
+ * ---------------------------------------------------------------------------------------- */
+
+/* enum move_state, movement.c:117-142 */
+enum pfnav_move_state { PFNAV_STATE_MOVING = 0, PFNAV_STATE_MOVING_IN_FORMATION, PFNAV_STATE_ARRIVED,
+                        PFNAV_STATE_SEEK_ENEMIES, PFNAV_STATE_WAITING, PFNAV_STATE_SURROUND_ENTITY,
+                        PFNAV_STATE_ENTER_ENTITY_RANGE, PFNAV_STATE_TURNING, PFNAV_STATE_ARRIVING_TO_CELL };
+
+/* Entity flags the path reads: the engine's own bit values (src/entity.h:59-82), so the
+ * entity flag word can be passed through verbatim. Only the low 24 bits are kept. */
+#define PFNAV_FLAG_MOVABLE      (1u << 3)
+#define PFNAV_FLAG_WATER        (1u << 14)
+#define PFNAV_FLAG_AIR          (1u << 15)
+#define PFNAV_FLAG_GARRISONED   (1u << 18)
+#define PFNAV_FLAG_COMBAT_HELD  (1u << 21)
+
+/* One entity as the movement tick sees it: struct gpu_ent_desc (movement.c:350-369) plus the
+ * two things the CPU path uses and the GLSL record lacks (prev_pos). 64 bytes. */
+typedef struct pfnav_agent {
+    float    pos[2];        /* xz, gamestate snapshot position            */
+    float    prev_pos[2];   /* ms->prev_pos: ClearPath self position + LOS sample (movement.c:4351,4137) */
+    float    velocity[2];   /* ms->velocity, world units per tick          */
+    float    vdes[2];       /* in: ignored when the tick computes vdes from the field pool */
+    float    radius;        /* selection radius                            */
+    float    max_speed;     /* ms->max_speed (wu/s)                        */
+    float    speed;         /* entity_speed() (wu/s)                       */
+    uint32_t state;         /* enum pfnav_move_state                       */
+    uint32_t flags;         /* PFNAV_FLAG_*                                */
+    int32_t  flock;         /* index into flocks, -1 = none                */
+    uint32_t has_dest_los;  /* in: ignored when computed from the pool     */
+    uint32_t _pad;
+} pfnav_agent;
+
+typedef struct pfnav_flock {
+    float    target[2];     /* flock->target_xz (movement.c:193)           */
+    int32_t  dest;          /* field-pool destination index, -1 = none     */
+    int32_t  layer;         /* N_DestLayer(dest_id)                        */
+} pfnav_flock;
+
+/* move_copy_gamestate (movement.c:3607): upload the entity snapshot. HOST pointers.
+ * uid == index. Rebuilds the device spatial index (position.c:359 G_Pos_CopyBitmapGrid). */
+int  pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n,
+                         const pfnav_flock *flocks, size_t nflocks, int hz);
+
+/* Work list (move_push_work, movement.c:3741): the uids that take a velocity update this tick.
+ * NULL = every agent whose state is not ARRIVED/WAITING (ent_still, movement.c:652). */
+int  pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_t nwork);
+
+/* flags for pfnav_agents_tick */
+#define PFNAV_TICK_VDES_FROM_POOL   (1u << 0)  /* compute vdes + has_dest_los on device (nav.c:3468, 4026) */
+
+/* navigation_tick_task's velocity phase (movement.c:4263-4287): desired velocity gather,
+ * boids steering, neighbour search, ClearPath. Asynchronous on `stream`. */
+int  pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream);
+
+/* R_GL_MoveReadNewVelocities (render.h:672): copy the nwork new velocities (xz, 8 bytes each,
+ * in work-list order) to HOST memory; blocks until the tick has finished. */
+int  pfnav_agents_read_velocities(pfnav_ctx *ctx, float *out_xz, size_t maxout);
+/* Diagnostics: preferred velocity (vpref), vdes and has_dest_los of each work item. */
+int  pfnav_agents_read_debug(pfnav_ctx *ctx, float *out_vpref_xz, float *out_vdes_xz,
+                             uint8_t *out_has_los, size_t maxout);
+
+/* G_Pos_EntsInCircleFrom (position.c:379): neighbour query through the device spatial index,
+ * returning uids in the reference's order. For parity tests of the index itself. */
+int  pfnav_ents_in_circle(pfnav_ctx *ctx, float x, float z, float range, uint32_t *out,
+                          int maxout, int *out_n);
+
+/* Device-side hooks for zero-copy callers (bench `value` leg, multi-GPU all-gather):
+ * raw device pointers to the resident 24-byte neighbour records (pos.xz, vel.xz, radius,
+ * state << 24 | flags) in uid order, and to the velocity output (work-list order). */
+int  pfnav_agents_device_ptrs(pfnav_ctx *ctx, void **d_records, void **d_velocities, size_t *n);
+/* Re-build the spatial index from the (externally updated, e.g. all-gathered) record array. */
+int  pfnav_agents_rebuild_index(pfnav_ctx *ctx, void *stream);
+
+/* Number of kernels launched by this context since creation (bench `gpu_launches`). */
+uint64_t pfnav_launch_count(const pfnav_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFNAV_H */

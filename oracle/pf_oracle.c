@@ -1,0 +1,781 @@
+/*
+ * oracle/pf_oracle.c -- TEST INFRASTRUCTURE ONLY (see pf_oracle.h).
+ *
+ * Plain-C restatement of the reference's hot path. Every function cites the reference
+ * file:line it follows (paths relative to the reference checkout's src/). Serial, scalar,
+ * written for clarity: it is a checker, not a product path. Compile with -ffp-contract=off so
+ * float expressions round exactly as the reference's x86-64 SSE build does.
+ */
+#include "pf_oracle.h"
+#include <math.h>
+#include <stdbool.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RES 64
+#define COST_IMPASSABLE 0xff
+#define ISLAND_NONE 0xffff
+#define TARGET_PORTAL 0
+#define TARGET_TILE 1
+enum { FD_NONE = 0, FD_NW, FD_N, FD_NE, FD_W, FD_E, FD_SW, FD_S, FD_SE };
+
+/* ------------------------------------------------------------------------------------------
+ * lib/public/pqueue.h:109-208 -- 1-indexed binary min-heap, float priority, hole-based sift
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float prio; int r, c; } pq_node;
+typedef struct { pq_node *nodes; int size, cap; } pq;
+
+static void pq_init(pq *q) { q->nodes = NULL; q->size = 0; q->cap = 0; }
+static void pq_free(pq *q) { free(q->nodes); q->nodes = NULL; }
+
+static void pq_push(pq *q, float prio, int r, int c)
+{
+    if(q->size + 1 >= q->cap) {
+        q->cap = q->cap ? q->cap * 2 : 32;
+        q->nodes = realloc(q->nodes, q->cap * sizeof(pq_node));
+    }
+    int curr = q->size + 1, parent = curr / 2;
+    while(curr > 1 && q->nodes[parent].prio > prio) {
+        q->nodes[curr] = q->nodes[parent];
+        curr = parent;
+        parent = parent / 2;
+    }
+    q->nodes[curr].prio = prio; q->nodes[curr].r = r; q->nodes[curr].c = c;
+    q->size++;
+}
+
+static void pq_pop(pq *q, int *r, int *c)
+{
+    *r = q->nodes[1].r; *c = q->nodes[1].c;
+    q->nodes[1] = q->nodes[q->size--];
+    int root = 1;
+    while(root != q->size + 1) {        /* _pq_balance */
+        int target = q->size + 1;
+        int l = root * 2, rr = l + 1;
+        if(l <= q->size && q->nodes[l].prio < q->nodes[target].prio) target = l;
+        if(rr <= q->size && q->nodes[rr].prio < q->nodes[target].prio) target = rr;
+        q->nodes[root] = q->nodes[target];
+        root = target;
+    }
+}
+
+static bool pq_contains(const pq *q, int r, int c)
+{
+    for(int i = 1; i <= q->size; i++)
+        if(q->nodes[i].r == r && q->nodes[i].c == c) return true;
+    return false;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * chunk accessors
+ * ---------------------------------------------------------------------------------------- */
+static const uint8_t *chunk_cost(const pfo_map *m, int cr, int cc) { return m->cost + ((size_t)cr * m->chunk_w + cc) * 4096; }
+static uint16_t chunk_blk(const pfo_map *m, int cr, int cc, int r, int c)
+{ return m->blockers ? m->blockers[((size_t)cr * m->chunk_w + cc) * 4096 + r * RES + c] : 0; }
+static uint16_t chunk_liid(const pfo_map *m, int cr, int cc, int r, int c)
+{ return m->local_islands[((size_t)cr * m->chunk_w + cc) * 4096 + r * RES + c]; }
+
+/* field_tile_passable (navigation/field.c:117) */
+static bool tile_passable(const pfo_map *m, int cr, int cc, int r, int c)
+{
+    if(chunk_cost(m, cr, cc)[r * RES + c] == COST_IMPASSABLE) return false;
+    if(chunk_blk(m, cr, cc, r, c) > 0) return false;
+    return true;
+}
+
+/* field_flow_dir (navigation/field.c:355): note the selection at :405-428 re-tests only equality
+ * with min_cost, not the "both side tiles finite" admissibility used to compute min_cost. */
+static int flow_dir(const float intf[RES][RES], int r, int c)
+{
+    float min_cost = INFINITY;
+#define MINF(a, b) ((a) < (b) ? (a) : (b))
+    if(r > 0) min_cost = MINF(min_cost, intf[r-1][c]);
+    if(r < RES-1) min_cost = MINF(min_cost, intf[r+1][c]);
+    if(c > 0) min_cost = MINF(min_cost, intf[r][c-1]);
+    if(c < RES-1) min_cost = MINF(min_cost, intf[r][c+1]);
+    if(r > 0 && c > 0 && intf[r-1][c] < INFINITY && intf[r][c-1] < INFINITY) min_cost = MINF(min_cost, intf[r-1][c-1]);
+    if(r > 0 && c < RES-1 && intf[r-1][c] < INFINITY && intf[r][c+1] < INFINITY) min_cost = MINF(min_cost, intf[r-1][c+1]);
+    if(r < RES-1 && c > 0 && intf[r+1][c] < INFINITY && intf[r][c-1] < INFINITY) min_cost = MINF(min_cost, intf[r+1][c-1]);
+    if(r < RES-1 && c < RES-1 && intf[r+1][c] < INFINITY && intf[r][c+1] < INFINITY) min_cost = MINF(min_cost, intf[r+1][c+1]);
+    if(r > 0 && intf[r-1][c] == min_cost) return FD_N;
+    else if(r < RES-1 && intf[r+1][c] == min_cost) return FD_S;
+    else if(c < RES-1 && intf[r][c+1] == min_cost) return FD_E;
+    else if(c > 0 && intf[r][c-1] == min_cost) return FD_W;
+    else if(r > 0 && c > 0 && intf[r-1][c-1] == min_cost) return FD_NW;
+    else if(r > 0 && c < RES-1 && intf[r-1][c+1] == min_cost) return FD_NE;
+    else if(r < RES-1 && c > 0 && intf[r+1][c-1] == min_cost) return FD_SW;
+    else if(r < RES-1 && c < RES-1 && intf[r+1][c+1] == min_cost) return FD_SE;
+    return 0;
+}
+
+/* N_FlowFieldInit + N_FlowFieldUpdate (navigation/field.c:2020-2083) for one request */
+static void flow_field_update(const pfo_map *m, const pfo_field_req *q, uint8_t *inout)
+{
+    if(q->init) memset(inout, FD_NONE, 4096);
+    float intf[RES][RES];
+    float (*f)[RES] = intf;
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) f[r][c] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    const int cr = q->chunk_r, cc = q->chunk_c;
+
+    if(q->target_type == TARGET_TILE) {
+        /* field_tile_initial_frontier (field.c:1096) */
+        if(tile_passable(m, cr, cc, q->tile_r, q->tile_c)) {
+            pq_push(&frontier, 0.0f, q->tile_r, q->tile_c);
+            f[q->tile_r][q->tile_c] = 0.0f;
+        }
+    }else{
+        /* field_portal_initial_frontier (field.c:1160) + field_tile_adjacent_to_next_iid (:1131) */
+        for(int r = q->port_r0; r <= q->port_r1; r++) {
+        for(int c = q->port_c0; c <= q->port_c1; c++) {
+            if(!tile_passable(m, cr, cc, r, c)) continue;
+            if(q->port_iid != ISLAND_NONE && chunk_liid(m, cr, cc, r, c) != q->port_iid) continue;
+            bool adj = false;
+            for(int r2 = q->next_r0; r2 <= q->next_r1 && !adj; r2++) {
+            for(int c2 = q->next_c0; c2 <= q->next_c1; c2++) {
+                int dr = (q->next_chunk_r * RES + r2) - (cr * RES + r);
+                int dc = (q->next_chunk_c * RES + c2) - (cc * RES + c);
+                if(abs(dr) + abs(dc) == 1 && chunk_liid(m, q->next_chunk_r, q->next_chunk_c, r2, c2) == q->next_iid) {
+                    adj = true; break;
+                }
+            }}
+            if(!adj) continue;
+            pq_push(&frontier, 0.0f, r, c);
+            f[r][c] = 0.0f;
+        }}
+    }
+    /* field_build_integration (field.c:539) with field_neighbours_grid (:203): 4-connected,
+     * edge weight = cost_base of the tile entered, accumulated in float */
+    const uint8_t *cost = chunk_cost(m, cr, cc);
+    while(frontier.size > 0) {
+        int r, c; pq_pop(&frontier, &r, &c);
+        for(int dr = -1; dr <= 1; dr++) {
+        for(int dc = -1; dc <= 1; dc++) {
+            int ar = r + dr, ac = c + dc;
+            if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+            if(dr == 0 && dc == 0) continue;
+            if(dr == dc || dr == -dc) continue;
+            if(!tile_passable(m, cr, cc, ar, ac)) continue;
+            float total = f[r][c] + cost[ar * RES + ac];
+            if(total < f[ar][ac]) { f[ar][ac] = total; pq_push(&frontier, total, ar, ac); }
+        }}
+    }
+    pq_free(&frontier);
+    /* field_build_flow (field.c:734) */
+    for(int r = 0; r < RES; r++) {
+    for(int c = 0; c < RES; c++) {
+        if(f[r][c] == INFINITY) continue;
+        if(f[r][c] == 0.0f) { inout[r * RES + c] = FD_NONE; continue; }
+        inout[r * RES + c] = (uint8_t)flow_dir((const float(*)[RES])f, r, c);
+    }}
+    /* field_fixup_portal_edges (field.c:830) */
+    if(q->target_type == TARGET_PORTAL) {
+        bool up = q->next_chunk_r < cr, down = q->next_chunk_r > cr, left = q->next_chunk_c < cc;
+        uint8_t d = up ? FD_N : down ? FD_S : left ? FD_W : FD_E;
+        for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++)
+            if(f[r][c] == 0.0f) inout[r * RES + c] = d;
+    }
+}
+
+void pfo_flow_fields_update(const pfo_map *map, const pfo_field_req *reqs, size_t n, uint8_t *inout)
+{
+    for(size_t i = 0; i < n; i++) flow_field_update(map, &reqs[i], inout + i * 4096);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * LOS field
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { uint8_t vis[RES][RES], blk[RES][RES]; } los_t;
+
+/* field_create_wavefront_blocked_line (field.c:463) with M_Tile_Bounds (map/tile.c:356) */
+static void blocked_line(const pfo_map *m, const pfo_los_req *q, int r, int c, los_t *out)
+{
+    float tbx = (m->map_x - (float)(q->tgt_chunk_c * 256)) - (float)(q->tgt_tile_c * 4);
+    float tbz = (m->map_z + (float)(q->tgt_chunk_r * 256)) + (float)(q->tgt_tile_r * 4);
+    float cbx = (m->map_x - (float)(q->chunk_c * 256)) - (float)(c * 4);
+    float cbz = (m->map_z + (float)(q->chunk_r * 256)) + (float)(r * 4);
+    float tcx = tbx - 4.0f / 2.0f, tcz = tbz + 4.0f / 2.0f;
+    float ccx = cbx - 4.0f / 2.0f, ccz = cbz + 4.0f / 2.0f;
+    float sx_ = tcx - ccx, sz_ = tcz - ccz;
+    float len = (float)sqrt(sx_ * sx_ + sz_ * sz_);
+    sx_ = sx_ / len; sz_ = sz_ / len;
+    int dx = abs((int)(sx_ * 1000));
+    int dy = -abs((int)(sz_ * 1000));
+    int sx = sx_ > 0.0f ? 1 : -1;
+    int sy = sz_ < 0.0f ? 1 : -1;
+    int err = dx + dy, e2;
+    do {
+        out->blk[r][c] = 1;
+        e2 = 2 * err;
+        if(e2 >= dy) { err += dy; c += sx; }
+        if(e2 <= dx) { err += dx; r += sy; }
+    }while(r >= 0 && r < RES && c >= 0 && c < RES);
+}
+
+static bool blocked_or_impass(const pfo_map *m, int cr, int cc, int r, int c) { return !tile_passable(m, cr, cc, r, c); }
+
+/* field_is_los_corner (field.c:435) */
+static bool is_los_corner(const pfo_map *m, int cr, int cc, int r, int c)
+{
+    if(r > 0 && r < RES-1) {
+        bool a = blocked_or_impass(m, cr, cc, r-1, c), b = blocked_or_impass(m, cr, cc, r+1, c);
+        if(a ^ b) return true;
+    }
+    if(c > 0 && c < RES-1) {
+        bool a = blocked_or_impass(m, cr, cc, r, c-1), b = blocked_or_impass(m, cr, cc, r, c+1);
+        if(a ^ b) return true;
+    }
+    return false;
+}
+
+/* N_LOSFieldCreate (field.c:2085) */
+static void los_field_create(const pfo_map *m, const pfo_los_req *q, const uint8_t *prev, uint8_t *outb)
+{
+    los_t out; memset(&out, 0, sizeof(out));
+    float intf[RES][RES];
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) intf[r][c] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    const int cr = q->chunk_r, cc = q->chunk_c;
+    const uint8_t *cost = chunk_cost(m, cr, cc);
+
+    if(cr == q->tgt_chunk_r && cc == q->tgt_chunk_c) {
+        pq_push(&frontier, 0.0f, q->tgt_tile_r, q->tgt_tile_c);
+        intf[q->tgt_tile_r][q->tgt_tile_c] = 0.0f;
+    }else{
+        bool horizontal; int curr_edge, prev_edge;
+        if(q->prev_chunk_r < cr)      { horizontal = false; curr_edge = 0;     prev_edge = RES-1; }
+        else if(q->prev_chunk_r > cr) { horizontal = false; curr_edge = RES-1; prev_edge = 0; }
+        else if(q->prev_chunk_c < cc) { horizontal = true;  curr_edge = 0;     prev_edge = RES-1; }
+        else                          { horizontal = true;  curr_edge = RES-1; prev_edge = 0; }
+        for(int e = 0; e < RES; e++) {
+            int r = horizontal ? e : curr_edge, c = horizontal ? curr_edge : e;
+            uint8_t pv = horizontal ? prev[e * RES + prev_edge] : prev[prev_edge * RES + e];
+            out.vis[r][c] = pv & 1; out.blk[r][c] = (pv >> 1) & 1;
+            if(out.blk[r][c]) blocked_line(m, q, r, c, &out);
+            if(out.vis[r][c]) { pq_push(&frontier, 0.0f, r, c); intf[r][c] = 0.0f; }
+        }
+    }
+    while(frontier.size > 0) {
+        int r, c; pq_pop(&frontier, &r, &c);
+        /* field_neighbours_grid_los (field.c:304) */
+        for(int dr = -1; dr <= 1; dr++) {
+        for(int dc = -1; dc <= 1; dc++) {
+            int ar = r + dr, ac = c + dc;
+            if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+            if(dr == 0 && dc == 0) continue;
+            if(dr == dc || dr == -dc) continue;
+            if(out.blk[ar][ac]) continue;
+            uint8_t ncost = cost[ar * RES + ac];
+            if(!tile_passable(m, cr, cc, ar, ac)) ncost = COST_IMPASSABLE;
+            if(ncost > 1) {
+                if(!is_los_corner(m, cr, cc, ar, ac)) continue;
+                blocked_line(m, q, ar, ac, &out);
+            }else{
+                float new_cost = intf[r][c] + 1;
+                out.vis[ar][ac] = 1;
+                if(new_cost < intf[ar][ac]) {
+                    intf[ar][ac] = new_cost;
+                    if(!pq_contains(&frontier, ar, ac)) pq_push(&frontier, new_cost, ar, ac);
+                }
+            }
+        }}
+    }
+    pq_free(&frontier);
+    /* field_pad_wavefront (field.c:519) */
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) {
+        if(!out.blk[r][c]) continue;
+        for(int rr = r-1; rr <= r+1; rr++) for(int c2 = c-1; c2 <= c+1; c2++) {
+            if(rr < 0 || rr > RES-1 || c2 < 0 || c2 > RES-1) continue;
+            out.vis[rr][c2] = 0;
+        }
+    }
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++)
+        outb[r * RES + c] = (uint8_t)(out.vis[r][c] | (out.blk[r][c] << 1));
+}
+
+void pfo_los_fields_create(const pfo_map *map, const pfo_los_req *reqs, size_t n, uint8_t *out)
+{
+    for(size_t i = 0; i < n; i++) {
+        const uint8_t *prev = reqs[i].prev_index >= 0 ? out + (size_t)reqs[i].prev_index * 4096 : NULL;
+        los_field_create(map, &reqs[i], prev, out + i * 4096);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * vec2 (pf_math.c:58-94)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float x, z; } v2;
+static v2 v2_add(v2 a, v2 b) { return (v2){a.x + b.x, a.z + b.z}; }
+static v2 v2_sub(v2 a, v2 b) { return (v2){a.x - b.x, a.z - b.z}; }
+static v2 v2_scale(v2 a, float s) { return (v2){a.x * s, a.z * s}; }
+static float v2_dot(v2 a, v2 b) { return a.x * b.x + a.z * b.z; }
+static float v2_len(v2 a) { return sqrt(a.x * a.x + a.z * a.z); }
+static v2 v2_normal(v2 a) { float l = v2_len(a); return (v2){a.x / l, a.z / l}; }
+static v2 v2_truncate(v2 a, float max_len)       /* game/movement.c:643 */
+{
+    if(v2_len(a) > max_len) { a = v2_normal(a); a = v2_scale(a, max_len); }
+    return a;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * tiles (map/tile.c:547, map/map.c:817-845)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int chunk_r, chunk_c, tile_r, tile_c; } tdesc;
+#define CLAMP(a, lo, hi) ((a) < (lo) ? (lo) : (a) > (hi) ? (hi) : (a))
+
+static bool desc_for_point(const pfo_map *m, float px, float pz, tdesc *out)
+{
+    float width = m->chunk_w * 256.0f, height = m->chunk_h * 256.0f;
+    if(px > m->map_x || px < m->map_x - width) return false;
+    if(pz < m->map_z || pz > m->map_z + height) return false;
+    int chunk_r = fabs(m->map_z - pz) / 256.0f;
+    int chunk_c = fabs(m->map_x - px) / 256.0f;
+    chunk_r = CLAMP(chunk_r, 0, m->chunk_h - 1);
+    chunk_c = CLAMP(chunk_c, 0, m->chunk_w - 1);
+    float base_x = m->map_x - (chunk_c * 256.0f);
+    float base_z = m->map_z + (chunk_r * 256.0f);
+    int tile_r = fabs(base_z - pz) / 4;
+    int tile_c = fabs(base_x - px) / 4;
+    out->chunk_r = chunk_r; out->chunk_c = chunk_c;
+    out->tile_r = CLAMP(tile_r, 0, RES-1); out->tile_c = CLAMP(tile_c, 0, RES-1);
+    return true;
+}
+
+static void probe(const pfo_map *m, float px, float pz, bool *pathable, bool *blocked)
+{
+    tdesc t; *pathable = false; *blocked = false;
+    if(!desc_for_point(m, px, pz, &t)) return;
+    *pathable = chunk_cost(m, t.chunk_r, t.chunk_c)[t.tile_r * RES + t.tile_c] != COST_IMPASSABLE;
+    *blocked = chunk_blk(m, t.chunk_r, t.chunk_c, t.tile_r, t.tile_c) > 0;
+}
+
+static v2 flow_dir_vec(int dir)     /* N_FlowDir (navigation/field.c:2429) */
+{
+    float d = 1.0f / sqrt(2.0f);
+    switch(dir) {
+    case FD_NW: return (v2){d, -d};   case FD_N: return (v2){0.0f, -1.0f}; case FD_NE: return (v2){-d, -d};
+    case FD_W:  return (v2){1.0f, 0.0f}; case FD_E: return (v2){-1.0f, 0.0f};
+    case FD_SW: return (v2){d, d};    case FD_S: return (v2){0.0f, 1.0f};  case FD_SE: return (v2){-d, d};
+    default: return (v2){0.0f, 0.0f};
+    }
+}
+
+/* N_DesiredPointSeekVelocity happy path + n_interpolated_flow_dir (navigation/nav.c:3468, 3407)
+ * and N_HasDestLOS (nav.c:4026); the n_request_path-on-miss branches are the host planner's job. */
+void pfo_desired_velocity(const pfo_map *m, const pfo_agent *agents, const pfo_flock *flocks,
+                          const uint32_t *work, size_t nwork, const int32_t *slot,
+                          const uint8_t *flow, const uint8_t *los, float *out_vdes, uint8_t *out_los)
+{
+    const int chunks = m->chunk_w * m->chunk_h;
+    for(size_t w = 0; w < nwork; w++) {
+        const pfo_agent *a = &agents[work[w]];
+        v2 vdes = {0.0f, 0.0f}; uint8_t l = 0;
+        int dest = a->flock >= 0 ? flocks[a->flock].dest : -1;
+        if(dest >= 0) {
+            const int32_t *sl = slot + (size_t)dest * chunks;
+            tdesc t;
+            if(los && desc_for_point(m, a->prev_pos[0], a->prev_pos[1], &t)) {
+                int s = sl[t.chunk_r * m->chunk_w + t.chunk_c];
+                if(s >= 0) l = los[(size_t)s * 4096 + t.tile_r * RES + t.tile_c] & 1;
+            }
+            if(desc_for_point(m, a->pos[0], a->pos[1], &t)) {
+                int s = sl[t.chunk_r * m->chunk_w + t.chunk_c];
+                if(s >= 0) {
+                    const uint8_t *base_ff = flow + (size_t)s * 4096;
+                    int base_dir = base_ff[t.tile_r * RES + t.tile_c] & 0xf;
+                    float bx = (m->map_x - (float)(t.chunk_c * 256)) - (float)(t.tile_c * 4);
+                    float bz = (m->map_z + (float)(t.chunk_r * 256)) + (float)(t.tile_r * 4);
+                    float cx = bx - 4.0f / 2.0f, cz = bz + 4.0f / 2.0f;
+                    float dx = a->pos[0] - cx, dz = a->pos[1] - cz;
+                    int dc = (dx < 0.0f) ? 1 : -1, dr = (dz > 0.0f) ? 1 : -1;
+                    float wc = fmin(fabs(dx) / 4.0f, 1.0f), wr = fmin(fabs(dz) / 4.0f, 1.0f);
+                    const int sdc[4] = {0, dc, 0, dc}, sdr[4] = {0, 0, dr, dr};
+                    const float sw[4] = {(1.0f - wc) * (1.0f - wr), wc * (1.0f - wr), (1.0f - wc) * wr, wc * wr};
+                    v2 acc = {0.0f, 0.0f}; float wsum = 0.0f;
+                    for(int i = 0; i < 4; i++) {
+                        if(sw[i] <= 0.0f) continue;
+                        int ar = t.chunk_r * RES + t.tile_r + sdr[i], ac = t.chunk_c * RES + t.tile_c + sdc[i];
+                        if(ar < 0 || ar >= m->chunk_h * RES || ac < 0 || ac >= m->chunk_w * RES) continue;
+                        const uint8_t *ff = base_ff;
+                        if(ar / RES != t.chunk_r || ac / RES != t.chunk_c) {
+                            int s2 = sl[(ar / RES) * m->chunk_w + ac / RES];
+                            if(s2 < 0) continue;
+                            ff = flow + (size_t)s2 * 4096;
+                        }
+                        int dir = ff[(ar % RES) * RES + ac % RES] & 0xf;
+                        if(dir == FD_NONE) continue;
+                        acc = v2_add(acc, v2_scale(flow_dir_vec(dir), sw[i]));
+                        wsum += sw[i];
+                    }
+                    if(wsum < 1e-6f || v2_len(acc) < 1e-6f) vdes = flow_dir_vec(base_dir);
+                    else vdes = v2_normal(acc);
+                }
+            }
+        }
+        out_vdes[2*w] = vdes.x; out_vdes[2*w+1] = vdes.z;
+        if(out_los) out_los[w] = l;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * position index (lib/public/bitmap_grid.h; game/position.c:264, 359, 379)
+ * ---------------------------------------------------------------------------------------- */
+struct pfo_world {
+    pfo_map map;
+    const pfo_agent *agents; size_t n;
+    const pfo_flock *flocks; size_t nflocks;
+    int hz;
+    int grid_w, grid_h; int32_t origin_x, origin_y;
+    uint32_t *cell_start;        /* [ncells+1] */
+    uint32_t *sid; int32_t *six, *siy;
+    uint32_t *flock_start, *flock_members;
+};
+
+static int32_t bg_scale(float x) { return (int32_t)lrintf(x * 256.0f); }
+static int cell_of(int32_t i, int32_t origin, int n) { int c = (i - origin) >> 12; return c < 0 ? 0 : c >= n ? n - 1 : c; }
+
+pfo_world *pfo_world_create(const pfo_map *map, const pfo_agent *agents, size_t n,
+                            const pfo_flock *flocks, size_t nflocks, int hz)
+{
+    pfo_world *w = calloc(1, sizeof(*w));
+    w->map = *map; w->agents = agents; w->n = n; w->flocks = flocks; w->nflocks = nflocks; w->hz = hz;
+    float W = map->chunk_w * 256.0f, H = map->chunk_h * 256.0f;
+    float cx = map->map_x - W / 2.0f, cz = map->map_z + H / 2.0f;
+    float xmin = cx - W / 2.0f, xmax = cx + W / 2.0f, zmin = cz - H / 2.0f, zmax = cz + H / 2.0f;
+    w->origin_x = bg_scale(xmin); w->origin_y = bg_scale(zmin);
+    int32_t span_x = bg_scale(xmax) - w->origin_x, span_y = bg_scale(zmax) - w->origin_y;
+    w->grid_w = (int)(((uint32_t)span_x + 4095u) >> 12); if(w->grid_w < 1) w->grid_w = 1;
+    w->grid_h = (int)(((uint32_t)span_y + 4095u) >> 12); if(w->grid_h < 1) w->grid_h = 1;
+    size_t ncells = (size_t)w->grid_w * w->grid_h;
+    w->cell_start = calloc(ncells + 1, 4);
+    w->sid = malloc((n ? n : 1) * 4); w->six = malloc((n ? n : 1) * 4); w->siy = malloc((n ? n : 1) * 4);
+    uint32_t *cnt = calloc(ncells + 1, 4);
+    for(size_t i = 0; i < n; i++) {
+        int c = cell_of(bg_scale(agents[i].pos[1]), w->origin_y, w->grid_h) * w->grid_w
+              + cell_of(bg_scale(agents[i].pos[0]), w->origin_x, w->grid_w);
+        cnt[c]++;
+    }
+    for(size_t c = 0; c < ncells; c++) w->cell_start[c + 1] = w->cell_start[c] + cnt[c];
+    memset(cnt, 0, (ncells + 1) * 4);
+    /* insert in uid order then bg_cleanup: each cell holds its members in DESCENDING uid order
+     * (LIFO overflow chain, bitmap_grid.h:1110-1130, 1477-1540) */
+    for(size_t k = n; k-- > 0;) {
+        int c = cell_of(bg_scale(agents[k].pos[1]), w->origin_y, w->grid_h) * w->grid_w
+              + cell_of(bg_scale(agents[k].pos[0]), w->origin_x, w->grid_w);
+        uint32_t slot = w->cell_start[c] + cnt[c]++;
+        w->sid[slot] = (uint32_t)k; w->six[slot] = bg_scale(agents[k].pos[0]); w->siy[slot] = bg_scale(agents[k].pos[1]);
+    }
+    free(cnt);
+    w->flock_start = calloc(nflocks + 1, 4); w->flock_members = malloc((n ? n : 1) * 4);
+    for(size_t i = 0; i < n; i++) if(agents[i].flock >= 0) w->flock_start[agents[i].flock + 1]++;
+    for(size_t f = 0; f < nflocks; f++) w->flock_start[f + 1] += w->flock_start[f];
+    uint32_t *cur = malloc((nflocks + 1) * 4); memcpy(cur, w->flock_start, (nflocks + 1) * 4);
+    for(size_t i = 0; i < n; i++) if(agents[i].flock >= 0) w->flock_members[cur[agents[i].flock]++] = (uint32_t)i;
+    free(cur);
+    return w;
+}
+
+void pfo_world_destroy(pfo_world *w)
+{
+    if(!w) return;
+    free(w->cell_start); free(w->sid); free(w->six); free(w->siy); free(w->flock_start); free(w->flock_members);
+    free(w);
+}
+
+/* bg_ent_inrange_circle (bitmap_grid.h:1376) */
+int pfo_ents_in_circle(const pfo_world *w, float x, float z, float range, uint32_t *out, int maxout)
+{
+    if(maxout <= 0 || range < 0.0f) return 0;
+    int32_t icx = bg_scale(x), icy = bg_scale(z), ir = bg_scale(range);
+    int64_t ir2 = (int64_t)ir * ir;
+    int32_t imnx = icx - ir, imxx = icx + ir, imny = icy - ir, imxy = icy + ir;
+    if(imxx < w->origin_x || imxy < w->origin_y) return 0;
+    if(imnx >= w->origin_x + (w->grid_w << 12) || imny >= w->origin_y + (w->grid_h << 12)) return 0;
+    int cx_lo = (imnx - w->origin_x) >> 12, cx_hi = (imxx - w->origin_x) >> 12;
+    int cy_lo = (imny - w->origin_y) >> 12, cy_hi = (imxy - w->origin_y) >> 12;
+    if(cx_lo < 0) cx_lo = 0; if(cy_lo < 0) cy_lo = 0;
+    if(cx_hi >= w->grid_w) cx_hi = w->grid_w - 1; if(cy_hi >= w->grid_h) cy_hi = w->grid_h - 1;
+    int written = 0;
+    int64_t extent = (int64_t)(cx_hi - cx_lo + 1) * (cy_hi - cy_lo + 1), total = (int64_t)w->grid_w * w->grid_h;
+    if(extent * 4 >= total * 3) {       /* wide query: whole pool in pool order */
+        for(size_t i = 0; i < w->n; i++) {
+            int64_t dx = (int64_t)w->six[i] - icx, dy = (int64_t)w->siy[i] - icy;
+            if(dx * dx + dy * dy <= ir2) { out[written++] = w->sid[i]; if(written >= maxout) return maxout; }
+        }
+        return written;
+    }
+    for(int cyc = cy_lo >> 3; cyc <= cy_hi >> 3; cyc++) {
+    for(int cxc = cx_lo >> 3; cxc <= cx_hi >> 3; cxc++) {
+        int fy0 = cyc * 8, fy1 = fy0 + 8, fx0 = cxc * 8, fx1 = fx0 + 8;
+        if(fy0 < cy_lo) fy0 = cy_lo; if(fy1 > cy_hi + 1) fy1 = cy_hi + 1;
+        if(fx0 < cx_lo) fx0 = cx_lo; if(fx1 > cx_hi + 1) fx1 = cx_hi + 1;
+        for(int fy = fy0; fy < fy1; fy++) {
+        for(int fx = fx0; fx < fx1; fx++) {
+            int c = fy * w->grid_w + fx;
+            for(uint32_t i = w->cell_start[c]; i < w->cell_start[c + 1]; i++) {
+                int64_t dx = (int64_t)w->six[i] - icx, dy = (int64_t)w->siy[i] - icy;
+                if(dx * dx + dy * dy <= ir2) { out[written++] = w->sid[i]; if(written >= maxout) return maxout; }
+            }
+        }}
+    }}
+    return written;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * ClearPath (game/clearpath.c) + line intersections (phys/collision.c:820-875)
+ * ---------------------------------------------------------------------------------------- */
+#define EPSILON (1.0 / 1024)
+#define EPSILON_F (1.0f / 1024)
+#define MAX_NEIGHBOURS 32
+typedef struct { v2 point, dir; } line2;
+typedef struct { v2 pos, vel; float radius; } cpent;
+
+static bool infinite_line_isect(line2 l1, line2 l2, v2 *out)      /* collision.c:820 */
+{
+    float s1 = fabs(l1.dir.x) < EPSILON_F ? NAN : (l1.dir.z / l1.dir.x);
+    float s2 = fabs(l2.dir.x) < EPSILON_F ? NAN : (l2.dir.z / l2.dir.x);
+    if(isnan(s1) && isnan(s2)) return false;
+    if(fabs(s1 - s2) < EPSILON_F) return false;
+    if(isnan(s1) && !isnan(s2)) {
+        out->x = l1.point.x;
+        out->z = (l1.point.x - l2.point.x) * s2 + l2.point.z;
+    }else if(!isnan(s1) && isnan(s2)) {
+        out->x = l2.point.x;
+        out->z = (l2.point.x - l1.point.x) * s1 + l2.point.z;     /* sic: l2.point (collision.c:839-840) */
+    }else{
+        out->x = (s1 * l1.point.x - s2 * l2.point.x + l2.point.z - l1.point.z) / (s1 - s2);
+        out->z = s2 * (out->x - l2.point.x) + l2.point.z;
+    }
+    return true;
+}
+
+static bool ray_ray_isect(line2 l1, line2 l2, v2 *out)            /* collision.c:854 */
+{
+    v2 p;
+    if(!infinite_line_isect(l1, l2, &p)) return false;
+    if((p.x - l1.point.x) / l1.dir.x < 0.0f) return false;
+    if((p.z - l1.point.z) / l1.dir.z < 0.0f) return false;
+    if((p.x - l2.point.x) / l2.dir.x < 0.0f) return false;
+    if((p.z - l2.point.z) / l2.dir.z < 0.0f) return false;
+    *out = p;
+    return true;
+}
+
+static bool inside_pcr(const line2 *rays, int n_rays, v2 test)    /* clearpath.c:249 */
+{
+    for(int i = 0; i < n_rays; i += 2) {
+        v2 ptt = v2_sub(test, rays[i].point);
+        if(v2_len(ptt) < EPSILON) continue;
+        ptt = v2_normal(ptt);
+        float left_det = (ptt.z * rays[i].dir.x) - (ptt.x * rays[i].dir.z);
+        if(left_det < EPSILON) continue;
+        ptt = v2_sub(test, rays[i+1].point);
+        if(v2_len(ptt) < EPSILON) continue;
+        ptt = v2_normal(ptt);
+        float right_det = (ptt.z * rays[i+1].dir.x) - (ptt.x * rays[i+1].dir.z);
+        if(right_det > -EPSILON) continue;
+        return true;
+    }
+    return false;
+}
+
+static void vo_edges(cpent ent, cpent nb, v2 *right, v2 *left)    /* clearpath.c:130 */
+{
+    v2 e2n = v2_normal(v2_sub(nb.pos, ent.pos));
+    v2 r = {-e2n.z, e2n.x};
+    r = v2_scale(r, nb.radius + ent.radius + 0.0f);
+    v2 rt = v2_add(nb.pos, r), lt = v2_sub(nb.pos, r);
+    *right = v2_normal(v2_sub(rt, ent.pos));
+    *left = v2_normal(v2_sub(lt, ent.pos));
+}
+
+/* clearpath_new_velocity (clearpath.c:552) */
+static bool clearpath_new_velocity(cpent ent, v2 des_v, const cpent *dyn, int ndyn, const cpent *stat, int nstat, v2 *out)
+{
+    line2 rays[4 * MAX_NEIGHBOURS];
+    int n_rays = 0;
+    for(int i = 0; i < ndyn; i++) {     /* compute_all_hrvos :232 -> compute_hrvo :174 */
+        cpent nb = dyn[i];
+        if(v2_len(v2_sub(nb.pos, ent.pos)) < EPSILON) continue;
+        v2 right, left; vo_edges(ent, nb, &right, &left);
+        v2 rvo_apex = v2_add(ent.pos, v2_scale(v2_add(ent.vel, nb.vel), 0.5f));
+        v2 centerline = v2_add(left, right);
+        v2 vo_apex = v2_add(ent.pos, nb.vel);
+        float det = (centerline.x * ent.vel.z) - (centerline.z * ent.vel.x);
+        v2 apex = rvo_apex, p;
+        if(det > EPSILON) { if(infinite_line_isect((line2){rvo_apex, left}, (line2){vo_apex, right}, &p)) apex = p; }
+        else if(det < -EPSILON) { if(infinite_line_isect((line2){rvo_apex, right}, (line2){vo_apex, left}, &p)) apex = p; }
+        rays[n_rays++] = (line2){apex, left};
+        rays[n_rays++] = (line2){apex, right};
+    }
+    for(int i = 0; i < nstat; i++) {    /* compute_all_vos :216 */
+        cpent nb = stat[i];
+        if(v2_len(v2_sub(nb.pos, ent.pos)) < EPSILON) continue;
+        v2 right, left; vo_edges(ent, nb, &right, &left);
+        v2 apex = v2_add(ent.pos, nb.vel);
+        rays[n_rays++] = (line2){apex, left};
+        rays[n_rays++] = (line2){apex, right};
+    }
+    v2 des_v_ws = v2_add(ent.pos, des_v);
+    if(!inside_pcr(rays, n_rays, des_v_ws)) { *out = des_v; return true; }
+    /* compute_vo_xpoints :321, compute_vdes_proj_points :344, compute_vnew :368 (fused) */
+    float min_dist = INFINITY; v2 ret = {0.0f, 0.0f}; int npoints = 0;
+    for(int i = 0; i < n_rays; i++) for(int j = 0; j < n_rays; j++) {
+        if(i == j) continue;
+        v2 p;
+        if(!ray_ray_isect(rays[i], rays[j], &p)) continue;
+        if(inside_pcr(rays, n_rays, p)) continue;
+        npoints++;
+        v2 curr = v2_sub(p, ent.pos); float len = v2_len(v2_sub(des_v, curr));
+        if(len < min_dist) { min_dist = len; ret = curr; }
+    }
+    for(int i = 0; i < n_rays; i++) {
+        float len = v2_dot(rays[i].dir, des_v);
+        v2 proj = v2_add(rays[i].point, v2_scale(rays[i].dir, len));
+        if(inside_pcr(rays, n_rays, proj)) continue;
+        npoints++;
+        v2 curr = v2_sub(proj, ent.pos); float l2 = v2_len(v2_sub(des_v, curr));
+        if(l2 < min_dist) { min_dist = l2; ret = curr; }
+    }
+    if(npoints == 0) return false;
+    *out = ret;
+    return true;
+}
+
+/* G_ClearPath_NewVelocity (clearpath.c:694) incl. remove_furthest (:390) */
+static v2 clearpath(cpent ent, v2 des_v, cpent *dyn, int ndyn, cpent *stat, int nstat)
+{
+    do {
+        v2 ret;
+        if(clearpath_new_velocity(ent, des_v, dyn, ndyn, stat, nstat, &ret)) return ret;
+        float max_dist = -INFINITY; int which = -1, idx = -1;
+        for(int j = 0; j < ndyn; j++) { float l = v2_len(v2_sub(ent.pos, dyn[j].pos)); if(l > max_dist) { max_dist = l; which = 0; idx = j; } }
+        for(int j = 0; j < nstat; j++) { float l = v2_len(v2_sub(ent.pos, stat[j].pos)); if(l > max_dist) { max_dist = l; which = 1; idx = j; } }
+        if(which == 0) dyn[idx] = dyn[--ndyn];
+        else if(which == 1) stat[idx] = stat[--nstat];
+    }while(ndyn > 0 && nstat > 0);
+    return (v2){0.0f, 0.0f};
+}
+
+/* ------------------------------------------------------------------------------------------
+ * move_velocity_work (game/movement.c:3395) for the point-seek states
+ * ---------------------------------------------------------------------------------------- */
+#define FLAG_MOVABLE (1u << 3)
+#define FLAG_AIR (1u << 15)
+#define FLAG_COMBAT_HELD (1u << 21)
+#define STATE_ARRIVED 2
+#define STATE_WAITING 4
+#define STATE_TURNING 7
+
+void pfo_velocity_work(const pfo_world *w, const uint32_t *work, size_t nwork, float *out_vel, float *out_vpref)
+{
+    const pfo_map *m = &w->map;
+    const int hz = w->hz;
+    /* SCALED_MAX_FORCE (movement.c:93): (MAX_FORCE / hz_count * 20.0) is a double */
+    const double smf_d = (double)(0.75f / hz) * 20.0;
+    const float smf = (float)smf_d;
+    for(size_t wi = 0; wi < nwork; wi++) {
+        const uint32_t uid = work[wi];
+        const pfo_agent *a = &w->agents[uid];
+        const uint32_t ent_flags = a->flags;
+        if(ent_flags & FLAG_COMBAT_HELD) {
+            out_vel[2*wi] = out_vel[2*wi+1] = 0.0f;
+            if(out_vpref) out_vpref[2*wi] = out_vpref[2*wi+1] = 0.0f;
+            continue;
+        }
+        v2 pos = {a->pos[0], a->pos[1]}, velocity = {a->velocity[0], a->velocity[1]};
+        v2 vdes = {a->vdes[0], a->vdes[1]};
+        v2 vpref = {0.0f, 0.0f};
+        if(a->state != STATE_TURNING) {
+            /* separation_force (movement.c:1690) */
+            uint32_t near_ents[128];
+            int num_near = pfo_ents_in_circle(w, pos.x, pos.z, 30.0f, near_ents, 128);
+            v2 separation = {0.0f, 0.0f};
+            for(int i = 0; i < num_near; i++) {
+                uint32_t curr = near_ents[i];
+                const pfo_agent *o = &w->agents[curr];
+                if(curr == uid) continue;
+                if(!(o->flags & FLAG_MOVABLE)) continue;
+                if((ent_flags & FLAG_AIR) != (o->flags & FLAG_AIR)) continue;
+                v2 diff = v2_sub((v2){o->pos[0], o->pos[1]}, pos);
+                float radius = a->radius + o->radius + 0.0f;
+                if(v2_len(diff) < EPSILON_F) continue;
+                float t = (v2_len(diff) - radius * 0.85f) / v2_len(diff);
+                float mt = -20.0f * t;
+                float scale = exp(mt < 40.0f ? mt : 40.0f);
+                separation = v2_add(separation, v2_scale(diff, scale));
+            }
+            if(num_near != 0) { separation = v2_scale(separation, -1.0f); separation = v2_truncate(separation, smf); }
+            else separation = (v2){0.0f, 0.0f};
+            /* arrive_force_point (movement.c:1546) */
+            v2 target = a->flock >= 0 ? (v2){w->flocks[a->flock].target[0], w->flocks[a->flock].target[1]} : pos;
+            v2 desired;
+            if(a->has_dest_los) {
+                desired = v2_sub(target, pos);
+                float distance = v2_len(desired);
+                desired = v2_normal(desired);
+                desired = v2_scale(desired, a->max_speed / hz);
+                if(distance < 10.0f) desired = v2_scale(desired, distance / 10.0f);
+            }else desired = v2_scale(vdes, a->max_speed / hz);
+            v2 arrive = v2_truncate(v2_sub(desired, velocity), smf);
+            /* cohesion_force (movement.c:1653), members in ascending uid */
+            v2 cohesion = {0.0f, 0.0f};
+            if(a->flock >= 0) {
+                v2 com = {0.0f, 0.0f}; size_t cnt = 0;
+                for(uint32_t k = w->flock_start[a->flock]; k < w->flock_start[a->flock + 1]; k++) {
+                    uint32_t cu = w->flock_members[k];
+                    if(cu == uid) continue;
+                    v2 cp = {w->agents[cu].pos[0], w->agents[cu].pos[1]};
+                    v2 diff = v2_sub(cp, pos);
+                    float t = (v2_len(diff) - 50.0f * 0.75) / 50.0f;
+                    float scale = exp(-6.0f * t);
+                    com = v2_add(com, v2_scale(cp, scale));
+                    cnt++;
+                }
+                if(cnt) { com = v2_scale(com, 1.0f / cnt); cohesion = v2_truncate(v2_sub(com, pos), smf); }
+            }
+            /* nullify_impass_components probes (movement.c:1831); ground layer 0 only */
+            bool on_blocked, d0, lp, lb, rp, rb, tp, tb, bp, bb;
+            probe(m, pos.x, pos.z, &d0, &on_blocked);
+            probe(m, pos.x + 4.0f, pos.z, &lp, &lb); probe(m, pos.x - 4.0f, pos.z, &rp, &rb);
+            probe(m, pos.x, pos.z + 4.0f, &tp, &tb); probe(m, pos.x, pos.z - 4.0f, &bp, &bb);
+            v2 steer = {0.0f, 0.0f};
+            for(int prio = 0; prio < 3; prio++) {       /* point_seek_vpref (movement.c:1870) */
+                if(prio == 0) {                         /* point_seek_total_force (movement.c:1745) */
+                    v2 A = v2_scale(arrive, 0.5f), C = v2_scale(cohesion, 0.15f), S = v2_scale(separation, 0.6f);
+                    v2 ret = {0.0f, 0.0f};
+                    ret = v2_add(ret, A); ret = v2_add(ret, S); ret = v2_add(ret, C);
+                    steer = v2_truncate(ret, smf);
+                }else if(prio == 1) steer = separation;
+                else steer = arrive;
+                if(steer.x > 0 && (!lp || (!on_blocked && lb))) steer.x = 0.0f;
+                if(steer.x < 0 && (!rp || (!on_blocked && rb))) steer.x = 0.0f;
+                if(steer.z > 0 && (!tp || (!on_blocked && tb))) steer.z = 0.0f;
+                if(steer.z < 0 && (!bp || (!on_blocked && bb))) steer.z = 0.0f;
+                if(v2_len(steer) > smf_d * 0.01) break;
+            }
+            vpref = v2_truncate(v2_add(velocity, v2_scale(steer, 1.0f / 1.0f)), a->speed / hz);
+        }
+        /* find_neighbours (movement.c:2768) */
+        uint32_t near_ents[512];
+        int num_near = pfo_ents_in_circle(w, pos.x, pos.z, 10.0f, near_ents, 512);
+        cpent dyn[MAX_NEIGHBOURS], stat[MAX_NEIGHBOURS]; int ndyn = 0, nstat = 0;
+        for(int i = 0; i < num_near; i++) {
+            uint32_t curr = near_ents[i];
+            const pfo_agent *o = &w->agents[curr];
+            if(curr == uid) continue;
+            if(!(o->flags & FLAG_MOVABLE)) continue;
+            if(o->radius == 0.0f) continue;
+            if((ent_flags & FLAG_AIR) != (o->flags & FLAG_AIR)) continue;
+            cpent nd = {{o->pos[0], o->pos[1]}, {o->velocity[0], o->velocity[1]}, o->radius};
+            bool still = (o->state == STATE_ARRIVED || o->state == STATE_WAITING);
+            if(still || v2_len(nd.vel) < 0.3f) { nd.vel = (v2){0.0f, 0.0f}; if(nstat < MAX_NEIGHBOURS) stat[nstat++] = nd; }
+            else { if(ndyn < MAX_NEIGHBOURS) dyn[ndyn++] = nd; }
+        }
+        cpent self = {{a->prev_pos[0], a->prev_pos[1]}, velocity, a->radius};
+        v2 nv = clearpath(self, vpref, dyn, ndyn, stat, nstat);
+        nv = v2_truncate(nv, a->max_speed / hz);
+        out_vel[2*wi] = nv.x; out_vel[2*wi+1] = nv.z;
+        if(out_vpref) { out_vpref[2*wi] = vpref.x; out_vpref[2*wi+1] = vpref.z; }
+    }
+}

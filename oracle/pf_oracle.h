@@ -1,0 +1,72 @@
+/*
+ * oracle/pf_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("port") of the reference algorithms on the hot path, in plain C99. It is the
+ * checker for the CUDA path when the compiled reference (oracle/_ref) is not at hand, and is
+ * itself pinned against oracle/_ref and the committed golden vectors (tests/test_oracle.py).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it; libpfnav.so never links or calls anything here.
+ *
+ * Request structs are layout-identical to include/pfnav.h so that one numpy record array feeds
+ * both sides.
+ */
+#ifndef PF_ORACLE_H
+#define PF_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+typedef struct pfo_map {
+    int chunk_w, chunk_h;
+    float map_x, map_z;
+    const uint8_t  *cost;            /* [chunks][64][64], one layer */
+    const uint16_t *blockers;        /* may be NULL (all zero) */
+    const uint16_t *local_islands;   /* may be NULL when no TARGET_PORTAL request is made */
+} pfo_map;
+
+typedef struct pfo_field_req {       /* == pfnav_field_req */
+    int32_t chunk_r, chunk_c, layer, faction_id, target_type, init, tile_r, tile_c;
+    int16_t port_r0, port_c0, port_r1, port_c1, next_r0, next_c0, next_r1, next_c1;
+    int32_t next_chunk_r, next_chunk_c;
+    uint16_t port_iid, next_iid;
+    int32_t _pad;
+} pfo_field_req;
+
+typedef struct pfo_los_req {         /* == pfnav_los_req */
+    int32_t chunk_r, chunk_c, layer, faction_id, tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c;
+    int32_t prev_index, prev_chunk_r, prev_chunk_c, _pad;
+} pfo_los_req;
+
+typedef struct pfo_agent {           /* == pfnav_agent */
+    float pos[2], prev_pos[2], velocity[2], vdes[2];
+    float radius, max_speed, speed;
+    uint32_t state, flags;
+    int32_t flock;
+    uint32_t has_dest_los, _pad;
+} pfo_agent;
+
+typedef struct pfo_flock {           /* == pfnav_flock */
+    float target[2];
+    int32_t dest, layer;
+} pfo_flock;
+
+/* N_FlowFieldInit + N_FlowFieldUpdate, TARGET_TILE / TARGET_PORTAL (field.c:2020-2083) */
+void pfo_flow_fields_update(const pfo_map *map, const pfo_field_req *reqs, size_t n, uint8_t *inout);
+/* N_LOSFieldCreate (field.c:2085-2245); requests may chain through prev_index */
+void pfo_los_fields_create(const pfo_map *map, const pfo_los_req *reqs, size_t n, uint8_t *out);
+
+/* Position index + velocity update (position.c:379, bitmap_grid.h:1376; movement.c:3395-3466;
+ * clearpath.c:694). Agents are indexed by uid; cohesion sums flock members in ascending uid. */
+typedef struct pfo_world pfo_world;
+pfo_world *pfo_world_create(const pfo_map *map, const pfo_agent *agents, size_t n,
+                            const pfo_flock *flocks, size_t nflocks, int hz);
+void pfo_world_destroy(pfo_world *w);
+int  pfo_ents_in_circle(const pfo_world *w, float x, float z, float range, uint32_t *out, int maxout);
+/* vdes / has_dest_los are taken from the agent records. out_vel/out_vpref: 2 floats per work item */
+void pfo_velocity_work(const pfo_world *w, const uint32_t *work, size_t nwork, float *out_vel,
+                       float *out_vpref);
+/* N_DesiredPointSeekVelocity + N_HasDestLOS against caller-supplied fields: slot[dest*chunks+chunk]
+ * indexes flow/los (4096 B each), -1 = absent (nav.c:3468, 4026, 3407) */
+void pfo_desired_velocity(const pfo_map *map, const pfo_agent *agents, const pfo_flock *flocks,
+                          const uint32_t *work, size_t nwork, const int32_t *slot,
+                          const uint8_t *flow, const uint8_t *los, float *out_vdes, uint8_t *out_los);
+#endif

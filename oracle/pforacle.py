@@ -1,0 +1,98 @@
+"""ctypes binding of oracle/libpforacle.so -- the plain-C CPU restatement (pf_oracle.c).
+TEST INFRASTRUCTURE: see the header of pf_oracle.h for who may import this."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpforacle.so")
+_lib = None
+
+
+class _Map(C.Structure):
+    _fields_ = [("chunk_w", C.c_int), ("chunk_h", C.c_int), ("map_x", C.c_float), ("map_z", C.c_float),
+                ("cost", C.c_void_p), ("blockers", C.c_void_p), ("local_islands", C.c_void_p)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.pfo_flow_fields_update.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pfo_los_fields_create.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pfo_world_create.restype = C.c_void_p
+        L.pfo_world_create.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        L.pfo_world_destroy.argtypes = [C.c_void_p]
+        L.pfo_ents_in_circle.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int]
+        L.pfo_velocity_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.pfo_desired_velocity.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class OracleMap:
+    def __init__(self, chunk_w, chunk_h, cost, blockers=None, local_islands=None, map_x=0.0, map_z=0.0):
+        self.cw, self.ch = chunk_w, chunk_h
+        self.cost = np.ascontiguousarray(cost, np.uint8)
+        self.blockers = None if blockers is None else np.ascontiguousarray(blockers, np.uint16)
+        self.liid = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
+        self.m = _Map(chunk_w, chunk_h, map_x, map_z, _p(self.cost), _p(self.blockers), _p(self.liid))
+
+    def flow_fields_update(self, reqs, inout=None):
+        reqs = np.ascontiguousarray(reqs)
+        n = len(reqs)
+        buf = np.zeros((n, 64, 64), np.uint8) if inout is None else np.ascontiguousarray(inout, np.uint8).reshape(n, 64, 64).copy()
+        lib().pfo_flow_fields_update(C.byref(self.m), _p(reqs), n, _p(buf))
+        return buf
+
+    def los_fields_create(self, reqs):
+        reqs = np.ascontiguousarray(reqs)
+        out = np.zeros((len(reqs), 64, 64), np.uint8)
+        lib().pfo_los_fields_create(C.byref(self.m), _p(reqs), len(reqs), _p(out))
+        return out
+
+    def desired_velocity(self, agents, flocks, work, slot, flow, los):
+        work = np.ascontiguousarray(work, np.uint32)
+        slot = np.ascontiguousarray(slot, np.int32)
+        vdes = np.zeros((len(work), 2), np.float32); lo = np.zeros(len(work), np.uint8)
+        lib().pfo_desired_velocity(C.byref(self.m), _p(agents), _p(flocks), _p(work), len(work), _p(slot),
+                                   _p(flow), _p(los), _p(vdes), _p(lo))
+        return vdes, lo
+
+
+class OracleWorld:
+    def __init__(self, omap, agents, flocks, hz=20):
+        self.omap = omap
+        self.agents = np.ascontiguousarray(agents)
+        self.flocks = np.ascontiguousarray(flocks)
+        self.h = lib().pfo_world_create(C.byref(omap.m), _p(self.agents), len(self.agents), _p(self.flocks),
+                                        len(self.flocks), hz)
+
+    def close(self):
+        if self.h:
+            lib().pfo_world_destroy(self.h)
+            self.h = None
+
+    def ents_in_circle(self, x, z, r, maxout=512):
+        out = np.zeros(maxout, np.uint32)
+        n = lib().pfo_ents_in_circle(self.h, x, z, r, _p(out), maxout)
+        return out[:n].copy()
+
+    def velocity_work(self, work):
+        work = np.ascontiguousarray(work, np.uint32)
+        vel = np.zeros((len(work), 2), np.float32); vpref = np.zeros((len(work), 2), np.float32)
+        lib().pfo_velocity_work(self.h, _p(work), len(work), _p(vel), _p(vpref))
+        return vel, vpref

@@ -1,0 +1,285 @@
+"""ctypes binding of libpfnav.so (the C ABI in include/pfnav.h).  Host-side mirror of the
+reference's field/movement interfaces for tests and bench.py: same names, same argument meaning.
+
+There is no fallback: importing works without a GPU (symbol checks), but Nav() raises when the
+library cannot create a context on an sm_100 device."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+FD_NONE, FD_NW, FD_N, FD_NE, FD_W, FD_E, FD_SW, FD_S, FD_SE = range(9)
+TARGET_PORTAL, TARGET_TILE = 0, 1
+FACTION_ID_NONE = 0xF
+ISLAND_NONE = 0xFFFF
+
+FIELD_REQ = np.dtype([
+    ("chunk_r", "<i4"), ("chunk_c", "<i4"), ("layer", "<i4"), ("faction_id", "<i4"),
+    ("target_type", "<i4"), ("init", "<i4"), ("tile_r", "<i4"), ("tile_c", "<i4"),
+    ("port_r0", "<i2"), ("port_c0", "<i2"), ("port_r1", "<i2"), ("port_c1", "<i2"),
+    ("next_r0", "<i2"), ("next_c0", "<i2"), ("next_r1", "<i2"), ("next_c1", "<i2"),
+    ("next_chunk_r", "<i4"), ("next_chunk_c", "<i4"), ("port_iid", "<u2"), ("next_iid", "<u2"),
+    ("_pad", "<i4")])
+assert FIELD_REQ.itemsize == 64
+
+LOS_REQ = np.dtype([
+    ("chunk_r", "<i4"), ("chunk_c", "<i4"), ("layer", "<i4"), ("faction_id", "<i4"),
+    ("tgt_chunk_r", "<i4"), ("tgt_chunk_c", "<i4"), ("tgt_tile_r", "<i4"), ("tgt_tile_c", "<i4"),
+    ("prev_index", "<i4"), ("prev_chunk_r", "<i4"), ("prev_chunk_c", "<i4"), ("_pad", "<i4")])
+assert LOS_REQ.itemsize == 48
+
+AGENT = np.dtype([
+    ("pos", "<f4", 2), ("prev_pos", "<f4", 2), ("velocity", "<f4", 2), ("vdes", "<f4", 2),
+    ("radius", "<f4"), ("max_speed", "<f4"), ("speed", "<f4"), ("state", "<u4"), ("flags", "<u4"),
+    ("flock", "<i4"), ("has_dest_los", "<u4"), ("_pad", "<u4")])
+assert AGENT.itemsize == 64
+
+FLOCK = np.dtype([("target", "<f4", 2), ("dest", "<i4"), ("layer", "<i4")])
+assert FLOCK.itemsize == 16
+
+TICK_VDES_FROM_POOL = 1
+FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 1 << 14, 1 << 15, 1 << 18, 1 << 21
+
+# every symbol include/pfnav.h declares
+SYMBOLS = [
+    "pfnav_last_error", "pfnav_version", "pfnav_create", "pfnav_destroy", "pfnav_map_create",
+    "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_flow_fields_update",
+    "pfnav_flow_fields_update_dev", "pfnav_los_fields_create", "pfnav_los_fields_create_dev",
+    "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear",
+    "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
+    "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
+    "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen libpfnav.so (building it first if the sources are newer). Raises if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    L.pfnav_last_error.restype = C.c_char_p
+    L.pfnav_launch_count.restype = C.c_uint64
+    L.pfnav_launch_count.argtypes = [C.c_void_p]
+    L.pfnav_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.pfnav_destroy.argtypes = [C.c_void_p]
+    L.pfnav_map_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.pfnav_map_upload_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pfnav_flow_fields_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pfnav_flow_fields_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.pfnav_flow_fields_update_general_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.pfnav_los_fields_create.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pfnav_los_fields_create_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfnav_set_tma.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_pool_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pfnav_pool_put.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.pfnav_pool_clear.argtypes = [C.c_void_p]
+    L.pfnav_agents_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    L.pfnav_agents_set_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_tick.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.pfnav_agents_read_velocities.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_read_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_ents_in_circle.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.pfnav_agents_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.pfnav_agents_rebuild_index.argtypes = [C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+class PfnavError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _chk(rc):
+    if rc != 0:
+        raise PfnavError("pfnav error %d: %s" % (rc, load().pfnav_last_error().decode()))
+
+
+def tile_req(chunk, tile, layer=0, init=1):
+    q = np.zeros(1, FIELD_REQ)
+    q["chunk_r"], q["chunk_c"] = chunk
+    q["layer"] = layer; q["faction_id"] = FACTION_ID_NONE
+    q["target_type"] = TARGET_TILE; q["init"] = init
+    q["tile_r"], q["tile_c"] = tile
+    return q
+
+
+def portal_req(chunk, port_ep, next_chunk, next_ep, port_iid, next_iid, layer=0, init=1):
+    q = np.zeros(1, FIELD_REQ)
+    q["chunk_r"], q["chunk_c"] = chunk
+    q["layer"] = layer; q["faction_id"] = FACTION_ID_NONE
+    q["target_type"] = TARGET_PORTAL; q["init"] = init
+    q["port_r0"], q["port_c0"], q["port_r1"], q["port_c1"] = port_ep
+    q["next_r0"], q["next_c0"], q["next_r1"], q["next_c1"] = next_ep
+    q["next_chunk_r"], q["next_chunk_c"] = next_chunk
+    q["port_iid"] = port_iid; q["next_iid"] = next_iid
+    return q
+
+
+def los_req(chunk, target_td, layer=0, prev_index=-1, prev_chunk=(0, 0)):
+    q = np.zeros(1, LOS_REQ)
+    q["chunk_r"], q["chunk_c"] = chunk
+    q["layer"] = layer; q["faction_id"] = FACTION_ID_NONE
+    q["tgt_chunk_r"], q["tgt_chunk_c"], q["tgt_tile_r"], q["tgt_tile_c"] = target_td
+    q["prev_index"] = prev_index
+    q["prev_chunk_r"], q["prev_chunk_c"] = prev_chunk
+    return q
+
+
+class Nav:
+    """One device navigation context (what `struct nav_private` is to the reference)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        _chk(self.L.pfnav_create(device, C.byref(h)))
+        self.h = h
+        self.nwork = 0
+
+    def close(self):
+        if self.h:
+            self.L.pfnav_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map ----
+    def map_create(self, chunk_w, chunk_h, nlayers=1, map_x=0.0, map_z=0.0):
+        self.cw, self.ch = chunk_w, chunk_h
+        _chk(self.L.pfnav_map_create(self.h, chunk_w, chunk_h, nlayers, map_x, map_z))
+
+    def map_upload_layer(self, layer, cost_base, blockers=None, local_islands=None):
+        cost_base = np.ascontiguousarray(cost_base, np.uint8)
+        blockers = None if blockers is None else np.ascontiguousarray(blockers, np.uint16)
+        local_islands = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
+        _chk(self.L.pfnav_map_upload_layer(self.h, layer, _p(cost_base), _p(blockers), _p(local_islands)))
+
+    def map_update_chunk(self, layer, chunk, cost_base=None, blockers=None, local_islands=None):
+        a = None if cost_base is None else np.ascontiguousarray(cost_base, np.uint8)
+        b = None if blockers is None else np.ascontiguousarray(blockers, np.uint16)
+        c = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
+        _chk(self.L.pfnav_map_update_chunk(self.h, layer, chunk[0], chunk[1], _p(a), _p(b), _p(c)))
+
+    def set_tma(self, enable):
+        _chk(self.L.pfnav_set_tma(self.h, int(enable)))
+
+    # ---- fields ----
+    def flow_fields_update(self, reqs, inout=None):
+        reqs = np.ascontiguousarray(reqs, FIELD_REQ)
+        n = len(reqs)
+        buf = np.zeros((n, 64, 64), np.uint8) if inout is None else np.ascontiguousarray(inout, np.uint8).reshape(n, 64, 64).copy()
+        _chk(self.L.pfnav_flow_fields_update(self.h, _p(reqs), n, _p(buf)))
+        return buf
+
+    def flow_fields_update_dev(self, d_reqs_ptr, n, d_fields_ptr, stream=0, general=False):
+        f = self.L.pfnav_flow_fields_update_general_dev if general else self.L.pfnav_flow_fields_update_dev
+        _chk(f(self.h, C.c_void_p(d_reqs_ptr), n, C.c_void_p(d_fields_ptr), C.c_void_p(stream)))
+
+    def los_fields_create(self, reqs):
+        reqs = np.ascontiguousarray(reqs, LOS_REQ)
+        n = len(reqs)
+        out = np.zeros((n, 64, 64), np.uint8)
+        _chk(self.L.pfnav_los_fields_create(self.h, _p(reqs), n, _p(out)))
+        return out
+
+    def los_fields_create_dev(self, d_reqs_ptr, n, d_fields_ptr, wave_offsets, stream=0):
+        wo = np.ascontiguousarray(wave_offsets, np.int32)
+        _chk(self.L.pfnav_los_fields_create_dev(self.h, C.c_void_p(d_reqs_ptr), n, C.c_void_p(d_fields_ptr),
+                                                len(wo) - 1, _p(wo), C.c_void_p(stream)))
+
+    # ---- field pool ----
+    def pool_create(self, ndests, max_fields):
+        _chk(self.L.pfnav_pool_create(self.h, ndests, max_fields))
+
+    def pool_put(self, dest, chunk, flow=None, los=None):
+        f = None if flow is None else np.ascontiguousarray(flow, np.uint8)
+        l = None if los is None else np.ascontiguousarray(los, np.uint8)
+        _chk(self.L.pfnav_pool_put(self.h, dest, chunk[0], chunk[1], _p(f), _p(l)))
+
+    def pool_clear(self):
+        _chk(self.L.pfnav_pool_clear(self.h))
+
+    # ---- agents ----
+    def agents_upload(self, agents, flocks, hz=20):
+        agents = np.ascontiguousarray(agents, AGENT)
+        flocks = np.ascontiguousarray(flocks, FLOCK)
+        self.nagents = len(agents)
+        _chk(self.L.pfnav_agents_upload(self.h, _p(agents), len(agents), _p(flocks), len(flocks), hz))
+
+    def agents_set_work(self, uids=None):
+        if uids is None:
+            _chk(self.L.pfnav_agents_set_work(self.h, None, 0))
+            self.nwork = -1
+        else:
+            uids = np.ascontiguousarray(uids, np.uint32)
+            self.nwork = len(uids)
+            _chk(self.L.pfnav_agents_set_work(self.h, _p(uids), len(uids)))
+
+    def agents_tick(self, flags=0, stream=0):
+        _chk(self.L.pfnav_agents_tick(self.h, flags, C.c_void_p(stream)))
+
+    def agents_read_velocities(self, nwork):
+        out = np.zeros((nwork, 2), np.float32)
+        _chk(self.L.pfnav_agents_read_velocities(self.h, _p(out), nwork))
+        return out
+
+    def agents_read_debug(self, nwork):
+        vpref = np.zeros((nwork, 2), np.float32)
+        vdes = np.zeros((nwork, 2), np.float32)
+        los = np.zeros(nwork, np.uint8)
+        _chk(self.L.pfnav_agents_read_debug(self.h, _p(vpref), _p(vdes), _p(los), nwork))
+        return vpref, vdes, los
+
+    def ents_in_circle(self, x, z, r, maxout=512):
+        out = np.zeros(maxout, np.uint32)
+        n = C.c_int(0)
+        _chk(self.L.pfnav_ents_in_circle(self.h, x, z, r, _p(out), maxout, C.byref(n)))
+        return out[:n.value].copy()
+
+    def agents_device_ptrs(self):
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _chk(self.L.pfnav_agents_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def agents_rebuild_index(self, stream=0):
+        _chk(self.L.pfnav_agents_rebuild_index(self.h, C.c_void_p(stream)))
+
+    def launch_count(self):
+        return int(self.L.pfnav_launch_count(self.h))
+
+
+def pack_agents(a):
+    """synth.make_agents() dict -> AGENT / FLOCK record arrays"""
+    n = len(a["radius"])
+    rec = np.zeros(n, AGENT)
+    rec["pos"] = a["pos"]; rec["prev_pos"] = a["prev_pos"]; rec["velocity"] = a["vel"]
+    rec["radius"] = a["radius"]; rec["max_speed"] = a["max_speed"]; rec["speed"] = a["speed"]
+    rec["state"] = a["state"]; rec["flags"] = a["flags"]; rec["flock"] = a["flock_of"]
+    if "vdes" in a:
+        rec["vdes"] = a["vdes"]
+    if "has_los" in a:
+        rec["has_dest_los"] = a["has_los"]
+    fl = np.zeros(len(a["flock_target"]), FLOCK)
+    fl["target"] = a["flock_target"]
+    fl["dest"] = np.arange(len(fl)) if "flock_dest_index" not in a else a["flock_dest_index"]
+    fl["layer"] = 0
+    return rec, fl

@@ -1,0 +1,1131 @@
+// pfnav_agents.cu -- device field pool, device spatial index, and the per-agent velocity update.
+//
+// Replaces (reference file:line):
+//   compute_los_state / compute_desired_velocity         src/game/movement.c:4129-4180
+//     N_DesiredPointSeekVelocity, n_interpolated_flow_dir  src/navigation/nav.c:3468, 3407
+//     N_HasDestLOS                                          src/navigation/nav.c:4026
+//     M_Tile_DescForPoint2D / M_Tile_Bounds / RelativeDesc  src/map/tile.c:547, 356, 391
+//   move_velocity_work                                    src/game/movement.c:3395-3466
+//     point_seek_vpref :1870, point_seek_total_force :1745, arrive_force_point :1546,
+//     cohesion_force :1653, separation_force :1690, nullify_impass_components :1831,
+//     vec2_truncate :643, find_neighbours :2768
+//   G_ClearPath_NewVelocity                               src/game/clearpath.c:694 (all of :123-418, 552-715)
+//     C_InfiniteLineIntersection / C_RayRayIntersection2D   src/phys/collision.c:820, 854
+//   G_Pos_EntsInCircleFrom -> bg_ent_inrange_circle       src/game/position.c:379, src/lib/public/bitmap_grid.h:1376
+//
+// Arithmetic mirrors the reference expression by expression (float storage, the same places
+// promoted to double, IEEE sqrt/div, no FMA contraction: the TU is built with -fmad=false), so
+// that every epsilon-threshold branch of ClearPath takes the same side as on the CPU.
+//
+// Kernels:
+//   K5  k_cell_count / k_cell_scan / k_cell_scatter / k_cell_sort : counting sort of agents into
+//       16-wu cells, in-cell order = descending uid (what insert-all + bg_cleanup leaves behind).
+//   K6a k_desired_velocity : one thread per work item, bilinear flow blend + LOS bit from the pool.
+//   K6b k_cohesion         : one thread per work item, O(|flock|) weighted centre of mass.
+//   K6c k_agent_velocity   : ONE WARP PER AGENT. Lanes scan the hash cells, evaluate separation
+//       terms, and split ClearPath's O(R^2) ray pairs / O(R) inside-PCR tests among themselves.
+#include "pfnav_internal.cuh"
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+
+#define EPS_F (1.0f / 1024)
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// vec2 helpers (pf_math.c:58-94) -- float storage, sqrt evaluated in double then rounded, which
+// is the correctly rounded float sqrt.
+// ------------------------------------------------------------------------------------------
+struct v2 { float x, z; };
+__device__ __forceinline__ v2 v2_add(v2 a, v2 b) { return {a.x + b.x, a.z + b.z}; }
+__device__ __forceinline__ v2 v2_sub(v2 a, v2 b) { return {a.x - b.x, a.z - b.z}; }
+__device__ __forceinline__ v2 v2_scale(v2 a, float s) { return {a.x * s, a.z * s}; }
+__device__ __forceinline__ float v2_dot(v2 a, v2 b) { return a.x * b.x + a.z * b.z; }
+__device__ __forceinline__ float v2_len(v2 a) { return sqrtf(a.x * a.x + a.z * a.z); }
+__device__ __forceinline__ v2 v2_normal(v2 a) { float l = v2_len(a); return {a.x / l, a.z / l}; }
+// vec2_truncate (movement.c:643)
+__device__ __forceinline__ v2 v2_truncate(v2 a, float max_len)
+{
+    if (v2_len(a) > max_len) { a = v2_normal(a); a = v2_scale(a, max_len); }
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// Map / pool views
+// ------------------------------------------------------------------------------------------
+struct MapView {
+    const uint8_t *cost; const uint16_t *blk;   // [layer][H64][W64]
+    int W64, H64, chunk_w, chunk_h;
+    float map_x, map_z;
+};
+struct PoolView {
+    const int32_t *slot;     // [ndests][chunks]
+    const uint8_t *flow;     // [max][4096]
+    const uint8_t *los;      // [max][4096] ; first byte of a never-written LOS slot region is valid 0s
+    const uint8_t *has;      // [max] bit0 flow present, bit1 LOS present
+    int ndests;
+};
+struct GridView {
+    const uint32_t *cell_start, *cell_count;
+    const int32_t *ix, *iy; const uint32_t *id;
+    int grid_w, grid_h; int32_t origin_x, origin_y;
+};
+
+struct tile_desc { int chunk_r, chunk_c, tile_r, tile_c; };
+
+// M_Tile_DescForPoint2D with the nav resolution (tile.c:547; n_res nav.c:240): returns false
+// outside the map box.
+__device__ __forceinline__ bool desc_for_point(const MapView &m, float px, float pz, tile_desc &out)
+{
+    const float width = (float)(m.chunk_w * 256), height = (float)(m.chunk_h * 256);
+    if (px > m.map_x || px < m.map_x - width) return false;
+    if (pz < m.map_z || pz > m.map_z + height) return false;
+    int chunk_r = (int)(fabs((double)(m.map_z - pz)) / 256.0);
+    int chunk_c = (int)(fabs((double)(m.map_x - px)) / 256.0);
+    chunk_r = min(max(chunk_r, 0), m.chunk_h - 1);
+    chunk_c = min(max(chunk_c, 0), m.chunk_w - 1);
+    const float base_x = m.map_x - (float)chunk_c * 256.0f;
+    const float base_z = m.map_z + (float)chunk_r * 256.0f;
+    int tile_r = (int)(fabs((double)(base_z - pz)) / 4);
+    int tile_c = (int)(fabs((double)(base_x - px)) / 4);
+    out.chunk_r = chunk_r; out.chunk_c = chunk_c;
+    out.tile_r = min(max(tile_r, 0), 63);
+    out.tile_c = min(max(tile_c, 0), 63);
+    return true;
+}
+
+// M_NavPositionPathable / M_NavPositionBlocked (map.c:817, 831): both false outside the map box.
+__device__ __forceinline__ void probe_tile(const MapView &m, int layer, float px, float pz, bool &pathable,
+                                           bool &blocked)
+{
+    tile_desc td;
+    pathable = false; blocked = false;
+    if (!desc_for_point(m, px, pz, td)) return;
+    const size_t off = ((size_t)layer * m.H64 + td.chunk_r * 64 + td.tile_r) * m.W64 + td.chunk_c * 64 + td.tile_c;
+    pathable = m.cost[off] != 0xFF;
+    blocked = m.blk[off] > 0;
+}
+
+// Entity_NavLayerWithRadius (entity.c:554)
+__device__ __forceinline__ int nav_layer_for(uint32_t flags, float radius)
+{
+    const bool water = flags & PFNAV_FLAG_WATER, air = flags & PFNAV_FLAG_AIR;
+    const int base = water ? 4 : air ? 8 : 0;
+    if (radius >= 15.0f) return base + 3;
+    if (radius >= 10.0f) return base + 2;
+    if (radius >= 5.0f) return base + 1;
+    return base;
+}
+
+// N_FlowDir (field.c:2429): 1.0f / sqrt(2.0f) is a double division rounded to float
+__device__ __forceinline__ v2 flow_dir_vec(int dir)
+{
+    const float d = (float)(1.0 / 1.4142135623730951);
+    switch (dir) {
+    case 1: return {d, -d};
+    case 2: return {0.0f, -1.0f};
+    case 3: return {-d, -d};
+    case 4: return {1.0f, 0.0f};
+    case 5: return {-1.0f, 0.0f};
+    case 6: return {d, d};
+    case 7: return {0.0f, 1.0f};
+    case 8: return {-d, d};
+    default: return {0.0f, 0.0f};
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6a: desired velocity + LOS from the device field pool
+// ------------------------------------------------------------------------------------------
+__global__ void k_desired_velocity(MapView m, PoolView pool, const pfnav_agent *__restrict__ agents,
+                                   const pfnav_flock *__restrict__ flocks, const uint32_t *__restrict__ work,
+                                   int nwork, float2 *__restrict__ vdes_out, uint8_t *__restrict__ los_out,
+                                   uint32_t *__restrict__ miss_count)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    const pfnav_agent a = agents[work[w]];
+    v2 vdes = {0.0f, 0.0f};
+    uint8_t los = 0;
+    const int dest = (a.flock >= 0) ? flocks[a.flock].dest : -1;
+    if (dest >= 0 && dest < pool.ndests) {
+        const int chunks = m.chunk_w * m.chunk_h;
+        const int32_t *slots = pool.slot + (size_t)dest * chunks;
+        tile_desc t;
+        // ---- N_HasDestLOS sampled at prev_pos (movement.c:4137) ----
+        if (desc_for_point(m, a.prev_pos[0], a.prev_pos[1], t)) {
+            const int s = slots[t.chunk_r * m.chunk_w + t.chunk_c];
+            if (s >= 0 && (pool.has[s] & 2)) los = pool.los[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 1;
+        }
+        // ---- N_DesiredPointSeekVelocity at pos ----
+        if (desc_for_point(m, a.pos[0], a.pos[1], t)) {
+            const int s = slots[t.chunk_r * m.chunk_w + t.chunk_c];
+            if (s < 0 || !(pool.has[s] & 1)) {
+                atomicAdd(miss_count, 1u);      // the host planner must request this (dest, chunk)
+            } else {
+                const uint8_t *base_ff = pool.flow + (size_t)s * 4096;
+                const int base_dir = base_ff[t.tile_r * 64 + t.tile_c] & 0xF;
+                // n_interpolated_flow_dir (nav.c:3407)
+                const float bx = (m.map_x - (float)(t.chunk_c * 256)) - (float)(t.tile_c * 4);
+                const float bz = (m.map_z + (float)(t.chunk_r * 256)) + (float)(t.tile_r * 4);
+                const float cx = bx - 4.0f / 2.0f, cz = bz + 4.0f / 2.0f;
+                const float dx = a.pos[0] - cx, dz = a.pos[1] - cz;
+                const int dc = (dx < 0.0f) ? 1 : -1;
+                const int dr = (dz > 0.0f) ? 1 : -1;
+                const float wc = (float)fmin(fabs((double)dx) / 4.0, 1.0);
+                const float wr = (float)fmin(fabs((double)dz) / 4.0, 1.0);
+                const int sdc[4] = {0, dc, 0, dc}, sdr[4] = {0, 0, dr, dr};
+                const float sw[4] = {(1.0f - wc) * (1.0f - wr), wc * (1.0f - wr), (1.0f - wc) * wr, wc * wr};
+                v2 acc = {0.0f, 0.0f};
+                float wsum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (sw[i] <= 0.0f) continue;
+                    const int abs_r = t.chunk_r * 64 + t.tile_r + sdr[i], abs_c = t.chunk_c * 64 + t.tile_c + sdc[i];
+                    if (abs_r < 0 || abs_r >= m.H64 || abs_c < 0 || abs_c >= m.W64) continue;
+                    const int cr2 = abs_r >> 6, cc2 = abs_c >> 6;
+                    const uint8_t *ff = base_ff;
+                    if (cr2 != t.chunk_r || cc2 != t.chunk_c) {
+                        const int s2 = slots[cr2 * m.chunk_w + cc2];
+                        if (s2 < 0 || !(pool.has[s2] & 1)) continue;
+                        ff = pool.flow + (size_t)s2 * 4096;
+                    }
+                    const int dir = ff[(abs_r & 63) * 64 + (abs_c & 63)] & 0xF;
+                    if (dir == 0) continue;
+                    const v2 fd = flow_dir_vec(dir);
+                    acc = v2_add(acc, v2_scale(fd, sw[i]));
+                    wsum += sw[i];
+                }
+                if (wsum < 1e-6f || v2_len(acc) < 1e-6f) vdes = flow_dir_vec(base_dir);
+                else vdes = v2_normal(acc);
+            }
+        }
+    }
+    vdes_out[w] = make_float2(vdes.x, vdes.z);
+    los_out[w] = los;
+}
+
+// ------------------------------------------------------------------------------------------
+// K6b: cohesion_force (movement.c:1653). One thread per work item; members in ascending uid.
+// ------------------------------------------------------------------------------------------
+__global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent *__restrict__ agents,
+                           const uint32_t *__restrict__ flock_start, const uint32_t *__restrict__ flock_members,
+                           const uint32_t *__restrict__ work, int nwork, float scaled_max_force,
+                           float2 *__restrict__ out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    const uint32_t uid = work[w];
+    const int fl = agents[uid].flock;
+    v2 ret = {0.0f, 0.0f};
+    if (fl >= 0) {
+        const pf_record self = rec[uid];
+        const uint32_t b = flock_start[fl], e = flock_start[fl + 1];
+        v2 com = {0.0f, 0.0f};
+        uint32_t cnt = 0;
+        for (uint32_t k = b; k < e; k++) {
+            const uint32_t cu = flock_members[k];
+            if (cu == uid) continue;
+            const float2 p = *reinterpret_cast<const float2 *>(&rec[cu]);
+            const v2 diff = {p.x - self.px, p.y - self.pz};
+            // (len - 50*0.75) / 50 is evaluated in double by the reference and rounded once; the
+            // float form differs by <= 1 ulp of t, far inside the 1e-4 budget (cohesion's summation
+            // order is not reproducible anyway: it follows khash bucket order, movement.c:1660)
+            const float t = (v2_len(diff) - 37.5f) / 50.0f;
+            const float scale = expf(-6.0f * t);
+            com.x += p.x * scale;
+            com.z += p.y * scale;
+            cnt++;
+        }
+        if (cnt > 0) {
+            com = v2_scale(com, 1.0f / (float)cnt);
+            ret = v2_sub(com, v2{self.px, self.pz});
+            ret = v2_truncate(ret, scaled_max_force);
+        }
+    }
+    out[w] = make_float2(ret.x, ret.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: spatial index build (bitmap_grid.h: 16-wu cells, scaled int32 coordinates)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t bg_scale(float x) { return __float2int_rn(x * 256.0f); }   // BG_SCALE_F
+__device__ __forceinline__ int cell_of(int32_t i, int32_t origin, int n)
+{
+    int c = (i - origin) >> 12;
+    return min(max(c, 0), n - 1);
+}
+
+__global__ void k_make_records(const pfnav_agent *__restrict__ agents, pf_record *__restrict__ rec, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const pfnav_agent a = agents[i];
+    pf_record r;
+    r.px = a.pos[0]; r.pz = a.pos[1]; r.vx = a.velocity[0]; r.vz = a.velocity[1];
+    r.radius = a.radius;
+    r.state_flags = (a.state << 24) | (a.flags & 0xFFFFFFu);
+    rec[i] = r;
+}
+
+__global__ void k_cell_count(const pf_record *__restrict__ rec, int n, GridView g, uint32_t *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = cell_of(bg_scale(rec[i].px), g.origin_x, g.grid_w);
+    const int cy = cell_of(bg_scale(rec[i].pz), g.origin_y, g.grid_h);
+    atomicAdd(&count[cy * g.grid_w + cx], 1u);
+}
+
+// single-CTA exclusive scan (cells <= 1M)
+__global__ void k_cell_scan(const uint32_t *__restrict__ count, uint32_t *__restrict__ start, int ncells)
+{
+    __shared__ uint32_t part[1024];
+    const int tid = threadIdx.x, per = (ncells + 1023) / 1024;
+    const int b = tid * per, e = min(b + per, ncells);
+    uint32_t s = 0;
+    for (int i = b; i < e; i++) s += count[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = tid >= off ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = tid ? part[tid - 1] : 0;
+    for (int i = b; i < e; i++) { start[i] = run; run += count[i]; }
+    if (tid == 1023) start[ncells] = part[1023];
+}
+
+__global__ void k_cell_scatter(const pf_record *__restrict__ rec, int n, GridView g,
+                               const uint32_t *__restrict__ start, uint32_t *__restrict__ fill,
+                               uint32_t *__restrict__ sid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = cell_of(bg_scale(rec[i].px), g.origin_x, g.grid_w);
+    const int cy = cell_of(bg_scale(rec[i].pz), g.origin_y, g.grid_h);
+    const int c = cy * g.grid_w + cx;
+    const uint32_t slot = start[c] + atomicAdd(&fill[c], 1u);
+    sid[slot] = (uint32_t)i;
+}
+
+// per-cell: order ids DESCENDING (LIFO overflow chain drained by bg_cleanup, bitmap_grid.h:1110,
+// 1477), then materialise the scaled coordinates next to them.
+__global__ void k_cell_sort(const pf_record *__restrict__ rec, GridView g, const uint32_t *__restrict__ start,
+                            uint32_t *__restrict__ sid, int32_t *__restrict__ six, int32_t *__restrict__ siy,
+                            int ncells)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t b = start[c], e = start[c + 1];
+    for (uint32_t i = b + 1; i < e; i++) {      // insertion sort, descending
+        const uint32_t v = sid[i];
+        uint32_t j = i;
+        while (j > b && sid[j - 1] < v) { sid[j] = sid[j - 1]; j--; }
+        sid[j] = v;
+    }
+    for (uint32_t i = b; i < e; i++) {
+        const pf_record r = rec[sid[i]];
+        six[i] = bg_scale(r.px);
+        siy[i] = bg_scale(r.pz);
+    }
+}
+
+// bg_ent_inrange_circle (bitmap_grid.h:1376): visit hits in the reference's order and hand them,
+// 32 candidates at a time, to `emit(hit, id)` (called convergently by all lanes; returns a
+// warp-uniform "stop").
+template <class F>
+__device__ __forceinline__ void grid_query(const GridView &g, float x, float z, float range, uint32_t lane,
+                                           F &&emit)
+{
+    const int32_t icx = bg_scale(x), icy = bg_scale(z), ir = bg_scale(range);
+    const long long ir2 = (long long)ir * ir;
+    const int32_t imnx = icx - ir, imxx = icx + ir, imny = icy - ir, imxy = icy + ir;
+    // _bg_cell_extent (bitmap_grid.h:1236)
+    if (imxx < g.origin_x || imxy < g.origin_y) return;
+    if (imnx >= g.origin_x + (g.grid_w << 12) || imny >= g.origin_y + (g.grid_h << 12)) return;
+    const int cx_lo = max((imnx - g.origin_x) >> 12, 0), cx_hi = min((imxx - g.origin_x) >> 12, g.grid_w - 1);
+    const int cy_lo = max((imny - g.origin_y) >> 12, 0), cy_hi = min((imxy - g.origin_y) >> 12, g.grid_h - 1);
+    // wide-query fast path: whole pool in pool order == cells in row-major order
+    const bool wide = (long long)(cx_hi - cx_lo + 1) * (cy_hi - cy_lo + 1) * 4 >= (long long)g.grid_w * g.grid_h * 3;
+    const int ax_lo = wide ? 0 : cx_lo, ax_hi = wide ? g.grid_w - 1 : cx_hi;
+    const int ay_lo = wide ? 0 : cy_lo, ay_hi = wide ? g.grid_h - 1 : cy_hi;
+    const int cstep = wide ? (1 << 30) : 8;                    // one "coarse block" spans everything when wide
+    const int cyc_lo = wide ? 0 : ay_lo >> 3, cyc_hi = wide ? 0 : ay_hi >> 3;
+    const int cxc_lo = wide ? 0 : ax_lo >> 3, cxc_hi = wide ? 0 : ax_hi >> 3;
+    for (int cyc = cyc_lo; cyc <= cyc_hi; cyc++) {
+        for (int cxc = cxc_lo; cxc <= cxc_hi; cxc++) {
+            const int fy0 = wide ? ay_lo : max(cyc * cstep, ay_lo), fy1 = wide ? ay_hi + 1 : min(cyc * cstep + cstep, ay_hi + 1);
+            const int fx0 = wide ? ax_lo : max(cxc * cstep, ax_lo), fx1 = wide ? ax_hi + 1 : min(cxc * cstep + cstep, ax_hi + 1);
+            for (int fy = fy0; fy < fy1; fy++) {
+                for (int fx = fx0; fx < fx1; fx++) {
+                    const int c = fy * g.grid_w + fx;
+                    const uint32_t b = g.cell_start[c], cnt = g.cell_count[c];
+                    for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        bool hit = false;
+                        uint32_t id = 0;
+                        if (k < cnt) {
+                            const long long dx = (long long)g.ix[b + k] - icx, dy = (long long)g.iy[b + k] - icy;
+                            hit = dx * dx + dy * dy <= ir2;
+                            id = g.id[b + k];
+                        }
+                        if (emit(hit, id)) return;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_ents_in_circle(GridView g, float x, float z, float range, uint32_t *out, int maxout, int *out_n)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    int written = 0;
+    grid_query(g, x, z, range, lane, [&](bool hit, uint32_t id) -> bool {
+        const uint32_t m = __ballot_sync(FULL, hit);
+        const int rank = __popc(m & ((1u << lane) - 1));
+        if (hit && written + rank < maxout) out[written + rank] = id;
+        written += __popc(m);
+        return written >= maxout;
+    });
+    if (lane == 0) *out_n = min(written, maxout);
+}
+
+// ------------------------------------------------------------------------------------------
+// ClearPath pieces
+// ------------------------------------------------------------------------------------------
+struct ray { v2 point, dir; };
+struct cp_ent { v2 pos, vel; float radius; };
+
+// C_InfiniteLineIntersection (collision.c:820) incl. the preserved "l2 vertical" y bug (:839-840)
+__device__ __forceinline__ bool line_isect(const ray l1, const ray l2, v2 &out)
+{
+    const float s1 = fabsf(l1.dir.x) < EPS_F ? __int_as_float(0x7fc00000) : (l1.dir.z / l1.dir.x);
+    const float s2 = fabsf(l2.dir.x) < EPS_F ? __int_as_float(0x7fc00000) : (l2.dir.z / l2.dir.x);
+    const bool n1 = isnan(s1), n2 = isnan(s2);
+    if (n1 && n2) return false;
+    if (fabsf(s1 - s2) < EPS_F) return false;
+    if (n1 && !n2) {
+        out.x = l1.point.x;
+        out.z = (l1.point.x - l2.point.x) * s2 + l2.point.z;
+    } else if (!n1 && n2) {
+        out.x = l2.point.x;
+        out.z = (l2.point.x - l1.point.x) * s1 + l2.point.z;
+    } else {
+        out.x = (s1 * l1.point.x - s2 * l2.point.x + l2.point.z - l1.point.z) / (s1 - s2);
+        out.z = s2 * (out.x - l2.point.x) + l2.point.z;
+    }
+    return true;
+}
+
+// C_RayRayIntersection2D (collision.c:854)
+__device__ __forceinline__ bool ray_isect(const ray l1, const ray l2, v2 &out)
+{
+    v2 p;
+    if (!line_isect(l1, l2, p)) return false;
+    if ((p.x - l1.point.x) / l1.dir.x < 0.0f) return false;
+    if ((p.z - l1.point.z) / l1.dir.z < 0.0f) return false;
+    if ((p.x - l2.point.x) / l2.dir.x < 0.0f) return false;
+    if ((p.z - l2.point.z) / l2.dir.z < 0.0f) return false;
+    out = p;
+    return true;
+}
+
+// inside_pcr (clearpath.c:249)
+__device__ __forceinline__ bool inside_pcr(const ray *rays, int n_rays, v2 test)
+{
+    for (int i = 0; i < n_rays; i += 2) {
+        const ray L = rays[i];
+        v2 ptt = v2_sub(test, L.point);
+        if (v2_len(ptt) < EPS_F) continue;
+        ptt = v2_normal(ptt);
+        const float left_det = (ptt.z * L.dir.x) - (ptt.x * L.dir.z);
+        if (left_det < EPS_F) continue;
+        const ray R = rays[i + 1];
+        ptt = v2_sub(test, R.point);
+        if (v2_len(ptt) < EPS_F) continue;
+        ptt = v2_normal(ptt);
+        const float right_det = (ptt.z * R.dir.x) - (ptt.x * R.dir.z);
+        if (right_det > -EPS_F) continue;
+        return true;
+    }
+    return false;
+}
+
+// compute_vo_edges (clearpath.c:130)
+__device__ __forceinline__ void vo_edges(const cp_ent ent, const cp_ent nb, v2 &right, v2 &left)
+{
+    v2 e2n = v2_normal(v2_sub(nb.pos, ent.pos));
+    v2 r = {-e2n.z, e2n.x};
+    r = v2_scale(r, nb.radius + ent.radius + 0.0f);
+    const v2 rt = v2_add(nb.pos, r), lt = v2_sub(nb.pos, r);
+    right = v2_normal(v2_sub(rt, ent.pos));
+    left = v2_normal(v2_sub(lt, ent.pos));
+}
+
+#define VEL_WARPS_PER_CTA 4
+struct VelSmem {
+    cp_ent dyn[PFNAV_MAX_NEIGHBOURS];
+    cp_ent stat[PFNAV_MAX_NEIGHBOURS];
+    ray rays[4 * PFNAV_MAX_NEIGHBOURS];
+    uint32_t near_id[128];
+    float2 term[128];
+};
+
+// clearpath_new_velocity (clearpath.c:552). Warp-cooperative; returns a warp-uniform status.
+__device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat,
+                                       uint32_t lane, v2 &out)
+{
+    // ---- compute_all_hrvos / compute_all_vos: one neighbour per lane, order-preserving compaction ----
+    int n_rays = 0;
+    {
+        bool keep = false;
+        ray L, R;
+        if ((int)lane < ndyn) {
+            const cp_ent nb = s.dyn[lane];
+            if (!(v2_len(v2_sub(nb.pos, ent.pos)) < EPS_F)) {        // same_position (clearpath.c:123)
+                keep = true;
+                v2 right, left;
+                vo_edges(ent, nb, right, left);
+                // compute_rvo / compute_hrvo (clearpath.c:161-214)
+                const v2 rvo_apex = v2_add(ent.pos, v2_scale(v2_add(ent.vel, nb.vel), 0.5f));
+                const v2 centerline = v2_add(left, right);
+                const v2 vo_apex = v2_add(ent.pos, nb.vel);
+                const float det = (centerline.x * ent.vel.z) - (centerline.z * ent.vel.x);
+                v2 apex = rvo_apex;
+                if (det > EPS_F) {
+                    v2 p;
+                    if (line_isect(ray{rvo_apex, left}, ray{vo_apex, right}, p)) apex = p;
+                } else if (det < -EPS_F) {
+                    v2 p;
+                    if (line_isect(ray{rvo_apex, right}, ray{vo_apex, left}, p)) apex = p;
+                }
+                L = ray{apex, left};
+                R = ray{apex, right};
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int k = __popc(m & ((1u << lane) - 1));
+            s.rays[2 * k] = L;
+            s.rays[2 * k + 1] = R;
+        }
+        n_rays = 2 * __popc(m);
+    }
+    {
+        bool keep = false;
+        ray L, R;
+        if ((int)lane < nstat) {
+            const cp_ent nb = s.stat[lane];
+            if (!(v2_len(v2_sub(nb.pos, ent.pos)) < EPS_F)) {
+                keep = true;
+                v2 right, left;
+                vo_edges(ent, nb, right, left);
+                const v2 apex = v2_add(ent.pos, nb.vel);              // compute_vo (clearpath.c:153)
+                L = ray{apex, left};
+                R = ray{apex, right};
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int k = __popc(m & ((1u << lane) - 1));
+            s.rays[n_rays + 2 * k] = L;
+            s.rays[n_rays + 2 * k + 1] = R;
+        }
+        n_rays += 2 * __popc(m);
+    }
+    __syncwarp();
+
+    const v2 des_v_ws = v2_add(ent.pos, des_v);
+    if (!inside_pcr(s.rays, n_rays, des_v_ws)) {          // every lane evaluates the same test
+        out = des_v;
+        return true;
+    }
+
+    // ---- compute_vo_xpoints + compute_vdes_proj_points + compute_vnew fused: the candidate list is
+    //      never materialised; we keep the first-minimum (distance, sequence index) per lane ----
+    float best = __int_as_float(0x7f800000);    // +inf ; `len < min_dist` with min_dist = INFINITY
+    int best_idx = 0x7fffffff;
+    v2 best_p = {0.0f, 0.0f};
+    int any = 0;
+    const int npairs = n_rays * n_rays;
+    for (int k = lane; k < npairs + n_rays; k += 32) {
+        v2 p;
+        bool ok;
+        if (k < npairs) {
+            const int i = k / n_rays, j = k - i * n_rays;
+            ok = (i != j) && ray_isect(s.rays[i], s.rays[j], p);
+        } else {
+            const ray r = s.rays[k - npairs];
+            const float len = v2_dot(r.dir, des_v);
+            p = v2_add(r.point, v2_scale(r.dir, len));
+            ok = true;
+        }
+        if (ok && !inside_pcr(s.rays, n_rays, p)) {
+            any = 1;
+            const v2 curr = v2_sub(p, ent.pos);
+            const float len = v2_len(v2_sub(des_v, curr));
+            if (len < best) { best = len; best_idx = k; best_p = curr; }   // k ascending per lane
+        }
+    }
+    any = __any_sync(FULL, any);
+    if (!any) return false;
+    // warp arg-min on (len, idx); lanes that never improved hold (+inf, INT_MAX)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, off);
+        const int oi = __shfl_xor_sync(FULL, best_idx, off);
+        const float ox = __shfl_xor_sync(FULL, best_p.x, off), oz = __shfl_xor_sync(FULL, best_p.z, off);
+        if (ob < best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; best_p = {ox, oz}; }
+    }
+    out = (best_idx == 0x7fffffff) ? v2{0.0f, 0.0f} : best_p;
+    return true;
+}
+
+// remove_furthest (clearpath.c:390): first strict maximum over dyn then stat; swap-with-last delete
+__device__ void remove_furthest(VelSmem &s, const v2 pos, int &ndyn, int &nstat, uint32_t lane)
+{
+    float d = -__int_as_float(0x7f800000);
+    int idx = 0x7fffffff;
+    const int n = ndyn + nstat;
+    // n <= 64: two candidates per lane, sequence index = position in (dyn ++ stat)
+    for (int k = lane; k < n; k += 32) {
+        const cp_ent e = k < ndyn ? s.dyn[k] : s.stat[k - ndyn];
+        const float len = v2_len(v2_sub(pos, e.pos));
+        if (len > d) { d = len; idx = k; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float od = __shfl_xor_sync(FULL, d, off);
+        const int oi = __shfl_xor_sync(FULL, idx, off);
+        if (od > d || (od == d && oi < idx)) { d = od; idx = oi; }
+    }
+    if (idx != 0x7fffffff) {
+        if (lane == 0) {
+            if (idx < ndyn) s.dyn[idx] = s.dyn[ndyn - 1];
+            else s.stat[idx - ndyn] = s.stat[nstat - 1];
+        }
+        if (idx < ndyn) ndyn--; else nstat--;
+    }
+    __syncwarp();
+}
+
+struct TickParams {
+    int hz;
+    float scaled_max_force;       // (float)SCALED_MAX_FORCE, as passed to vec2_truncate
+    double scaled_max_force_d;    // SCALED_MAX_FORCE as the double it is in comparisons (movement.c:1895)
+};
+
+// ------------------------------------------------------------------------------------------
+// K6c: one warp per agent
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32)
+k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__restrict__ agents,
+                 const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
+                 const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
+                 const uint8_t *__restrict__ los_in, const float2 *__restrict__ cohesion_in,
+                 float2 *__restrict__ vel_out, float2 *__restrict__ vpref_out)
+{
+    __shared__ VelSmem smem[VEL_WARPS_PER_CTA];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    VelSmem &s = smem[warp];
+    const int total_warps = gridDim.x * VEL_WARPS_PER_CTA;
+    for (int w = blockIdx.x * VEL_WARPS_PER_CTA + warp; w < nwork; w += total_warps) {
+        const uint32_t uid = work[w];
+        const pfnav_agent a = agents[uid];
+        const uint32_t ent_flags = a.flags & 0xFFFFFFu;
+        // COMBAT_HELD (movement.c:3405)
+        if (ent_flags & PFNAV_FLAG_COMBAT_HELD) {
+            if (lane == 0) { vel_out[w] = make_float2(0.f, 0.f); vpref_out[w] = make_float2(0.f, 0.f); }
+            continue;
+        }
+        const v2 pos = {a.pos[0], a.pos[1]};
+        const v2 velocity = {a.velocity[0], a.velocity[1]};
+        const float2 vd = vdes_in[w];
+        const v2 vdes = {vd.x, vd.y};
+        const bool has_los = los_in[w] != 0;
+        const float hzf = (float)tp.hz;
+
+        v2 vpref = {0.0f, 0.0f};
+        if (a.state == PFNAV_STATE_TURNING) {
+            vpref = {0.0f, 0.0f};
+        } else {
+            // ================= point_seek_vpref (movement.c:1870) =================
+            // ---- separation_force (movement.c:1690): 30-wu query, first 128 hits in index order ----
+            int num_near = 0;
+            grid_query(g, pos.x, pos.z, 30.0f, lane, [&](bool hit, uint32_t id) -> bool {
+                const uint32_t mk = __ballot_sync(FULL, hit);
+                const int rank = __popc(mk & ((1u << lane) - 1));
+                if (hit && num_near + rank < 128) s.near_id[num_near + rank] = id;
+                num_near += __popc(mk);
+                return num_near >= 128;
+            });
+            num_near = min(num_near, 128);
+            __syncwarp();
+            for (int k = lane; k < num_near; k += 32) {
+                const uint32_t cu = s.near_id[k];
+                float2 term = make_float2(0.f, 0.f);
+                if (cu != uid) {
+                    const pf_record r = rec[cu];
+                    const uint32_t fl = r.state_flags & 0xFFFFFFu;
+                    if ((fl & PFNAV_FLAG_MOVABLE) && ((ent_flags & PFNAV_FLAG_AIR) == (fl & PFNAV_FLAG_AIR))) {
+                        v2 diff = {r.px - pos.x, r.pz - pos.z};
+                        const float radius = a.radius + r.radius + 0.0f;
+                        const float len = v2_len(diff);
+                        if (!(len < EPS_F)) {
+                            const float t = (len - radius * 0.85f) / len;
+                            const float scale = (float)exp((double)fminf(-20.0f * t, 40.0f));
+                            diff = v2_scale(diff, scale);
+                            term = make_float2(diff.x, diff.z);
+                        }
+                    }
+                }
+                s.term[k] = term;
+            }
+            __syncwarp();
+            v2 separation = {0.0f, 0.0f};
+            for (int k = 0; k < num_near; k++) {         // the reference's summation order
+                const float2 t = s.term[k];
+                separation.x += t.x;
+                separation.z += t.y;
+            }
+            if (num_near == 0) separation = {0.0f, 0.0f};
+            else {
+                separation = v2_scale(separation, -1.0f);
+                separation = v2_truncate(separation, tp.scaled_max_force);
+            }
+            // ---- arrive_force_point (movement.c:1546) ----
+            const v2 target = a.flock >= 0 ? v2{flocks[a.flock].target[0], flocks[a.flock].target[1]} : pos;
+            v2 desired;
+            if (has_los) {
+                desired = v2_sub(target, pos);
+                const float distance = v2_len(desired);
+                desired = v2_normal(desired);
+                desired = v2_scale(desired, a.max_speed / hzf);
+                if (distance < 10.0f) desired = v2_scale(desired, distance / 10.0f);
+            } else {
+                desired = v2_scale(vdes, a.max_speed / hzf);
+            }
+            v2 arrive = v2_truncate(v2_sub(desired, velocity), tp.scaled_max_force);
+            // ---- cohesion (pre-pass) ----
+            const float2 ch = cohesion_in[w];
+            const v2 cohesion = {ch.x, ch.y};
+
+            const int layer = nav_layer_for(ent_flags, a.radius);
+            bool on_blocked, dummy, lp, lb, rp, rb, tpth, tb, bp, bb;
+            probe_tile(m, layer, pos.x, pos.z, dummy, on_blocked);
+            probe_tile(m, layer, pos.x + 4.0f, pos.z, lp, lb);      // left  = x + nt_dims.x
+            probe_tile(m, layer, pos.x - 4.0f, pos.z, rp, rb);      // right
+            probe_tile(m, layer, pos.x, pos.z + 4.0f, tpth, tb);    // top   = z + nt_dims.z
+            probe_tile(m, layer, pos.x, pos.z - 4.0f, bp, bb);      // bot
+
+            v2 steer = {0.0f, 0.0f};
+            for (int prio = 0; prio < 3; prio++) {
+                if (prio == 0) {
+                    // point_seek_total_force (movement.c:1745)
+                    const v2 A = v2_scale(arrive, 0.5f), C = v2_scale(cohesion, 0.15f), S = v2_scale(separation, 0.6f);
+                    v2 ret = {0.0f, 0.0f};
+                    ret = v2_add(ret, A);
+                    ret = v2_add(ret, S);
+                    ret = v2_add(ret, C);
+                    steer = v2_truncate(ret, tp.scaled_max_force);
+                } else if (prio == 1) steer = separation;
+                else steer = arrive;
+                // nullify_impass_components (movement.c:1831)
+                if (steer.x > 0 && (!lp || (!on_blocked && lb))) steer.x = 0.0f;
+                if (steer.x < 0 && (!rp || (!on_blocked && rb))) steer.x = 0.0f;
+                if (steer.z > 0 && (!tpth || (!on_blocked && tb))) steer.z = 0.0f;
+                if (steer.z < 0 && (!bp || (!on_blocked && bb))) steer.z = 0.0f;
+                if ((double)v2_len(steer) > tp.scaled_max_force_d * 0.01) break;
+            }
+            const v2 accel = v2_scale(steer, 1.0f / 1.0f);
+            vpref = v2_truncate(v2_add(velocity, accel), a.speed / hzf);
+        }
+
+        // ================= find_neighbours (movement.c:2768) =================
+        int ndyn = 0, nstat = 0, raw = 0;
+        grid_query(g, pos.x, pos.z, 10.0f, lane, [&](bool hit, uint32_t id) -> bool {
+            const uint32_t mk = __ballot_sync(FULL, hit);
+            const int rrank = __popc(mk & ((1u << lane) - 1));
+            bool isdyn = false, isstat = false;
+            cp_ent nd;
+            if (hit && raw + rrank < 512 && id != uid) {
+                const pf_record r = rec[id];
+                const uint32_t fl = r.state_flags & 0xFFFFFFu;
+                const uint32_t st = r.state_flags >> 24;
+                if ((fl & PFNAV_FLAG_MOVABLE) && r.radius != 0.0f &&
+                    ((ent_flags & PFNAV_FLAG_AIR) == (fl & PFNAV_FLAG_AIR))) {
+                    nd.pos = {r.px, r.pz}; nd.vel = {r.vx, r.vz}; nd.radius = r.radius;
+                    const bool still = (st == PFNAV_STATE_ARRIVED || st == PFNAV_STATE_WAITING);
+                    if (still || v2_len(nd.vel) < 0.3f) { nd.vel = {0.0f, 0.0f}; isstat = true; }
+                    else isdyn = true;
+                }
+            }
+            const uint32_t md = __ballot_sync(FULL, isdyn), ms = __ballot_sync(FULL, isstat);
+            if (isdyn) { const int k = ndyn + __popc(md & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) s.dyn[k] = nd; }
+            if (isstat) { const int k = nstat + __popc(ms & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) s.stat[k] = nd; }
+            ndyn = min(ndyn + __popc(md), PFNAV_MAX_NEIGHBOURS);
+            nstat = min(nstat + __popc(ms), PFNAV_MAX_NEIGHBOURS);
+            raw += __popc(mk);
+            return raw >= 512;
+        });
+        __syncwarp();
+
+        // ================= G_ClearPath_NewVelocity (clearpath.c:694) =================
+        const cp_ent self = {{a.prev_pos[0], a.prev_pos[1]}, velocity, a.radius};
+        v2 new_vel = {0.0f, 0.0f};
+        while (true) {
+            v2 r;
+            const bool found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r);
+            if (found) { new_vel = r; break; }
+            remove_furthest(s, self.pos, ndyn, nstat, lane);
+            if (!(ndyn > 0 && nstat > 0)) { new_vel = {0.0f, 0.0f}; break; }
+        }
+        new_vel = v2_truncate(new_vel, a.max_speed / hzf);      // movement.c:3464
+        if (lane == 0) {
+            vel_out[w] = make_float2(new_vel.x, new_vel.z);
+            vpref_out[w] = make_float2(vpref.x, vpref.z);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+static uint8_t *g_dummy = nullptr;
+
+void pfnav_agents_free(pfnav_ctx *ctx)
+{
+    cudaFree(ctx->d_agents); cudaFree(ctx->d_records); cudaFree(ctx->d_flocks);
+    cudaFree(ctx->d_flock_start); cudaFree(ctx->d_flock_members); cudaFree(ctx->d_cohesion);
+    cudaFree(ctx->d_cell_count); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_cell_fill);
+    cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
+    cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
+    ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
+    ctx->d_flock_members = nullptr; ctx->d_cohesion = nullptr; ctx->d_cell_count = nullptr; ctx->d_cell_start = nullptr;
+    ctx->d_cell_fill = nullptr; ctx->d_sorted_ix = nullptr; ctx->d_sorted_iy = nullptr; ctx->d_sorted_id = nullptr;
+    ctx->d_work = nullptr; ctx->d_vel_out = nullptr; ctx->d_vpref_out = nullptr; ctx->d_vdes_out = nullptr;
+    ctx->d_los_out = nullptr; ctx->d_work_count = nullptr; ctx->d_scan_tmp = nullptr;
+    ctx->cap_agents = ctx->cap_flocks = ctx->cap_cells = ctx->cap_work = 0;
+}
+
+// ---- field pool ----
+extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(ndests > 0 && max_fields > 0, "ndests/max_fields");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
+    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
+    const size_t nslots = (size_t)ndests * ctx->chunk_w * ctx->chunk_h;
+    PF_CUDA(cudaMalloc(&ctx->d_pool_slot, nslots * sizeof(int32_t)));
+    PF_CUDA(cudaMalloc(&ctx->d_pool_flow, (size_t)max_fields * 4096));
+    // LOS region carries a trailing `has` byte per slot
+    PF_CUDA(cudaMalloc(&ctx->d_pool_los, (size_t)max_fields * 4096 + max_fields));
+    PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, nslots * sizeof(int32_t)));
+    PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)max_fields * 4096, 0, max_fields));
+    ctx->h_pool_slot.assign(nslots, -1);
+    ctx->pool_ndests = ndests; ctx->pool_max = max_fields; ctx->pool_used = 0;
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
+{
+    PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, ctx->h_pool_slot.size() * sizeof(int32_t)));
+    PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, 0, ctx->pool_max));
+    std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
+    ctx->pool_used = 0;
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, const uint8_t *flow_field,
+                              const uint8_t *los_field)
+{
+    PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const size_t si = (size_t)dest * ctx->chunk_w * ctx->chunk_h + chunk_r * ctx->chunk_w + chunk_c;
+    int slot = ctx->h_pool_slot[si];
+    uint8_t has = 0;
+    uint8_t *d_has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096;
+    if (slot < 0) {
+        if (ctx->pool_used >= ctx->pool_max) { pfnav_set_error("pfnav_pool_put: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+        slot = ctx->pool_used++;
+        ctx->h_pool_slot[si] = slot;
+        PF_CUDA(cudaMemcpy(ctx->d_pool_slot + si, &slot, sizeof(int32_t), cudaMemcpyHostToDevice));
+    } else {
+        PF_CUDA(cudaMemcpy(&has, d_has + slot, 1, cudaMemcpyDeviceToHost));
+    }
+    if (flow_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_flow + (size_t)slot * 4096, flow_field, 4096, cudaMemcpyHostToDevice)); has |= 1; }
+    if (los_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)slot * 4096, los_field, 4096, cudaMemcpyHostToDevice)); has |= 2; }
+    PF_CUDA(cudaMemcpy(d_has + slot, &has, 1, cudaMemcpyHostToDevice));
+    return PFNAV_OK;
+}
+
+// ---- agents ----
+template <typename T>
+static int ensure(T *&p, size_t &cap, size_t need)
+{
+    if (cap >= need && p) return 0;
+    cudaFree(p);
+    p = nullptr;
+    PF_CUDA(cudaMalloc(&p, std::max<size_t>(need, 1) * sizeof(T)));
+    return 0;
+}
+
+static GridView grid_of(const pfnav_ctx *ctx)
+{
+    GridView g;
+    g.cell_start = ctx->d_cell_start; g.cell_count = ctx->d_cell_count;
+    g.ix = ctx->d_sorted_ix; g.iy = ctx->d_sorted_iy; g.id = ctx->d_sorted_id;
+    g.grid_w = ctx->grid_w; g.grid_h = ctx->grid_h; g.origin_x = ctx->origin_x; g.origin_y = ctx->origin_y;
+    return g;
+}
+
+static int build_index(pfnav_ctx *ctx, cudaStream_t st)
+{
+    const int n = (int)ctx->n_agents;
+    const int ncells = ctx->grid_w * ctx->grid_h;
+    PF_CUDA(cudaMemsetAsync(ctx->d_cell_count, 0, (size_t)ncells * 4, st));
+    PF_CUDA(cudaMemsetAsync(ctx->d_cell_fill, 0, (size_t)ncells * 4, st));
+    if (n > 0) {
+        const GridView g = grid_of(ctx);
+        k_cell_count<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_records, n, g, ctx->d_cell_count);
+        k_cell_scan<<<1, 1024, 0, st>>>(ctx->d_cell_count, ctx->d_cell_start, ncells);
+        k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_records, n, g, ctx->d_cell_start, ctx->d_cell_fill,
+                                                       ctx->d_sorted_id);
+        k_cell_sort<<<(ncells + 127) / 128, 128, 0, st>>>(ctx->d_records, g, ctx->d_cell_start, ctx->d_sorted_id,
+                                                         ctx->d_sorted_ix, ctx->d_sorted_iy, ncells);
+        ctx->launches += 4;
+    } else {
+        PF_CUDA(cudaMemsetAsync(ctx->d_cell_start, 0, (size_t)(ncells + 1) * 4, st));
+    }
+    PF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n, const pfnav_flock *flocks,
+                                   size_t nflocks, int hz)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(n == 0 || agents, "agents");
+    PF_ARG(nflocks == 0 || flocks, "flocks");
+    PF_ARG(hz == 20 || hz == 10 || hz == 5 || hz == 1, "hz must be 20, 10, 5 or 1 (movement.c:2210)");
+    PF_ARG(n < (1u << 31), "n");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->tick_stream;
+    ctx->hz = hz;
+    int rc;
+    if (n > ctx->cap_agents) {
+        size_t cap = 0;
+        if ((rc = ensure(ctx->d_agents, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_records, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_flock_members, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_sorted_ix, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_sorted_iy, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_sorted_id, cap, n))) return rc;
+        ctx->cap_agents = n;
+    }
+    if (nflocks + 1 > ctx->cap_flocks) {
+        size_t cap = 0;
+        if ((rc = ensure(ctx->d_flocks, cap, nflocks + 1))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_flock_start, cap, nflocks + 2))) return rc;
+        ctx->cap_flocks = nflocks + 1;
+    }
+    ctx->n_agents = n; ctx->n_flocks = nflocks;
+    // flock member lists, ascending uid (the iteration order our cohesion sum is defined over)
+    std::vector<uint32_t> fstart(nflocks + 1, 0), members(n ? n : 1);
+    for (size_t i = 0; i < n; i++) {
+        PF_ARG(agents[i].flock < (int)nflocks, "agent flock index out of range");
+        {   // Entity_NavLayerWithRadius (entity.c:554): the layer this agent's tile probes read
+            const uint32_t f = agents[i].flags; const float r = agents[i].radius;
+            const int base = (f & PFNAV_FLAG_WATER) ? 4 : (f & PFNAV_FLAG_AIR) ? 8 : 0;
+            const int layer = base + (r >= 15.0f ? 3 : r >= 10.0f ? 2 : r >= 5.0f ? 1 : 0);
+            PF_ARG(layer < ctx->nlayers, "agent needs a navigation layer that was not created (radius/flags)");
+        }
+        if (agents[i].flock >= 0) fstart[agents[i].flock + 1]++;
+    }
+    for (size_t f = 0; f < nflocks; f++) fstart[f + 1] += fstart[f];
+    {
+        std::vector<uint32_t> cur(fstart.begin(), fstart.end() - 1);
+        for (size_t i = 0; i < n; i++)
+            if (agents[i].flock >= 0) members[cur[agents[i].flock]++] = (uint32_t)i;
+    }
+    PF_CUDA(cudaMemcpyAsync(ctx->d_agents, agents, n * sizeof(pfnav_agent), cudaMemcpyHostToDevice, st));
+    if (nflocks) PF_CUDA(cudaMemcpyAsync(ctx->d_flocks, flocks, nflocks * sizeof(pfnav_flock), cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_flock_start, fstart.data(), (nflocks + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n) PF_CUDA(cudaMemcpyAsync(ctx->d_flock_members, members.data(), n * 4, cudaMemcpyHostToDevice, st));
+    // spatial index geometry: G_Pos_Init (position.c:264) + bg_init (bitmap_grid.h:959)
+    {
+        const float W = (float)(ctx->chunk_w * 256), H = (float)(ctx->chunk_h * 256);
+        const float cx = ctx->map_x - W / 2.0f, cz = ctx->map_z + H / 2.0f;
+        const float xmin = cx - W / 2.0f, xmax = cx + W / 2.0f, zmin = cz - H / 2.0f, zmax = cz + H / 2.0f;
+        ctx->origin_x = (int32_t)lrintf(xmin * 256.0f);
+        ctx->origin_y = (int32_t)lrintf(zmin * 256.0f);
+        const int32_t span_x = (int32_t)lrintf(xmax * 256.0f) - ctx->origin_x;
+        const int32_t span_y = (int32_t)lrintf(zmax * 256.0f) - ctx->origin_y;
+        ctx->grid_w = std::max(1, (int)(((uint32_t)span_x + 4095u) >> 12));
+        ctx->grid_h = std::max(1, (int)(((uint32_t)span_y + 4095u) >> 12));
+        const size_t ncells = (size_t)ctx->grid_w * ctx->grid_h;
+        if (ncells + 1 > ctx->cap_cells) {
+            size_t cap = 0;
+            if ((rc = ensure(ctx->d_cell_count, cap, ncells + 1))) return rc; cap = 0;
+            if ((rc = ensure(ctx->d_cell_start, cap, ncells + 1))) return rc; cap = 0;
+            if ((rc = ensure(ctx->d_cell_fill, cap, ncells + 1))) return rc;
+            ctx->cap_cells = ncells + 1;
+        }
+    }
+    if (n) {
+        k_make_records<<<((int)n + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_records, (int)n);
+        ctx->launches++;
+    }
+    if ((rc = build_index(ctx, st))) return rc;
+    // default work list: none until pfnav_agents_set_work
+    ctx->n_work = 0;
+    PF_CUDA(cudaStreamSynchronize(st));      // host vectors above go out of scope
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_rebuild_index(pfnav_ctx *ctx, void *stream)
+{
+    PF_ARG(ctx && ctx->d_records, "agents not uploaded");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    return build_index(ctx, (cudaStream_t)stream);
+}
+
+extern "C" int pfnav_agents_device_ptrs(pfnav_ctx *ctx, void **d_records, void **d_velocities, size_t *n)
+{
+    PF_ARG(ctx, "ctx");
+    if (d_records) *d_records = ctx->d_records;
+    if (d_velocities) *d_velocities = ctx->d_vel_out;
+    if (n) *n = ctx->n_agents;
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_t nwork)
+{
+    PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> all;
+    if (!uids) {
+        // every agent that is not still (ent_still, movement.c:652) -- needs the host copy of state
+        std::vector<pfnav_agent> h(ctx->n_agents);
+        PF_CUDA(cudaMemcpy(h.data(), ctx->d_agents, ctx->n_agents * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ctx->n_agents; i++)
+            if (h[i].state != PFNAV_STATE_ARRIVED && h[i].state != PFNAV_STATE_WAITING) all.push_back((uint32_t)i);
+        uids = all.data();
+        nwork = all.size();
+    }
+    for (size_t i = 0; i < nwork; i++) PF_ARG(uids[i] < ctx->n_agents, "work uid out of range");
+    if (nwork > ctx->cap_work) {
+        size_t cap = 0; int rc;
+        if ((rc = ensure(ctx->d_work, cap, nwork))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_vel_out, cap, nwork))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_vpref_out, cap, nwork))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_vdes_out, cap, nwork))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_cohesion, cap, nwork))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_los_out, cap, nwork))) return rc;
+        ctx->cap_work = nwork;
+    }
+    if (!ctx->d_work_count) PF_CUDA(cudaMalloc(&ctx->d_work_count, 16));
+    if (nwork) PF_CUDA(cudaMemcpy(ctx->d_work, uids, nwork * 4, cudaMemcpyHostToDevice));
+    ctx->n_work = nwork;
+    return PFNAV_OK;
+}
+
+__global__ void k_copy_vdes(const pfnav_agent *__restrict__ agents, const uint32_t *__restrict__ work, int nwork,
+                            float2 *__restrict__ vdes, uint8_t *__restrict__ los)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    const pfnav_agent &a = agents[work[w]];
+    vdes[w] = make_float2(a.vdes[0], a.vdes[1]);
+    los[w] = a.has_dest_los ? 1 : 0;
+}
+
+extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
+{
+    PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
+    if (ctx->n_work == 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->tick_stream;
+    const int nwork = (int)ctx->n_work;
+    MapView m;
+    m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
+    m.chunk_w = ctx->chunk_w; m.chunk_h = ctx->chunk_h; m.map_x = ctx->map_x; m.map_z = ctx->map_z;
+    // SCALED_MAX_FORCE = (MAX_FORCE / hz_count(hz) * 20.0): float division, double product (movement.c:93)
+    TickParams tp;
+    tp.hz = ctx->hz;
+    tp.scaled_max_force_d = (double)(0.75f / (float)ctx->hz) * 20.0;
+    tp.scaled_max_force = (float)tp.scaled_max_force_d;
+    PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
+    if (flags & PFNAV_TICK_VDES_FROM_POOL) {
+        PF_ARG(ctx->d_pool_slot, "PFNAV_TICK_VDES_FROM_POOL needs a field pool");
+        PoolView pv;
+        pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
+        pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
+        k_desired_velocity<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
+                                                               ctx->d_vdes_out, ctx->d_los_out, ctx->d_work_count);
+    } else {
+        k_copy_vdes<<<(nwork + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out);
+    }
+    k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
+                                                   ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
+    const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
+    k_agent_velocity<<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+                                                             ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
+                                                             ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out);
+    ctx->launches += 3;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(ctx->tick_done, st));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_read_velocities(pfnav_ctx *ctx, float *out_xz, size_t maxout)
+{
+    PF_ARG(ctx && out_xz, "null");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaEventSynchronize(ctx->tick_done));
+    const size_t n = std::min(maxout, ctx->n_work);
+    if (n) PF_CUDA(cudaMemcpy(out_xz, ctx->d_vel_out, n * 8, cudaMemcpyDeviceToHost));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_read_debug(pfnav_ctx *ctx, float *out_vpref_xz, float *out_vdes_xz, uint8_t *out_has_los,
+                                       size_t maxout)
+{
+    PF_ARG(ctx, "null");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaEventSynchronize(ctx->tick_done));
+    const size_t n = std::min(maxout, ctx->n_work);
+    if (n && out_vpref_xz) PF_CUDA(cudaMemcpy(out_vpref_xz, ctx->d_vpref_out, n * 8, cudaMemcpyDeviceToHost));
+    if (n && out_vdes_xz) PF_CUDA(cudaMemcpy(out_vdes_xz, ctx->d_vdes_out, n * 8, cudaMemcpyDeviceToHost));
+    if (n && out_has_los) PF_CUDA(cudaMemcpy(out_has_los, ctx->d_los_out, n, cudaMemcpyDeviceToHost));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_ents_in_circle(pfnav_ctx *ctx, float x, float z, float range, uint32_t *out, int maxout, int *out_n)
+{
+    PF_ARG(ctx && ctx->d_records && out && out_n && maxout > 0, "args");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    if (range < 0.0f) { *out_n = 0; return PFNAV_OK; }
+    uint32_t *d_out = nullptr; int *d_n = nullptr;
+    PF_CUDA(cudaMalloc(&d_out, (size_t)maxout * 4));
+    PF_CUDA(cudaMalloc(&d_n, 4));
+    k_ents_in_circle<<<1, 32, 0, ctx->tick_stream>>>(grid_of(ctx), x, z, range, d_out, maxout, d_n);
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->tick_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out_n, d_n, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && *out_n > 0) e = cudaMemcpy(out, d_out, (size_t)*out_n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_out); cudaFree(d_n);
+    if (e != cudaSuccess) { pfnav_set_error("pfnav_ents_in_circle: %s", cudaGetErrorString(e)); return PFNAV_ERR_CUDA; }
+    return PFNAV_OK;
+}

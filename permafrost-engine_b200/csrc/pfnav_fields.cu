@@ -1,0 +1,1181 @@
+// pfnav_fields.cu -- context, device map state, flow-field and LOS-field kernels.
+//
+// Replaces (reference file:line):
+//   N_FlowFieldInit / N_FlowFieldUpdate TARGET_TILE | TARGET_PORTAL   src/navigation/field.c:2020-2083
+//     field_build_integration :539, field_build_flow/field_flow_dir :734/:355,
+//     field_portal_initial_frontier :1160, field_fixup_portal_edges :830
+//   N_LOSFieldCreate                                                   src/navigation/field.c:2085-2245
+//     field_neighbours_grid_los :304, field_is_los_corner :435,
+//     field_create_wavefront_blocked_line :463, field_pad_wavefront :519, pqueue.h:109-208
+//
+// Design (B200): the nav grids live in HBM as row-major images per layer so that any 64x64
+// window is one TMA box (cp.async.bulk.tensor.3d, coordinates {x, y, layer}).
+//   * K1 flow field, unit-cost chunks (the only costs a finished map holds are 1 and 0xFF,
+//     nav.c:339-342): ONE WARP PER FIELD, bit-parallel multi-source BFS. A row of 64 tiles is one
+//     64-bit word, a lane owns two rows, a BFS level is a handful of shifts/ORs plus two warp
+//     shuffles for the rows above/below; the flow direction of every tile reached at level d is
+//     derived in the same step from the level d-1 / d-2 frontiers (the integration field is
+//     never materialised). The reference's float Dijkstra sums small integers exactly, so the
+//     distance field is unique and any correct SSSP is bit-exact.
+//   * K1g general costs (transient 0-cost tiles, nav.c:359): one CTA per field, Bellman-Ford
+//     relaxation on u32 distances in shared memory, then the reference's 8-neighbour rule.
+//   * K3 LOS field: order-dependent (heap pop order among equal priorities is observable,
+//     SURVEY.md 8a-2), so lane 0 of a warp replays the reference's binary heap exactly in
+//     shared memory while the whole warp does tile staging, padding and the store.
+#include "pfnav_internal.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void pfnav_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *pfnav_last_error(void) { return g_err; }
+extern "C" int pfnav_version(void) { return PFNAV_VERSION; }
+extern "C" uint64_t pfnav_launch_count(const pfnav_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers (mbarrier + TMA)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
+                                            int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// bit helpers
+// ------------------------------------------------------------------------------------------
+// 4 byte-masks (0xFF/0x00) -> 4 bits
+__device__ __forceinline__ uint32_t bytemask_to_bits(uint32_t m)
+{
+    return (((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+}
+// bits for 16 cost bytes: impassable (==0xFF) and "not unit" (!= 1)
+__device__ __forceinline__ void cost16_bits(const uint4 v, uint32_t &imp, uint32_t &nonunit)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    imp = 0; nonunit = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        imp |= bytemask_to_bits(__vcmpeq4(w[i], 0xFFFFFFFFu)) << (4 * i);
+        nonunit |= bytemask_to_bits(__vcmpne4(w[i], 0x01010101u)) << (4 * i);
+    }
+}
+// bits for 8 u16 blockers: nonzero
+__device__ __forceinline__ uint32_t blk8_bits(const uint4 v)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t b = ((w[i] & 0xFFFFu) ? 1u : 0u) | ((w[i] >> 16) ? 2u : 0u);
+        r |= b << (2 * i);
+    }
+    return r;
+}
+// 4 bits -> 4 bytes (bit j -> bit 0 of byte j)
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, uint32_t lane)
+{
+    uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, 1);
+    uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), 1);
+    return lane == 0 ? 0ull : (((uint64_t)hi << 32) | lo);
+}
+__device__ __forceinline__ uint64_t shfl_down64(uint64_t v, uint32_t lane)
+{
+    uint32_t lo = __shfl_down_sync(0xffffffffu, (uint32_t)v, 1);
+    uint32_t hi = __shfl_down_sync(0xffffffffu, (uint32_t)(v >> 32), 1);
+    return lane == 31 ? 0ull : (((uint64_t)hi << 32) | lo);
+}
+
+// ------------------------------------------------------------------------------------------
+// Map-state kernels
+// ------------------------------------------------------------------------------------------
+// chunk-blocked [chunk][64][64] -> image [H64][W64]
+template <typename T>
+__global__ void k_deblock(const T *__restrict__ src, T *__restrict__ dst, int chunk_w, int chunk_h)
+{
+    const int W64 = chunk_w * 64;
+    size_t total = (size_t)chunk_w * chunk_h * 4096;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t chunk = i >> 12;
+        int t = (int)(i & 4095);
+        int cr = (int)(chunk / chunk_w), cc = (int)(chunk % chunk_w);
+        dst[(size_t)(cr * 64 + (t >> 6)) * W64 + cc * 64 + (t & 63)] = src[i];
+    }
+}
+
+// per-chunk flag: 1 if every passable tile has cost 1. One warp per chunk.
+__global__ void k_unit_flags(const uint8_t *__restrict__ cost, uint8_t *__restrict__ unit, int chunk_w, int chunk_h)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= chunk_w * chunk_h) return;
+    int cr = warp / chunk_w, cc = warp % chunk_w;
+    const int W64 = chunk_w * 64;
+    bool bad = false;
+    for (int t = lane; t < 4096; t += 32) {
+        uint8_t c = cost[(size_t)(cr * 64 + (t >> 6)) * W64 + cc * 64 + (t & 63)];
+        bad |= (c != 1 && c != 0xFF);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) unit[warp] = bad ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: flow field, unit-cost fast path. One warp per field.
+// ------------------------------------------------------------------------------------------
+struct FlowGrids {
+    const uint8_t *cost;     // [layer][H64][W64]
+    const uint16_t *blk;
+    const uint16_t *liid;
+    const uint8_t *unit;     // [layer][chunks]
+    int W64, H64, chunk_w, chunk_h;
+};
+
+#define FLOW_WARPS_PER_CTA 8
+#define FLOW_SMEM_PER_WARP 12288   // cost tile 4096 + blockers tile 8192
+
+// Load the passable masks of the lane's two rows (rows 2*lane, 2*lane+1).
+// P bit c = cost != 0xFF && blockers == 0 (field_tile_passable, field.c:117).
+template <bool USE_TMA>
+__device__ __forceinline__ void load_pass_rows(const FlowGrids &g, const CUtensorMap *tm_cost,
+                                               const CUtensorMap *tm_blk, uint8_t *sm, uint64_t *bar,
+                                               uint32_t &phase, int layer, int chunk_r, int chunk_c,
+                                               uint32_t lane, uint64_t &P0, uint64_t &P1, bool &nonunit)
+{
+    uint64_t P[2] = {0, 0};
+    uint32_t nu = 0;
+    if (USE_TMA) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, FLOW_SMEM_PER_WARP);
+            tma_load_3d(sm, tm_cost, bar, chunk_c * 64, chunk_r * 64, layer);
+            tma_load_3d(sm + 4096, tm_blk, bar, chunk_c * 64, chunk_r * 64, layer);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        // lane's cost bytes: 128 contiguous bytes at lane*128 (8 x 16B); rotate the chunk order by
+        // lane so the 8 lanes of a quarter-warp hit distinct bank groups.
+        const uint4 *sc = reinterpret_cast<const uint4 *>(sm + lane * 128);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int q = (k + lane) & 7;
+            uint32_t imp, n1;
+            cost16_bits(sc[q], imp, n1);
+            uint32_t pass = (~imp) & 0xFFFFu;
+            nu |= n1 & pass;
+            const uint64_t val = (uint64_t)pass << ((q & 3) * 16);
+            if (q >> 2) P[1] |= val; else P[0] |= val;
+        }
+        const uint4 *sb = reinterpret_cast<const uint4 *>(sm + 4096 + lane * 256);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int q = (k + lane) & 15;
+            const uint64_t b = (uint64_t)blk8_bits(sb[q]) << ((q & 7) * 8);
+            if (q >> 3) P[1] &= ~b; else P[0] &= ~b;
+        }
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            int row = 2 * lane + rr;
+            size_t off = ((size_t)layer * g.H64 + chunk_r * 64 + row) * g.W64 + chunk_c * 64;
+            const uint4 *pc = reinterpret_cast<const uint4 *>(g.cost + off);
+            const uint4 *pb = reinterpret_cast<const uint4 *>(g.blk + off);
+            uint4 c4[4], b4[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) c4[k] = __ldg(pc + k);
+#pragma unroll
+            for (int k = 0; k < 8; k++) b4[k] = __ldg(pb + k);
+            uint64_t p = 0, blocked = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t imp, n1;
+                cost16_bits(c4[k], imp, n1);
+                uint32_t pass = (~imp) & 0xFFFFu;
+                nu |= n1 & pass;
+                p |= (uint64_t)pass << (16 * k);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) blocked |= (uint64_t)blk8_bits(b4[k]) << (8 * k);
+            P[rr] = p & ~blocked;
+        }
+    }
+    P0 = P[0];
+    P1 = P[1];
+    nonunit = nu != 0;
+}
+
+// Seeds of a TARGET_PORTAL field (field_portal_initial_frontier, field.c:1160 +
+// field_tile_adjacent_to_next_iid :1131). Returns the seed masks of the lane's two rows.
+__device__ __forceinline__ void portal_seeds(const FlowGrids &g, const pfnav_field_req &q, uint32_t lane,
+                                             uint64_t P0, uint64_t P1, uint64_t &S0, uint64_t &S1)
+{
+    S0 = 0; S1 = 0;
+    const int nr = q.port_r1 - q.port_r0 + 1, nc = q.port_c1 - q.port_c0 + 1;
+    const int ntiles = nr * nc;
+    const size_t lbase = (size_t)q.layer * g.H64 * g.W64;
+    for (int base = 0; base < ntiles; base += 32) {
+        int i = base + (int)lane;
+        int r = -1, c = -1;
+        bool ok = false;
+        if (i < ntiles) {
+            r = q.port_r0 + i / nc;
+            c = q.port_c0 + i % nc;
+            ok = true;
+            if (q.port_iid != PFNAV_ISLAND_NONE) {
+                uint16_t li = g.liid[lbase + (size_t)(q.chunk_r * 64 + r) * g.W64 + q.chunk_c * 64 + c];
+                ok = (li == q.port_iid);
+            }
+            if (ok) {
+                // adjacency to a tile of the next portal whose local island is next_iid
+                const int gr = q.chunk_r * 64 + r, gc = q.chunk_c * 64 + c;
+                const int dr[4] = {-1, 1, 0, 0}, dc[4] = {0, 0, -1, 1};
+                bool adj = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int ngr = gr + dr[k], ngc = gc + dc[k];
+                    if (ngr < 0 || ngc < 0 || ngr >= g.H64 || ngc >= g.W64) continue;
+                    if ((ngr >> 6) != q.next_chunk_r || (ngc >> 6) != q.next_chunk_c) continue;
+                    int tr = ngr & 63, tc = ngc & 63;
+                    if (tr < q.next_r0 || tr > q.next_r1 || tc < q.next_c0 || tc > q.next_c1) continue;
+                    uint16_t li = g.liid[lbase + (size_t)ngr * g.W64 + ngc];
+                    if (li == q.next_iid) adj = true;
+                }
+                ok = adj;
+            }
+        }
+        // route each accepted tile to the lane that owns its row
+#pragma unroll 1
+        for (int src = 0; src < 32; src++) {
+            int rr = __shfl_sync(0xffffffffu, r, src);
+            int cc = __shfl_sync(0xffffffffu, c, src);
+            int oo = __shfl_sync(0xffffffffu, (int)ok, src);
+            if (oo && (rr >> 1) == (int)lane) {
+                if (rr & 1) S1 |= 1ull << cc; else S0 |= 1ull << cc;
+            }
+        }
+    }
+    // only passable tiles seed the frontier (field.c:1186-1193)
+    S0 &= P0;
+    S1 &= P1;
+}
+
+// Expand one row (4 bit planes + reached mask) into 64 dir bytes and store them.
+__device__ __forceinline__ void store_row(uint8_t *dst_row, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                          uint64_t reached, bool init)
+{
+    uint4 *dst = reinterpret_cast<uint4 *>(dst_row);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {      // 16 tiles per uint4
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // 4 tiles per u32
+            int sh = k * 16 + j * 4;
+            uint32_t x0 = (uint32_t)(b0 >> sh), x1 = (uint32_t)(b1 >> sh), x2 = (uint32_t)(b2 >> sh),
+                     x3 = (uint32_t)(b3 >> sh);
+            w[j] = spread4(x0) | (spread4(x1) << 1) | (spread4(x2) << 2) | (spread4(x3) << 3);
+        }
+        if (!init) {
+            // tiles the integration never reached keep their previous direction (field.c:744-745)
+            uint4 old = dst[k];
+            uint32_t o[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int sh = k * 16 + j * 4;
+                uint32_t keep = spread4((uint32_t)(~reached >> sh)) * 0xFFu;
+                w[j] = (w[j] & ~keep) | (o[j] & keep);
+            }
+        }
+        dst[k] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(FLOW_WARPS_PER_CTA * 32)
+k_flow_unit(const __grid_constant__ CUtensorMap tm_cost, const __grid_constant__ CUtensorMap tm_blk, FlowGrids g,
+            const pfnav_field_req *__restrict__ reqs, int n, uint8_t *__restrict__ fields)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *sm = smem + warp * FLOW_SMEM_PER_WARP;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + FLOW_WARPS_PER_CTA * FLOW_SMEM_PER_WARP) + warp;
+    uint32_t phase = 0;
+    if (USE_TMA) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    const int total_warps = gridDim.x * FLOW_WARPS_PER_CTA;
+    for (int i = blockIdx.x * FLOW_WARPS_PER_CTA + warp; i < n; i += total_warps) {
+        const pfnav_field_req q = reqs[i];
+        // the general-cost kernel owns chunks that hold a passable cost other than 1
+        if (!g.unit[(size_t)q.layer * g.chunk_w * g.chunk_h + q.chunk_r * g.chunk_w + q.chunk_c]) continue;
+
+        uint64_t P0, P1;
+        bool nonunit;
+        if (USE_TMA) { fence_proxy_async(); __syncwarp(); }
+        load_pass_rows<USE_TMA>(g, &tm_cost, &tm_blk, sm, bar, phase, q.layer, q.chunk_r, q.chunk_c, lane, P0, P1,
+                                nonunit);
+
+        // ---- seeds (field_initial_frontier, field.c:1372) ----
+        uint64_t S0 = 0, S1 = 0;
+        if (q.target_type == PFNAV_TARGET_TILE) {
+            if ((q.tile_r >> 1) == (int)lane) {
+                if (q.tile_r & 1) S1 = (1ull << q.tile_c) & P1; else S0 = (1ull << q.tile_c) & P0;
+            }
+        } else {
+            portal_seeds(g, q, lane, P0, P1, S0, S1);
+        }
+
+        // ---- bit-parallel BFS with on-the-fly direction derivation ----
+        const uint64_t Pu = shfl_up64(P1, lane), Pd = shfl_down64(P0, lane);
+        uint64_t V0 = S0, V1 = S1, F0 = S0, F1 = S1, G0 = 0, G1 = 0, Gu = 0, Gd = 0;
+        uint64_t D00 = 0, D01 = 0, D02 = 0, D03 = 0, D10 = 0, D11 = 0, D12 = 0, D13 = 0;
+        const uint64_t P0l = P0 << 1, P0r = P0 >> 1, P1l = P1 << 1, P1r = P1 >> 1;
+        while (true) {
+            const uint64_t Fu = shfl_up64(F1, lane), Fd = shfl_down64(F0, lane);
+            const uint64_t N0 = ((F0 << 1) | (F0 >> 1) | Fu | F1) & P0 & ~V0;
+            const uint64_t N1 = ((F1 << 1) | (F1 >> 1) | F0 | Fd) & P1 & ~V1;
+            if (!__any_sync(0xffffffffu, (N0 | N1) != 0)) break;
+            {   // row 0: above = lane-1's row 1 (Fu/Gu/Pu), below = own row 1
+                const uint64_t dNW = (Gu << 1) & Pu & P0l, dNE = (Gu >> 1) & Pu & P0r;
+                const uint64_t dSW = (G1 << 1) & P1 & P0l, dSE = (G1 >> 1) & P1 & P0r;
+                const uint64_t anyd = (dNW | dNE | dSW | dSE) & N0;
+                // min_cost is d-2 where an admissible diagonal exists; the selection then takes the
+                // first neighbour EQUAL to min_cost without re-checking admissibility (field.c:405-428)
+                uint64_t t;
+                const uint64_t m1 = (Gu << 1) & anyd;            t = m1;
+                const uint64_t m3 = (Gu >> 1) & anyd & ~t;       t |= m3;
+                const uint64_t m6 = (G1 << 1) & anyd & ~t;       t |= m6;
+                const uint64_t m8 = (G1 >> 1) & anyd & ~t;
+                const uint64_t card = N0 & ~anyd;
+                const uint64_t m2 = Fu & card;                   t = m2;
+                const uint64_t m7 = F1 & card & ~t;              t |= m7;
+                const uint64_t m5 = (F0 >> 1) & card & ~t;       t |= m5;
+                const uint64_t m4 = (F0 << 1) & card & ~t;
+                D00 |= m1 | m3 | m5 | m7;
+                D01 |= m2 | m3 | m6 | m7;
+                D02 |= m4 | m5 | m6 | m7;
+                D03 |= m8;
+            }
+            {   // row 1: above = own row 0, below = lane+1's row 0 (Fd/Gd/Pd)
+                const uint64_t dNW = (G0 << 1) & P0 & P1l, dNE = (G0 >> 1) & P0 & P1r;
+                const uint64_t dSW = (Gd << 1) & Pd & P1l, dSE = (Gd >> 1) & Pd & P1r;
+                const uint64_t anyd = (dNW | dNE | dSW | dSE) & N1;
+                uint64_t t;
+                const uint64_t m1 = (G0 << 1) & anyd;            t = m1;
+                const uint64_t m3 = (G0 >> 1) & anyd & ~t;       t |= m3;
+                const uint64_t m6 = (Gd << 1) & anyd & ~t;       t |= m6;
+                const uint64_t m8 = (Gd >> 1) & anyd & ~t;
+                const uint64_t card = N1 & ~anyd;
+                const uint64_t m2 = F0 & card;                   t = m2;
+                const uint64_t m7 = Fd & card & ~t;              t |= m7;
+                const uint64_t m5 = (F1 >> 1) & card & ~t;       t |= m5;
+                const uint64_t m4 = (F1 << 1) & card & ~t;
+                D10 |= m1 | m3 | m5 | m7;
+                D11 |= m2 | m3 | m6 | m7;
+                D12 |= m4 | m5 | m6 | m7;
+                D13 |= m8;
+            }
+            G0 = F0; G1 = F1; Gu = Fu; Gd = Fd;
+            F0 = N0; F1 = N1;
+            V0 |= N0; V1 |= N1;
+        }
+
+        // ---- portal fixup: seeds point across the border (field_fixup_portal_edges, field.c:830) ----
+        if (q.target_type == PFNAV_TARGET_PORTAL) {
+            const bool up = q.next_chunk_r < q.chunk_r, down = q.next_chunk_r > q.chunk_r;
+            const bool left = q.next_chunk_c < q.chunk_c;
+            // FD_N = 2, FD_S = 7, FD_W = 4, FD_E = 5
+            const uint32_t code = up ? 2u : down ? 7u : left ? 4u : 5u;
+            if (code & 1) { D00 |= S0; D10 |= S1; }
+            if (code & 2) { D01 |= S0; D11 |= S1; }
+            if (code & 4) { D02 |= S0; D12 |= S1; }
+        }
+
+        uint8_t *dst = fields + (size_t)i * 4096 + lane * 128;
+        store_row(dst, D00, D01, D02, D03, V0, q.init != 0);
+        store_row(dst + 64, D10, D11, D12, D13, V1, q.init != 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1g: flow field, general u8 costs. One CTA (128 threads) per field.
+// ------------------------------------------------------------------------------------------
+#define FLOWG_THREADS 128
+__global__ void __launch_bounds__(FLOWG_THREADS)
+k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uint8_t *__restrict__ fields,
+               int only_nonunit)
+{
+    __shared__ uint32_t dist[4096];
+    __shared__ uint8_t cost[4096];       // 0xFF = impassable or blocked
+    __shared__ uint8_t seed[4096];
+    __shared__ int changed;
+    const int tid = threadIdx.x;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const pfnav_field_req q = reqs[i];
+        if (only_nonunit &&
+            g.unit[(size_t)q.layer * g.chunk_w * g.chunk_h + q.chunk_r * g.chunk_w + q.chunk_c])
+            continue;
+        const size_t lbase = (size_t)q.layer * g.H64 * g.W64;
+        for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+            size_t off = lbase + (size_t)(q.chunk_r * 64 + (t >> 6)) * g.W64 + q.chunk_c * 64 + (t & 63);
+            uint8_t c = g.cost[off];
+            if (g.blk[off] > 0) c = 0xFF;
+            cost[t] = c;
+            dist[t] = 0xFFFFFFFFu;
+            seed[t] = 0;
+        }
+        __syncthreads();
+        if (q.target_type == PFNAV_TARGET_TILE) {
+            if (tid == 0) {
+                int t = q.tile_r * 64 + q.tile_c;
+                if (cost[t] != 0xFF) { seed[t] = 1; dist[t] = 0; }
+            }
+        } else {
+            const int nc = q.port_c1 - q.port_c0 + 1, ntiles = (q.port_r1 - q.port_r0 + 1) * nc;
+            for (int k = tid; k < ntiles; k += FLOWG_THREADS) {
+                int r = q.port_r0 + k / nc, c = q.port_c0 + k % nc;
+                if (cost[r * 64 + c] == 0xFF) continue;
+                if (q.port_iid != PFNAV_ISLAND_NONE &&
+                    g.liid[lbase + (size_t)(q.chunk_r * 64 + r) * g.W64 + q.chunk_c * 64 + c] != q.port_iid)
+                    continue;
+                const int gr = q.chunk_r * 64 + r, gc = q.chunk_c * 64 + c;
+                const int dr[4] = {-1, 1, 0, 0}, dc[4] = {0, 0, -1, 1};
+                bool adj = false;
+                for (int e = 0; e < 4; e++) {
+                    int ngr = gr + dr[e], ngc = gc + dc[e];
+                    if (ngr < 0 || ngc < 0 || ngr >= g.H64 || ngc >= g.W64) continue;
+                    if ((ngr >> 6) != q.next_chunk_r || (ngc >> 6) != q.next_chunk_c) continue;
+                    int tr = ngr & 63, tc = ngc & 63;
+                    if (tr < q.next_r0 || tr > q.next_r1 || tc < q.next_c0 || tc > q.next_c1) continue;
+                    if (g.liid[lbase + (size_t)ngr * g.W64 + ngc] == q.next_iid) adj = true;
+                }
+                if (adj) { seed[r * 64 + c] = 1; dist[r * 64 + c] = 0; }
+            }
+        }
+        __syncthreads();
+        // Bellman-Ford to the unique shortest-distance fixpoint; edge weight = cost of the tile
+        // entered (field_build_integration, field.c:556-563).
+        do {
+            __syncthreads();
+            if (tid == 0) changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+                const uint8_t c = cost[t];
+                if (c == 0xFF || seed[t]) continue;
+                const int r = t >> 6, cc = t & 63;
+                uint32_t m = 0xFFFFFFFFu;
+                if (r > 0)   m = min(m, dist[t - 64]);
+                if (r < 63)  m = min(m, dist[t + 64]);
+                if (cc > 0)  m = min(m, dist[t - 1]);
+                if (cc < 63) m = min(m, dist[t + 1]);
+                if (m != 0xFFFFFFFFu && m + c < dist[t]) { dist[t] = m + c; ch = true; }
+            }
+            if (ch) changed = 1;
+            __syncthreads();
+        } while (changed);
+
+        const bool up = q.next_chunk_r < q.chunk_r, down = q.next_chunk_r > q.chunk_r;
+        const bool left = q.next_chunk_c < q.chunk_c;
+        const uint8_t fix = up ? 2 : down ? 7 : left ? 4 : 5;
+        uint8_t *dst = fields + (size_t)i * 4096;
+        for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+            const uint32_t d = dist[t];
+            if (d == 0xFFFFFFFFu) { if (q.init) dst[t] = 0; continue; }
+            if (d == 0) { dst[t] = (q.target_type == PFNAV_TARGET_PORTAL) ? fix : 0; continue; }
+            const int r = t >> 6, c = t & 63;
+            const uint32_t INF = 0xFFFFFFFFu;
+            const uint32_t dn = r > 0 ? dist[t - 64] : INF, ds = r < 63 ? dist[t + 64] : INF;
+            const uint32_t dw = c > 0 ? dist[t - 1] : INF, de = c < 63 ? dist[t + 1] : INF;
+            const uint32_t dnw = (r > 0 && c > 0) ? dist[t - 65] : INF, dne = (r > 0 && c < 63) ? dist[t - 63] : INF;
+            const uint32_t dsw = (r < 63 && c > 0) ? dist[t + 63] : INF, dse = (r < 63 && c < 63) ? dist[t + 65] : INF;
+            uint32_t m = min(min(dn, ds), min(dw, de));
+            if (dn != INF && dw != INF) m = min(m, dnw);
+            if (dn != INF && de != INF) m = min(m, dne);
+            if (ds != INF && dw != INF) m = min(m, dsw);
+            if (ds != INF && de != INF) m = min(m, dse);
+            uint8_t dir;   // field.c:405-428 priority N,S,E,W,NW,NE,SW,SE
+            if (dn == m) dir = 2; else if (ds == m) dir = 7; else if (de == m) dir = 5; else if (dw == m) dir = 4;
+            else if (dnw == m) dir = 1; else if (dne == m) dir = 3; else if (dsw == m) dir = 6; else dir = 8;
+            dst[t] = dir;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: LOS field. One warp per field; lane 0 replays the reference heap exactly.
+// ------------------------------------------------------------------------------------------
+#define LOS_WARPS_PER_CTA 4
+struct LosSmem {
+    uint64_t pass[64];       // cost != 0xFF && blockers == 0
+    uint64_t open[64];       // pass && cost <= 1  (neighbour_costs[i] > 1 test, field.c:2211)
+    uint64_t assigned[64];   // integration_field < INF
+    uint64_t vis[64];
+    uint64_t blk[64];
+    uint16_t heap[4100];     // 1-indexed; entry = prio2 << 12 | r << 6 | c
+};
+
+struct LosMapInfo {
+    float map_x, map_z;
+};
+
+// field_create_wavefront_blocked_line (field.c:463-517)
+__device__ void los_blocked_line(LosSmem &s, const LosMapInfo mi, int tgt_cr, int tgt_cc, int tgt_r, int tgt_c,
+                                 int cr, int cc, int r, int c)
+{
+    // M_Tile_Bounds (tile.c:356): x decreases with the column, z increases with the row
+    const float tbx = (mi.map_x - (float)(tgt_cc * 256)) - (float)(tgt_c * 4);
+    const float tbz = (mi.map_z + (float)(tgt_cr * 256)) + (float)(tgt_r * 4);
+    const float cbx = (mi.map_x - (float)(cc * 256)) - (float)(c * 4);
+    const float cbz = (mi.map_z + (float)(cr * 256)) + (float)(r * 4);
+    const float tcx = tbx - 4.0f / 2.0f, tcz = tbz + 4.0f / 2.0f;
+    const float ccx = cbx - 4.0f / 2.0f, ccz = cbz + 4.0f / 2.0f;
+    float sx_ = tcx - ccx, sz_ = tcz - ccz;
+    const float len = sqrtf(sx_ * sx_ + sz_ * sz_);   // PFM_Vec2_Len: float sum, correctly rounded sqrt
+    sx_ = sx_ / len;
+    sz_ = sz_ / len;
+    int dx = abs((int)(sx_ * 1000));
+    int dy = -abs((int)(sz_ * 1000));
+    const int sx = sx_ > 0.0f ? 1 : -1;
+    const int sy = sz_ < 0.0f ? 1 : -1;
+    int err = dx + dy, e2;
+    int rr = r, c2 = c;
+    do {
+        s.blk[rr] |= 1ull << c2;
+        e2 = 2 * err;
+        if (e2 >= dy) { err += dy; c2 += sx; }
+        if (e2 <= dx) { err += dx; rr += sy; }
+    } while (rr >= 0 && rr < 64 && c2 >= 0 && c2 < 64);
+}
+
+// field_is_los_corner (field.c:435)
+__device__ __forceinline__ bool los_is_corner(const LosSmem &s, int r, int c)
+{
+    if (r > 0 && r < 63) {
+        bool a = !((s.pass[r - 1] >> c) & 1), b = !((s.pass[r + 1] >> c) & 1);
+        if (a ^ b) return true;
+    }
+    if (c > 0 && c < 63) {
+        bool a = !((s.pass[r] >> (c - 1)) & 1), b = !((s.pass[r] >> (c + 1)) & 1);
+        if (a ^ b) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool heap_lt(uint16_t a, uint16_t b) { return (((b >> 12) - (a >> 12)) & 3) == 1; }
+
+// pq_coord_push (pqueue.h:165-188)
+__device__ __forceinline__ void heap_push(uint16_t *h, int &size, uint16_t e)
+{
+    int curr = size + 1, parent = curr >> 1;
+    while (curr > 1 && heap_lt(e, h[parent])) {    // nodes[parent].priority > in_prio
+        h[curr] = h[parent];
+        curr = parent;
+        parent >>= 1;
+    }
+    h[curr] = e;
+    size++;
+}
+// pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200)
+__device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
+{
+    const uint16_t out = h[1];
+    h[1] = h[size];
+    size--;
+    int root = 1;
+    while (root != size + 1) {
+        int target = size + 1;
+        const int l = root * 2, r = l + 1;
+        if (l <= size && heap_lt(h[l], h[target])) target = l;
+        if (r <= size && heap_lt(h[r], h[target])) target = r;
+        h[root] = h[target];
+        root = target;
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(LOS_WARPS_PER_CTA * 32)
+k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int first, int n,
+      uint8_t *fields)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LosSmem &s = reinterpret_cast<LosSmem *>(smem_raw)[warp];
+    const int total_warps = gridDim.x * LOS_WARPS_PER_CTA;
+    for (int k = blockIdx.x * LOS_WARPS_PER_CTA + warp; k < n; k += total_warps) {
+        const int i = first + k;
+        const pfnav_los_req q = reqs[i];
+        // ---- stage tile -> bit rows (2 rows per lane) ----
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int row = 2 * lane + rr;
+            const size_t off = ((size_t)q.layer * g.H64 + q.chunk_r * 64 + row) * g.W64 + q.chunk_c * 64;
+            const uint4 *pc = reinterpret_cast<const uint4 *>(g.cost + off);
+            const uint4 *pb = reinterpret_cast<const uint4 *>(g.blk + off);
+            uint64_t p = 0, blocked = 0, gt1 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = __ldg(pc + j);
+                uint32_t imp, n1;
+                cost16_bits(v, imp, n1);
+                p |= (uint64_t)((~imp) & 0xFFFFu) << (16 * j);
+                // cost > 1  <=>  cost not in {0, 1}
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t g1 = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    g1 |= bytemask_to_bits(__vcmpgtu4(w[e], 0x01010101u)) << (4 * e);
+                gt1 |= (uint64_t)g1 << (16 * j);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) blocked |= (uint64_t)blk8_bits(__ldg(pb + j)) << (8 * j);
+            s.pass[row] = p & ~blocked;
+            s.open[row] = p & ~blocked & ~gt1;
+            s.assigned[row] = 0;
+            s.vis[row] = 0;
+            s.blk[row] = 0;
+        }
+        __syncwarp();
+
+        if (lane == 0) {
+            uint16_t *h = s.heap;
+            int size = 0;
+            const bool dest_chunk = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
+            if (dest_chunk) {
+                heap_push(h, size, (uint16_t)((q.tgt_tile_r << 6) | q.tgt_tile_c));
+                s.assigned[q.tgt_tile_r] |= 1ull << q.tgt_tile_c;
+            } else {
+                // carry the shared edge over from the previous chunk's field (field.c:2122-2196)
+                const uint8_t *prev = fields + (size_t)q.prev_index * 4096;
+                bool horizontal; int curr_edge, prev_edge;
+                if (q.prev_chunk_r < q.chunk_r)      { horizontal = false; curr_edge = 0;  prev_edge = 63; }
+                else if (q.prev_chunk_r > q.chunk_r) { horizontal = false; curr_edge = 63; prev_edge = 0;  }
+                else if (q.prev_chunk_c < q.chunk_c) { horizontal = true;  curr_edge = 0;  prev_edge = 63; }
+                else                                 { horizontal = true;  curr_edge = 63; prev_edge = 0;  }
+                for (int e = 0; e < 64; e++) {
+                    const int r = horizontal ? e : curr_edge, c = horizontal ? curr_edge : e;
+                    const uint8_t pv = horizontal ? prev[e * 64 + prev_edge] : prev[prev_edge * 64 + e];
+                    const uint64_t bit = 1ull << c;
+                    // struct assignment overwrites both flags of the edge tile
+                    s.vis[r] = (s.vis[r] & ~bit) | ((pv & 1) ? bit : 0);
+                    s.blk[r] = (s.blk[r] & ~bit) | ((pv & 2) ? bit : 0);
+                    if (pv & 2)
+                        los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
+                                         q.chunk_r, q.chunk_c, r, c);
+                    if ((s.vis[r] >> c) & 1) {
+                        heap_push(h, size, (uint16_t)((r << 6) | c));     // priority 0
+                        s.assigned[r] |= bit;
+                    }
+                }
+            }
+            while (size > 0) {
+                const uint16_t cur = heap_pop(h, size);
+                const int r = (cur >> 6) & 63, c = cur & 63;
+                const uint16_t nprio = (uint16_t)((((cur >> 12) + 1) & 3) << 12);
+                // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0)
+                const int nr[4] = {r - 1, r, r, r + 1}, ncc[4] = {c, c - 1, c + 1, c};
+#pragma unroll 1
+                for (int e = 0; e < 4; e++) {
+                    const int rr = nr[e], cc = ncc[e];
+                    if (rr < 0 || rr > 63 || cc < 0 || cc > 63) continue;
+                    const uint64_t bit = 1ull << cc;
+                    if (s.blk[rr] & bit) continue;
+                    if (!(s.open[rr] & bit)) {
+                        if (!los_is_corner(s, rr, cc)) continue;
+                        los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
+                                         q.chunk_r, q.chunk_c, rr, cc);
+                    } else {
+                        s.vis[rr] |= bit;
+                        if (!(s.assigned[rr] & bit)) {
+                            s.assigned[rr] |= bit;
+                            heap_push(h, size, (uint16_t)(nprio | (rr << 6) | cc));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- field_pad_wavefront (field.c:519): clear `visible` within 1 tile of a blocked tile ----
+        uint8_t *dst = fields + (size_t)i * 4096;
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int row = 2 * lane + rr;
+            uint64_t b = s.blk[row];
+            if (row > 0) b |= s.blk[row - 1];
+            if (row < 63) b |= s.blk[row + 1];
+            b = b | (b << 1) | (b >> 1);
+            const uint64_t v = s.vis[row] & ~b, w = s.blk[row];
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + row * 64);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int sh = j * 16 + e * 4;
+                    o[e] = spread4((uint32_t)(v >> sh)) | (spread4((uint32_t)(w >> sh)) << 1);
+                }
+                d4[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: context + map state
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int make_tensor_maps(pfnav_ctx *ctx)
+{
+    ctx->tma_ok = false;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+    cuuint64_t dims[3] = {(cuuint64_t)ctx->W64, (cuuint64_t)ctx->H64, (cuuint64_t)ctx->nlayers};
+    cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+    cuuint64_t str8[2] = {(cuuint64_t)ctx->W64, (cuuint64_t)ctx->W64 * ctx->H64};
+    cuuint64_t str16[2] = {(cuuint64_t)ctx->W64 * 2, (cuuint64_t)ctx->W64 * ctx->H64 * 2};
+    CUresult r1 = enc(&ctx->tmap_cost, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->d_cost, dims, str8, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&ctx->tmap_blk, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ctx->d_blk, dims, str16, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ctx->tma_ok = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
+    return 0;
+}
+
+extern "C" int pfnav_create(int device, pfnav_ctx **out)
+{
+    if (!out) { pfnav_set_error("pfnav_create: out == NULL"); return PFNAV_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        pfnav_set_error("pfnav_create: no CUDA device (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return PFNAV_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { pfnav_set_error("pfnav_create: device %d out of range", device); return PFNAV_ERR_ARG; }
+    PF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        pfnav_set_error("pfnav_create: device %d is sm_%d%d; libpfnav is built for sm_100a only", device,
+                        prop.major, prop.minor);
+        return PFNAV_ERR_NO_DEVICE;
+    }
+    pfnav_ctx *ctx = new pfnav_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->tick_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->tick_done, cudaEventDisableTiming) != cudaSuccess) {
+        pfnav_set_error("pfnav_create: stream/event creation failed");
+        delete ctx;
+        return PFNAV_ERR_CUDA;
+    }
+    int rc = pfnav_fields_init(ctx);
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return PFNAV_OK;
+}
+
+int pfnav_fields_init(pfnav_ctx *ctx)
+{
+    PF_CUDA(cudaFuncSetAttribute(k_flow_unit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FLOW_WARPS_PER_CTA * FLOW_SMEM_PER_WARP + 128));
+    PF_CUDA(cudaFuncSetAttribute(k_los, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(LOS_WARPS_PER_CTA * sizeof(LosSmem))));
+    return 0;
+}
+
+static void free_map(pfnav_ctx *ctx)
+{
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_blk); cudaFree(ctx->d_liid); cudaFree(ctx->d_unit);
+    ctx->d_cost = nullptr; ctx->d_blk = nullptr; ctx->d_liid = nullptr; ctx->d_unit = nullptr;
+}
+
+void pfnav_fields_free(pfnav_ctx *ctx)
+{
+    free_map(ctx);
+    cudaFree(ctx->d_stage); ctx->d_stage = nullptr;
+    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
+    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
+}
+
+extern "C" void pfnav_destroy(pfnav_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    pfnav_fields_free(ctx);
+    pfnav_agents_free(ctx);
+    if (ctx->tick_done) cudaEventDestroy(ctx->tick_done);
+    if (ctx->tick_stream) cudaStreamDestroy(ctx->tick_stream);
+    delete ctx;
+}
+
+extern "C" int pfnav_set_tma(pfnav_ctx *ctx, int enable)
+{
+    PF_ARG(ctx, "ctx");
+    ctx->use_tma = enable != 0;
+    return PFNAV_OK;
+}
+
+static int ensure_stage(pfnav_ctx *ctx, size_t bytes)
+{
+    if (ctx->stage_bytes >= bytes) return 0;
+    cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr; ctx->stage_bytes = 0;
+    PF_CUDA(cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+    return 0;
+}
+
+extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nlayers, float map_x, float map_z)
+{
+    PF_ARG(ctx, "ctx");
+    PF_ARG(chunk_w > 0 && chunk_h > 0 && chunk_w <= 64 && chunk_h <= 64, "chunk_w/chunk_h must be in 1..64 (dest_id has 6 bits per chunk coordinate, nav.c:841)");
+    PF_ARG(nlayers > 0 && nlayers <= PFNAV_NAV_LAYER_MAX, "nlayers");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    free_map(ctx);
+    ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
+    ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;
+    ctx->map_x = map_x; ctx->map_z = map_z;
+    const size_t tiles = (size_t)ctx->W64 * ctx->H64 * nlayers;
+    PF_CUDA(cudaMalloc(&ctx->d_cost, tiles));
+    PF_CUDA(cudaMalloc(&ctx->d_blk, tiles * 2));
+    PF_CUDA(cudaMalloc(&ctx->d_liid, tiles * 2));
+    PF_CUDA(cudaMalloc(&ctx->d_unit, (size_t)chunk_w * chunk_h * nlayers));
+    PF_CUDA(cudaMemset(ctx->d_cost, 0xFF, tiles));
+    PF_CUDA(cudaMemset(ctx->d_blk, 0, tiles * 2));
+    PF_CUDA(cudaMemset(ctx->d_liid, 0xFF, tiles * 2));
+    PF_CUDA(cudaMemset(ctx->d_unit, 1, (size_t)chunk_w * chunk_h * nlayers));
+    ctx->h_unit.assign((size_t)chunk_w * chunk_h * nlayers, 1);
+    make_tensor_maps(ctx);
+    return PFNAV_OK;
+}
+
+static int refresh_unit_flags(pfnav_ctx *ctx, int layer)
+{
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    k_unit_flags<<<(chunks * 32 + 127) / 128, 128>>>(ctx->d_cost + ltiles * layer, ctx->d_unit + (size_t)chunks * layer,
+                                                     ctx->chunk_w, ctx->chunk_h);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaMemcpy(ctx->h_unit.data() + (size_t)chunks * layer, ctx->d_unit + (size_t)chunks * layer, chunks,
+                       cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *cost_base, const uint16_t *blockers,
+                                      const uint16_t *local_islands)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(cost_base, "cost_base");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    int rc = ensure_stage(ctx, ltiles * 2);
+    if (rc) return rc;
+    const int nblk = std::min<size_t>((ltiles + 255) / 256, 148 * 8);
+    PF_CUDA(cudaMemcpy(ctx->d_stage, cost_base, ltiles, cudaMemcpyHostToDevice));
+    k_deblock<uint8_t><<<nblk, 256>>>((const uint8_t *)ctx->d_stage, ctx->d_cost + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
+    ctx->launches++;
+    if (blockers) {
+        PF_CUDA(cudaMemcpy(ctx->d_stage, blockers, ltiles * 2, cudaMemcpyHostToDevice));
+        k_deblock<uint16_t><<<nblk, 256>>>((const uint16_t *)ctx->d_stage, ctx->d_blk + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
+        ctx->launches++;
+    } else {
+        PF_CUDA(cudaMemset(ctx->d_blk + ltiles * layer, 0, ltiles * 2));
+    }
+    if (local_islands) {
+        PF_CUDA(cudaMemcpy(ctx->d_stage, local_islands, ltiles * 2, cudaMemcpyHostToDevice));
+        k_deblock<uint16_t><<<nblk, 256>>>((const uint16_t *)ctx->d_stage, ctx->d_liid + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
+        ctx->launches++;
+    }
+    PF_CUDA(cudaGetLastError());
+    return refresh_unit_flags(ctx, layer);
+}
+
+extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c, const uint8_t *cost_base,
+                                      const uint16_t *blockers, const uint16_t *local_islands)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk coords");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    const size_t off = ltiles * layer + (size_t)chunk_r * 64 * ctx->W64 + chunk_c * 64;
+    if (cost_base)
+        PF_CUDA(cudaMemcpy2D(ctx->d_cost + off, ctx->W64, cost_base, 64, 64, 64, cudaMemcpyHostToDevice));
+    if (blockers)
+        PF_CUDA(cudaMemcpy2D(ctx->d_blk + off, ctx->W64 * 2, blockers, 128, 128, 64, cudaMemcpyHostToDevice));
+    if (local_islands)
+        PF_CUDA(cudaMemcpy2D(ctx->d_liid + off, ctx->W64 * 2, local_islands, 128, 128, 64, cudaMemcpyHostToDevice));
+    if (cost_base) {
+        bool unit = true;
+        for (int i = 0; i < 4096; i++) unit &= (cost_base[i] == 1 || cost_base[i] == 0xFF);
+        const size_t idx = (size_t)ctx->chunk_w * ctx->chunk_h * layer + chunk_r * ctx->chunk_w + chunk_c;
+        uint8_t u = unit ? 1 : 0;
+        ctx->h_unit[idx] = u;
+        PF_CUDA(cudaMemcpy(ctx->d_unit + idx, &u, 1, cudaMemcpyHostToDevice));
+    }
+    return PFNAV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: flow / LOS batch APIs
+// ------------------------------------------------------------------------------------------
+static FlowGrids grids_of(const pfnav_ctx *ctx)
+{
+    FlowGrids g;
+    g.cost = ctx->d_cost; g.blk = ctx->d_blk; g.liid = ctx->d_liid; g.unit = ctx->d_unit;
+    g.W64 = ctx->W64; g.H64 = ctx->H64; g.chunk_w = ctx->chunk_w; g.chunk_h = ctx->chunk_h;
+    return g;
+}
+
+extern "C" int pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n,
+                                            uint8_t *d_inout_fields, void *stream)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(d_reqs && d_inout_fields, "null buffer");
+    PF_ARG(n < (1u << 30), "n");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const FlowGrids g = grids_of(ctx);
+    // persistent-style grid: a multiple of the SM count (2 CTAs of 8 warps fit per SM)
+    const int ctas_needed = (int)((n + FLOW_WARPS_PER_CTA - 1) / FLOW_WARPS_PER_CTA);
+    const int grid = std::max(1, std::min(ctas_needed, ctx->sm_count * 2 * 4));
+    if (ctx->use_tma && ctx->tma_ok) {
+        const size_t smem = FLOW_WARPS_PER_CTA * FLOW_SMEM_PER_WARP + 128;
+        k_flow_unit<true><<<grid, FLOW_WARPS_PER_CTA * 32, smem, st>>>(ctx->tmap_cost, ctx->tmap_blk, g, d_reqs, (int)n,
+                                                                      d_inout_fields);
+    } else {
+        k_flow_unit<false><<<grid, FLOW_WARPS_PER_CTA * 32, 0, st>>>(ctx->tmap_cost, ctx->tmap_blk, g, d_reqs, (int)n,
+                                                                    d_inout_fields);
+    }
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    bool any_nonunit = false;
+    for (uint8_t u : ctx->h_unit) any_nonunit |= (u == 0);
+    if (any_nonunit) {
+        const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
+        k_flow_general<<<gridg, FLOWG_THREADS, 0, st>>>(g, d_reqs, (int)n, d_inout_fields, 1);
+        ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+    }
+    return PFNAV_OK;
+}
+
+// Test hook: force every request through the general-cost kernel (cross-checks the two paths).
+extern "C" int pfnav_flow_fields_update_general_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n,
+                                                    uint8_t *d_inout_fields, void *stream)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (n == 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
+    k_flow_general<<<gridg, FLOWG_THREADS, 0, (cudaStream_t)stream>>>(grids_of(ctx), d_reqs, (int)n, d_inout_fields, 0);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFNAV_OK;
+}
+
+static int validate_field_reqs(const pfnav_ctx *ctx, const pfnav_field_req *reqs, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        const pfnav_field_req &q = reqs[i];
+        PF_ARG(q.layer >= 0 && q.layer < ctx->nlayers, "field req: layer");
+        PF_ARG(q.chunk_r >= 0 && q.chunk_r < ctx->chunk_h && q.chunk_c >= 0 && q.chunk_c < ctx->chunk_w, "field req: chunk");
+        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE, "field req: faction-aware (attacking) fields are not implemented");
+        if (q.target_type == PFNAV_TARGET_TILE) {
+            PF_ARG(q.tile_r >= 0 && q.tile_r < 64 && q.tile_c >= 0 && q.tile_c < 64, "field req: tile");
+        } else if (q.target_type == PFNAV_TARGET_PORTAL) {
+            PF_ARG(q.port_r0 >= 0 && q.port_r0 <= q.port_r1 && q.port_r1 < 64 && q.port_c0 >= 0 && q.port_c0 <= q.port_c1 && q.port_c1 < 64, "field req: portal endpoints");
+            PF_ARG(q.next_r0 >= 0 && q.next_r0 <= q.next_r1 && q.next_r1 < 64 && q.next_c0 >= 0 && q.next_c0 <= q.next_c1 && q.next_c1 < 64, "field req: next endpoints");
+            PF_ARG(abs(q.next_chunk_r - q.chunk_r) + abs(q.next_chunk_c - q.chunk_c) == 1, "field req: next chunk must be adjacent");
+        } else {
+            PF_ARG(false, "field req: target_type");
+        }
+    }
+    return 0;
+}
+
+extern "C" int pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *reqs, size_t n, uint8_t *inout_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(reqs && inout_fields, "null buffer");
+    int rc = validate_field_reqs(ctx, reqs, n);
+    if (rc) return rc;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    pfnav_field_req *d_reqs = nullptr;
+    uint8_t *d_fields = nullptr;
+    PF_CUDA(cudaMalloc(&d_reqs, n * sizeof(pfnav_field_req)));
+    if (cudaMalloc(&d_fields, n * 4096) != cudaSuccess) { cudaFree(d_reqs); pfnav_set_error("cudaMalloc fields"); return PFNAV_ERR_NOMEM; }
+    cudaStream_t st = ctx->tick_stream;
+    bool need_in = false;
+    for (size_t i = 0; i < n; i++) need_in |= (reqs[i].init == 0);
+    cudaError_t e = cudaMemcpyAsync(d_reqs, reqs, n * sizeof(pfnav_field_req), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && need_in) e = cudaMemcpyAsync(d_fields, inout_fields, n * 4096, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = pfnav_flow_fields_update_dev(ctx, d_reqs, n, d_fields, st);
+        if (rc == 0) e = cudaMemcpyAsync(inout_fields, d_fields, n * 4096, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_reqs); cudaFree(d_fields);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_flow_fields_update: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_los_fields_create_dev(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint8_t *d_out_fields,
+                                           int n_waves, const int32_t *h_wave_offsets, void *stream)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(d_reqs && d_out_fields && n_waves >= 1 && h_wave_offsets, "null buffer");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const FlowGrids g = grids_of(ctx);
+    LosMapInfo mi{ctx->map_x, ctx->map_z};
+    const size_t smem = LOS_WARPS_PER_CTA * sizeof(LosSmem);
+    for (int w = 0; w < n_waves; w++) {
+        const int first = h_wave_offsets[w], cnt = h_wave_offsets[w + 1] - first;
+        if (cnt <= 0) continue;
+        const int grid = std::max(1, std::min((cnt + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA, ctx->sm_count * 5 * 4));
+        k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(g, mi, d_reqs, first, cnt, d_out_fields);
+        ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+    }
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs, size_t n, uint8_t *out_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(reqs && out_fields, "null buffer");
+    // dependency depth = wave; requests are re-ordered wave-major on the device side
+    std::vector<int> depth(n, 0), order(n), newidx(n);
+    int maxd = 0;
+    for (size_t i = 0; i < n; i++) {
+        const pfnav_los_req &q = reqs[i];
+        PF_ARG(q.layer >= 0 && q.layer < ctx->nlayers, "los req: layer");
+        PF_ARG(q.chunk_r >= 0 && q.chunk_r < ctx->chunk_h && q.chunk_c >= 0 && q.chunk_c < ctx->chunk_w, "los req: chunk");
+        PF_ARG(q.tgt_chunk_r >= 0 && q.tgt_chunk_r < ctx->chunk_h && q.tgt_chunk_c >= 0 && q.tgt_chunk_c < ctx->chunk_w, "los req: target chunk");
+        PF_ARG(q.tgt_tile_r >= 0 && q.tgt_tile_r < 64 && q.tgt_tile_c >= 0 && q.tgt_tile_c < 64, "los req: target tile");
+        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE, "los req: faction-aware fields are not implemented");
+        const bool dest = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
+        if (dest) { PF_ARG(q.prev_index < 0, "los req: destination chunk must not name a prev field"); }
+        else {
+            PF_ARG(q.prev_index >= 0 && (size_t)q.prev_index < i, "los req: prev_index must name an earlier request");
+            PF_ARG(abs(q.prev_chunk_r - q.chunk_r) + abs(q.prev_chunk_c - q.chunk_c) == 1, "los req: prev chunk must be adjacent");
+            depth[i] = depth[q.prev_index] + 1;
+            maxd = std::max(maxd, depth[i]);
+        }
+    }
+    std::vector<int32_t> wave_off(maxd + 2, 0);
+    for (size_t i = 0; i < n; i++) wave_off[depth[i] + 1]++;
+    for (int w = 0; w <= maxd; w++) wave_off[w + 1] += wave_off[w];
+    std::vector<int32_t> cursor(wave_off.begin(), wave_off.end() - 1);
+    for (size_t i = 0; i < n; i++) { newidx[i] = cursor[depth[i]]++; order[newidx[i]] = (int)i; }
+    std::vector<pfnav_los_req> sorted(n);
+    for (size_t k = 0; k < n; k++) {
+        sorted[k] = reqs[order[k]];
+        if (sorted[k].prev_index >= 0) sorted[k].prev_index = newidx[sorted[k].prev_index];
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    pfnav_los_req *d_reqs = nullptr;
+    uint8_t *d_fields = nullptr;
+    PF_CUDA(cudaMalloc(&d_reqs, n * sizeof(pfnav_los_req)));
+    if (cudaMalloc(&d_fields, n * 4096) != cudaSuccess) { cudaFree(d_reqs); pfnav_set_error("cudaMalloc fields"); return PFNAV_ERR_NOMEM; }
+    cudaStream_t st = ctx->tick_stream;
+    std::vector<uint8_t> tmp(n * 4096);
+    cudaError_t e = cudaMemcpyAsync(d_reqs, sorted.data(), n * sizeof(pfnav_los_req), cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        rc = pfnav_los_fields_create_dev(ctx, d_reqs, n, d_fields, maxd + 1, wave_off.data(), st);
+        if (rc == 0) e = cudaMemcpyAsync(tmp.data(), d_fields, n * 4096, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_reqs); cudaFree(d_fields);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_los_fields_create: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    for (size_t k = 0; k < n; k++) memcpy(out_fields + (size_t)order[k] * 4096, tmp.data() + k * 4096, 4096);
+    return PFNAV_OK;
+}

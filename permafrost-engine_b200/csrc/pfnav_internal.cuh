@@ -1,0 +1,103 @@
+// pfnav_internal.cuh -- shared declarations of libpfnav.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/pfnav.h"
+
+#define PFNAV_VERSION 100
+
+void pfnav_set_error(const char *fmt, ...);
+
+#define PF_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            pfnav_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                   \
+                            cudaGetErrorString(_e));                                        \
+            return PFNAV_ERR_CUDA;                                                          \
+        }                                                                                   \
+    } while (0)
+
+#define PF_ARG(cond, msg)                                                                   \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            pfnav_set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, msg);            \
+            return PFNAV_ERR_ARG;                                                           \
+        }                                                                                   \
+    } while (0)
+
+// 24-byte neighbour record: exactly what one agent needs to know about another
+// (SURVEY.md 8e). This is also the unit of the per-tick NCCL all-gather.
+struct __align__(8) pf_record {
+    float    px, pz;
+    float    vx, vz;
+    float    radius;
+    uint32_t state_flags;     // state << 24 | (flags & 0xFFFFFF)
+};
+static_assert(sizeof(pf_record) == 24, "pf_record must be 24 bytes");
+
+struct pfnav_ctx {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    bool use_tma = true;
+    bool tma_ok = false;
+
+    // ---- map state (row-major images per layer: [layer][H*64][W*64]) ----
+    int chunk_w = 0, chunk_h = 0, nlayers = 0;
+    int W64 = 0, H64 = 0;
+    float map_x = 0.f, map_z = 0.f;
+    uint8_t  *d_cost = nullptr;      // u8
+    uint16_t *d_blk = nullptr;       // u16 blockers refcounts
+    uint16_t *d_liid = nullptr;      // u16 local islands
+    uint8_t  *d_unit = nullptr;      // [layer][chunk] 1 if every passable cost in the chunk == 1
+    std::vector<uint8_t> h_unit;     // host mirror
+    CUtensorMap tmap_cost, tmap_blk; // rank-3 {x, y, layer}, box 64x64x1
+    void *d_stage = nullptr; size_t stage_bytes = 0;   // upload staging
+
+    // ---- field pool ----
+    int pool_ndests = 0, pool_max = 0, pool_used = 0;
+    int32_t *d_pool_slot = nullptr;   // [ndests][chunks] -> slot or -1
+    std::vector<int32_t> h_pool_slot;
+    uint8_t *d_pool_flow = nullptr;   // [max][4096]
+    uint8_t *d_pool_los = nullptr;    // [max][4096]
+
+    // ---- agents ----
+    size_t n_agents = 0, cap_agents = 0, n_flocks = 0, cap_flocks = 0;
+    int hz = 20;
+    pfnav_agent *d_agents = nullptr;      // AoS input as uploaded
+    pf_record   *d_records = nullptr;     // 24-B records (uid order)
+    pfnav_flock *d_flocks = nullptr;
+    uint32_t *d_flock_start = nullptr;    // [nflocks+1] offsets into d_flock_members
+    uint32_t *d_flock_members = nullptr;  // agent ids grouped by flock, ascending uid
+    float2   *d_cohesion = nullptr;       // per-agent cohesion force (pre-pass)
+    // spatial index (bitmap_grid.h equivalent)
+    int grid_w = 0, grid_h = 0; int32_t origin_x = 0, origin_y = 0;
+    uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
+    size_t cap_cells = 0;
+    int32_t  *d_sorted_ix = nullptr, *d_sorted_iy = nullptr;
+    uint32_t *d_sorted_id = nullptr;
+    void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+    // work list + outputs
+    size_t n_work = 0, cap_work = 0;
+    uint32_t *d_work = nullptr;
+    float2 *d_vel_out = nullptr, *d_vpref_out = nullptr, *d_vdes_out = nullptr;
+    uint8_t *d_los_out = nullptr;
+    uint32_t *d_work_count = nullptr;
+    cudaStream_t tick_stream = nullptr;
+    cudaEvent_t tick_done = nullptr;
+};
+
+// ---- pfnav_fields.cu ----
+int pfnav_fields_init(pfnav_ctx *ctx);
+void pfnav_fields_free(pfnav_ctx *ctx);
+
+// ---- pfnav_agents.cu ----
+void pfnav_agents_free(pfnav_ctx *ctx);
+
+// ---- device helpers shared by kernels ----
+__device__ __forceinline__ uint32_t pf_lane() { return threadIdx.x & 31; }
