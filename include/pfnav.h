@@ -87,6 +87,19 @@ int  pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c,
                             const uint8_t *cost_base, const uint16_t *blockers,
                             const uint16_t *local_islands);
 
+/* Structural part of N_NewCtxForMapData for one layer (nav.c:2284), computed on the host from the
+ * uploaded cost_base + blockers: local islands (n_update_local_islands, nav.c:967: ids from 1 in
+ * row-major discovery order) and the portal table (n_create_portals / n_link_chunks, nav.c:563,
+ * 477: identical indices and endpoints). The islands are pushed to the device. */
+int  pfnav_map_build_nav(pfnav_ctx *ctx, int layer);
+/* n_update_dirty_local_islands (nav.c:986) for one chunk after pfnav_map_update_chunk changed
+ * its blockers; pushes the refreshed islands to the device. */
+int  pfnav_map_refresh_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c);
+/* Read back: local islands ([chunk][64][64] u16) and portals (10 ints per portal: chunk_r, chunk_c,
+ * index, endpoints[0].r/.c, endpoints[1].r/.c, connected chunk index, connected portal index, 0). */
+int  pfnav_local_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out);
+int  pfnav_portals_get(pfnav_ctx *ctx, int layer, int32_t *out, int maxout, int *out_n);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Flow fields + LOS fields (seam B2: src/navigation/field.h:115-202)
  * ---------------------------------------------------------------------------------------- */
@@ -141,6 +154,20 @@ int  pfnav_los_fields_create_dev(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, si
                                  uint8_t *d_out_fields, int n_waves, const int32_t *h_wave_offsets,
                                  void *stream);
 
+/* Goal planner (the request-generation half of n_request_path, nav.c:1774-2047): emits, for every
+ * chunk connected to the goal tile, the TARGET_TILE / TARGET_PORTAL flow request and the chained
+ * LOS request that guide agents there. Breadth-first over (chunk, local island) nodes, i.e. it
+ * minimises portal hops rather than AStar_PortalGraphPath's travel cost (a_star.c:429).
+ *   flow_chunk[i] / los_chunk[i] : chunk index (r*chunk_w+c) a request's output belongs to
+ *   flow_wave[i]                 : 0 for a chunk's first request (init=1); k>0 for the k-th further
+ *                                  target merged into the same field (init=0, nav.c:1998-2008);
+ *                                  wave k must run after wave k-1 on that chunk's field.
+ *   los requests are emitted parent-before-child with prev_index into los_out. */
+int  pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r,
+                     int tgt_tile_c, pfnav_field_req *flow_out, int32_t *flow_chunk,
+                     int32_t *flow_wave, int max_flow, int *n_flow, pfnav_los_req *los_out,
+                     int32_t *los_chunk, int max_los, int *n_los);
+
 /* Selects how the 64x64 tiles are staged into shared memory: 1 = TMA tensor maps
  * (cp.async.bulk.tensor), 0 = plain coalesced loads. Default 1. */
 int  pfnav_set_tma(pfnav_ctx *ctx, int enable);
@@ -157,6 +184,12 @@ int  pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields);
 int  pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c,
                     const uint8_t *flow_field, const uint8_t *los_field);
 int  pfnav_pool_clear(pfnav_ctx *ctx);
+/* N_RequestPath's field-building half (nav.c:1819-2042), resident on the device: plan the goal
+ * (pfnav_plan_goal), then run the flow waves and the LOS chain straight into the pool slots of
+ * destination `dest`. No field bytes cross PCIe. Launches are asynchronous on `stream`. */
+int  pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_r, int tgt_chunk_c,
+                             int tgt_tile_r, int tgt_tile_c, void *stream, int *out_n_flow,
+                             int *out_n_los);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls
@@ -235,6 +268,13 @@ int  pfnav_ents_in_circle(pfnav_ctx *ctx, float x, float z, float range, uint32_
 int  pfnav_agents_device_ptrs(pfnav_ctx *ctx, void **d_records, void **d_velocities, size_t *n);
 /* Re-build the spatial index from the (externally updated, e.g. all-gathered) record array. */
 int  pfnav_agents_rebuild_index(pfnav_ctx *ctx, void *stream);
+
+/* Optional per-kernel-group device timing (CUDA events on the launching stream) used by bench.py
+ * for its roofline line. pfnav_profile_read drains the recorded intervals: ms_out / count_out have
+ * 8 entries: 0 flow kernels, 1 LOS kernels, 2 spatial-index build, 3 desired velocity, 4 cohesion,
+ * 5 agent velocity (ClearPath). */
+int  pfnav_profile_enable(pfnav_ctx *ctx, int enable);
+int  pfnav_profile_read(pfnav_ctx *ctx, float *ms_out, uint32_t *count_out);
 
 /* Number of kernels launched by this context since creation (bench `gpu_launches`). */
 uint64_t pfnav_launch_count(const pfnav_ctx *ctx);

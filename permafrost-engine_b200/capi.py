@@ -44,12 +44,14 @@ FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 
 # every symbol include/pfnav.h declares
 SYMBOLS = [
     "pfnav_last_error", "pfnav_version", "pfnav_create", "pfnav_destroy", "pfnav_map_create",
-    "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_flow_fields_update",
+    "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_map_build_nav", "pfnav_map_refresh_chunk",
+    "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_plan_goal", "pfnav_flow_fields_update",
     "pfnav_flow_fields_update_dev", "pfnav_los_fields_create", "pfnav_los_fields_create_dev",
-    "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear",
+    "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear", "pfnav_pool_request_goal",
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
-    "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count",
+    "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
+    "pfnav_profile_read",
 ]
 
 _lib = None
@@ -76,6 +78,12 @@ def load():
     L.pfnav_map_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
     L.pfnav_map_upload_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pfnav_map_build_nav.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_map_refresh_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.pfnav_local_islands_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pfnav_portals_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.pfnav_plan_goal.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.pfnav_flow_fields_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_flow_fields_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.pfnav_flow_fields_update_general_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -85,6 +93,7 @@ def load():
     L.pfnav_pool_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.pfnav_pool_put.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.pfnav_pool_clear.argtypes = [C.c_void_p]
+    L.pfnav_pool_request_goal.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_agents_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     L.pfnav_agents_set_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_agents_tick.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -93,6 +102,8 @@ def load():
     L.pfnav_ents_in_circle.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.pfnav_agents_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.pfnav_agents_rebuild_index.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -179,6 +190,34 @@ class Nav:
         c = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
         _chk(self.L.pfnav_map_update_chunk(self.h, layer, chunk[0], chunk[1], _p(a), _p(b), _p(c)))
 
+    def map_build_nav(self, layer=0):
+        _chk(self.L.pfnav_map_build_nav(self.h, layer))
+
+    def map_refresh_chunk(self, layer, chunk):
+        _chk(self.L.pfnav_map_refresh_chunk(self.h, layer, chunk[0], chunk[1]))
+
+    def local_islands(self, layer=0):
+        out = np.zeros((self.cw * self.ch, 64, 64), np.uint16)
+        _chk(self.L.pfnav_local_islands_get(self.h, layer, _p(out)))
+        return out
+
+    def portals(self, layer=0):
+        n = C.c_int(0)
+        _chk(self.L.pfnav_portals_get(self.h, layer, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 10), np.int32)
+        _chk(self.L.pfnav_portals_get(self.h, layer, _p(out), n.value, C.byref(n)))
+        return out
+
+    def plan_goal(self, target_td, layer=0):
+        """-> (flow_reqs, flow_chunk, flow_wave, los_reqs, los_chunk)"""
+        cap = self.cw * self.ch * 8 + 8
+        fr = np.zeros(cap, FIELD_REQ); fc = np.zeros(cap, np.int32); fw = np.zeros(cap, np.int32)
+        lr = np.zeros(cap, LOS_REQ); lc = np.zeros(cap, np.int32)
+        nf, nl = C.c_int(0), C.c_int(0)
+        _chk(self.L.pfnav_plan_goal(self.h, layer, target_td[0], target_td[1], target_td[2], target_td[3],
+                                    _p(fr), _p(fc), _p(fw), cap, C.byref(nf), _p(lr), _p(lc), cap, C.byref(nl)))
+        return fr[:nf.value].copy(), fc[:nf.value].copy(), fw[:nf.value].copy(), lr[:nl.value].copy(), lc[:nl.value].copy()
+
     def set_tma(self, enable):
         _chk(self.L.pfnav_set_tma(self.h, int(enable)))
 
@@ -217,6 +256,12 @@ class Nav:
 
     def pool_clear(self):
         _chk(self.L.pfnav_pool_clear(self.h))
+
+    def pool_request_goal(self, dest, target_td, layer=0, stream=0):
+        nf, nl = C.c_int(0), C.c_int(0)
+        _chk(self.L.pfnav_pool_request_goal(self.h, dest, layer, target_td[0], target_td[1], target_td[2],
+                                            target_td[3], C.c_void_p(stream), C.byref(nf), C.byref(nl)))
+        return nf.value, nl.value
 
     # ---- agents ----
     def agents_upload(self, agents, flocks, hz=20):
@@ -262,6 +307,16 @@ class Nav:
 
     def agents_rebuild_index(self, stream=0):
         _chk(self.L.pfnav_agents_rebuild_index(self.h, C.c_void_p(stream)))
+
+    def profile_enable(self, on=True):
+        _chk(self.L.pfnav_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """-> dict name -> (total_ms, launches_groups)"""
+        ms = np.zeros(8, np.float32); cnt = np.zeros(8, np.uint32)
+        _chk(self.L.pfnav_profile_read(self.h, _p(ms), _p(cnt)))
+        names = ["flow", "los", "index", "vdes", "cohesion", "velocity"]
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(names)}
 
     def launch_count(self):
         return int(self.L.pfnav_launch_count(self.h))

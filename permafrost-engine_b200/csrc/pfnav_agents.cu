@@ -830,6 +830,7 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, nslots * sizeof(int32_t)));
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)max_fields * 4096, 0, max_fields));
     ctx->h_pool_slot.assign(nslots, -1);
+    ctx->h_pool_has.assign(max_fields, 0);
     ctx->pool_ndests = ndests; ctx->pool_max = max_fields; ctx->pool_used = 0;
     return PFNAV_OK;
 }
@@ -841,6 +842,7 @@ extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
     PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, ctx->h_pool_slot.size() * sizeof(int32_t)));
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, 0, ctx->pool_max));
     std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
+    std::fill(ctx->h_pool_has.begin(), ctx->h_pool_has.end(), 0);
     ctx->pool_used = 0;
     return PFNAV_OK;
 }
@@ -854,18 +856,17 @@ extern "C" int pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
     PF_CUDA(cudaSetDevice(ctx->device));
     const size_t si = (size_t)dest * ctx->chunk_w * ctx->chunk_h + chunk_r * ctx->chunk_w + chunk_c;
     int slot = ctx->h_pool_slot[si];
-    uint8_t has = 0;
     uint8_t *d_has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096;
     if (slot < 0) {
         if (ctx->pool_used >= ctx->pool_max) { pfnav_set_error("pfnav_pool_put: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
         slot = ctx->pool_used++;
         ctx->h_pool_slot[si] = slot;
         PF_CUDA(cudaMemcpy(ctx->d_pool_slot + si, &slot, sizeof(int32_t), cudaMemcpyHostToDevice));
-    } else {
-        PF_CUDA(cudaMemcpy(&has, d_has + slot, 1, cudaMemcpyDeviceToHost));
     }
+    uint8_t has = ctx->h_pool_has[slot];
     if (flow_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_flow + (size_t)slot * 4096, flow_field, 4096, cudaMemcpyHostToDevice)); has |= 1; }
     if (los_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)slot * 4096, los_field, 4096, cudaMemcpyHostToDevice)); has |= 2; }
+    ctx->h_pool_has[slot] = has;
     PF_CUDA(cudaMemcpy(d_has + slot, &has, 1, cudaMemcpyHostToDevice));
     return PFNAV_OK;
 }
@@ -894,6 +895,7 @@ static int build_index(pfnav_ctx *ctx, cudaStream_t st)
 {
     const int n = (int)ctx->n_agents;
     const int ncells = ctx->grid_w * ctx->grid_h;
+    pf_prof_scope prof(ctx, st, PF_PROF_INDEX);
     PF_CUDA(cudaMemsetAsync(ctx->d_cell_count, 0, (size_t)ncells * 4, st));
     PF_CUDA(cudaMemsetAsync(ctx->d_cell_fill, 0, (size_t)ncells * 4, st));
     if (n > 0) {
@@ -1067,6 +1069,8 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     tp.scaled_max_force_d = (double)(0.75f / (float)ctx->hz) * 20.0;
     tp.scaled_max_force = (float)tp.scaled_max_force_d;
     PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
+    {
+    pf_prof_scope prof(ctx, st, PF_PROF_VDES);
     if (flags & PFNAV_TICK_VDES_FROM_POOL) {
         PF_ARG(ctx->d_pool_slot, "PFNAV_TICK_VDES_FROM_POOL needs a field pool");
         PoolView pv;
@@ -1077,14 +1081,20 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     } else {
         k_copy_vdes<<<(nwork + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out);
     }
+    }
+    {
+    pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
     k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
                                                    ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
+    }
+    pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
     const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
     k_agent_velocity<<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                              ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
                                                              ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out);
     ctx->launches += 3;
     PF_CUDA(cudaGetLastError());
+    prof.~pf_prof_scope(); prof.a = nullptr;
     PF_CUDA(cudaEventRecord(ctx->tick_done, st));
     return PFNAV_OK;
 }

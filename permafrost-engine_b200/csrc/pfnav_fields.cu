@@ -344,7 +344,8 @@ __device__ __forceinline__ void store_row(uint8_t *dst_row, uint64_t b0, uint64_
 template <bool USE_TMA>
 __global__ void __launch_bounds__(FLOW_WARPS_PER_CTA * 32)
 k_flow_unit(const __grid_constant__ CUtensorMap tm_cost, const __grid_constant__ CUtensorMap tm_blk, FlowGrids g,
-            const pfnav_field_req *__restrict__ reqs, int n, uint8_t *__restrict__ fields)
+            const pfnav_field_req *__restrict__ reqs, int n, uint8_t *__restrict__ fields,
+            const int32_t *__restrict__ out_slot)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -446,7 +447,7 @@ k_flow_unit(const __grid_constant__ CUtensorMap tm_cost, const __grid_constant__
             if (code & 4) { D02 |= S0; D12 |= S1; }
         }
 
-        uint8_t *dst = fields + (size_t)i * 4096 + lane * 128;
+        uint8_t *dst = fields + (size_t)(out_slot ? out_slot[i] : i) * 4096 + lane * 128;
         store_row(dst, D00, D01, D02, D03, V0, q.init != 0);
         store_row(dst + 64, D10, D11, D12, D13, V1, q.init != 0);
     }
@@ -458,7 +459,7 @@ k_flow_unit(const __grid_constant__ CUtensorMap tm_cost, const __grid_constant__
 #define FLOWG_THREADS 128
 __global__ void __launch_bounds__(FLOWG_THREADS)
 k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uint8_t *__restrict__ fields,
-               int only_nonunit)
+               const int32_t *__restrict__ out_slot, int only_nonunit)
 {
     __shared__ uint32_t dist[4096];
     __shared__ uint8_t cost[4096];       // 0xFF = impassable or blocked
@@ -533,7 +534,7 @@ k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uin
         const bool up = q.next_chunk_r < q.chunk_r, down = q.next_chunk_r > q.chunk_r;
         const bool left = q.next_chunk_c < q.chunk_c;
         const uint8_t fix = up ? 2 : down ? 7 : left ? 4 : 5;
-        uint8_t *dst = fields + (size_t)i * 4096;
+        uint8_t *dst = fields + (size_t)(out_slot ? out_slot[i] : i) * 4096;
         for (int t = tid; t < 4096; t += FLOWG_THREADS) {
             const uint32_t d = dist[t];
             if (d == 0xFFFFFFFFu) { if (q.init) dst[t] = 0; continue; }
@@ -652,7 +653,7 @@ __device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
 
 __global__ void __launch_bounds__(LOS_WARPS_PER_CTA * 32)
 k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int first, int n,
-      uint8_t *fields)
+      uint8_t *fields, const int32_t *__restrict__ out_slot)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,7 +703,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
                 s.assigned[q.tgt_tile_r] |= 1ull << q.tgt_tile_c;
             } else {
                 // carry the shared edge over from the previous chunk's field (field.c:2122-2196)
-                const uint8_t *prev = fields + (size_t)q.prev_index * 4096;
+                const uint8_t *prev = fields + (size_t)(out_slot ? out_slot[q.prev_index] : q.prev_index) * 4096;
                 bool horizontal; int curr_edge, prev_edge;
                 if (q.prev_chunk_r < q.chunk_r)      { horizontal = false; curr_edge = 0;  prev_edge = 63; }
                 else if (q.prev_chunk_r > q.chunk_r) { horizontal = false; curr_edge = 63; prev_edge = 0;  }
@@ -752,7 +753,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
         }
         __syncwarp();
         // ---- field_pad_wavefront (field.c:519): clear `visible` within 1 tile of a blocked tile ----
-        uint8_t *dst = fields + (size_t)i * 4096;
+        uint8_t *dst = fields + (size_t)(out_slot ? out_slot[i] : i) * 4096;
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             const int row = 2 * lane + rr;
@@ -881,6 +882,31 @@ extern "C" void pfnav_destroy(pfnav_ctx *ctx)
     delete ctx;
 }
 
+// Per-kernel-group device timings, for bench.py's roofline line. ms_out/count_out: PF_PROF_SLOTS (8)
+// entries: 0 flow, 1 LOS, 2 index build, 3 desired velocity, 4 cohesion, 5 agent velocity.
+extern "C" int pfnav_profile_enable(pfnav_ctx *ctx, int enable)
+{
+    PF_ARG(ctx, "ctx");
+    ctx->profiling = enable != 0;
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_profile_read(pfnav_ctx *ctx, float *ms_out, uint32_t *count_out)
+{
+    PF_ARG(ctx && ms_out && count_out, "args");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < PF_PROF_SLOTS; i++) { ms_out[i] = 0.f; count_out[i] = 0; }
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_out[r.slot] += ms; count_out[r.slot]++; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    ctx->prof_pending.clear();
+    cudaGetLastError();
+    return PFNAV_OK;
+}
+
 extern "C" int pfnav_set_tma(pfnav_ctx *ctx, int enable)
 {
     PF_ARG(ctx, "ctx");
@@ -918,6 +944,10 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     PF_CUDA(cudaMemset(ctx->d_liid, 0xFF, tiles * 2));
     PF_CUDA(cudaMemset(ctx->d_unit, 1, (size_t)chunk_w * chunk_h * nlayers));
     ctx->h_unit.assign((size_t)chunk_w * chunk_h * nlayers, 1);
+    ctx->h_cost.assign(tiles, 0xFF);
+    ctx->h_blk.assign(tiles, 0);
+    ctx->h_liid.assign(tiles, 0xFFFF);
+    ctx->portals.assign(nlayers, {});
     make_tensor_maps(ctx);
     return PFNAV_OK;
 }
@@ -946,6 +976,10 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     int rc = ensure_stage(ctx, ltiles * 2);
     if (rc) return rc;
     const int nblk = std::min<size_t>((ltiles + 255) / 256, 148 * 8);
+    memcpy(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);
+    if (blockers) memcpy(ctx->h_blk.data() + ltiles * layer, blockers, ltiles * 2);
+    else std::fill(ctx->h_blk.begin() + ltiles * layer, ctx->h_blk.begin() + ltiles * (layer + 1), 0);
+    if (local_islands) memcpy(ctx->h_liid.data() + ltiles * layer, local_islands, ltiles * 2);
     PF_CUDA(cudaMemcpy(ctx->d_stage, cost_base, ltiles, cudaMemcpyHostToDevice));
     k_deblock<uint8_t><<<nblk, 256>>>((const uint8_t *)ctx->d_stage, ctx->d_cost + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
     ctx->launches++;
@@ -974,6 +1008,10 @@ extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, in
     PF_CUDA(cudaSetDevice(ctx->device));
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     const size_t off = ltiles * layer + (size_t)chunk_r * 64 * ctx->W64 + chunk_c * 64;
+    const size_t hoff = ltiles * layer + ((size_t)chunk_r * ctx->chunk_w + chunk_c) * 4096;
+    if (cost_base) memcpy(ctx->h_cost.data() + hoff, cost_base, 4096);
+    if (blockers) memcpy(ctx->h_blk.data() + hoff, blockers, 8192);
+    if (local_islands) memcpy(ctx->h_liid.data() + hoff, local_islands, 8192);
     if (cost_base)
         PF_CUDA(cudaMemcpy2D(ctx->d_cost + off, ctx->W64, cost_base, 64, 64, 64, cudaMemcpyHostToDevice));
     if (blockers)
@@ -1002,8 +1040,17 @@ static FlowGrids grids_of(const pfnav_ctx *ctx)
     return g;
 }
 
+int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, uint8_t *d_inout_fields,
+                      const int32_t *d_out_slot, void *stream);
+
 extern "C" int pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n,
                                             uint8_t *d_inout_fields, void *stream)
+{
+    return pfnav_flow_launch(ctx, d_reqs, n, d_inout_fields, nullptr, stream);
+}
+
+int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, uint8_t *d_inout_fields,
+                      const int32_t *d_out_slot, void *stream)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
     if (n == 0) return PFNAV_OK;
@@ -1012,16 +1059,17 @@ extern "C" int pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_re
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const FlowGrids g = grids_of(ctx);
+    pf_prof_scope prof(ctx, st, PF_PROF_FLOW);
     // persistent-style grid: a multiple of the SM count (2 CTAs of 8 warps fit per SM)
     const int ctas_needed = (int)((n + FLOW_WARPS_PER_CTA - 1) / FLOW_WARPS_PER_CTA);
     const int grid = std::max(1, std::min(ctas_needed, ctx->sm_count * 2 * 4));
     if (ctx->use_tma && ctx->tma_ok) {
         const size_t smem = FLOW_WARPS_PER_CTA * FLOW_SMEM_PER_WARP + 128;
         k_flow_unit<true><<<grid, FLOW_WARPS_PER_CTA * 32, smem, st>>>(ctx->tmap_cost, ctx->tmap_blk, g, d_reqs, (int)n,
-                                                                      d_inout_fields);
+                                                                      d_inout_fields, d_out_slot);
     } else {
         k_flow_unit<false><<<grid, FLOW_WARPS_PER_CTA * 32, 0, st>>>(ctx->tmap_cost, ctx->tmap_blk, g, d_reqs, (int)n,
-                                                                    d_inout_fields);
+                                                                    d_inout_fields, d_out_slot);
     }
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -1029,7 +1077,7 @@ extern "C" int pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_re
     for (uint8_t u : ctx->h_unit) any_nonunit |= (u == 0);
     if (any_nonunit) {
         const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
-        k_flow_general<<<gridg, FLOWG_THREADS, 0, st>>>(g, d_reqs, (int)n, d_inout_fields, 1);
+        k_flow_general<<<gridg, FLOWG_THREADS, 0, st>>>(g, d_reqs, (int)n, d_inout_fields, d_out_slot, 1);
         ctx->launches++;
         PF_CUDA(cudaGetLastError());
     }
@@ -1044,7 +1092,7 @@ extern "C" int pfnav_flow_fields_update_general_dev(pfnav_ctx *ctx, const pfnav_
     if (n == 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
     const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
-    k_flow_general<<<gridg, FLOWG_THREADS, 0, (cudaStream_t)stream>>>(grids_of(ctx), d_reqs, (int)n, d_inout_fields, 0);
+    k_flow_general<<<gridg, FLOWG_THREADS, 0, (cudaStream_t)stream>>>(grids_of(ctx), d_reqs, (int)n, d_inout_fields, nullptr, 0);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFNAV_OK;
@@ -1101,8 +1149,17 @@ extern "C" int pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *r
     return PFNAV_OK;
 }
 
+int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint8_t *d_out_fields,
+                     const int32_t *d_out_slot, int n_waves, const int32_t *h_wave_offsets, void *stream);
+
 extern "C" int pfnav_los_fields_create_dev(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint8_t *d_out_fields,
                                            int n_waves, const int32_t *h_wave_offsets, void *stream)
+{
+    return pfnav_los_launch(ctx, d_reqs, n, d_out_fields, nullptr, n_waves, h_wave_offsets, stream);
+}
+
+int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint8_t *d_out_fields,
+                     const int32_t *d_out_slot, int n_waves, const int32_t *h_wave_offsets, void *stream)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
     if (n == 0) return PFNAV_OK;
@@ -1111,11 +1168,12 @@ extern "C" int pfnav_los_fields_create_dev(pfnav_ctx *ctx, const pfnav_los_req *
     const FlowGrids g = grids_of(ctx);
     LosMapInfo mi{ctx->map_x, ctx->map_z};
     const size_t smem = LOS_WARPS_PER_CTA * sizeof(LosSmem);
+    pf_prof_scope prof(ctx, (cudaStream_t)stream, PF_PROF_LOS);
     for (int w = 0; w < n_waves; w++) {
         const int first = h_wave_offsets[w], cnt = h_wave_offsets[w + 1] - first;
         if (cnt <= 0) continue;
         const int grid = std::max(1, std::min((cnt + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA, ctx->sm_count * 5 * 4));
-        k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(g, mi, d_reqs, first, cnt, d_out_fields);
+        k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(g, mi, d_reqs, first, cnt, d_out_fields, d_out_slot);
         ctx->launches++;
         PF_CUDA(cudaGetLastError());
     }

@@ -58,11 +58,18 @@ struct pfnav_ctx {
     std::vector<uint8_t> h_unit;     // host mirror
     CUtensorMap tmap_cost, tmap_blk; // rank-3 {x, y, layer}, box 64x64x1
     void *d_stage = nullptr; size_t stage_bytes = 0;   // upload staging
+    // host mirrors (chunk-blocked, [layer][chunk][64][64]) for the host-side planner
+    std::vector<uint8_t>  h_cost;
+    std::vector<uint16_t> h_blk, h_liid;
+    struct portal_t { int16_t chunk_r, chunk_c, r0, c0, r1, c1; int32_t conn_chunk, conn_idx; };
+    std::vector<std::vector<std::vector<portal_t>>> portals;   // [layer][chunk][idx]
 
     // ---- field pool ----
     int pool_ndests = 0, pool_max = 0, pool_used = 0;
     int32_t *d_pool_slot = nullptr;   // [ndests][chunks] -> slot or -1
     std::vector<int32_t> h_pool_slot;
+    std::vector<uint8_t> h_pool_has;
+    void *d_plan_buf = nullptr; size_t plan_buf_bytes = 0;    // request staging for pfnav_pool_request_goal
     uint8_t *d_pool_flow = nullptr;   // [max][4096]
     uint8_t *d_pool_los = nullptr;    // [max][4096]
 
@@ -90,11 +97,41 @@ struct pfnav_ctx {
     uint32_t *d_work_count = nullptr;
     cudaStream_t tick_stream = nullptr;
     cudaEvent_t tick_done = nullptr;
+
+    // ---- optional per-kernel timing (pfnav_profile_enable) ----
+    bool profiling = false;
+    struct prof_rec { int slot; cudaEvent_t a, b; };
+    std::vector<prof_rec> prof_pending;
+};
+
+enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
+       PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };
+
+// RAII helper: brackets the launches of one kernel group with events when profiling is on
+struct pf_prof_scope {
+    pfnav_ctx *ctx; cudaStream_t st; int slot; cudaEvent_t a = nullptr, b = nullptr;
+    pf_prof_scope(pfnav_ctx *c, cudaStream_t s, int sl) : ctx(c), st(s), slot(sl)
+    {
+        if (!ctx->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    ~pf_prof_scope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        ctx->prof_pending.push_back({slot, a, b});
+    }
 };
 
 // ---- pfnav_fields.cu ----
 int pfnav_fields_init(pfnav_ctx *ctx);
 void pfnav_fields_free(pfnav_ctx *ctx);
+
+int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, uint8_t *d_inout_fields,
+                      const int32_t *d_out_slot, void *stream);
+int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint8_t *d_out_fields,
+                     const int32_t *d_out_slot, int n_waves, const int32_t *h_wave_offsets, void *stream);
 
 // ---- pfnav_agents.cu ----
 void pfnav_agents_free(pfnav_ctx *ctx);

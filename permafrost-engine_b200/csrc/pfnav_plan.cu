@@ -1,0 +1,361 @@
+// pfnav_plan.cu -- host-side navigation structure: local islands, portals, and a goal planner
+// that emits the flow/LOS field requests the device kernels consume.
+//
+// Restates (reference file:line):
+//   n_update_local_islands / n_visit_island_local     src/navigation/nav.c:967-984, 903-950
+//   n_create_portals / n_link_chunks                  src/navigation/nav.c:563-591, 477-561
+// and provides a breadth-first goal planner over (chunk, local island) nodes that yields, for
+// EVERY chunk connected to the goal, the same kind of TARGET_TILE / TARGET_PORTAL requests
+// n_request_path (nav.c:1774-2047) issues along one portal path. It minimises hop count, not the
+// reference's portal travel cost, so which portal a chunk steers to may differ from
+// AStar_PortalGraphPath's choice (a_star.c:429); each emitted field is still the reference's
+// field for that request. The cost-faithful search is listed under "next" in DESIGN.md.
+#include "pfnav_internal.cuh"
+#include <algorithm>
+#include <deque>
+#include <string.h>
+
+static inline size_t chunk_off(const pfnav_ctx *ctx, int layer, int cr, int cc)
+{
+    return ((size_t)layer * ctx->chunk_w * ctx->chunk_h + (size_t)cr * ctx->chunk_w + cc) * 4096;
+}
+
+// n_update_local_islands (nav.c:967): ids from 1 in row-major discovery order, 4-connected flood
+// inside the chunk over tiles that are passable and not blocked; 0xFFFF elsewhere.
+static void local_islands_chunk(const uint8_t *cost, const uint16_t *blk, uint16_t *out)
+{
+    for (int i = 0; i < 4096; i++) out[i] = 0xFFFF;
+    uint16_t next = 0;
+    std::vector<int> q;
+    q.reserve(4096);
+    for (int t = 0; t < 4096; t++) {
+        if (out[t] != 0xFFFF || cost[t] == 0xFF || blk[t] > 0) continue;
+        const uint16_t id = ++next;
+        q.clear();
+        q.push_back(t);
+        out[t] = id;
+        for (size_t h = 0; h < q.size(); h++) {
+            const int cur = q[h], r = cur >> 6, c = cur & 63;
+            const int nb[4] = {c > 0 ? cur - 1 : -1, c < 63 ? cur + 1 : -1, r > 0 ? cur - 64 : -1, r < 63 ? cur + 64 : -1};
+            for (int e = 0; e < 4; e++) {
+                const int n = nb[e];
+                if (n < 0 || out[n] != 0xFFFF || cost[n] == 0xFF || blk[n] > 0) continue;
+                out[n] = id;
+                q.push_back(n);
+            }
+        }
+    }
+}
+
+// n_link_chunks (nav.c:477): a portal is a maximal run of border tiles passable on both sides
+// (cost only, blockers ignored); a run that would start on the last tile of the line is never
+// closed and therefore dropped, exactly as the reference's loop does.
+static void link_chunks(pfnav_ctx *ctx, int layer, int ar, int ac, int br, int bc, bool vertical_pair)
+{
+    // vertical_pair: a is above b (a's bottom row vs b's top row); else a is left of b
+    auto &pa = ctx->portals[layer][ar * ctx->chunk_w + ac];
+    auto &pb = ctx->portals[layer][br * ctx->chunk_w + bc];
+    const uint8_t *ca = ctx->h_cost.data() + chunk_off(ctx, layer, ar, ac);
+    const uint8_t *cb = ctx->h_cost.data() + chunk_off(ctx, layer, br, bc);
+    bool in_portal = false;
+    int start = 0;
+    for (int i = 0; i < 64; i++) {
+        const uint8_t va = vertical_pair ? ca[63 * 64 + i] : ca[i * 64 + 63];
+        const uint8_t vb = vertical_pair ? cb[i] : cb[i * 64];
+        const bool can_cross = va != 0xFF && vb != 0xFF;
+        if (can_cross && !in_portal) {
+            in_portal = true;
+            start = i;
+        } else if (in_portal && (!can_cross || i == 63)) {
+            const int end = !can_cross ? i - 1 : i;
+            in_portal = false;
+            pfnav_ctx::portal_t A, B;
+            A.chunk_r = (int16_t)ar; A.chunk_c = (int16_t)ac; B.chunk_r = (int16_t)br; B.chunk_c = (int16_t)bc;
+            if (vertical_pair) {
+                A.r0 = 63; A.c0 = (int16_t)start; A.r1 = 63; A.c1 = (int16_t)end;
+                B.r0 = 0;  B.c0 = (int16_t)start; B.r1 = 0;  B.c1 = (int16_t)end;
+            } else {
+                A.r0 = (int16_t)start; A.c0 = 63; A.r1 = (int16_t)end; A.c1 = 63;
+                B.r0 = (int16_t)start; B.c0 = 0;  B.r1 = (int16_t)end; B.c1 = 0;
+            }
+            A.conn_chunk = br * ctx->chunk_w + bc; A.conn_idx = (int32_t)pb.size();
+            B.conn_chunk = ar * ctx->chunk_w + ac; B.conn_idx = (int32_t)pa.size();
+            pa.push_back(A);
+            pb.push_back(B);
+        }
+    }
+}
+
+// N_NewCtxForMapData's structural part for one layer (nav.c:2284): local islands (uploaded to the
+// device for TARGET_PORTAL seeding) and the portal table. Call after pfnav_map_upload_layer.
+extern "C" int pfnav_map_build_nav(pfnav_ctx *ctx, int layer)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    const size_t ltiles = (size_t)chunks * 4096;
+    for (int ch = 0; ch < chunks; ch++)
+        local_islands_chunk(ctx->h_cost.data() + ltiles * layer + (size_t)ch * 4096,
+                            ctx->h_blk.data() + ltiles * layer + (size_t)ch * 4096,
+                            ctx->h_liid.data() + ltiles * layer + (size_t)ch * 4096);
+    // n_create_portals (nav.c:563): chunks row-major, bottom link before right link
+    ctx->portals[layer].assign(chunks, {});
+    for (int r = 0; r < ctx->chunk_h; r++)
+        for (int c = 0; c < ctx->chunk_w; c++) {
+            if (r < ctx->chunk_h - 1) link_chunks(ctx, layer, r, c, r + 1, c, true);
+            if (c < ctx->chunk_w - 1) link_chunks(ctx, layer, r, c, r, c + 1, false);
+        }
+    for (int ch = 0; ch < chunks; ch++)
+        if (ctx->portals[layer][ch].size() > 64) {
+            pfnav_set_error("pfnav_map_build_nav: chunk %d has %zu portals (MAX_PORTALS_PER_CHUNK is 64, nav_data.h:44)",
+                            ch, ctx->portals[layer][ch].size());
+            return PFNAV_ERR_STATE;
+        }
+    // push the islands to the device image
+    return pfnav_map_upload_layer(ctx, layer, ctx->h_cost.data() + ltiles * layer, ctx->h_blk.data() + ltiles * layer,
+                                  ctx->h_liid.data() + ltiles * layer);
+}
+
+// Recompute the local islands of one chunk after its blockers changed (n_update_dirty_local_islands,
+// nav.c:986) and push the chunk to the device.
+extern "C" int pfnav_map_refresh_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk coords");
+    const size_t off = chunk_off(ctx, layer, chunk_r, chunk_c);
+    local_islands_chunk(ctx->h_cost.data() + off, ctx->h_blk.data() + off, ctx->h_liid.data() + off);
+    return pfnav_map_update_chunk(ctx, layer, chunk_r, chunk_c, nullptr, ctx->h_blk.data() + off, ctx->h_liid.data() + off);
+}
+
+extern "C" int pfnav_local_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out)
+{
+    PF_ARG(ctx && out && layer >= 0 && layer < ctx->nlayers, "args");
+    const size_t ltiles = (size_t)ctx->chunk_w * ctx->chunk_h * 4096;
+    memcpy(out, ctx->h_liid.data() + ltiles * layer, ltiles * 2);
+    return PFNAV_OK;
+}
+
+// Portal table in the same 10-int row format as the oracle harness (chunk_r, chunk_c, idx, ep0.r,
+// ep0.c, ep1.r, ep1.c, conn_chunk_idx, conn_portal_idx, 0). Returns the count via *out_n.
+extern "C" int pfnav_portals_get(pfnav_ctx *ctx, int layer, int32_t *out, int maxout, int *out_n)
+{
+    PF_ARG(ctx && out_n && layer >= 0 && layer < ctx->nlayers, "args");
+    PF_ARG((size_t)layer < ctx->portals.size() && !ctx->portals[layer].empty(), "pfnav_map_build_nav not called for this layer");
+    int n = 0;
+    for (size_t ch = 0; ch < ctx->portals[layer].size(); ch++)
+        for (size_t p = 0; p < ctx->portals[layer][ch].size(); p++) {
+            const auto &P = ctx->portals[layer][ch][p];
+            if (out && n < maxout) {
+                int32_t *o = out + (size_t)n * 10;
+                o[0] = P.chunk_r; o[1] = P.chunk_c; o[2] = (int32_t)p; o[3] = P.r0; o[4] = P.c0; o[5] = P.r1; o[6] = P.c1;
+                o[7] = P.conn_chunk; o[8] = P.conn_idx; o[9] = 0;
+            }
+            n++;
+        }
+    *out_n = n;
+    return PFNAV_OK;
+}
+
+// Goal planner: breadth-first over (chunk, local island) nodes from the goal tile. For every node
+// emits one flow request (TARGET_TILE for the goal's own node, TARGET_PORTAL towards the parent
+// node otherwise; a chunk's first node has init=1, later nodes of the same chunk merge in place
+// like nav.c:1998-2008) and, for a chunk's first node, one LOS request chained to its parent chunk.
+// `field_slot[i]` / `los_slot[i]` give the chunk index each request's output belongs to, and
+// `flow_wave[i]` the launch wave (requests that update the same chunk are serialised by wave).
+extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r,
+                               int tgt_tile_c, pfnav_field_req *flow_out, int32_t *flow_chunk, int32_t *flow_wave,
+                               int max_flow, int *n_flow, pfnav_los_req *los_out, int32_t *los_chunk, int max_los,
+                               int *n_los)
+{
+    PF_ARG(ctx && ctx->d_cost && n_flow && n_los, "args");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG((size_t)layer < ctx->portals.size() && !ctx->portals[layer].empty(), "pfnav_map_build_nav not called for this layer");
+    PF_ARG(tgt_chunk_r >= 0 && tgt_chunk_r < ctx->chunk_h && tgt_chunk_c >= 0 && tgt_chunk_c < ctx->chunk_w &&
+           tgt_tile_r >= 0 && tgt_tile_r < 64 && tgt_tile_c >= 0 && tgt_tile_c < 64, "target tile");
+    const int cw = ctx->chunk_w, chunks = cw * ctx->chunk_h;
+    const size_t ltiles = (size_t)chunks * 4096;
+    const uint16_t *liid = ctx->h_liid.data() + ltiles * layer;
+    *n_flow = 0; *n_los = 0;
+    struct node { int chunk; uint16_t li; };
+    std::deque<node> q;
+    std::vector<std::vector<uint16_t>> seen(chunks);      // islands already planned per chunk
+    std::vector<int> los_index(chunks, -1), nodes_in_chunk(chunks, 0);
+    const int tchunk = tgt_chunk_r * cw + tgt_chunk_c;
+    const uint16_t tli = liid[(size_t)tchunk * 4096 + tgt_tile_r * 64 + tgt_tile_c];
+    auto emit_flow = [&](const pfnav_field_req &rq, int chunk) -> bool {
+        if (*n_flow >= max_flow) return false;
+        flow_out[*n_flow] = rq;
+        flow_out[*n_flow].init = nodes_in_chunk[chunk] == 0;
+        flow_chunk[*n_flow] = chunk;
+        flow_wave[*n_flow] = nodes_in_chunk[chunk];
+        nodes_in_chunk[chunk]++;
+        (*n_flow)++;
+        return true;
+    };
+    pfnav_field_req base;
+    memset(&base, 0, sizeof(base));
+    base.layer = layer; base.faction_id = PFNAV_FACTION_ID_NONE;
+    {   // the goal's own chunk: TARGET_TILE field + destination LOS (nav.c:1819-1847)
+        pfnav_field_req rq = base;
+        rq.chunk_r = tgt_chunk_r; rq.chunk_c = tgt_chunk_c; rq.target_type = PFNAV_TARGET_TILE;
+        rq.tile_r = tgt_tile_r; rq.tile_c = tgt_tile_c;
+        if (!emit_flow(rq, tchunk)) { pfnav_set_error("pfnav_plan_goal: flow output too small"); return PFNAV_ERR_NOMEM; }
+        if (*n_los >= max_los) { pfnav_set_error("pfnav_plan_goal: los output too small"); return PFNAV_ERR_NOMEM; }
+        pfnav_los_req lq;
+        memset(&lq, 0, sizeof(lq));
+        lq.chunk_r = tgt_chunk_r; lq.chunk_c = tgt_chunk_c; lq.layer = layer; lq.faction_id = PFNAV_FACTION_ID_NONE;
+        lq.tgt_chunk_r = tgt_chunk_r; lq.tgt_chunk_c = tgt_chunk_c; lq.tgt_tile_r = tgt_tile_r; lq.tgt_tile_c = tgt_tile_c;
+        lq.prev_index = -1;
+        los_index[tchunk] = *n_los;
+        los_out[*n_los] = lq; los_chunk[*n_los] = tchunk; (*n_los)++;
+    }
+    if (tli == 0xFFFF) return PFNAV_OK;      // goal tile impassable/blocked: nothing can flow to it
+    seen[tchunk].push_back(tli);
+    q.push_back({tchunk, tli});
+    while (!q.empty()) {
+        const node cur = q.front();
+        q.pop_front();
+        const auto &ports = ctx->portals[layer][cur.chunk];
+        for (size_t pi = 0; pi < ports.size(); pi++) {
+            const auto &P = ports[pi];                                // portal of the current (parent) chunk
+            const auto &Q = ctx->portals[layer][P.conn_chunk][P.conn_idx];   // facing portal in the neighbour chunk
+            const int nchunk = P.conn_chunk;
+            // every island M of the neighbour that touches island cur.li across this portal
+            const int len = (P.r1 - P.r0) + (P.c1 - P.c0) + 1;
+            for (int k = 0; k < len; k++) {
+                const int pr = P.r0 + (P.r1 > P.r0 ? k : 0), pc = P.c0 + (P.c1 > P.c0 ? k : 0);
+                const int qr = Q.r0 + (Q.r1 > Q.r0 ? k : 0), qc = Q.c0 + (Q.c1 > Q.c0 ? k : 0);
+                if (liid[(size_t)cur.chunk * 4096 + pr * 64 + pc] != cur.li) continue;
+                const uint16_t M = liid[(size_t)nchunk * 4096 + qr * 64 + qc];
+                if (M == 0xFFFF) continue;
+                auto &sv = seen[nchunk];
+                if (std::find(sv.begin(), sv.end(), M) != sv.end()) continue;
+                sv.push_back(M);
+                pfnav_field_req rq = base;
+                rq.chunk_r = Q.chunk_r; rq.chunk_c = Q.chunk_c; rq.target_type = PFNAV_TARGET_PORTAL;
+                rq.port_r0 = Q.r0; rq.port_c0 = Q.c0; rq.port_r1 = Q.r1; rq.port_c1 = Q.c1;
+                rq.next_r0 = P.r0; rq.next_c0 = P.c0; rq.next_r1 = P.r1; rq.next_c1 = P.c1;
+                rq.next_chunk_r = P.chunk_r; rq.next_chunk_c = P.chunk_c;
+                rq.port_iid = M; rq.next_iid = cur.li;
+                const bool first = nodes_in_chunk[nchunk] == 0;
+                if (!emit_flow(rq, nchunk)) { pfnav_set_error("pfnav_plan_goal: flow output too small"); return PFNAV_ERR_NOMEM; }
+                if (first) {
+                    if (*n_los >= max_los) { pfnav_set_error("pfnav_plan_goal: los output too small"); return PFNAV_ERR_NOMEM; }
+                    pfnav_los_req lq;
+                    memset(&lq, 0, sizeof(lq));
+                    lq.chunk_r = Q.chunk_r; lq.chunk_c = Q.chunk_c; lq.layer = layer; lq.faction_id = PFNAV_FACTION_ID_NONE;
+                    lq.tgt_chunk_r = tgt_chunk_r; lq.tgt_chunk_c = tgt_chunk_c; lq.tgt_tile_r = tgt_tile_r; lq.tgt_tile_c = tgt_tile_c;
+                    lq.prev_index = los_index[cur.chunk];
+                    lq.prev_chunk_r = P.chunk_r; lq.prev_chunk_c = P.chunk_c;
+                    los_index[nchunk] = *n_los;
+                    los_out[*n_los] = lq; los_chunk[*n_los] = nchunk; (*n_los)++;
+                }
+                q.push_back({nchunk, M});
+            }
+        }
+    }
+    return PFNAV_OK;
+}
+
+// n_request_path's field-building half, resident on the device: plan the goal, then run the flow
+// waves and the LOS chain straight into the field pool (no host round trip of field bytes).
+// Asynchronous on `stream` (the small request upload is stream-ordered too).
+extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_r, int tgt_chunk_c,
+                                       int tgt_tile_r, int tgt_tile_c, void *stream, int *out_n_flow, int *out_n_los)
+{
+    PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    const int cap = chunks * 8 + 8;
+    std::vector<pfnav_field_req> fr(cap);
+    std::vector<pfnav_los_req> lr(cap);
+    std::vector<int32_t> fc(cap), fw(cap), lc(cap);
+    int nf = 0, nl = 0;
+    int rc = pfnav_plan_goal(ctx, layer, tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c, fr.data(), fc.data(), fw.data(),
+                             cap, &nf, lr.data(), lc.data(), cap, &nl);
+    if (rc) return rc;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // pool slots for every chunk touched
+    auto slot_for = [&](int chunk, uint8_t bits) -> int {
+        const size_t si = (size_t)dest * chunks + chunk;
+        int slot = ctx->h_pool_slot[si];
+        if (slot < 0) {
+            if (ctx->pool_used >= ctx->pool_max) return -1;
+            slot = ctx->pool_used++;
+            ctx->h_pool_slot[si] = slot;
+        }
+        ctx->h_pool_has[slot] |= bits;
+        return slot;
+    };
+    // order flow requests by wave (stable), LOS requests by dependency depth
+    int maxw = 0;
+    for (int i = 0; i < nf; i++) maxw = std::max(maxw, fw[i]);
+    std::vector<int> forder;
+    std::vector<int32_t> fwave_off(maxw + 2, 0);
+    for (int w = 0; w <= maxw; w++) {
+        for (int i = 0; i < nf; i++) if (fw[i] == w) forder.push_back(i);
+        fwave_off[w + 1] = (int32_t)forder.size();
+    }
+    std::vector<int> depth(nl, 0), lorder(nl), lnew(nl);
+    int maxd = 0;
+    for (int i = 0; i < nl; i++) if (lr[i].prev_index >= 0) { depth[i] = depth[lr[i].prev_index] + 1; maxd = std::max(maxd, depth[i]); }
+    std::vector<int32_t> lwave_off(maxd + 2, 0);
+    for (int i = 0; i < nl; i++) lwave_off[depth[i] + 1]++;
+    for (int d = 0; d <= maxd; d++) lwave_off[d + 1] += lwave_off[d];
+    {
+        std::vector<int32_t> cur(lwave_off.begin(), lwave_off.end() - 1);
+        for (int i = 0; i < nl; i++) { lnew[i] = cur[depth[i]]++; lorder[lnew[i]] = i; }
+    }
+    // staging layout: [flow reqs][flow slots][los reqs][los slots]
+    const size_t b_fr = (size_t)nf * sizeof(pfnav_field_req), b_fs = (size_t)nf * 4;
+    const size_t b_lr = (size_t)nl * sizeof(pfnav_los_req), b_ls = (size_t)nl * 4;
+    const size_t total = b_fr + b_fs + b_lr + b_ls;
+    std::vector<uint8_t> host(total);
+    pfnav_field_req *hfr = (pfnav_field_req *)host.data();
+    int32_t *hfs = (int32_t *)(host.data() + b_fr);
+    pfnav_los_req *hlr = (pfnav_los_req *)(host.data() + b_fr + b_fs);
+    int32_t *hls = (int32_t *)(host.data() + b_fr + b_fs + b_lr);
+    for (int k = 0; k < nf; k++) {
+        hfr[k] = fr[forder[k]];
+        hfs[k] = slot_for(fc[forder[k]], 1);
+        if (hfs[k] < 0) { pfnav_set_error("pfnav_pool_request_goal: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+    }
+    for (int k = 0; k < nl; k++) {
+        hlr[k] = lr[lorder[k]];
+        if (hlr[k].prev_index >= 0) hlr[k].prev_index = lnew[hlr[k].prev_index];
+        hls[k] = slot_for(lc[lorder[k]], 2);
+        if (hls[k] < 0) { pfnav_set_error("pfnav_pool_request_goal: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+    }
+    // NOTE: one staging buffer per context; callers serialise goal requests on one stream
+    if (ctx->plan_buf_bytes < total) {
+        PF_CUDA(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_plan_buf);
+        ctx->d_plan_buf = nullptr; ctx->plan_buf_bytes = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_plan_buf, total * 2));
+        ctx->plan_buf_bytes = total * 2;
+    }
+    uint8_t *dev = (uint8_t *)ctx->d_plan_buf;
+    PF_CUDA(cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + (size_t)dest * chunks, ctx->h_pool_slot.data() + (size_t)dest * chunks,
+                            (size_t)chunks * 4, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
+                            cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaStreamSynchronize(st));      // `host` is pageable and about to go out of scope
+    const pfnav_field_req *dfr = (const pfnav_field_req *)dev;
+    const int32_t *dfs = (const int32_t *)(dev + b_fr);
+    const pfnav_los_req *dlr = (const pfnav_los_req *)(dev + b_fr + b_fs);
+    const int32_t *dls = (const int32_t *)(dev + b_fr + b_fs + b_lr);
+    for (int w = 0; w <= maxw; w++) {
+        const int first = fwave_off[w], cnt = fwave_off[w + 1] - first;
+        if (cnt <= 0) continue;
+        rc = pfnav_flow_launch(ctx, dfr + first, cnt, ctx->d_pool_flow, dfs + first, st);
+        if (rc) return rc;
+    }
+    rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), st);
+    if (rc) return rc;
+    if (out_n_flow) *out_n_flow = nf;
+    if (out_n_los) *out_n_los = nl;
+    return PFNAV_OK;
+}

@@ -131,8 +131,11 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
     target_tiles = np.zeros((nflocks, 4), np.int32)
     passable = np.argwhere(img != 0xFF)
     k = 0
-    step = spacing * radius
+    radii = np.broadcast_to(np.asarray(radius, np.float32), (nflocks,)) if np.ndim(radius) <= 1 and np.size(radius) in (1, nflocks) \
+        else np.asarray(radius, np.float32)
+    rad_agent = np.zeros(n, np.float32)
     for f in range(nflocks):
+        step = spacing * float(radii[f])
         # spawn centre
         cr, cc = passable[g.integers(0, len(passable))]
         cx = map_x - (cc + 0.5) * NAV_TILE
@@ -160,6 +163,7 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
         pos[k:k + need, 0] = xs[:need]
         pos[k:k + need, 1] = zs[:need]
         flock_of[k:k + need] = f
+        rad_agent[k:k + need] = radii[f]
         # goal tile far enough from the spawn centre
         for _ in range(10000):
             tr_, tc_ = passable[g.integers(0, len(passable))]
@@ -178,7 +182,7 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
     jitter = (g.random((n, 2)).astype(np.float32) - 0.5) * np.float32(0.05)
     vel = (vel + jitter).astype(np.float32)
     prev = (pos - vel).astype(np.float32)
-    return dict(pos=pos, prev_pos=prev, vel=vel, radius=np.full(n, radius, np.float32),
+    return dict(pos=pos, prev_pos=prev, vel=vel, radius=rad_agent,
                 max_speed=np.full(n, max_speed, np.float32), speed=np.full(n, max_speed, np.float32),
                 state=np.zeros(n, np.int32), flags=np.full(n, 1 << 3, np.uint32), flock_of=flock_of,
                 flock_target=targets, flock_target_tile=target_tiles, hz=hz)

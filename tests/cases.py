@@ -1,0 +1,129 @@
+"""Seeded scenario builders shared by the golden-vector generator, the CPU tests and the GPU tests.
+Everything is a pure function of its seed (numpy + the package's synth module)."""
+import importlib
+import numpy as np
+
+pf = importlib.import_module("permafrost-engine_b200")
+capi, synth = pf.capi, pf.synth
+
+
+def noise_map(cw, ch, seed, density):
+    rng = np.random.default_rng(seed)
+    p = synth.make_map(cw, ch, seed, frac_blocked=0.12, rivers=(cw * ch > 1))
+    if density > 0:
+        p[rng.random(p.shape) < density] = 0
+    return p
+
+
+def local_islands_np(cost, blockers=None):
+    """numpy/python restatement of n_update_local_islands (nav.c:967) for test inputs: ids from 1 in
+    row-major discovery order."""
+    out = np.full(cost.shape, 0xFFFF, np.uint16)
+    for ch in range(cost.shape[0]):
+        nxt = 0
+        free = cost[ch] != 0xFF
+        if blockers is not None:
+            free &= blockers[ch] == 0
+        lab = out[ch]
+        for r, c in np.argwhere(free):
+            if lab[r, c] != 0xFFFF:
+                continue
+            nxt += 1
+            stack = [(r, c)]
+            lab[r, c] = nxt
+            while stack:
+                y, x = stack.pop()
+                for yy, xx in ((y, x - 1), (y, x + 1), (y - 1, x), (y + 1, x)):
+                    if 0 <= yy < 64 and 0 <= xx < 64 and free[yy, xx] and lab[yy, xx] == 0xFFFF:
+                        lab[yy, xx] = nxt
+                        stack.append((yy, xx))
+    return out
+
+
+def flow_tile_case(seed, dens, n=8):
+    """-> cost[1,64,64], reqs"""
+    p = noise_map(1, 1, seed, dens)
+    cost = synth.cost_from_pathable(p, 1, 1)
+    rng = np.random.default_rng(seed)
+    tiles = np.argwhere(cost[0] != 255)
+    sel = tiles[rng.integers(0, len(tiles), n)]
+    if (cost[0] == 255).any():
+        sel = np.concatenate([sel, np.argwhere(cost[0] == 255)[:1]])      # impassable target: empty frontier
+    reqs = np.concatenate([capi.tile_req((0, 0), (int(r), int(c))) for r, c in sel])
+    return p, cost, reqs
+
+
+def portal_specs(portals, liid, cw, limit=None):
+    """TARGET_PORTAL request specs for every portal: (chunk, idx, ep, next_chunk, next_ep, port_iid, next_iid)"""
+    out = []
+    key = portals[:, 0] * cw + portals[:, 1]
+    for row in portals:
+        cr, cc, idx, r0, c0, r1, c1, conn_chunk, conn_idx = [int(v) for v in row[:9]]
+        nrow = portals[(key == conn_chunk) & (portals[:, 2] == conn_idx)][0]
+        ncr, ncc = int(nrow[0]), int(nrow[1])
+        nr0, nc0, nr1, nc1 = [int(v) for v in nrow[3:7]]
+        piids = np.unique(liid[cr * cw + cc][r0:r1 + 1, c0:c1 + 1]); piids = piids[piids != 0xFFFF]
+        niids = np.unique(liid[ncr * cw + ncc][nr0:nr1 + 1, nc0:nc1 + 1]); niids = niids[niids != 0xFFFF]
+        for pi in list(piids[:2]) + [0xFFFF]:
+            for ni in niids[:2]:
+                out.append(((cr, cc), idx, (r0, c0, r1, c1), (ncr, ncc), (nr0, nc0, nr1, nc1), int(pi), int(ni)))
+    return out[:limit] if limit else out
+
+
+def portal_reqs(specs, init=1):
+    return np.concatenate([capi.portal_req(s[0], s[2], s[3], s[4], s[5], s[6], init=init) for s in specs])
+
+
+def los_case(cost, cw, ch, seed, ntargets=4):
+    """LOS request batch: destination chunk + chained neighbours (+ one more hop). -> reqs"""
+    rng = np.random.default_rng(seed)
+    reqs = []
+    for t in range(ntargets):
+        chunk = (int(rng.integers(0, ch)), int(rng.integers(0, cw)))
+        tiles = np.argwhere(cost[chunk[0] * cw + chunk[1]] != 255)
+        tr, tc = [int(v) for v in tiles[rng.integers(0, len(tiles))]]
+        td = (chunk[0], chunk[1], tr, tc)
+        i0 = len(reqs)
+        reqs.append(capi.los_req(chunk, td))
+        for nb in ((chunk[0] + 1, chunk[1]), (chunk[0] - 1, chunk[1]), (chunk[0], chunk[1] + 1), (chunk[0], chunk[1] - 1)):
+            if not (0 <= nb[0] < ch and 0 <= nb[1] < cw):
+                continue
+            i1 = len(reqs)
+            reqs.append(capi.los_req(nb, td, prev_index=i0, prev_chunk=chunk))
+            for nb2 in ((nb[0] + 1, nb[1]), (nb[0], nb[1] + 1), (nb[0] - 1, nb[1]), (nb[0], nb[1] - 1)):
+                if not (0 <= nb2[0] < ch and 0 <= nb2[1] < cw) or nb2 == chunk:
+                    continue
+                reqs.append(capi.los_req(nb2, td, prev_index=i1, prev_chunk=nb))
+    return np.concatenate(reqs)
+
+
+def ref_los_batch(ref, reqs):
+    """run a LOS request batch through the compiled reference"""
+    out = np.zeros((len(reqs), 64, 64), np.uint8)
+    for i, q in enumerate(reqs):
+        td = (int(q["tgt_chunk_r"]), int(q["tgt_chunk_c"]), int(q["tgt_tile_r"]), int(q["tgt_tile_c"]))
+        chunk = (int(q["chunk_r"]), int(q["chunk_c"]))
+        if q["prev_index"] < 0:
+            out[i] = ref.los(chunk, td)
+        else:
+            out[i] = ref.los(chunk, td, prev=out[int(q["prev_index"])], prev_chunk=(int(q["prev_chunk_r"]), int(q["prev_chunk_c"])))
+    return out
+
+
+def agent_case(cw, n, nflocks, seed, dens, spacing):
+    """-> pathable, cost, agents dict (with ~10% ARRIVED and ~10% slow movers)"""
+    p = noise_map(cw, cw, seed, dens)
+    cost = synth.cost_from_pathable(p, cw, cw)
+    a = synth.make_agents(cost, cw, cw, n, nflocks, seed, radius=1.0, spacing=spacing)
+    rng = np.random.default_rng(seed)
+    st = a["state"].copy(); st[rng.random(n) < 0.1] = 2
+    a["state"] = st
+    slow = rng.random(n) < 0.1
+    a["vel"][slow] *= np.float32(0.05)
+    a["prev_pos"] = (a["pos"] - a["vel"]).astype(np.float32)
+    return p, cost, a
+
+
+def relerr(g, e):
+    d = np.abs(g - e).max(axis=1)
+    return d / np.maximum(np.abs(e).max(axis=1), 1e-3)

@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/libpfref.so, built
+from /root/reference by `make -C oracle ref`) on the seeded cases of tests/cases.py.
+
+Run in the build container (the reference checkout does not exist on the GPU box):
+    python tests/golden/make_golden.py
+The reference publishes no golden vectors / KATs of its own for this path, so
+these files are what pins the oracle port and the CUDA path."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases
+import pfref
+
+capi, synth = cases.capi, cases.synth
+
+
+def gen_flow_tile():
+    out = {}
+    for k, (seed, dens) in enumerate(((1, 0.0), (2, 0.25), (4, 0.4))):
+        p, cost, reqs = cases.flow_tile_case(seed, dens)
+        ref = pfref.RefMap(1, 1, p)
+        assert (ref.cost_base() == cost).all()
+        exp = np.stack([ref.flow_tile((0, 0), (int(q["tile_r"]), int(q["tile_c"]))) for q in reqs])
+        out[f"cost{k}"] = cost; out[f"reqs{k}"] = reqs.view(np.uint8); out[f"exp{k}"] = exp
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "flow_tile.npz"), **out)
+
+
+def gen_portal_los():
+    cw = ch = 3
+    p = cases.noise_map(cw, ch, 12, 0.15)
+    ref = pfref.RefMap(cw, ch, p)
+    cost, liid, ports = ref.cost_base(), ref.local_islands(), ref.portals()
+    specs = cases.portal_specs(ports, liid, cw, limit=48)
+    exp = np.stack([ref.flow_portal(s[0], s[1], s[5], s[6]) for s in specs])
+    # in-place merge of a second target (nav.c:1998-2008)
+    s0 = specs[0]
+    base = ref.flow_tile(s0[0], (5, 5))
+    merged = ref.flow_portal(s0[0], s0[1], s0[5], s0[6], inout=base)
+    los_reqs = cases.los_case(cost, cw, ch, 22, ntargets=3)
+    los_exp = cases.ref_los_batch(ref, los_reqs)
+    np.savez_compressed(os.path.join(HERE, "portal_los.npz"), pathable=p, cost=cost, liid=liid, portals=ports,
+                        islands=ref.islands(), reqs=cases.portal_reqs(specs).view(np.uint8), exp=exp,
+                        merge_base=base, merge_exp=merged, los_reqs=los_reqs.view(np.uint8), los_exp=los_exp)
+    ref.close()
+
+
+def gen_agents(name, cw, n, nflocks, seed, dens, spacing):
+    p, cost, a = cases.agent_case(cw, n, nflocks, seed, dens, spacing)
+    ref = pfref.RefMap(cw, cw, p)
+    dest_ids = []
+    for f in range(nflocks):
+        src = a["pos"][np.argmax(a["flock_of"] == f)]
+        tgt = a["flock_target"][f]
+        ok, did = ref.request_path((float(src[0]), float(src[1])), (float(tgt[0]), float(tgt[1])))
+        dest_ids.append(did if ok else ref.dest_id((float(tgt[0]), float(tgt[1]))))
+    ref.agents_set(a["pos"], a["prev_pos"], a["vel"], a["radius"], a["max_speed"], a["state"], a["flags"],
+                   a["flock_of"], a["flock_target"], np.array(dest_ids, np.uint32), hz=20)
+    work = np.nonzero((a["state"] != 2) & (a["state"] != 4))[0].astype(np.uint32)
+    vdes = np.zeros((len(work), 2), np.float32); los = np.zeros(len(work), np.uint8)
+    for _pass in range(2):       # pass 0 settles the reference's field cache (see tools/gpu_check.py)
+        for f in range(nflocks):
+            sel = np.nonzero(a["flock_of"][work] == f)[0]
+            if len(sel) == 0:
+                continue
+            v, l = ref.desired_velocity(dest_ids[f], a["pos"][work[sel]], a["prev_pos"][work[sel]], a["flock_target"][f])
+            vdes[sel] = v; los[sel] = l
+    ref.work_set(work, vdes, los, a["speed"][work])
+    vel, _ = ref.velocity_work(1)
+    vpref = ref.vpref()
+    rng = np.random.default_rng(seed)
+    qi = rng.integers(0, n, 12)
+    q10 = [ref.ents_in_circle(float(a["pos"][i, 0]), float(a["pos"][i, 1]), 10.0, 512) for i in qi]
+    q30 = [ref.ents_in_circle(float(a["pos"][i, 0]), float(a["pos"][i, 1]), 30.0, 128) for i in qi]
+    pool_chunks, pool_flow, pool_los = [], [], []
+    for f in range(nflocks):
+        for cr in range(cw):
+            for cc in range(cw):
+                ff, _ = ref.fc_flow(dest_ids[f], (cr, cc)); lf = ref.fc_los(dest_ids[f], (cr, cc))
+                if ff is None and lf is None:
+                    continue
+                pool_chunks.append((f, cr, cc, ff is not None, lf is not None))
+                pool_flow.append(ff if ff is not None else np.zeros((64, 64), np.uint8))
+                pool_los.append(lf if lf is not None else np.zeros((64, 64), np.uint8))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pathable=p, cost=cost,
+                        **{"a_" + k: v for k, v in a.items() if isinstance(v, np.ndarray)},
+                        work=work, vdes=vdes, los=los, vel=vel, vpref=vpref, qi=qi,
+                        q10=np.concatenate(q10), q10_len=np.array([len(x) for x in q10]),
+                        q30=np.concatenate(q30), q30_len=np.array([len(x) for x in q30]),
+                        pool_chunks=np.array(pool_chunks, np.int32), pool_flow=np.array(pool_flow, np.uint8),
+                        pool_los=np.array(pool_los, np.uint8), liid=ref.local_islands())
+    ref.close()
+
+
+if __name__ == "__main__":
+    gen_flow_tile()
+    gen_portal_los()
+    gen_agents("agents_1x1", 1, 256, 1, 31, 0.02, 4.0)
+    gen_agents("agents_dense", 1, 400, 2, 32, 0.05, 2.6)
+    gen_agents("agents_3x3", 3, 1500, 3, 33, 0.03, 2.6)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,185 @@
+"""CPU suite (-m "not gpu"): the oracle port against the committed golden vectors (generated from the
+compiled reference by tests/golden/make_golden.py), against the compiled reference itself when it is
+available, plus host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+capi, synth = cases.capi, cases.synth
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+# ---------------------------------------------------------------- oracle port vs golden vectors
+def test_port_flow_tile_golden(pforacle):
+    g = gold("flow_tile")
+    for k in range(3):
+        om = pforacle.OracleMap(1, 1, g[f"cost{k}"])
+        reqs = g[f"reqs{k}"].view(capi.FIELD_REQ)
+        got = om.flow_fields_update(reqs)
+        assert (got == g[f"exp{k}"]).all()
+        # empty frontier (impassable target) leaves the initialised field untouched: all FD_NONE
+        if (g[f"cost{k}"][0][reqs[-1]["tile_r"], reqs[-1]["tile_c"]] == 255):
+            assert (got[-1] == 0).all()
+
+
+def test_port_flow_portal_and_merge_golden(pforacle):
+    g = gold("portal_los")
+    om = pforacle.OracleMap(3, 3, g["cost"], None, g["liid"])
+    reqs = g["reqs"].view(capi.FIELD_REQ)
+    assert (om.flow_fields_update(reqs) == g["exp"]).all()
+    q = reqs[:1].copy(); q["init"] = 0
+    assert (om.flow_fields_update(q, inout=g["merge_base"][None])[0] == g["merge_exp"]).all()
+
+
+def test_port_los_golden(pforacle):
+    g = gold("portal_los")
+    om = pforacle.OracleMap(3, 3, g["cost"])
+    got = om.los_fields_create(g["los_reqs"].view(capi.LOS_REQ))
+    assert (got == g["los_exp"]).all()
+
+
+def test_local_islands_restatement_golden():
+    g = gold("portal_los")
+    assert (cases.local_islands_np(g["cost"]) == g["liid"]).all()
+
+
+def _agents_from_gold(g):
+    a = {k[2:]: g[k] for k in g.files if k.startswith("a_")}
+    a["vdes"] = np.zeros((len(a["radius"]), 2), np.float32); a["vdes"][g["work"]] = g["vdes"]
+    a["has_los"] = np.zeros(len(a["radius"]), np.uint32); a["has_los"][g["work"]] = g["los"]
+    return a
+
+
+@pytest.mark.parametrize("name,cw", [("agents_1x1", 1), ("agents_dense", 1), ("agents_3x3", 3)])
+def test_port_agents_golden(pforacle, name, cw):
+    g = gold(name)
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    om = pforacle.OracleMap(cw, cw, g["cost"])
+    w = pforacle.OracleWorld(om, rec, fl, 20)
+    # spatial index: same hits in the same order as bg_ent_inrange_circle
+    o10 = np.cumsum(np.concatenate([[0], g["q10_len"]])); o30 = np.cumsum(np.concatenate([[0], g["q30_len"]]))
+    for k, i in enumerate(g["qi"]):
+        x, z = float(a["pos"][i, 0]), float(a["pos"][i, 1])
+        assert (w.ents_in_circle(x, z, 10.0, 512) == g["q10"][o10[k]:o10[k + 1]]).all()
+        assert (w.ents_in_circle(x, z, 30.0, 128) == g["q30"][o30[k]:o30[k + 1]]).all()
+    vel, vpref = w.velocity_work(g["work"])
+    # tolerance: north_star's 1e-4 relative. (Cohesion sums flock members in khash bucket order in the
+    # reference and in ascending uid here; with one flock of dense uids the two coincide bit for bit.)
+    assert cases.relerr(vpref, g["vpref"]).max() <= 1e-4
+    assert cases.relerr(vel, g["vel"]).max() <= 1e-4
+    if name != "agents_3x3":
+        assert (vel == g["vel"]).all() and (vpref == g["vpref"]).all()
+    w.close()
+
+
+def test_port_desired_velocity_golden(pforacle):
+    g = gold("agents_3x3")
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    om = pforacle.OracleMap(3, 3, g["cost"])
+    slot = np.full(3 * 9, -1, np.int32)
+    for s, (f, cr, cc, hf, hl) in enumerate(g["pool_chunks"]):
+        slot[f * 9 + cr * 3 + cc] = s
+    vdes, los = om.desired_velocity(rec, fl, g["work"], slot, g["pool_flow"], g["pool_los"])
+    assert (los == g["los"]).all()
+    assert (vdes == g["vdes"]).all()       # bit-exact: pure float ops, no transcendental
+
+
+# ---------------------------------------------------------------- oracle port vs compiled reference
+@pytest.mark.parametrize("seed,dens", [(3, 0.05), (5, 0.3)])
+def test_port_vs_ref_fields(pfref, pforacle, seed, dens):
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, seed, dens)
+    ref = pfref.RefMap(cw, ch, p)
+    cost, liid = ref.cost_base(), ref.local_islands()
+    assert (cost == synth.cost_from_pathable(p, cw, ch)).all()
+    assert (liid == cases.local_islands_np(cost)).all()
+    om = pforacle.OracleMap(cw, ch, cost, None, liid)
+    specs = cases.portal_specs(ref.portals(), liid, cw, limit=24)
+    got = om.flow_fields_update(cases.portal_reqs(specs))
+    for k, s in enumerate(specs):
+        assert (ref.flow_portal(s[0], s[1], s[5], s[6]) == got[k]).all()
+    lr = cases.los_case(cost, cw, ch, seed, ntargets=2)
+    assert (om.los_fields_create(lr) == cases.ref_los_batch(ref, lr)).all()
+    ref.close()
+
+
+def test_port_vs_ref_blockers(pfref, pforacle):
+    """dynamic obstacles: N_BlockersIncref + N_Update on the reference, then fields with blockers > 0"""
+    p = cases.noise_map(1, 1, 9, 0.05)
+    ref = pfref.RefMap(1, 1, p)
+    rng = np.random.default_rng(9)
+    for _ in range(25):
+        x, z = -rng.uniform(10, 246), rng.uniform(10, 246)
+        ref.blockers_incref(float(x), float(z), 3.0, 0, 1 << 3)
+    ref.update()
+    cost, blk, liid = ref.cost_base(), ref.blockers(), ref.local_islands()
+    assert (blk > 0).any()
+    assert (liid == cases.local_islands_np(cost, blk)).all()
+    om = pforacle.OracleMap(1, 1, cost, blk, liid)
+    free = np.argwhere((cost[0] != 255) & (blk[0] == 0))
+    for r, c in free[::501]:
+        q = capi.tile_req((0, 0), (int(r), int(c)))
+        assert (om.flow_fields_update(q)[0] == ref.flow_tile((0, 0), (int(r), int(c)))).all()
+        lq = capi.los_req((0, 0), (0, 0, int(r), int(c)))
+        assert (om.los_fields_create(lq)[0] == ref.los((0, 0), (0, 0, int(r), int(c)))).all()
+    ref.close()
+
+
+# ---------------------------------------------------------------- host logic + ABI surface
+def test_synth_is_deterministic():
+    p1 = synth.make_map(2, 2, 0x5EED0002); p2 = synth.make_map(2, 2, 0x5EED0002)
+    assert (p1 == p2).all() and 0.05 < (p1 == 0).mean() < 0.5
+    c = synth.cost_from_pathable(p1, 2, 2)
+    a1 = synth.make_agents(c, 2, 2, 500, 2, 7); a2 = synth.make_agents(c, 2, 2, 500, 2, 7)
+    for k in ("pos", "vel", "flock_target"):
+        assert (a1[k] == a2[k]).all()
+    img = synth.blocked_to_image(c, 2, 2)
+    assert (synth.image_to_blocked(img, 2, 2) == c).all()
+    tr, tc = synth.tile_for_xz(a1["pos"][:, 0], a1["pos"][:, 1], 2, 2)
+    assert (img[tr, tc] != 0xFF).all()          # agents stand on passable ground
+
+
+def test_record_layouts_match_header():
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "include", "pfnav.h")).read()
+    assert capi.FIELD_REQ.itemsize == 64 and capi.LOS_REQ.itemsize == 48
+    assert capi.AGENT.itemsize == 64 and capi.FLOCK.itemsize == 16
+    for name in capi.SYMBOLS:
+        assert re.search(r"\b%s\s*\(" % name, hdr), name + " is bound but not declared in include/pfnav.h"
+    declared = set(re.findall(r"\b(pfnav_[a-z0-9_]+)\s*\(", hdr))
+    assert declared <= set(capi.SYMBOLS), declared - set(capi.SYMBOLS)
+
+
+def test_abi_library_loads_and_exports_every_symbol():
+    L = capi.load()
+    for name in capi.SYMBOLS:
+        assert hasattr(L, name), name
+    assert L.pfnav_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a usable GPU the product path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.PfnavError):
+        capi.Nav(0)
+
+
+def test_product_does_not_touch_oracle():
+    root = os.path.join(os.path.dirname(GOLD), "..", "permafrost-engine_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert "pforacle" not in src and "pfref" not in src and "oracle/" not in src, f
