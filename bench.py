@@ -185,12 +185,11 @@ def run_ours(args):
     rec_view = torch.as_tensor(CudaArrayView(d_rec_ptr, n_total * 24), device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
 
+    goal_dests = np.arange(len(goals), dtype=np.int32)
+    goal_targets = np.array(goals, np.int32)
+
     def fields_phase():
-        nf = nl = 0
-        for d, td in enumerate(goals):
-            a, b = nav.pool_request_goal(d, td, 0, sp)
-            nf += a; nl += b
-        return nf, nl
+        return nav.pool_request_goals(goal_dests, goal_targets, 0, sp)
 
     def gather_phase():
         if world > 1:

@@ -190,6 +190,11 @@ int  pfnav_pool_clear(pfnav_ctx *ctx);
 int  pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_r, int tgt_chunk_c,
                              int tgt_tile_r, int tgt_tile_c, void *stream, int *out_n_flow,
                              int *out_n_los);
+/* The same for a batch of goals (the reference runs up to 256 field tasks concurrently, nav.c:88):
+ * the flow waves and the LOS dependency waves of all goals are launched together.
+ * dests[ngoals]; targets: 4 ints per goal {chunk_r, chunk_c, tile_r, tile_c}. */
+int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
+                              const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls

@@ -47,7 +47,7 @@ SYMBOLS = [
     "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_map_build_nav", "pfnav_map_refresh_chunk",
     "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_plan_goal", "pfnav_flow_fields_update",
     "pfnav_flow_fields_update_dev", "pfnav_los_fields_create", "pfnav_los_fields_create_dev",
-    "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear", "pfnav_pool_request_goal",
+    "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear", "pfnav_pool_request_goal", "pfnav_pool_request_goals",
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
@@ -94,6 +94,8 @@ def load():
     L.pfnav_pool_put.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.pfnav_pool_clear.argtypes = [C.c_void_p]
     L.pfnav_pool_request_goal.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pfnav_pool_request_goals.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_agents_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     L.pfnav_agents_set_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_agents_tick.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -261,6 +263,14 @@ class Nav:
         nf, nl = C.c_int(0), C.c_int(0)
         _chk(self.L.pfnav_pool_request_goal(self.h, dest, layer, target_td[0], target_td[1], target_td[2],
                                             target_td[3], C.c_void_p(stream), C.byref(nf), C.byref(nl)))
+        return nf.value, nl.value
+
+    def pool_request_goals(self, dests, targets, layer=0, stream=0):
+        dests = np.ascontiguousarray(dests, np.int32)
+        targets = np.ascontiguousarray(targets, np.int32).reshape(-1, 4)
+        nf, nl = C.c_int(0), C.c_int(0)
+        _chk(self.L.pfnav_pool_request_goals(self.h, len(dests), _p(dests), layer, _p(targets), C.c_void_p(stream),
+                                             C.byref(nf), C.byref(nl)))
         return nf.value, nl.value
 
     # ---- agents ----

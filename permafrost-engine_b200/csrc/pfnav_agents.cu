@@ -622,7 +622,7 @@ struct TickParams {
 // ------------------------------------------------------------------------------------------
 // K6c: one warp per agent
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, 4)
 k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__restrict__ agents,
                  const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,

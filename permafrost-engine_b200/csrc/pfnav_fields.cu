@@ -662,6 +662,24 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
     for (int k = blockIdx.x * LOS_WARPS_PER_CTA + warp; k < n; k += total_warps) {
         const int i = first + k;
         const pfnav_los_req q = reqs[i];
+        // A chunk other than the destination whose shared edge with the previous chunk carries no
+        // `visible` and no `wavefront_blocked` tile starts with an empty frontier and draws no line
+        // (field.c:2157-2195): the field is all zero. Most chunks far from the goal end here.
+        if (!(q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c)) {
+            const uint8_t *prev = fields + (size_t)(out_slot ? out_slot[q.prev_index] : q.prev_index) * 4096;
+            int pe; bool horiz;
+            if (q.prev_chunk_r < q.chunk_r)      { horiz = false; pe = 63; }
+            else if (q.prev_chunk_r > q.chunk_r) { horiz = false; pe = 0;  }
+            else if (q.prev_chunk_c < q.chunk_c) { horiz = true;  pe = 63; }
+            else                                 { horiz = true;  pe = 0;  }
+            uint32_t any = 0;
+            for (int e = lane; e < 64; e += 32) any |= horiz ? prev[e * 64 + pe] : prev[pe * 64 + e];
+            if (!__any_sync(0xffffffffu, any != 0)) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(fields + (size_t)(out_slot ? out_slot[i] : i) * 4096);
+                for (int j = lane; j < 256; j += 32) d4[j] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
+        }
         // ---- stage tile -> bit rows (2 rows per lane) ----
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {

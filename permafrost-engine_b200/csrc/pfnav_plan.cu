@@ -258,27 +258,24 @@ extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int t
     return PFNAV_OK;
 }
 
-// n_request_path's field-building half, resident on the device: plan the goal, then run the flow
-// waves and the LOS chain straight into the field pool (no host round trip of field bytes).
-// Asynchronous on `stream` (the small request upload is stream-ordered too).
-extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_r, int tgt_chunk_c,
-                                       int tgt_tile_r, int tgt_tile_c, void *stream, int *out_n_flow, int *out_n_los)
+// n_request_path's field-building half, resident on the device, for a batch of goals: plan every
+// goal, then run the flow waves and the LOS dependency waves of ALL goals together straight into the
+// field pool (no host round trip of field bytes; one launch per wave, not per goal).
+// targets: 4 ints per goal {chunk_r, chunk_c, tile_r, tile_c}. Asynchronous on `stream`.
+extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
+                                        const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los)
 {
     PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
-    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    PF_ARG(ngoals >= 0 && (ngoals == 0 || (dests && targets)), "goals");
+    if (out_n_flow) *out_n_flow = 0;
+    if (out_n_los) *out_n_los = 0;
+    if (ngoals == 0) return PFNAV_OK;
     const int chunks = ctx->chunk_w * ctx->chunk_h;
     const int cap = chunks * 8 + 8;
-    std::vector<pfnav_field_req> fr(cap);
-    std::vector<pfnav_los_req> lr(cap);
-    std::vector<int32_t> fc(cap), fw(cap), lc(cap);
-    int nf = 0, nl = 0;
-    int rc = pfnav_plan_goal(ctx, layer, tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c, fr.data(), fc.data(), fw.data(),
-                             cap, &nf, lr.data(), lc.data(), cap, &nl);
-    if (rc) return rc;
-    PF_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    // pool slots for every chunk touched
-    auto slot_for = [&](int chunk, uint8_t bits) -> int {
+    std::vector<pfnav_field_req> fr(cap), all_fr;
+    std::vector<pfnav_los_req> lr(cap), all_lr;
+    std::vector<int32_t> fc(cap), fw(cap), lc(cap), all_fs, all_fw, all_ls, all_ld;
+    auto slot_for = [&](int dest, int chunk, uint8_t bits) -> int {
         const size_t si = (size_t)dest * chunks + chunk;
         int slot = ctx->h_pool_slot[si];
         if (slot < 0) {
@@ -289,26 +286,38 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
         ctx->h_pool_has[slot] |= bits;
         return slot;
     };
-    // order flow requests by wave (stable), LOS requests by dependency depth
-    int maxw = 0;
-    for (int i = 0; i < nf; i++) maxw = std::max(maxw, fw[i]);
-    std::vector<int> forder;
-    std::vector<int32_t> fwave_off(maxw + 2, 0);
-    for (int w = 0; w <= maxw; w++) {
-        for (int i = 0; i < nf; i++) if (fw[i] == w) forder.push_back(i);
-        fwave_off[w + 1] = (int32_t)forder.size();
+    for (int g = 0; g < ngoals; g++) {
+        PF_ARG(dests[g] >= 0 && dests[g] < ctx->pool_ndests, "dest");
+        int nf = 0, nl = 0;
+        int rc = pfnav_plan_goal(ctx, layer, targets[4 * g], targets[4 * g + 1], targets[4 * g + 2], targets[4 * g + 3],
+                                 fr.data(), fc.data(), fw.data(), cap, &nf, lr.data(), lc.data(), cap, &nl);
+        if (rc) return rc;
+        for (int i = 0; i < nf; i++) {
+            const int s = slot_for(dests[g], fc[i], 1);
+            if (s < 0) { pfnav_set_error("pfnav_pool_request_goals: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+            all_fr.push_back(fr[i]); all_fs.push_back(s); all_fw.push_back(fw[i]);
+        }
+        const int lbase = (int)all_lr.size();
+        std::vector<int> depth(nl, 0);
+        for (int i = 0; i < nl; i++) {
+            const int s = slot_for(dests[g], lc[i], 2);
+            if (s < 0) { pfnav_set_error("pfnav_pool_request_goals: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+            pfnav_los_req q = lr[i];
+            if (q.prev_index >= 0) { depth[i] = depth[q.prev_index] + 1; q.prev_index += lbase; }
+            all_lr.push_back(q); all_ls.push_back(s); all_ld.push_back(depth[i]);
+        }
     }
-    std::vector<int> depth(nl, 0), lorder(nl), lnew(nl);
-    int maxd = 0;
-    for (int i = 0; i < nl; i++) if (lr[i].prev_index >= 0) { depth[i] = depth[lr[i].prev_index] + 1; maxd = std::max(maxd, depth[i]); }
-    std::vector<int32_t> lwave_off(maxd + 2, 0);
-    for (int i = 0; i < nl; i++) lwave_off[depth[i] + 1]++;
+    const int nf = (int)all_fr.size(), nl = (int)all_lr.size();
+    // stable order by wave / depth
+    int maxw = 0, maxd = 0;
+    for (int i = 0; i < nf; i++) maxw = std::max(maxw, all_fw[i]);
+    for (int i = 0; i < nl; i++) maxd = std::max(maxd, all_ld[i]);
+    std::vector<int32_t> fwave_off(maxw + 2, 0), lwave_off(maxd + 2, 0);
+    for (int i = 0; i < nf; i++) fwave_off[all_fw[i] + 1]++;
+    for (int w = 0; w <= maxw; w++) fwave_off[w + 1] += fwave_off[w];
+    for (int i = 0; i < nl; i++) lwave_off[all_ld[i] + 1]++;
     for (int d = 0; d <= maxd; d++) lwave_off[d + 1] += lwave_off[d];
-    {
-        std::vector<int32_t> cur(lwave_off.begin(), lwave_off.end() - 1);
-        for (int i = 0; i < nl; i++) { lnew[i] = cur[depth[i]]++; lorder[lnew[i]] = i; }
-    }
-    // staging layout: [flow reqs][flow slots][los reqs][los slots]
+    std::vector<int> lnew(nl);
     const size_t b_fr = (size_t)nf * sizeof(pfnav_field_req), b_fs = (size_t)nf * 4;
     const size_t b_lr = (size_t)nl * sizeof(pfnav_los_req), b_ls = (size_t)nl * 4;
     const size_t total = b_fr + b_fs + b_lr + b_ls;
@@ -317,18 +326,20 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
     int32_t *hfs = (int32_t *)(host.data() + b_fr);
     pfnav_los_req *hlr = (pfnav_los_req *)(host.data() + b_fr + b_fs);
     int32_t *hls = (int32_t *)(host.data() + b_fr + b_fs + b_lr);
-    for (int k = 0; k < nf; k++) {
-        hfr[k] = fr[forder[k]];
-        hfs[k] = slot_for(fc[forder[k]], 1);
-        if (hfs[k] < 0) { pfnav_set_error("pfnav_pool_request_goal: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+    {
+        std::vector<int32_t> cur(fwave_off.begin(), fwave_off.end() - 1);
+        for (int i = 0; i < nf; i++) { const int k = cur[all_fw[i]]++; hfr[k] = all_fr[i]; hfs[k] = all_fs[i]; }
+        std::vector<int32_t> cur2(lwave_off.begin(), lwave_off.end() - 1);
+        for (int i = 0; i < nl; i++) lnew[i] = cur2[all_ld[i]]++;
+        for (int i = 0; i < nl; i++) {
+            pfnav_los_req q = all_lr[i];
+            if (q.prev_index >= 0) q.prev_index = lnew[q.prev_index];
+            hlr[lnew[i]] = q; hls[lnew[i]] = all_ls[i];
+        }
     }
-    for (int k = 0; k < nl; k++) {
-        hlr[k] = lr[lorder[k]];
-        if (hlr[k].prev_index >= 0) hlr[k].prev_index = lnew[hlr[k].prev_index];
-        hls[k] = slot_for(lc[lorder[k]], 2);
-        if (hls[k] < 0) { pfnav_set_error("pfnav_pool_request_goal: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
-    }
-    // NOTE: one staging buffer per context; callers serialise goal requests on one stream
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // one staging buffer per context: goal batches are serialised on one stream by the caller
     if (ctx->plan_buf_bytes < total) {
         PF_CUDA(cudaStreamSynchronize(st));
         cudaFree(ctx->d_plan_buf);
@@ -338,8 +349,7 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
     }
     uint8_t *dev = (uint8_t *)ctx->d_plan_buf;
     PF_CUDA(cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, st));
-    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + (size_t)dest * chunks, ctx->h_pool_slot.data() + (size_t)dest * chunks,
-                            (size_t)chunks * 4, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot, ctx->h_pool_slot.data(), ctx->h_pool_slot.size() * 4, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
                             cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaStreamSynchronize(st));      // `host` is pageable and about to go out of scope
@@ -347,6 +357,7 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
     const int32_t *dfs = (const int32_t *)(dev + b_fr);
     const pfnav_los_req *dlr = (const pfnav_los_req *)(dev + b_fr + b_fs);
     const int32_t *dls = (const int32_t *)(dev + b_fr + b_fs + b_lr);
+    int rc = 0;
     for (int w = 0; w <= maxw; w++) {
         const int first = fwave_off[w], cnt = fwave_off[w + 1] - first;
         if (cnt <= 0) continue;
@@ -358,4 +369,11 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
     if (out_n_flow) *out_n_flow = nf;
     if (out_n_los) *out_n_los = nl;
     return PFNAV_OK;
+}
+
+extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_r, int tgt_chunk_c,
+                                       int tgt_tile_r, int tgt_tile_c, void *stream, int *out_n_flow, int *out_n_los)
+{
+    const int32_t d = dest, t[4] = {tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c};
+    return pfnav_pool_request_goals(ctx, 1, &d, layer, t, stream, out_n_flow, out_n_los);
 }

@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Micro-benchmark (GPU box): flow-field and LOS-field kernels alone, device-resident requests,
+CUDA-event timing, L2 flushed between iterations. Prints one JSON line per variant."""
+import importlib, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+pf = importlib.import_module("permafrost-engine_b200")
+capi, synth = pf.capi, pf.synth
+
+def main():
+    cw = ch = 16
+    p = synth.make_map(cw, ch, 0x5EED0001)
+    cost = synth.cost_from_pathable(p, cw, ch)
+    nav = capi.Nav(0)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost); nav.map_build_nav(0)
+    rng = np.random.default_rng(0)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    tiles = synth.random_passable_tiles(cost, n, rng)
+    tile_reqs = np.concatenate([capi.tile_req((int(t[0]) // cw, int(t[0]) % cw), (int(t[1]), int(t[2]))) for t in tiles])
+    los_reqs = np.concatenate([capi.los_req((int(t[0]) // cw, int(t[0]) % cw), (int(t[0]) // cw, int(t[0]) % cw, int(t[1]), int(t[2]))) for t in tiles])
+    # portal requests: the planner's own requests for a few goals, repeated
+    pr = []
+    for t in tiles[:8]:
+        fr, fc, fw, lr, lc = nav.plan_goal((int(t[0]) // cw, int(t[0]) % cw, int(t[1]), int(t[2])))
+        pr.append(fr[(fw == 0) & (fr["target_type"] == capi.TARGET_PORTAL)])
+    portal_reqs = np.concatenate(pr)
+    portal_reqs = np.concatenate([portal_reqs] * (n // len(portal_reqs) + 1))[:n]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros((n, 4096), dtype=torch.uint8, device="cuda")
+    def timeit(fn, iters=5):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+    for name, reqs, bytes_per in (("flow_tile", tile_reqs, 16384), ("flow_portal", portal_reqs, 24704)):
+        d = torch.from_numpy(reqs.view(np.uint8)).cuda()
+        for tma in (0, 1):
+            nav.set_tma(tma)
+            ms = timeit(lambda: nav.flow_fields_update_dev(d.data_ptr(), n, out.data_ptr(), st))
+            print(json.dumps({"kernel": "k_flow_unit", "case": name, "tma": tma, "n": n, "ms": ms, "fields_per_s": n / ms * 1e3,
+                              "alg_GBps": n * bytes_per / ms / 1e6}), flush=True)
+        ms = timeit(lambda: nav.flow_fields_update_dev(d.data_ptr(), n, out.data_ptr(), st, general=True), iters=3)
+        print(json.dumps({"kernel": "k_flow_general", "case": name, "n": n, "ms": ms, "fields_per_s": n / ms * 1e3}), flush=True)
+    nl = min(n, 4096)
+    d = torch.from_numpy(los_reqs[:nl].view(np.uint8)).cuda()
+    ms = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), nl, out.data_ptr(), [0, nl], st), iters=3)
+    print(json.dumps({"kernel": "k_los", "case": "destination chunk", "n": nl, "ms": ms, "fields_per_s": nl / ms * 1e3,
+                      "alg_GBps": nl * 16512 / ms / 1e6}), flush=True)
+    ms1 = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), 1, out.data_ptr(), [0, 1], st), iters=3)
+    print(json.dumps({"kernel": "k_los", "case": "single field latency", "ms": ms1}), flush=True)
+
+if __name__ == "__main__":
+    main()
