@@ -168,6 +168,39 @@ int  pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int tgt_chunk_c
                      int32_t *flow_wave, int max_flow, int *n_flow, pfnav_los_req *los_out,
                      int32_t *los_chunk, int max_los, int *n_los);
 
+/* Cost-faithful routing structure of one layer (after pfnav_map_build_nav): portal edges with
+ * AStar_GridPath costs (nav.c:593, a_star.c:303), per-portal travel index (nav.c:1314), global
+ * islands (nav.c:1731), edge states (nav.c:693). Host-side; bit-identical costs and ids. */
+int  pfnav_route_build(pfnav_ctx *ctx, int layer);
+int  pfnav_route_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out);
+/* edges of one portal, 3 u32 per edge {neighbour portal_ref, edge_state, cost float bits} */
+int  pfnav_route_edges_get(pfnav_ctx *ctx, int layer, int chunk, int portal, uint32_t *out, int maxout,
+                           int *out_n);
+/* n_request_path (nav.c:1774-2047), request-generation half: the flow requests (with their
+ * N_FlowFieldID, field.c:1952) and LOS requests, in the reference's order, that the path src -> dst
+ * needs given what (dest, chunk) entries already exist: have_flow[chunk] = mapped ff_id or 0,
+ * have_los[chunk] = 0/1. LOS prev_index: -1 destination chunk, >= 0 index in this batch, -2 the
+ * previous chunk's field pre-exists (caller supplies it). *out_ok = the function's bool result. */
+int  pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, float src_z, float dst_x,
+                              float dst_z, const uint64_t *have_flow, const uint8_t *have_los,
+                              pfnav_field_req *flow_out, uint64_t *flow_ffid, int32_t *flow_chunk,
+                              int max_flow, int *n_flow, pfnav_los_req *los_out, int32_t *los_chunk,
+                              int max_los, int *n_los, uint32_t *out_dest_id, int *out_ok);
+/* N_RequestPath (nav.c:3386) against the device field pool: route src -> dst exactly as the
+ * reference does and build, on the device, the fields the pool does not hold yet for `dest`
+ * (cached (dest, chunk) entries and their ff_ids are honoured like the field cache's). */
+int  pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, float src_x, float src_z,
+                             float dst_x, float dst_z, void *stream, uint32_t *out_dest_id,
+                             int *out_ok, int *out_n_flow, int *out_n_los);
+/* Read one pool entry back (4096 B each, pointers may be NULL). *out_has: bit0 flow, bit1 LOS;
+ * *out_ffid: the N_FlowFieldID currently mapped for (dest, chunk). */
+int  pfnav_pool_get(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, uint8_t *flow_out,
+                    uint8_t *los_out, int *out_has, uint64_t *out_ffid);
+/* Host-only context for the HOST-side structure code above (islands, portals, routing) on a
+ * machine without a GPU. It has no compute path: kernel-launching entry points fail with
+ * PFNAV_ERR_NO_DEVICE. */
+int  pfnav_create_hostonly(pfnav_ctx **out);
+
 /* Selects how the 64x64 tiles are staged into shared memory: 1 = TMA tensor maps
  * (cp.async.bulk.tensor), 0 = plain coalesced loads. Default 1. */
 int  pfnav_set_tma(pfnav_ctx *ctx, int enable);

@@ -257,7 +257,10 @@ static void los_field_create(const pfo_map *m, const pfo_los_req *q, const uint8
     }
     while(frontier.size > 0) {
         int r, c; pq_pop(&frontier, &r, &c);
-        /* field_neighbours_grid_los (field.c:304) */
+        /* field_neighbours_grid_los (field.c:304): the neighbour list -- including the
+         * wavefront_blocked filter -- is collected BEFORE any neighbour is processed, so a line drawn
+         * while handling an earlier neighbour does not remove a later one from this pop */
+        int nbr[4][2], nn = 0;
         for(int dr = -1; dr <= 1; dr++) {
         for(int dc = -1; dc <= 1; dc++) {
             int ar = r + dr, ac = c + dc;
@@ -265,6 +268,11 @@ static void los_field_create(const pfo_map *m, const pfo_los_req *q, const uint8
             if(dr == 0 && dc == 0) continue;
             if(dr == dc || dr == -dc) continue;
             if(out.blk[ar][ac]) continue;
+            nbr[nn][0] = ar; nbr[nn][1] = ac; nn++;
+        }}
+        for(int i = 0; i < nn; i++) {
+        {
+            int ar = nbr[i][0], ac = nbr[i][1];
             uint8_t ncost = cost[ar * RES + ac];
             if(!tile_passable(m, cr, cc, ar, ac)) ncost = COST_IMPASSABLE;
             if(ncost > 1) {

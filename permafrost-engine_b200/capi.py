@@ -45,7 +45,8 @@ FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 
 SYMBOLS = [
     "pfnav_last_error", "pfnav_version", "pfnav_create", "pfnav_destroy", "pfnav_map_create",
     "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_map_build_nav", "pfnav_map_refresh_chunk",
-    "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_plan_goal", "pfnav_flow_fields_update",
+    "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_plan_goal", "pfnav_route_build", "pfnav_route_islands_get",
+    "pfnav_route_edges_get", "pfnav_route_request_path", "pfnav_create_hostonly", "pfnav_pool_request_path", "pfnav_pool_get", "pfnav_flow_fields_update",
     "pfnav_flow_fields_update_dev", "pfnav_los_fields_create", "pfnav_los_fields_create_dev",
     "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear", "pfnav_pool_request_goal", "pfnav_pool_request_goals",
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
@@ -84,6 +85,16 @@ def load():
     L.pfnav_portals_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.pfnav_plan_goal.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.pfnav_create_hostonly.argtypes = [C.POINTER(C.c_void_p)]
+    L.pfnav_pool_request_path.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pfnav_pool_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    L.pfnav_route_build.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_route_islands_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pfnav_route_edges_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.pfnav_route_request_path.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                           C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     L.pfnav_flow_fields_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_flow_fields_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.pfnav_flow_fields_update_general_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -157,10 +168,14 @@ def los_req(chunk, target_td, layer=0, prev_index=-1, prev_chunk=(0, 0)):
 class Nav:
     """One device navigation context (what `struct nav_private` is to the reference)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, hostonly=False):
+        """hostonly=True: a context with NO compute path, for the host-side structure code only"""
         self.L = load()
         h = C.c_void_p()
-        _chk(self.L.pfnav_create(device, C.byref(h)))
+        if hostonly:
+            _chk(self.L.pfnav_create_hostonly(C.byref(h)))
+        else:
+            _chk(self.L.pfnav_create(device, C.byref(h)))
         self.h = h
         self.nwork = 0
 
@@ -220,6 +235,32 @@ class Nav:
                                     _p(fr), _p(fc), _p(fw), cap, C.byref(nf), _p(lr), _p(lc), cap, C.byref(nl)))
         return fr[:nf.value].copy(), fc[:nf.value].copy(), fw[:nf.value].copy(), lr[:nl.value].copy(), lc[:nl.value].copy()
 
+    def route_build(self, layer=0):
+        _chk(self.L.pfnav_route_build(self.h, layer))
+
+    def route_islands(self, layer=0):
+        out = np.zeros((self.cw * self.ch, 64, 64), np.uint16)
+        _chk(self.L.pfnav_route_islands_get(self.h, layer, _p(out)))
+        return out
+
+    def route_edges(self, chunk_idx, portal_idx, layer=0):
+        out = np.zeros((64, 3), np.uint32); n = C.c_int(0)
+        _chk(self.L.pfnav_route_edges_get(self.h, layer, chunk_idx, portal_idx, _p(out), 64, C.byref(n)))
+        return out[:n.value]
+
+    def route_request_path(self, src, dst, layer=0, have_flow=None, have_los=None):
+        """-> ok, dest_id, flow_reqs, flow_ffid, flow_chunk, los_reqs, los_chunk"""
+        chunks = self.cw * self.ch
+        hf = np.zeros(chunks, np.uint64) if have_flow is None else np.ascontiguousarray(have_flow, np.uint64)
+        hl = np.zeros(chunks, np.uint8) if have_los is None else np.ascontiguousarray(have_los, np.uint8)
+        cap = chunks * 4 + 8
+        fr = np.zeros(cap, FIELD_REQ); fid = np.zeros(cap, np.uint64); fc = np.zeros(cap, np.int32)
+        lr = np.zeros(cap, LOS_REQ); lc = np.zeros(cap, np.int32)
+        nf, nl, ok, did = C.c_int(0), C.c_int(0), C.c_int(0), C.c_uint32(0)
+        _chk(self.L.pfnav_route_request_path(self.h, layer, src[0], src[1], dst[0], dst[1], _p(hf), _p(hl), _p(fr), _p(fid), _p(fc),
+                                             cap, C.byref(nf), _p(lr), _p(lc), cap, C.byref(nl), C.byref(did), C.byref(ok)))
+        return bool(ok.value), did.value, fr[:nf.value].copy(), fid[:nf.value].copy(), fc[:nf.value].copy(), lr[:nl.value].copy(), lc[:nl.value].copy()
+
     def set_tma(self, enable):
         _chk(self.L.pfnav_set_tma(self.h, int(enable)))
 
@@ -264,6 +305,20 @@ class Nav:
         _chk(self.L.pfnav_pool_request_goal(self.h, dest, layer, target_td[0], target_td[1], target_td[2],
                                             target_td[3], C.c_void_p(stream), C.byref(nf), C.byref(nl)))
         return nf.value, nl.value
+
+    def pool_request_path(self, dest, src, dst, layer=0, stream=0):
+        """-> ok, dest_id, n_flow, n_los"""
+        did, ok, nf, nl = C.c_uint32(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _chk(self.L.pfnav_pool_request_path(self.h, dest, layer, src[0], src[1], dst[0], dst[1], C.c_void_p(stream),
+                                            C.byref(did), C.byref(ok), C.byref(nf), C.byref(nl)))
+        return bool(ok.value), did.value, nf.value, nl.value
+
+    def pool_get(self, dest, chunk):
+        """-> (flow or None, los or None, ffid)"""
+        f = np.zeros((64, 64), np.uint8); l = np.zeros((64, 64), np.uint8)
+        has, ffid = C.c_int(0), C.c_uint64(0)
+        _chk(self.L.pfnav_pool_get(self.h, dest, chunk[0], chunk[1], _p(f), _p(l), C.byref(has), C.byref(ffid)))
+        return (f if has.value & 1 else None), (l if has.value & 2 else None), ffid.value
 
     def pool_request_goals(self, dests, targets, layer=0, stream=0):
         dests = np.ascontiguousarray(dests, np.int32)

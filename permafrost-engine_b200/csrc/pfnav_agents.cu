@@ -818,6 +818,7 @@ void pfnav_agents_free(pfnav_ctx *ctx)
 extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     PF_ARG(ndests > 0 && max_fields > 0, "ndests/max_fields");
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
@@ -831,6 +832,7 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)max_fields * 4096, 0, max_fields));
     ctx->h_pool_slot.assign(nslots, -1);
     ctx->h_pool_has.assign(max_fields, 0);
+    ctx->h_pool_ffid.assign(nslots, 0);
     ctx->pool_ndests = ndests; ctx->pool_max = max_fields; ctx->pool_used = 0;
     return PFNAV_OK;
 }
@@ -843,6 +845,7 @@ extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, 0, ctx->pool_max));
     std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
     std::fill(ctx->h_pool_has.begin(), ctx->h_pool_has.end(), 0);
+    std::fill(ctx->h_pool_ffid.begin(), ctx->h_pool_ffid.end(), 0);
     ctx->pool_used = 0;
     return PFNAV_OK;
 }
@@ -918,6 +921,7 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
                                    size_t nflocks, int hz)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     PF_ARG(n == 0 || agents, "agents");
     PF_ARG(nflocks == 0 || flocks, "flocks");
     PF_ARG(hz == 20 || hz == 10 || hz == 5 || hz == 1, "hz must be 20, 10, 5 or 1 (movement.c:2210)");

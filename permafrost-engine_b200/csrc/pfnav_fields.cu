@@ -666,7 +666,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
         // `visible` and no `wavefront_blocked` tile starts with an empty frontier and draws no line
         // (field.c:2157-2195): the field is all zero. Most chunks far from the goal end here.
         if (!(q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c)) {
-            const uint8_t *prev = fields + (size_t)(out_slot ? out_slot[q.prev_index] : q.prev_index) * 4096;
+            const uint8_t *prev = fields + (size_t)(q.prev_index >= 0 ? (out_slot ? out_slot[q.prev_index] : q.prev_index) : q._pad) * 4096;
             int pe; bool horiz;
             if (q.prev_chunk_r < q.chunk_r)      { horiz = false; pe = 63; }
             else if (q.prev_chunk_r > q.chunk_r) { horiz = false; pe = 0;  }
@@ -721,7 +721,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
                 s.assigned[q.tgt_tile_r] |= 1ull << q.tgt_tile_c;
             } else {
                 // carry the shared edge over from the previous chunk's field (field.c:2122-2196)
-                const uint8_t *prev = fields + (size_t)(out_slot ? out_slot[q.prev_index] : q.prev_index) * 4096;
+                const uint8_t *prev = fields + (size_t)(q.prev_index >= 0 ? (out_slot ? out_slot[q.prev_index] : q.prev_index) : q._pad) * 4096;
                 bool horizontal; int curr_edge, prev_edge;
                 if (q.prev_chunk_r < q.chunk_r)      { horizontal = false; curr_edge = 0;  prev_edge = 63; }
                 else if (q.prev_chunk_r > q.chunk_r) { horizontal = false; curr_edge = 63; prev_edge = 0;  }
@@ -749,12 +749,21 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
                 const uint16_t nprio = (uint16_t)((((cur >> 12) + 1) & 3) << 12);
                 // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0)
                 const int nr[4] = {r - 1, r, r, r + 1}, ncc[4] = {c, c - 1, c + 1, c};
-#pragma unroll 1
+                // the neighbour list (incl. the wavefront_blocked filter) is collected before any
+                // neighbour is processed (field.c:2205): a line drawn for an earlier neighbour of this
+                // pop must not hide a later one
+                uint32_t take = 0;
+#pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int rr = nr[e], cc = ncc[e];
                     if (rr < 0 || rr > 63 || cc < 0 || cc > 63) continue;
+                    if (!((s.blk[rr] >> cc) & 1)) take |= 1u << e;
+                }
+#pragma unroll 1
+                for (int e = 0; e < 4; e++) {
+                    if (!((take >> e) & 1)) continue;
+                    const int rr = nr[e], cc = ncc[e];
                     const uint64_t bit = 1ull << cc;
-                    if (s.blk[rr] & bit) continue;
                     if (!(s.open[rr] & bit)) {
                         if (!los_is_corner(s, rr, cc)) continue;
                         los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
@@ -865,6 +874,18 @@ extern "C" int pfnav_create(int device, pfnav_ctx **out)
     return PFNAV_OK;
 }
 
+// Host-only context: holds the host mirrors of the map so that the HOST-side structure code
+// (local islands, portals, routing) can be exercised on a machine without a GPU. It has NO compute
+// path: every entry point that would launch a kernel fails with PFNAV_ERR_NO_DEVICE.
+extern "C" int pfnav_create_hostonly(pfnav_ctx **out)
+{
+    if (!out) { pfnav_set_error("pfnav_create_hostonly: out == NULL"); return PFNAV_ERR_ARG; }
+    pfnav_ctx *ctx = new pfnav_ctx();
+    ctx->device = -1;
+    *out = ctx;
+    return PFNAV_OK;
+}
+
 int pfnav_fields_init(pfnav_ctx *ctx)
 {
     PF_CUDA(cudaFuncSetAttribute(k_flow_unit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -888,9 +909,13 @@ void pfnav_fields_free(pfnav_ctx *ctx)
     ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
 }
 
+void pfnav_route_forget(const pfnav_ctx *ctx);
+
 extern "C" void pfnav_destroy(pfnav_ctx *ctx)
 {
     if (!ctx) return;
+    pfnav_route_forget(ctx);
+    if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     pfnav_fields_free(ctx);
@@ -947,12 +972,19 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     PF_ARG(ctx, "ctx");
     PF_ARG(chunk_w > 0 && chunk_h > 0 && chunk_w <= 64 && chunk_h <= 64, "chunk_w/chunk_h must be in 1..64 (dest_id has 6 bits per chunk coordinate, nav.c:841)");
     PF_ARG(nlayers > 0 && nlayers <= PFNAV_NAV_LAYER_MAX, "nlayers");
-    PF_CUDA(cudaSetDevice(ctx->device));
-    free_map(ctx);
     ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
     ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;
     ctx->map_x = map_x; ctx->map_z = map_z;
     const size_t tiles = (size_t)ctx->W64 * ctx->H64 * nlayers;
+    if (ctx->device < 0) {
+        ctx->d_cost = reinterpret_cast<uint8_t *>(1);      // "map created" marker; never dereferenced
+        ctx->h_unit.assign((size_t)chunk_w * chunk_h * nlayers, 1);
+        ctx->h_cost.assign(tiles, 0xFF); ctx->h_blk.assign(tiles, 0); ctx->h_liid.assign(tiles, 0xFFFF);
+        ctx->portals.assign(nlayers, {});
+        return PFNAV_OK;
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    free_map(ctx);
     PF_CUDA(cudaMalloc(&ctx->d_cost, tiles));
     PF_CUDA(cudaMalloc(&ctx->d_blk, tiles * 2));
     PF_CUDA(cudaMalloc(&ctx->d_liid, tiles * 2));
@@ -989,15 +1021,22 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(cost_base, "cost_base");
-    PF_CUDA(cudaSetDevice(ctx->device));
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    if (ctx->device < 0) {
+        memmove(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);
+        if (blockers) memmove(ctx->h_blk.data() + ltiles * layer, blockers, ltiles * 2);
+        else std::fill(ctx->h_blk.begin() + ltiles * layer, ctx->h_blk.begin() + ltiles * (layer + 1), 0);
+        if (local_islands) memmove(ctx->h_liid.data() + ltiles * layer, local_islands, ltiles * 2);
+        return PFNAV_OK;
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
     int rc = ensure_stage(ctx, ltiles * 2);
     if (rc) return rc;
     const int nblk = std::min<size_t>((ltiles + 255) / 256, 148 * 8);
-    memcpy(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);
-    if (blockers) memcpy(ctx->h_blk.data() + ltiles * layer, blockers, ltiles * 2);
+    memmove(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);      // callers may pass the mirrors themselves
+    if (blockers) memmove(ctx->h_blk.data() + ltiles * layer, blockers, ltiles * 2);
     else std::fill(ctx->h_blk.begin() + ltiles * layer, ctx->h_blk.begin() + ltiles * (layer + 1), 0);
-    if (local_islands) memcpy(ctx->h_liid.data() + ltiles * layer, local_islands, ltiles * 2);
+    if (local_islands) memmove(ctx->h_liid.data() + ltiles * layer, local_islands, ltiles * 2);
     PF_CUDA(cudaMemcpy(ctx->d_stage, cost_base, ltiles, cudaMemcpyHostToDevice));
     k_deblock<uint8_t><<<nblk, 256>>>((const uint8_t *)ctx->d_stage, ctx->d_cost + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
     ctx->launches++;
@@ -1023,13 +1062,14 @@ extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, in
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk coords");
-    PF_CUDA(cudaSetDevice(ctx->device));
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     const size_t off = ltiles * layer + (size_t)chunk_r * 64 * ctx->W64 + chunk_c * 64;
     const size_t hoff = ltiles * layer + ((size_t)chunk_r * ctx->chunk_w + chunk_c) * 4096;
-    if (cost_base) memcpy(ctx->h_cost.data() + hoff, cost_base, 4096);
-    if (blockers) memcpy(ctx->h_blk.data() + hoff, blockers, 8192);
-    if (local_islands) memcpy(ctx->h_liid.data() + hoff, local_islands, 8192);
+    if (cost_base) memmove(ctx->h_cost.data() + hoff, cost_base, 4096);
+    if (blockers) memmove(ctx->h_blk.data() + hoff, blockers, 8192);
+    if (local_islands) memmove(ctx->h_liid.data() + hoff, local_islands, 8192);
+    if (ctx->device < 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
     if (cost_base)
         PF_CUDA(cudaMemcpy2D(ctx->d_cost + off, ctx->W64, cost_base, 64, 64, 64, cudaMemcpyHostToDevice));
     if (blockers)
@@ -1071,6 +1111,7 @@ int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, u
                       const int32_t *d_out_slot, void *stream)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     if (n == 0) return PFNAV_OK;
     PF_ARG(d_reqs && d_inout_fields, "null buffer");
     PF_ARG(n < (1u << 30), "n");
@@ -1107,6 +1148,7 @@ extern "C" int pfnav_flow_fields_update_general_dev(pfnav_ctx *ctx, const pfnav_
                                                     uint8_t *d_inout_fields, void *stream)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     if (n == 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
     const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
@@ -1139,6 +1181,7 @@ static int validate_field_reqs(const pfnav_ctx *ctx, const pfnav_field_req *reqs
 extern "C" int pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *reqs, size_t n, uint8_t *inout_fields)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     if (n == 0) return PFNAV_OK;
     PF_ARG(reqs && inout_fields, "null buffer");
     int rc = validate_field_reqs(ctx, reqs, n);
@@ -1180,6 +1223,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
                      const int32_t *d_out_slot, int n_waves, const int32_t *h_wave_offsets, void *stream)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     if (n == 0) return PFNAV_OK;
     PF_ARG(d_reqs && d_out_fields && n_waves >= 1 && h_wave_offsets, "null buffer");
     PF_CUDA(cudaSetDevice(ctx->device));
@@ -1201,6 +1245,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
 extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs, size_t n, uint8_t *out_fields)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
     if (n == 0) return PFNAV_OK;
     PF_ARG(reqs && out_fields, "null buffer");
     // dependency depth = wave; requests are re-ordered wave-major on the device side

@@ -22,6 +22,14 @@ void pfnav_set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 
+#define PF_NEED_DEVICE(ctx)                                                                         \
+    do {                                                                                            \
+        if ((ctx)->device < 0) {                                                                    \
+            pfnav_set_error("%s: host-only context has no compute path (no CPU fallback)", __func__); \
+            return PFNAV_ERR_NO_DEVICE;                                                             \
+        }                                                                                           \
+    } while (0)
+
 #define PF_ARG(cond, msg)                                                                   \
     do {                                                                                    \
         if (!(cond)) {                                                                      \
@@ -69,6 +77,7 @@ struct pfnav_ctx {
     int32_t *d_pool_slot = nullptr;   // [ndests][chunks] -> slot or -1
     std::vector<int32_t> h_pool_slot;
     std::vector<uint8_t> h_pool_has;
+    std::vector<uint64_t> h_pool_ffid;     // [ndests][chunks]: ff_id currently mapped (dest, chunk) -> field, 0 = none
     void *d_plan_buf = nullptr; size_t plan_buf_bytes = 0;    // request staging for pfnav_pool_request_goal
     uint8_t *d_pool_flow = nullptr;   // [max][4096]
     uint8_t *d_pool_los = nullptr;    // [max][4096]

@@ -111,7 +111,7 @@ extern "C" int pfnav_map_build_nav(pfnav_ctx *ctx, int layer)
                             ch, ctx->portals[layer][ch].size());
             return PFNAV_ERR_STATE;
         }
-    // push the islands to the device image
+    // push the islands to the device image (host-only contexts just keep the mirrors)
     return pfnav_map_upload_layer(ctx, layer, ctx->h_cost.data() + ltiles * layer, ctx->h_blk.data() + ltiles * layer,
                                   ctx->h_liid.data() + ltiles * layer);
 }
@@ -266,6 +266,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
                                         const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los)
 {
     PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_NEED_DEVICE(ctx);
     PF_ARG(ngoals >= 0 && (ngoals == 0 || (dests && targets)), "goals");
     if (out_n_flow) *out_n_flow = 0;
     if (out_n_los) *out_n_los = 0;

@@ -1,0 +1,795 @@
+// pfnav_route.cu -- host-side, cost-faithful restatement of the reference's hierarchical path
+// request (the part of the hot path that decides WHICH chunk fields a destination needs).
+//
+// Restates (reference file:line):
+//   n_update_island_field / n_visit_island              src/navigation/nav.c:1731-1772, 856-901
+//   n_link_chunk_portals + AStar_GridPath               src/navigation/nav.c:593-636, a_star.c:303-427
+//   n_build_portal_travel_index + N_GridNeighbours      src/navigation/nav.c:1314-1363, 4878-4910
+//   n_update_edge_states / n_local_ports_connected      src/navigation/nav.c:668-717
+//   N_PortalReachableFromTile                           src/navigation/nav.c:4852
+//   N_ClosestPathableLocalIsland                        src/navigation/nav.c:5131
+//   n_closest_reachable_portal / _from_location         src/navigation/nav.c:1365, 1398
+//   AStar_PortalGraphPath + neighbours_portal_graph     src/navigation/a_star.c:429-552, 212-262
+//   n_request_path                                      src/navigation/nav.c:1774-2047
+//   N_FlowFieldID                                       src/navigation/field.c:1952
+//
+// Everything here is pointer-heavy host logic over a tiny graph; the fields it asks for are built by
+// the CUDA kernels. Float costs follow the reference's evaluation order exactly (same heap, same
+// neighbour order), because the chosen portal path depends on them.
+#include "pfnav_internal.cuh"
+#include <algorithm>
+#include <deque>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+#include <unordered_map>
+
+namespace {
+
+struct coord { int r, c; };
+struct tdesc { int chunk_r, chunk_c, tile_r, tile_c; };
+
+// pqueue.h:109-208 (1-indexed heap, float priority, hole sift)
+template <class T>
+struct pq {
+    struct node { float prio; T data; };
+    std::vector<node> n{1};
+    int size = 0;
+    void push(float prio, const T &d)
+    {
+        if ((int)n.size() < size + 2) n.resize(std::max<size_t>(32, n.size() * 2));
+        int curr = size + 1, parent = curr / 2;
+        while (curr > 1 && n[parent].prio > prio) { n[curr] = n[parent]; curr = parent; parent /= 2; }
+        n[curr].prio = prio; n[curr].data = d;
+        size++;
+    }
+    T pop()
+    {
+        T out = n[1].data;
+        n[1] = n[size--];
+        int root = 1;
+        while (root != size + 1) {
+            int target = size + 1;
+            const int l = root * 2, r = l + 1;
+            if (l <= size && n[l].prio < n[target].prio) target = l;
+            if (r <= size && n[r].prio < n[target].prio) target = r;
+            n[root] = n[target];
+            root = target;
+        }
+        return out;
+    }
+};
+
+// N_GridNeighbours (nav.c:4878) == a_star.c neighbours_grid (:101)
+static int grid_neighbours(const uint8_t *cost, coord at, coord *out, float *costs)
+{
+    int ret = 0;
+    for (int r = -1; r <= 1; r++)
+        for (int c = -1; c <= 1; c++) {
+            const int ar = at.r + r, ac = at.c + c;
+            if (ar < 0 || ar >= 64 || ac < 0 || ac >= 64) continue;
+            if (r == 0 && c == 0) continue;
+            if (cost[ar * 64 + ac] == 0xFF) continue;
+            const bool diag = (r == c) || (r == -c);
+            if (diag && cost[ar * 64 + at.c] == 0xFF && cost[at.r * 64 + ac] == 0xFF) continue;
+            const float cost_mult = diag ? (float)sqrt(2) : 1.0f;
+            out[ret] = {ar, ac};
+            costs[ret] = cost[ar * 64 + ac] * cost_mult;
+            ret++;
+        }
+    return ret;
+}
+
+// heuristic (a_star.c:282)
+static float heuristic(coord a, coord b)
+{
+    const float D = 1.0f;
+    const float D2 = sqrt(2) * D;
+    const int dx = abs(a.r - b.r), dy = abs(a.c - b.c);
+    return D * (dx + dy) + (D2 - 2 * D) * std::min(dx, dy);
+}
+
+// AStar_GridPath (a_star.c:303), cost only
+static bool astar_grid_cost(const uint8_t *cost, coord start, coord finish, float *out_cost)
+{
+    pq<coord> frontier;
+    float running[4096];
+    bool has_cost[4096], has_from[4096];
+    memset(has_cost, 0, sizeof(has_cost));
+    memset(has_from, 0, sizeof(has_from));
+    running[start.r * 64 + start.c] = 0.0f;
+    has_cost[start.r * 64 + start.c] = true;
+    frontier.push(0.0f, start);
+    while (frontier.size > 0) {
+        const coord curr = frontier.pop();
+        if (curr.r == finish.r && curr.c == finish.c) break;
+        coord nb[8]; float nc[8];
+        const int n = grid_neighbours(cost, curr, nb, nc);
+        for (int i = 0; i < n; i++) {
+            const int k = nb[i].r * 64 + nb[i].c;
+            const float new_cost = running[curr.r * 64 + curr.c] + nc[i];
+            if (!has_cost[k] || new_cost < running[k]) {
+                running[k] = new_cost; has_cost[k] = true;
+                frontier.push(new_cost + heuristic(finish, nb[i]), nb[i]);
+                has_from[k] = true;
+            }
+        }
+    }
+    if (!has_from[finish.r * 64 + finish.c]) return false;
+    *out_cost = running[finish.r * 64 + finish.c];
+    return true;
+}
+
+static inline uint16_t cost_pack(float cost)          // portal_cost_pack (nav_data.h:56)
+{
+    if (cost == FLT_MAX) return 0xffff;
+    const float scaled = cost * 8 + 0.5f;
+    if (scaled >= 0xffff) return 0xffff - 1;
+    return (uint16_t)scaled;
+}
+static inline float cost_unpack(uint16_t p) { return p == 0xffff ? FLT_MAX : (float)p / 8; }
+
+}   // namespace
+
+struct pfnav_route_edge { int es; int nb; float cost; };          // nb: portal index in the same chunk
+struct pfnav_route_chunk {
+    std::vector<std::vector<pfnav_route_edge>> edges;             // per portal
+    std::vector<uint16_t> travel;                                 // [nportals][4096]
+};
+struct pfnav_route_layer {
+    bool built = false;
+    std::vector<pfnav_route_chunk> chunks;
+    std::vector<uint16_t> islands;                                // global islands, chunk-blocked
+};
+static std::unordered_map<const pfnav_ctx *, std::vector<pfnav_route_layer>> g_routes;
+
+void pfnav_route_forget(const pfnav_ctx *ctx) { g_routes.erase(ctx); }
+
+static inline const uint8_t *L_cost(const pfnav_ctx *ctx, int layer, int chunk)
+{ return ctx->h_cost.data() + ((size_t)layer * ctx->chunk_w * ctx->chunk_h + chunk) * 4096; }
+static inline const uint16_t *L_blk(const pfnav_ctx *ctx, int layer, int chunk)
+{ return ctx->h_blk.data() + ((size_t)layer * ctx->chunk_w * ctx->chunk_h + chunk) * 4096; }
+static inline const uint16_t *L_liid(const pfnav_ctx *ctx, int layer, int chunk)
+{ return ctx->h_liid.data() + ((size_t)layer * ctx->chunk_w * ctx->chunk_h + chunk) * 4096; }
+
+// n_update_edge_states (nav.c:693) for one chunk
+static void update_edge_states(pfnav_ctx *ctx, pfnav_route_layer &RL, int layer, int chunk)
+{
+    const auto &ports = ctx->portals[layer][chunk];
+    const uint16_t *blk = L_blk(ctx, layer, chunk), *li = L_liid(ctx, layer, chunk);
+    for (size_t i = 0; i < ports.size(); i++)
+        for (auto &e : RL.chunks[chunk].edges[i]) {
+            const auto &a = ports[i], &b = ports[e.nb];
+            bool conn = false;
+            for (int r1 = a.r0; r1 <= a.r1 && !conn; r1++)
+                for (int c1 = a.c0; c1 <= a.c1 && !conn; c1++) {
+                    if (blk[r1 * 64 + c1] > 0) continue;
+                    for (int r2 = b.r0; r2 <= b.r1 && !conn; r2++)
+                        for (int c2 = b.c0; c2 <= b.c1; c2++) {
+                            if (blk[r2 * 64 + c2] > 0) continue;
+                            if (li[r1 * 64 + c1] == li[r2 * 64 + c2]) { conn = true; break; }
+                        }
+                }
+            e.es = conn ? 0 : 1;       // EDGE_STATE_ACTIVE : EDGE_STATE_BLOCKED
+        }
+}
+
+// Build the routing structure of one layer (needs pfnav_map_build_nav first).
+extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG((size_t)layer < ctx->portals.size() && !ctx->portals[layer].empty(), "pfnav_map_build_nav not called for this layer");
+    auto &RV = g_routes[ctx];
+    if ((int)RV.size() < ctx->nlayers) RV.resize(ctx->nlayers);
+    pfnav_route_layer &RL = RV[layer];
+    const int cw = ctx->chunk_w, chh = ctx->chunk_h, chunks = cw * chh;
+    RL.chunks.assign(chunks, {});
+    for (int ch = 0; ch < chunks; ch++) {
+        const auto &ports = ctx->portals[layer][ch];
+        const uint8_t *cost = L_cost(ctx, layer, ch);
+        auto &RC = RL.chunks[ch];
+        RC.edges.assign(ports.size(), {});
+        // n_link_chunk_portals (nav.c:593): A* between portal centres, i-major j-minor
+        for (size_t i = 0; i < ports.size(); i++)
+            for (size_t j = 0; j < ports.size(); j++) {
+                if (i == j) continue;
+                const coord a = {(ports[i].r0 + ports[i].r1) / 2, (ports[i].c0 + ports[i].c1) / 2};
+                const coord b = {(ports[j].r0 + ports[j].r1) / 2, (ports[j].c0 + ports[j].c1) / 2};
+                float c;
+                if (astar_grid_cost(cost, a, b, &c)) RC.edges[i].push_back({0, (int)j, c});
+            }
+        // n_build_portal_travel_index (nav.c:1314): FIFO expansion, first visit fixes the cost
+        RC.travel.assign(ports.size() * 4096, 0xffff);
+        for (size_t pi = 0; pi < ports.size(); pi++) {
+            bool visited[4096];
+            memset(visited, 0, sizeof(visited));
+            std::deque<std::pair<float, coord>> q;
+            for (int r = ports[pi].r0; r <= ports[pi].r1; r++)
+                for (int c = ports[pi].c0; c <= ports[pi].c1; c++) { q.push_back({0.0f, {r, c}}); visited[r * 64 + c] = true; }
+            while (!q.empty()) {
+                const auto cur = q.front();
+                q.pop_front();
+                RC.travel[pi * 4096 + cur.second.r * 64 + cur.second.c] = cost_pack(cur.first);
+                coord nb[8]; float nc[8];
+                const int n = grid_neighbours(cost, cur.second, nb, nc);
+                for (int i = 0; i < n; i++) {
+                    const int k = nb[i].r * 64 + nb[i].c;
+                    if (visited[k]) continue;
+                    q.push_back({cur.first + nc[i], nb[i]});
+                    visited[k] = true;
+                }
+            }
+        }
+    }
+    // n_update_island_field (nav.c:1731): global islands ignoring blockers, ids from 0
+    RL.islands.assign((size_t)chunks * 4096, 0xffff);
+    {
+        uint16_t id = 0;
+        std::deque<tdesc> q;
+        for (int cr = 0; cr < chh; cr++)
+            for (int cc = 0; cc < cw; cc++)
+                for (int t = 0; t < 4096; t++) {
+                    const int ch = cr * cw + cc;
+                    if (RL.islands[(size_t)ch * 4096 + t] != 0xffff || L_cost(ctx, layer, ch)[t] == 0xFF) continue;
+                    RL.islands[(size_t)ch * 4096 + t] = id;
+                    q.push_back({cr, cc, t >> 6, t & 63});
+                    while (!q.empty()) {
+                        const tdesc cur = q.front();
+                        q.pop_front();
+                        const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+                        for (int e = 0; e < 4; e++) {
+                            const int ar = cur.chunk_r * 64 + cur.tile_r + dr[e], ac = cur.chunk_c * 64 + cur.tile_c + dc[e];
+                            if (ar < 0 || ar >= chh * 64 || ac < 0 || ac >= cw * 64) continue;
+                            const int nch = (ar >> 6) * cw + (ac >> 6), nt = (ar & 63) * 64 + (ac & 63);
+                            if (RL.islands[(size_t)nch * 4096 + nt] == 0xffff && L_cost(ctx, layer, nch)[nt] != 0xFF) {
+                                RL.islands[(size_t)nch * 4096 + nt] = id;
+                                q.push_back({ar >> 6, ac >> 6, ar & 63, ac & 63});
+                            }
+                        }
+                    }
+                    id++;
+                }
+    }
+    for (int ch = 0; ch < chunks; ch++) update_edge_states(ctx, RL, layer, ch);
+    RL.built = true;
+    return PFNAV_OK;
+}
+
+// Read-back for parity tests: islands and the edge table of one portal (neighbour ref, state, cost)
+extern "C" int pfnav_route_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out)
+{
+    PF_ARG(ctx && out, "args");
+    auto it = g_routes.find(ctx);
+    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
+    memcpy(out, it->second[layer].islands.data(), it->second[layer].islands.size() * 2);
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_route_edges_get(pfnav_ctx *ctx, int layer, int chunk, int portal, uint32_t *out, int maxout, int *out_n)
+{
+    PF_ARG(ctx && out && out_n, "args");
+    auto it = g_routes.find(ctx);
+    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
+    const auto &RL = it->second[layer];
+    PF_ARG(chunk >= 0 && chunk < (int)RL.chunks.size() && portal >= 0 && portal < (int)RL.chunks[chunk].edges.size(), "chunk/portal");
+    int n = 0;
+    for (const auto &e : RL.chunks[chunk].edges[portal]) {
+        if (n >= maxout) break;
+        out[n * 3 + 0] = ((uint32_t)chunk << 8) | (uint32_t)e.nb;        // portal_ref_make (nav_data.h:90)
+        out[n * 3 + 1] = (uint32_t)e.es;
+        memcpy(&out[n * 3 + 2], &e.cost, 4);
+        n++;
+    }
+    *out_n = n;
+    return PFNAV_OK;
+}
+
+namespace {
+
+struct Router {
+    pfnav_ctx *ctx; pfnav_route_layer &RL; int layer; int cw, chh;
+    const pfnav_ctx::portal_t &P(int chunk, int idx) const { return ctx->portals[layer][chunk][idx]; }
+    int nports(int chunk) const { return (int)ctx->portals[layer][chunk].size(); }
+    const uint16_t *li(int chunk) const { return L_liid(ctx, layer, chunk); }
+
+    // N_PortalReachableFromTile (nav.c:4852)
+    bool portal_reachable_from_tile(int chunk, int pi, coord tile) const
+    {
+        const auto &p = P(chunk, pi);
+        const uint16_t *l = li(chunk);
+        for (int r = p.r0; r <= p.r1; r++)
+            for (int c = p.c0; c <= p.c1; c++) {
+                if (l[r * 64 + c] == 0xffff) continue;
+                for (int r1 = tile.r - 1; r1 <= tile.r + 1; r1++)
+                    for (int c1 = tile.c - 1; c1 <= tile.c + 1; c1++) {
+                        if (r1 < 0 || r1 >= 64 || c1 < 0 || c1 >= 64) continue;
+                        if (l[r * 64 + c] == l[r1 * 64 + c1]) return true;
+                    }
+            }
+        return false;
+    }
+
+    // N_ClosestPathableLocalIsland (nav.c:5131): note `visited[tile_r * tile_h + tile_c]`
+    uint16_t closest_pathable_liid(int chunk, coord target) const
+    {
+        const uint16_t *l = li(chunk);
+        if (l[target.r * 64 + target.c] != 0xffff) return l[target.r * 64 + target.c];
+        bool visited[4096];
+        memset(visited, 0, sizeof(visited));
+        std::deque<coord> q;
+        q.push_back(target);
+        visited[target.r * 64 + target.c] = true;
+        while (!q.empty()) {
+            const coord cur = q.front();
+            q.pop_front();
+            const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+            for (int e = 0; e < 4; e++) {
+                const int nr = cur.r + dr[e], nc = cur.c + dc[e];
+                // M_Tile_RelativeDesc succeeds across chunk borders; tiles outside this chunk are skipped
+                if (nr < 0 || nr >= 64 || nc < 0 || nc >= 64) continue;
+                if (visited[nr * 64 + nc]) continue;
+                if (l[nr * 64 + nc] != 0xffff) return l[nr * 64 + nc];
+                visited[nr * 64 + nc] = true;
+                q.push_back({nr, nc});
+            }
+        }
+        return 0xffff;
+    }
+
+    // n_closest_reachable_portal (nav.c:1365)
+    int closest_reachable_portal(int chunk, coord start, bool unblocked) const
+    {
+        int ret = -1;
+        float min_cost = FLT_MAX;
+        for (int i = 0; i < nports(chunk); i++) {
+            const float cost = cost_unpack(RL.chunks[chunk].travel[(size_t)i * 4096 + start.r * 64 + start.c]);
+            if (unblocked && !portal_reachable_from_tile(chunk, i, start)) continue;
+            if (cost < min_cost) { ret = i; min_cost = cost; }
+        }
+        return ret;
+    }
+
+    struct hop { int chunk, pi; uint16_t liid; };
+    static uint64_t hop_key(const hop &h) { return ((uint64_t)h.liid << 32) | ((uint64_t)h.chunk << 8) | (uint64_t)h.pi; }
+
+    // neighbours_portal_graph (a_star.c:212) incl. portal_reachable_from_island (:138) and
+    // portal_connected_liids (:151)
+    int neighbours(const hop &cur, hop *out, float *costs) const
+    {
+        int ret = 0;
+        const int maxout = 256;
+        const uint16_t *l = li(cur.chunk);
+        for (const auto &e : RL.chunks[cur.chunk].edges[cur.pi]) {
+            if (ret == maxout) return ret;
+            if (e.es == 1) continue;
+            const auto &np = P(cur.chunk, e.nb);
+            bool reach = false;
+            for (int r = np.r0; r <= np.r1 && !reach; r++)
+                for (int c = np.c0; c <= np.c1; c++)
+                    if (l[r * 64 + c] == cur.liid) { reach = true; break; }
+            if (!reach) continue;
+            out[ret] = {cur.chunk, e.nb, cur.liid};
+            costs[ret] = e.cost;
+            ret++;
+        }
+        const auto &p = P(cur.chunk, cur.pi);
+        const auto &conn = P(p.conn_chunk, p.conn_idx);
+        const uint16_t *cl = li(p.conn_chunk);
+        uint16_t conn_liids[256];
+        int nconn = 0;
+        for (int r1 = p.r0; r1 <= p.r1; r1++)
+            for (int c1 = p.c0; c1 <= p.c1; c1++) {
+                if (l[r1 * 64 + c1] != cur.liid) continue;
+                for (int r2 = conn.r0; r2 <= conn.r1; r2++)
+                    for (int c2 = conn.c0; c2 <= conn.c1; c2++) {
+                        if (nconn == 256) goto done_conn;
+                        const int dr = (conn.chunk_r * 64 + r2) - (p.chunk_r * 64 + r1);
+                        const int dc = (conn.chunk_c * 64 + c2) - (p.chunk_c * 64 + c1);
+                        if (abs(dr) + abs(dc) == 1) {
+                            const uint16_t nl = cl[r2 * 64 + c2];
+                            bool contains = false;
+                            for (int i = 0; i < nconn; i++) if (conn_liids[i] == nl) { contains = true; break; }
+                            if (!contains && nl != 0xffff) conn_liids[nconn++] = nl;
+                        }
+                    }
+            }
+    done_conn:
+        for (int i = 0; i < nconn; i++) {
+            if (ret == maxout) return ret;
+            out[ret] = {p.conn_chunk, p.conn_idx, conn_liids[i]};
+            costs[ret] = 1;
+            ret++;
+        }
+        return ret;
+    }
+
+    // AStar_PortalGraphPath (a_star.c:429)
+    bool portal_graph_path(tdesc start, tdesc end, int fin_chunk, int fin_pi, std::vector<hop> &path, float *out_cost) const
+    {
+        const int bchunk = start.chunk_r * cw + start.chunk_c, echunk = end.chunk_r * cw + end.chunk_c;
+        const uint16_t start_liid = closest_pathable_liid(bchunk, {start.tile_r, start.tile_c});
+        if (start_liid == 0xffff) return false;
+        const uint16_t end_liid = closest_pathable_liid(echunk, {end.tile_r, end.tile_c});
+        if (end_liid == 0xffff) return false;
+        pq<hop> frontier;
+        std::unordered_map<uint64_t, float> running;
+        std::unordered_map<uint64_t, hop> came_from;
+        for (int i = 0; i < nports(bchunk); i++) {
+            const coord tc = {start.tile_r, start.tile_c};
+            if (!portal_reachable_from_tile(bchunk, i, tc)) continue;
+            const float cost = cost_unpack(RL.chunks[bchunk].travel[(size_t)i * 4096 + tc.r * 64 + tc.c]);
+            if (cost != FLT_MAX) {
+                const hop h = {bchunk, i, start_liid};
+                running[hop_key(h)] = cost;
+                frontier.push(cost, h);
+            }
+        }
+        const float penalty = (float)sqrt(pow(64, 2.0f) + pow(64, 2.0f));     // portal_node_penalty (a_star.c:298)
+        while (frontier.size > 0) {
+            const hop cur = frontier.pop();
+            if (cur.chunk == fin_chunk && cur.pi == fin_pi && cur.liid == end_liid) break;
+            hop nb[256]; float nc[256];
+            const int n = neighbours(cur, nb, nc);
+            for (int i = 0; i < n; i++) {
+                const float new_cost = running[hop_key(cur)] + nc[i] + penalty;
+                auto it = running.find(hop_key(nb[i]));
+                if (it == running.end() || new_cost < it->second) {
+                    running[hop_key(nb[i])] = new_cost;
+                    frontier.push(new_cost, nb[i]);
+                    came_from[hop_key(nb[i])] = cur;
+                }
+            }
+        }
+        const hop last = {fin_chunk, fin_pi, end_liid};
+        if (came_from.find(hop_key(last)) == came_from.end()) return false;
+        path.clear();
+        hop cur = last;
+        while (true) {
+            path.push_back(cur);
+            auto it = came_from.find(hop_key(cur));
+            if (it == came_from.end()) break;
+            cur = it->second;
+        }
+        std::reverse(path.begin(), path.end());
+        *out_cost = running[hop_key(last)];
+        return true;
+    }
+
+    // n_closest_reachable_from_location (nav.c:1398)
+    int closest_reachable_from_location(int chunk, tdesc loc, tdesc *out_nearest) const
+    {
+        float shortest = FLT_MAX;
+        int ret = -1;
+        tdesc nearest = {0, 0, 0, 0};
+        std::vector<hop> path;
+        const uint16_t *l = li(chunk);
+        for (int i = 0; i < nports(chunk); i++) {
+            uint16_t liids[64];
+            int nl = 0;
+            const auto &p = P(chunk, i);
+            for (int r = p.r0; r <= p.r1; r++)
+                for (int c = p.c0; c <= p.c1; c++) {
+                    const tdesc cur = {p.chunk_r, p.chunk_c, r, c};
+                    const uint16_t cl = l[r * 64 + c];
+                    bool contains = false;
+                    for (int k = 0; k < nl; k++) if (liids[k] == cl) { contains = true; break; }
+                    if (!contains && nl < 64) {
+                        liids[nl++] = cl;
+                        float cost;
+                        if (portal_graph_path(loc, cur, chunk, i, path, &cost) && cost < shortest) {
+                            nearest = cur; shortest = cost; ret = i;
+                        }
+                    }
+                }
+        }
+        if (ret >= 0) *out_nearest = nearest;
+        return ret;
+    }
+
+    bool blocked_off(int chunk, coord tile) const       // n_blocked_off (nav.c:1544)
+    {
+        for (int i = 0; i < nports(chunk); i++) if (portal_reachable_from_tile(chunk, i, tile)) return false;
+        return true;
+    }
+    bool normally_reachable(int chunk, coord a, coord b) const      // n_normally_reachable (nav.c:1531)
+    {
+        for (int i = 0; i < nports(chunk); i++) {
+            const bool ar = RL.chunks[chunk].travel[(size_t)i * 4096 + a.r * 64 + a.c] != 0xffff;
+            const bool br = RL.chunks[chunk].travel[(size_t)i * 4096 + b.r * 64 + b.c] != 0xffff;
+            if (ar != br) return false;
+        }
+        return true;
+    }
+};
+
+// M_Tile_DescForPoint2D with the nav resolution (tile.c:547)
+static bool desc_for_point(const pfnav_ctx *ctx, float px, float pz, tdesc *out)
+{
+    const float width = (float)(ctx->chunk_w * 256), height = (float)(ctx->chunk_h * 256);
+    if (px > ctx->map_x || px < ctx->map_x - width) return false;
+    if (pz < ctx->map_z || pz > ctx->map_z + height) return false;
+    int chunk_r = (int)(fabs(ctx->map_z - pz) / 256.0f), chunk_c = (int)(fabs(ctx->map_x - px) / 256.0f);
+    chunk_r = std::min(std::max(chunk_r, 0), ctx->chunk_h - 1);
+    chunk_c = std::min(std::max(chunk_c, 0), ctx->chunk_w - 1);
+    const float bx = ctx->map_x - (chunk_c * 256.0f), bz = ctx->map_z + (chunk_r * 256.0f);
+    int tile_r = (int)(fabs(bz - pz) / 4), tile_c = (int)(fabs(bx - px) / 4);
+    out->chunk_r = chunk_r; out->chunk_c = chunk_c;
+    out->tile_r = std::min(std::max(tile_r, 0), 63); out->tile_c = std::min(std::max(tile_c, 0), 63);
+    return true;
+}
+
+}   // namespace
+
+// n_request_path (nav.c:1774-2047), request-generation half. Emits, in the reference's order, the
+// flow requests (with the N_FlowFieldID of each, field.c:1952) and LOS requests a cold field cache
+// would have to build for (src -> dst), given which (dest, chunk) entries `have_flow` / `have_los`
+// already hold (arrays of `chunks` entries; have_flow holds the ff_id mapped for the chunk or 0).
+// Returns 1 in *out_ok when a path exists (the function's bool), plus the dest_id.
+extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, float src_z, float dst_x, float dst_z,
+                                        const uint64_t *have_flow, const uint8_t *have_los,
+                                        pfnav_field_req *flow_out, uint64_t *flow_ffid, int32_t *flow_chunk, int max_flow,
+                                        int *n_flow, pfnav_los_req *los_out, int32_t *los_chunk, int max_los, int *n_los,
+                                        uint32_t *out_dest_id, int *out_ok)
+{
+    PF_ARG(ctx && n_flow && n_los && out_ok && out_dest_id, "args");
+    auto it = g_routes.find(ctx);
+    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
+    pfnav_route_layer &RL = it->second[layer];
+    const int cw = ctx->chunk_w, chunks = cw * ctx->chunk_h;
+    Router R{ctx, RL, layer, cw, ctx->chunk_h};
+    *n_flow = 0; *n_los = 0; *out_ok = 0;
+    // n_update_dirty_local_islands + n_update_all_edge_states (nav.c:1786-1787)
+    for (int ch = 0; ch < chunks; ch++) update_edge_states(ctx, RL, layer, ch);
+    tdesc src, dst;
+    PF_ARG(desc_for_point(ctx, src_x, src_z, &src) && desc_for_point(ctx, dst_x, dst_z, &dst), "position outside the map");
+    const uint32_t dest_id = (((uint32_t)dst.chunk_r & 0x3f) << 26) | (((uint32_t)dst.chunk_c & 0x3f) << 20) |
+                             (((uint32_t)dst.tile_r & 0x3f) << 14) | (((uint32_t)dst.tile_c & 0x3f) << 8) |
+                             (((uint32_t)layer & 0xf) << 4) | 0xfu;          // n_dest_id (nav.c:839), FACTION_ID_NONE
+    *out_dest_id = dest_id;
+    const int schunk = src.chunk_r * cw + src.chunk_c, dchunk = dst.chunk_r * cw + dst.chunk_c;
+    if (RL.islands[(size_t)schunk * 4096 + src.tile_r * 64 + src.tile_c] != RL.islands[(size_t)dchunk * 4096 + dst.tile_r * 64 + dst.tile_c])
+        return PFNAV_OK;
+    std::vector<uint64_t> mapped(have_flow, have_flow + chunks);      // local copy of the (dest, chunk) -> ffid mapping
+    std::vector<uint8_t> los_have(have_los, have_los + chunks);
+    std::vector<int> los_index(chunks, -1);
+    auto ffid_tile = [&](int chunk, int tr, int tc) -> uint64_t {
+        return ((uint64_t)layer << 60) | ((uint64_t)1 << 56) | ((uint64_t)tr << 24) | ((uint64_t)tc << 16) |
+               ((uint64_t)(chunk / cw) << 8) | (uint64_t)(chunk % cw);
+    };
+    auto emit_flow = [&](const pfnav_field_req &q, uint64_t id, int chunk) -> bool {
+        if (*n_flow >= max_flow) return false;
+        flow_out[*n_flow] = q; flow_ffid[*n_flow] = id; flow_chunk[*n_flow] = chunk; (*n_flow)++;
+        return true;
+    };
+    auto emit_los = [&](int chunk, int prev_chunk) -> bool {
+        if (*n_los >= max_los) return false;
+        pfnav_los_req q;
+        memset(&q, 0, sizeof(q));
+        q.chunk_r = chunk / cw; q.chunk_c = chunk % cw; q.layer = layer; q.faction_id = PFNAV_FACTION_ID_NONE;
+        q.tgt_chunk_r = dst.chunk_r; q.tgt_chunk_c = dst.chunk_c; q.tgt_tile_r = dst.tile_r; q.tgt_tile_c = dst.tile_c;
+        // -1: destination chunk; >= 0: request of this batch; -2: the previous chunk's field already
+        // exists (have_los) and the executor substitutes its pool slot into _pad
+        q.prev_index = prev_chunk < 0 ? -1 : (los_index[prev_chunk] >= 0 ? los_index[prev_chunk] : -2);
+        if (prev_chunk >= 0) { q.prev_chunk_r = prev_chunk / cw; q.prev_chunk_c = prev_chunk % cw; }
+        los_index[chunk] = *n_los;
+        los_out[*n_los] = q; los_chunk[*n_los] = chunk; (*n_los)++;
+        los_have[chunk] = 1;
+        return true;
+    };
+    pfnav_field_req base;
+    memset(&base, 0, sizeof(base));
+    base.layer = layer; base.faction_id = PFNAV_FACTION_ID_NONE;
+    // destination chunk field + LOS (nav.c:1815-1847)
+    if (!mapped[dchunk]) {
+        pfnav_field_req q = base;
+        q.chunk_r = dst.chunk_r; q.chunk_c = dst.chunk_c; q.target_type = PFNAV_TARGET_TILE; q.init = 1;
+        q.tile_r = dst.tile_r; q.tile_c = dst.tile_c;
+        const uint64_t id = ffid_tile(dchunk, dst.tile_r, dst.tile_c);
+        if (!emit_flow(q, id, dchunk)) { pfnav_set_error("flow output too small"); return PFNAV_ERR_NOMEM; }
+        mapped[dchunk] = id;
+    }
+    if (!los_have[dchunk] && !emit_los(dchunk, -1)) { pfnav_set_error("los output too small"); return PFNAV_ERR_NOMEM; }
+    const uint16_t dst_cl = R.closest_pathable_liid(dchunk, {dst.tile_r, dst.tile_c});
+    if (schunk == dchunk && R.closest_pathable_liid(schunk, {src.tile_r, src.tile_c}) == dst_cl) { *out_ok = 1; return PFNAV_OK; }
+    if (schunk == dchunk) {
+        const bool either = R.blocked_off(schunk, {src.tile_r, src.tile_c}) || R.blocked_off(schunk, {dst.tile_r, dst.tile_c});
+        if (either && R.normally_reachable(schunk, {src.tile_r, src.tile_c}, {dst.tile_r, dst.tile_c})) { *out_ok = 1; return PFNAV_OK; }
+    }
+    int dst_port = R.closest_reachable_portal(dchunk, {dst.tile_r, dst.tile_c}, true);
+    if (dst_port < 0) dst_port = R.closest_reachable_portal(dchunk, {dst.tile_r, dst.tile_c}, false);
+    if (dst_port < 0) return PFNAV_OK;
+    std::vector<Router::hop> path;
+    float cost;
+    int dst_port_chunk = dchunk;
+    bool exists = R.portal_graph_path(src, dst, dchunk, dst_port, path, &cost);
+    if (!exists) {
+        const tdesc orig = dst;
+        tdesc nd = dst;
+        dst_port = R.closest_reachable_from_location(dchunk, src, &nd);
+        if (dst_port >= 0) dst = nd;
+        if (R.closest_pathable_liid(dchunk, {dst.tile_r, dst.tile_c}) != R.closest_pathable_liid(dchunk, {orig.tile_r, orig.tile_c}) &&
+            src.chunk_r == dst.chunk_r && src.chunk_c == dst.chunk_c) { *out_ok = 1; return PFNAV_OK; }
+        if (dst_port >= 0) exists = R.portal_graph_path(src, dst, dchunk, dst_port, path, &cost);
+    }
+    if (!exists) {
+        if (src.chunk_r == dst.chunk_r && src.chunk_c == dst.chunk_c) *out_ok = 1;
+        return PFNAV_OK;
+    }
+    (void)dst_port_chunk;
+    int prev_los_chunk = dst.chunk_r * cw + dst.chunk_c;
+    const uint16_t dst_liid_now = R.closest_pathable_liid(dchunk, {dst.tile_r, dst.tile_c});
+    // walk the portal path backwards (nav.c:1941-2042)
+    for (int i = (int)path.size() - 1; i > 0; i--) {
+        int next_hop_idx = i;
+        if (i == 1 && path[i].chunk != schunk) next_hop_idx = 0;
+        const Router::hop curr_hop = path[std::max(next_hop_idx - 1, 0)];
+        const Router::hop next_hop = path[next_hop_idx];
+        const auto &cp = R.P(curr_hop.chunk, curr_hop.pi);
+        if (cp.conn_chunk == next_hop.chunk && cp.conn_idx == next_hop.pi) continue;
+        if (curr_hop.chunk == dchunk && next_hop.chunk == dchunk && next_hop.pi == dst_port && next_hop.liid == dst_liid_now) continue;
+        const int chunk = curr_hop.chunk;
+        const auto &np = R.P(next_hop.chunk, next_hop.pi);
+        const auto &nn = R.P(np.conn_chunk, np.conn_idx);
+        pfnav_field_req q = base;
+        q.chunk_r = chunk / cw; q.chunk_c = chunk % cw; q.target_type = PFNAV_TARGET_PORTAL;
+        q.port_r0 = np.r0; q.port_c0 = np.c0; q.port_r1 = np.r1; q.port_c1 = np.c1;
+        q.next_r0 = nn.r0; q.next_c0 = nn.c0; q.next_r1 = nn.r1; q.next_c1 = nn.c1;
+        q.next_chunk_r = nn.chunk_r; q.next_chunk_c = nn.chunk_c;
+        q.port_iid = next_hop.liid;
+        q.next_iid = (i < (int)path.size() - 1) ? path[next_hop_idx + 1].liid : dst_liid_now;
+        // N_FlowFieldID TARGET_PORTAL (field.c:1954)
+        const uint64_t new_id = ((uint64_t)layer << 60) | ((uint64_t)0 << 56) | (((uint64_t)q.next_iid & 0xf) << 48) |
+                                (((uint64_t)q.port_iid & 0xf) << 40) | ((uint64_t)np.r0 << 34) | ((uint64_t)np.c0 << 28) |
+                                ((uint64_t)np.r1 << 22) | ((uint64_t)np.c1 << 16) | ((uint64_t)q.chunk_r << 8) | (uint64_t)q.chunk_c;
+        if (mapped[chunk]) {
+            if (mapped[chunk] != new_id) {
+                q.init = 0;          // merge into the chunk's existing field (nav.c:1994-2010)
+                if (!emit_flow(q, new_id, chunk)) { pfnav_set_error("flow output too small"); return PFNAV_ERR_NOMEM; }
+                mapped[chunk] = new_id;
+            }
+        } else {
+            q.init = 1;
+            if (!emit_flow(q, new_id, chunk)) { pfnav_set_error("flow output too small"); return PFNAV_ERR_NOMEM; }
+            mapped[chunk] = new_id;
+        }
+        if (!los_have[chunk]) {
+            if (!emit_los(chunk, prev_los_chunk)) { pfnav_set_error("los output too small"); return PFNAV_ERR_NOMEM; }
+        }
+        prev_los_chunk = chunk;
+    }
+    *out_ok = 1;
+    return PFNAV_OK;
+}
+
+// N_RequestPath (nav.c:3386) against the device field pool: route src -> dst exactly as the reference
+// does, then build only the fields the pool does not hold yet, in place, on the device.
+extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, float src_x, float src_z, float dst_x,
+                                       float dst_z, void *stream, uint32_t *out_dest_id, int *out_ok, int *out_n_flow,
+                                       int *out_n_los)
+{
+    PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    std::vector<uint8_t> have_los(chunks, 0);
+    for (int c = 0; c < chunks; c++) {
+        const int s = ctx->h_pool_slot[(size_t)dest * chunks + c];
+        have_los[c] = (s >= 0 && (ctx->h_pool_has[s] & 2)) ? 1 : 0;
+    }
+    const int cap = chunks * 4 + 8;
+    std::vector<pfnav_field_req> fr(cap);
+    std::vector<pfnav_los_req> lr(cap);
+    std::vector<uint64_t> fid(cap);
+    std::vector<int32_t> fc(cap), lc(cap);
+    int nf = 0, nl = 0, ok = 0;
+    uint32_t did = 0;
+    int rc = pfnav_route_request_path(ctx, layer, src_x, src_z, dst_x, dst_z, ctx->h_pool_ffid.data() + (size_t)dest * chunks,
+                                      have_los.data(), fr.data(), fid.data(), fc.data(), cap, &nf, lr.data(), lc.data(), cap,
+                                      &nl, &did, &ok);
+    if (rc) return rc;
+    if (out_dest_id) *out_dest_id = did;
+    if (out_ok) *out_ok = ok;
+    if (out_n_flow) *out_n_flow = nf;
+    if (out_n_los) *out_n_los = nl;
+    if (nf == 0 && nl == 0) return PFNAV_OK;
+    auto slot_for = [&](int chunk, uint8_t bits) -> int {
+        const size_t si = (size_t)dest * chunks + chunk;
+        int slot = ctx->h_pool_slot[si];
+        if (slot < 0) {
+            if (ctx->pool_used >= ctx->pool_max) return -1;
+            slot = ctx->pool_used++;
+            ctx->h_pool_slot[si] = slot;
+        }
+        ctx->h_pool_has[slot] |= bits;
+        return slot;
+    };
+    // flow waves: a request that updates a chunk already written in this batch runs one wave later
+    std::vector<int32_t> fslot(nf), fwave(nf), lslot(nl), ldepth(nl, 0);
+    std::vector<int> seen(chunks, 0);
+    int maxw = 0, maxd = 0;
+    for (int i = 0; i < nf; i++) {
+        fslot[i] = slot_for(fc[i], 1);
+        if (fslot[i] < 0) { pfnav_set_error("pfnav_pool_request_path: pool full"); return PFNAV_ERR_NOMEM; }
+        fwave[i] = seen[fc[i]]++;
+        maxw = std::max(maxw, fwave[i]);
+        ctx->h_pool_ffid[(size_t)dest * chunks + fc[i]] = fid[i];
+    }
+    for (int i = 0; i < nl; i++) {
+        lslot[i] = slot_for(lc[i], 2);
+        if (lslot[i] < 0) { pfnav_set_error("pfnav_pool_request_path: pool full"); return PFNAV_ERR_NOMEM; }
+        if (lr[i].prev_index >= 0) ldepth[i] = ldepth[lr[i].prev_index] + 1;
+        else if (lr[i].prev_index == -2) {
+            const int pchunk = lr[i].prev_chunk_r * ctx->chunk_w + lr[i].prev_chunk_c;
+            lr[i]._pad = ctx->h_pool_slot[(size_t)dest * chunks + pchunk];       // absolute pool slot of prev_los
+        }
+        maxd = std::max(maxd, ldepth[i]);
+    }
+    std::vector<int32_t> fwave_off(maxw + 2, 0), lwave_off(maxd + 2, 0);
+    for (int i = 0; i < nf; i++) fwave_off[fwave[i] + 1]++;
+    for (int w = 0; w <= maxw; w++) fwave_off[w + 1] += fwave_off[w];
+    for (int i = 0; i < nl; i++) lwave_off[ldepth[i] + 1]++;
+    for (int d = 0; d <= maxd; d++) lwave_off[d + 1] += lwave_off[d];
+    const size_t b_fr = (size_t)nf * sizeof(pfnav_field_req), b_fs = (size_t)nf * 4;
+    const size_t b_lr = (size_t)nl * sizeof(pfnav_los_req), b_ls = (size_t)nl * 4;
+    const size_t total = b_fr + b_fs + b_lr + b_ls;
+    std::vector<uint8_t> host(total ? total : 1);
+    pfnav_field_req *hfr = (pfnav_field_req *)host.data();
+    int32_t *hfs = (int32_t *)(host.data() + b_fr);
+    pfnav_los_req *hlr = (pfnav_los_req *)(host.data() + b_fr + b_fs);
+    int32_t *hls = (int32_t *)(host.data() + b_fr + b_fs + b_lr);
+    {
+        std::vector<int32_t> cur(fwave_off.begin(), fwave_off.end() - 1), cur2(lwave_off.begin(), lwave_off.end() - 1), lnew(nl);
+        for (int i = 0; i < nf; i++) { const int k = cur[fwave[i]]++; hfr[k] = fr[i]; hfs[k] = fslot[i]; }
+        for (int i = 0; i < nl; i++) lnew[i] = cur2[ldepth[i]]++;
+        for (int i = 0; i < nl; i++) {
+            pfnav_los_req q = lr[i];
+            if (q.prev_index >= 0) q.prev_index = lnew[q.prev_index];
+            hlr[lnew[i]] = q; hls[lnew[i]] = lslot[i];
+        }
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->plan_buf_bytes < total) {
+        PF_CUDA(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_plan_buf);
+        ctx->d_plan_buf = nullptr; ctx->plan_buf_bytes = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_plan_buf, total * 2));
+        ctx->plan_buf_bytes = total * 2;
+    }
+    uint8_t *dev = (uint8_t *)ctx->d_plan_buf;
+    PF_CUDA(cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + (size_t)dest * chunks, ctx->h_pool_slot.data() + (size_t)dest * chunks,
+                            (size_t)chunks * 4, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
+                            cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    for (int w = 0; w <= maxw; w++) {
+        const int first = fwave_off[w], cnt = fwave_off[w + 1] - first;
+        if (cnt <= 0) continue;
+        rc = pfnav_flow_launch(ctx, (const pfnav_field_req *)dev + first, cnt, ctx->d_pool_flow, (const int32_t *)(dev + b_fr) + first, st);
+        if (rc) return rc;
+    }
+    if (nl) rc = pfnav_los_launch(ctx, (const pfnav_los_req *)(dev + b_fr + b_fs), nl, ctx->d_pool_los,
+                                  (const int32_t *)(dev + b_fr + b_fs + b_lr), maxd + 1, lwave_off.data(), st);
+    return rc;
+}
+
+// Read one pool entry back to the host (4096 B each; either pointer may be NULL). *out_has: bit0 flow, bit1 LOS.
+extern "C" int pfnav_pool_get(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, uint8_t *flow_out, uint8_t *los_out,
+                              int *out_has, uint64_t *out_ffid)
+{
+    PF_ARG(ctx && ctx->d_pool_slot && out_has, "args");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests && chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "dest/chunk");
+    const size_t si = (size_t)dest * ctx->chunk_w * ctx->chunk_h + chunk_r * ctx->chunk_w + chunk_c;
+    const int slot = ctx->h_pool_slot[si];
+    *out_has = slot < 0 ? 0 : ctx->h_pool_has[slot];
+    if (out_ffid) *out_ffid = ctx->h_pool_ffid[si];
+    if (slot < 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaDeviceSynchronize());
+    if (flow_out && (*out_has & 1)) PF_CUDA(cudaMemcpy(flow_out, ctx->d_pool_flow + (size_t)slot * 4096, 4096, cudaMemcpyDeviceToHost));
+    if (los_out && (*out_has & 2)) PF_CUDA(cudaMemcpy(los_out, ctx->d_pool_los + (size_t)slot * 4096, 4096, cudaMemcpyDeviceToHost));
+    return PFNAV_OK;
+}

@@ -127,3 +127,27 @@ def agent_case(cw, n, nflocks, seed, dens, spacing):
 def relerr(g, e):
     d = np.abs(g - e).max(axis=1)
     return d / np.maximum(np.abs(e).max(axis=1), 1e-3)
+
+
+def route_pairs(cost, cw, ch, seed, n):
+    """n seeded (src_xz, dst_xz) pairs on passable tile centres"""
+    rng = np.random.default_rng(seed)
+    img = synth.blocked_to_image(cost, cw, ch)
+    pas = np.argwhere(img != 255)
+    out = []
+    for _ in range(n):
+        (sr, sc), (dr, dc) = pas[rng.integers(0, len(pas), 2)]
+        out.append(((float(-(sc + 0.5) * 4), float((sr + 0.5) * 4)), (float(-(dc + 0.5) * 4), float((dr + 0.5) * 4))))
+    return out
+
+
+def execute_route(flow_exec, los_exec, fr, fc, lr, lc):
+    """run a route's requests in order (flow merges in place per chunk; LOS as one chained batch)
+    -> {chunk: flow}, {chunk: los}"""
+    fields = {}
+    for k in range(len(fr)):
+        base = fields.get(int(fc[k]))
+        out = flow_exec(fr[k:k + 1], None if fr[k]["init"] else base[None])
+        fields[int(fc[k])] = out[0]
+    los = los_exec(lr) if len(lr) else np.zeros((0, 64, 64), np.uint8)
+    return fields, {int(lc[k]): los[k] for k in range(len(lr))}

@@ -98,7 +98,47 @@ def gen_agents(name, cw, n, nflocks, seed, dens, spacing):
     ref.close()
 
 
+def gen_route():
+    """N_RequestPath on a cold field cache for seeded (src, dst) pairs: the (chunk -> ff_id) mapping, the
+    cached flow and LOS fields. Includes pairs whose chained LOS exercises the neighbour-snapshot
+    order of field_neighbours_grid_los (field.c:2205)."""
+    cw = ch = 3
+    out = {}
+    for k, (seed, dens) in enumerate(((81, 0.08), (5, 0.3))):
+        p = cases.noise_map(cw, ch, seed, dens)
+        ref = pfref.RefMap(cw, ch, p)
+        cost = ref.cost_base()
+        pairs = cases.route_pairs(cost, cw, ch, seed, 24)
+        oks, dids, ffids, flows, loss, has = [], [], [], [], [], []
+        for src, dst in pairs:
+            ref.fc_clear()
+            ok, did = ref.request_path(src, dst)
+            oks.append(ok); dids.append(did)
+            fid = np.zeros(cw * ch, np.uint64); hs = np.zeros(cw * ch, np.uint8)
+            fl = np.zeros((cw * ch, 64, 64), np.uint8); ls = np.zeros((cw * ch, 64, 64), np.uint8)
+            if ok:
+                for c in range(cw * ch):
+                    f, i = ref.fc_flow(did, (c // cw, c % cw)); l = ref.fc_los(did, (c // cw, c % cw))
+                    if f is not None:
+                        fl[c] = f; fid[c] = i; hs[c] |= 1
+                    if l is not None:
+                        ls[c] = l; hs[c] |= 2
+            ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs)
+        out.update({f"pathable{k}": p, f"cost{k}": cost, f"liid{k}": ref.local_islands(), f"islands{k}": ref.islands(),
+                    f"pairs{k}": np.array(pairs, np.float32), f"ok{k}": np.array(oks), f"did{k}": np.array(dids, np.uint32),
+                    f"ffid{k}": np.array(ffids), f"flow{k}": np.array(flows), f"los{k}": np.array(loss), f"has{k}": np.array(has)})
+        ports = ref.portals()
+        edges = []
+        for row in ports:
+            e = ref.portal_edges(0, int(row[0]) * cw + int(row[1]), int(row[2]))
+            edges.append(np.concatenate([[len(e)], e.ravel()]).astype(np.uint32))
+        out[f"portals{k}"] = ports; out[f"edges{k}"] = np.concatenate(edges)
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "route_3x3.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_route()
     gen_flow_tile()
     gen_portal_los()
     gen_agents("agents_1x1", 1, 256, 1, 31, 0.02, 4.0)

@@ -259,6 +259,35 @@ def test_request_goal_fields_vs_ref(nav, pfref):
     ref.close()
 
 
+def test_pool_request_path_golden(nav):
+    """N_RequestPath end to end on the device: route on the host (cost-faithful), fields built into the
+    pool by the kernels; (chunk -> ff_id) mapping, flow and chained LOS fields equal the reference's cache"""
+    g = gold("route_3x3")
+    for k in range(2):
+        _upload(nav, 3, 3, g[f"cost{k}"])
+        nav.map_build_nav(0); nav.route_build(0)
+        for i, (src, dst) in enumerate(g[f"pairs{k}"]):
+            nav.pool_create(1, 9)                      # cold cache per request, like the fixture
+            ok, did, nf, nl = nav.pool_request_path(0, tuple(src), tuple(dst))
+            assert ok == bool(g[f"ok{k}"][i])
+            if not ok:
+                continue
+            assert did == int(g[f"did{k}"][i])
+            for c in range(9):
+                f, l, ffid = nav.pool_get(0, (c // 3, c % 3))
+                assert (f is not None) == bool(g[f"has{k}"][i][c] & 1) and (l is not None) == bool(g[f"has{k}"][i][c] & 2)
+                if f is not None:
+                    assert ffid == int(g[f"ffid{k}"][i][c]) and (f == g[f"flow{k}"][i][c]).all()
+                if l is not None:
+                    assert (l == g[f"los{k}"][i][c]).all()
+        # warm cache: a second request from another source reuses / merges into the cached fields
+        nav.pool_create(1, 9)
+        (s0, d0), (s1, _) = g[f"pairs{k}"][0], g[f"pairs{k}"][1]
+        ok0, _, nf0, nl0 = nav.pool_request_path(0, tuple(s0), tuple(d0))
+        ok1, _, nf1, nl1 = nav.pool_request_path(0, tuple(s0), tuple(d0))
+        assert ok0 == ok1 and nf1 == 0 and nl1 == 0          # everything cached the second time
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
 FD_STEP = {1: (-1, -1), 2: (-1, 0), 3: (-1, 1), 4: (0, -1), 5: (0, 1), 6: (1, -1), 7: (1, 0), 8: (1, 1)}
 

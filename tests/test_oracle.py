@@ -136,6 +136,75 @@ def test_port_vs_ref_blockers(pfref, pforacle):
     ref.close()
 
 
+# ---------------------------------------------------------------- host-side planner (host-only context: no compute)
+def _check_route_against(nav, om, cw, ch, pairs, ok_e, did_e, ffid_e, flow_e, los_e, has_e):
+    for k, (src, dst) in enumerate(pairs):
+        ok, did, fr, fid, fc, lr, lc = nav.route_request_path(tuple(src), tuple(dst))
+        assert ok == bool(ok_e[k])
+        if not ok:
+            continue
+        assert did == int(did_e[k])
+        fields, los = cases.execute_route(lambda r, io: om.flow_fields_update(r, inout=io), om.los_fields_create, fr, fc, lr, lc)
+        last_id = {int(fc[i]): int(fid[i]) for i in range(len(fr))}
+        for c in range(cw * ch):
+            assert bool(has_e[k][c] & 1) == (c in fields) and bool(has_e[k][c] & 2) == (c in los)
+            if c in fields:
+                assert last_id[c] == int(ffid_e[k][c])                 # N_FlowFieldID of the mapped field
+                assert (fields[c] == flow_e[k][c]).all()
+            if c in los:
+                assert (los[c] == los_e[k][c]).all()
+
+
+def test_route_request_path_golden(pforacle):
+    """n_request_path restated on the host (pfnav_route.cu), fields executed by the oracle port: identical
+    (chunk -> ff_id) mapping, flow fields and chained LOS fields as the reference's field cache holds"""
+    g = gold("route_3x3")
+    for k in range(2):
+        nav = capi.Nav(hostonly=True)
+        nav.map_create(3, 3, 1); nav.map_upload_layer(0, g[f"cost{k}"]); nav.map_build_nav(0); nav.route_build(0)
+        assert (nav.local_islands(0) == g[f"liid{k}"]).all()
+        assert (nav.route_islands(0) == g[f"islands{k}"]).all()          # global island ids
+        ports = nav.portals(0)
+        assert (ports[:, :9] == g[f"portals{k}"][:, :9]).all()
+        e, off = g[f"edges{k}"], 0
+        for row in ports:                                                   # portal-graph edges: ref, state, cost bits
+            n = int(e[off]); exp = e[off + 1:off + 1 + 3 * n].reshape(n, 3); off += 1 + 3 * n
+            assert (nav.route_edges(int(row[0]) * 3 + int(row[1]), int(row[2])) == exp).all()
+        om = pforacle.OracleMap(3, 3, g[f"cost{k}"], None, g[f"liid{k}"])
+        _check_route_against(nav, om, 3, 3, g[f"pairs{k}"], g[f"ok{k}"], g[f"did{k}"], g[f"ffid{k}"], g[f"flow{k}"], g[f"los{k}"], g[f"has{k}"])
+        with pytest.raises(capi.PfnavError):                                # host-only context: no compute path
+            nav.flow_fields_update(capi.tile_req((0, 0), (1, 1)))
+        nav.close()
+
+
+def test_route_request_path_vs_ref(pfref, pforacle):
+    cw = ch = 4
+    p = cases.noise_map(cw, ch, 91, 0.1)
+    ref = pfref.RefMap(cw, ch, p)
+    cost = ref.cost_base()
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost); nav.map_build_nav(0); nav.route_build(0)
+    om = pforacle.OracleMap(cw, ch, cost, None, ref.local_islands())
+    pairs = cases.route_pairs(cost, cw, ch, 91, 16)
+    oks, dids, ffids, flows, loss, has = [], [], [], [], [], []
+    for src, dst in pairs:
+        ref.fc_clear()
+        ok, did = ref.request_path(src, dst)
+        oks.append(ok); dids.append(did)
+        fid = np.zeros(cw * ch, np.uint64); hs = np.zeros(cw * ch, np.uint8)
+        fl = np.zeros((cw * ch, 64, 64), np.uint8); ls = np.zeros((cw * ch, 64, 64), np.uint8)
+        for c in range(cw * ch):
+            f, i = ref.fc_flow(did, (c // cw, c % cw)) if ok else (None, None)
+            l = ref.fc_los(did, (c // cw, c % cw)) if ok else None
+            if f is not None:
+                fl[c] = f; fid[c] = i; hs[c] |= 1
+            if l is not None:
+                ls[c] = l; hs[c] |= 2
+        ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs)
+    _check_route_against(nav, om, cw, ch, pairs, oks, dids, ffids, flows, loss, has)
+    ref.close(); nav.close()
+
+
 # ---------------------------------------------------------------- host logic + ABI surface
 def test_synth_is_deterministic():
     p1 = synth.make_map(2, 2, 0x5EED0002); p2 = synth.make_map(2, 2, 0x5EED0002)
