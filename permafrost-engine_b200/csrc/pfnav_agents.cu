@@ -400,59 +400,42 @@ __global__ void k_ents_in_circle(GridView g, float x, float z, float range, uint
 struct ray { v2 point, dir; };
 struct cp_ent { v2 pos, vel; float radius; };
 
-// C_InfiniteLineIntersection (collision.c:820) incl. the preserved "l2 vertical" y bug (:839-840)
-__device__ __forceinline__ bool line_isect(const ray l1, const ray l2, v2 &out)
+#define QNAN __int_as_float(0x7fc00000)
+
+// slope used by C_InfiniteLineIntersection (collision.c:822): NaN marks a (near-)vertical line
+__device__ __forceinline__ float line_slope(v2 dir) { return fabsf(dir.x) < EPS_F ? QNAN : (dir.z / dir.x); }
+
+// C_InfiniteLineIntersection (collision.c:820) incl. the preserved "l2 vertical" y bug (:839-840),
+// with the two slopes supplied by the caller
+__device__ __forceinline__ bool line_isect_s(const v2 p1, const float s1, const v2 p2, const float s2, v2 &out)
 {
-    const float s1 = fabsf(l1.dir.x) < EPS_F ? __int_as_float(0x7fc00000) : (l1.dir.z / l1.dir.x);
-    const float s2 = fabsf(l2.dir.x) < EPS_F ? __int_as_float(0x7fc00000) : (l2.dir.z / l2.dir.x);
     const bool n1 = isnan(s1), n2 = isnan(s2);
     if (n1 && n2) return false;
     if (fabsf(s1 - s2) < EPS_F) return false;
     if (n1 && !n2) {
-        out.x = l1.point.x;
-        out.z = (l1.point.x - l2.point.x) * s2 + l2.point.z;
+        out.x = p1.x;
+        out.z = (p1.x - p2.x) * s2 + p2.z;
     } else if (!n1 && n2) {
-        out.x = l2.point.x;
-        out.z = (l2.point.x - l1.point.x) * s1 + l2.point.z;
+        out.x = p2.x;
+        out.z = (p2.x - p1.x) * s1 + p2.z;
     } else {
-        out.x = (s1 * l1.point.x - s2 * l2.point.x + l2.point.z - l1.point.z) / (s1 - s2);
-        out.z = s2 * (out.x - l2.point.x) + l2.point.z;
+        out.x = (s1 * p1.x - s2 * p2.x + p2.z - p1.z) / (s1 - s2);
+        out.z = s2 * (out.x - p2.x) + p2.z;
     }
     return true;
 }
-
-// C_RayRayIntersection2D (collision.c:854)
-__device__ __forceinline__ bool ray_isect(const ray l1, const ray l2, v2 &out)
+__device__ __forceinline__ bool line_isect(const ray l1, const ray l2, v2 &out)
 {
-    v2 p;
-    if (!line_isect(l1, l2, p)) return false;
-    if ((p.x - l1.point.x) / l1.dir.x < 0.0f) return false;
-    if ((p.z - l1.point.z) / l1.dir.z < 0.0f) return false;
-    if ((p.x - l2.point.x) / l2.dir.x < 0.0f) return false;
-    if ((p.z - l2.point.z) / l2.dir.z < 0.0f) return false;
-    out = p;
-    return true;
+    return line_isect_s(l1.point, line_slope(l1.dir), l2.point, line_slope(l2.dir), out);
 }
 
-// inside_pcr (clearpath.c:249)
-__device__ __forceinline__ bool inside_pcr(const ray *rays, int n_rays, v2 test)
+// (a / b < 0.0f) for |b| <= 1 without the division: the quotient of a non-zero a by such a b never
+// underflows to zero, so only the signs (and NaNs, and b == +-0) matter. Bit-equivalent to the
+// reference's four tests in C_RayRayIntersection2D (collision.c:861-871).
+__device__ __forceinline__ bool quot_lt0(float a, float b)
 {
-    for (int i = 0; i < n_rays; i += 2) {
-        const ray L = rays[i];
-        v2 ptt = v2_sub(test, L.point);
-        if (v2_len(ptt) < EPS_F) continue;
-        ptt = v2_normal(ptt);
-        const float left_det = (ptt.z * L.dir.x) - (ptt.x * L.dir.z);
-        if (left_det < EPS_F) continue;
-        const ray R = rays[i + 1];
-        ptt = v2_sub(test, R.point);
-        if (v2_len(ptt) < EPS_F) continue;
-        ptt = v2_normal(ptt);
-        const float right_det = (ptt.z * R.dir.x) - (ptt.x * R.dir.z);
-        if (right_det > -EPS_F) continue;
-        return true;
-    }
-    return false;
+    const bool bneg = signbit(b), bnum = (b == b);
+    return bnum && ((a < 0.0f && !bneg) || (a > 0.0f && bneg));
 }
 
 // compute_vo_edges (clearpath.c:130)
@@ -467,13 +450,109 @@ __device__ __forceinline__ void vo_edges(const cp_ent ent, const cp_ent nb, v2 &
 }
 
 #define VEL_WARPS_PER_CTA 4
+#define CQ_CAP 160
 struct VelSmem {
     cp_ent dyn[PFNAV_MAX_NEIGHBOURS];
     cp_ent stat[PFNAV_MAX_NEIGHBOURS];
-    ray rays[4 * PFNAV_MAX_NEIGHBOURS];
+    // rays, SoA (2 per velocity obstacle: even = left side, odd = right side)
+    float rpx[4 * PFNAV_MAX_NEIGHBOURS], rpz[4 * PFNAV_MAX_NEIGHBOURS];
+    float rdx[4 * PFNAV_MAX_NEIGHBOURS], rdz[4 * PFNAV_MAX_NEIGHBOURS];
+    float rsl[4 * PFNAV_MAX_NEIGHBOURS];
     uint32_t near_id[128];
     float2 term[128];
+    float cqx[CQ_CAP], cqz[CQ_CAP];      // candidate points awaiting the inside-PCR test
+    int cqk[CQ_CAP];                      // their sequence index in the reference's push order
 };
+
+// One velocity obstacle of inside_pcr (clearpath.c:252-287): is `test` strictly inside VO `i`?
+// The reference normalises (test - apex) and compares a 2-D cross product with +-1/1024. Away from
+// those thresholds the unnormalised cross product decides with certainty (margins of 1 % on the
+// threshold versus ~1e-6 relative float error), so the sqrt and the two IEEE divisions are only paid
+// in the thin band around a threshold, where the reference's exact sequence is replayed.
+__device__ __forceinline__ bool vo_contains(const VelSmem &s, int i, v2 test)
+{
+    const float E_LO2 = (EPS_F * 0.99f) * (EPS_F * 0.99f), E_HI2 = (EPS_F * 1.01f) * (EPS_F * 1.01f);
+    {   // left side: "left_of_vo" <=> det < EPS  -> not inside
+        const int k = 2 * i;
+        const v2 ptt = {test.x - s.rpx[k], test.z - s.rpz[k]};
+        const float len2 = ptt.x * ptt.x + ptt.z * ptt.z;
+        const float u = (ptt.z * s.rdx[k]) - (ptt.x * s.rdz[k]);
+        const float u2 = u * u;
+        bool decided = false, skip = false;
+        if (len2 > E_HI2 && len2 < 1e30f) {             // |ptt| certainly >= EPS
+            if (u <= 0.0f || u2 < E_LO2 * len2) { decided = true; skip = true; }        // det < EPS
+            else if (u2 > E_HI2 * len2) { decided = true; skip = false; }               // det >= EPS
+        }
+        if (!decided) {
+            const float len = sqrtf(len2);
+            if (len < EPS_F) skip = true;
+            else {
+                const v2 n = {ptt.x / len, ptt.z / len};
+                const float det = (n.z * s.rdx[k]) - (n.x * s.rdz[k]);
+                skip = det < EPS_F;
+            }
+        }
+        if (skip) return false;
+    }
+    {   // right side: "right_of_vo" <=> det > -EPS -> not inside
+        const int k = 2 * i + 1;
+        const v2 ptt = {test.x - s.rpx[k], test.z - s.rpz[k]};
+        const float len2 = ptt.x * ptt.x + ptt.z * ptt.z;
+        const float u = (ptt.z * s.rdx[k]) - (ptt.x * s.rdz[k]);
+        const float u2 = u * u;
+        bool decided = false, skip = false;
+        if (len2 > E_HI2 && len2 < 1e30f) {
+            if (u >= 0.0f || u2 < E_LO2 * len2) { decided = true; skip = true; }        // det > -EPS
+            else if (u2 > E_HI2 * len2) { decided = true; skip = false; }               // det <= -EPS
+        }
+        if (!decided) {
+            const float len = sqrtf(len2);
+            if (len < EPS_F) skip = true;
+            else {
+                const v2 n = {ptt.x / len, ptt.z / len};
+                const float det = (n.z * s.rdx[k]) - (n.x * s.rdz[k]);
+                skip = det > -EPS_F;
+            }
+        }
+        if (skip) return false;
+    }
+    return true;
+}
+
+// Drain the candidate queue: every lane keeps one candidate in flight and tests one velocity obstacle
+// per iteration; a lane whose candidate is decided immediately takes the next one, so all lanes stay
+// busy whatever the early-exit pattern of inside_pcr is. Keeps the per-lane first-minimum of
+// compute_vnew (clearpath.c:368) on (distance, sequence index).
+__device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int nvo, const v2 ent_pos, const v2 des_v,
+                                                 uint32_t lane, float &best, int &best_idx, v2 &best_p, int &any)
+{
+    int next = 0, my = -1, vo = 0, myk = 0;
+    v2 myp = {0.0f, 0.0f};
+    while (true) {
+        const bool need = my < 0;
+        const uint32_t mneed = __ballot_sync(FULL, need);
+        const int avail = qn - next;
+        if (need) {
+            const int rank = __popc(mneed & ((1u << lane) - 1));
+            if (rank < avail) { my = next + rank; vo = 0; myp = {s.cqx[my], s.cqz[my]}; myk = s.cqk[my]; }
+        }
+        next += min(__popc(mneed), avail);
+        if (!__any_sync(FULL, my >= 0)) break;
+        if (my >= 0) {
+            bool finished = false, inside = false;
+            if (vo < nvo) inside = vo_contains(s, vo, myp);
+            if (inside) finished = true;
+            else if (++vo >= nvo) {
+                finished = true;
+                any = 1;
+                const v2 curr = v2_sub(myp, ent_pos);
+                const float len = v2_len(v2_sub(des_v, curr));
+                if (len < best || (len == best && best_idx != 0x7fffffff && myk < best_idx)) { best = len; best_idx = myk; best_p = curr; }
+            }
+            if (finished) my = -1;
+        }
+    }
+}
 
 // clearpath_new_velocity (clearpath.c:552). Warp-cooperative; returns a warp-uniform status.
 __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat,
@@ -483,19 +562,18 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
     int n_rays = 0;
     {
         bool keep = false;
-        ray L, R;
+        v2 apex = {0.f, 0.f}, left = {0.f, 0.f}, right = {0.f, 0.f};
         if ((int)lane < ndyn) {
             const cp_ent nb = s.dyn[lane];
             if (!(v2_len(v2_sub(nb.pos, ent.pos)) < EPS_F)) {        // same_position (clearpath.c:123)
                 keep = true;
-                v2 right, left;
                 vo_edges(ent, nb, right, left);
                 // compute_rvo / compute_hrvo (clearpath.c:161-214)
                 const v2 rvo_apex = v2_add(ent.pos, v2_scale(v2_add(ent.vel, nb.vel), 0.5f));
                 const v2 centerline = v2_add(left, right);
                 const v2 vo_apex = v2_add(ent.pos, nb.vel);
                 const float det = (centerline.x * ent.vel.z) - (centerline.z * ent.vel.x);
-                v2 apex = rvo_apex;
+                apex = rvo_apex;
                 if (det > EPS_F) {
                     v2 p;
                     if (line_isect(ray{rvo_apex, left}, ray{vo_apex, right}, p)) apex = p;
@@ -503,72 +581,90 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
                     v2 p;
                     if (line_isect(ray{rvo_apex, right}, ray{vo_apex, left}, p)) apex = p;
                 }
-                L = ray{apex, left};
-                R = ray{apex, right};
             }
         }
         const uint32_t m = __ballot_sync(FULL, keep);
         if (keep) {
-            const int k = __popc(m & ((1u << lane) - 1));
-            s.rays[2 * k] = L;
-            s.rays[2 * k + 1] = R;
+            const int k = 2 * __popc(m & ((1u << lane) - 1));
+            s.rpx[k] = apex.x; s.rpz[k] = apex.z; s.rdx[k] = left.x; s.rdz[k] = left.z; s.rsl[k] = line_slope(left);
+            s.rpx[k + 1] = apex.x; s.rpz[k + 1] = apex.z; s.rdx[k + 1] = right.x; s.rdz[k + 1] = right.z; s.rsl[k + 1] = line_slope(right);
         }
         n_rays = 2 * __popc(m);
     }
     {
         bool keep = false;
-        ray L, R;
+        v2 apex = {0.f, 0.f}, left = {0.f, 0.f}, right = {0.f, 0.f};
         if ((int)lane < nstat) {
             const cp_ent nb = s.stat[lane];
             if (!(v2_len(v2_sub(nb.pos, ent.pos)) < EPS_F)) {
                 keep = true;
-                v2 right, left;
                 vo_edges(ent, nb, right, left);
-                const v2 apex = v2_add(ent.pos, nb.vel);              // compute_vo (clearpath.c:153)
-                L = ray{apex, left};
-                R = ray{apex, right};
+                apex = v2_add(ent.pos, nb.vel);                       // compute_vo (clearpath.c:153)
             }
         }
         const uint32_t m = __ballot_sync(FULL, keep);
         if (keep) {
-            const int k = __popc(m & ((1u << lane) - 1));
-            s.rays[n_rays + 2 * k] = L;
-            s.rays[n_rays + 2 * k + 1] = R;
+            const int k = n_rays + 2 * __popc(m & ((1u << lane) - 1));
+            s.rpx[k] = apex.x; s.rpz[k] = apex.z; s.rdx[k] = left.x; s.rdz[k] = left.z; s.rsl[k] = line_slope(left);
+            s.rpx[k + 1] = apex.x; s.rpz[k + 1] = apex.z; s.rdx[k + 1] = right.x; s.rdz[k + 1] = right.z; s.rsl[k + 1] = line_slope(right);
         }
         n_rays += 2 * __popc(m);
     }
     __syncwarp();
+    const int nvo = n_rays >> 1;
 
+    // ---- is the preferred velocity admissible? one velocity obstacle per lane ----
     const v2 des_v_ws = v2_add(ent.pos, des_v);
-    if (!inside_pcr(s.rays, n_rays, des_v_ws)) {          // every lane evaluates the same test
+    bool in_any = false;
+    for (int i = lane; i < nvo; i += 32) in_any |= vo_contains(s, i, des_v_ws);
+    if (!__any_sync(FULL, in_any)) {
         out = des_v;
         return true;
     }
 
-    // ---- compute_vo_xpoints + compute_vdes_proj_points + compute_vnew fused: the candidate list is
-    //      never materialised; we keep the first-minimum (distance, sequence index) per lane ----
+    // ---- compute_vo_xpoints + compute_vdes_proj_points + compute_vnew, fused: ray pairs are intersected
+    //      32 at a time, the survivors are compacted into a small queue, and the queue is drained by
+    //      drain_candidates(); the candidate list is never materialised ----
     float best = __int_as_float(0x7f800000);    // +inf ; `len < min_dist` with min_dist = INFINITY
     int best_idx = 0x7fffffff;
     v2 best_p = {0.0f, 0.0f};
-    int any = 0;
-    const int npairs = n_rays * n_rays;
-    for (int k = lane; k < npairs + n_rays; k += 32) {
-        v2 p;
-        bool ok;
+    int any = 0, qn = 0;
+    const int npairs = n_rays * n_rays, ntotal = npairs + n_rays;
+    int i = 0, j = (int)lane;                   // pair index of this lane: k = i * n_rays + j
+    while (j >= n_rays) { j -= n_rays; i++; }
+    for (int base = 0; base < ntotal; base += 32) {
+        const int k = base + (int)lane;
+        v2 p = {0.f, 0.f};
+        bool ok = false;
         if (k < npairs) {
-            const int i = k / n_rays, j = k - i * n_rays;
-            ok = (i != j) && ray_isect(s.rays[i], s.rays[j], p);
-        } else {
-            const ray r = s.rays[k - npairs];
-            const float len = v2_dot(r.dir, des_v);
-            p = v2_add(r.point, v2_scale(r.dir, len));
+            if (i != j) {
+                // C_RayRayIntersection2D (collision.c:854)
+                const v2 p1 = {s.rpx[i], s.rpz[i]}, p2 = {s.rpx[j], s.rpz[j]};
+                if (line_isect_s(p1, s.rsl[i], p2, s.rsl[j], p)) {
+                    ok = !(quot_lt0(p.x - p1.x, s.rdx[i]) || quot_lt0(p.z - p1.z, s.rdz[i]) ||
+                           quot_lt0(p.x - p2.x, s.rdx[j]) || quot_lt0(p.z - p2.z, s.rdz[j]));
+                }
+            }
+        } else if (k < ntotal) {
+            const int r = k - npairs;
+            const v2 d = {s.rdx[r], s.rdz[r]};
+            const float len = v2_dot(d, des_v);
+            p = v2_add(v2{s.rpx[r], s.rpz[r]}, v2_scale(d, len));
             ok = true;
         }
-        if (ok && !inside_pcr(s.rays, n_rays, p)) {
-            any = 1;
-            const v2 curr = v2_sub(p, ent.pos);
-            const float len = v2_len(v2_sub(des_v, curr));
-            if (len < best) { best = len; best_idx = k; best_p = curr; }   // k ascending per lane
+        const uint32_t m = __ballot_sync(FULL, ok);
+        if (ok) {
+            const int q = qn + __popc(m & ((1u << lane) - 1));
+            s.cqx[q] = p.x; s.cqz[q] = p.z; s.cqk[q] = k;
+        }
+        qn += __popc(m);
+        j += 32;
+        while (j >= n_rays) { j -= n_rays; i++; }
+        if (qn > CQ_CAP - 32 || base + 32 >= ntotal) {
+            __syncwarp();
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            __syncwarp();
+            qn = 0;
         }
     }
     any = __any_sync(FULL, any);

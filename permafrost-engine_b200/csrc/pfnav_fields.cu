@@ -563,18 +563,34 @@ k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uin
 // K3: LOS field. One warp per field; lane 0 replays the reference heap exactly.
 // ------------------------------------------------------------------------------------------
 #define LOS_WARPS_PER_CTA 4
-struct LosSmem {
+// previous-chunk field bytes may have been written by another SM during this launch (dependency-driven
+// scheduling): read them through L2
+#define LOS_PREV_LOAD(p) __ldcg(p)
+struct __align__(16) LosSmem {
     uint64_t pass[64];       // cost != 0xFF && blockers == 0
     uint64_t open[64];       // pass && cost <= 1  (neighbour_costs[i] > 1 test, field.c:2211)
     uint64_t assigned[64];   // integration_field < INF
-    uint64_t vis[64];
     uint64_t blk[64];
-    uint16_t heap[4100];     // 1-indexed; entry = prio2 << 12 | r << 6 | c
+    uint8_t  visb[4096];     // `visible`, one byte per tile: the serial loop only ever stores 1 (no read-modify-write)
+    uint16_t heap[4104];     // 1-indexed; entry = r << 6 | c (size keeps the struct a multiple of 16 B)
+    uint64_t dbits[64];      // heap slot i holds the current minimum priority d (word 0 is mirrored in a register)
 };
+
+static_assert(sizeof(LosSmem) % 16 == 0, "LosSmem must keep 16-byte alignment per warp");
 
 struct LosMapInfo {
     float map_x, map_z;
 };
+
+// OR 64 bits into a shared-memory row with two native 32-bit reductions (a 64-bit shared atomicOr
+// compiles to a compare-and-swap spin loop)
+__device__ __forceinline__ void or_row(uint64_t *row, uint64_t bits)
+{
+    unsigned *w = reinterpret_cast<unsigned *>(row);
+    const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32);
+    if (lo) atomicOr(w, lo);
+    if (hi) atomicOr(w + 1, hi);
+}
 
 // field_create_wavefront_blocked_line (field.c:463-517)
 __device__ void los_blocked_line(LosSmem &s, const LosMapInfo mi, int tgt_cr, int tgt_cc, int tgt_r, int tgt_c,
@@ -597,12 +613,18 @@ __device__ void los_blocked_line(LosSmem &s, const LosMapInfo mi, int tgt_cr, in
     const int sy = sz_ < 0.0f ? 1 : -1;
     int err = dx + dy, e2;
     int rr = r, c2 = c;
+    // bits of the row being walked accumulate in a register and are OR-ed into shared memory with a
+    // fire-and-forget reduction when the walk leaves the row: no load-use stall per step
+    int acc_row = rr;
+    uint64_t acc = 0;
     do {
-        s.blk[rr] |= 1ull << c2;
+        if (rr != acc_row) { or_row(&s.blk[acc_row], acc); acc_row = rr; acc = 0; }
+        acc |= 1ull << c2;
         e2 = 2 * err;
         if (e2 >= dy) { err += dy; c2 += sx; }
         if (e2 <= dx) { err += dx; rr += sy; }
     } while (rr >= 0 && rr < 64 && c2 >= 0 && c2 < 64);
+    or_row(&s.blk[acc_row], acc);
 }
 
 // field_is_los_corner (field.c:435)
@@ -619,49 +641,67 @@ __device__ __forceinline__ bool los_is_corner(const LosSmem &s, int r, int c)
     return false;
 }
 
+// The reference's binary heap (pqueue.h:109-208), 1-indexed, entries = prio2 << 12 | r << 6 | c.
+// A unit-cost wavefront only ever holds two adjacent priorities (d and d+1), so priorities are kept
+// modulo 4 and compared through their difference; and a push (always priority d+1, i.e. >= every
+// priority in the heap) never sifts up: it is an append.
+// (Two restructurings of this loop were measured on B200 and rejected: computing the sift path from a
+//  "holds priority d" bit per slot, lane 0 only: 3.7 ms per open 64x64 field; the same with the pop loop
+//  in lockstep on 32 lanes, neighbours on 4 lanes: 3.2 ms; this plain form: 2.2 ms. The loop is bound
+//  by the dependent-instruction chain of one thread)
 __device__ __forceinline__ bool heap_lt(uint16_t a, uint16_t b) { return (((b >> 12) - (a >> 12)) & 3) == 1; }
 
-// pq_coord_push (pqueue.h:165-188)
-__device__ __forceinline__ void heap_push(uint16_t *h, int &size, uint16_t e)
-{
-    int curr = size + 1, parent = curr >> 1;
-    while (curr > 1 && heap_lt(e, h[parent])) {    // nodes[parent].priority > in_prio
-        h[curr] = h[parent];
-        curr = parent;
-        parent >>= 1;
-    }
-    h[curr] = e;
-    size++;
-}
 // pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200)
 __device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
 {
     const uint16_t out = h[1];
     h[1] = h[size];
     size--;
+    // sift the former last element X (parked at h[size+1]) down from the root. Both children are
+    // loaded up front so that each level costs one shared-memory round trip.
+    const uint16_t x = h[size + 1];
     int root = 1;
-    while (root != size + 1) {
-        int target = size + 1;
+    while (true) {
         const int l = root * 2, r = l + 1;
-        if (l <= size && heap_lt(h[l], h[target])) target = l;
-        if (r <= size && heap_lt(h[r], h[target])) target = r;
-        h[root] = h[target];
+        if (l > size) break;
+        const uint16_t hl = h[l], hr = h[min(r, size)];
+        int target = -1;
+        uint16_t tv = x;
+        if (heap_lt(hl, tv)) { target = l; tv = hl; }
+        if (r <= size && heap_lt(hr, tv)) { target = r; tv = hr; }
+        if (target < 0) break;
+        h[root] = tv;
         root = target;
     }
+    h[root] = x;
     return out;
 }
 
 __global__ void __launch_bounds__(LOS_WARPS_PER_CTA * 32)
-k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int first, int n,
-      uint8_t *fields, const int32_t *__restrict__ out_slot)
+k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
+      uint8_t *fields, const int32_t *__restrict__ out_slot, unsigned *counter, int *done)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LosSmem &s = reinterpret_cast<LosSmem *>(smem_raw)[warp];
-    const int total_warps = gridDim.x * LOS_WARPS_PER_CTA;
-    for (int k = blockIdx.x * LOS_WARPS_PER_CTA + warp; k < n; k += total_warps) {
-        const int i = first + k;
+    // Dependency-driven scheduling: requests are sorted so that a request's prev_index is smaller than
+    // its own index; warps take indices in order from a global counter and wait (only) for the one
+    // field they depend on. No barrier between dependency levels: the LOS phase costs the slowest
+    // chain, not the sum over levels of the slowest field of each level.
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(counter, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
         const pfnav_los_req q = reqs[i];
+        if (q.prev_index >= 0) {
+            if (lane == 0) {
+                volatile int *flag = done + q.prev_index;
+                while (*flag == 0) __nanosleep(100);
+            }
+            __syncwarp();
+            __threadfence();
+        }
         // A chunk other than the destination whose shared edge with the previous chunk carries no
         // `visible` and no `wavefront_blocked` tile starts with an empty frontier and draws no line
         // (field.c:2157-2195): the field is all zero. Most chunks far from the goal end here.
@@ -673,10 +713,13 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
             else if (q.prev_chunk_c < q.chunk_c) { horiz = true;  pe = 63; }
             else                                 { horiz = true;  pe = 0;  }
             uint32_t any = 0;
-            for (int e = lane; e < 64; e += 32) any |= horiz ? prev[e * 64 + pe] : prev[pe * 64 + e];
+            for (int e = lane; e < 64; e += 32) any |= LOS_PREV_LOAD(horiz ? prev + e * 64 + pe : prev + pe * 64 + e);
             if (!__any_sync(0xffffffffu, any != 0)) {
                 uint4 *d4 = reinterpret_cast<uint4 *>(fields + (size_t)(out_slot ? out_slot[i] : i) * 4096);
                 for (int j = lane; j < 256; j += 32) d4[j] = make_uint4(0, 0, 0, 0);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *(volatile int *)(done + i) = 1;
                 continue;
             }
         }
@@ -707,8 +750,10 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
             s.pass[row] = p & ~blocked;
             s.open[row] = p & ~blocked & ~gt1;
             s.assigned[row] = 0;
-            s.vis[row] = 0;
             s.blk[row] = 0;
+            s.dbits[row] = 0;
+            uint4 *vz = reinterpret_cast<uint4 *>(s.visb + row * 64);
+            vz[0] = make_uint4(0, 0, 0, 0); vz[1] = make_uint4(0, 0, 0, 0); vz[2] = make_uint4(0, 0, 0, 0); vz[3] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
 
@@ -717,7 +762,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
             int size = 0;
             const bool dest_chunk = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
             if (dest_chunk) {
-                heap_push(h, size, (uint16_t)((q.tgt_tile_r << 6) | q.tgt_tile_c));
+                h[++size] = (uint16_t)((q.tgt_tile_r << 6) | q.tgt_tile_c);
                 s.assigned[q.tgt_tile_r] |= 1ull << q.tgt_tile_c;
             } else {
                 // carry the shared edge over from the previous chunk's field (field.c:2122-2196)
@@ -729,16 +774,16 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
                 else                                 { horizontal = true;  curr_edge = 63; prev_edge = 0;  }
                 for (int e = 0; e < 64; e++) {
                     const int r = horizontal ? e : curr_edge, c = horizontal ? curr_edge : e;
-                    const uint8_t pv = horizontal ? prev[e * 64 + prev_edge] : prev[prev_edge * 64 + e];
+                    const uint8_t pv = LOS_PREV_LOAD(horizontal ? prev + e * 64 + prev_edge : prev + prev_edge * 64 + e);
                     const uint64_t bit = 1ull << c;
                     // struct assignment overwrites both flags of the edge tile
-                    s.vis[r] = (s.vis[r] & ~bit) | ((pv & 1) ? bit : 0);
+                    s.visb[r * 64 + c] = pv & 1;
                     s.blk[r] = (s.blk[r] & ~bit) | ((pv & 2) ? bit : 0);
                     if (pv & 2)
                         los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
                                          q.chunk_r, q.chunk_c, r, c);
-                    if ((s.vis[r] >> c) & 1) {
-                        heap_push(h, size, (uint16_t)((r << 6) | c));     // priority 0
+                    if (pv & 1) {
+                        h[++size] = (uint16_t)((r << 6) | c);     // priority 0: an append, all seeds are equal
                         s.assigned[r] |= bit;
                     }
                 }
@@ -747,35 +792,49 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
                 const uint16_t cur = heap_pop(h, size);
                 const int r = (cur >> 6) & 63, c = cur & 63;
                 const uint16_t nprio = (uint16_t)((((cur >> 12) + 1) & 3) << 12);
-                // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0)
-                const int nr[4] = {r - 1, r, r, r + 1}, ncc[4] = {c, c - 1, c + 1, c};
-                // the neighbour list (incl. the wavefront_blocked filter) is collected before any
-                // neighbour is processed (field.c:2205): a line drawn for an earlier neighbour of this
-                // pop must not hide a later one
-                uint32_t take = 0;
+                // every bitmap row this pop can read, loaded together (one shared-memory round trip):
+                // rows r-1..r+1 of blocked/open/assigned, rows r-2..r+2 of passable (corner tests)
+                const int rm = max(r - 1, 0), rp = min(r + 1, 63), rmm = max(r - 2, 0), rpp = min(r + 2, 63);
+                const uint64_t b_m = s.blk[rm], b_0 = s.blk[r], b_p = s.blk[rp];
+                const uint64_t o_m = s.open[rm], o_0 = s.open[r], o_p = s.open[rp];
+                uint64_t a_m = s.assigned[rm], a_0 = s.assigned[r], a_p = s.assigned[rp];
+                const uint64_t p_mm = s.pass[rmm], p_m = s.pass[rm], p_0 = s.pass[r], p_p = s.pass[rp], p_pp = s.pass[rpp];
+                const uint64_t a_m0 = a_m, a_00 = a_0, a_p0 = a_p;
+                // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0). The list
+                // (incl. the wavefront_blocked filter) is collected before any neighbour is processed
+                // (field.c:2205): a line drawn for an earlier neighbour of this pop must not hide a later one
+                const bool t0 = r > 0 && !((b_m >> c) & 1), t1 = c > 0 && !((b_0 >> (c - 1)) & 1);
+                const bool t2 = c < 63 && !((b_0 >> (c + 1)) & 1), t3 = r < 63 && !((b_p >> c) & 1);
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int rr = nr[e], cc = ncc[e];
-                    if (rr < 0 || rr > 63 || cc < 0 || cc > 63) continue;
-                    if (!((s.blk[rr] >> cc) & 1)) take |= 1u << e;
-                }
-#pragma unroll 1
-                for (int e = 0; e < 4; e++) {
-                    if (!((take >> e) & 1)) continue;
-                    const int rr = nr[e], cc = ncc[e];
+                    const bool take = e == 0 ? t0 : e == 1 ? t1 : e == 2 ? t2 : t3;
+                    if (!take) continue;
+                    const int rr = e == 0 ? r - 1 : e == 3 ? r + 1 : r, cc = e == 1 ? c - 1 : e == 2 ? c + 1 : c;
                     const uint64_t bit = 1ull << cc;
-                    if (!(s.open[rr] & bit)) {
-                        if (!los_is_corner(s, rr, cc)) continue;
+                    const uint64_t orow = e == 0 ? o_m : e == 3 ? o_p : o_0;
+                    if (!(orow & bit)) {
+                        // field_is_los_corner (field.c:435) on the preloaded passable rows
+                        const uint64_t up = e == 0 ? p_mm : e == 3 ? p_0 : p_m;     // row rr-1
+                        const uint64_t dn = e == 0 ? p_0 : e == 3 ? p_pp : p_p;     // row rr+1
+                        const uint64_t me = e == 0 ? p_m : e == 3 ? p_p : p_0;      // row rr
+                        bool corner = false;
+                        if (rr > 0 && rr < 63) corner = (((up >> cc) ^ (dn >> cc)) & 1) != 0;
+                        if (!corner && cc > 0 && cc < 63) corner = (((me >> (cc - 1)) ^ (me >> (cc + 1))) & 1) != 0;
+                        if (!corner) continue;
                         los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
                                          q.chunk_r, q.chunk_c, rr, cc);
                     } else {
-                        s.vis[rr] |= bit;
-                        if (!(s.assigned[rr] & bit)) {
-                            s.assigned[rr] |= bit;
-                            heap_push(h, size, (uint16_t)(nprio | (rr << 6) | cc));
+                        s.visb[rr * 64 + cc] = 1;
+                        uint64_t &arow = e == 0 ? a_m : e == 3 ? a_p : a_0;
+                        if (!(arow & bit)) {
+                            arow |= bit;
+                            h[++size] = (uint16_t)(nprio | (rr << 6) | cc);
                         }
                     }
                 }
+                if (r > 0 && a_m != a_m0) s.assigned[r - 1] = a_m;
+                if (a_0 != a_00) s.assigned[r] = a_0;
+                if (r < 63 && a_p != a_p0) s.assigned[r + 1] = a_p;
             }
         }
         __syncwarp();
@@ -788,20 +847,25 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int fi
             if (row > 0) b |= s.blk[row - 1];
             if (row < 63) b |= s.blk[row + 1];
             b = b | (b << 1) | (b >> 1);
-            const uint64_t v = s.vis[row] & ~b, w = s.blk[row];
+            const uint64_t keep = ~b, w = s.blk[row];
             uint4 *d4 = reinterpret_cast<uint4 *>(dst + row * 64);
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(s.visb + row * 64);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                const uint4 vv = v4[j];
+                const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int sh = j * 16 + e * 4;
-                    o[e] = spread4((uint32_t)(v >> sh)) | (spread4((uint32_t)(w >> sh)) << 1);
+                    o[e] = (vw[e] & spread4((uint32_t)(keep >> sh))) | (spread4((uint32_t)(w >> sh)) << 1);
                 }
                 d4[j] = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
+        __threadfence();
         __syncwarp();
+        if (lane == 0) *(volatile int *)(done + i) = 1;
     }
 }
 
@@ -905,6 +969,7 @@ void pfnav_fields_free(pfnav_ctx *ctx)
 {
     free_map(ctx);
     cudaFree(ctx->d_stage); ctx->d_stage = nullptr;
+    cudaFree(ctx->d_los_sched); ctx->d_los_sched = nullptr; ctx->los_sched_bytes = 0;
     cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
     ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
 }
@@ -1230,15 +1295,24 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
     const FlowGrids g = grids_of(ctx);
     LosMapInfo mi{ctx->map_x, ctx->map_z};
     const size_t smem = LOS_WARPS_PER_CTA * sizeof(LosSmem);
-    pf_prof_scope prof(ctx, (cudaStream_t)stream, PF_PROF_LOS);
-    for (int w = 0; w < n_waves; w++) {
-        const int first = h_wave_offsets[w], cnt = h_wave_offsets[w + 1] - first;
-        if (cnt <= 0) continue;
-        const int grid = std::max(1, std::min((cnt + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA, ctx->sm_count * 5 * 4));
-        k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(g, mi, d_reqs, first, cnt, d_out_fields, d_out_slot);
-        ctx->launches++;
-        PF_CUDA(cudaGetLastError());
+    (void)n_waves; (void)h_wave_offsets;        // requests are dependency-sorted; the kernel schedules them itself
+    cudaStream_t st = (cudaStream_t)stream;
+    // scheduler state: [counter][done flags]
+    const size_t need = (n + 1) * sizeof(int);
+    if (ctx->los_sched_bytes < need) {
+        PF_CUDA(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_los_sched);
+        ctx->d_los_sched = nullptr; ctx->los_sched_bytes = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_los_sched, need * 2));
+        ctx->los_sched_bytes = need * 2;
     }
+    PF_CUDA(cudaMemsetAsync(ctx->d_los_sched, 0, need, st));
+    pf_prof_scope prof(ctx, st, PF_PROF_LOS);
+    const int grid = std::max(1, std::min((int)((n + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA), ctx->sm_count * 3));
+    k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, st>>>(g, mi, d_reqs, (int)n, d_out_fields, d_out_slot,
+                                                      (unsigned *)ctx->d_los_sched, (int *)ctx->d_los_sched + 1);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
     return PFNAV_OK;
 }
 

@@ -57,5 +57,32 @@ def main():
     ms1 = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), 1, out.data_ptr(), [0, 1], st), iters=3)
     print(json.dumps({"kernel": "k_los", "case": "single field latency", "ms": ms1}), flush=True)
 
+def goals():
+    """the bench's field phase alone: 16 goals, dense plan, flow waves + LOS chain into the pool"""
+    cw = ch = 16
+    p = synth.make_map(cw, ch, 0x5EED0001)
+    cost = synth.cost_from_pathable(p, cw, ch)
+    nav = capi.Nav(0)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost); nav.map_build_nav(0)
+    rng = np.random.default_rng(3)
+    tiles = synth.random_passable_tiles(cost, 16, rng)
+    targets = np.array([[int(t[0]) // cw, int(t[0]) % cw, int(t[1]), int(t[2])] for t in tiles], np.int32)
+    nav.pool_create(16, 16 * 256)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3): nf, nl = nav.pool_request_goals(np.arange(16, dtype=np.int32), targets, 0, st)
+    torch.cuda.synchronize()
+    nav.profile_enable(True)
+    ms = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); nav.pool_request_goals(np.arange(16, dtype=np.int32), targets, 0, st); b.record(); torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    prof = nav.profile_read()
+    print(json.dumps({"case": "16 goals dense", "flow": nf, "los": nl, "ms_total_median": float(np.median(ms)),
+                      "prof_flow_ms": prof["flow"][0] / 5, "prof_los_ms": prof["los"][0] / 5}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "goals":
+        goals(); sys.exit(0)
     main()
