@@ -235,7 +235,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    nav.profile_enable(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -247,16 +246,35 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = nav.launch_count() - launches0
-    prof = nav.profile_read()
-    nav.profile_enable(False)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(sum(step_ms))
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
         tl = torch.tensor([float(launches)], device="cuda"); dist.all_reduce(tl); launches = int(tl.item())
+    # ---- per-phase device times, each phase alone between synchronisations (kernel time without the
+    #      host-side gaps of the full step); used for the roofline line and flow_fields_per_sec ----
+    def phase_time(fn, iters=3):
+        ms = []
+        for _ in range(iters):
+            flush.zero_(); torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream); fn(); b_.record(stream); torch.cuda.synchronize()
+            ms.append(a_.elapsed_time(b_))
+        return float(np.median(ms))
+    nav.profile_enable(True)
+    phase_time(fields_phase); prof_f = nav.profile_read()
+    phase_time(lambda: nav.agents_rebuild_index(sp)); prof_i = nav.profile_read()
+    phase_time(lambda: nav.agents_tick(capi.TICK_VDES_FROM_POOL, sp)); prof_t = nav.profile_read()
+    nav.profile_enable(False)
+    prof = {"flow": prof_f["flow"], "los": prof_f["los"], "index": prof_i["index"], "vdes": prof_t["vdes"],
+            "cohesion": prof_t["cohesion"], "velocity": prof_t["velocity"]}
+    prof_iters = 3
     # miss counter sanity: every agent must have found its field in the pool
     vpref, vdes, los = nav.agents_read_debug(nwork)
     frac_no_dir = float((np.abs(vdes).sum(axis=1) == 0).mean())
+    if frac_no_dir > 0.01:
+        raise SystemExit("bench.py: %.2f%% of the agents found no flow direction in the field pool -- the step did not do "
+                         "the work it claims" % (100 * frac_no_dir))
 
     # ---- timed: e2e through the host-buffer ABI ----
     for _ in range(2):
@@ -280,7 +298,7 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     # dominant kernel by measured device time
-    groups = {k: v[0] for k, v in prof.items()}
+    groups = {k: v[0] / prof_iters * args.steps for k, v in prof.items()}      # normalised to `steps` like the rest
     dom = max(groups, key=groups.get)
     per_launch = {"velocity": nwork * ALG_BYTES_PER_AGENT, "cohesion": nwork * ALG_BYTES_PER_AGENT,
                   "flow": nf * ALG_BYTES_PER_FLOW_FIELD, "los": nl * ALG_BYTES_PER_LOS_FIELD,

@@ -100,6 +100,19 @@ int  pfnav_map_refresh_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c
 int  pfnav_local_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out);
 int  pfnav_portals_get(pfnav_ctx *ctx, int layer, int32_t *out, int maxout, int *out_n);
 
+/* N_BlockersIncref / N_BlockersDecref (nav.c:4663-4683): reference-count the tiles under a circle
+ * (M_Tile_AllUnderCircle, tile.c:687) plus 1/2/3 contour rings (M_Tile_Contour, tile.c:759) for the
+ * 3x3/5x5/7x7 layers, on the ground AND water layers for non-air entities, air layers otherwise.
+ * Layers the context does not hold are skipped. Host-side; the device sees the change at commit. */
+int  pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags);
+int  pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags);
+int  pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out);
+/* N_Update + N_ApplyDeferredInvalidations (nav.c:2119-2223): for every chunk whose occupancy
+ * changed, recompute the local islands, refresh the portal edge states, push the chunk's blockers +
+ * islands to the device, and invalidate the pool: entries AT the chunk, and -- when an edge state
+ * flipped -- every field of every destination routed THROUGH it (fieldcache.c:460-545). */
+int  pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Flow fields + LOS fields (seam B2: src/navigation/field.h:115-202)
  * ---------------------------------------------------------------------------------------- */

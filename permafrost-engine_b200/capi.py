@@ -45,7 +45,8 @@ FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 
 SYMBOLS = [
     "pfnav_last_error", "pfnav_version", "pfnav_create", "pfnav_destroy", "pfnav_map_create",
     "pfnav_map_upload_layer", "pfnav_map_update_chunk", "pfnav_map_build_nav", "pfnav_map_refresh_chunk",
-    "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_plan_goal", "pfnav_route_build", "pfnav_route_islands_get",
+    "pfnav_local_islands_get", "pfnav_portals_get", "pfnav_blockers_incref", "pfnav_blockers_decref", "pfnav_blockers_get",
+    "pfnav_map_commit", "pfnav_plan_goal", "pfnav_route_build", "pfnav_route_islands_get",
     "pfnav_route_edges_get", "pfnav_route_request_path", "pfnav_create_hostonly", "pfnav_pool_request_path", "pfnav_pool_get", "pfnav_flow_fields_update",
     "pfnav_flow_fields_update_dev", "pfnav_los_fields_create", "pfnav_los_fields_create_dev",
     "pfnav_set_tma", "pfnav_pool_create", "pfnav_pool_put", "pfnav_pool_clear", "pfnav_pool_request_goal", "pfnav_pool_request_goals",
@@ -86,6 +87,10 @@ def load():
     L.pfnav_plan_goal.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.pfnav_create_hostonly.argtypes = [C.POINTER(C.c_void_p)]
+    L.pfnav_blockers_incref.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
+    L.pfnav_blockers_decref.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
+    L.pfnav_blockers_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pfnav_map_commit.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.pfnav_pool_request_path.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_pool_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
@@ -234,6 +239,22 @@ class Nav:
         _chk(self.L.pfnav_plan_goal(self.h, layer, target_td[0], target_td[1], target_td[2], target_td[3],
                                     _p(fr), _p(fc), _p(fw), cap, C.byref(nf), _p(lr), _p(lc), cap, C.byref(nl)))
         return fr[:nf.value].copy(), fc[:nf.value].copy(), fw[:nf.value].copy(), lr[:nl.value].copy(), lc[:nl.value].copy()
+
+    def blockers_incref(self, x, z, radius, faction=0, flags=FLAG_MOVABLE):
+        _chk(self.L.pfnav_blockers_incref(self.h, x, z, radius, faction, flags))
+
+    def blockers_decref(self, x, z, radius, faction=0, flags=FLAG_MOVABLE):
+        _chk(self.L.pfnav_blockers_decref(self.h, x, z, radius, faction, flags))
+
+    def blockers(self, layer=0):
+        out = np.zeros((self.cw * self.ch, 64, 64), np.uint16)
+        _chk(self.L.pfnav_blockers_get(self.h, layer, _p(out)))
+        return out
+
+    def map_commit(self):
+        n = C.c_int(0)
+        _chk(self.L.pfnav_map_commit(self.h, C.byref(n)))
+        return n.value
 
     def route_build(self, layer=0):
         _chk(self.L.pfnav_route_build(self.h, layer))

@@ -930,6 +930,7 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     ctx->h_pool_has.assign(max_fields, 0);
     ctx->h_pool_ffid.assign(nslots, 0);
     ctx->pool_ndests = ndests; ctx->pool_max = max_fields; ctx->pool_used = 0;
+    ctx->goal_batch.valid = false;
     return PFNAV_OK;
 }
 
@@ -942,6 +943,7 @@ extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
     std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
     std::fill(ctx->h_pool_has.begin(), ctx->h_pool_has.end(), 0);
     std::fill(ctx->h_pool_ffid.begin(), ctx->h_pool_ffid.end(), 0);
+    ctx->goal_batch.valid = false;
     ctx->pool_used = 0;
     return PFNAV_OK;
 }
@@ -967,6 +969,7 @@ extern "C" int pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
     if (los_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)slot * 4096, los_field, 4096, cudaMemcpyHostToDevice)); has |= 2; }
     ctx->h_pool_has[slot] = has;
     PF_CUDA(cudaMemcpy(d_has + slot, &has, 1, cudaMemcpyHostToDevice));
+    ctx->goal_batch.valid = false;
     return PFNAV_OK;
 }
 

@@ -1,0 +1,257 @@
+// pfnav_blockers.cu -- dynamic obstacles: host-side restatement of the blocker reference counting and
+// of N_Update, pushing only the chunks that changed to the device (deltas, not whole-state re-uploads
+// as the reference's GLSL path does every tick, src/game/movement.c:3894-3900).
+//
+// Restates (reference file:line):
+//   N_BlockersIncref / N_BlockersDecref                src/navigation/nav.c:4663-4683
+//   n_update_blockers_circle_{ground,water,air}        src/navigation/nav.c:1051-1127
+//   n_update_blockers                                  src/navigation/nav.c:1017-1049
+//   M_Tile_AllUnderCircle / M_Tile_Contour             src/map/tile.c:687-718, 759-852
+//   C_CircleRectIntersection, C_PointInsideRect2D, C_LineCircleIntersection
+//                                                      src/phys/collision.c:997-1027, 756-768, 960-996
+//   N_Update + N_ApplyDeferredInvalidations            src/navigation/nav.c:2119-2223
+//   N_FC_InvalidateAllAtChunk / ...ThroughChunk        src/navigation/fieldcache.c:460-472, 481-545
+#include "pfnav_internal.cuh"
+#include <algorithm>
+#include <limits.h>
+#include <math.h>
+#include <set>
+#include <string.h>
+#include <unordered_map>
+
+int pfnav_route_refresh_edges(pfnav_ctx *ctx, int layer, int chunk);      // pfnav_route.cu; -1 if routing not built
+
+namespace {
+
+struct td { int chunk_r, chunk_c, tile_r, tile_c; };
+struct v2f { float x, z; };
+#define EPS_COLL (1.0f / 1024.0f)          // collision.c:64
+
+static bool point_inside_rect(v2f p, v2f a, v2f b, v2f d)
+{
+    const v2f ap = {p.x - a.x, p.z - a.z}, ab = {b.x - a.x, b.z - a.z}, ad = {d.x - a.x, d.z - a.z};
+    const float ap_ab = ap.x * ab.x + ap.z * ab.z, ap_ad = ap.x * ad.x + ap.z * ad.z;
+    return (ap_ab >= 0.0f && ap_ab <= ab.x * ab.x + ab.z * ab.z) && (ap_ad >= 0.0f && ap_ad <= ad.x * ad.x + ad.z * ad.z);
+}
+
+static bool line_circle(float ax, float az, float bx, float bz, v2f c, float radius)
+{
+    const float dx = bx - ax, dz = bz - az;
+    const float A = pow(dx, 2) + pow(dz, 2);
+    const float B = 2 * (dx * (ax - c.x) + dz * (az - c.z));
+    const float C = pow(ax - c.x, 2) + pow(az - c.z, 2) - pow(radius, 2);
+    const float det = pow(B, 2) - (4 * A * C);
+    float t;
+    if (det < 0.0f || A < EPS_COLL) return false;
+    else if (det == 0.0f) t = -B / (2 * A);
+    else {
+        const float t1 = (-B + sqrt(det)) / (2 * A), t2 = (-B - sqrt(det)) / (2 * A);
+        t = std::min(t1, t2);
+    }
+    if (t < 0.0f || t > 1.0f) return false;
+    return true;
+}
+
+// C_CircleRectIntersection (collision.c:997); rect = {x, z, width, height}, x decreasing with the column
+static bool circle_rect(v2f center, float radius, float rx, float rz, float w, float h)
+{
+    const v2f corners[4] = {{rx - w, rz}, {rx, rz}, {rx, rz + h}, {rx - w, rz + h}};
+    if (point_inside_rect(center, corners[0], corners[1], corners[3])) return true;
+    for (int i = 0; i < 4; i++) {
+        const float ddx = corners[i].x - center.x, ddz = corners[i].z - center.z;
+        if ((float)sqrt(ddx * ddx + ddz * ddz) <= radius) return true;
+    }
+    for (int i = 0; i < 4; i++) {
+        const v2f a = corners[i], b = corners[(i + 1) & 3];
+        if (line_circle(a.x, a.z, b.x, b.z, center, radius)) return true;
+    }
+    return false;
+}
+
+// M_Tile_DescForPoint2D with the nav resolution (tile.c:547)
+static bool desc_for_point(const pfnav_ctx *ctx, float px, float pz, td *out)
+{
+    const float width = (float)(ctx->chunk_w * 256), height = (float)(ctx->chunk_h * 256);
+    if (px > ctx->map_x || px < ctx->map_x - width) return false;
+    if (pz < ctx->map_z || pz > ctx->map_z + height) return false;
+    int chunk_r = (int)(fabs(ctx->map_z - pz) / 256.0f), chunk_c = (int)(fabs(ctx->map_x - px) / 256.0f);
+    chunk_r = std::min(std::max(chunk_r, 0), ctx->chunk_h - 1);
+    chunk_c = std::min(std::max(chunk_c, 0), ctx->chunk_w - 1);
+    const float bx = ctx->map_x - (chunk_c * 256.0f), bz = ctx->map_z + (chunk_r * 256.0f);
+    int tile_r = (int)(fabs(bz - pz) / 4), tile_c = (int)(fabs(bx - px) / 4);
+    out->chunk_r = chunk_r; out->chunk_c = chunk_c;
+    out->tile_r = std::min(std::max(tile_r, 0), 63); out->tile_c = std::min(std::max(tile_c, 0), 63);
+    return true;
+}
+
+// M_Tile_AllUnderCircle (tile.c:687)
+static size_t tiles_under_circle(const pfnav_ctx *ctx, v2f c, float radius, td *out, size_t maxout)
+{
+    td tile;
+    if (!desc_for_point(ctx, c.x, c.z, &tile)) return 0;
+    const int ntiles = (int)ceil(radius / 4);
+    size_t ret = 0;
+    for (int dr = -ntiles; dr <= ntiles; dr++)
+        for (int dc = -ntiles; dc <= ntiles; dc++) {
+            const int ar = tile.chunk_r * 64 + tile.tile_r + dr, ac = tile.chunk_c * 64 + tile.tile_c + dc;
+            if (ar < 0 || ar >= ctx->chunk_h * 64 || ac < 0 || ac >= ctx->chunk_w * 64) continue;
+            const td cur = {ar / 64, ac / 64, ar % 64, ac % 64};
+            // M_Tile_Bounds (tile.c:356)
+            const float bx = (ctx->map_x - (float)(cur.chunk_c * 256)) - (float)(cur.tile_c * 4);
+            const float bz = (ctx->map_z + (float)(cur.chunk_r * 256)) + (float)(cur.tile_r * 4);
+            if (!circle_rect(c, radius, bx, bz, 4.0f, 4.0f)) continue;
+            out[ret++] = cur;
+            if (ret == maxout) return ret;
+        }
+    return ret;
+}
+
+// M_Tile_Contour (tile.c:759)
+static size_t tiles_contour(const pfnav_ctx *ctx, size_t ntds, const td *tds, td *out, size_t maxout)
+{
+    if (ntds == 0) return 0;
+    int minr = INT_MAX, minc = INT_MAX, maxr = INT_MIN, maxc = INT_MIN;
+    for (size_t i = 0; i < ntds; i++) {
+        const int ar = tds[i].chunk_r * 64 + tds[i].tile_r, ac = tds[i].chunk_c * 64 + tds[i].tile_c;
+        minr = std::min(minr, ar); minc = std::min(minc, ac); maxr = std::max(maxr, ar); maxc = std::max(maxc, ac);
+    }
+    const int dr = maxr - minr + 1, dc = maxc - minc + 1;
+    const size_t width = dc + 2, height = dr + 2;
+    std::vector<uint8_t> marked(width * height, 0);
+    for (size_t i = 0; i < ntds; i++) {
+        const int ar = tds[i].chunk_r * 64 + tds[i].tile_r, ac = tds[i].chunk_c * 64 + tds[i].tile_c;
+        marked[(ar - minr + 1) * width + (ac - minc + 1)] = 1;
+    }
+    size_t ret = 0;
+    for (int r = minr - 1; r <= maxr + 1; r++)
+        for (int c = minc - 1; c <= maxc + 1; c++) {
+            if (r < 0 || r >= ctx->chunk_h * 64 || c < 0 || c >= ctx->chunk_w * 64) continue;
+            const int relr = r - minr + 1, relc = c - minc + 1;
+            if (marked[relr * width + relc]) continue;
+            if (ret == maxout) return ret;
+            bool contour = false;
+            if ((relr > 0 && marked[(relr - 1) * (dc + 2) + relc]) || (relr < dr && marked[(relr + 1) * (dc + 2) + relc]) ||
+                (relc > 0 && marked[relr * (dc + 2) + (relc - 1)]) || (relc < dc && marked[relr * (dc + 2) + (relc + 1)]))
+                contour = true;
+            if ((relr > 0 && relc > 0 && marked[(relr - 1) * (dc + 2) + (relc - 1)]) ||
+                (relr > 0 && relc < dc && marked[(relr - 1) * (dc + 2) + (relc + 1)]) ||
+                (relr < dr && relc > 0 && marked[(relr + 1) * (dc + 2) + (relc - 1)]) ||
+                (relr < dr && relc < dc && marked[(relr + 1) * (dc + 2) + (relc + 1)]))
+                contour = true;
+            if (contour) out[ret++] = {r / 64, c / 64, r % 64, c % 64};
+        }
+    return ret;
+}
+
+static std::unordered_map<const pfnav_ctx *, std::set<std::pair<int, int>>> g_dirty;     // (layer, chunk)
+
+// n_update_blockers (nav.c:1017) on the host mirror; layers the context does not hold are skipped
+static void apply(pfnav_ctx *ctx, int layer, const td *tds, size_t n, int delta)
+{
+    if (layer >= ctx->nlayers) return;
+    const size_t lbase = (size_t)layer * ctx->chunk_w * ctx->chunk_h * 4096;
+    for (size_t i = 0; i < n; i++) {
+        const int chunk = tds[i].chunk_r * ctx->chunk_w + tds[i].chunk_c;
+        uint16_t &v = ctx->h_blk[lbase + (size_t)chunk * 4096 + tds[i].tile_r * 64 + tds[i].tile_c];
+        const int prev = v;
+        v = (uint16_t)(prev + delta);
+        if (!!v != !!prev) g_dirty[ctx].insert({layer, chunk});
+    }
+}
+
+static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, uint32_t flags, int delta)
+{
+    td tds[1024], o3[1024], o5[1024], o7[1024];
+    const size_t n = tiles_under_circle(ctx, {x, z}, range, tds, 1024);
+    const size_t n3 = tiles_contour(ctx, n, tds, o3, 1024);
+    const size_t n5 = tiles_contour(ctx, n3, o3, o5, 1024);
+    const size_t n7 = tiles_contour(ctx, n5, o5, o7, 1024);
+    // layer groups: ground 0..3, water 4..7, air 8..11 (nav.h:78-92); non-air entities block ground AND water
+    const int groups[2] = {(flags & PFNAV_FLAG_AIR) ? 8 : 4, (flags & PFNAV_FLAG_AIR) ? -1 : 0};
+    for (int gi = 0; gi < 2; gi++) {
+        const int g = groups[gi];
+        if (g < 0) continue;
+        apply(ctx, g + 0, tds, n, delta);
+        apply(ctx, g + 1, tds, n, delta); apply(ctx, g + 1, o3, n3, delta);
+        apply(ctx, g + 2, tds, n, delta); apply(ctx, g + 2, o3, n3, delta); apply(ctx, g + 2, o5, n5, delta);
+        apply(ctx, g + 3, tds, n, delta); apply(ctx, g + 3, o3, n3, delta); apply(ctx, g + 3, o5, n5, delta); apply(ctx, g + 3, o7, n7, delta);
+    }
+    return PFNAV_OK;
+}
+
+}   // namespace
+
+void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); }
+
+extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    (void)faction_id;        // per-faction counts (chunk->factions) feed attacking paths only: not implemented
+    return blockers_circle(ctx, x, z, range, flags, +1);
+}
+
+extern "C" int pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    (void)faction_id;
+    return blockers_circle(ctx, x, z, range, flags, -1);
+}
+
+// N_Update + N_ApplyDeferredInvalidations: recompute the local islands of every dirty chunk, refresh the
+// portal edge states there, push the chunk (blockers + islands) to the device, and invalidate pool
+// entries: everything AT a dirty chunk; and, when an edge state flipped, every field of every
+// destination whose path runs THROUGH that chunk. *out_ndirty = number of (layer, chunk) pairs handled.
+extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    auto it = g_dirty.find(ctx);
+    int nd = 0;
+    if (it != g_dirty.end()) {
+        const int chunks = ctx->chunk_w * ctx->chunk_h;
+        bool pool_touched = false;
+        for (const auto &lc : it->second) {
+            const int layer = lc.first, chunk = lc.second;
+            int rc = pfnav_map_refresh_chunk(ctx, layer, chunk / ctx->chunk_w, chunk % ctx->chunk_w);
+            if (rc) return rc;
+            const int flipped = pfnav_route_refresh_edges(ctx, layer, chunk);
+            nd++;
+            if (!ctx->h_pool_slot.empty()) {
+                for (int d = 0; d < ctx->pool_ndests; d++) {
+                    const size_t si = (size_t)d * chunks + chunk;
+                    const int slot = ctx->h_pool_slot[si];
+                    if (slot < 0 || !ctx->h_pool_has[slot]) continue;
+                    pool_touched = true;
+                    if (flipped > 0) {
+                        // N_FC_InvalidateAllThroughChunk: the whole path of this destination goes
+                        for (int c2 = 0; c2 < chunks; c2++) {
+                            const int s2 = ctx->h_pool_slot[(size_t)d * chunks + c2];
+                            if (s2 >= 0) ctx->h_pool_has[s2] = 0;
+                            ctx->h_pool_ffid[(size_t)d * chunks + c2] = 0;
+                        }
+                    } else {
+                        ctx->h_pool_has[slot] = 0;
+                        ctx->h_pool_ffid[si] = 0;
+                    }
+                }
+            }
+        }
+        it->second.clear();
+        if (pool_touched && ctx->device >= 0) {
+            PF_CUDA(cudaSetDevice(ctx->device));
+            PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
+                               cudaMemcpyHostToDevice));
+        }
+        ctx->goal_batch.valid = false;
+    }
+    if (out_ndirty) *out_ndirty = nd;
+    return PFNAV_OK;
+}
+
+// Read back one layer's blocker counts ([chunk][64][64] u16) from the host mirror (parity tests).
+extern "C" int pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out)
+{
+    PF_ARG(ctx && out && layer >= 0 && layer < ctx->nlayers, "args");
+    const size_t ltiles = (size_t)ctx->chunk_w * ctx->chunk_h * 4096;
+    memcpy(out, ctx->h_blk.data() + ltiles * layer, ltiles * 2);
+    return PFNAV_OK;
+}

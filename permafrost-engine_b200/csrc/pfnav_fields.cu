@@ -975,11 +975,13 @@ void pfnav_fields_free(pfnav_ctx *ctx)
 }
 
 void pfnav_route_forget(const pfnav_ctx *ctx);
+void pfnav_blockers_forget(const pfnav_ctx *ctx);
 
 extern "C" void pfnav_destroy(pfnav_ctx *ctx)
 {
     if (!ctx) return;
     pfnav_route_forget(ctx);
+    pfnav_blockers_forget(ctx);
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
@@ -1037,6 +1039,7 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     PF_ARG(ctx, "ctx");
     PF_ARG(chunk_w > 0 && chunk_h > 0 && chunk_w <= 64 && chunk_h <= 64, "chunk_w/chunk_h must be in 1..64 (dest_id has 6 bits per chunk coordinate, nav.c:841)");
     PF_ARG(nlayers > 0 && nlayers <= PFNAV_NAV_LAYER_MAX, "nlayers");
+    ctx->map_epoch++;
     ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
     ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;
     ctx->map_x = map_x; ctx->map_z = map_z;
@@ -1086,6 +1089,7 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(cost_base, "cost_base");
+    ctx->map_epoch++;
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     if (ctx->device < 0) {
         memmove(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);
@@ -1127,6 +1131,7 @@ extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, in
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk coords");
+    ctx->map_epoch++;
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     const size_t off = ltiles * layer + (size_t)chunk_r * 64 * ctx->W64 + chunk_c * 64;
     const size_t hoff = ltiles * layer + ((size_t)chunk_r * ctx->chunk_w + chunk_c) * 4096;

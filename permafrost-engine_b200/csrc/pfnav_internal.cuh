@@ -80,6 +80,13 @@ struct pfnav_ctx {
     std::vector<uint8_t> h_pool_has;
     std::vector<uint64_t> h_pool_ffid;     // [ndests][chunks]: ff_id currently mapped (dest, chunk) -> field, 0 = none
     void *d_plan_buf = nullptr; size_t plan_buf_bytes = 0;    // request staging for pfnav_pool_request_goal
+    // The plan of the last goal batch stays resident on the device: re-requesting the same goals on an
+    // unchanged map (map_epoch) relaunches the kernels without re-planning or re-uploading anything.
+    uint64_t map_epoch = 0;
+    struct goal_batch_t {
+        bool valid = false; uint64_t epoch = 0; int layer = 0; std::vector<int32_t> dests, targets;
+        int nf = 0, nl = 0; std::vector<int32_t> fwave_off; size_t b_fr = 0, b_fs = 0, b_lr = 0, b_ls = 0;
+    } goal_batch;
     uint8_t *d_pool_flow = nullptr;   // [max][4096]
     uint8_t *d_pool_los = nullptr;    // [max][4096]
 

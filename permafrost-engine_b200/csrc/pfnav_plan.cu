@@ -272,6 +272,31 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     if (out_n_los) *out_n_los = 0;
     if (ngoals == 0) return PFNAV_OK;
     const int chunks = ctx->chunk_w * ctx->chunk_h;
+    {   // fast path: the same batch on an unchanged map and pool -> the plan is still resident on the device
+        auto &gb = ctx->goal_batch;
+        if (gb.valid && gb.epoch == ctx->map_epoch && gb.layer == layer && (int)gb.dests.size() == ngoals &&
+            memcmp(gb.dests.data(), dests, (size_t)ngoals * 4) == 0 && memcmp(gb.targets.data(), targets, (size_t)ngoals * 16) == 0) {
+            PF_CUDA(cudaSetDevice(ctx->device));
+            cudaStream_t st = (cudaStream_t)stream;
+            const uint8_t *dev = (const uint8_t *)ctx->d_plan_buf;
+            int rc = 0;
+            for (size_t w = 0; w + 1 < gb.fwave_off.size(); w++) {
+                const int first = gb.fwave_off[w], cnt = gb.fwave_off[w + 1] - first;
+                if (cnt <= 0) continue;
+                rc = pfnav_flow_launch(ctx, (const pfnav_field_req *)dev + first, cnt, ctx->d_pool_flow,
+                                       (const int32_t *)(dev + gb.b_fr) + first, st);
+                if (rc) return rc;
+            }
+            const int32_t one_wave[2] = {0, gb.nl};
+            rc = pfnav_los_launch(ctx, (const pfnav_los_req *)(dev + gb.b_fr + gb.b_fs), gb.nl, ctx->d_pool_los,
+                                  (const int32_t *)(dev + gb.b_fr + gb.b_fs + gb.b_lr), 1, one_wave, st);
+            if (rc) return rc;
+            if (out_n_flow) *out_n_flow = gb.nf;
+            if (out_n_los) *out_n_los = gb.nl;
+            return PFNAV_OK;
+        }
+        gb.valid = false;
+    }
     const int cap = chunks * 8 + 8;
     std::vector<pfnav_field_req> fr(cap), all_fr;
     std::vector<pfnav_los_req> lr(cap), all_lr;
@@ -367,6 +392,12 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     }
     rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), st);
     if (rc) return rc;
+    {
+        auto &gb = ctx->goal_batch;
+        gb.valid = true; gb.epoch = ctx->map_epoch; gb.layer = layer;
+        gb.dests.assign(dests, dests + ngoals); gb.targets.assign(targets, targets + 4 * (size_t)ngoals);
+        gb.nf = nf; gb.nl = nl; gb.fwave_off = fwave_off; gb.b_fr = b_fr; gb.b_fs = b_fs; gb.b_lr = b_lr; gb.b_ls = b_ls;
+    }
     if (out_n_flow) *out_n_flow = nf;
     if (out_n_los) *out_n_los = nl;
     return PFNAV_OK;

@@ -174,6 +174,21 @@ static void update_edge_states(pfnav_ctx *ctx, pfnav_route_layer &RL, int layer,
         }
 }
 
+// n_update_edge_states for one chunk after its islands changed; returns the number of flipped edges,
+// or -1 when the routing structure of the layer has not been built.
+int pfnav_route_refresh_edges(pfnav_ctx *ctx, int layer, int chunk)
+{
+    auto it = g_routes.find(ctx);
+    if (it == g_routes.end() || layer >= (int)it->second.size() || !it->second[layer].built) return -1;
+    auto &RL = it->second[layer];
+    std::vector<int> before;
+    for (auto &ev : RL.chunks[chunk].edges) for (auto &e : ev) before.push_back(e.es);
+    update_edge_states(ctx, RL, layer, chunk);
+    int flipped = 0; size_t k = 0;
+    for (auto &ev : RL.chunks[chunk].edges) for (auto &e : ev) flipped += (e.es != before[k++]);
+    return flipped;
+}
+
 // Build the routing structure of one layer (needs pfnav_map_build_nav first).
 extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
 {
@@ -693,6 +708,7 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
     if (out_n_flow) *out_n_flow = nf;
     if (out_n_los) *out_n_los = nl;
     if (nf == 0 && nl == 0) return PFNAV_OK;
+    ctx->goal_batch.valid = false;          // the staging buffer is about to be reused
     auto slot_for = [&](int chunk, uint8_t bits) -> int {
         const size_t si = (size_t)dest * chunks + chunk;
         int slot = ctx->h_pool_slot[si];

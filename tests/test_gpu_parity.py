@@ -288,6 +288,62 @@ def test_pool_request_path_golden(nav):
         assert ok0 == ok1 and nf1 == 0 and nl1 == 0          # everything cached the second time
 
 
+def test_pool_request_goals_vs_port(nav, pforacle):
+    """batched goal requests (flow waves + dependency-scheduled LOS chains straight into the pool), the
+    resident-plan fast path on a repeated batch, and invalidation of that plan when the map changes"""
+    cw = ch = 4
+    p = cases.noise_map(cw, ch, 95, 0.1)
+    cost = synth.cost_from_pathable(p, cw, ch)
+    _upload(nav, cw, ch, cost)
+    nav.map_build_nav(0)
+    liid = nav.local_islands(0)
+    om = pforacle.OracleMap(cw, ch, cost, None, liid)
+    rng = np.random.default_rng(95)
+    tiles = synth.random_passable_tiles(cost, 5, rng)
+    targets = np.array([[int(t[0]) // cw, int(t[0]) % cw, int(t[1]), int(t[2])] for t in tiles], np.int32)
+    nav.pool_create(5, 5 * cw * ch)
+
+    def expected(om_):
+        exp = []
+        for d in range(5):
+            fr, fc, fw, lr, lc = nav.plan_goal(tuple(int(v) for v in targets[d]))
+            fields = {}
+            for w in range(int(fw.max()) + 1):
+                sel = np.nonzero(fw == w)[0]
+                base = np.stack([fields.get(int(fc[i]), np.zeros((64, 64), np.uint8)) for i in sel])
+                out = om_.flow_fields_update(fr[sel], inout=base)
+                for k, i in enumerate(sel):
+                    fields[int(fc[i])] = out[k]
+            los = om_.los_fields_create(lr)
+            exp.append((fields, {int(lc[k]): los[k] for k in range(len(lr))}))
+        return exp
+
+    def check(exp):
+        for d in range(5):
+            for c in range(cw * ch):
+                f, l, _ = nav.pool_get(d, (c // cw, c % cw))
+                assert (f is not None) == (c in exp[d][0]) and (l is not None) == (c in exp[d][1])
+                if f is not None:
+                    assert (f == exp[d][0][c]).all()
+                if l is not None:
+                    assert (l == exp[d][1][c]).all()
+
+    exp = expected(om)
+    for _ in range(3):                                   # 2nd and 3rd call take the resident-plan path
+        nf, nl = nav.pool_request_goals(np.arange(5, dtype=np.int32), targets)
+        assert nf >= 5 and nl >= 5
+        check(exp)
+    # block a band of tiles in one chunk: islands change, the resident plan must be dropped
+    blk = np.zeros((64, 64), np.uint16); blk[20:23, 5:60] = 1
+    nav.map_update_chunk(0, (1, 1), None, blk, None)
+    nav.map_refresh_chunk(0, (1, 1))
+    blk_all = np.zeros(cost.shape, np.uint16); blk_all[1 * cw + 1] = blk
+    om2 = pforacle.OracleMap(cw, ch, cost, blk_all, nav.local_islands(0))
+    nav.pool_create(5, 5 * cw * ch)
+    nav.pool_request_goals(np.arange(5, dtype=np.int32), targets)
+    check(expected(om2))
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
 FD_STEP = {1: (-1, -1), 2: (-1, 0), 3: (-1, 1), 4: (0, -1), 5: (0, 1), 6: (1, -1), 7: (1, 0), 8: (1, 1)}
 

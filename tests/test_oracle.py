@@ -205,6 +205,56 @@ def test_route_request_path_vs_ref(pfref, pforacle):
     ref.close(); nav.close()
 
 
+def test_blockers_commit_and_route_vs_ref(pfref, pforacle):
+    """N_BlockersIncref/Decref (circle + contour rings on the 4 ground layers), N_Update (islands, edge
+    states) and path requests on the churned map: identical counts, island ids, edges, routes, fields"""
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, 9, 0.05)
+    ref = pfref.RefMap(cw, ch, p)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 4)
+    for l in range(4):
+        nav.map_upload_layer(l, ref.cost_base(l)); nav.map_build_nav(l)
+    nav.route_build(0)
+    rng = np.random.default_rng(9)
+    placed = []
+    for it in range(60):
+        x, z, r = -float(rng.uniform(2, 510)), float(rng.uniform(2, 510)), float(rng.choice([1.5, 3.0, 6.0, 11.0]))
+        ref.blockers_incref(x, z, r, 0, capi.FLAG_MOVABLE); nav.blockers_incref(x, z, r, 0, capi.FLAG_MOVABLE)
+        placed.append((x, z, r))
+        if it % 3 == 2:
+            x, z, r = placed.pop(int(rng.integers(0, len(placed))))
+            ref.blockers_decref(x, z, r, 0, capi.FLAG_MOVABLE); nav.blockers_decref(x, z, r, 0, capi.FLAG_MOVABLE)
+    ref.update()
+    assert nav.map_commit() > 0
+    for l in range(4):
+        assert (ref.blockers(l) == nav.blockers(l)).all()
+        assert (ref.local_islands(l) == nav.local_islands(l)).all()
+    for row in ref.portals():
+        ci = int(row[0]) * cw + int(row[1])
+        assert (ref.portal_edges(0, ci, int(row[2])) == nav.route_edges(ci, int(row[2]))).all()
+    cost, blk = ref.cost_base(), ref.blockers()
+    om = pforacle.OracleMap(cw, ch, cost, blk, ref.local_islands())
+    pairs = cases.route_pairs(np.where(blk > 0, 255, cost).astype(np.uint8), cw, ch, 9, 12)
+    oks, dids, ffids, flows, loss, has = [], [], [], [], [], []
+    for src, dst in pairs:
+        ref.fc_clear()
+        ok, did = ref.request_path(src, dst)
+        oks.append(ok); dids.append(did)
+        fid = np.zeros(cw * ch, np.uint64); hs = np.zeros(cw * ch, np.uint8)
+        fl = np.zeros((cw * ch, 64, 64), np.uint8); ls = np.zeros((cw * ch, 64, 64), np.uint8)
+        for c in range(cw * ch):
+            f, i = ref.fc_flow(did, (c // cw, c % cw)) if ok else (None, None)
+            l = ref.fc_los(did, (c // cw, c % cw)) if ok else None
+            if f is not None:
+                fl[c] = f; fid[c] = i; hs[c] |= 1
+            if l is not None:
+                ls[c] = l; hs[c] |= 2
+        ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs)
+    _check_route_against(nav, om, cw, ch, pairs, oks, dids, ffids, flows, loss, has)
+    ref.close(); nav.close()
+
+
 # ---------------------------------------------------------------- host logic + ABI surface
 def test_synth_is_deterministic():
     p1 = synth.make_map(2, 2, 0x5EED0002); p2 = synth.make_map(2, 2, 0x5EED0002)
