@@ -573,7 +573,6 @@ struct __align__(16) LosSmem {
     uint64_t blk[64];
     uint8_t  visb[4096];     // `visible`, one byte per tile: the serial loop only ever stores 1 (no read-modify-write)
     uint16_t heap[4104];     // 1-indexed; entry = r << 6 | c (size keeps the struct a multiple of 16 B)
-    uint64_t dbits[64];      // heap slot i holds the current minimum priority d (word 0 is mirrored in a register)
 };
 
 static_assert(sizeof(LosSmem) % 16 == 0, "LosSmem must keep 16-byte alignment per warp");
@@ -645,10 +644,12 @@ __device__ __forceinline__ bool los_is_corner(const LosSmem &s, int r, int c)
 // A unit-cost wavefront only ever holds two adjacent priorities (d and d+1), so priorities are kept
 // modulo 4 and compared through their difference; and a push (always priority d+1, i.e. >= every
 // priority in the heap) never sifts up: it is an append.
-// (Two restructurings of this loop were measured on B200 and rejected: computing the sift path from a
-//  "holds priority d" bit per slot, lane 0 only: 3.7 ms per open 64x64 field; the same with the pop loop
-//  in lockstep on 32 lanes, neighbours on 4 lanes: 3.2 ms; this plain form: 2.2 ms. The loop is bound
-//  by the dependent-instruction chain of one thread)
+// (Restructurings of this loop that were measured on B200 and rejected -- time per open 64x64 field,
+//  this plain form: 2.2-2.5 ms -- : sift path from a "holds priority d" bit per slot, lane 0 only: 3.7 ms;
+//  the same with the pop loop in lockstep on 32 lanes and the neighbours on 4 lanes: 3.2 ms; one state
+//  byte per tile in a padded array + bit-derived sift path: 2.45 ms; that plus a resumable lane-0 loop
+//  handing every wavefront-blocked line to the whole warp (closed-form line positions): 5.4 ms. The loop
+//  is bound by the dependent chain of one thread, not by instruction count or memory.)
 __device__ __forceinline__ bool heap_lt(uint16_t a, uint16_t b) { return (((b >> 12) - (a >> 12)) & 3) == 1; }
 
 // pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200)
@@ -751,7 +752,6 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
             s.open[row] = p & ~blocked & ~gt1;
             s.assigned[row] = 0;
             s.blk[row] = 0;
-            s.dbits[row] = 0;
             uint4 *vz = reinterpret_cast<uint4 *>(s.visb + row * 64);
             vz[0] = make_uint4(0, 0, 0, 0); vz[1] = make_uint4(0, 0, 0, 0); vz[2] = make_uint4(0, 0, 0, 0); vz[3] = make_uint4(0, 0, 0, 0);
         }

@@ -53,6 +53,19 @@ def test_los_golden(nav):
     g = gold("portal_los")
     _upload(nav, 3, 3, g["cost"])
     assert (nav.los_fields_create(g["los_reqs"].view(capi.LOS_REQ)) == g["los_exp"]).all()
+    # chained LOS along real routes (order-sensitive cases) from the route fixture
+    r = gold("route_3x3")
+    for k in range(2):
+        _upload(nav, 3, 3, r[f"cost{k}"])
+        nav.map_build_nav(0); nav.route_build(0)
+        for i, (src, dst) in enumerate(r[f"pairs{k}"]):
+            if not r[f"ok{k}"][i]:
+                continue
+            nav.pool_create(1, 9)
+            nav.pool_request_path(0, tuple(src), tuple(dst))
+            for c in range(9):
+                if r[f"has{k}"][i][c] & 2:
+                    assert (nav.pool_get(0, (c // 3, c % 3))[1] == r[f"los{k}"][i][c]).all()
 
 
 def test_islands_and_portals_golden(nav):

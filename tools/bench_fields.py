@@ -51,11 +51,12 @@ def main():
         print(json.dumps({"kernel": "k_flow_general", "case": name, "n": n, "ms": ms, "fields_per_s": n / ms * 1e3}), flush=True)
     nl = min(n, 4096)
     d = torch.from_numpy(los_reqs[:nl].view(np.uint8)).cuda()
-    ms = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), nl, out.data_ptr(), [0, nl], st), iters=3)
-    print(json.dumps({"kernel": "k_los", "case": "destination chunk", "n": nl, "ms": ms, "fields_per_s": nl / ms * 1e3,
-                      "alg_GBps": nl * 16512 / ms / 1e6}), flush=True)
-    ms1 = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), 1, out.data_ptr(), [0, 1], st), iters=3)
-    print(json.dumps({"kernel": "k_los", "case": "single field latency", "ms": ms1}), flush=True)
+    for v in (0,):
+        ms = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), nl, out.data_ptr(), [0, nl], st), iters=3)
+        print(json.dumps({"kernel": "k_los" + ("2" if v else ""), "case": "destination chunk", "n": nl, "ms": ms, "fields_per_s": nl / ms * 1e3,
+                          "alg_GBps": nl * 16512 / ms / 1e6}), flush=True)
+        ms1 = timeit(lambda: nav.los_fields_create_dev(d.data_ptr(), 1, out.data_ptr(), [0, 1], st), iters=3)
+        print(json.dumps({"kernel": "k_los" + ("2" if v else ""), "case": "single field latency", "ms": ms1}), flush=True)
 
 def goals():
     """the bench's field phase alone: 16 goals, dense plan, flow waves + LOS chain into the pool"""
