@@ -81,6 +81,22 @@ int  pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nlayers,
 int  pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *cost_base,
                             const uint16_t *blockers, const uint16_t *local_islands);
 
+/* Cost pass of N_NewCtxForMapData for one layer ON THE DEVICE (nav.c:2311-2336): n_set_cost_for_tile
+ * (nav.c:267) for every tile type incl. corner tiles (M_Tile_{NW,NE,SW,SE}Height, map/tile.c:117-180)
+ * + n_make_cliff_edges (nav.c:431); blockers of the layer are cleared (nav.c:2332). Bit-exact.
+ *   chunk_tiles[chunk_r*chunk_w + chunk_c] -> 32x32 records of `tile_stride` bytes whose first 16
+ *   bytes are the head of the engine's `struct tile` (map/public/tile.h:101): bool pathable @0,
+ *   enum tiletype @4, int base_height @8, int ramp_height @12. Pass the engine's own
+ *   `const struct tile **chunk_tiles` with tile_stride = sizeof(struct tile) (36).
+ *   ref_layer: the reference's enum nav_layer (0-3 ground, 4-7 water, 8-11 air; nav.h:78-92) whose
+ *   pathability rule applies to `layer`. Follow with pfnav_map_build_nav(layer). */
+int  pfnav_map_cost_from_tiles(pfnav_ctx *ctx, int layer, int ref_layer, const void *const *chunk_tiles,
+                               size_t tile_stride);
+/* Read one layer's DEVICE grids back in the packed chunk-blocked layout of N_CopyCostBasePacked /
+ * N_CopyBlockersPacked (nav.c:2432, 2462). Any out pointer may be NULL. */
+int  pfnav_map_get_layer(pfnav_ctx *ctx, int layer, uint8_t *cost_base, uint16_t *blockers,
+                         uint16_t *local_islands);
+
 /* Sparse update of one chunk (what N_BlockersIncref/Decref + N_Update change, nav.c:4663-4705,
  * 2119): any pointer may be NULL to keep that grid. HOST pointers, [64][64] each. */
 int  pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c,

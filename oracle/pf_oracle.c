@@ -787,3 +787,77 @@ void pfo_velocity_work(const pfo_world *w, const uint32_t *work, size_t nwork, f
         if(out_vpref) { out_vpref[2*wi] = vpref.x; out_vpref[2*wi+1] = vpref.z; }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Tile attributes -> cost_base: n_set_cost_for_tile (nav.c:267-344) + n_make_cliff_edges
+ * (nav.c:431-475) with n_tile_pathable / n_tile_water_pathable / n_height_pathable
+ * (nav.c:215-233, 258-265) and the corner heights of M_Tile_{NW,NE,SW,SE}Height
+ * (map/tile.c:117-180). M_Tile_HeightAtPos (tile.c:249) is only consulted for corner tiles at
+ * the four tile corners, where its ray/plane construction returns 4*corner_height up to float
+ * rounding; the int conversion and the comparison against -1 make that rounding irrelevant
+ * (|error| << 1 around multiples of 4), so the integer corner height is used.
+ * attrs: int32[chunk_h*32][chunk_w*32][4] = {pathable, type, base_height, ramp_height}.
+ * out: [chunks][64][64] chunk-blocked (the reference's layout).
+ * ------------------------------------------------------------------------------------------ */
+enum { TT_FLAT = 0, TT_RAMP_SN, TT_RAMP_NS, TT_RAMP_EW, TT_RAMP_WE, TT_CC_SW, TT_CV_SW, TT_CC_SE, TT_CV_SE,
+       TT_CC_NW, TT_CV_NW, TT_CC_NE, TT_CV_NE };
+
+static int tile_corner_raised(int type, int sub_r, int sub_c)
+{
+    /* bit sets of tile types whose {NW, NE, SW, SE} corner is raised (tile.c:117-180) */
+    static const unsigned raised[2][2] = {
+        { (1u<<TT_RAMP_SN)|(1u<<TT_RAMP_EW)|(1u<<TT_CV_SW)|(1u<<TT_CV_SE)|(1u<<TT_CC_SE)|(1u<<TT_CV_NE),   /* NW */
+          (1u<<TT_RAMP_SN)|(1u<<TT_RAMP_WE)|(1u<<TT_CV_SW)|(1u<<TT_CC_SW)|(1u<<TT_CV_SE)|(1u<<TT_CV_NW) }, /* NE */
+        { (1u<<TT_RAMP_NS)|(1u<<TT_RAMP_EW)|(1u<<TT_CV_SE)|(1u<<TT_CV_NW)|(1u<<TT_CC_NE)|(1u<<TT_CV_NE),   /* SW */
+          (1u<<TT_RAMP_NS)|(1u<<TT_RAMP_WE)|(1u<<TT_CV_SW)|(1u<<TT_CV_NE)|(1u<<TT_CC_NW)|(1u<<TT_CV_NW) }, /* SE */
+    };
+    return (raised[sub_r][sub_c] >> type) & 1u;
+}
+
+static int tile_path_bit(int type, int sub_r, int sub_c)
+{
+    /* the 2x2 "tile_path_map" of n_set_cost_for_tile (nav.c:276-322) */
+    switch(type) {
+    case TT_CC_SW: case TT_CV_NE: return sub_r == 1 && sub_c == 0;   /* bl */
+    case TT_CC_SE: case TT_CV_NW: return sub_r == 1 && sub_c == 1;   /* br */
+    case TT_CC_NW: case TT_CV_SE: return sub_r == 0 && sub_c == 0;   /* tl */
+    case TT_CC_NE: case TT_CV_SW: return sub_r == 0 && sub_c == 1;   /* tr */
+    default: return 0;
+    }
+}
+
+void pfo_cost_from_tiles(int chunk_w, int chunk_h, const int32_t *attrs, int ref_layer, uint8_t *out)
+{
+    const int H = chunk_h * 32, W = chunk_w * 32;
+    const int group = ref_layer / 4;     /* 0 ground, 1 water, 2 air (nav.h enum nav_layer) */
+    for(int r = 0; r < H; r++)
+    for(int c = 0; c < W; c++) {
+        const int32_t *t = attrs + ((size_t)r * W + c) * 4;
+        const int path = t[0] != 0, type = t[1], base = t[2], ramp = t[3];
+        int pathable;
+        if(group == 0)      pathable = path && base >= -1 && !(type != TT_FLAT && ramp > 1);
+        else if(group == 1) pathable = path && !(base + ramp > -1);
+        else                pathable = 1;
+        for(int sr = 0; sr < 2; sr++)
+        for(int sc = 0; sc < 2; sc++) {
+            const int h = (tile_corner_raised(type, sr, sc) ? base + ramp : base) * 4;
+            const int hp = group == 1 ? (h <= -1) : group == 2 ? 1 : (h >= -1);
+            uint8_t v = pathable ? 1 : (tile_path_bit(type, sr, sc) && hp) ? 1 : 0xFF;
+            /* cliff edges: both tiles FLAT with different base heights. Note n_set_cost_edge blocks
+             * the half of the tile where its map is ZERO (nav.c:415), i.e. EDGE_BOT blocks the top
+             * sub-row and EDGE_RIGHT the left sub-column. */
+            if(type == TT_FLAT) {
+                #define CLIFF(rr, cc) ((rr) >= 0 && (rr) < H && (cc) >= 0 && (cc) < W \
+                    && attrs[((size_t)(rr) * W + (cc)) * 4 + 1] == TT_FLAT \
+                    && attrs[((size_t)(rr) * W + (cc)) * 4 + 2] != base)
+                if(CLIFF(r + 1, c) && sr == 0) v = 0xFF;
+                if(CLIFF(r - 1, c) && sr == 1) v = 0xFF;
+                if(CLIFF(r, c - 1) && sc == 1) v = 0xFF;
+                if(CLIFF(r, c + 1) && sc == 0) v = 0xFF;
+                #undef CLIFF
+            }
+            const int nr = 2 * r + sr, nc = 2 * c + sc;
+            out[((size_t)(nr / 64) * chunk_w + nc / 64) * 4096 + (nr % 64) * 64 + nc % 64] = v;
+        }
+    }
+}

@@ -69,4 +69,8 @@ void pfo_velocity_work(const pfo_world *w, const uint32_t *work, size_t nwork, f
 void pfo_desired_velocity(const pfo_map *map, const pfo_agent *agents, const pfo_flock *flocks,
                           const uint32_t *work, size_t nwork, const int32_t *slot,
                           const uint8_t *flow, const uint8_t *los, float *out_vdes, uint8_t *out_los);
+/* n_set_cost_for_tile + n_make_cliff_edges (nav.c:267, 431): attrs int32[chunk_h*32][chunk_w*32][4]
+ * = {pathable, type, base_height, ramp_height}; ref_layer = the reference's enum nav_layer (0..11);
+ * out = cost_base [chunks][64][64] */
+void pfo_cost_from_tiles(int chunk_w, int chunk_h, const int32_t *attrs, int ref_layer, uint8_t *out);
 #endif

@@ -35,12 +35,22 @@ def lib():
         L.pfo_velocity_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.pfo_desired_velocity.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfo_cost_from_tiles.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def cost_from_tiles(chunk_w, chunk_h, tiles, ref_layer):
+    """tiles: int32[H32][W32][4] -> cost_base u8[chunks][64][64] (nav.c:267, 431)."""
+    tiles = np.ascontiguousarray(tiles, np.int32)
+    assert tiles.shape == (chunk_h * 32, chunk_w * 32, 4)
+    out = np.zeros((chunk_w * chunk_h, 64, 64), np.uint8)
+    lib().pfo_cost_from_tiles(chunk_w, chunk_h, _p(tiles), ref_layer, _p(out))
+    return out
 
 
 class OracleMap:

@@ -22,6 +22,8 @@ def lib():
         L = _lib
         L.pfref_map_new.restype = C.c_void_p
         L.pfref_map_new.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float]
+        L.pfref_map_new_tiles.restype = C.c_void_p
+        L.pfref_map_new_tiles.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float]
         L.pfref_map_free.argtypes = [C.c_void_p]
         L.pfref_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_get_portals.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -60,12 +62,19 @@ def _p(a):
 class RefMap:
     """One reference nav context (N_NewCtxForMapData) over a synthetic pathable-tile grid."""
 
-    def __init__(self, chunk_w, chunk_h, pathable, map_x=0.0, map_z=0.0):
-        pathable = np.ascontiguousarray(pathable, dtype=np.uint8)
-        assert pathable.shape == (chunk_h * 32, chunk_w * 32)
+    def __init__(self, chunk_w, chunk_h, pathable=None, map_x=0.0, map_z=0.0, tiles=None):
+        """pathable: u8[H32][W32] (all tiles FLAT, height 0)  -- or --
+        tiles: int32[H32][W32][4] = {pathable, type, base_height, ramp_height}."""
         self.cw, self.ch = chunk_w, chunk_h
         self.map_x, self.map_z = float(map_x), float(map_z)
-        self.h = lib().pfref_map_new(chunk_w, chunk_h, _p(pathable), map_x, map_z)
+        if tiles is not None:
+            tiles = np.ascontiguousarray(tiles, dtype=np.int32)
+            assert tiles.shape == (chunk_h * 32, chunk_w * 32, 4)
+            self.h = lib().pfref_map_new_tiles(chunk_w, chunk_h, _p(tiles), map_x, map_z)
+        else:
+            pathable = np.ascontiguousarray(pathable, dtype=np.uint8)
+            assert pathable.shape == (chunk_h * 32, chunk_w * 32)
+            self.h = lib().pfref_map_new(chunk_w, chunk_h, _p(pathable), map_x, map_z)
         if not self.h:
             raise RuntimeError("pfref_map_new failed")
 

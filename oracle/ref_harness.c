@@ -228,6 +228,44 @@ PFREF_EXPORT void *pfref_map_new(int chunk_w, int chunk_h, const uint8_t *pathab
     return map;
 }
 
+/* Same, but from explicit tile attributes: tiles = int32[chunk_h*32][chunk_w*32][4] =
+ * {pathable, type, base_height, ramp_height} in global row-major order. Exercises
+ * n_set_cost_for_tile / n_make_cliff_edges (nav.c:267, 431) for every tile type. */
+PFREF_EXPORT void *pfref_map_new_tiles(int chunk_w, int chunk_h, const int32_t *attrs,
+                                       float map_x, float map_z)
+{
+    pfref_init();
+    struct map *map = calloc(1, sizeof(struct map));
+    map->width = chunk_w;
+    map->height = chunk_h;
+    map->pos = (vec3_t){map_x, 0.0f, map_z};
+    map->chunk_tiles = calloc(chunk_w * chunk_h, sizeof(struct tile*));
+
+    const int TW = TILES_PER_CHUNK_WIDTH, TH = TILES_PER_CHUNK_HEIGHT;
+    for(int cr = 0; cr < chunk_h; cr++) {
+    for(int cc = 0; cc < chunk_w; cc++) {
+        struct tile *tiles = calloc(TW * TH, sizeof(struct tile));
+        for(int r = 0; r < TH; r++) {
+        for(int c = 0; c < TW; c++) {
+            size_t gr = cr * TH + r, gc = cc * TW + c;
+            const int32_t *a = attrs + (gr * (chunk_w * TW) + gc) * 4;
+            struct tile *t = &tiles[r * TW + c];
+            t->pathable = a[0] != 0;
+            t->type = (enum tiletype)a[1];
+            t->base_height = a[2];
+            t->ramp_height = a[3];
+        }}
+        map->chunk_tiles[cr * chunk_w + cc] = tiles;
+    }}
+    map->nav_private = N_NewCtxForMapData(chunk_w, chunk_h, TW, TH,
+        (const struct tile**)map->chunk_tiles, true);
+    if(!map->nav_private) {
+        free(map);
+        return NULL;
+    }
+    return map;
+}
+
 PFREF_EXPORT void pfref_map_free(void *m)
 {
     struct map *map = m;

@@ -53,7 +53,7 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer",
 ]
 
 _lib = None
@@ -81,6 +81,8 @@ def load():
     L.pfnav_map_upload_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_build_nav.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_map_cost_from_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.pfnav_map_get_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_refresh_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.pfnav_local_islands_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_portals_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -211,6 +213,27 @@ class Nav:
         b = None if blockers is None else np.ascontiguousarray(blockers, np.uint16)
         c = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
         _chk(self.L.pfnav_map_update_chunk(self.h, layer, chunk[0], chunk[1], _p(a), _p(b), _p(c)))
+
+    def map_cost_from_tiles(self, layer, ref_layer, tiles):
+        """tiles: int32[H32][W32][4] = {pathable, type, base_height, ramp_height} (global row-major).
+        Re-blocked here into per-chunk 16-byte records shaped like the head of the engine's
+        `struct tile`, then passed as the engine would pass `chunk_tiles` (nav.c:2284)."""
+        tiles = np.ascontiguousarray(tiles, np.int32)
+        assert tiles.shape == (self.ch * 32, self.cw * 32, 4)
+        rec = tiles.reshape(self.ch, 32, self.cw, 32, 4).transpose(0, 2, 1, 3, 4).copy()   # [cr][cc][32][32][4]
+        rec[..., 0] = rec[..., 0] != 0         # `bool pathable` occupies byte 0 of the first word
+        ptrs = (C.c_void_p * (self.cw * self.ch))()
+        for i in range(self.cw * self.ch):
+            ptrs[i] = rec[i // self.cw, i % self.cw].ctypes.data
+        _chk(self.L.pfnav_map_cost_from_tiles(self.h, layer, ref_layer, ptrs, 16))
+
+    def map_get_layer(self, layer=0):
+        n = self.cw * self.ch
+        cost = np.zeros((n, 64, 64), np.uint8)
+        blk = np.zeros((n, 64, 64), np.uint16)
+        liid = np.zeros((n, 64, 64), np.uint16)
+        _chk(self.L.pfnav_map_get_layer(self.h, layer, _p(cost), _p(blk), _p(liid)))
+        return cost, blk, liid
 
     def map_build_nav(self, layer=0):
         _chk(self.L.pfnav_map_build_nav(self.h, layer))

@@ -156,6 +156,72 @@ __global__ void k_deblock(const T *__restrict__ src, T *__restrict__ dst, int ch
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tile attributes -> cost_base image (n_set_cost_for_tile nav.c:267-344 + n_make_cliff_edges
+// nav.c:431-475). One thread per MAP tile (= 2x2 nav tiles); tiles are packed char4
+// {pathable, type, base_height, ramp_height} in a global row-major [H32][W32] image.
+// M_Tile_HeightAtPos (map/tile.c:249) is only consulted at the four corners of corner tiles,
+// where it returns 4*corner_height up to float rounding that the int conversion + compare
+// against -1 erase, so the integer corner height (tile.c:117-180) is used directly.
+__device__ __forceinline__ bool tile_corner_raised(int type, int sr, int sc)
+{
+    // bit i set = tile type i raises this corner (tile.c:117-180); order NW, NE, SW, SE
+    const unsigned raised[4] = {
+        (1u<<1)|(1u<<3)|(1u<<6)|(1u<<8)|(1u<<7)|(1u<<12),
+        (1u<<1)|(1u<<4)|(1u<<6)|(1u<<5)|(1u<<8)|(1u<<10),
+        (1u<<2)|(1u<<3)|(1u<<8)|(1u<<10)|(1u<<11)|(1u<<12),
+        (1u<<2)|(1u<<4)|(1u<<6)|(1u<<12)|(1u<<9)|(1u<<10)};
+    const int k = sr * 2 + sc;
+    const unsigned m = k == 0 ? raised[0] : k == 1 ? raised[1] : k == 2 ? raised[2] : raised[3];
+    return (m >> type) & 1u;
+}
+
+__device__ __forceinline__ bool tile_path_bit(int type, int sr, int sc)
+{
+    // "tile_path_map" of n_set_cost_for_tile (nav.c:276-322): the one passable quarter of a corner tile
+    const unsigned bl = (1u<<5)|(1u<<12), br = (1u<<7)|(1u<<10), tl = (1u<<9)|(1u<<8), tr = (1u<<11)|(1u<<6);
+    const unsigned m = sr ? (sc ? br : bl) : (sc ? tr : tl);
+    return (m >> type) & 1u;
+}
+
+__global__ void k_cost_from_tiles(const char4 *__restrict__ tiles, uint8_t *__restrict__ cost, int W32, int H32,
+                                  int group)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= W32 || r >= H32) return;
+    const char4 t = tiles[(size_t)r * W32 + c];
+    const int path = t.x != 0, type = t.y, base = t.z, ramp = t.w;
+    bool pathable;
+    if (group == 0)      pathable = path && base >= -1 && !(type != 0 && ramp > 1);   // n_tile_pathable nav.c:215
+    else if (group == 1) pathable = path && !(base + ramp > -1);                       // n_tile_water_pathable :226
+    else                 pathable = true;
+    // cliff edges between FLAT tiles of different base height (nav.c:420-475); n_set_cost_edge blocks the
+    // half where its map is ZERO (nav.c:415): EDGE_BOT -> top sub-row, EDGE_TOP -> bottom sub-row,
+    // EDGE_LEFT -> right sub-column, EDGE_RIGHT -> left sub-column.
+    bool cb = false, ct = false, cl = false, crt = false;
+    if (type == 0) {
+        if (r + 1 < H32) { char4 o = tiles[(size_t)(r + 1) * W32 + c]; cb = o.y == 0 && o.z != base; }
+        if (r > 0)       { char4 o = tiles[(size_t)(r - 1) * W32 + c]; ct = o.y == 0 && o.z != base; }
+        if (c > 0)       { char4 o = tiles[(size_t)r * W32 + c - 1];   cl = o.y == 0 && o.z != base; }
+        if (c + 1 < W32) { char4 o = tiles[(size_t)r * W32 + c + 1];   crt = o.y == 0 && o.z != base; }
+    }
+    const int W64 = W32 * 2;
+#pragma unroll
+    for (int sr = 0; sr < 2; sr++) {
+        uint8_t v[2];
+#pragma unroll
+        for (int sc = 0; sc < 2; sc++) {
+            const int h = (tile_corner_raised(type, sr, sc) ? base + ramp : base) * 4;   // Y_COORDS_PER_TILE
+            const bool hp = group == 1 ? (h <= -1) : group == 2 ? true : (h >= -1);      // n_height_pathable :258
+            uint8_t x = pathable ? 1 : (tile_path_bit(type, sr, sc) && hp) ? 1 : 0xFF;
+            if ((cb && sr == 0) || (ct && sr == 1) || (cl && sc == 1) || (crt && sc == 0)) x = 0xFF;
+            v[sc] = x;
+        }
+        *(uint16_t *)(cost + (size_t)(2 * r + sr) * W64 + 2 * c) = (uint16_t)(v[0] | (v[1] << 8));
+    }
+}
+
 // per-chunk flag: 1 if every passable tile has cost 1. One warp per chunk.
 __global__ void k_unit_flags(const uint8_t *__restrict__ cost, uint8_t *__restrict__ unit, int chunk_w, int chunk_h)
 {
@@ -1123,6 +1189,90 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     }
     PF_CUDA(cudaGetLastError());
     return refresh_unit_flags(ctx, layer);
+}
+
+// N_NewCtxForMapData's cost pass for one layer (nav.c:2311-2336), on the device.
+extern "C" int pfnav_map_cost_from_tiles(pfnav_ctx *ctx, int layer, int ref_layer, const void *const *chunk_tiles,
+                                         size_t tile_stride)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(ref_layer >= 0 && ref_layer < PFNAV_NAV_LAYER_MAX, "ref_layer");
+    PF_ARG(chunk_tiles && tile_stride >= 16, "chunk_tiles / tile_stride");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const int W32 = ctx->chunk_w * 32, H32 = ctx->chunk_h * 32;
+    const size_t ntiles = (size_t)W32 * H32, ltiles = (size_t)ctx->W64 * ctx->H64;
+    // pack the head of the engine's `struct tile` (tile.h:101: bool pathable @0, enum type @4,
+    // int base_height @8, int ramp_height @12) into 4-byte records, de-blocking the chunks
+    std::vector<char4> packed(ntiles);
+    for (int cr = 0; cr < ctx->chunk_h; cr++)
+        for (int cc = 0; cc < ctx->chunk_w; cc++) {
+            const uint8_t *base = (const uint8_t *)chunk_tiles[cr * ctx->chunk_w + cc];
+            PF_ARG(base, "chunk_tiles[i] is NULL");
+            for (int t = 0; t < 1024; t++) {
+                const uint8_t *rec = base + (size_t)t * tile_stride;
+                int32_t type, bh, rh;
+                memcpy(&type, rec + 4, 4); memcpy(&bh, rec + 8, 4); memcpy(&rh, rec + 12, 4);
+                PF_ARG(type >= 0 && type <= 12, "tile type outside enum tiletype (tile.h:58-73)");
+                PF_ARG(bh >= -128 && bh <= 127 && rh >= -128 && rh <= 127, "tile height outside int8 range");
+                packed[(size_t)(cr * 32 + (t >> 5)) * W32 + cc * 32 + (t & 31)] =
+                    make_char4((char)(rec[0] != 0), (char)type, (char)bh, (char)rh);
+            }
+        }
+    int rc = ensure_stage(ctx, std::max(ntiles * 4, ltiles * 2));
+    if (rc) return rc;
+    ctx->map_epoch++;
+    PF_CUDA(cudaMemcpy(ctx->d_stage, packed.data(), ntiles * 4, cudaMemcpyHostToDevice));
+    dim3 blk(32, 8), grd((W32 + 31) / 32, (H32 + 7) / 8);
+    k_cost_from_tiles<<<grd, blk>>>((const char4 *)ctx->d_stage, ctx->d_cost + ltiles * layer, W32, H32, ref_layer / 4);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaMemset(ctx->d_blk + ltiles * layer, 0, ltiles * 2));       // nav.c:2332
+    std::fill(ctx->h_blk.begin() + ltiles * layer, ctx->h_blk.begin() + ltiles * (layer + 1), 0);
+    // host mirror (chunk-blocked) for the route planner
+    std::vector<uint8_t> img(ltiles);
+    PF_CUDA(cudaMemcpy(img.data(), ctx->d_cost + ltiles * layer, ltiles, cudaMemcpyDeviceToHost));
+    uint8_t *hc = ctx->h_cost.data() + ltiles * layer;
+    for (int cr = 0; cr < ctx->chunk_h; cr++)
+        for (int cc = 0; cc < ctx->chunk_w; cc++)
+            for (int r = 0; r < 64; r++)
+                memcpy(hc + ((size_t)cr * ctx->chunk_w + cc) * 4096 + r * 64,
+                       img.data() + (size_t)(cr * 64 + r) * ctx->W64 + cc * 64, 64);
+    return refresh_unit_flags(ctx, layer);
+}
+
+// Packed read-back of one layer's DEVICE grids (N_CopyCostBasePacked / N_CopyBlockersPacked layout,
+// nav.c:2432, 2462). Any pointer may be NULL.
+extern "C" int pfnav_map_get_layer(pfnav_ctx *ctx, int layer, uint8_t *cost_base, uint16_t *blockers,
+                                   uint16_t *local_islands)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    std::vector<uint16_t> img(ltiles);
+    auto reblock = [&](auto *dst, const auto *src) {
+        for (int cr = 0; cr < ctx->chunk_h; cr++)
+            for (int cc = 0; cc < ctx->chunk_w; cc++)
+                for (int r = 0; r < 64; r++)
+                    memcpy(dst + ((size_t)cr * ctx->chunk_w + cc) * 4096 + r * 64,
+                           src + (size_t)(cr * 64 + r) * ctx->W64 + cc * 64, 64 * sizeof(*dst));
+    };
+    if (cost_base) {
+        PF_CUDA(cudaMemcpy(img.data(), ctx->d_cost + ltiles * layer, ltiles, cudaMemcpyDeviceToHost));
+        reblock(cost_base, (const uint8_t *)img.data());
+    }
+    if (blockers) {
+        PF_CUDA(cudaMemcpy(img.data(), ctx->d_blk + ltiles * layer, ltiles * 2, cudaMemcpyDeviceToHost));
+        reblock(blockers, (const uint16_t *)img.data());
+    }
+    if (local_islands) {
+        PF_CUDA(cudaMemcpy(img.data(), ctx->d_liid + ltiles * layer, ltiles * 2, cudaMemcpyDeviceToHost));
+        reblock(local_islands, (const uint16_t *)img.data());
+    }
+    return PFNAV_OK;
 }
 
 extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c, const uint8_t *cost_base,

@@ -151,3 +151,30 @@ def execute_route(flow_exec, los_exec, fr, fc, lr, lc):
         fields[int(fc[k])] = out[0]
     los = los_exec(lr) if len(lr) else np.zeros((0, 64, 64), np.uint8)
     return fields, {int(lc[k]): los[k] for k in range(len(lr))}
+
+
+def tile_attr_case(cw, ch, seed, terrain=False):
+    """int32[H32][W32][4] = {pathable, type, base_height, ramp_height} (struct tile, tile.h:101).
+    terrain=False: every tile type / height combination at random (stress for n_set_cost_for_tile and
+    the cliff rule); terrain=True: plateaus of different heights joined by ramps and corner tiles,
+    mostly pathable, so that portals / islands downstream are non-trivial."""
+    rng = np.random.default_rng(seed)
+    H, W = ch * 32, cw * 32
+    t = np.zeros((H, W, 4), np.int32)
+    if not terrain:
+        t[..., 0] = rng.random((H, W)) < 0.9
+        t[..., 1] = np.where(rng.random((H, W)) < 0.6, 0, rng.integers(0, 13, (H, W)))
+        t[..., 2] = rng.integers(-3, 4, (H, W))
+        t[..., 3] = rng.integers(0, 4, (H, W))
+        return t
+    t[..., 0] = 1
+    for _ in range(3 * cw * ch):                       # plateaus (cliffs all around) and lakes
+        h, w = rng.integers(4, 14, 2)
+        r, c = rng.integers(0, H - h), rng.integers(0, W - w)
+        t[r:r + h, c:c + w, 2] = rng.integers(-2, 3)
+    for _ in range(6 * cw * ch):                       # ramps / corner tiles sprinkled on the borders
+        r, c = rng.integers(0, H), rng.integers(0, W)
+        t[r, c, 1] = rng.integers(1, 13)
+        t[r, c, 3] = rng.integers(1, 3)
+    t[..., 0] &= (rng.random((H, W)) > 0.03).astype(np.int32)
+    return t

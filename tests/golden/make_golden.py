@@ -137,7 +137,25 @@ def gen_route():
     np.savez_compressed(os.path.join(HERE, "route_3x3.npz"), **out)
 
 
+def gen_tiles():
+    """N_NewCtxForMapData from explicit tile attributes (nav.c:2284): cost_base of a ground, water
+    and air layer, then the structures derived from it on the ground layer."""
+    out = {}
+    for k, (cw, ch, seed, terrain) in enumerate(((2, 2, 41, False), (3, 2, 42, True))):
+        t = cases.tile_attr_case(cw, ch, seed, terrain)
+        ref = pfref.RefMap(cw, ch, tiles=t)
+        out[f"tiles{k}"] = t.astype(np.int8)
+        for layer in (0, 3, 4, 8):
+            out[f"cost{k}_{layer}"] = ref.cost_base(layer)
+        out[f"liid{k}"] = ref.local_islands(0)
+        out[f"portals{k}"] = ref.portals(0)
+        out[f"islands{k}"] = ref.islands(0)
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "tiles.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_tiles()
     gen_route()
     gen_flow_tile()
     gen_portal_los()

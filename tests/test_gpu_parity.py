@@ -456,3 +456,23 @@ def test_full_size_agents_properties(nav):
     assert len(np.unique(ids)) == len(ids) and i in ids
     d = np.linalg.norm(a["pos"][ids] - a["pos"][i], axis=1)
     assert (d <= 30.0 + 1e-2).all()
+
+
+def test_cost_from_tiles_golden(nav, pforacle):
+    """a-11: n_set_cost_for_tile + n_make_cliff_edges on the device, every tile type; then the
+    structural build (local islands, portals) on top of the device-made costs."""
+    g = gold("tiles")
+    for k, (cw, ch) in enumerate(((2, 2), (3, 2))):
+        t = g[f"tiles{k}"].astype(np.int32)
+        nav.map_create(cw, ch, 4)
+        for slot, layer in enumerate((0, 3, 4, 8)):
+            nav.map_cost_from_tiles(slot, layer, t)
+            cost, blk, _ = nav.map_get_layer(slot)
+            assert (cost == g[f"cost{k}_{layer}"]).all(), (k, layer)
+            assert (cost == pforacle.cost_from_tiles(cw, ch, t, layer)).all()
+            assert not blk.any()
+        nav.map_build_nav(0)
+        assert (nav.local_islands(0) == g[f"liid{k}"]).all()
+        ports = nav.portals(0)
+        assert len(ports) == len(g[f"portals{k}"])
+        assert (ports[:, :9] == g[f"portals{k}"][:, :9]).all()

@@ -47,6 +47,26 @@ def test_port_los_golden(pforacle):
     assert (got == g["los_exp"]).all()
 
 
+TILE_CASES = ((2, 2), (3, 2))
+
+
+def test_port_cost_from_tiles_golden(pforacle):
+    g = gold("tiles")
+    for k, (cw, ch) in enumerate(TILE_CASES):
+        t = g[f"tiles{k}"].astype(np.int32)
+        for layer in (0, 3, 4, 8):
+            assert (pforacle.cost_from_tiles(cw, ch, t, layer) == g[f"cost{k}_{layer}"]).all(), (k, layer)
+
+
+def test_port_cost_from_tiles_vs_ref(pfref, pforacle):
+    for seed, terrain in ((51, False), (52, True), (53, False)):
+        t = cases.tile_attr_case(2, 3, seed, terrain)
+        ref = pfref.RefMap(2, 3, tiles=t)
+        for layer in range(12):
+            assert (pforacle.cost_from_tiles(2, 3, t, layer) == ref.cost_base(layer)).all(), (seed, layer)
+        ref.close()
+
+
 def test_local_islands_restatement_golden():
     g = gold("portal_los")
     assert (cases.local_islands_np(g["cost"]) == g["liid"]).all()
