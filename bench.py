@@ -179,8 +179,11 @@ def run_ours(args):
 
     nav.agents_upload(rec_np, W["flocks"], HZ)
     nav.agents_set_work(work)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream carries the whole step: torch ops, NCCL and the library calls
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
     d_rec_ptr, _, _ = nav.agents_device_ptrs()
     rec_view = torch.as_tensor(CudaArrayView(d_rec_ptr, n_total * 24), device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
@@ -262,7 +265,7 @@ def run_ours(args):
             ms.append(a_.elapsed_time(b_))
         return float(np.median(ms))
     nav.profile_enable(True)
-    phase_time(fields_phase); prof_f = nav.profile_read()
+    phase_time(lambda: (fields_phase(), nav.fields_join(sp))); prof_f = nav.profile_read()
     phase_time(lambda: nav.agents_rebuild_index(sp)); prof_i = nav.profile_read()
     phase_time(lambda: nav.agents_tick(capi.TICK_VDES_FROM_POOL, sp)); prof_t = nav.profile_read()
     nav.profile_enable(False)

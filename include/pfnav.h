@@ -67,6 +67,9 @@ const char *pfnav_last_error(void);
 int  pfnav_version(void);
 
 /* device: CUDA ordinal. Fails (PFNAV_ERR_NO_DEVICE) without a usable GPU. */
+/* Streams: every `void *stream` argument is a cudaStream_t. NULL names the context's own
+ * non-blocking stream -- NOT the legacy default stream (work queued there would not be ordered
+ * against the context's stream). Calls on one stream are ordered as issued. */
 int  pfnav_create(int device, pfnav_ctx **out);
 void pfnav_destroy(pfnav_ctx *ctx);
 
@@ -257,6 +260,11 @@ int  pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_
  * dests[ngoals]; targets: 4 ints per goal {chunk_r, chunk_c, tile_r, tile_c}. */
 int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
                               const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los);
+/* pfnav_pool_request_goals runs the LOS dependency chains on a context-owned stream so that work which
+ * does not read fields (position index, cohesion) overlaps them; pfnav_agents_tick and the pool entry
+ * points order themselves after it. A caller that reads pool LOS fields through raw device pointers
+ * on its own stream calls this first. */
+int  pfnav_fields_join(pfnav_ctx *ctx, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls

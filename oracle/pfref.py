@@ -49,6 +49,9 @@ def lib():
         L.pfref_velocity_work_mt.restype = C.c_double
         L.pfref_velocity_work_mt.argtypes = [C.c_int]
         L.pfref_work_get.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_movestate_set.argtypes = [C.c_int] + [C.c_void_p] * 9
+        L.pfref_compute_updates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfref_apply_velocity_patch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_vpref.argtypes = [C.c_int, C.c_void_p]
         L.pfref_fields_mt.restype = C.c_double
         L.pfref_fields_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -196,6 +199,32 @@ class RefMap:
         out = np.zeros((self._nwork, 2), dtype=np.float32)
         lib().pfref_work_get(self._nwork, _p(out))
         return out, secs
+
+    def movestate_set(self, next_pos, next_rot, step, left, vel_hist, vel_hist_idx, wait_prev, wait_ticks,
+                      combat_facing):
+        """interpolation / orientation / wait fields of struct movestate (movement.c:150-215), by uid"""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        k = [f32(next_pos), f32(next_rot), f32(step), i32(left), f32(vel_hist), i32(vel_hist_idx), i32(wait_prev),
+             i32(wait_ticks), f32(combat_facing)]
+        lib().pfref_movestate_set(len(k[2]), *[_p(a) for a in k])
+
+    def compute_updates(self, new_vel):
+        """entity_compute_update (movement.c:2303) per work item -> (ints[n,4], floats[n,28]);
+        layout in oracle/ref_harness.c:pfref_compute_updates"""
+        new_vel = np.ascontiguousarray(new_vel, dtype=np.float32)
+        oi = np.zeros((self._nwork, 4), np.int32)
+        of = np.zeros((self._nwork, 28), np.float32)
+        lib().pfref_compute_updates(self._nwork, _p(new_vel), _p(oi), _p(of))
+        return oi, of
+
+    def apply_velocity_patch(self, next_velocity, flags):
+        nv = np.ascontiguousarray(next_velocity, dtype=np.float32)
+        fl = np.ascontiguousarray(flags, dtype=np.int32)
+        hist = np.zeros((self._nwork, 14, 2), np.float32)
+        idx = np.zeros(self._nwork, np.int32)
+        lib().pfref_apply_velocity_patch(self._nwork, _p(nv), _p(fl), _p(hist), _p(idx))
+        return hist, idx
 
     def vpref(self):
         out = np.zeros((self._nwork, 2), dtype=np.float32)

@@ -102,6 +102,29 @@ bool M_NavPositionBlocked(const struct map *map, enum nav_layer layer, vec2_t xz
     return N_PositionBlocked(xz_pos, layer, map->nav_private, map->pos);
 }
 
+bool M_NavClosestPathable(const struct map *map, enum nav_layer layer, vec2_t xz_src, vec2_t *out)
+{
+    /* map.c:868 */
+    return N_ClosestPathable(map->nav_private, layer, map->pos, xz_src, out);
+}
+
+bool M_NavIsMaximallyClose(const struct map *map, enum nav_layer layer, vec2_t xz_pos,
+                           vec2_t xz_dest, float tolerance)
+{
+    /* map.c:1033 */
+    return N_IsMaximallyClose(map->nav_private, layer, map->pos, xz_pos, xz_dest, tolerance);
+}
+
+bool M_NavIsAdjacentToImpassable(const struct map *map, enum nav_layer layer, vec2_t xz_pos)
+{
+    /* map.c:1039 */
+    return N_IsAdjacentToImpassable(map->nav_private, layer, map->pos, xz_pos);
+}
+
+/* Terrain render height (map.c M_HeightAtPoint): not on the navigation path -- every oracle map
+ * is evaluated with y = 0 (entity y is only consumed by the renderer). */
+float M_HeightAtPoint(const struct map *map, vec2_t xz) { (void)map; (void)xz; return 0.0f; }
+
 vec2_t M_NavDesiredPointSeekVelocity(const struct map *map, dest_id_t id, vec2_t curr_pos, vec2_t xz_dest)
 {
     return N_DesiredPointSeekVelocity(id, curr_pos, xz_dest, map->nav_private, map->pos);
@@ -652,6 +675,7 @@ PFREF_EXPORT void pfref_work_set(int nwork, const uint32_t *uids, const float *v
         in->ent_des_v = (vec2_t){vdes[2*i], vdes[2*i+1]};
         in->speed = speed[i];
         in->has_dest_los = has_los[i];
+        in->fstate.fid = NULL_FID;
         in->cp_ent = (struct cp_ent){
             .xz_pos = (vec2_t){ms->prev_pos.x, ms->prev_pos.z},
             .xz_vel = ms->velocity,
@@ -661,6 +685,93 @@ PFREF_EXPORT void pfref_work_set(int nwork, const uint32_t *uids, const float *v
         in->stat_neighbs = malloc(sizeof(vec_cp_ent_t));
         vec_cp_ent_init(in->dyn_neighbs);  vec_cp_ent_resize(in->dyn_neighbs, MAX_NEIGHBOURS);
         vec_cp_ent_init(in->stat_neighbs); vec_cp_ent_resize(in->stat_neighbs, MAX_NEIGHBOURS);
+    }
+}
+
+/* Interpolation / orientation / wait part of `struct movestate` (movement.c:150-215) for the
+ * state-update pass. Arrays are indexed by uid; quaternions are {x, y, z, w}. */
+PFREF_EXPORT void pfref_movestate_set(int n, const float *next_pos_xz, const float *next_rot,
+                                      const float *step, const int32_t *left,
+                                      const float *vel_hist, const int32_t *vel_hist_idx,
+                                      const int32_t *wait_prev, const int32_t *wait_ticks,
+                                      const float *combat_facing)
+{
+    for(int i = 0; i < n; i++) {
+        struct movestate *ms = movestate_get(i);
+        ms->next_pos = (vec3_t){next_pos_xz[2*i], 0.0f, next_pos_xz[2*i+1]};
+        ms->next_rot = (quat_t){next_rot[4*i], next_rot[4*i+1], next_rot[4*i+2], next_rot[4*i+3]};
+        ms->prev_rot = ms->next_rot;
+        ms->step = step[i];
+        ms->left = left[i];
+        for(int k = 0; k < VEL_HIST_LEN; k++)
+            ms->vel_hist[k] = (vec2_t){vel_hist[(i*VEL_HIST_LEN + k)*2], vel_hist[(i*VEL_HIST_LEN + k)*2 + 1]};
+        ms->vel_hist_idx = vel_hist_idx[i];
+        ms->wait_prev = wait_prev[i];
+        ms->wait_ticks_left = wait_ticks[i];
+        ms->combat_facing = (quat_t){combat_facing[4*i], combat_facing[4*i+1], combat_facing[4*i+2], combat_facing[4*i+3]};
+        ms->surround_target_uid = NULL_UID;
+    }
+}
+
+/* entity_compute_update (movement.c:2303) for every work item, the way move_update_work
+ * (movement.c:3468) calls it: new velocity + desired velocity in, `struct movestate_patch` out.
+ * Per item: out_i[4] = {flags, next_state, next_block, wait_ticks_left after the call};
+ * out_f[28] = next_velocity[2] next_pos[3] next_rot[4] next_ppos[3] next_npos[3] next_step
+ *             next_left next_nrot[4] next_prot[4] (3 pad). Fields the patch flags do not select are
+ * zeroed so that the comparison is deterministic. */
+PFREF_EXPORT void pfref_compute_updates(int nwork, const float *new_vel, int32_t *out_i, float *out_f)
+{
+    for(int i = 0; i < nwork; i++) {
+        const struct move_work_in *in = &s_move_work.in[i];
+        struct movestate_patch p;
+        memset(&p, 0, sizeof(p));
+        entity_compute_update(s_move_work.hz, in->ent_uid, (vec2_t){new_vel[2*i], new_vel[2*i+1]},
+                              in->ent_des_v, in, &p);
+        const struct movestate *ms = movestate_get(in->ent_uid);
+        int32_t *oi = out_i + 4*i;
+        float *of = out_f + 28*i;
+        memset(of, 0, 28 * sizeof(float));
+        oi[0] = p.flags;
+        oi[1] = (p.flags & (UPDATE_SET_STATE | UPDATE_SET_MOVING)) ? (int32_t)p.next_state : -1;
+        oi[2] = (p.flags & UPDATE_SET_STATE) ? (int32_t)p.next_block : 0;
+        oi[3] = ms->wait_ticks_left;
+        if(p.flags & UPDATE_SET_VELOCITY) { of[0] = p.next_velocity.x; of[1] = p.next_velocity.z; }
+        if(p.flags & UPDATE_SET_POSITION) { of[2] = p.next_pos.x; of[3] = p.next_pos.y; of[4] = p.next_pos.z; }
+        if(p.flags & UPDATE_SET_ROTATION) { of[5] = p.next_rot.x; of[6] = p.next_rot.y; of[7] = p.next_rot.z; of[8] = p.next_rot.w; }
+        if(p.flags & UPDATE_SET_PREV_POS) { of[9] = p.next_ppos.x; of[10] = p.next_ppos.y; of[11] = p.next_ppos.z; }
+        if(p.flags & UPDATE_SET_NEXT_POS) { of[12] = p.next_npos.x; of[13] = p.next_npos.y; of[14] = p.next_npos.z; }
+        if(p.flags & UPDATE_SET_STEP) of[15] = p.next_step;
+        if(p.flags & UPDATE_SET_LEFT) of[16] = p.next_left;
+        if(p.flags & UPDATE_SET_NEXT_ROT) { of[17] = p.next_nrot.x; of[18] = p.next_nrot.y; of[19] = p.next_nrot.z; of[20] = p.next_nrot.w; }
+        if(p.flags & UPDATE_SET_PREV_ROT) { of[21] = p.next_prot.x; of[22] = p.next_prot.y; of[23] = p.next_prot.z; of[24] = p.next_prot.w; }
+    }
+}
+
+/* The movestate part of entity_apply_update (movement.c:2693-2757) for moving entities: velocity +
+ * velocity history (update_vel_hist / seed_vel_hist_facing, movement.c:2025-2052), interpolation
+ * fields, rotation. State transitions (entity_finish_moving: blockers, events) and G_Pos_Set stay
+ * with the engine. Returns the resulting history so that a device-side apply can be checked.
+ * out per uid: vel_hist[28], vel_hist_idx */
+PFREF_EXPORT void pfref_apply_velocity_patch(int nwork, const float *next_velocity, const int32_t *flags,
+                                             float *out_hist, int32_t *out_idx)
+{
+    for(int i = 0; i < nwork; i++) {
+        struct movestate *ms = movestate_get(s_move_work.in[i].ent_uid);
+        if(flags[i] & UPDATE_SET_VELOCITY) {
+            ms->velocity = (vec2_t){next_velocity[2*i], next_velocity[2*i+1]};
+            if(flags[i] & UPDATE_TURNING_IN_PLACE) {
+                memset(ms->vel_hist, 0, sizeof(ms->vel_hist));
+            }else{
+                if(vel_hist_empty(ms) && PFM_Vec2_Len(&ms->velocity) > EPSILON)
+                    seed_vel_hist_facing(ms);
+                update_vel_hist(ms, ms->velocity);
+            }
+        }
+        for(int k = 0; k < VEL_HIST_LEN; k++) {
+            out_hist[(i*VEL_HIST_LEN + k)*2] = ms->vel_hist[k].x;
+            out_hist[(i*VEL_HIST_LEN + k)*2 + 1] = ms->vel_hist[k].z;
+        }
+        out_idx[i] = ms->vel_hist_idx;
     }
 }
 

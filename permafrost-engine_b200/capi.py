@@ -53,7 +53,7 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join",
 ]
 
 _lib = None
@@ -81,6 +81,7 @@ def load():
     L.pfnav_map_upload_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_build_nav.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_fields_join.argtypes = [C.c_void_p, C.c_void_p]
     L.pfnav_map_cost_from_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.pfnav_map_get_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_refresh_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -234,6 +235,9 @@ class Nav:
         liid = np.zeros((n, 64, 64), np.uint16)
         _chk(self.L.pfnav_map_get_layer(self.h, layer, _p(cost), _p(blk), _p(liid)))
         return cost, blk, liid
+
+    def fields_join(self, stream=0):
+        _chk(self.L.pfnav_fields_join(self.h, C.c_void_p(stream)))
 
     def map_build_nav(self, layer=0):
         _chk(self.L.pfnav_map_build_nav(self.h, layer))

@@ -938,6 +938,7 @@ extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
 {
     PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
     PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
     PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, ctx->h_pool_slot.size() * sizeof(int32_t)));
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, 0, ctx->pool_max));
     std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
@@ -955,6 +956,7 @@ extern "C" int pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
     PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
     PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk");
     PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
     const size_t si = (size_t)dest * ctx->chunk_w * ctx->chunk_h + chunk_r * ctx->chunk_w + chunk_c;
     int slot = ctx->h_pool_slot[si];
     uint8_t *d_has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096;
@@ -1103,7 +1105,7 @@ extern "C" int pfnav_agents_rebuild_index(pfnav_ctx *ctx, void *stream)
 {
     PF_ARG(ctx && ctx->d_records, "agents not uploaded");
     PF_CUDA(cudaSetDevice(ctx->device));
-    return build_index(ctx, (cudaStream_t)stream);
+    return build_index(ctx, pf_stream(ctx, stream));
 }
 
 extern "C" int pfnav_agents_device_ptrs(pfnav_ctx *ctx, void **d_records, void **d_velocities, size_t *n)
@@ -1161,7 +1163,7 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
     if (ctx->n_work == 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->tick_stream;
+    cudaStream_t st = pf_stream(ctx, stream);
     const int nwork = (int)ctx->n_work;
     MapView m;
     m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
@@ -1172,6 +1174,14 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     tp.scaled_max_force_d = (double)(0.75f / (float)ctx->hz) * 20.0;
     tp.scaled_max_force = (float)tp.scaled_max_force_d;
     PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
+    {
+    pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
+    k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
+                                                   ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
+    }
+    // everything above is independent of the flow/LOS fields; the LOS chains forked by
+    // pfnav_pool_request_goals have been running alongside it
+    PF_CUDA(pf_fields_join(ctx, st));
     {
     pf_prof_scope prof(ctx, st, PF_PROF_VDES);
     if (flags & PFNAV_TICK_VDES_FROM_POOL) {
@@ -1184,11 +1194,6 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     } else {
         k_copy_vdes<<<(nwork + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out);
     }
-    }
-    {
-    pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
-    k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
-                                                   ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
     }
     pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
     const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);

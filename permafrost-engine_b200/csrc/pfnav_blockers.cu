@@ -204,6 +204,10 @@ extern "C" int pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float ran
 extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (ctx->device >= 0) {
+        PF_CUDA(cudaSetDevice(ctx->device));
+        PF_CUDA(pf_fields_sync(ctx));     // forked LOS chains still read the map that is about to change
+    }
     auto it = g_dirty.find(ctx);
     int nd = 0;
     if (it != g_dirty.end()) {

@@ -993,6 +993,9 @@ extern "C" int pfnav_create(int device, pfnav_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->tick_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->field_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_los, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->tick_done, cudaEventDisableTiming) != cudaSuccess) {
         pfnav_set_error("pfnav_create: stream/event creation failed");
         delete ctx;
@@ -1055,6 +1058,9 @@ extern "C" void pfnav_destroy(pfnav_ctx *ctx)
     pfnav_agents_free(ctx);
     if (ctx->tick_done) cudaEventDestroy(ctx->tick_done);
     if (ctx->tick_stream) cudaStreamDestroy(ctx->tick_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_los) cudaEventDestroy(ctx->ev_los);
+    if (ctx->field_stream) cudaStreamDestroy(ctx->field_stream);
     delete ctx;
 }
 
@@ -1336,7 +1342,7 @@ int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, u
     PF_ARG(d_reqs && d_inout_fields, "null buffer");
     PF_ARG(n < (1u << 30), "n");
     PF_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = pf_stream(ctx, stream);
     const FlowGrids g = grids_of(ctx);
     pf_prof_scope prof(ctx, st, PF_PROF_FLOW);
     // persistent-style grid: a multiple of the SM count (2 CTAs of 8 warps fit per SM)
@@ -1372,7 +1378,7 @@ extern "C" int pfnav_flow_fields_update_general_dev(pfnav_ctx *ctx, const pfnav_
     if (n == 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
     const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
-    k_flow_general<<<gridg, FLOWG_THREADS, 0, (cudaStream_t)stream>>>(grids_of(ctx), d_reqs, (int)n, d_inout_fields, nullptr, 0);
+    k_flow_general<<<gridg, FLOWG_THREADS, 0, pf_stream(ctx, stream)>>>(grids_of(ctx), d_reqs, (int)n, d_inout_fields, nullptr, 0);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFNAV_OK;
@@ -1451,7 +1457,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
     LosMapInfo mi{ctx->map_x, ctx->map_z};
     const size_t smem = LOS_WARPS_PER_CTA * sizeof(LosSmem);
     (void)n_waves; (void)h_wave_offsets;        // requests are dependency-sorted; the kernel schedules them itself
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = pf_stream(ctx, stream);
     // scheduler state: [counter][done flags]
     const size_t need = (n + 1) * sizeof(int);
     if (ctx->los_sched_bytes < need) {

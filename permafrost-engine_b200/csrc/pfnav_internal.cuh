@@ -114,12 +114,39 @@ struct pfnav_ctx {
     uint32_t *d_work_count = nullptr;
     cudaStream_t tick_stream = nullptr;
     cudaEvent_t tick_done = nullptr;
+    // LOS chains of a goal batch run on their own stream so that the parts of the tick that do not read
+    // fields (all-gather, position index, cohesion) overlap the latency-bound LOS dependency chain
+    cudaStream_t field_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_los = nullptr;
+    bool los_inflight = false;
 
     // ---- optional per-kernel timing (pfnav_profile_enable) ----
     bool profiling = false;
     struct prof_rec { int slot; cudaEvent_t a, b; };
     std::vector<prof_rec> prof_pending;
 };
+
+// Every entry point that takes a `void *stream`: NULL names the context's own non-blocking stream
+// (never the legacy default stream, which would not be ordered against it).
+static inline cudaStream_t pf_stream(pfnav_ctx *ctx, void *stream)
+{
+    return stream ? (cudaStream_t)stream : ctx->tick_stream;
+}
+
+// order `st` after the LOS work forked onto field_stream (no-op when none was forked)
+static inline cudaError_t pf_fields_join(pfnav_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->los_inflight) return cudaSuccess;
+    return cudaStreamWaitEvent(st, ctx->ev_los, 0);
+}
+// host-side wait for the forked LOS work (setup-time entry points that use blocking copies)
+static inline cudaError_t pf_fields_sync(pfnav_ctx *ctx)
+{
+    if (!ctx->los_inflight) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(ctx->ev_los);
+    if (e == cudaSuccess) ctx->los_inflight = false;
+    return e;
+}
 
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
        PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };

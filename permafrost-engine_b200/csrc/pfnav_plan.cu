@@ -258,6 +258,24 @@ extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int t
     return PFNAV_OK;
 }
 
+// The LOS dependency chains of a goal batch are latency-bound (one thread per field replays the
+// reference's heap) and read nothing the flow kernels write: they run on ctx->field_stream, forked
+// after everything already queued on the caller's stream and joined (pf_fields_join) by whichever
+// entry point next reads or writes LOS fields of the pool. The flow kernels, the position-index
+// rebuild and the cohesion pass overlap them.
+static int los_fork(pfnav_ctx *ctx, cudaStream_t st)
+{
+    PF_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    PF_CUDA(cudaStreamWaitEvent(ctx->field_stream, ctx->ev_fork, 0));
+    return 0;
+}
+static int los_forked(pfnav_ctx *ctx)
+{
+    PF_CUDA(cudaEventRecord(ctx->ev_los, ctx->field_stream));
+    ctx->los_inflight = true;
+    return 0;
+}
+
 // n_request_path's field-building half, resident on the device, for a batch of goals: plan every
 // goal, then run the flow waves and the LOS dependency waves of ALL goals together straight into the
 // field pool (no host round trip of field bytes; one launch per wave, not per goal).
@@ -277,7 +295,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
         if (gb.valid && gb.epoch == ctx->map_epoch && gb.layer == layer && (int)gb.dests.size() == ngoals &&
             memcmp(gb.dests.data(), dests, (size_t)ngoals * 4) == 0 && memcmp(gb.targets.data(), targets, (size_t)ngoals * 16) == 0) {
             PF_CUDA(cudaSetDevice(ctx->device));
-            cudaStream_t st = (cudaStream_t)stream;
+            cudaStream_t st = pf_stream(ctx, stream);
             const uint8_t *dev = (const uint8_t *)ctx->d_plan_buf;
             int rc = 0;
             for (size_t w = 0; w + 1 < gb.fwave_off.size(); w++) {
@@ -288,8 +306,12 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
                 if (rc) return rc;
             }
             const int32_t one_wave[2] = {0, gb.nl};
+            rc = los_fork(ctx, st);
+            if (rc) return rc;
             rc = pfnav_los_launch(ctx, (const pfnav_los_req *)(dev + gb.b_fr + gb.b_fs), gb.nl, ctx->d_pool_los,
-                                  (const int32_t *)(dev + gb.b_fr + gb.b_fs + gb.b_lr), 1, one_wave, st);
+                                  (const int32_t *)(dev + gb.b_fr + gb.b_fs + gb.b_lr), 1, one_wave, ctx->field_stream);
+            if (rc) return rc;
+            rc = los_forked(ctx);
             if (rc) return rc;
             if (out_n_flow) *out_n_flow = gb.nf;
             if (out_n_los) *out_n_los = gb.nl;
@@ -297,6 +319,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
         }
         gb.valid = false;
     }
+    PF_CUDA(pf_fields_sync(ctx));       // the plan buffer below may still be read by a forked LOS kernel
     const int cap = chunks * 8 + 8;
     std::vector<pfnav_field_req> fr(cap), all_fr;
     std::vector<pfnav_los_req> lr(cap), all_lr;
@@ -364,7 +387,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
         }
     }
     PF_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = pf_stream(ctx, stream);
     // one staging buffer per context: goal batches are serialised on one stream by the caller
     if (ctx->plan_buf_bytes < total) {
         PF_CUDA(cudaStreamSynchronize(st));
@@ -390,7 +413,11 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
         rc = pfnav_flow_launch(ctx, dfr + first, cnt, ctx->d_pool_flow, dfs + first, st);
         if (rc) return rc;
     }
-    rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), st);
+    rc = los_fork(ctx, st);
+    if (rc) return rc;
+    rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), ctx->field_stream);
+    if (rc) return rc;
+    rc = los_forked(ctx);
     if (rc) return rc;
     {
         auto &gb = ctx->goal_batch;
@@ -408,4 +435,15 @@ extern "C" int pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int 
 {
     const int32_t d = dest, t[4] = {tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c};
     return pfnav_pool_request_goals(ctx, 1, &d, layer, t, stream, out_n_flow, out_n_los);
+}
+
+// Order `stream` after the LOS chains that pfnav_pool_request_goals forked onto the context's field
+// stream. pfnav_agents_tick and the pool entry points do this themselves.
+extern "C" int pfnav_fields_join(pfnav_ctx *ctx, void *stream)
+{
+    PF_ARG(ctx, "ctx");
+    PF_NEED_DEVICE(ctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_join(ctx, pf_stream(ctx, stream)));
+    return PFNAV_OK;
 }

@@ -686,6 +686,8 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
     PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
     PF_NEED_DEVICE(ctx);
     PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
     const int chunks = ctx->chunk_w * ctx->chunk_h;
     std::vector<uint8_t> have_los(chunks, 0);
     for (int c = 0; c < chunks; c++) {
@@ -765,7 +767,7 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
         }
     }
     PF_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = pf_stream(ctx, stream);
     if (ctx->plan_buf_bytes < total) {
         PF_CUDA(cudaStreamSynchronize(st));
         cudaFree(ctx->d_plan_buf);

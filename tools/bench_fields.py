@@ -28,7 +28,8 @@ def main():
     portal_reqs = np.concatenate(pr)
     portal_reqs = np.concatenate([portal_reqs] * (n // len(portal_reqs) + 1))[:n]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    _stream = torch.cuda.Stream(); torch.cuda.set_stream(_stream)     # NULL would name the context's own stream
+    st = _stream.cuda_stream
     out = torch.zeros((n, 4096), dtype=torch.uint8, device="cuda")
     def timeit(fn, iters=5):
         for _ in range(3): fn()
@@ -69,14 +70,15 @@ def goals():
     tiles = synth.random_passable_tiles(cost, 16, rng)
     targets = np.array([[int(t[0]) // cw, int(t[0]) % cw, int(t[1]), int(t[2])] for t in tiles], np.int32)
     nav.pool_create(16, 16 * 256)
-    st = torch.cuda.current_stream().cuda_stream
+    _stream = torch.cuda.Stream(); torch.cuda.set_stream(_stream)
+    st = _stream.cuda_stream
     for _ in range(3): nf, nl = nav.pool_request_goals(np.arange(16, dtype=np.int32), targets, 0, st)
     torch.cuda.synchronize()
     nav.profile_enable(True)
     ms = []
     for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); nav.pool_request_goals(np.arange(16, dtype=np.int32), targets, 0, st); b.record(); torch.cuda.synchronize()
+        a.record(); nav.pool_request_goals(np.arange(16, dtype=np.int32), targets, 0, st); nav.fields_join(st); b.record(); torch.cuda.synchronize()
         ms.append(a.elapsed_time(b))
     prof = nav.profile_read()
     print(json.dumps({"case": "16 goals dense", "flow": nf, "los": nl, "ms_total_median": float(np.median(ms)),
