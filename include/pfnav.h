@@ -318,6 +318,72 @@ int  pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n,
  * NULL = every agent whose state is not ARRIVED/WAITING (ent_still, movement.c:652). */
 int  pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_t nwork);
 
+/* ---------------------------------------------------------------------------------------- */
+/* State update: entity_compute_update (game/movement.c:2303-2650) on the device, one
+ * `struct movestate_patch` (movement.c:245-262) per work item, for the point-seek states the velocity
+ * pass covers (STATE_MOVING / STATE_SEEK_ENEMIES; formation, surround, enter-range and turning states
+ * belong to engine subsystems outside this path and are rejected). The engine applies the patches on
+ * its main thread (entity_apply_update, movement.c:2693: blockers, events, G_Pos_Set);
+ * pfnav_agents_apply_updates is the device-side equivalent for the movestate fields so that
+ * consecutive ticks can run without a host round trip. */
+#define PFNAV_VEL_HIST_LEN 14           /* VEL_HIST_LEN, movement.c:94 */
+typedef struct pfnav_movestate {        /* the part of struct movestate (movement.c:146-215) the update reads */
+    float   next_pos[3];                /* ms->next_pos                                  */
+    float   step;                       /* ms->step                                      */
+    float   next_rot[4];                /* ms->next_rot, quaternion {x, y, z, w}          */
+    float   combat_facing[4];           /* ms->combat_facing                             */
+    float   vel_hist[PFNAV_VEL_HIST_LEN][2];
+    int32_t left;                       /* ms->left                                      */
+    int32_t vel_hist_idx;
+    int32_t _pad[2];
+} pfnav_movestate;                      /* 176 bytes */
+
+/* enum movestate_flags (movement.c:226-242), same bit values */
+#define PFNAV_UPDATE_SET_STATE        (1u << 0)
+#define PFNAV_UPDATE_SET_VELOCITY     (1u << 1)
+#define PFNAV_UPDATE_SET_POSITION     (1u << 2)
+#define PFNAV_UPDATE_SET_ROTATION     (1u << 3)
+#define PFNAV_UPDATE_SET_NEXT_POS     (1u << 4)
+#define PFNAV_UPDATE_SET_PREV_POS     (1u << 5)
+#define PFNAV_UPDATE_SET_STEP         (1u << 6)
+#define PFNAV_UPDATE_SET_LEFT         (1u << 7)
+#define PFNAV_UPDATE_SET_NEXT_ROT     (1u << 8)
+#define PFNAV_UPDATE_SET_PREV_ROT     (1u << 9)
+#define PFNAV_UPDATE_TURNING_IN_PLACE (1u << 14)
+
+typedef struct pfnav_patch {            /* struct movestate_patch (movement.c:245-262); unselected fields are 0 */
+    uint32_t flags;
+    int32_t  next_state;                /* -1 unless SET_STATE                            */
+    int32_t  next_block;
+    int32_t  _pad;
+    float    next_velocity[2];
+    float    next_pos[3];               /* y: 0 (AIR_UNIT_HEIGHT for air units); terrain height
+                                         * (M_HeightAtPoint) is render state, added by the engine  */
+    float    next_rot[4];
+    float    next_ppos[3];
+    float    next_npos[3];
+    float    next_step;
+    float    next_left;
+    float    next_nrot[4];
+    float    next_prot[4];
+    float    _padf[3];
+} pfnav_patch;                          /* 128 bytes */
+
+/* HOST array of n_agents records, uid == index. */
+int  pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movestate *ms, size_t n);
+/* After pfnav_agents_tick on the same stream: entity_compute_update for every work item, reading the
+ * tick's new velocities and desired velocities. Needs pfnav_route_build for every layer the agents
+ * use (global islands feed arrived(), movement.c:2170). */
+int  pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream);
+/* Work-item order. Blocks until the update pass has finished. */
+int  pfnav_agents_read_patches(pfnav_ctx *ctx, pfnav_patch *out, size_t maxout);
+/* Device-side entity_apply_update for the movestate fields (movement.c:2693-2757: state, velocity +
+ * velocity history, position, interpolation fields, next rotation), then refreshes the neighbour
+ * records; follow with pfnav_agents_rebuild_index before the next tick. */
+int  pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream);
+/* Read the (updated) entity snapshot back: agents_out / ms_out may be NULL. */
+int  pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, pfnav_movestate *ms_out, size_t maxout);
+
 /* flags for pfnav_agents_tick */
 #define PFNAV_TICK_VDES_FROM_POOL   (1u << 0)  /* compute vdes + has_dest_los on device (nav.c:3468, 4026) */
 

@@ -491,7 +491,7 @@ void pfo_world_destroy(pfo_world *w)
 }
 
 /* bg_ent_inrange_circle (bitmap_grid.h:1376) */
-int pfo_ents_in_circle(const pfo_world *w, float x, float z, float range, uint32_t *out, int maxout)
+static int bg_inrange_circle(const pfo_world *w, float x, float z, float range, uint32_t *out, int maxout)
 {
     if(maxout <= 0 || range < 0.0f) return 0;
     int32_t icx = bg_scale(x), icy = bg_scale(z), ir = bg_scale(range);
@@ -527,6 +527,22 @@ int pfo_ents_in_circle(const pfo_world *w, float x, float z, float range, uint32
         }}
     }}
     return written;
+}
+
+/* G_Pos_EntsInCircleFrom (position.c:379): the raw grid query, then filter_garrisoned
+ * (position.c:100-119) -- a swap-remove from the back, which REORDERS the survivors. */
+#define FLAG_GARRISONED_Q (1u << 18)
+int pfo_ents_in_circle(const pfo_world *w, float x, float z, float range, uint32_t *out, int maxout)
+{
+    int count = bg_inrange_circle(w, x, z, range, out, maxout);
+    int ret = count;
+    for(int i = count - 1; i >= 0; i--) {
+        if(w->agents[out[i]].flags & FLAG_GARRISONED_Q) {
+            out[i] = out[ret - 1];
+            ret--;
+        }
+    }
+    return ret;
 }
 
 /* ------------------------------------------------------------------------------------------

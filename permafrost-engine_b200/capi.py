@@ -38,6 +38,18 @@ assert AGENT.itemsize == 64
 FLOCK = np.dtype([("target", "<f4", 2), ("dest", "<i4"), ("layer", "<i4")])
 assert FLOCK.itemsize == 16
 
+MOVESTATE = np.dtype([
+    ("next_pos", "<f4", 3), ("step", "<f4"), ("next_rot", "<f4", 4), ("combat_facing", "<f4", 4),
+    ("vel_hist", "<f4", (14, 2)), ("left", "<i4"), ("vel_hist_idx", "<i4"), ("_pad", "<i4", 2)])
+assert MOVESTATE.itemsize == 176
+
+PATCH = np.dtype([
+    ("flags", "<u4"), ("next_state", "<i4"), ("next_block", "<i4"), ("_pad", "<i4"),
+    ("next_velocity", "<f4", 2), ("next_pos", "<f4", 3), ("next_rot", "<f4", 4), ("next_ppos", "<f4", 3),
+    ("next_npos", "<f4", 3), ("next_step", "<f4"), ("next_left", "<f4"), ("next_nrot", "<f4", 4),
+    ("next_prot", "<f4", 4), ("_padf", "<f4", 3)])
+assert PATCH.itemsize == 128
+
 TICK_VDES_FROM_POOL = 1
 FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 1 << 14, 1 << 15, 1 << 18, 1 << 21
 
@@ -53,7 +65,8 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
+    "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
 ]
 
 _lib = None
@@ -82,6 +95,11 @@ def load():
     L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_build_nav.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_fields_join.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_agents_upload_movestate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_compute_updates.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_agents_read_patches.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_apply_updates.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_agents_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_map_cost_from_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.pfnav_map_get_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_refresh_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -399,6 +417,27 @@ class Nav:
         out = np.zeros((nwork, 2), np.float32)
         _chk(self.L.pfnav_agents_read_velocities(self.h, _p(out), nwork))
         return out
+
+    def agents_upload_movestate(self, ms):
+        ms = np.ascontiguousarray(ms, MOVESTATE)
+        _chk(self.L.pfnav_agents_upload_movestate(self.h, _p(ms), len(ms)))
+
+    def agents_compute_updates(self, stream=0):
+        _chk(self.L.pfnav_agents_compute_updates(self.h, C.c_void_p(stream)))
+
+    def agents_read_patches(self, nwork):
+        out = np.zeros(nwork, PATCH)
+        _chk(self.L.pfnav_agents_read_patches(self.h, _p(out), nwork))
+        return out
+
+    def agents_apply_updates(self, stream=0):
+        _chk(self.L.pfnav_agents_apply_updates(self.h, C.c_void_p(stream)))
+
+    def agents_read_state(self, n, movestate=True):
+        a = np.zeros(n, AGENT)
+        ms = np.zeros(n, MOVESTATE) if movestate else None
+        _chk(self.L.pfnav_agents_read_state(self.h, _p(a), _p(ms), n))
+        return a, ms
 
     def agents_read_debug(self, nwork):
         vpref = np.zeros((nwork, 2), np.float32)

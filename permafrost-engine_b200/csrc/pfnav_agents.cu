@@ -380,7 +380,10 @@ __device__ __forceinline__ void grid_query(const GridView &g, float x, float z, 
     }
 }
 
-__global__ void k_ents_in_circle(GridView g, float x, float z, float range, uint32_t *out, int maxout, int *out_n)
+__device__ __forceinline__ int filter_garrisoned(uint32_t *ids, int count, const pf_record *__restrict__ rec, uint32_t lane);
+
+__global__ void k_ents_in_circle(GridView g, float x, float z, float range, uint32_t *out, int maxout, int *out_n,
+                                 const pf_record *__restrict__ rec, int filter_garr)
 {
     const uint32_t lane = threadIdx.x & 31;
     int written = 0;
@@ -391,7 +394,26 @@ __global__ void k_ents_in_circle(GridView g, float x, float z, float range, uint
         written += __popc(m);
         return written >= maxout;
     });
-    if (lane == 0) *out_n = min(written, maxout);
+    written = min(written, maxout);
+    __syncwarp();
+    if (filter_garr) written = filter_garrisoned(out, written, rec, lane);      // position.c:379
+    if (lane == 0) *out_n = written;
+}
+
+// filter_garrisoned (position.c:100-119): swap-remove from the back, applied by G_Pos_EntsInCircleFrom
+// (position.c:379) AFTER the raw query was cut at maxout; it reorders the survivors. Serial on lane 0
+// (only runs when the population holds garrisoned entities at all); returns the new count to all lanes.
+__device__ __forceinline__ int filter_garrisoned(uint32_t *ids, int count, const pf_record *__restrict__ rec, uint32_t lane)
+{
+    int ret = count;
+    if (lane == 0) {
+        for (int i = count - 1; i >= 0; i--) {
+            if (rec[ids[i]].state_flags & PFNAV_FLAG_GARRISONED) { ids[i] = ids[ret - 1]; ret--; }
+        }
+    }
+    ret = __shfl_sync(FULL, ret, 0);
+    __syncwarp();
+    return ret;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -723,7 +745,8 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                  const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
                  const uint8_t *__restrict__ los_in, const float2 *__restrict__ cohesion_in,
-                 float2 *__restrict__ vel_out, float2 *__restrict__ vpref_out)
+                 float2 *__restrict__ vel_out, float2 *__restrict__ vpref_out, int filter_garr,
+                 uint32_t *__restrict__ nb_scratch)
 {
     __shared__ VelSmem smem[VEL_WARPS_PER_CTA];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -761,6 +784,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             });
             num_near = min(num_near, 128);
             __syncwarp();
+            if (filter_garr) num_near = filter_garrisoned(s.near_id, num_near, rec, lane);
             for (int k = lane; k < num_near; k += 32) {
                 const uint32_t cu = s.near_id[k];
                 float2 term = make_float2(0.f, 0.f);
@@ -843,7 +867,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
 
         // ================= find_neighbours (movement.c:2768) =================
         int ndyn = 0, nstat = 0, raw = 0;
-        grid_query(g, pos.x, pos.z, 10.0f, lane, [&](bool hit, uint32_t id) -> bool {
+        auto classify = [&](bool hit, uint32_t id) -> bool {
             const uint32_t mk = __ballot_sync(FULL, hit);
             const int rrank = __popc(mk & ((1u << lane) - 1));
             bool isdyn = false, isstat = false;
@@ -867,7 +891,29 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             nstat = min(nstat + __popc(ms), PFNAV_MAX_NEIGHBOURS);
             raw += __popc(mk);
             return raw >= 512;
-        });
+        };
+        if (!filter_garr) {
+            grid_query(g, pos.x, pos.z, 10.0f, lane, classify);
+        } else {
+            // garrisoned entities exist: G_Pos_EntsInCircleFrom (position.c:379) first takes the raw hits (<= 512),
+            // then filter_garrisoned swap-removes them, which reorders the survivors -> materialise the list
+            uint32_t *lst = nb_scratch + (size_t)(blockIdx.x * VEL_WARPS_PER_CTA + warp) * 512;
+            int cnt = 0;
+            grid_query(g, pos.x, pos.z, 10.0f, lane, [&](bool hit, uint32_t id) -> bool {
+                const uint32_t mk = __ballot_sync(FULL, hit);
+                const int rank = __popc(mk & ((1u << lane) - 1));
+                if (hit && cnt + rank < 512) lst[cnt + rank] = id;
+                cnt += __popc(mk);
+                return cnt >= 512;
+            });
+            cnt = min(cnt, 512);
+            __syncwarp();
+            cnt = filter_garrisoned(lst, cnt, rec, lane);
+            for (int k0 = 0; k0 < cnt; k0 += 32) {
+                const int k = k0 + (int)lane;
+                if (classify(k < cnt, k < cnt ? lst[k] : 0u)) break;
+            }
+        }
         __syncwarp();
 
         // ================= G_ClearPath_NewVelocity (clearpath.c:694) =================
@@ -901,6 +947,8 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_cell_count); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_cell_fill);
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
+    cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
+    if (ctx->update_done) cudaEventDestroy(ctx->update_done);
     cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
     ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
     ctx->d_flock_members = nullptr; ctx->d_cohesion = nullptr; ctx->d_cell_count = nullptr; ctx->d_cell_start = nullptr;
@@ -1050,6 +1098,8 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
     ctx->n_agents = n; ctx->n_flocks = nflocks;
     // flock member lists, ascending uid (the iteration order our cohesion sum is defined over)
     std::vector<uint32_t> fstart(nflocks + 1, 0), members(n ? n : 1);
+    ctx->flock_layer_used.assign(nflocks * PFNAV_NAV_LAYER_MAX, 0);
+    ctx->max_radius = 0.0f; ctx->has_unsupported_state = false; ctx->any_garrisoned = false;
     for (size_t i = 0; i < n; i++) {
         PF_ARG(agents[i].flock < (int)nflocks, "agent flock index out of range");
         {   // Entity_NavLayerWithRadius (entity.c:554): the layer this agent's tile probes read
@@ -1057,9 +1107,18 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
             const int base = (f & PFNAV_FLAG_WATER) ? 4 : (f & PFNAV_FLAG_AIR) ? 8 : 0;
             const int layer = base + (r >= 15.0f ? 3 : r >= 10.0f ? 2 : r >= 5.0f ? 1 : 0);
             PF_ARG(layer < ctx->nlayers, "agent needs a navigation layer that was not created (radius/flags)");
+            if (agents[i].flock >= 0) ctx->flock_layer_used[(size_t)agents[i].flock * PFNAV_NAV_LAYER_MAX + layer] = 1;
+            ctx->max_radius = std::max(ctx->max_radius, r);
+            if (f & PFNAV_FLAG_GARRISONED) ctx->any_garrisoned = true;
+            const uint32_t stt = agents[i].state;
+            if (stt == PFNAV_STATE_MOVING_IN_FORMATION || stt == PFNAV_STATE_SURROUND_ENTITY ||
+                stt == PFNAV_STATE_ENTER_ENTITY_RANGE || stt == PFNAV_STATE_TURNING || stt == PFNAV_STATE_ARRIVING_TO_CELL)
+                ctx->has_unsupported_state = true;
         }
         if (agents[i].flock >= 0) fstart[agents[i].flock + 1]++;
     }
+    ctx->h_flocks.assign(flocks, flocks + nflocks);
+    ctx->arrival_valid = false;
     for (size_t f = 0; f < nflocks; f++) fstart[f + 1] += fstart[f];
     {
         std::vector<uint32_t> cur(fstart.begin(), fstart.end() - 1);
@@ -1197,9 +1256,16 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     }
     pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
     const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
+    if (ctx->any_garrisoned && ctx->nb_scratch_warps < (size_t)ctas * VEL_WARPS_PER_CTA) {
+        // per-warp raw neighbour lists for the garrisoned-filter path (find_neighbours, 512 ids each)
+        cudaFree(ctx->d_nb_scratch); ctx->d_nb_scratch = nullptr; ctx->nb_scratch_warps = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_nb_scratch, (size_t)ctas * VEL_WARPS_PER_CTA * 512 * sizeof(uint32_t)));
+        ctx->nb_scratch_warps = (size_t)ctas * VEL_WARPS_PER_CTA;
+    }
     k_agent_velocity<<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                              ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
-                                                             ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out);
+                                                             ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
+                                                             ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch);
     ctx->launches += 3;
     PF_CUDA(cudaGetLastError());
     prof.~pf_prof_scope(); prof.a = nullptr;
@@ -1238,12 +1304,454 @@ extern "C" int pfnav_ents_in_circle(pfnav_ctx *ctx, float x, float z, float rang
     uint32_t *d_out = nullptr; int *d_n = nullptr;
     PF_CUDA(cudaMalloc(&d_out, (size_t)maxout * 4));
     PF_CUDA(cudaMalloc(&d_n, 4));
-    k_ents_in_circle<<<1, 32, 0, ctx->tick_stream>>>(grid_of(ctx), x, z, range, d_out, maxout, d_n);
+    k_ents_in_circle<<<1, 32, 0, ctx->tick_stream>>>(grid_of(ctx), x, z, range, d_out, maxout, d_n, ctx->d_records,
+                                                     ctx->any_garrisoned ? 1 : 0);
     ctx->launches++;
     cudaError_t e = cudaStreamSynchronize(ctx->tick_stream);
     if (e == cudaSuccess) e = cudaMemcpy(out_n, d_n, 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && *out_n > 0) e = cudaMemcpy(out, d_out, (size_t)*out_n * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_out); cudaFree(d_n);
     if (e != cudaSuccess) { pfnav_set_error("pfnav_ents_in_circle: %s", cudaGetErrorString(e)); return PFNAV_ERR_CUDA; }
+    return PFNAV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// State update: entity_compute_update (movement.c:2303-2650) + the movestate part of
+// entity_apply_update (movement.c:2693-2757). One thread per work item.
+// The quaternion helpers keep the reference's mix of float and double arithmetic (pf_math.c).
+// ------------------------------------------------------------------------------------------
+struct quat { float x, y, z, w; };
+struct pf_arrival_dev { int32_t nearest_ok; float nearest[2]; int32_t mc_n; int32_t mc_off; int32_t _pad[3]; };
+
+#define PF_PI_D 3.14159265358979323846
+
+// first column of PFM_Mat4x4_RotFromQuat (pf_math.c:324) applied to (1,0,0,1) by PFM_Quat_PitchDiff (:677)
+__device__ __forceinline__ void quat_front(const quat &q, float &dx, float &dz)
+{
+    dx = (float)(1 - 2 * ((double)q.y * (double)q.y) - 2 * ((double)q.z * (double)q.z));   // pow(y,2) is exact y*y in double
+    dz = 2 * q.x * q.z + 2 * q.w * q.y;
+    // dir_homo.w == 1; the zero products of PFM_Mat4x4_Mult4x1 add nothing for finite inputs
+}
+
+// PFM_Quat_PitchDiff (pf_math.c:677-704)
+__device__ __forceinline__ float quat_pitch_diff(const quat &a, const quat &b)
+{
+    float ax, az, bx, bz;
+    quat_front(a, ax, az);
+    quat_front(b, bx, bz);
+    const float dot = ax * bx + az * bz;
+    const float det = ax * bz - az * bx;
+    return (float)atan2((double)det, (double)dot);
+}
+
+// dir_quat_from_velocity (movement.c:1411)
+__device__ __forceinline__ quat dir_quat_from_velocity(v2 v)
+{
+    const float angle_rad = (float)(atan2((double)v.z, (double)v.x) - PF_PI_D / 2.0f);
+    quat q;
+    q.x = 0.0f; q.z = 0.0f;
+    q.y = (float)(1.0f * sin((double)(angle_rad / 2.0f)));
+    q.w = (float)cos((double)(angle_rad / 2.0f));
+    return q;
+}
+
+// turn_toward (movement.c:2249): PFM_Mat4x4_MakeRotY -> PFM_Quat_FromRotMat -> MultQuat -> Normal
+__device__ quat turn_toward(const quat &cur, const quat &target, float max_deg)
+{
+    float angle_deg = (float)((double)quat_pitch_diff(cur, target) * (180.0f / PF_PI_D));
+    if (180.0f - fabs((double)angle_deg) < 1.0f) angle_deg = 180.0f;
+    const double mn = ((double)max_deg < fabs((double)angle_deg)) ? (double)max_deg : fabs((double)angle_deg);
+    const int sg = (angle_deg > 0) - (angle_deg < 0);
+    const float turn_deg = (float)(mn * -sg);
+    const float radians = (float)((double)turn_deg * (PF_PI_D / 180.0f));
+    const float c = (float)cos((double)radians), sn = (float)sin((double)radians);
+    // rotation matrix about Y: cols[0][0] = c, cols[0][2] = -s, cols[2][0] = s, cols[2][2] = c, cols[1][1] = 1
+    const float m00 = c, m02 = -sn, m20 = sn, m22 = c, m11 = 1.0f;
+    quat rot;
+    const float tr = m00 + m11 + m22;
+    if (tr > 0) {
+        const float S = (float)(sqrt((double)tr + 1.0) * 2);
+        rot.w = (float)(0.25 * (double)S);
+        rot.x = (0.0f - 0.0f) / S;
+        rot.y = (m02 - m20) / S;
+        rot.z = (0.0f - 0.0f) / S;
+    } else if ((m00 > m11) && (m00 > m22)) {
+        const float S = (float)(sqrt(1.0 + (double)m00 - (double)m11 - (double)m22) * 2);
+        rot.w = (0.0f - 0.0f) / S; rot.x = (float)(0.25 * (double)S); rot.y = (0.0f + 0.0f) / S; rot.z = (m02 + m20) / S;
+    } else if (m11 > m22) {
+        const float S = (float)(sqrt(1.0 + (double)m11 - (double)m00 - (double)m22) * 2);
+        rot.w = (m02 - m20) / S; rot.x = (0.0f + 0.0f) / S; rot.y = (float)(0.25 * (double)S); rot.z = (0.0f + 0.0f) / S;
+    } else {
+        const float S = (float)(sqrt(1.0 + (double)m22 - (double)m00 - (double)m11) * 2);
+        rot.w = (0.0f - 0.0f) / S; rot.x = (m02 + m20) / S; rot.y = (0.0f + 0.0f) / S; rot.z = (float)(0.25 * (double)S);
+    }
+    // PFM_Quat_MultQuat(&rot, &cur) (pf_math.c:639)
+    quat f;
+    f.x = ( rot.x * cur.w) + (rot.y * cur.z) - (rot.z * cur.y) + (rot.w * cur.x);
+    f.y = (-rot.x * cur.z) + (rot.y * cur.w) + (rot.z * cur.x) + (rot.w * cur.y);
+    f.z = ( rot.x * cur.y) - (rot.y * cur.x) + (rot.z * cur.w) + (rot.w * cur.z);
+    f.w = (-rot.x * cur.x) - (rot.y * cur.y) - (rot.z * cur.z) + (rot.w * cur.w);
+    const float len = (float)sqrt((double)(f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w));
+    f.x = f.x / len; f.y = f.y / len; f.z = f.z / len; f.w = f.w / len;
+    return f;
+}
+
+// n_tile_blocked (nav.c:235)
+__device__ __forceinline__ bool tile_blocked_abs(const MapView &m, int layer, int ar, int ac)
+{
+    const size_t off = ((size_t)layer * m.H64 + ar) * m.W64 + ac;
+    return m.cost[off] == 0xFF || m.blk[off] > 0;
+}
+
+struct UpdateParams { int hz; float turn_rate; float adj_query_r; };
+
+__global__ void __launch_bounds__(128)
+k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__restrict__ agents,
+                const pf_record *__restrict__ rec, const pfnav_movestate *__restrict__ mss,
+                const pfnav_flock *__restrict__ flocks, const pf_arrival_dev *__restrict__ arr,
+                const float2 *__restrict__ mc_tiles, int nlayers, const uint32_t *__restrict__ work, int nwork,
+                const float2 *__restrict__ vel_in, const float2 *__restrict__ vdes_in, pfnav_patch *__restrict__ out)
+{
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwork) return;
+    const uint32_t uid = work[wi];
+    const pfnav_agent a = agents[uid];
+    const pfnav_movestate ms = mss[uid];
+    const float EPS = 1.0f / 1024;
+    pfnav_patch p;
+    memset(&p, 0, sizeof(p));
+    p.next_state = -1;
+    const quat ms_rot = {ms.next_rot[0], ms.next_rot[1], ms.next_rot[2], ms.next_rot[3]};
+    v2 new_vel = {vel_in[wi].x, vel_in[wi].y};
+    const v2 vdes = {vdes_in[wi].x, vdes_in[wi].y};
+    const v2 ms_vel = {a.velocity[0], a.velocity[1]};
+    const v2 curr_xz = {a.pos[0], a.pos[1]};
+    const uint32_t state = a.state;
+
+    // flush an unfinished interpolation (movement.c:2311)
+    if (ms.left > 0) {
+        p.flags |= PFNAV_UPDATE_SET_POSITION | PFNAV_UPDATE_SET_ROTATION | PFNAV_UPDATE_SET_LEFT;
+        p.next_pos[0] = ms.next_pos[0]; p.next_pos[1] = ms.next_pos[1]; p.next_pos[2] = ms.next_pos[2];
+        p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+        p.next_left = 0;
+    }
+    // heading gate (movement.c:2323-2335)
+    bool turn_to_move = false;
+    quat travel_dir = ms_rot;
+    const bool gated = state == PFNAV_STATE_MOVING || state == PFNAV_STATE_SEEK_ENEMIES ||
+                       state == PFNAV_STATE_SURROUND_ENTITY || state == PFNAV_STATE_ENTER_ENTITY_RANGE;
+    if (v2_len(new_vel) > EPS && gated) {
+        travel_dir = dir_quat_from_velocity(v2_len(vdes) > EPS ? vdes : new_vel);
+        const float heading_err = (float)fabs((double)quat_pitch_diff(ms_rot, travel_dir) * (180.0f / PF_PI_D));
+        const float tolerance = (v2_len(ms_vel) > EPS) ? 90.0f : 10.0f;
+        if (heading_err > tolerance) { turn_to_move = true; new_vel = {0.0f, 0.0f}; }
+    }
+    v2 new_pos_xz = v2_add(curr_xz, new_vel);
+    const int layer = nav_layer_for(a.flags, a.radius);
+    const bool still = state == PFNAV_STATE_ARRIVED || state == PFNAV_STATE_WAITING;
+    if (a.flags & PFNAV_FLAG_GARRISONED) {
+        if (!still) { p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 0; }
+        out[wi] = p;
+        return;
+    }
+    bool dummy, on_blocked, np_path, np_blocked;
+    probe_tile(m, layer, curr_xz.x, curr_xz.z, dummy, on_blocked);
+    probe_tile(m, layer, new_pos_xz.x, new_pos_xz.z, np_path, np_blocked);
+    const float turn_rate = up.turn_rate;
+    if (v2_len(new_vel) > 0 && np_path && (on_blocked || !np_blocked)) {
+        // unit_height (movement.c:2198) with M_HeightAtPoint == 0: terrain height is render state
+        const float y = (a.flags & PFNAV_FLAG_WATER) ? 0.0f : (a.flags & PFNAV_FLAG_AIR) ? 20.0f : 0.0f  /* AIR_UNIT_HEIGHT, game.h:50 */;
+        p.flags |= PFNAV_UPDATE_SET_PREV_POS | PFNAV_UPDATE_SET_NEXT_POS | PFNAV_UPDATE_SET_STEP | PFNAV_UPDATE_SET_LEFT;
+        p.next_ppos[0] = ms.next_pos[0]; p.next_ppos[1] = ms.next_pos[1]; p.next_ppos[2] = ms.next_pos[2];
+        p.next_npos[0] = new_pos_xz.x; p.next_npos[1] = y; p.next_npos[2] = new_pos_xz.z;
+        p.next_step = 1.0f / (20 / up.hz);
+        p.next_left = (float)((20 / up.hz) - 1);
+        p.flags |= PFNAV_UPDATE_SET_POSITION;
+        if ((20 / up.hz) - 1 == 0) {
+            p.next_pos[0] = new_pos_xz.x; p.next_pos[1] = y; p.next_pos[2] = new_pos_xz.z;
+        } else {
+            // interpolate_positions(next_ppos, next_npos, ms->step) (movement.c:2221)
+            float ix, iy, iz;
+            if (fabs(1.0 - (double)ms.step) < EPS) { ix = p.next_npos[0]; iy = p.next_npos[1]; iz = p.next_npos[2]; }
+            else {
+                ix = p.next_ppos[0] + (p.next_npos[0] - p.next_ppos[0]) * ms.step;
+                iy = p.next_ppos[1] + (p.next_npos[1] - p.next_ppos[1]) * ms.step;
+                iz = p.next_ppos[2] + (p.next_npos[2] - p.next_ppos[2]) * ms.step;
+            }
+            new_pos_xz = {ix, iz};
+            p.next_pos[0] = ix; p.next_pos[1] = iy; p.next_pos[2] = iz;
+        }
+        p.flags |= PFNAV_UPDATE_SET_VELOCITY;
+        p.next_velocity[0] = new_vel.x; p.next_velocity[1] = new_vel.z;
+        p.flags |= PFNAV_UPDATE_SET_PREV_ROT | PFNAV_UPDATE_SET_NEXT_ROT | PFNAV_UPDATE_SET_ROTATION;
+        p.next_prot[0] = ms_rot.x; p.next_prot[1] = ms_rot.y; p.next_prot[2] = ms_rot.z; p.next_prot[3] = ms_rot.w;
+        // orient_to_velocity_history (movement.c:2291) over vel_wma (movement.c:2067)
+        v2 wma = {0.0f, 0.0f};
+        float denom = 0.0f;
+        for (int i = 0; i < PFNAV_VEL_HIST_LEN; i++) {
+            const int k = (ms.vel_hist_idx + i) % PFNAV_VEL_HIST_LEN;
+            const float wgt = (float)(PFNAV_VEL_HIST_LEN - i);
+            wma.x = wma.x + ms.vel_hist[k][0] * wgt;
+            wma.z = wma.z + ms.vel_hist[k][1] * wgt;
+            denom += wgt;
+        }
+        if (denom > EPS) { const float inv = 1.0f / denom; wma.x = wma.x * inv; wma.z = wma.z * inv; }
+        quat nrot = ms_rot;
+        if (v2_len(wma) > EPS) nrot = turn_toward(ms_rot, dir_quat_from_velocity(wma), turn_rate);
+        p.next_nrot[0] = nrot.x; p.next_nrot[1] = nrot.y; p.next_nrot[2] = nrot.z; p.next_nrot[3] = nrot.w;
+        p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+    } else {
+        p.flags |= PFNAV_UPDATE_SET_VELOCITY;
+        p.next_velocity[0] = 0.0f; p.next_velocity[1] = 0.0f;
+        const bool held = a.flags & PFNAV_FLAG_COMBAT_HELD;
+        if (held || turn_to_move) {
+            p.flags |= PFNAV_UPDATE_SET_PREV_ROT | PFNAV_UPDATE_SET_NEXT_ROT | PFNAV_UPDATE_SET_ROTATION |
+                       PFNAV_UPDATE_TURNING_IN_PLACE;
+            const quat tgt = held ? quat{ms.combat_facing[0], ms.combat_facing[1], ms.combat_facing[2], ms.combat_facing[3]}
+                                  : travel_dir;
+            const quat nrot = turn_toward(ms_rot, tgt, turn_rate);
+            p.next_prot[0] = ms_rot.x; p.next_prot[1] = ms_rot.y; p.next_prot[2] = ms_rot.z; p.next_prot[3] = ms_rot.w;
+            p.next_nrot[0] = nrot.x; p.next_nrot[1] = nrot.y; p.next_nrot[2] = nrot.z; p.next_nrot[3] = nrot.w;
+            p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+        }
+    }
+    // stuck on non-pathable terrain: keep the state (movement.c:2417)
+    bool cur_path, cur_blk;
+    probe_tile(m, layer, new_pos_xz.x, new_pos_xz.z, cur_path, cur_blk);
+    if (!cur_path || a.flock < 0 || state != PFNAV_STATE_MOVING) { out[wi] = p; return; }
+
+    // ---- STATE_MOVING (movement.c:2421-2495), no formation, no arrival group ----
+    const pfnav_flock fl = flocks[a.flock];
+    const pf_arrival_dev ac = arr[(size_t)a.flock * nlayers + layer];
+    bool arrived = false;
+    {   // arrived() (movement.c:2170)
+        const v2 tgt = {fl.target[0], fl.target[1]};
+        const float thresh = a.radius * 1.5f;
+        if (v2_len(v2_sub(tgt, new_pos_xz)) < thresh) arrived = true;
+        if (!arrived) {
+            // N_IsAdjacentToImpassable (nav.c:4745) && N_IsMaximallyClose (nav.c:4707)
+            tile_desc td;
+            bool adj = false;
+            if (desc_for_point(m, new_pos_xz.x, new_pos_xz.z, td)) {
+                const int ar = td.chunk_r * 64 + td.tile_r, acol = td.chunk_c * 64 + td.tile_c;
+                const int dr[4] = {-1, 0, 0, 1}, dc[4] = {0, -1, 1, 0};
+                for (int e = 0; e < 4 && !adj; e++) {
+                    const int nr = ar + dr[e], nc = acol + dc[e];
+                    if (nr < 0 || nr >= m.H64 || nc < 0 || nc >= m.W64) continue;
+                    adj = tile_blocked_abs(m, layer, nr, nc);
+                }
+            }
+            if (adj) {
+                for (int i = 0; i < ac.mc_n && !arrived; i++) {
+                    const float2 tc = mc_tiles[ac.mc_off + i];
+                    const v2 d = {tc.x - new_pos_xz.x, tc.y - new_pos_xz.z};
+                    if (v2_len(d) <= thresh) arrived = true;
+                }
+            }
+        }
+        if (!arrived && ac.nearest_ok) {
+            const v2 d = {ac.nearest[0] - new_pos_xz.x, ac.nearest[1] - new_pos_xz.z};
+            if (v2_len(d) < thresh) arrived = true;
+        }
+    }
+    if (!arrived) {
+        // adjacent_flock_members (movement.c:953): any flock member within r + r' + ADJACENCY_SEP_DIST that has
+        // ARRIVED. The spatial index pre-selects (radius r + max radius + 5 plus slack); the test itself is
+        // the reference's float comparison, so the outcome does not depend on the pre-selection.
+        const int32_t icx = bg_scale(curr_xz.x), icy = bg_scale(curr_xz.z), ir = bg_scale(a.radius + up.adj_query_r);
+        const int cx_lo = max((icx - ir - g.origin_x) >> 12, 0), cx_hi = min((icx + ir - g.origin_x) >> 12, g.grid_w - 1);
+        const int cy_lo = max((icy - ir - g.origin_y) >> 12, 0), cy_hi = min((icy + ir - g.origin_y) >> 12, g.grid_h - 1);
+        for (int cy = cy_lo; cy <= cy_hi && !arrived; cy++)
+            for (int cx = cx_lo; cx <= cx_hi && !arrived; cx++) {
+                const int c = cy * g.grid_w + cx;
+                const uint32_t b = g.cell_start[c], cnt = g.cell_count[c];
+                for (uint32_t k = 0; k < cnt; k++) {
+                    const uint32_t o = g.id[b + k];
+                    if (o == uid) continue;
+                    const pf_record r = rec[o];
+                    if ((r.state_flags >> 24) != PFNAV_STATE_ARRIVED) continue;
+                    if (agents[o].flock != a.flock) continue;
+                    const v2 d = {curr_xz.x - r.px, curr_xz.z - r.pz};
+                    if (v2_len(d) <= a.radius + r.radius + 5.0f) { arrived = true; break; }
+                }
+            }
+    }
+    if (arrived) {
+        p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
+    } else if (v2_len(vdes) < EPS) {
+        p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_WAITING; p.next_block = 1;
+    }
+    out[wi] = p;
+}
+
+// entity_apply_update (movement.c:2693-2757), movestate fields only
+__global__ void k_entity_apply(pfnav_agent *__restrict__ agents, pfnav_movestate *__restrict__ mss,
+                               pf_record *__restrict__ rec, const uint32_t *__restrict__ work, int nwork,
+                               const pfnav_patch *__restrict__ patches)
+{
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwork) return;
+    const uint32_t uid = work[wi];
+    const pfnav_patch p = patches[wi];
+    pfnav_agent a = agents[uid];
+    pfnav_movestate ms = mss[uid];
+    const float EPS = 1.0f / 1024;
+    if (a.flags & PFNAV_FLAG_GARRISONED) return;
+    if (p.flags & PFNAV_UPDATE_SET_STATE) {
+        a.state = (uint32_t)p.next_state;
+        if (p.next_state == PFNAV_STATE_ARRIVED || p.next_state == PFNAV_STATE_WAITING) {
+            a.velocity[0] = 0.0f; a.velocity[1] = 0.0f;      // entity_finish_moving (movement.c:685)
+        }
+    }
+    if (p.flags & PFNAV_UPDATE_SET_VELOCITY) {
+        a.velocity[0] = p.next_velocity[0]; a.velocity[1] = p.next_velocity[1];
+        if (p.flags & PFNAV_UPDATE_TURNING_IN_PLACE) {
+            for (int i = 0; i < PFNAV_VEL_HIST_LEN; i++) { ms.vel_hist[i][0] = 0.0f; ms.vel_hist[i][1] = 0.0f; }
+        } else {
+            bool empty = true;
+            for (int i = 0; i < PFNAV_VEL_HIST_LEN; i++)
+                if (sqrtf(ms.vel_hist[i][0] * ms.vel_hist[i][0] + ms.vel_hist[i][1] * ms.vel_hist[i][1]) > EPS) empty = false;
+            const float vl = sqrtf(a.velocity[0] * a.velocity[0] + a.velocity[1] * a.velocity[1]);
+            if (empty && vl > EPS) {
+                // seed_vel_hist_facing (movement.c:2046) / facing_dir (:2040)
+                const float theta = (float)(2.0 * atan2((double)ms.next_rot[1], (double)ms.next_rot[3]));
+                const float dx = (float)(-sin((double)theta)), dz = (float)cos((double)theta);
+                for (int i = 0; i < PFNAV_VEL_HIST_LEN; i++) { ms.vel_hist[i][0] = dx * vl; ms.vel_hist[i][1] = dz * vl; }
+            }
+            ms.vel_hist[ms.vel_hist_idx][0] = a.velocity[0]; ms.vel_hist[ms.vel_hist_idx][1] = a.velocity[1];
+            ms.vel_hist_idx = (ms.vel_hist_idx + 1) % PFNAV_VEL_HIST_LEN;
+        }
+    }
+    if (p.flags & PFNAV_UPDATE_SET_POSITION) { a.pos[0] = p.next_pos[0]; a.pos[1] = p.next_pos[2]; }
+    if (p.flags & PFNAV_UPDATE_SET_PREV_POS) { a.prev_pos[0] = p.next_ppos[0]; a.prev_pos[1] = p.next_ppos[2]; }
+    if (p.flags & PFNAV_UPDATE_SET_NEXT_POS) { ms.next_pos[0] = p.next_npos[0]; ms.next_pos[1] = p.next_npos[1]; ms.next_pos[2] = p.next_npos[2]; }
+    if (p.flags & PFNAV_UPDATE_SET_STEP) ms.step = p.next_step;
+    if (p.flags & PFNAV_UPDATE_SET_LEFT) ms.left = (int)p.next_left;
+    if (p.flags & PFNAV_UPDATE_SET_NEXT_ROT) { ms.next_rot[0] = p.next_nrot[0]; ms.next_rot[1] = p.next_nrot[1]; ms.next_rot[2] = p.next_nrot[2]; ms.next_rot[3] = p.next_nrot[3]; }
+    agents[uid] = a;
+    mss[uid] = ms;
+    pf_record r;
+    r.px = a.pos[0]; r.pz = a.pos[1]; r.vx = a.velocity[0]; r.vz = a.velocity[1];
+    r.radius = a.radius;
+    r.state_flags = (a.state << 24) | (a.flags & 0xFFFFFFu);
+    rec[uid] = r;
+}
+
+extern "C" int pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movestate *ms, size_t n)
+{
+    PF_ARG(ctx && ctx->d_agents && ms, "agents not uploaded / ms == NULL");
+    PF_ARG(n == ctx->n_agents, "one movestate record per uploaded agent");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if (n > ctx->cap_movestate) {
+        if ((rc = ensure(ctx->d_movestate, ctx->cap_movestate, n))) return rc;
+        ctx->cap_movestate = n;
+    }
+    PF_CUDA(cudaMemcpy(ctx->d_movestate, ms, n * sizeof(pfnav_movestate), cudaMemcpyHostToDevice));
+    ctx->movestate_set = true;
+    return PFNAV_OK;
+}
+
+static int refresh_arrival_consts(pfnav_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->arrival_valid && ctx->arrival_epoch == ctx->map_epoch) return 0;
+    const size_t nf = ctx->n_flocks, nl = (size_t)ctx->nlayers;
+    std::vector<pf_arrival_dev> dev(nf * nl);
+    std::vector<float2> tiles;
+    pf_arrival_consts c;
+    for (size_t f = 0; f < nf; f++)
+        for (size_t l = 0; l < nl; l++) {
+            pf_arrival_dev &d = dev[f * nl + l];
+            memset(&d, 0, sizeof(d));
+            if (!ctx->flock_layer_used[f * PFNAV_NAV_LAYER_MAX + l]) continue;
+            int rc = pfnav_arrival_consts(ctx, (int)l, ctx->h_flocks[f].target[0], ctx->h_flocks[f].target[1], &c);
+            if (rc) return rc;
+            d.nearest_ok = c.nearest_ok; d.nearest[0] = c.nearest[0]; d.nearest[1] = c.nearest[1];
+            d.mc_n = c.mc_n; d.mc_off = (int32_t)tiles.size();
+            for (int i = 0; i < c.mc_n; i++) tiles.push_back(make_float2(c.mc[i][0], c.mc[i][1]));
+        }
+    const size_t b0 = dev.size() * sizeof(pf_arrival_dev), b1 = std::max<size_t>(tiles.size(), 1) * sizeof(float2);
+    if (b0 + b1 > ctx->arrival_bytes) {
+        cudaFree(ctx->d_arrival); ctx->d_arrival = nullptr; ctx->arrival_bytes = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_arrival, b0 + b1));
+        ctx->arrival_bytes = b0 + b1;
+    }
+    PF_CUDA(cudaStreamSynchronize(st));
+    if (b0) PF_CUDA(cudaMemcpy(ctx->d_arrival, dev.data(), b0, cudaMemcpyHostToDevice));
+    if (!tiles.empty()) PF_CUDA(cudaMemcpy((uint8_t *)ctx->d_arrival + b0, tiles.data(), tiles.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    ctx->arrival_valid = true; ctx->arrival_epoch = ctx->map_epoch;
+    return 0;
+}
+
+extern "C" int pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream)
+{
+    PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
+    PF_ARG(ctx->movestate_set, "pfnav_agents_upload_movestate not called");
+    PF_ARG(!ctx->has_unsupported_state, "formation / surround / enter-range / turning states are outside this path");
+    if (ctx->n_work == 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pf_stream(ctx, stream);
+    int rc;
+    if (ctx->n_work > ctx->cap_patches) {
+        if ((rc = ensure(ctx->d_patches, ctx->cap_patches, ctx->n_work))) return rc;
+        ctx->cap_patches = ctx->n_work;
+    }
+    if ((rc = refresh_arrival_consts(ctx, st))) return rc;
+    if (!ctx->update_done) PF_CUDA(cudaEventCreateWithFlags(&ctx->update_done, cudaEventDisableTiming));
+    MapView m;
+    m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
+    m.chunk_w = ctx->chunk_w; m.chunk_h = ctx->chunk_h; m.map_x = ctx->map_x; m.map_z = ctx->map_z;
+    UpdateParams up;
+    up.hz = ctx->hz;
+    up.turn_rate = (float)((double)(15.0f / (float)ctx->hz) * 20.0);      // SCALED_MAX_TURN_RATE (movement.c:434)
+    up.adj_query_r = ctx->max_radius + 5.0f + 0.0625f;
+    const int nwork = (int)ctx->n_work;
+    const size_t b0 = ctx->n_flocks * (size_t)ctx->nlayers * sizeof(pf_arrival_dev);
+    k_entity_update<<<(nwork + 127) / 128, 128, 0, st>>>(m, grid_of(ctx), up, ctx->d_agents, ctx->d_records, ctx->d_movestate,
+        ctx->d_flocks, (const pf_arrival_dev *)ctx->d_arrival, (const float2 *)((const uint8_t *)ctx->d_arrival + b0),
+        ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(ctx->update_done, st));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_read_patches(pfnav_ctx *ctx, pfnav_patch *out, size_t maxout)
+{
+    PF_ARG(ctx && out && ctx->d_patches && ctx->update_done, "no update pass has run");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaEventSynchronize(ctx->update_done));
+    const size_t n = std::min(maxout, ctx->n_work);
+    PF_CUDA(cudaMemcpy(out, ctx->d_patches, n * sizeof(pfnav_patch), cudaMemcpyDeviceToHost));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream)
+{
+    PF_ARG(ctx && ctx->d_patches && ctx->update_done, "no update pass has run");
+    if (ctx->n_work == 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pf_stream(ctx, stream);
+    const int nwork = (int)ctx->n_work;
+    k_entity_apply<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_agents, ctx->d_movestate, ctx->d_records, ctx->d_work, nwork,
+                                                       ctx->d_patches);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(ctx->update_done, st));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, pfnav_movestate *ms_out, size_t maxout)
+{
+    PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaDeviceSynchronize());
+    const size_t n = std::min(maxout, ctx->n_agents);
+    if (agents_out) PF_CUDA(cudaMemcpy(agents_out, ctx->d_agents, n * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
+    if (ms_out) {
+        PF_ARG(ctx->movestate_set, "no movestate uploaded");
+        PF_CUDA(cudaMemcpy(ms_out, ctx->d_movestate, n * sizeof(pfnav_movestate), cudaMemcpyDeviceToHost));
+    }
     return PFNAV_OK;
 }

@@ -112,6 +112,18 @@ struct pfnav_ctx {
     float2 *d_vel_out = nullptr, *d_vpref_out = nullptr, *d_vdes_out = nullptr;
     uint8_t *d_los_out = nullptr;
     uint32_t *d_work_count = nullptr;
+    // state update (entity_compute_update)
+    pfnav_movestate *d_movestate = nullptr; size_t cap_movestate = 0; bool movestate_set = false;
+    pfnav_patch *d_patches = nullptr; size_t cap_patches = 0;
+    void *d_arrival = nullptr; size_t arrival_bytes = 0;     // [nflocks][nlayers] pf_arrival_dev + tile lists
+    uint64_t arrival_epoch = ~0ull; bool arrival_valid = false;
+    std::vector<uint8_t> flock_layer_used;                   // [nflocks][12]
+    std::vector<pfnav_flock> h_flocks;
+    float max_radius = 0.0f;
+    bool has_unsupported_state = false;
+    bool any_garrisoned = false;                             // G_Pos_EntsInCircleFrom filters + reorders (position.c:100)
+    uint32_t *d_nb_scratch = nullptr; size_t nb_scratch_warps = 0;
+    cudaEvent_t update_done = nullptr;
     cudaStream_t tick_stream = nullptr;
     cudaEvent_t tick_done = nullptr;
     // LOS chains of a goal batch run on their own stream so that the parts of the tick that do not read
@@ -147,6 +159,14 @@ static inline cudaError_t pf_fields_sync(pfnav_ctx *ctx)
     if (e == cudaSuccess) ctx->los_inflight = false;
     return e;
 }
+
+// per (flock, layer) constants of arrived() (movement.c:2170), see pfnav_route.cu
+#define PF_ARRIVAL_MC_MAX 256           /* FIELD_RES_R*2 + FIELD_RES_C*2 (nav.c:4721) */
+struct pf_arrival_consts {
+    int32_t nearest_ok; float nearest[2]; int32_t mc_n;
+    float mc[PF_ARRIVAL_MC_MAX][2];
+};
+int pfnav_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, pf_arrival_consts *out);
 
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
        PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };

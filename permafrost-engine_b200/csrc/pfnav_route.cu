@@ -811,3 +811,92 @@ extern "C" int pfnav_pool_get(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
     if (los_out && (*out_has & 2)) PF_CUDA(cudaMemcpy(los_out, ctx->d_pool_los + (size_t)slot * 4096, 4096, cudaMemcpyDeviceToHost));
     return PFNAV_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// arrived() support (movement.c:2170-2196): the two map searches it makes depend only on the flock
+// target and the layer, not on the entity, so they are evaluated once per (flock, layer) on the host
+// mirrors and handed to the state-update kernel as constants:
+//   * N_ClosestPathable (nav.c:4126): nearest not-blocked tile to the target, breadth-first over the
+//     4-neighbourhood in the order {0,-1} {0,+1} {-1,0} {+1,0}; result = M_Tile_Bounds corner (x, z)
+//   * N_IsMaximallyClose (nav.c:4707) -> n_closest_island_tiles (nav.c:1226, ignore_blockers = false):
+//     the tiles of the target's global island, without blockers, at the smallest Manhattan distance
+//     from the target (the target tile itself is never reported: it is marked visited up front and the
+//     {0,0} delta is skipped), as "tile centres" map_pos -/+ (abs tile index) * 4 (nav.c:4729-4732)
+// ------------------------------------------------------------------------------------------
+int pfnav_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, pf_arrival_consts *out)
+{
+    out->nearest_ok = 0; out->nearest[0] = out->nearest[1] = 0.0f; out->mc_n = 0;
+    auto it = g_routes.find(ctx);
+    if (it == g_routes.end() || layer < 0 || layer >= (int)it->second.size() || !it->second[layer].built) {
+        pfnav_set_error("pfnav_agents_compute_updates: pfnav_route_build(layer %d) is needed (global islands, nav.c:1731)", layer);
+        return PFNAV_ERR_ARG;
+    }
+    const pfnav_route_layer &RL = it->second[layer];
+    tdesc t;
+    if (!desc_for_point(ctx, tx, tz, &t)) return PFNAV_OK;       // target outside the map: the reference asserts
+    const int cw = ctx->chunk_w, chh = ctx->chunk_h, W = cw * 64, H = chh * 64;
+    auto blocked = [&](int ar, int ac) {
+        const int ch = (ar >> 6) * cw + (ac >> 6), tt = (ar & 63) * 64 + (ac & 63);
+        return L_cost(ctx, layer, ch)[tt] == 0xFF || L_blk(ctx, layer, ch)[tt] > 0;
+    };
+    const int tr = t.chunk_r * 64 + t.tile_r, tc = t.chunk_c * 64 + t.tile_c;
+    // ---- N_ClosestPathable ----
+    if (!blocked(tr, tc)) {
+        out->nearest_ok = 1; out->nearest[0] = tx; out->nearest[1] = tz;
+    } else {
+        std::vector<uint8_t> vis((size_t)W * H, 0);
+        std::vector<int> q; q.push_back(tr * W + tc);
+        for (size_t qi = 0; qi < q.size(); qi++) {
+            const int ar = q[qi] / W, ac = q[qi] % W;
+            if (!blocked(ar, ac)) {
+                // M_Tile_Bounds (tile.c:356): x decreases with the column, z increases with the row
+                out->nearest_ok = 1;
+                out->nearest[0] = (ctx->map_x - (float)((ac >> 6) * 256)) - (float)((ac & 63) * 4);
+                out->nearest[1] = (ctx->map_z + (float)((ar >> 6) * 256)) + (float)((ar & 63) * 4);
+                break;
+            }
+            const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+            for (int e = 0; e < 4; e++) {
+                const int nr = ar + dr[e], nc = ac + dc[e];
+                if (nr < 0 || nr >= H || nc < 0 || nc >= W) continue;
+                if (vis[(size_t)nr * W + nc]) continue;
+                vis[(size_t)nr * W + nc] = 1;
+                q.push_back(nr * W + nc);
+            }
+        }
+    }
+    // ---- n_closest_island_tiles(target, giid(target), ignore_blockers = false, maxout = 256) ----
+    {
+        const uint16_t giid = RL.islands[(size_t)(t.chunk_r * cw + t.chunk_c) * 4096 + t.tile_r * 64 + t.tile_c];
+        std::vector<uint8_t> vis((size_t)W * H, 0);
+        std::vector<int> q; q.push_back(tr * W + tc);
+        vis[(size_t)tr * W + tc] = 1;
+        int first_mh = -1, n = 0;
+        bool done = false;
+        for (size_t qi = 0; qi < q.size() && !done; qi++) {
+            const int ar = q[qi] / W, ac = q[qi] % W;
+            const int dr[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1}, dc[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+            for (int e = 0; e < 9; e++) {
+                const int nr = ar + dr[e], nc = ac + dc[e];
+                if (nr < 0 || nr >= H || nc < 0 || nc >= W) continue;
+                if (vis[(size_t)nr * W + nc]) continue;
+                const int ch = (nr >> 6) * cw + (nc >> 6), tt = (nr & 63) * 64 + (nc & 63);
+                bool skip = RL.islands[(size_t)ch * 4096 + tt] != giid;
+                if (L_blk(ctx, layer, ch)[tt] > 0) skip = true;
+                const int mh = abs(tr - nr) + abs(tc - nc);
+                if (first_mh > 0 && mh > first_mh) { done = true; break; }
+                if (!skip) {
+                    out->mc[n][0] = ctx->map_x - (float)nc * 4.0f;      // (chunk_c*64 + tile_c) * tile_dims.x
+                    out->mc[n][1] = ctx->map_z + (float)nr * 4.0f;
+                    n++;
+                    if (first_mh == -1) first_mh = mh;
+                    if (n == PF_ARRIVAL_MC_MAX) { done = true; break; }
+                }
+                vis[(size_t)nr * W + nc] = 1;
+                q.push_back(nr * W + nc);
+            }
+        }
+        out->mc_n = n;
+    }
+    return PFNAV_OK;
+}

@@ -178,3 +178,62 @@ def tile_attr_case(cw, ch, seed, terrain=False):
         t[r, c, 3] = rng.integers(1, 3)
     t[..., 0] &= (rng.random((H, W)) > 0.03).astype(np.int32)
     return t
+
+
+def dir_quat(v):
+    """dir_quat_from_velocity (movement.c:1411), float64 maths is fine for INPUT generation"""
+    ang = np.arctan2(v[..., 1], v[..., 0]) - np.pi / 2
+    q = np.zeros(v.shape[:-1] + (4,), np.float32)
+    q[..., 1] = np.sin(ang / 2); q[..., 3] = np.cos(ang / 2)
+    return q
+
+
+def update_case(seed, hz):
+    """Agents + movestate for the state-update pass (entity_compute_update, movement.c:2303):
+    flock 0 aims at its own centre (arrivals, adjacent-arrived cascade, closest-pathable clause),
+    flock 1 aims into an obstacle, random facings trip the heading gate, some histories are empty,
+    a few agents are combat-held / garrisoned / have no desired velocity."""
+    cw = 3
+    p, cost, a = agent_case(cw, 1500, 3, seed, 0.03, 2.6)
+    rng = np.random.default_rng(seed + 1000)
+    n = len(a["radius"])
+    img = synth.blocked_to_image(cost, cw, cw)
+    # flock 0 -> centre of its own disc; flock 1 -> the impassable tile nearest to its disc centre
+    c0 = a["pos"][a["flock_of"] == 0].mean(axis=0)
+    a["flock_target"][0] = c0
+    c1 = a["pos"][a["flock_of"] == 1].mean(axis=0)
+    imp = np.argwhere(img == 255)
+    if len(imp):
+        xz = np.stack([-(imp[:, 1] + 0.5) * 4.0, (imp[:, 0] + 0.5) * 4.0], axis=1)
+        a["flock_target"][1] = xz[np.argmin(((xz - c1) ** 2).sum(axis=1))]
+    tgt = a["flock_target"][a["flock_of"]]
+    d = tgt - a["pos"]
+    dist = np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-3)
+    a["vel"] = (d / dist * (0.5 * a["max_speed"][:, None] / hz)).astype(np.float32)
+    a["vel"][rng.random(n) < 0.1] *= np.float32(0.05)
+    a["vel"][rng.random(n) < 0.05] = 0.0
+    a["prev_pos"] = (a["pos"] - a["vel"]).astype(np.float32)
+    # ARRIVED members start the adjacent-arrived cascade (movement.c:2457): many in flock 0, none in 1, few in 2
+    st = np.zeros(n, np.int32)
+    u = rng.random(n)
+    st[(a["flock_of"] == 0) & (u < 0.05)] = 2
+    st[(a["flock_of"] == 2) & (u < 0.004)] = 2
+    a["state"] = st
+    fl = a["flags"].copy()
+    fl[rng.random(n) < 0.03] |= capi.FLAG_COMBAT_HELD
+    fl[rng.random(n) < 0.01] |= capi.FLAG_GARRISONED
+    a["flags"] = fl
+    ms = np.zeros(n, capi.MOVESTATE)
+    ms["next_pos"][:, 0] = a["pos"][:, 0]; ms["next_pos"][:, 2] = a["pos"][:, 1]
+    ms["step"] = 1.0 / (20 // hz)
+    ms["left"] = 0 if hz == 20 else (rng.random(n) < 0.3).astype(np.int32)
+    face = np.where(np.linalg.norm(a["vel"], axis=1, keepdims=True) > 1e-3, a["vel"], d / dist)
+    ang = rng.uniform(-2.4, 2.4, n) * (rng.random(n) < 0.5)
+    rot = np.stack([face[:, 0] * np.cos(ang) - face[:, 1] * np.sin(ang), face[:, 0] * np.sin(ang) + face[:, 1] * np.cos(ang)], axis=1)
+    ms["next_rot"] = dir_quat(rot)
+    ms["combat_facing"] = dir_quat(rng.normal(size=(n, 2)))
+    hist = np.repeat(a["vel"][:, None, :], 14, axis=1) + rng.normal(scale=0.02, size=(n, 14, 2))
+    hist[rng.random(n) < 0.3] = 0.0
+    ms["vel_hist"] = hist.astype(np.float32)
+    ms["vel_hist_idx"] = rng.integers(0, 14, n)
+    return p, cost, a, ms

@@ -154,7 +154,49 @@ def gen_tiles():
     np.savez_compressed(os.path.join(HERE, "tiles.npz"), **out)
 
 
+def gen_update(name, seed, hz):
+    """entity_compute_update (movement.c:2303) + the movestate part of entity_apply_update (:2693)"""
+    cw = 3
+    p, cost, a, ms = cases.update_case(seed, hz)
+    nflocks = len(a["flock_target"])
+    ref = pfref.RefMap(cw, cw, p)
+    dest_ids = []
+    for f in range(nflocks):
+        src = a["pos"][np.argmax(a["flock_of"] == f)]
+        tgt = a["flock_target"][f]
+        ok, did = ref.request_path((float(src[0]), float(src[1])), (float(tgt[0]), float(tgt[1])))
+        dest_ids.append(did if ok else ref.dest_id((float(tgt[0]), float(tgt[1]))))
+    ref.agents_set(a["pos"], a["prev_pos"], a["vel"], a["radius"], a["max_speed"], a["state"], a["flags"],
+                   a["flock_of"], a["flock_target"], np.array(dest_ids, np.uint32), hz=hz)
+    ref.movestate_set(ms["next_pos"][:, [0, 2]], ms["next_rot"], ms["step"], ms["left"], ms["vel_hist"],
+                      ms["vel_hist_idx"], np.zeros(len(ms), np.int32), np.zeros(len(ms), np.int32), ms["combat_facing"])
+    work = np.nonzero((a["state"] != 2) & (a["state"] != 4))[0].astype(np.uint32)
+    vdes = np.zeros((len(work), 2), np.float32); los = np.zeros(len(work), np.uint8)
+    for _pass in range(2):
+        for f in range(nflocks):
+            sel = np.nonzero(a["flock_of"][work] == f)[0]
+            if len(sel) == 0:
+                continue
+            v, l = ref.desired_velocity(dest_ids[f], a["pos"][work[sel]], a["prev_pos"][work[sel]], a["flock_target"][f])
+            vdes[sel] = v; los[sel] = l
+    rng = np.random.default_rng(seed)
+    vdes[rng.random(len(work)) < 0.03] = 0.0          # "navigation cannot guide the entity any closer" -> WAITING
+    ref.work_set(work, vdes, los, a["speed"][work])
+    vel, _ = ref.velocity_work(1)
+    oi, of = ref.compute_updates(vel)
+    hist, hidx = ref.apply_velocity_patch(of[:, 0:2], oi[:, 0])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pathable=p, cost=cost,
+                        **{"a_" + k: v for k, v in a.items() if isinstance(v, np.ndarray)},
+                        ms=ms.view(np.uint8), work=work, vdes=vdes, los=los, vel=vel, patch_i=oi, patch_f=of,
+                        hist=hist, hidx=hidx, hz=np.int32(hz))
+    print(name, "flags histogram", {int(k): int(v) for k, v in zip(*np.unique(oi[:, 0], return_counts=True))},
+          "states", {int(k): int(v) for k, v in zip(*np.unique(oi[:, 1], return_counts=True))})
+    ref.close()
+
+
 if __name__ == "__main__":
+    gen_update("update_hz20", 61, 20)
+    gen_update("update_hz10", 62, 10)
     gen_tiles()
     gen_route()
     gen_flow_tile()

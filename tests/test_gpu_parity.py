@@ -476,3 +476,50 @@ def test_cost_from_tiles_golden(nav, pforacle):
         ports = nav.portals(0)
         assert len(ports) == len(g[f"portals{k}"])
         assert (ports[:, :9] == g[f"portals{k}"][:, :9]).all()
+
+
+@pytest.mark.parametrize("name", ["update_hz20", "update_hz10"])
+def test_entity_update_golden(nav, name):
+    """a-8: entity_compute_update patches (movement.c:2303) and the movestate part of entity_apply_update
+    (movement.c:2693) against the compiled reference: flags / states identical, floats within 1e-4."""
+    g = gold(name)
+    hz = int(g["hz"])
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    ms = g["ms"].view(capi.MOVESTATE)
+    work = g["work"]
+    nav.map_create(3, 3, 1); nav.map_upload_layer(0, g["cost"]); nav.map_build_nav(0); nav.route_build(0)
+    nav.agents_upload(rec, fl, hz)
+    nav.agents_upload_movestate(ms)
+    nav.agents_set_work(work)
+    nav.agents_tick(0)
+    vel = nav.agents_read_velocities(len(work))
+    assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995
+    nav.agents_compute_updates()
+    p = nav.agents_read_patches(len(work))
+    oi, of = g["patch_i"], g["patch_f"]
+    # discrete outcome: identical wherever the input velocity itself was within tolerance
+    good = cases.relerr(vel, g["vel"]) <= VEL_RTOL
+    same = (p["flags"] == oi[:, 0].astype(np.uint32)) & (p["next_state"] == oi[:, 1]) & (p["next_block"] == oi[:, 2])
+    assert same[good].mean() >= 0.998, (same[good].mean(), np.nonzero(~same & good)[0][:10])
+    sel = same & good
+    got = np.concatenate([p["next_velocity"], p["next_pos"], p["next_rot"], p["next_ppos"], p["next_npos"],
+                          p["next_step"][:, None], p["next_left"][:, None], p["next_nrot"], p["next_prot"]], axis=1)
+    exp = of[:, :25]
+    err = np.abs(got[sel] - exp[sel]) / np.maximum(np.abs(exp[sel]), 1.0)
+    assert err.max() <= 1e-4, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    # every transition kind is present in the fixture
+    assert {-1, 2, 4} <= set(np.unique(oi[:, 1]).tolist())
+    # device-side apply: velocity history + interpolation fields
+    nav.agents_apply_updates()
+    a2, ms2 = nav.agents_read_state(len(rec))
+    herr = np.abs(ms2["vel_hist"][work][sel] - g["hist"][sel]).max()
+    assert herr <= 1e-4, herr
+    assert (ms2["vel_hist_idx"][work][sel] == g["hidx"][sel]).all()
+    setpos = sel & ((oi[:, 0] & 4) != 0) & ((a["flags"][work] & capi.FLAG_GARRISONED) == 0)
+    assert np.abs(a2["pos"][work][setpos] - of[setpos][:, [2, 4]]).max() <= 1e-3
+    # entity_apply_update skips garrisoned entities altogether (movement.c:2697)
+    garr = (a["flags"][work] & capi.FLAG_GARRISONED) != 0
+    setst = sel & ((oi[:, 0] & 1) != 0) & ~garr
+    assert (a2["state"][work][setst] == oi[setst, 1]).all()
+    assert (a2["state"][work][garr] == a["state"][work][garr]).all()

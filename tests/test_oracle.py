@@ -102,6 +102,22 @@ def test_port_agents_golden(pforacle, name, cw):
     w.close()
 
 
+@pytest.mark.parametrize("name", ["update_hz20", "update_hz10"])
+def test_port_velocity_with_garrisoned_and_los_golden(pforacle, name):
+    """the state-update fixtures also pin the velocity pass where the older ones are blind: agents with
+    line of sight next to their goal, zero-velocity movers, COMBAT_HELD units, and GARRISONED entities,
+    which G_Pos_EntsInCircleFrom swap-removes from every radius query (position.c:100-119, 379)"""
+    g = gold(name)
+    a = _agents_from_gold(g)
+    assert (a["flags"] & capi.FLAG_GARRISONED).any() and g["los"].any()
+    rec, fl = capi.pack_agents(a)
+    om = pforacle.OracleMap(3, 3, g["cost"])
+    w = pforacle.OracleWorld(om, rec, fl, int(g["hz"]))
+    vel, _ = w.velocity_work(g["work"])
+    assert (cases.relerr(vel, g["vel"]) <= 1e-6).all()
+    w.close()
+
+
 def test_port_desired_velocity_golden(pforacle):
     g = gold("agents_3x3")
     a = _agents_from_gold(g)
