@@ -651,10 +651,41 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
     int best_idx = 0x7fffffff;
     v2 best_p = {0.0f, 0.0f};
     int any = 0, qn = 0;
-    const int npairs = n_rays * n_rays, ntotal = npairs + n_rays;
+    const int npairs = n_rays * n_rays;
+    // Exact pruning: compute_vnew (clearpath.c:368) keeps the admissible candidate nearest to des_v (first
+    // one on ties), so a candidate that is certainly farther than an admissible candidate already found
+    // can neither win nor change the tie-break and need not be tested against the obstacles at all. The
+    // projection points of compute_vdes_proj_points (sequence indices npairs..npairs+n_rays-1) are the
+    // nearest points of each ray to des_v: they are drained FIRST to get a tight bound, then the ray-pair
+    // intersections are filtered against the warp-wide bound before they enter the queue.
+    for (int base = 0; base < n_rays; base += 32) {
+        const int r = base + (int)lane;
+        const bool ok = r < n_rays;
+        if (ok) {
+            const v2 d = {s.rdx[r], s.rdz[r]};
+            const float len = v2_dot(d, des_v);
+            const v2 p = v2_add(v2{s.rpx[r], s.rpz[r]}, v2_scale(d, len));
+            s.cqx[qn + (int)lane] = p.x; s.cqz[qn + (int)lane] = p.z; s.cqk[qn + (int)lane] = npairs + r;
+        }
+        qn += min(32, n_rays - base);
+        if (qn > CQ_CAP - 32 || base + 32 >= n_rays) {
+            __syncwarp();
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            __syncwarp();
+            qn = 0;
+        }
+    }
+    float bound2 = __int_as_float(0x7f800000);
+    auto refresh_bound = [&]() {
+        float b = best;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) b = fminf(b, __shfl_xor_sync(FULL, b, off));
+        bound2 = b * b * 1.00001f;              // margin >> float rounding of the two squared lengths
+    };
+    refresh_bound();
     int i = 0, j = (int)lane;                   // pair index of this lane: k = i * n_rays + j
     while (j >= n_rays) { j -= n_rays; i++; }
-    for (int base = 0; base < ntotal; base += 32) {
+    for (int base = 0; base < npairs; base += 32) {
         const int k = base + (int)lane;
         v2 p = {0.f, 0.f};
         bool ok = false;
@@ -663,16 +694,12 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
                 // C_RayRayIntersection2D (collision.c:854)
                 const v2 p1 = {s.rpx[i], s.rpz[i]}, p2 = {s.rpx[j], s.rpz[j]};
                 if (line_isect_s(p1, s.rsl[i], p2, s.rsl[j], p)) {
-                    ok = !(quot_lt0(p.x - p1.x, s.rdx[i]) || quot_lt0(p.z - p1.z, s.rdz[i]) ||
+                    const float ddx = des_v.x - (p.x - ent.pos.x), ddz = des_v.z - (p.z - ent.pos.z);
+                    ok = !(ddx * ddx + ddz * ddz > bound2) &&
+                         !(quot_lt0(p.x - p1.x, s.rdx[i]) || quot_lt0(p.z - p1.z, s.rdz[i]) ||
                            quot_lt0(p.x - p2.x, s.rdx[j]) || quot_lt0(p.z - p2.z, s.rdz[j]));
                 }
             }
-        } else if (k < ntotal) {
-            const int r = k - npairs;
-            const v2 d = {s.rdx[r], s.rdz[r]};
-            const float len = v2_dot(d, des_v);
-            p = v2_add(v2{s.rpx[r], s.rpz[r]}, v2_scale(d, len));
-            ok = true;
         }
         const uint32_t m = __ballot_sync(FULL, ok);
         if (ok) {
@@ -682,11 +709,12 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
         qn += __popc(m);
         j += 32;
         while (j >= n_rays) { j -= n_rays; i++; }
-        if (qn > CQ_CAP - 32 || base + 32 >= ntotal) {
+        if (qn > CQ_CAP - 32 || base + 32 >= npairs) {
             __syncwarp();
             drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
             __syncwarp();
             qn = 0;
+            refresh_bound();
         }
     }
     any = __any_sync(FULL, any);
