@@ -160,6 +160,17 @@ typedef struct pfnav_field_req {
 int  pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *reqs, size_t n,
                               uint8_t *inout_fields);
 
+/* Repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554) for an entity standing on a tile whose
+ * cached direction is FD_NONE, applied in place to HOST fields (4096 bytes each):
+ *   PFNAV_REPAIR_NEAREST_PATHABLE  N_FlowFieldUpdateToNearestPathable (field.c:2247): args[i] =
+ *       start_r << 8 | start_c, a NON-passable tile of the chunk; directions lead out of the blocked blob
+ *   PFNAV_REPAIR_ISLAND_TO_NEAREST N_FlowFieldUpdateIslandToNearest (field.c:2307): args[i] = the local
+ *       island id cut off from the field's frontier; needs pfnav_route_build(layer) (global islands)
+ * targets[i] = the request that built field i (its chunk, layer and target). */
+enum pfnav_repair_kind { PFNAV_REPAIR_NEAREST_PATHABLE = 0, PFNAV_REPAIR_ISLAND_TO_NEAREST = 1 };
+int  pfnav_flow_fields_repair(pfnav_ctx *ctx, const pfnav_field_req *targets, const int32_t *kinds,
+                              const int32_t *args, size_t n, uint8_t *inout_fields);
+
 /* Same, DEVICE-resident reqs / fields, asynchronous on `stream`. */
 int  pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n,
                                   uint8_t *d_inout_fields, void *stream);

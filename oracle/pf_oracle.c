@@ -877,3 +877,177 @@ void pfo_cost_from_tiles(int chunk_w, int chunk_h, const int32_t *attrs, int ref
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554) for an entity standing on a tile whose
+ * cached flow direction is FD_NONE although a path exists.
+ * ---------------------------------------------------------------------------------------- */
+
+/* N_FlowFieldUpdateToNearestPathable (field.c:2247): the entity sits on a non-passable tile. Frontier =
+ * the passable tiles that border the impassable blob containing `start` (field_passable_frontier,
+ * field.c:1441: 4-connected flood over non-passable tiles, chunk-local); Dijkstra over NON-passable
+ * tiles only (field_build_integration_nonpass, field.c:643: edge weight = cost_base of the tile
+ * entered); directions are written for 0 < cost < INF only. */
+void pfo_flow_update_nearest_pathable(const pfo_map *m, int cr, int cc, int start_r, int start_c, uint8_t *inout)
+{
+    float intf[RES][RES];
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) intf[r][c] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    {
+        static const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+        bool visited[RES][RES]; memset(visited, 0, sizeof(visited));
+        int q[RES * RES][2], head = 0, tail = 0;
+        q[tail][0] = start_r; q[tail][1] = start_c; tail++;
+        visited[start_r][start_c] = true;
+        while(head < tail) {
+            int r = q[head][0], c = q[head][1]; head++;
+            if(tile_passable(m, cr, cc, r, c)) {
+                pq_push(&frontier, 0.0f, r, c);
+                intf[r][c] = 0.0f;
+                continue;
+            }
+            for(int e = 0; e < 4; e++) {
+                int ar = r + dr[e], ac = c + dc[e];
+                if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+                if(visited[ar][ac]) continue;
+                visited[ar][ac] = true;
+                q[tail][0] = ar; q[tail][1] = ac; tail++;
+            }
+        }
+    }
+    const uint8_t *cost = chunk_cost(m, cr, cc);
+    while(frontier.size > 0) {
+        int r, c; pq_pop(&frontier, &r, &c);
+        for(int dr = -1; dr <= 1; dr++) {
+        for(int dc = -1; dc <= 1; dc++) {
+            int ar = r + dr, ac = c + dc;
+            if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+            if(dr == 0 && dc == 0) continue;
+            if(dr == dc || dr == -dc) continue;
+            if(tile_passable(m, cr, cc, ar, ac)) continue;
+            float total = intf[r][c] + cost[ar * RES + ac];
+            if(total < intf[ar][ac]) { intf[ar][ac] = total; pq_push(&frontier, total, ar, ac); }
+        }}
+    }
+    pq_free(&frontier);
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) {
+        if(intf[r][c] == INFINITY || intf[r][c] == 0.0f) continue;
+        inout[r * RES + c] = (uint8_t)flow_dir((const float(*)[RES])intf, r, c);
+    }
+}
+
+/* field_closest_tiles_local (field.c:1010): breadth-first rings around `target` inside the chunk; the
+ * tiles of the first Manhattan ring that holds a passable, unblocked tile of the wanted islands. */
+static int closest_tiles_local(const pfo_map *m, const uint16_t *gisl, int cr, int cc, int tr, int tc,
+                               uint16_t local_iid, uint16_t global_iid, int (*out)[2], int maxout)
+{
+    static const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+    bool visited[RES][RES]; memset(visited, 0, sizeof(visited));
+    int q[RES * RES][2], head = 0, tail = 0, ret = 0, first = -1;
+    q[tail][0] = tr; q[tail][1] = tc; tail++;
+    visited[tr][tc] = true;
+    const uint8_t *cost = chunk_cost(m, cr, cc);
+    const uint16_t *gi = gisl + ((size_t)cr * m->chunk_w + cc) * 4096;
+    while(head < tail) {
+        int r = q[head][0], c = q[head][1]; head++;
+        for(int e = 0; e < 4; e++) {
+            int ar = r + dr[e], ac = c + dc[e];
+            if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+            if(visited[ar][ac]) continue;
+            visited[ar][ac] = true;
+            q[tail][0] = ar; q[tail][1] = ac; tail++;
+        }
+        int mh = abs(tr - r) + abs(tc - c);
+        if(first > -1 && mh > first) break;
+        if(cost[r * RES + c] == COST_IMPASSABLE) continue;
+        if(chunk_blk(m, cr, cc, r, c) > 0) continue;
+        if(global_iid != ISLAND_NONE && gi[r * RES + c] != global_iid) continue;
+        if(local_iid != ISLAND_NONE && chunk_liid(m, cr, cc, r, c) != local_iid) continue;
+        if(first == -1) first = mh;
+        out[ret][0] = r; out[ret][1] = c; ret++;
+        if(ret == maxout) break;
+    }
+    return ret;
+}
+
+/* N_FlowFieldUpdateIslandToNearest (field.c:2307) for TARGET_TILE / TARGET_PORTAL fields: the entity's
+ * local island was cut off from the field's frontier by blockers. New frontier = the tiles of that
+ * island nearest (Manhattan) to the original frontier; then the ordinary integration + flow + fixup.
+ * q = the request that built the field (its target); gisl = global islands [chunks][64][64]. */
+void pfo_flow_update_island_to_nearest(const pfo_map *m, const uint16_t *gisl, const pfo_field_req *q,
+                                       uint16_t local_iid, uint8_t *inout)
+{
+    const int cr = q->chunk_r, cc = q->chunk_c;
+    int init[RES * RES][2], ninit = 0;
+    if(q->target_type == TARGET_TILE) {
+        /* field_tile_initial_frontier (field.c:1096), then again with ignoreblock (field.c:2367) */
+        init[0][0] = q->tile_r; init[0][1] = q->tile_c; ninit = 1;
+    }else{
+        for(int r = q->port_r0; r <= q->port_r1; r++) {
+        for(int c = q->port_c0; c <= q->port_c1; c++) {
+            if(!tile_passable(m, cr, cc, r, c)) continue;
+            if(q->port_iid != ISLAND_NONE && chunk_liid(m, cr, cc, r, c) != q->port_iid) continue;
+            bool adj = false;
+            for(int r2 = q->next_r0; r2 <= q->next_r1 && !adj; r2++) {
+            for(int c2 = q->next_c0; c2 <= q->next_c1; c2++) {
+                int dr = (q->next_chunk_r * RES + r2) - (cr * RES + r);
+                int dc = (q->next_chunk_c * RES + c2) - (cc * RES + c);
+                if(abs(dr) + abs(dc) == 1 && chunk_liid(m, q->next_chunk_r, q->next_chunk_c, r2, c2) == q->next_iid) {
+                    adj = true; break;
+                }
+            }}
+            if(!adj) continue;
+            init[ninit][0] = r; init[ninit][1] = c; ninit++;
+        }}
+    }
+    const uint16_t *gi = gisl + ((size_t)cr * m->chunk_w + cc) * 4096;
+    int min_mh = INT32_MAX, nnew = 0;
+    static int newf[RES * RES][2], tmp[RES * RES][2];
+    for(int i = 0; i < ninit; i++) {
+        int r = init[i][0], c = init[i][1];
+        uint16_t cg = gi[r * RES + c], cl = chunk_liid(m, cr, cc, r, c);
+        if(cl == local_iid) {
+            if(min_mh > 0) nnew = 0;
+            min_mh = 0;
+            newf[nnew][0] = r; newf[nnew][1] = c; nnew++;
+            continue;
+        }
+        int nextra = closest_tiles_local(m, gisl, cr, cc, r, c, local_iid, cg, tmp, RES * RES - nnew);
+        if(!nextra) continue;
+        int mh = abs(tmp[0][0] - r) + abs(tmp[0][1] - c);
+        if(mh < min_mh) { min_mh = mh; nnew = 0; }
+        if(mh > min_mh) continue;
+        memcpy(newf + nnew, tmp, nextra * sizeof(tmp[0]));
+        nnew += nextra;
+    }
+    float intf[RES][RES];
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) intf[r][c] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    for(int i = 0; i < nnew; i++) { pq_push(&frontier, 0.0f, newf[i][0], newf[i][1]); intf[newf[i][0]][newf[i][1]] = 0.0f; }
+    const uint8_t *cost = chunk_cost(m, cr, cc);
+    while(frontier.size > 0) {
+        int r, c; pq_pop(&frontier, &r, &c);
+        for(int dr = -1; dr <= 1; dr++) {
+        for(int dc = -1; dc <= 1; dc++) {
+            int ar = r + dr, ac = c + dc;
+            if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
+            if(dr == 0 && dc == 0) continue;
+            if(dr == dc || dr == -dc) continue;
+            if(!tile_passable(m, cr, cc, ar, ac)) continue;
+            float total = intf[r][c] + cost[ar * RES + ac];
+            if(total < intf[ar][ac]) { intf[ar][ac] = total; pq_push(&frontier, total, ar, ac); }
+        }}
+    }
+    pq_free(&frontier);
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) {
+        if(intf[r][c] == INFINITY) continue;
+        if(intf[r][c] == 0.0f) { inout[r * RES + c] = FD_NONE; continue; }
+        inout[r * RES + c] = (uint8_t)flow_dir((const float(*)[RES])intf, r, c);
+    }
+    if(q->target_type == TARGET_PORTAL) {
+        bool up = q->next_chunk_r < cr, down = q->next_chunk_r > cr, left = q->next_chunk_c < cc;
+        uint8_t d = up ? FD_N : down ? FD_S : left ? FD_W : FD_E;
+        for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++)
+            if(intf[r][c] == 0.0f) inout[r * RES + c] = d;
+    }
+}

@@ -69,6 +69,12 @@ void pfo_velocity_work(const pfo_world *w, const uint32_t *work, size_t nwork, f
 void pfo_desired_velocity(const pfo_map *map, const pfo_agent *agents, const pfo_flock *flocks,
                           const uint32_t *work, size_t nwork, const int32_t *slot,
                           const uint8_t *flow, const uint8_t *los, float *out_vdes, uint8_t *out_los);
+/* Repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554): in-place updates of one cached field.
+ * N_FlowFieldUpdateToNearestPathable (field.c:2247) / N_FlowFieldUpdateIslandToNearest (field.c:2307);
+ * q = the request that built the field; gisl = global islands [chunks][64][64] */
+void pfo_flow_update_nearest_pathable(const pfo_map *m, int chunk_r, int chunk_c, int start_r, int start_c, uint8_t *inout);
+void pfo_flow_update_island_to_nearest(const pfo_map *m, const uint16_t *gisl, const pfo_field_req *q,
+                                       uint16_t local_iid, uint8_t *inout);
 /* n_set_cost_for_tile + n_make_cliff_edges (nav.c:267, 431): attrs int32[chunk_h*32][chunk_w*32][4]
  * = {pathable, type, base_height, ramp_height}; ref_layer = the reference's enum nav_layer (0..11);
  * out = cost_base [chunks][64][64] */

@@ -35,6 +35,8 @@ def lib():
         L.pfo_velocity_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.pfo_desired_velocity.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfo_flow_update_nearest_pathable.argtypes = [C.POINTER(_Map)] + [C.c_int] * 4 + [C.c_void_p]
+        L.pfo_flow_update_island_to_nearest.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_uint16, C.c_void_p]
         L.pfo_cost_from_tiles.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -67,6 +69,19 @@ class OracleMap:
         buf = np.zeros((n, 64, 64), np.uint8) if inout is None else np.ascontiguousarray(inout, np.uint8).reshape(n, 64, 64).copy()
         lib().pfo_flow_fields_update(C.byref(self.m), _p(reqs), n, _p(buf))
         return buf
+
+    def flow_nearest_pathable(self, chunk, start, inout):
+        buf = np.ascontiguousarray(inout, np.uint8).reshape(-1).copy()
+        lib().pfo_flow_update_nearest_pathable(C.byref(self.m), chunk[0], chunk[1], start[0], start[1], _p(buf))
+        return buf.reshape(64, 64)
+
+    def flow_island_to_nearest(self, gisl, req, local_iid, inout):
+        """req: the FIELD_REQ record (1 element) that built the field; gisl: global islands [chunks][64][64]"""
+        buf = np.ascontiguousarray(inout, np.uint8).reshape(-1).copy()
+        gisl = np.ascontiguousarray(gisl, np.uint16)
+        req = np.ascontiguousarray(req)
+        lib().pfo_flow_update_island_to_nearest(C.byref(self.m), _p(gisl), _p(req), int(local_iid), _p(buf))
+        return buf.reshape(64, 64)
 
     def los_fields_create(self, reqs):
         reqs = np.ascontiguousarray(reqs)

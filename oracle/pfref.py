@@ -30,6 +30,8 @@ def lib():
         L.pfref_get_portal_edges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.pfref_flow_field_tile.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
         L.pfref_flow_field_portal.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+        L.pfref_flow_nearest_pathable.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        L.pfref_flow_island_to_nearest.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_request_path.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
         L.pfref_dest_id.restype = C.c_uint32
@@ -112,6 +114,20 @@ class RefMap:
         init = inout is None
         buf = np.zeros(4096, dtype=np.uint8) if init else np.ascontiguousarray(inout, dtype=np.uint8).reshape(-1).copy()
         lib().pfref_flow_field_tile(self.h, layer, chunk[0], chunk[1], tile[0], tile[1], faction, int(init), _p(buf))
+        return buf.reshape(64, 64)
+
+    def flow_nearest_pathable(self, chunk, start, inout, layer=0):
+        buf = np.ascontiguousarray(inout, dtype=np.uint8).reshape(-1).copy()
+        lib().pfref_flow_nearest_pathable(self.h, layer, chunk[0], chunk[1], start[0], start[1], _p(buf))
+        return buf.reshape(64, 64)
+
+    def flow_island_to_nearest(self, chunk, local_iid, inout, tile=None, portal=None, layer=0):
+        """portal = (portal_idx, port_iid, next_iid) or tile = (r, c): the target that built the field"""
+        buf = np.ascontiguousarray(inout, dtype=np.uint8).reshape(-1).copy()
+        t = tile if tile is not None else (0, 0)
+        pi = portal if portal is not None else (-1, 0xFFFF, 0xFFFF)
+        lib().pfref_flow_island_to_nearest(self.h, layer, chunk[0], chunk[1], t[0], t[1], pi[0], pi[1], pi[2],
+                                           int(local_iid), _p(buf))
         return buf.reshape(64, 64)
 
     def flow_portal(self, chunk, portal_idx, port_iid, next_iid, layer=0, faction=0xF, inout=None):

@@ -423,6 +423,42 @@ PFREF_EXPORT void pfref_flow_field_portal(void *m, int layer, int chunk_r, int c
     pfref_flow_pack(&ff, inout);
 }
 
+/* Repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554), applied to one field in place.
+ * N_FlowFieldUpdateToNearestPathable (field.c:2247): `start` must be a non-passable tile. */
+PFREF_EXPORT void pfref_flow_nearest_pathable(void *m, int layer, int chunk_r, int chunk_c,
+                                              int start_r, int start_c, uint8_t *inout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    struct flow_field ff;
+    ff.chunk = (struct coord){chunk_r, chunk_c};
+    pfref_flow_unpack(inout, &ff);
+    N_FlowFieldUpdateToNearestPathable(priv, layer, (struct coord){chunk_r, chunk_c},
+        (struct coord){start_r, start_c}, FACTION_ID_NONE, priv->unit_query_ctx, &ff);
+    pfref_flow_pack(&ff, inout);
+}
+
+/* N_FlowFieldUpdateIslandToNearest (field.c:2307). portal_idx < 0: the field's target is the tile
+ * (tile_r, tile_c); else the portal (portal_idx, port_iid, next_iid) of the chunk. */
+PFREF_EXPORT void pfref_flow_island_to_nearest(void *m, int layer, int chunk_r, int chunk_c,
+                                               int tile_r, int tile_c, int portal_idx, int port_iid,
+                                               int next_iid, int local_iid, uint8_t *inout)
+{
+    struct nav_private *priv = pfref_priv(m);
+    const struct nav_chunk *ch = &priv->chunks[layer][chunk_r * priv->width + chunk_c];
+    struct flow_field ff;
+    ff.chunk = (struct coord){chunk_r, chunk_c};
+    pfref_flow_unpack(inout, &ff);
+    if(portal_idx < 0) {
+        ff.target = (struct field_target){ .type = TARGET_TILE, .tile = (struct coord){tile_r, tile_c} };
+    }else{
+        const struct portal *port = &ch->portals[portal_idx];
+        ff.target = (struct field_target){ .type = TARGET_PORTAL, .pd = (struct portal_desc){
+            port, (uint16_t)port_iid, n_portal(priv, layer, port->connected), (uint16_t)next_iid } };
+    }
+    N_FlowFieldUpdateIslandToNearest((uint16_t)local_iid, priv, layer, FACTION_ID_NONE, priv->unit_query_ctx, &ff);
+    pfref_flow_pack(&ff, inout);
+}
+
 /* N_LOSFieldCreate; field.c:2085. prev may be NULL (destination chunk). */
 PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
                                   int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,

@@ -626,6 +626,87 @@ k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// K1r: repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554) on one cached field, in place.
+// One CTA per field, Bellman-Ford to the unique fixpoint like k_flow_general; the seeds come from the host
+// (pfnav_repair_seeds). kind 0 = N_FlowFieldUpdateToNearestPathable (field.c:2247): the integration runs
+// over NON-passable tiles only (field_build_integration_nonpass, field.c:643; edge weight = raw cost_base
+// of the tile entered) and only tiles with 0 < cost < INF get a direction. kind 1 =
+// N_FlowFieldUpdateIslandToNearest (field.c:2307): ordinary integration / flow / portal fixup from the
+// substitute frontier.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FLOWG_THREADS)
+k_flow_repair(FlowGrids g, const pfnav_field_req *__restrict__ reqs, const int32_t *__restrict__ kinds,
+              const uint64_t *__restrict__ seed_masks, int n, uint8_t *__restrict__ fields)
+{
+    __shared__ uint32_t dist[4096];
+    __shared__ uint8_t cost[4096];       // raw cost_base
+    __shared__ uint8_t dom[4096];        // 1 = tile takes part in the integration
+    __shared__ int changed;
+    const int tid = threadIdx.x;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const pfnav_field_req q = reqs[i];
+        const int kind = kinds[i];
+        const size_t lbase = (size_t)q.layer * g.H64 * g.W64;
+        for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+            const size_t off = lbase + (size_t)(q.chunk_r * 64 + (t >> 6)) * g.W64 + q.chunk_c * 64 + (t & 63);
+            const uint8_t c = g.cost[off];
+            const bool pass = c != 0xFF && g.blk[off] == 0;
+            const bool seed = (seed_masks[(size_t)i * 64 + (t >> 6)] >> (t & 63)) & 1;
+            cost[t] = c;
+            dom[t] = seed ? 2 : (kind == 0 ? !pass : pass) ? 1 : 0;      // 2 = seed (distance pinned at 0)
+            dist[t] = seed ? 0u : 0xFFFFFFFFu;
+        }
+        do {
+            __syncthreads();
+            if (tid == 0) changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+                if (dom[t] != 1) continue;
+                const int r = t >> 6, cc = t & 63;
+                uint32_t m = 0xFFFFFFFFu;
+                if (r > 0)   m = min(m, dist[t - 64]);
+                if (r < 63)  m = min(m, dist[t + 64]);
+                if (cc > 0)  m = min(m, dist[t - 1]);
+                if (cc < 63) m = min(m, dist[t + 1]);
+                if (m != 0xFFFFFFFFu && m + cost[t] < dist[t]) { dist[t] = m + cost[t]; ch = true; }
+            }
+            if (ch) changed = 1;
+            __syncthreads();
+        } while (changed);
+
+        const bool up = q.next_chunk_r < q.chunk_r, down = q.next_chunk_r > q.chunk_r;
+        const bool left = q.next_chunk_c < q.chunk_c;
+        const uint8_t fix = up ? 2 : down ? 7 : left ? 4 : 5;
+        uint8_t *dst = fields + (size_t)i * 4096;
+        for (int t = tid; t < 4096; t += FLOWG_THREADS) {
+            const uint32_t d = dist[t];
+            if (d == 0xFFFFFFFFu) continue;
+            if (d == 0) {
+                if (kind == 1) dst[t] = (q.target_type == PFNAV_TARGET_PORTAL) ? fix : 0;
+                continue;
+            }
+            const int r = t >> 6, c = t & 63;
+            const uint32_t INF = 0xFFFFFFFFu;
+            const uint32_t dn = r > 0 ? dist[t - 64] : INF, ds = r < 63 ? dist[t + 64] : INF;
+            const uint32_t dw = c > 0 ? dist[t - 1] : INF, de = c < 63 ? dist[t + 1] : INF;
+            const uint32_t dnw = (r > 0 && c > 0) ? dist[t - 65] : INF, dne = (r > 0 && c < 63) ? dist[t - 63] : INF;
+            const uint32_t dsw = (r < 63 && c > 0) ? dist[t + 63] : INF, dse = (r < 63 && c < 63) ? dist[t + 65] : INF;
+            uint32_t m = min(min(dn, ds), min(dw, de));
+            if (dn != INF && dw != INF) m = min(m, dnw);
+            if (dn != INF && de != INF) m = min(m, dne);
+            if (ds != INF && dw != INF) m = min(m, dsw);
+            if (ds != INF && de != INF) m = min(m, dse);
+            uint8_t dir;   // field.c:405-428 priority N,S,E,W,NW,NE,SW,SE
+            if (dn == m) dir = 2; else if (ds == m) dir = 7; else if (de == m) dir = 5; else if (dw == m) dir = 4;
+            else if (dnw == m) dir = 1; else if (dne == m) dir = 3; else if (dsw == m) dir = 6; else dir = 8;
+            dst[t] = dir;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: LOS field. One warp per field; lane 0 replays the reference heap exactly.
 // ------------------------------------------------------------------------------------------
 #define LOS_WARPS_PER_CTA 4
@@ -1431,6 +1512,47 @@ extern "C" int pfnav_flow_fields_update(pfnav_ctx *ctx, const pfnav_field_req *r
     if (rc) return rc;
     if (e != cudaSuccess || e2 != cudaSuccess) {
         pfnav_set_error("pfnav_flow_fields_update: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+// Repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554) applied to caller-held fields, in place.
+extern "C" int pfnav_flow_fields_repair(pfnav_ctx *ctx, const pfnav_field_req *targets, const int32_t *kinds,
+                                        const int32_t *args, size_t n, uint8_t *inout_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(targets && kinds && args && inout_fields, "null buffer");
+    int rc = validate_field_reqs(ctx, targets, n);
+    if (rc) return rc;
+    std::vector<uint64_t> masks(n * 64);
+    for (size_t i = 0; i < n; i++) {
+        PF_ARG(kinds[i] == PFNAV_REPAIR_NEAREST_PATHABLE || kinds[i] == PFNAV_REPAIR_ISLAND_TO_NEAREST, "repair kind");
+        if ((rc = pfnav_repair_seeds(ctx, targets[i], kinds[i], args[i], masks.data() + i * 64))) return rc;
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->tick_stream;
+    uint8_t *d_buf = nullptr;
+    const size_t b_req = n * sizeof(pfnav_field_req), b_kind = n * 4, b_mask = n * 512, b_f = n * 4096;
+    PF_CUDA(cudaMalloc(&d_buf, b_req + b_kind + b_mask + b_f));
+    uint8_t *d_req = d_buf, *d_mask = d_buf + b_req, *d_kind = d_mask + b_mask, *d_f = d_kind + b_kind;   // masks stay 8-byte aligned
+    cudaError_t e = cudaMemcpyAsync(d_req, targets, b_req, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, masks.data(), b_mask, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_kind, kinds, b_kind, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, inout_fields, b_f, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_flow_repair<<<(unsigned)std::min<size_t>(n, (size_t)ctx->sm_count * 8), FLOWG_THREADS, 0, st>>>(
+            grids_of(ctx), (const pfnav_field_req *)d_req, (const int32_t *)d_kind, (const uint64_t *)d_mask, (int)n, d_f);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(inout_fields, d_f, b_f, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_flow_fields_repair: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
         return PFNAV_ERR_CUDA;
     }
     return PFNAV_OK;

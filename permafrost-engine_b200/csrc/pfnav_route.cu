@@ -900,3 +900,115 @@ int pfnav_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, pf_arriv
     }
     return PFNAV_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Seeds of the repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554), host side (they need the
+// global islands and breadth-first ring searches over the chunk; the integration itself runs on the
+// device, k_flow_repair):
+//   kind 0  N_FlowFieldUpdateToNearestPathable (field.c:2247): the passable tiles that border the
+//           non-passable blob containing (start_r, start_c)   (field_passable_frontier, field.c:1441)
+//   kind 1  N_FlowFieldUpdateIslandToNearest (field.c:2307): the tiles of local island `local_iid`
+//           nearest (Manhattan) to the field's own frontier     (field_closest_tiles_local, field.c:1010)
+// mask: 64 rows of 64 bits.
+// ------------------------------------------------------------------------------------------
+int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int arg, uint64_t *mask)
+{
+    memset(mask, 0, 64 * sizeof(uint64_t));
+    const int layer = q.layer, cw = ctx->chunk_w;
+    const int chunk = q.chunk_r * cw + q.chunk_c;
+    const uint8_t *cost = L_cost(ctx, layer, chunk);
+    const uint16_t *blk = L_blk(ctx, layer, chunk), *liid = L_liid(ctx, layer, chunk);
+    auto passable = [&](int r, int c) { return cost[r * 64 + c] != 0xFF && blk[r * 64 + c] == 0; };
+    static const int dr4[4] = {0, 0, -1, 1}, dc4[4] = {-1, 1, 0, 0};
+    if (kind == 0) {
+        const int sr = arg >> 8, sc = arg & 0xFF;
+        PF_ARG(sr >= 0 && sr < 64 && sc >= 0 && sc < 64, "repair start tile");
+        PF_ARG(!passable(sr, sc), "N_FlowFieldUpdateToNearestPathable needs a non-passable start tile (field.c:1455)");
+        std::vector<uint8_t> vis(4096, 0);
+        std::vector<int> fq; fq.push_back(sr * 64 + sc);
+        vis[sr * 64 + sc] = 1;
+        for (size_t qi = 0; qi < fq.size(); qi++) {
+            const int r = fq[qi] >> 6, c = fq[qi] & 63;
+            if (passable(r, c)) { mask[r] |= 1ull << c; continue; }
+            for (int e = 0; e < 4; e++) {
+                const int ar = r + dr4[e], ac = c + dc4[e];
+                if (ar < 0 || ar >= 64 || ac < 0 || ac >= 64 || vis[ar * 64 + ac]) continue;
+                vis[ar * 64 + ac] = 1;
+                fq.push_back(ar * 64 + ac);
+            }
+        }
+        return PFNAV_OK;
+    }
+    // ---- kind 1 ----
+    auto it = g_routes.find(ctx);
+    PF_ARG(it != g_routes.end() && layer < (int)it->second.size() && it->second[layer].built,
+           "pfnav_route_build(layer) is needed (global islands, nav.c:1731)");
+    const uint16_t *gisl = it->second[layer].islands.data() + (size_t)chunk * 4096;
+    const uint16_t local_iid = (uint16_t)arg;
+    std::vector<int> init;
+    if ((q.target_type & 0xFF) == PFNAV_TARGET_TILE) {
+        // field_tile_initial_frontier (field.c:1096); when the tile is blocked the reference retries with
+        // ignoreblock (field.c:2367) -- either way the frontier is the tile itself
+        init.push_back(q.tile_r * 64 + q.tile_c);
+    } else {
+        const uint16_t *nliid = L_liid(ctx, layer, q.next_chunk_r * cw + q.next_chunk_c);
+        for (int r = q.port_r0; r <= q.port_r1; r++)
+            for (int c = q.port_c0; c <= q.port_c1; c++) {
+                if (!passable(r, c)) continue;
+                if (q.port_iid != PFNAV_ISLAND_NONE && liid[r * 64 + c] != q.port_iid) continue;
+                bool adj = false;
+                for (int r2 = q.next_r0; r2 <= q.next_r1 && !adj; r2++)
+                    for (int c2 = q.next_c0; c2 <= q.next_c1; c2++) {
+                        const int ddr = (q.next_chunk_r * 64 + r2) - (q.chunk_r * 64 + r);
+                        const int ddc = (q.next_chunk_c * 64 + c2) - (q.chunk_c * 64 + c);
+                        if (abs(ddr) + abs(ddc) == 1 && nliid[r2 * 64 + c2] == q.next_iid) { adj = true; break; }
+                    }
+                if (adj) init.push_back(r * 64 + c);
+            }
+    }
+    int min_mh = INT_MAX;
+    std::vector<int> newf;
+    std::vector<uint8_t> vis(4096);
+    std::vector<int> fq, tmp;
+    for (int t0 : init) {
+        const int r0 = t0 >> 6, c0 = t0 & 63;
+        const uint16_t cg = gisl[t0], cl = liid[t0];
+        if (cl == local_iid) {
+            if (min_mh > 0) newf.clear();
+            min_mh = 0;
+            newf.push_back(t0);
+            continue;
+        }
+        // field_closest_tiles_local(chunk, curr, local_iid, curr_giid)
+        std::fill(vis.begin(), vis.end(), 0);
+        fq.clear(); tmp.clear();
+        fq.push_back(t0); vis[t0] = 1;
+        int first = -1;
+        const size_t cap = 4096 - newf.size();
+        for (size_t qi = 0; qi < fq.size(); qi++) {
+            const int r = fq[qi] >> 6, c = fq[qi] & 63;
+            for (int e = 0; e < 4; e++) {
+                const int ar = r + dr4[e], ac = c + dc4[e];
+                if (ar < 0 || ar >= 64 || ac < 0 || ac >= 64 || vis[ar * 64 + ac]) continue;
+                vis[ar * 64 + ac] = 1;
+                fq.push_back(ar * 64 + ac);
+            }
+            const int mh = abs(r0 - r) + abs(c0 - c);
+            if (first > -1 && mh > first) break;
+            if (cost[r * 64 + c] == 0xFF) continue;
+            if (blk[r * 64 + c] > 0) continue;
+            if (cg != PFNAV_ISLAND_NONE && gisl[r * 64 + c] != cg) continue;
+            if (local_iid != PFNAV_ISLAND_NONE && liid[r * 64 + c] != local_iid) continue;
+            if (first == -1) first = mh;
+            tmp.push_back(r * 64 + c);
+            if (tmp.size() == cap) break;
+        }
+        if (tmp.empty()) continue;
+        const int mh = abs((tmp[0] >> 6) - r0) + abs((tmp[0] & 63) - c0);
+        if (mh < min_mh) { min_mh = mh; newf.clear(); }
+        if (mh > min_mh) continue;
+        newf.insert(newf.end(), tmp.begin(), tmp.end());
+    }
+    for (int t : newf) mask[t >> 6] |= 1ull << (t & 63);
+    return PFNAV_OK;
+}

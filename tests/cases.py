@@ -237,3 +237,42 @@ def update_case(seed, hz):
     ms["vel_hist"] = hist.astype(np.float32)
     ms["vel_hist_idx"] = rng.integers(0, 14, n)
     return p, cost, a, ms
+
+
+def repair_case(ref, cw, ch, seed, per_chunk=4):
+    """Requests for the repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554) on a map with blockers.
+    ref: a pfref.RefMap that already holds the blockers (after update()). Returns (targets FIELD_REQ[n],
+    kinds, args, base fields[n,64,64], expected[n,64,64])."""
+    rng = np.random.default_rng(seed)
+    cost, blk, liid = ref.cost_base(), ref.blockers(), ref.local_islands()
+    ports = ref.portals()
+    T, K, A, B, E = [], [], [], [], []
+    for chunk in range(cw * ch):
+        cr, cc = chunk // cw, chunk % cw
+        npass = np.argwhere((cost[chunk] != 255) & (blk[chunk] == 0))
+        nonp = np.argwhere((cost[chunk] == 255) | (blk[chunk] > 0))
+        if len(npass) == 0:
+            continue
+        bases = []
+        t = npass[rng.integers(len(npass))]
+        bases.append((capi.tile_req((cr, cc), (int(t[0]), int(t[1]))), ref.flow_tile((cr, cc), (int(t[0]), int(t[1]))),
+                      dict(tile=(int(t[0]), int(t[1])))))
+        # a blocked target tile: the frontier is empty until `ignoreblock` (field.c:2367)
+        bt = np.argwhere((cost[chunk] != 255) & (blk[chunk] > 0))
+        if len(bt):
+            t = bt[rng.integers(len(bt))]
+            bases.append((capi.tile_req((cr, cc), (int(t[0]), int(t[1]))), ref.flow_tile((cr, cc), (int(t[0]), int(t[1]))),
+                          dict(tile=(int(t[0]), int(t[1])))))
+        specs = portal_specs(ports[(ports[:, 0] == cr) & (ports[:, 1] == cc)][:2] if False else ports, liid, cw)
+        specs = [s for s in specs if s[0] == (cr, cc)][:3]
+        for s in specs:
+            bases.append((portal_reqs([s]), ref.flow_portal(s[0], s[1], s[5], s[6]), dict(portal=(s[1], s[5], s[6]))))
+        iids = [int(i) for i in np.unique(liid[chunk]) if i != 0xFFFF]
+        for req, base, kw in bases:
+            for s in (nonp[rng.integers(0, len(nonp), per_chunk)] if len(nonp) else []):
+                T.append(req); K.append(0); A.append((int(s[0]) << 8) | int(s[1])); B.append(base)
+                E.append(ref.flow_nearest_pathable((cr, cc), (int(s[0]), int(s[1])), base))
+            for iid in iids[:per_chunk + 2]:
+                T.append(req); K.append(1); A.append(iid); B.append(base)
+                E.append(ref.flow_island_to_nearest((cr, cc), iid, base, **kw))
+    return (np.concatenate(T), np.array(K, np.int32), np.array(A, np.int32), np.stack(B), np.stack(E))

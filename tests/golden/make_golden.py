@@ -194,7 +194,27 @@ def gen_update(name, seed, hz):
     ref.close()
 
 
+def gen_repair():
+    """N_FlowFieldUpdateToNearestPathable / N_FlowFieldUpdateIslandToNearest (field.c:2247, 2307) on a map whose
+    local islands were cut by blockers"""
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, 77, 0.2)
+    ref = pfref.RefMap(cw, ch, p)
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        ref.blockers_incref(float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)),
+                            float(rng.uniform(3, 14)), 0, 0)
+    ref.update()
+    T, K, A, B, E = cases.repair_case(ref, cw, ch, 9)
+    np.savez_compressed(os.path.join(HERE, "repair.npz"), pathable=p, cost=ref.cost_base(), blk=ref.blockers(),
+                        liid=ref.local_islands(), islands=ref.islands(), targets=T.view(np.uint8), kinds=K, args=A,
+                        base=B, exp=E)
+    print("repair cases", len(K), "changed tiles per case", float((B != E).reshape(len(K), -1).sum(1).mean()))
+    ref.close()
+
+
 if __name__ == "__main__":
+    gen_repair()
     gen_update("update_hz20", 61, 20)
     gen_update("update_hz10", 62, 10)
     gen_tiles()

@@ -523,3 +523,17 @@ def test_entity_update_golden(nav, name):
     setst = sel & ((oi[:, 0] & 1) != 0) & ~garr
     assert (a2["state"][work][setst] == oi[setst, 1]).all()
     assert (a2["state"][work][garr] == a["state"][work][garr]).all()
+
+
+def test_repair_chain_golden(nav, pforacle):
+    """a-4: the on-miss repair chain of N_DesiredPointSeekVelocity (nav.c:3508-3554): both field updates, tile and
+    portal targets, on a map whose local islands were cut by blockers -- bit-exact vs the compiled reference."""
+    g = gold("repair")
+    nav.map_create(2, 2, 1)
+    nav.map_upload_layer(0, g["cost"], g["blk"], g["liid"])
+    nav.map_build_nav(0); nav.route_build(0)
+    assert (nav.local_islands(0) == g["liid"]).all()
+    T = g["targets"].view(capi.FIELD_REQ)
+    got = nav.flow_fields_repair(T, g["kinds"], g["args"], g["base"])
+    bad = np.nonzero((got != g["exp"]).reshape(len(T), -1).any(axis=1))[0]
+    assert len(bad) == 0, (bad[:10], g["kinds"][bad[:10]])

@@ -47,6 +47,42 @@ def test_port_los_golden(pforacle):
     assert (got == g["los_exp"]).all()
 
 
+def _port_repair(pforacle, om, gisl, T, K, A, B):
+    out = []
+    for i in range(len(K)):
+        q = T[i:i + 1]
+        if K[i] == 0:
+            out.append(om.flow_nearest_pathable((int(q["chunk_r"][0]), int(q["chunk_c"][0])), (int(A[i]) >> 8, int(A[i]) & 255), B[i]))
+        else:
+            out.append(om.flow_island_to_nearest(gisl, q, int(A[i]), B[i]))
+    return np.stack(out)
+
+
+def test_port_repair_chain_golden(pforacle):
+    """N_FlowFieldUpdateToNearestPathable / N_FlowFieldUpdateIslandToNearest (field.c:2247, 2307)"""
+    g = gold("repair")
+    om = pforacle.OracleMap(2, 2, g["cost"], g["blk"], g["liid"])
+    T = g["targets"].view(capi.FIELD_REQ)
+    got = _port_repair(pforacle, om, g["islands"], T, g["kinds"], g["args"], g["base"])
+    assert (got == g["exp"]).all()
+    assert (g["base"] != g["exp"]).any()
+
+
+def test_port_repair_chain_vs_ref(pfref, pforacle):
+    p = cases.noise_map(3, 2, 91, 0.25)
+    ref = pfref.RefMap(3, 2, p)
+    rng = np.random.default_rng(17)
+    for _ in range(70):
+        ref.blockers_incref(float(-rng.uniform(10, 3 * 256 - 10)), float(rng.uniform(10, 2 * 256 - 10)),
+                            float(rng.uniform(2, 16)), 0, 0)
+    ref.update()
+    T, K, A, B, E = cases.repair_case(ref, 3, 2, 23, per_chunk=3)
+    om = pforacle.OracleMap(3, 2, ref.cost_base(), ref.blockers(), ref.local_islands())
+    got = _port_repair(pforacle, om, ref.islands(), T, K, A, B)
+    assert (got == E).all()
+    ref.close()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 
