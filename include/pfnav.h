@@ -276,6 +276,13 @@ int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, 
  * points order themselves after it. A caller that reads pool LOS fields through raw device pointers
  * on its own stream calls this first. */
 int  pfnav_fields_join(pfnav_ctx *ctx, void *stream);
+/* On-miss chain of N_DesiredPointSeekVelocity (nav.c:3484-3554) for the uploaded work list, against the pool:
+ * every work agent whose own tile has no direction (field absent or FD_NONE) is collected on the device; per
+ * (dest, chunk, local island | blocked tile), in work order, the host then (1) requests the path from that
+ * agent's position (n_request_path, nav.c:3486/3499 == pfnav_pool_request_path), and if the tile is still
+ * FD_NONE (2) repairs the field in place: N_FlowFieldUpdateToNearestPathable when the tile is non-passable,
+ * N_FlowFieldUpdateIslandToNearest otherwise. Blocking; needs pfnav_route_build. The caller re-runs the tick. */
+int  pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nrepairs);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls

@@ -1004,6 +1004,7 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)max_fields * 4096, 0, max_fields));
     ctx->h_pool_slot.assign(nslots, -1);
     ctx->h_pool_has.assign(max_fields, 0);
+    ctx->h_pool_req.assign(max_fields, pfnav_field_req{});
     ctx->h_pool_ffid.assign(nslots, 0);
     ctx->pool_ndests = ndests; ctx->pool_max = max_fields; ctx->pool_used = 0;
     ctx->goal_batch.valid = false;
@@ -1781,5 +1782,127 @@ extern "C" int pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, 
         PF_ARG(ctx->movestate_set, "no movestate uploaded");
         PF_CUDA(cudaMemcpy(ms_out, ctx->d_movestate, n * sizeof(pfnav_movestate), cudaMemcpyDeviceToHost));
     }
+    return PFNAV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// On-miss chain of N_DesiredPointSeekVelocity (nav.c:3484-3554) against the device field pool.
+// ------------------------------------------------------------------------------------------
+struct pf_miss { uint32_t wi, uid; int32_t dest, chunk, tile, liid; float px, pz; };
+
+// work agents whose own tile has no flow direction in the pool (field absent, or dir_idx == FD_NONE)
+__global__ void k_collect_misses(MapView m, PoolView pool, const uint16_t *__restrict__ liid_img,
+                                 const pfnav_agent *__restrict__ agents, const pfnav_flock *__restrict__ flocks,
+                                 const uint32_t *__restrict__ work, int nwork, pf_miss *__restrict__ out,
+                                 uint32_t *__restrict__ count, uint32_t cap)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    const uint32_t uid = work[w];
+    const pfnav_agent a = agents[uid];
+    if (a.flock < 0) return;
+    const pfnav_flock fl = flocks[a.flock];
+    if (fl.dest < 0 || fl.dest >= pool.ndests) return;
+    tile_desc t;
+    if (!desc_for_point(m, a.pos[0], a.pos[1], t)) return;
+    const int chunks = m.chunk_w * m.chunk_h, chunk = t.chunk_r * m.chunk_w + t.chunk_c;
+    const int s = pool.slot[(size_t)fl.dest * chunks + chunk];
+    bool miss = (s < 0) || !(pool.has[s] & 1);
+    if (!miss) miss = (pool.flow[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 0xF) == 0;
+    if (!miss) return;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k >= cap) return;
+    pf_miss r;
+    r.wi = (uint32_t)w; r.uid = uid; r.dest = fl.dest; r.chunk = chunk; r.tile = t.tile_r * 64 + t.tile_c;
+    r.liid = liid_img[((size_t)fl.layer * m.H64 + t.chunk_r * 64 + t.tile_r) * m.W64 + t.chunk_c * 64 + t.tile_c];
+    r.px = a.pos[0]; r.pz = a.pos[1];
+    out[k] = r;
+}
+
+extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nrepairs)
+{
+    PF_ARG(ctx && ctx->d_agents && ctx->d_pool_slot, "agents / pool missing");
+    if (out_nrequests) *out_nrequests = 0;
+    if (out_nrepairs) *out_nrepairs = 0;
+    if (ctx->n_work == 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
+    cudaStream_t st = ctx->tick_stream;
+    PF_CUDA(cudaDeviceSynchronize());
+    const int nwork = (int)ctx->n_work;
+    pf_miss *d_miss = nullptr; uint32_t *d_cnt = nullptr;
+    PF_CUDA(cudaMalloc(&d_miss, (size_t)nwork * sizeof(pf_miss)));
+    if (cudaMalloc(&d_cnt, 4) != cudaSuccess) { cudaFree(d_miss); pfnav_set_error("cudaMalloc"); return PFNAV_ERR_NOMEM; }
+    cudaMemsetAsync(d_cnt, 0, 4, st);
+    MapView m;
+    m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
+    m.chunk_w = ctx->chunk_w; m.chunk_h = ctx->chunk_h; m.map_x = ctx->map_x; m.map_z = ctx->map_z;
+    PoolView pv;
+    pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
+    pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
+    k_collect_misses<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_liid, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
+                                                         d_miss, d_cnt, (uint32_t)nwork);
+    ctx->launches++;
+    uint32_t cnt = 0;
+    cudaError_t e = cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    std::vector<pf_miss> miss(std::min<uint32_t>(cnt, (uint32_t)nwork));
+    if (e == cudaSuccess && !miss.empty())
+        e = cudaMemcpy(miss.data(), d_miss, miss.size() * sizeof(pf_miss), cudaMemcpyDeviceToHost);
+    cudaFree(d_miss); cudaFree(d_cnt);
+    if (e != cudaSuccess) { pfnav_set_error("pfnav_pool_repair: %s", cudaGetErrorString(e)); return PFNAV_ERR_CUDA; }
+    if (miss.empty()) return PFNAV_OK;
+    // the reference walks the entities in work order; one representative per (dest, chunk, island | tile)
+    std::sort(miss.begin(), miss.end(), [](const pf_miss &a, const pf_miss &b) { return a.wi < b.wi; });
+    std::vector<pf_miss> reps;
+    {
+        std::vector<uint64_t> seen;
+        for (const pf_miss &r : miss) {
+            const uint64_t key = ((uint64_t)r.dest << 40) | ((uint64_t)r.chunk << 20) |
+                                 (r.liid == 0xFFFF ? (0x10000u | (uint32_t)r.tile) : (uint32_t)r.liid);
+            if (std::find(seen.begin(), seen.end(), key) != seen.end()) continue;
+            seen.push_back(key);
+            reps.push_back(r);
+        }
+    }
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    // (1) n_request_path from the entity's own position (nav.c:3486, 3499)
+    int nreq = 0;
+    std::vector<int> flock_of_dest(ctx->pool_ndests, -1);
+    for (size_t f = 0; f < ctx->h_flocks.size(); f++)
+        if (ctx->h_flocks[f].dest >= 0 && ctx->h_flocks[f].dest < ctx->pool_ndests) flock_of_dest[ctx->h_flocks[f].dest] = (int)f;
+    std::vector<uint8_t> path_ok(reps.size(), 0);
+    for (size_t k = 0; k < reps.size(); k++) {
+        const pf_miss &r = reps[k];
+        const int f = flock_of_dest[r.dest];
+        if (f < 0) continue;
+        const pfnav_flock &fl = ctx->h_flocks[f];
+        int ok = 0, nf = 0, nl = 0; uint32_t did = 0;
+        int rc = pfnav_pool_request_path(ctx, r.dest, fl.layer, r.px, r.pz, fl.target[0], fl.target[1], nullptr, &did, &ok, &nf, &nl);
+        if (rc) return rc;
+        path_ok[k] = ok ? 1 : 0;        // no path from here: the reference returns a zero vector and repairs nothing (nav.c:3501)
+        if (nf + nl > 0) nreq++;
+    }
+    PF_CUDA(cudaDeviceSynchronize());
+    // (2) still FD_NONE -> repair the field in place (nav.c:3520-3546)
+    std::vector<pfnav_field_req> tg; std::vector<int32_t> kinds, args, slots;
+    for (size_t k = 0; k < reps.size(); k++) {
+        const pf_miss &r = reps[k];
+        if (!path_ok[k]) continue;
+        const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
+        if (slot < 0 || !(ctx->h_pool_has[slot] & 1)) continue;          // no path: the reference returns a zero vector
+        uint8_t dir = 0;
+        PF_CUDA(cudaMemcpy(&dir, ctx->d_pool_flow + (size_t)slot * 4096 + r.tile, 1, cudaMemcpyDeviceToHost));
+        if ((dir & 0xF) != 0) continue;                                   // case 1: the path query fixed it
+        tg.push_back(ctx->h_pool_req[slot]);
+        slots.push_back(slot);
+        if (r.liid == 0xFFFF) { kinds.push_back(PFNAV_REPAIR_NEAREST_PATHABLE); args.push_back(((r.tile >> 6) << 8) | (r.tile & 63)); }
+        else                  { kinds.push_back(PFNAV_REPAIR_ISLAND_TO_NEAREST); args.push_back(r.liid); }
+    }
+    int rc = pfnav_flow_repair_pool(ctx, tg.data(), kinds.data(), args.data(), slots.data(), tg.size());
+    if (rc) return rc;
+    if (!tg.empty() || nreq) ctx->goal_batch.valid = ctx->goal_batch.valid && tg.empty();   // pool bytes changed under a resident plan
+    if (out_nrequests) *out_nrequests = nreq;
+    if (out_nrepairs) *out_nrepairs = (int)tg.size();
     return PFNAV_OK;
 }

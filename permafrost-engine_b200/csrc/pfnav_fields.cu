@@ -636,7 +636,8 @@ k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uin
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FLOWG_THREADS)
 k_flow_repair(FlowGrids g, const pfnav_field_req *__restrict__ reqs, const int32_t *__restrict__ kinds,
-              const uint64_t *__restrict__ seed_masks, int n, uint8_t *__restrict__ fields)
+              const uint64_t *__restrict__ seed_masks, int n, uint8_t *__restrict__ fields,
+              const int32_t *__restrict__ out_slot)
 {
     __shared__ uint32_t dist[4096];
     __shared__ uint8_t cost[4096];       // raw cost_base
@@ -678,7 +679,7 @@ k_flow_repair(FlowGrids g, const pfnav_field_req *__restrict__ reqs, const int32
         const bool up = q.next_chunk_r < q.chunk_r, down = q.next_chunk_r > q.chunk_r;
         const bool left = q.next_chunk_c < q.chunk_c;
         const uint8_t fix = up ? 2 : down ? 7 : left ? 4 : 5;
-        uint8_t *dst = fields + (size_t)i * 4096;
+        uint8_t *dst = fields + (size_t)(out_slot ? out_slot[i] : i) * 4096;
         for (int t = tid; t < 4096; t += FLOWG_THREADS) {
             const uint32_t d = dist[t];
             if (d == 0xFFFFFFFFu) continue;
@@ -1544,7 +1545,7 @@ extern "C" int pfnav_flow_fields_repair(pfnav_ctx *ctx, const pfnav_field_req *t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, inout_fields, b_f, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         k_flow_repair<<<(unsigned)std::min<size_t>(n, (size_t)ctx->sm_count * 8), FLOWG_THREADS, 0, st>>>(
-            grids_of(ctx), (const pfnav_field_req *)d_req, (const int32_t *)d_kind, (const uint64_t *)d_mask, (int)n, d_f);
+            grids_of(ctx), (const pfnav_field_req *)d_req, (const int32_t *)d_kind, (const uint64_t *)d_mask, (int)n, d_f, nullptr);
         ctx->launches++;
         e = cudaGetLastError();
     }
@@ -1553,6 +1554,40 @@ extern "C" int pfnav_flow_fields_repair(pfnav_ctx *ctx, const pfnav_field_req *t
     cudaFree(d_buf);
     if (e != cudaSuccess || e2 != cudaSuccess) {
         pfnav_set_error("pfnav_flow_fields_repair: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+// Repairs applied straight to pool slots (pfnav_pool_repair). Host arrays in, blocking.
+int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const int32_t *kinds, const int32_t *args,
+                           const int32_t *slots, size_t n)
+{
+    if (n == 0) return PFNAV_OK;
+    int rc;
+    std::vector<uint64_t> masks(n * 64);
+    for (size_t i = 0; i < n; i++)
+        if ((rc = pfnav_repair_seeds(ctx, targets[i], kinds[i], args[i], masks.data() + i * 64))) return rc;
+    cudaStream_t st = ctx->tick_stream;
+    uint8_t *d_buf = nullptr;
+    const size_t b_req = n * sizeof(pfnav_field_req), b_mask = n * 512, b_kind = n * 4, b_slot = n * 4;
+    PF_CUDA(cudaMalloc(&d_buf, b_req + b_mask + b_kind + b_slot));
+    uint8_t *d_req = d_buf, *d_mask = d_buf + b_req, *d_kind = d_mask + b_mask, *d_slot = d_kind + b_kind;
+    cudaError_t e = cudaMemcpyAsync(d_req, targets, b_req, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, masks.data(), b_mask, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_kind, kinds, b_kind, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slot, slots, b_slot, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        // one CTA per request, serialised per slot by launching requests that share a slot one after another
+        k_flow_repair<<<1, FLOWG_THREADS, 0, st>>>(grids_of(ctx), (const pfnav_field_req *)d_req, (const int32_t *)d_kind,
+                                                  (const uint64_t *)d_mask, (int)n, ctx->d_pool_flow, (const int32_t *)d_slot);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_flow_repair_pool: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
         return PFNAV_ERR_CUDA;
     }
     return PFNAV_OK;

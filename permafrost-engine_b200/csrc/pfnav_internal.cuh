@@ -78,6 +78,7 @@ struct pfnav_ctx {
     int32_t *d_pool_slot = nullptr;   // [ndests][chunks] -> slot or -1
     std::vector<int32_t> h_pool_slot;
     std::vector<uint8_t> h_pool_has;
+    std::vector<pfnav_field_req> h_pool_req;   // [slot]: the last request applied to the slot (== flow_field::target, field.c:2076)
     std::vector<uint64_t> h_pool_ffid;     // [ndests][chunks]: ff_id currently mapped (dest, chunk) -> field, 0 = none
     void *d_plan_buf = nullptr; size_t plan_buf_bytes = 0;    // request staging for pfnav_pool_request_goal
     // The plan of the last goal batch stays resident on the device: re-requesting the same goals on an
@@ -170,6 +171,9 @@ int pfnav_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, pf_arriv
 
 // seeds of the flow-field repair chain (pfnav_route.cu), 64 rows x 64 bits
 int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int arg, uint64_t *mask);
+
+int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const int32_t *kinds, const int32_t *args,
+                           const int32_t *slots, size_t n);
 
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
        PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };

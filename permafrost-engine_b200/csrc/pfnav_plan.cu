@@ -345,6 +345,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
             const int s = slot_for(dests[g], fc[i], 1);
             if (s < 0) { pfnav_set_error("pfnav_pool_request_goals: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
             all_fr.push_back(fr[i]); all_fs.push_back(s); all_fw.push_back(fw[i]);
+            ctx->h_pool_req[s] = fr[i];
         }
         const int lbase = (int)all_lr.size();
         std::vector<int> depth(nl, 0);

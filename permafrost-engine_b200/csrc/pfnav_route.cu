@@ -732,6 +732,7 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
         fwave[i] = seen[fc[i]]++;
         maxw = std::max(maxw, fwave[i]);
         ctx->h_pool_ffid[(size_t)dest * chunks + fc[i]] = fid[i];
+        ctx->h_pool_req[fslot[i]] = fr[i];
     }
     for (int i = 0; i < nl; i++) {
         lslot[i] = slot_for(lc[i], 2);

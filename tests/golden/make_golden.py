@@ -213,7 +213,44 @@ def gen_repair():
     ref.close()
 
 
+def gen_repair_pool():
+    """N_DesiredPointSeekVelocity with its on-miss chain (nav.c:3468-3554) for entities standing on blocked tiles,
+    on cut-off local islands and in chunks the first path request never touched. Steady state: the reference's
+    answers on a second pass over the same positions (the first pass mutates its field cache entity by entity)."""
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, 83, 0.15)
+    ref = pfref.RefMap(cw, ch, p)
+    rng = np.random.default_rng(11)
+    for _ in range(45):
+        ref.blockers_incref(float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)),
+                            float(rng.uniform(3, 12)), 0, 0)
+    ref.update()
+    cost, blk, liid = ref.cost_base(), ref.blockers(), ref.local_islands()
+    img_c = synth.blocked_to_image(cost, cw, ch); img_b = synth.blocked_to_image(blk.astype(np.uint16), cw, ch) if False else \
+        blk.reshape(ch, cw, 64, 64).transpose(0, 2, 1, 3).reshape(ch * 64, cw * 64)
+    free = np.argwhere((img_c != 255) & (img_b == 0))
+    blocked = np.argwhere((img_c != 255) & (img_b > 0))
+    wall = np.argwhere(img_c == 255)
+    def centre(t): return np.stack([-(t[:, 1] + 0.5) * 4.0, (t[:, 0] + 0.5) * 4.0], axis=1).astype(np.float32)
+    tgt_tile = free[(free[:, 0] >= 64) & (free[:, 1] >= 64)][7]
+    target = centre(tgt_tile[None])[0]
+    pos = np.concatenate([centre(free[rng.integers(0, len(free), 160)]) + rng.uniform(-1.5, 1.5, (160, 2)).astype(np.float32),
+                          centre(blocked[rng.integers(0, len(blocked), 100)]),
+                          centre(wall[rng.integers(0, len(wall), 40)])]).astype(np.float32)
+    ok, did = ref.request_path((float(pos[0, 0]), float(pos[0, 1])), (float(target[0]), float(target[1])))
+    assert ok
+    v1, l1 = ref.desired_velocity(did, pos, pos, target)
+    v2, l2 = ref.desired_velocity(did, pos, pos, target)
+    v3, l3 = ref.desired_velocity(did, pos, pos, target)
+    assert (v2 == v3).all()
+    print("repair_pool: pass1 != pass2 for", int((v1 != v2).any(axis=1).sum()), "agents; zero vdes", int((np.abs(v2).sum(1) == 0).sum()))
+    np.savez_compressed(os.path.join(HERE, "repair_pool.npz"), pathable=p, cost=cost, blk=blk, liid=liid, pos=pos,
+                        target=target, vdes=v2, los=l2, did=np.uint32(did))
+    ref.close()
+
+
 if __name__ == "__main__":
+    gen_repair_pool()
     gen_repair()
     gen_update("update_hz20", 61, 20)
     gen_update("update_hz10", 62, 10)

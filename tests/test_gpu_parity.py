@@ -537,3 +537,37 @@ def test_repair_chain_golden(nav, pforacle):
     got = nav.flow_fields_repair(T, g["kinds"], g["args"], g["base"])
     bad = np.nonzero((got != g["exp"]).reshape(len(T), -1).any(axis=1))[0]
     assert len(bad) == 0, (bad[:10], g["kinds"][bad[:10]])
+
+
+def test_pool_repair_chain_golden(nav):
+    """a-4 end to end: N_DesiredPointSeekVelocity's on-miss chain (nav.c:3484-3554) against the device pool.
+    Entities on blocked tiles, inside walls, on islands cut off by blockers and in chunks the first request never
+    touched; steady-state answers equal the reference's bit for bit."""
+    g = gold("repair_pool")
+    pos, target = g["pos"], g["target"]
+    n = len(pos)
+    nav.map_create(2, 2, 1)
+    nav.map_upload_layer(0, g["cost"], g["blk"], g["liid"])
+    nav.map_build_nav(0); nav.route_build(0)
+    nav.pool_create(1, 8)
+    ok, did, nf, nl = nav.pool_request_path(0, (float(pos[0, 0]), float(pos[0, 1])), (float(target[0]), float(target[1])))
+    assert ok and did == int(g["did"])
+    rec = np.zeros(n, capi.AGENT)
+    rec["pos"] = pos; rec["prev_pos"] = pos; rec["radius"] = 1.0; rec["max_speed"] = 20.0; rec["speed"] = 20.0
+    rec["flags"] = capi.FLAG_MOVABLE; rec["flock"] = 0
+    fl = np.zeros(1, capi.FLOCK); fl["target"] = target; fl["dest"] = 0; fl["layer"] = 0
+    nav.agents_upload(rec, fl, 20)
+    nav.agents_set_work(np.arange(n, dtype=np.uint32))
+    total = 0
+    for _ in range(4):
+        nav.agents_tick(capi.TICK_VDES_FROM_POOL)
+        nreq, nrep = nav.pool_repair()
+        total += nreq + nrep
+        if nreq + nrep == 0:
+            break
+    assert total > 0
+    nav.agents_tick(capi.TICK_VDES_FROM_POOL)
+    _, vdes, los = nav.agents_read_debug(n)
+    bad = np.nonzero((vdes != g["vdes"]).any(axis=1))[0]
+    assert len(bad) == 0, (len(bad), bad[:10], vdes[bad[:5]], g["vdes"][bad[:5]])
+    assert (los == g["los"]).all()

@@ -83,6 +83,67 @@ def test_port_repair_chain_vs_ref(pfref, pforacle):
     ref.close()
 
 
+def test_repair_chain_sequence_golden(pforacle):
+    """the SEQUENCE of the on-miss chain (nav.c:3484-3554) as pfnav_pool_repair runs it -- misses in work order, one
+    representative per (chunk, local island | blocked tile), path request from its position, repair only when that
+    request succeeded and the tile is still FD_NONE -- executed here with the host planner + the oracle port in
+    place of the kernels, against the reference's steady-state desired velocities."""
+    g = gold("repair_pool")
+    cw = ch = 2
+    pos, target, liid = g["pos"], g["target"], g["liid"]
+    n = len(pos)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, g["cost"], g["blk"], liid); nav.map_build_nav(0); nav.route_build(0)
+    gisl = nav.route_islands(0)
+    om = pforacle.OracleMap(cw, ch, g["cost"], g["blk"], liid)
+    flow, last, ffid = {}, {}, np.zeros(cw * ch, np.uint64)
+
+    def tile_of(p):
+        ar, ac = min(int(abs(p[1]) / 4), ch * 64 - 1), min(int(abs(p[0]) / 4), cw * 64 - 1)
+        return (ar >> 6) * cw + (ac >> 6), ar & 63, ac & 63
+
+    def request(src):
+        ok, did, fr, fid, fc, lr, lc = nav.route_request_path((float(src[0]), float(src[1])), (float(target[0]), float(target[1])),
+                                                              0, ffid.copy(), np.ones(cw * ch, np.uint8))
+        for k in range(len(fr)):
+            c = int(fc[k])
+            flow[c] = om.flow_fields_update(fr[k:k + 1], None if fr[k]["init"] else flow[c][None])[0]
+            ffid[c] = fid[k]; last[c] = fr[k:k + 1].copy()
+        return ok, len(fr)
+
+    assert request(pos[0])[0]
+    for _ in range(4):
+        reps, seen = [], set()
+        for i in range(n):
+            c, r, cc = tile_of(pos[i])
+            if c in flow and flow[c][r, cc] != 0:
+                continue
+            li = int(liid[c][r, cc])
+            key = (c, ("t", r, cc) if li == 0xFFFF else li)
+            if key not in seen:
+                seen.add(key); reps.append((i, c, r, cc, li))
+        done = 0
+        oks = {}
+        for i, c, r, cc, li in reps:
+            oks[i], nf = request(pos[i]); done += nf > 0
+        for i, c, r, cc, li in reps:
+            if not oks[i] or c not in flow or flow[c][r, cc] != 0:
+                continue
+            flow[c] = om.flow_nearest_pathable((c // cw, c % cw), (r, cc), flow[c]) if li == 0xFFFF \
+                else om.flow_island_to_nearest(gisl, last[c], li, flow[c])
+            done += 1
+        if not done:
+            break
+    rec = np.zeros(n, capi.AGENT); rec["pos"] = pos; rec["prev_pos"] = pos; rec["flock"] = 0
+    fl = np.zeros(1, capi.FLOCK); fl["target"] = target; fl["dest"] = 0
+    slot = np.full((1, cw * ch), -1, np.int32); F = np.zeros((cw * ch, 64, 64), np.uint8)
+    for k, c in enumerate(sorted(flow)):
+        slot[0, c] = k; F[k] = flow[c]
+    vd, _ = om.desired_velocity(rec, fl, np.arange(n, dtype=np.uint32), slot, F, np.zeros_like(F))
+    assert (vd == g["vdes"]).all()
+    nav.close()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 
