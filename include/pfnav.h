@@ -119,6 +119,14 @@ int  pfnav_map_refresh_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c
 int  pfnav_local_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out);
 int  pfnav_portals_get(pfnav_ctx *ctx, int layer, int32_t *out, int maxout, int *out_n);
 
+/* "Attacking" requests (N_RequestPathAttacking, nav.c:3393): a field / LOS request whose faction_id is not
+ * PFNAV_FACTION_ID_NONE treats a blocked tile as passable when every faction holding a blocker refcount on it
+ * is at war with the requesting faction (field_tile_passable_no_enemies, field.c:179).
+ *   pfnav_set_enemy_factions: G_GetEnemyFactions (game.h:184), bit i of the mask = faction i is an enemy.
+ *   pfnav_map_upload_factions: chunk->factions of one layer, u8 [chunk][15][64][64]; pfnav_blockers_incref /
+ *   decref maintain the same counts when given a faction id in 0..14 (nav.c:1032). */
+int  pfnav_set_enemy_factions(pfnav_ctx *ctx, int faction_id, uint16_t enemies_mask);
+int  pfnav_map_upload_factions(pfnav_ctx *ctx, int layer, const uint8_t *factions);
 /* N_BlockersIncref / N_BlockersDecref (nav.c:4663-4683): reference-count the tiles under a circle
  * (M_Tile_AllUnderCircle, tile.c:687) plus 1/2/3 contour rings (M_Tile_Contour, tile.c:759) for the
  * 3x3/5x5/7x7 layers, on the ground AND water layers for non-air entities, air layers otherwise.

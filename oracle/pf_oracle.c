@@ -83,6 +83,20 @@ static bool tile_passable(const pfo_map *m, int cr, int cc, int r, int c)
     return true;
 }
 
+/* field_tile_passable_no_enemies (field.c:179) when the request carries a faction, else field_tile_passable */
+static bool tile_passable_f(const pfo_map *m, int faction, int cr, int cc, int r, int c)
+{
+    if(faction == 0xF || !m->factions) return tile_passable(m, cr, cc, r, c);
+    if(chunk_cost(m, cr, cc)[r * RES + c] == COST_IMPASSABLE) return false;
+    const uint8_t *fac = m->factions + ((size_t)cr * m->chunk_w + cc) * 15 * 4096;
+    const uint16_t enemies = m->enemies[faction & 0xF];
+    bool enemies_only = true;
+    for(int i = 0; i < 15; i++)
+        if(fac[(size_t)i * 4096 + r * RES + c] && !(enemies & (1u << i))) { enemies_only = false; break; }
+    if(enemies_only) return true;
+    return chunk_blk(m, cr, cc, r, c) == 0;
+}
+
 /* field_flow_dir (navigation/field.c:355): note the selection at :405-428 re-tests only equality
  * with min_cost, not the "both side tiles finite" admissibility used to compute min_cost. */
 static int flow_dir(const float intf[RES][RES], int r, int c)
@@ -120,7 +134,7 @@ static void flow_field_update(const pfo_map *m, const pfo_field_req *q, uint8_t 
 
     if(q->target_type == TARGET_TILE) {
         /* field_tile_initial_frontier (field.c:1096) */
-        if(tile_passable(m, cr, cc, q->tile_r, q->tile_c)) {
+        if(tile_passable_f(m, q->faction_id, cr, cc, q->tile_r, q->tile_c)) {
             pq_push(&frontier, 0.0f, q->tile_r, q->tile_c);
             f[q->tile_r][q->tile_c] = 0.0f;
         }
@@ -128,7 +142,7 @@ static void flow_field_update(const pfo_map *m, const pfo_field_req *q, uint8_t 
         /* field_portal_initial_frontier (field.c:1160) + field_tile_adjacent_to_next_iid (:1131) */
         for(int r = q->port_r0; r <= q->port_r1; r++) {
         for(int c = q->port_c0; c <= q->port_c1; c++) {
-            if(!tile_passable(m, cr, cc, r, c)) continue;
+            if(!tile_passable_f(m, q->faction_id, cr, cc, r, c)) continue;
             if(q->port_iid != ISLAND_NONE && chunk_liid(m, cr, cc, r, c) != q->port_iid) continue;
             bool adj = false;
             for(int r2 = q->next_r0; r2 <= q->next_r1 && !adj; r2++) {
@@ -155,7 +169,7 @@ static void flow_field_update(const pfo_map *m, const pfo_field_req *q, uint8_t 
             if(ar < 0 || ar >= RES || ac < 0 || ac >= RES) continue;
             if(dr == 0 && dc == 0) continue;
             if(dr == dc || dr == -dc) continue;
-            if(!tile_passable(m, cr, cc, ar, ac)) continue;
+            if(!tile_passable_f(m, q->faction_id, cr, cc, ar, ac)) continue;
             float total = f[r][c] + cost[ar * RES + ac];
             if(total < f[ar][ac]) { f[ar][ac] = total; pq_push(&frontier, total, ar, ac); }
         }}
@@ -274,7 +288,7 @@ static void los_field_create(const pfo_map *m, const pfo_los_req *q, const uint8
         {
             int ar = nbr[i][0], ac = nbr[i][1];
             uint8_t ncost = cost[ar * RES + ac];
-            if(!tile_passable(m, cr, cc, ar, ac)) ncost = COST_IMPASSABLE;
+            if(!tile_passable_f(m, q->faction_id, cr, cc, ar, ac)) ncost = COST_IMPASSABLE;
             if(ncost > 1) {
                 if(!is_los_corner(m, cr, cc, ar, ac)) continue;
                 blocked_line(m, q, ar, ac, &out);

@@ -21,6 +21,8 @@ typedef struct pfo_map {
     const uint8_t  *cost;            /* [chunks][64][64], one layer */
     const uint16_t *blockers;        /* may be NULL (all zero) */
     const uint16_t *local_islands;   /* may be NULL when no TARGET_PORTAL request is made */
+    const uint8_t  *factions;        /* [chunks][15][64][64] per-faction blocker refcounts, may be NULL */
+    uint16_t enemies[16];            /* enemies[f] = bit mask of the factions at war with f (field.c:151) */
 } pfo_map;
 
 typedef struct pfo_field_req {       /* == pfnav_field_req */

@@ -12,7 +12,8 @@ _lib = None
 
 class _Map(C.Structure):
     _fields_ = [("chunk_w", C.c_int), ("chunk_h", C.c_int), ("map_x", C.c_float), ("map_z", C.c_float),
-                ("cost", C.c_void_p), ("blockers", C.c_void_p), ("local_islands", C.c_void_p)]
+                ("cost", C.c_void_p), ("blockers", C.c_void_p), ("local_islands", C.c_void_p),
+                ("factions", C.c_void_p), ("enemies", C.c_uint16 * 16)]
 
 
 def build():
@@ -56,12 +57,19 @@ def cost_from_tiles(chunk_w, chunk_h, tiles, ref_layer):
 
 
 class OracleMap:
-    def __init__(self, chunk_w, chunk_h, cost, blockers=None, local_islands=None, map_x=0.0, map_z=0.0):
+    def __init__(self, chunk_w, chunk_h, cost, blockers=None, local_islands=None, map_x=0.0, map_z=0.0,
+                 factions=None, enemies=None):
+        """factions: u8[chunks][15][64][64] per-faction blocker refcounts; enemies[f] = war bit mask of faction f"""
         self.cw, self.ch = chunk_w, chunk_h
         self.cost = np.ascontiguousarray(cost, np.uint8)
         self.blockers = None if blockers is None else np.ascontiguousarray(blockers, np.uint16)
         self.liid = None if local_islands is None else np.ascontiguousarray(local_islands, np.uint16)
-        self.m = _Map(chunk_w, chunk_h, map_x, map_z, _p(self.cost), _p(self.blockers), _p(self.liid))
+        self.factions = None if factions is None else np.ascontiguousarray(factions, np.uint8)
+        en = (C.c_uint16 * 16)(*([0] * 16))
+        if enemies is not None:
+            for f in range(16):
+                en[f] = int(enemies[f])
+        self.m = _Map(chunk_w, chunk_h, map_x, map_z, _p(self.cost), _p(self.blockers), _p(self.liid), _p(self.factions), en)
 
     def flow_fields_update(self, reqs, inout=None):
         reqs = np.ascontiguousarray(reqs)

@@ -32,6 +32,8 @@ def lib():
         L.pfref_flow_field_portal.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
         L.pfref_flow_nearest_pathable.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
         L.pfref_flow_island_to_nearest.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
+        L.pfref_set_war.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.pfref_los_field_faction.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_request_path.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
         L.pfref_dest_id.restype = C.c_uint32
@@ -94,6 +96,15 @@ class RefMap:
         lib().pfref_get_field(self.h, layer, kind, _p(out))
         return out
 
+    def factions(self, layer=0):
+        """u8[chunks][15][64][64] per-faction blocker refcounts (nav_data.h chunk->factions)"""
+        out = np.zeros((self.ch * self.cw, 15, 64, 64), np.uint8)
+        for f in range(15):
+            tmp = np.zeros((self.ch * self.cw, 64, 64), np.uint8)
+            lib().pfref_get_field(self.h, layer, 16 + f, _p(tmp))
+            out[:, f] = tmp
+        return out
+
     def cost_base(self, layer=0): return self.field(layer, 0)
     def blockers(self, layer=0): return self.field(layer, 1)
     def islands(self, layer=0): return self.field(layer, 2)
@@ -137,9 +148,16 @@ class RefMap:
                                       faction, int(init), _p(buf))
         return buf.reshape(64, 64)
 
-    def los(self, chunk, target_td, layer=0, prev=None, prev_chunk=(0, 0)):
+    def set_war(self, a, b, at_war=True):
+        lib().pfref_set_war(a, b, int(at_war))
+
+    def los(self, chunk, target_td, layer=0, prev=None, prev_chunk=(0, 0), faction=0xF):
         out = np.zeros(4096, dtype=np.uint8)
         pv = None if prev is None else np.ascontiguousarray(prev, dtype=np.uint8).reshape(-1)
+        if faction != 0xF:
+            lib().pfref_los_field_faction(self.h, faction, layer, chunk[0], chunk[1], target_td[0], target_td[1],
+                                          target_td[2], target_td[3], _p(pv), prev_chunk[0], prev_chunk[1], _p(out))
+            return out.reshape(64, 64)
         lib().pfref_los_field(self.h, layer, chunk[0], chunk[1], target_td[0], target_td[1], target_td[2],
                               target_td[3], _p(pv), prev_chunk[0], prev_chunk[1], _p(out))
         return out.reshape(64, 64)

@@ -171,6 +171,23 @@ int Entity_NavLayerWithRadius(uint32_t flags, float radius)
         return water ? NAV_LAYER_WATER_1X1 : air ? NAV_LAYER_AIR_1X1 : NAV_LAYER_GROUND_1X1;
 }
 
+/* Diplomacy: a settable war matrix stands in for the game state (game.c). */
+static uint8_t s_pfref_war[MAX_FACTIONS][MAX_FACTIONS];
+PFREF_EXPORT void pfref_set_war(int a, int b, int at_war) { s_pfref_war[a][b] = s_pfref_war[b][a] = (uint8_t)at_war; }
+bool G_GetDiplomacyState(int fac_id_a, int fac_id_b, enum diplomacy_state *out)
+{
+    if(fac_id_a == fac_id_b) return false;
+    *out = s_pfref_war[fac_id_a][fac_id_b] ? DIPLOMACY_STATE_WAR : DIPLOMACY_STATE_PEACE;
+    return true;
+}
+uint16_t G_GetEnemyFactions(int faction_id)
+{
+    uint16_t ret = 0;
+    for(int i = 0; i < MAX_FACTIONS; i++)
+        if(i != faction_id && s_pfref_war[i][faction_id]) ret |= (uint16_t)(1u << i);
+    return ret;
+}
+
 /* Arrival / formation are inactive in every oracle scenario: the reference
  * then falls through to the plain point-seek branch (movement.c:1516, 1752, 1888). */
 struct arrival_state *G_ArrivalGroup_ForLayer(const struct arrival_group *g, enum nav_layer layer) { return NULL; }
@@ -316,6 +333,7 @@ PFREF_EXPORT void pfref_get_field(void *m, int layer, int kind, void *out)
         case 1: memcpy((uint16_t*)out + i * 4096, ch->blockers, 8192); break;
         case 2: memcpy((uint16_t*)out + i * 4096, ch->islands, 8192); break;
         case 3: memcpy((uint16_t*)out + i * 4096, ch->local_islands, 8192); break;
+        default: if(kind >= 16 && kind < 16 + MAX_FACTIONS) memcpy((uint8_t*)out + i * 4096, ch->factions[kind - 16], 4096); break;
         }
     }
 }
@@ -472,6 +490,28 @@ PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
     dest_id_t id = (((uint32_t)target.chunk_r & 0x3f) << 26) | (((uint32_t)target.chunk_c & 0x3f) << 20)
                  | (((uint32_t)target.tile_r  & 0x3f) << 14) | (((uint32_t)target.tile_c  & 0x3f) <<  8)
                  | (((uint32_t)layer & 0x0f) << 4) | (uint32_t)FACTION_ID_NONE;
+    struct LOS_field lf, prev_lf;
+    if(prev) {
+        prev_lf.chunk = (struct coord){prev_chunk_r, prev_chunk_c};
+        pfref_los_unpack(prev, &prev_lf);
+    }
+    N_LOSFieldCreate(id, (struct coord){chunk_r, chunk_c}, target, priv, map->pos,
+        priv->unit_query_ctx, &lf, prev ? &prev_lf : NULL);
+    pfref_los_pack(&lf, out);
+}
+
+PFREF_EXPORT void pfref_los_field_faction(void *m, int faction_id, int layer, int chunk_r, int chunk_c,
+                                  int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,
+                                  const uint8_t *prev, int prev_chunk_r, int prev_chunk_c,
+                                  uint8_t *out)
+{
+    struct map *map = m;
+    struct nav_private *priv = pfref_priv(m);
+    struct tile_desc target = {tgt_chunk_r, tgt_chunk_c, tgt_tile_r, tgt_tile_c};
+    /* n_dest_id bit packing, nav.c:839-854 */
+    dest_id_t id = (((uint32_t)target.chunk_r & 0x3f) << 26) | (((uint32_t)target.chunk_c & 0x3f) << 20)
+                 | (((uint32_t)target.tile_r  & 0x3f) << 14) | (((uint32_t)target.tile_c  & 0x3f) <<  8)
+                 | (((uint32_t)layer & 0x0f) << 4) | ((uint32_t)faction_id & 0x0f);
     struct LOS_field lf, prev_lf;
     if(prev) {
         prev_lf.chunk = (struct coord){prev_chunk_r, prev_chunk_c};

@@ -65,7 +65,8 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions",
+    "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
 ]
 
@@ -95,6 +96,8 @@ def load():
     L.pfnav_map_update_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pfnav_map_build_nav.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_fields_join.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_set_enemy_factions.argtypes = [C.c_void_p, C.c_int, C.c_uint16]
+    L.pfnav_map_upload_factions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_pool_repair.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_flow_fields_repair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_agents_upload_movestate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -268,6 +271,14 @@ class Nav:
         a, b = C.c_int(0), C.c_int(0)
         _chk(self.L.pfnav_pool_repair(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def set_enemy_factions(self, faction_id, mask):
+        _chk(self.L.pfnav_set_enemy_factions(self.h, faction_id, int(mask)))
+
+    def map_upload_factions(self, layer, factions):
+        f = np.ascontiguousarray(factions, np.uint8)
+        assert f.shape == (self.cw * self.ch, 15, 64, 64)
+        _chk(self.L.pfnav_map_upload_factions(self.h, layer, _p(f)))
 
     def fields_join(self, stream=0):
         _chk(self.L.pfnav_fields_join(self.h, C.c_void_p(stream)))

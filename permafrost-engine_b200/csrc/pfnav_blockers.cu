@@ -144,22 +144,41 @@ static size_t tiles_contour(const pfnav_ctx *ctx, size_t ntds, const td *tds, td
 }
 
 static std::unordered_map<const pfnav_ctx *, std::set<std::pair<int, int>>> g_dirty;     // (layer, chunk)
+static std::unordered_map<const pfnav_ctx *, std::set<std::pair<int, int>>> g_fdirty;    // faction mask changed
 
 // n_update_blockers (nav.c:1017) on the host mirror; layers the context does not hold are skipped
-static void apply(pfnav_ctx *ctx, int layer, const td *tds, size_t n, int delta)
+static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size_t n, int delta)
 {
     if (layer >= ctx->nlayers) return;
-    const size_t lbase = (size_t)layer * ctx->chunk_w * ctx->chunk_h * 4096;
+    const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h, ltiles = chunks * 4096;
+    const size_t lbase = (size_t)layer * ltiles;
+    const bool fac = faction_id >= 0 && faction_id < 15;
+    if (fac) {      // chunk->factions[faction_id] (nav.c:1032), allocated on first use
+        if (ctx->h_fac.size() < (size_t)ctx->nlayers) ctx->h_fac.resize(ctx->nlayers);
+        if (ctx->h_fac[layer].empty()) ctx->h_fac[layer].assign(ltiles * 15, 0);
+        if (ctx->h_fmask.size() < ltiles * ctx->nlayers) ctx->h_fmask.assign(ltiles * ctx->nlayers, 0);
+    }
     for (size_t i = 0; i < n; i++) {
         const int chunk = tds[i].chunk_r * ctx->chunk_w + tds[i].chunk_c;
-        uint16_t &v = ctx->h_blk[lbase + (size_t)chunk * 4096 + tds[i].tile_r * 64 + tds[i].tile_c];
+        const int t = tds[i].tile_r * 64 + tds[i].tile_c;
+        uint16_t &v = ctx->h_blk[lbase + (size_t)chunk * 4096 + t];
         const int prev = v;
         v = (uint16_t)(prev + delta);
         if (!!v != !!prev) g_dirty[ctx].insert({layer, chunk});
+        if (fac) {
+            uint8_t &fv = ctx->h_fac[layer][((size_t)chunk * 15 + faction_id) * 4096 + t];
+            const int fprev = fv;
+            fv = (uint8_t)(fprev + delta);
+            if (!!fv != !!fprev) {
+                uint16_t &m = ctx->h_fmask[lbase + (size_t)chunk * 4096 + t];
+                m = fv ? (uint16_t)(m | (1u << faction_id)) : (uint16_t)(m & ~(1u << faction_id));
+                g_fdirty[ctx].insert({layer, chunk});
+            }
+        }
     }
 }
 
-static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, uint32_t flags, int delta)
+static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags, int delta)
 {
     td tds[1024], o3[1024], o5[1024], o7[1024];
     const size_t n = tiles_under_circle(ctx, {x, z}, range, tds, 1024);
@@ -171,30 +190,28 @@ static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, uint32
     for (int gi = 0; gi < 2; gi++) {
         const int g = groups[gi];
         if (g < 0) continue;
-        apply(ctx, g + 0, tds, n, delta);
-        apply(ctx, g + 1, tds, n, delta); apply(ctx, g + 1, o3, n3, delta);
-        apply(ctx, g + 2, tds, n, delta); apply(ctx, g + 2, o3, n3, delta); apply(ctx, g + 2, o5, n5, delta);
-        apply(ctx, g + 3, tds, n, delta); apply(ctx, g + 3, o3, n3, delta); apply(ctx, g + 3, o5, n5, delta); apply(ctx, g + 3, o7, n7, delta);
+        apply(ctx, g + 0, faction_id, tds, n, delta);
+        apply(ctx, g + 1, faction_id, tds, n, delta); apply(ctx, g + 1, faction_id, o3, n3, delta);
+        apply(ctx, g + 2, faction_id, tds, n, delta); apply(ctx, g + 2, faction_id, o3, n3, delta); apply(ctx, g + 2, faction_id, o5, n5, delta);
+        apply(ctx, g + 3, faction_id, tds, n, delta); apply(ctx, g + 3, faction_id, o3, n3, delta); apply(ctx, g + 3, faction_id, o5, n5, delta); apply(ctx, g + 3, faction_id, o7, n7, delta);
     }
     return PFNAV_OK;
 }
 
 }   // namespace
 
-void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); }
+void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); g_fdirty.erase(ctx); }
 
 extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
-    (void)faction_id;        // per-faction counts (chunk->factions) feed attacking paths only: not implemented
-    return blockers_circle(ctx, x, z, range, flags, +1);
+    return blockers_circle(ctx, x, z, range, faction_id, flags, +1);
 }
 
 extern "C" int pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
-    (void)faction_id;
-    return blockers_circle(ctx, x, z, range, flags, -1);
+    return blockers_circle(ctx, x, z, range, faction_id, flags, -1);
 }
 
 // N_Update + N_ApplyDeferredInvalidations: recompute the local islands of every dirty chunk, refresh the
@@ -207,6 +224,14 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
     if (ctx->device >= 0) {
         PF_CUDA(cudaSetDevice(ctx->device));
         PF_CUDA(pf_fields_sync(ctx));     // forked LOS chains still read the map that is about to change
+    }
+    {   // faction masks follow the refcounts at once (they only matter to attacking requests)
+        auto fit = g_fdirty.find(ctx);
+        if (fit != g_fdirty.end()) {
+            for (const auto &lc : fit->second) { int rc = pfnav_fmask_push_chunk(ctx, lc.first, lc.second); if (rc) return rc; }
+            if (!fit->second.empty()) ctx->map_epoch++;
+            fit->second.clear();
+        }
     }
     auto it = g_dirty.find(ctx);
     int nd = 0;

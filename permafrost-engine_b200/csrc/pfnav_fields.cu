@@ -248,7 +248,18 @@ struct FlowGrids {
     const uint16_t *liid;
     const uint8_t *unit;     // [layer][chunks]
     int W64, H64, chunk_w, chunk_h;
+    const uint16_t *fmask;   // [layer][H64][W64] bit f <=> faction f holds a blocker refcount on the tile
+    uint16_t enemies[16];    // enemies[f]: factions at war with f
 };
+
+// field_tile_passable_no_enemies (field.c:179): a blocked tile stays passable for an "attacking" request when
+// every faction holding a refcount on it is an enemy of the requesting faction
+__device__ __forceinline__ bool blocked_for(const FlowGrids &g, int faction_id, size_t off)
+{
+    if (g.blk[off] == 0) return false;
+    if (faction_id == PFNAV_FACTION_ID_NONE) return true;
+    return (g.fmask[off] & ~g.enemies[faction_id & 0xF]) != 0;
+}
 
 #define FLOW_WARPS_PER_CTA 8
 #define FLOW_SMEM_PER_WARP 12288   // cost tile 4096 + blockers tile 8192
@@ -430,6 +441,8 @@ k_flow_unit(const __grid_constant__ CUtensorMap tm_cost, const __grid_constant__
         const pfnav_field_req q = reqs[i];
         // the general-cost kernel owns chunks that hold a passable cost other than 1
         if (!g.unit[(size_t)q.layer * g.chunk_w * g.chunk_h + q.chunk_r * g.chunk_w + q.chunk_c]) continue;
+        // ... and the faction-aware ("attacking") requests, whose passability is per request
+        if (q.faction_id != PFNAV_FACTION_ID_NONE) continue;
 
         uint64_t P0, P1;
         bool nonunit;
@@ -534,14 +547,14 @@ k_flow_general(FlowGrids g, const pfnav_field_req *__restrict__ reqs, int n, uin
     const int tid = threadIdx.x;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const pfnav_field_req q = reqs[i];
-        if (only_nonunit &&
+        if (only_nonunit && q.faction_id == PFNAV_FACTION_ID_NONE &&
             g.unit[(size_t)q.layer * g.chunk_w * g.chunk_h + q.chunk_r * g.chunk_w + q.chunk_c])
             continue;
         const size_t lbase = (size_t)q.layer * g.H64 * g.W64;
         for (int t = tid; t < 4096; t += FLOWG_THREADS) {
             size_t off = lbase + (size_t)(q.chunk_r * 64 + (t >> 6)) * g.W64 + q.chunk_c * 64 + (t & 63);
             uint8_t c = g.cost[off];
-            if (g.blk[off] > 0) c = 0xFF;
+            if (blocked_for(g, q.faction_id, off)) c = 0xFF;
             cost[t] = c;
             dist[t] = 0xFFFFFFFFu;
             seed[t] = 0;
@@ -651,7 +664,7 @@ k_flow_repair(FlowGrids g, const pfnav_field_req *__restrict__ reqs, const int32
         for (int t = tid; t < 4096; t += FLOWG_THREADS) {
             const size_t off = lbase + (size_t)(q.chunk_r * 64 + (t >> 6)) * g.W64 + q.chunk_c * 64 + (t & 63);
             const uint8_t c = g.cost[off];
-            const bool pass = c != 0xFF && g.blk[off] == 0;
+            const bool pass = c != 0xFF && !blocked_for(g, q.faction_id, off);
             const bool seed = (seed_masks[(size_t)i * 64 + (t >> 6)] >> (t & 63)) & 1;
             cost[t] = c;
             dom[t] = seed ? 2 : (kind == 0 ? !pass : pass) ? 1 : 0;      // 2 = seed (distance pinned at 0)
@@ -896,8 +909,19 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) blocked |= (uint64_t)blk8_bits(__ldg(pb + j)) << (8 * j);
+            // an "attacking" request (dest_id carries a faction, field.c:2095) walks over tiles blocked only by its
+            // enemies (field_tile_passable_no_enemies, field.c:179); the corner test keeps the plain rule (field.c:435)
+            uint64_t blocked_f = blocked;
+            if (q.faction_id != PFNAV_FACTION_ID_NONE && blocked) {
+                const uint16_t en = g.enemies[q.faction_id & 0xF];
+                const uint16_t *pf = g.fmask + off;
+                for (uint64_t rest = blocked; rest; rest &= rest - 1) {
+                    const int c = __ffsll((long long)rest) - 1;
+                    if ((pf[c] & ~en) == 0) blocked_f &= ~(1ull << c);
+                }
+            }
             s.pass[row] = p & ~blocked;
-            s.open[row] = p & ~blocked & ~gt1;
+            s.open[row] = p & ~blocked_f & ~gt1;
             s.assigned[row] = 0;
             s.blk[row] = 0;
             uint4 *vz = reinterpret_cast<uint4 *>(s.visb + row * 64);
@@ -1112,7 +1136,8 @@ int pfnav_fields_init(pfnav_ctx *ctx)
 
 static void free_map(pfnav_ctx *ctx)
 {
-    cudaFree(ctx->d_cost); cudaFree(ctx->d_blk); cudaFree(ctx->d_liid); cudaFree(ctx->d_unit);
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_blk); cudaFree(ctx->d_liid); cudaFree(ctx->d_unit); cudaFree(ctx->d_fmask);
+    ctx->d_fmask = nullptr; ctx->h_fac.clear(); ctx->h_fmask.clear();
     ctx->d_cost = nullptr; ctx->d_blk = nullptr; ctx->d_liid = nullptr; ctx->d_unit = nullptr;
 }
 
@@ -1194,6 +1219,10 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     PF_ARG(chunk_w > 0 && chunk_h > 0 && chunk_w <= 64 && chunk_h <= 64, "chunk_w/chunk_h must be in 1..64 (dest_id has 6 bits per chunk coordinate, nav.c:841)");
     PF_ARG(nlayers > 0 && nlayers <= PFNAV_NAV_LAYER_MAX, "nlayers");
     ctx->map_epoch++;
+    // structures derived from the previous map (dirty sets, routes, per-faction counts) do not carry over
+    pfnav_route_forget(ctx);
+    pfnav_blockers_forget(ctx);
+    ctx->h_fac.clear(); ctx->h_fmask.clear();
     ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
     ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;
     ctx->map_x = map_x; ctx->map_z = map_z;
@@ -1214,6 +1243,8 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     PF_CUDA(cudaMemset(ctx->d_cost, 0xFF, tiles));
     PF_CUDA(cudaMemset(ctx->d_blk, 0, tiles * 2));
     PF_CUDA(cudaMemset(ctx->d_liid, 0xFF, tiles * 2));
+    PF_CUDA(cudaMalloc(&ctx->d_fmask, tiles * 2));
+    PF_CUDA(cudaMemset(ctx->d_fmask, 0, tiles * 2));
     PF_CUDA(cudaMemset(ctx->d_unit, 1, (size_t)chunk_w * chunk_h * nlayers));
     ctx->h_unit.assign((size_t)chunk_w * chunk_h * nlayers, 1);
     ctx->h_cost.assign(tiles, 0xFF);
@@ -1363,6 +1394,59 @@ extern "C" int pfnav_map_get_layer(pfnav_ctx *ctx, int layer, uint8_t *cost_base
     return PFNAV_OK;
 }
 
+// chunk->factions (nav_data.h): direct upload of the per-faction blocker refcounts of one layer,
+// [chunk][15][64][64] u8 (what N_BlockersIncref accumulates, nav.c:1032).
+extern "C" int pfnav_map_upload_factions(pfnav_ctx *ctx, int layer, const uint8_t *factions)
+{
+    PF_ARG(ctx && ctx->d_cost && factions, "map not created / null");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h, ltiles = chunks * 4096;
+    if (ctx->h_fac.size() < (size_t)ctx->nlayers) ctx->h_fac.resize(ctx->nlayers);
+    if (ctx->h_fmask.size() < ltiles * ctx->nlayers) ctx->h_fmask.assign(ltiles * ctx->nlayers, 0);
+    ctx->h_fac[layer].assign(factions, factions + ltiles * 15);
+    uint16_t *fm = ctx->h_fmask.data() + ltiles * layer;
+    for (size_t ch = 0; ch < chunks; ch++)
+        for (int t = 0; t < 4096; t++) {
+            uint16_t m = 0;
+            for (int f = 0; f < 15; f++) if (factions[(ch * 15 + f) * 4096 + t]) m |= (uint16_t)(1u << f);
+            fm[ch * 4096 + t] = m;
+        }
+    ctx->map_epoch++;
+    if (ctx->device < 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_stage(ctx, ltiles * 2);
+    if (rc) return rc;
+    PF_CUDA(cudaMemcpy(ctx->d_stage, fm, ltiles * 2, cudaMemcpyHostToDevice));
+    const int nblk = (int)std::min<size_t>((ltiles + 255) / 256, 148 * 8);
+    k_deblock<uint16_t><<<nblk, 256>>>((const uint16_t *)ctx->d_stage, ctx->d_fmask + ltiles * layer, ctx->chunk_w, ctx->chunk_h);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaDeviceSynchronize());
+    return PFNAV_OK;
+}
+
+// Push the faction masks of one chunk after blocker refcount changes (called by pfnav_map_commit).
+int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk)
+{
+    if (ctx->device < 0 || ctx->h_fmask.empty()) return PFNAV_OK;
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    const int cr = chunk / ctx->chunk_w, cc = chunk % ctx->chunk_w;
+    PF_CUDA(cudaMemcpy2D(ctx->d_fmask + ltiles * layer + (size_t)cr * 64 * ctx->W64 + cc * 64, ctx->W64 * 2,
+                         ctx->h_fmask.data() + ltiles * layer + (size_t)chunk * 4096, 128, 128, 64, cudaMemcpyHostToDevice));
+    return PFNAV_OK;
+}
+
+// G_GetEnemyFactions (game.h:184): the factions at war with `faction_id`, bit i = faction i.
+extern "C" int pfnav_set_enemy_factions(pfnav_ctx *ctx, int faction_id, uint16_t enemies_mask)
+{
+    PF_ARG(ctx, "ctx");
+    PF_ARG(faction_id >= 0 && faction_id < 15, "faction_id");
+    ctx->enemies[faction_id] = enemies_mask;
+    ctx->faction_enabled = true;
+    ctx->map_epoch++;
+    return PFNAV_OK;
+}
+
 extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c, const uint8_t *cost_base,
                                       const uint16_t *blockers, const uint16_t *local_islands)
 {
@@ -1403,6 +1487,8 @@ static FlowGrids grids_of(const pfnav_ctx *ctx)
     FlowGrids g;
     g.cost = ctx->d_cost; g.blk = ctx->d_blk; g.liid = ctx->d_liid; g.unit = ctx->d_unit;
     g.W64 = ctx->W64; g.H64 = ctx->H64; g.chunk_w = ctx->chunk_w; g.chunk_h = ctx->chunk_h;
+    g.fmask = ctx->d_fmask;
+    for (int f = 0; f < 16; f++) g.enemies[f] = ctx->enemies[f];
     return g;
 }
 
@@ -1442,7 +1528,7 @@ int pfnav_flow_launch(pfnav_ctx *ctx, const pfnav_field_req *d_reqs, size_t n, u
     PF_CUDA(cudaGetLastError());
     bool any_nonunit = false;
     for (uint8_t u : ctx->h_unit) any_nonunit |= (u == 0);
-    if (any_nonunit) {
+    if (any_nonunit || ctx->faction_enabled) {
         const int gridg = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 8);
         k_flow_general<<<gridg, FLOWG_THREADS, 0, st>>>(g, d_reqs, (int)n, d_inout_fields, d_out_slot, 1);
         ctx->launches++;
@@ -1472,7 +1558,8 @@ static int validate_field_reqs(const pfnav_ctx *ctx, const pfnav_field_req *reqs
         const pfnav_field_req &q = reqs[i];
         PF_ARG(q.layer >= 0 && q.layer < ctx->nlayers, "field req: layer");
         PF_ARG(q.chunk_r >= 0 && q.chunk_r < ctx->chunk_h && q.chunk_c >= 0 && q.chunk_c < ctx->chunk_w, "field req: chunk");
-        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE, "field req: faction-aware (attacking) fields are not implemented");
+        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE || (q.faction_id >= 0 && q.faction_id < 15 && ctx->faction_enabled),
+               "field req: faction_id (attacking requests need pfnav_set_enemy_factions first)");
         if (q.target_type == PFNAV_TARGET_TILE) {
             PF_ARG(q.tile_r >= 0 && q.tile_r < 64 && q.tile_c >= 0 && q.tile_c < 64, "field req: tile");
         } else if (q.target_type == PFNAV_TARGET_PORTAL) {
@@ -1649,7 +1736,8 @@ extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs
         PF_ARG(q.chunk_r >= 0 && q.chunk_r < ctx->chunk_h && q.chunk_c >= 0 && q.chunk_c < ctx->chunk_w, "los req: chunk");
         PF_ARG(q.tgt_chunk_r >= 0 && q.tgt_chunk_r < ctx->chunk_h && q.tgt_chunk_c >= 0 && q.tgt_chunk_c < ctx->chunk_w, "los req: target chunk");
         PF_ARG(q.tgt_tile_r >= 0 && q.tgt_tile_r < 64 && q.tgt_tile_c >= 0 && q.tgt_tile_c < 64, "los req: target tile");
-        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE, "los req: faction-aware fields are not implemented");
+        PF_ARG(q.faction_id == PFNAV_FACTION_ID_NONE || (q.faction_id >= 0 && q.faction_id < 15 && ctx->faction_enabled),
+               "los req: faction_id (attacking requests need pfnav_set_enemy_factions first)");
         const bool dest = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
         if (dest) { PF_ARG(q.prev_index < 0, "los req: destination chunk must not name a prev field"); }
         else {

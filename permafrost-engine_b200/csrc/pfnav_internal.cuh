@@ -62,6 +62,14 @@ struct pfnav_ctx {
     uint8_t  *d_cost = nullptr;      // u8
     uint16_t *d_blk = nullptr;       // u16 blockers refcounts
     uint16_t *d_liid = nullptr;      // u16 local islands
+    // per-faction blocker refcounts (chunk->factions, nav_data.h): host counts per layer (allocated on first
+    // use, [chunk][15][4096]) and a device bit mask per tile (bit f <=> factions[f] > 0) for the "attacking"
+    // passability rule field_tile_passable_no_enemies (field.c:179)
+    uint16_t *d_fmask = nullptr;
+    std::vector<std::vector<uint8_t>> h_fac;     // [layer]
+    std::vector<uint16_t> h_fmask;               // [layer][chunk][4096]
+    uint16_t enemies[16] = {0};                  // enemies[f] = factions at war with f (G_GetEnemyFactions)
+    bool faction_enabled = false;
     uint8_t  *d_unit = nullptr;      // [layer][chunk] 1 if every passable cost in the chunk == 1
     std::vector<uint8_t> h_unit;     // host mirror
     CUtensorMap tmap_cost, tmap_blk; // rank-3 {x, y, layer}, box 64x64x1
@@ -174,6 +182,8 @@ int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int a
 
 int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const int32_t *kinds, const int32_t *args,
                            const int32_t *slots, size_t n);
+
+int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk);
 
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
        PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };

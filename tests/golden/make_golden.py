@@ -249,7 +249,58 @@ def gen_repair_pool():
     ref.close()
 
 
+def gen_faction():
+    """"attacking" requests (N_RequestPathAttacking, nav.c:3393): flow (tile + portal targets) and LOS fields whose
+    passability follows field_tile_passable_no_enemies (field.c:179) over per-faction blocker refcounts"""
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, 55, 0.12)
+    ref = pfref.RefMap(cw, ch, p)
+    rng = np.random.default_rng(3)
+    wars = [(0, 1), (0, 2), (3, 1)]
+    for a, b in wars:
+        ref.set_war(a, b)
+    blockers = []
+    for _ in range(60):
+        b = (float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)), float(rng.uniform(2, 10)), int(rng.integers(0, 4)))
+        blockers.append(b)
+        ref.blockers_incref(b[0], b[1], b[2], b[3], 0)
+    ref.update()
+    cost, blk, liid, fac = ref.cost_base(), ref.blockers(), ref.local_islands(), ref.factions()
+    ports = ref.portals()
+    specs = cases.portal_specs(ports, liid, cw, limit=24)
+    treq, texp, preq, pexp, lreq, lexp = [], [], [], [], [], []
+    for f in (0, 1, 3):
+        for chunk in range(cw * ch):
+            cr, cc = chunk // cw, chunk % cw
+            npass = np.argwhere(cost[chunk] != 255)
+            for t in npass[rng.integers(0, len(npass), 4)]:
+                q = capi.tile_req((cr, cc), (int(t[0]), int(t[1]))); q["faction_id"] = f
+                treq.append(q); texp.append(ref.flow_tile((cr, cc), (int(t[0]), int(t[1])), faction=f))
+                td = (cr, cc, int(t[0]), int(t[1]))
+                i0 = len(lreq)
+                ql = capi.los_req((cr, cc), td); ql["faction_id"] = f
+                lreq.append(ql); lexp.append(ref.los((cr, cc), td, faction=f))
+                nb = (cr, cc + 1) if cc + 1 < cw else (cr, cc - 1)
+                qn = capi.los_req(nb, td, prev_index=i0, prev_chunk=(cr, cc)); qn["faction_id"] = f
+                lreq.append(qn); lexp.append(ref.los(nb, td, prev=lexp[i0], prev_chunk=(cr, cc), faction=f))
+        for s_ in specs:
+            q = cases.portal_reqs([s_]); q["faction_id"] = f
+            preq.append(q); pexp.append(ref.flow_portal(s_[0], s_[1], s_[5], s_[6], faction=f))
+    enemies = np.zeros(16, np.uint16)
+    for a, b in wars:
+        enemies[a] |= 1 << b; enemies[b] |= 1 << a
+    np.savez_compressed(os.path.join(HERE, "faction.npz"), pathable=p, cost=cost, blk=blk, liid=liid, factions=fac,
+                        enemies=enemies, blockers=np.array(blockers, np.float32),
+                        treq=np.concatenate(treq).view(np.uint8), texp=np.stack(texp),
+                        preq=np.concatenate(preq).view(np.uint8), pexp=np.stack(pexp),
+                        lreq=np.concatenate(lreq).view(np.uint8), lexp=np.stack(lexp))
+    plain = np.stack([ref.flow_tile((int(q["chunk_r"][0]), int(q["chunk_c"][0])), (int(q["tile_r"][0]), int(q["tile_c"][0]))) for q in treq])
+    print("faction: tile fields differing from the plain rule:", int((plain != np.stack(texp)).reshape(len(treq), -1).any(axis=1).sum()), "of", len(treq))
+    ref.close()
+
+
 if __name__ == "__main__":
+    gen_faction()
     gen_repair_pool()
     gen_repair()
     gen_update("update_hz20", 61, 20)

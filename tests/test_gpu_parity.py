@@ -571,3 +571,30 @@ def test_pool_repair_chain_golden(nav):
     bad = np.nonzero((vdes != g["vdes"]).any(axis=1))[0]
     assert len(bad) == 0, (len(bad), bad[:10], vdes[bad[:5]], g["vdes"][bad[:5]])
     assert (los == g["los"]).all()
+
+
+def test_faction_fields_golden(nav):
+    """"attacking" requests (N_RequestPathAttacking): flow + LOS fields over per-faction blocker refcounts, first with
+    the reference's counts uploaded, then with the counts rebuilt by pfnav_blockers_incref(faction) + pfnav_map_commit"""
+    g = gold("faction")
+    treq, preq, lreq = g["treq"].view(capi.FIELD_REQ), g["preq"].view(capi.FIELD_REQ), g["lreq"].view(capi.LOS_REQ)
+    for mode in ("upload", "incref"):
+        nav.map_create(2, 2, 1)
+        for f in range(15):
+            nav.set_enemy_factions(f, int(g["enemies"][f]))
+        if mode == "upload":
+            nav.map_upload_layer(0, g["cost"], g["blk"], g["liid"])
+            nav.map_upload_factions(0, g["factions"])
+        else:
+            nav.map_upload_layer(0, g["cost"]); nav.map_build_nav(0)
+            for x, z, r, f in g["blockers"]:
+                nav.blockers_incref(float(x), float(z), float(r), int(f), 0)
+            nav.map_commit()
+            assert (nav.blockers(0) == g["blk"]).all() and (nav.local_islands(0) == g["liid"]).all()
+        assert (nav.flow_fields_update(treq) == g["texp"]).all(), mode
+        assert (nav.flow_fields_update(preq) == g["pexp"]).all(), mode
+        assert (nav.los_fields_create(lreq) == g["lexp"]).all(), mode
+    # a faction id without an enemy table is refused, not guessed
+    nav2_req = treq[:1].copy(); nav2_req["faction_id"] = 20
+    with pytest.raises(Exception):
+        nav.flow_fields_update(nav2_req)

@@ -144,6 +144,15 @@ def test_repair_chain_sequence_golden(pforacle):
     nav.close()
 
 
+def test_port_faction_fields_golden(pforacle):
+    """attacking requests: field_tile_passable_no_enemies (field.c:179) in flow (tile, portal) and LOS fields"""
+    g = gold("faction")
+    om = pforacle.OracleMap(2, 2, g["cost"], g["blk"], g["liid"], factions=g["factions"], enemies=g["enemies"])
+    assert (om.flow_fields_update(g["treq"].view(capi.FIELD_REQ)) == g["texp"]).all()
+    assert (om.flow_fields_update(g["preq"].view(capi.FIELD_REQ)) == g["pexp"]).all()
+    assert (om.los_fields_create(g["lreq"].view(capi.LOS_REQ)) == g["lexp"]).all()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 
@@ -389,6 +398,19 @@ def test_blockers_commit_and_route_vs_ref(pfref, pforacle):
 
 
 # ---------------------------------------------------------------- host logic + ABI surface
+def test_map_create_drops_state_of_previous_map():
+    """dirty sets / routes / per-faction counts of an earlier, larger map must not leak into the next one"""
+    nav = capi.Nav(hostonly=True)
+    p = cases.noise_map(3, 3, 5, 0.05)
+    nav.map_create(3, 3, 1); nav.map_upload_layer(0, synth.cost_from_pathable(p, 3, 3)); nav.map_build_nav(0)
+    nav.blockers_incref(-700.0, 700.0, 9.0, 2, 0)           # lands in chunk (2, 2): out of range for the next map
+    p2 = cases.noise_map(1, 1, 6, 0.05)
+    nav.map_create(1, 1, 1); nav.map_upload_layer(0, synth.cost_from_pathable(p2, 1, 1)); nav.map_build_nav(0)
+    assert nav.map_commit() == 0
+    assert not nav.blockers(0).any()
+    nav.close()
+
+
 def test_synth_is_deterministic():
     p1 = synth.make_map(2, 2, 0x5EED0002); p2 = synth.make_map(2, 2, 0x5EED0002)
     assert (p1 == p2).all() and 0.05 < (p1 == 0).mean() < 0.5
