@@ -216,9 +216,9 @@ def run_ours(args):
         return nfl
 
     def step_e2e():
+        fields_phase()                                        # asynchronous; the LOS chains overlap the upload below
         nav.agents_upload(rec_np, W["flocks"], HZ)            # H2D of the whole snapshot from pinned memory
         nav.agents_set_work(work)
-        fields_phase()
         nav.agents_tick(capi.TICK_VDES_FROM_POOL, sp)
         v = nav.agents_read_velocities(nwork)                 # D2H of the result
         return v

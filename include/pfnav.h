@@ -237,6 +237,10 @@ int  pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, float src_
                               pfnav_field_req *flow_out, uint64_t *flow_ffid, int32_t *flow_chunk,
                               int max_flow, int *n_flow, pfnav_los_req *los_out, int32_t *los_chunk,
                               int max_los, int *n_los, uint32_t *out_dest_id, int *out_ok);
+/* N_RequestPathAttacking (nav.c:3393): the faction applied to the path requests that follow (route + pool
+ * entry points); PFNAV_FACTION_ID_NONE restores N_RequestPath. It is packed into the dest_id (nav.c:853) and
+ * forwarded to every flow / LOS request, which is all n_request_path does with it. */
+int  pfnav_request_faction(pfnav_ctx *ctx, int faction_id);
 /* N_RequestPath (nav.c:3386) against the device field pool: route src -> dst exactly as the
  * reference does and build, on the device, the fields the pool does not hold yet for `dest`
  * (cached (dest, chunk) entries and their ff_ids are honoured like the field cache's). */

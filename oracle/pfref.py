@@ -36,6 +36,7 @@ def lib():
         L.pfref_los_field_faction.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_request_path.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
+        L.pfref_request_path_attacking.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
         L.pfref_dest_id.restype = C.c_uint32
         L.pfref_dest_id.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.pfref_fc_get_flow.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -162,9 +163,12 @@ class RefMap:
                               target_td[3], _p(pv), prev_chunk[0], prev_chunk[1], _p(out))
         return out.reshape(64, 64)
 
-    def request_path(self, src, dst, layer=0):
+    def request_path(self, src, dst, layer=0, faction=0xF):
         did = C.c_uint32(0)
-        ok = lib().pfref_request_path(self.h, layer, src[0], src[1], dst[0], dst[1], C.byref(did))
+        if faction != 0xF:
+            ok = lib().pfref_request_path_attacking(self.h, layer, faction, src[0], src[1], dst[0], dst[1], C.byref(did))
+        else:
+            ok = lib().pfref_request_path(self.h, layer, src[0], src[1], dst[0], dst[1], C.byref(did))
         return bool(ok), did.value
 
     def dest_id(self, dst, layer=0):

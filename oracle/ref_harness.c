@@ -532,6 +532,16 @@ PFREF_EXPORT int pfref_request_path(void *m, int layer, float sx, float sz, floa
     return ok;
 }
 
+PFREF_EXPORT int pfref_request_path_attacking(void *m, int layer, int faction_id, float sx, float sz, float dx, float dz,
+                                              uint32_t *out_dest_id)
+{
+    struct map *map = m;
+    dest_id_t id = DEST_ID_INVALID;
+    bool ok = N_RequestPathAttacking(map->nav_private, (vec2_t){sx, sz}, (vec2_t){dx, dz}, faction_id, map->pos, layer, &id);
+    *out_dest_id = id;
+    return ok;
+}
+
 PFREF_EXPORT uint32_t pfref_dest_id(void *m, int layer, float dx, float dz)
 {
     struct map *map = m;

@@ -70,6 +70,7 @@ struct pfnav_ctx {
     std::vector<uint16_t> h_fmask;               // [layer][chunk][4096]
     uint16_t enemies[16] = {0};                  // enemies[f] = factions at war with f (G_GetEnemyFactions)
     bool faction_enabled = false;
+    int req_faction = 0xF;                       // faction of the path request being planned (n_request_path's faction_id)
     uint8_t  *d_unit = nullptr;      // [layer][chunk] 1 if every passable cost in the chunk == 1
     std::vector<uint8_t> h_unit;     // host mirror
     CUtensorMap tmap_cost, tmap_blk; // rank-3 {x, y, layer}, box 64x64x1

@@ -560,7 +560,7 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
     PF_ARG(desc_for_point(ctx, src_x, src_z, &src) && desc_for_point(ctx, dst_x, dst_z, &dst), "position outside the map");
     const uint32_t dest_id = (((uint32_t)dst.chunk_r & 0x3f) << 26) | (((uint32_t)dst.chunk_c & 0x3f) << 20) |
                              (((uint32_t)dst.tile_r & 0x3f) << 14) | (((uint32_t)dst.tile_c & 0x3f) << 8) |
-                             (((uint32_t)layer & 0xf) << 4) | 0xfu;          // n_dest_id (nav.c:839), FACTION_ID_NONE
+                             (((uint32_t)layer & 0xf) << 4) | ((uint32_t)ctx->req_faction & 0xfu);   // n_dest_id (nav.c:839)
     *out_dest_id = dest_id;
     const int schunk = src.chunk_r * cw + src.chunk_c, dchunk = dst.chunk_r * cw + dst.chunk_c;
     if (RL.islands[(size_t)schunk * 4096 + src.tile_r * 64 + src.tile_c] != RL.islands[(size_t)dchunk * 4096 + dst.tile_r * 64 + dst.tile_c])
@@ -581,7 +581,7 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
         if (*n_los >= max_los) return false;
         pfnav_los_req q;
         memset(&q, 0, sizeof(q));
-        q.chunk_r = chunk / cw; q.chunk_c = chunk % cw; q.layer = layer; q.faction_id = PFNAV_FACTION_ID_NONE;
+        q.chunk_r = chunk / cw; q.chunk_c = chunk % cw; q.layer = layer; q.faction_id = ctx->req_faction;
         q.tgt_chunk_r = dst.chunk_r; q.tgt_chunk_c = dst.chunk_c; q.tgt_tile_r = dst.tile_r; q.tgt_tile_c = dst.tile_c;
         // -1: destination chunk; >= 0: request of this batch; -2: the previous chunk's field already
         // exists (have_los) and the executor substitutes its pool slot into _pad
@@ -594,7 +594,7 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
     };
     pfnav_field_req base;
     memset(&base, 0, sizeof(base));
-    base.layer = layer; base.faction_id = PFNAV_FACTION_ID_NONE;
+    base.layer = layer; base.faction_id = ctx->req_faction;
     // destination chunk field + LOS (nav.c:1815-1847)
     if (!mapped[dchunk]) {
         pfnav_field_req q = base;
@@ -1011,5 +1011,15 @@ int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int a
         newf.insert(newf.end(), tmp.begin(), tmp.end());
     }
     for (int t : newf) mask[t >> 6] |= 1ull << (t & 63);
+    return PFNAV_OK;
+}
+
+// N_RequestPathAttacking (nav.c:3393): the faction carried by the path requests that follow -- packed into the
+// dest_id and forwarded to every flow / LOS request, exactly what n_request_path does with its faction_id.
+extern "C" int pfnav_request_faction(pfnav_ctx *ctx, int faction_id)
+{
+    PF_ARG(ctx, "ctx");
+    PF_ARG(faction_id == PFNAV_FACTION_ID_NONE || (faction_id >= 0 && faction_id < 15), "faction_id");
+    ctx->req_faction = faction_id;
     return PFNAV_OK;
 }

@@ -279,6 +279,46 @@ def test_port_vs_ref_blockers(pfref, pforacle):
 
 
 # ---------------------------------------------------------------- host-side planner (host-only context: no compute)
+def test_route_request_path_attacking_vs_ref(pfref, pforacle):
+    """N_RequestPathAttacking (nav.c:3393): same route, faction packed into the dest_id and applied to every field"""
+    cw = ch = 3
+    p = cases.noise_map(cw, ch, 57, 0.1)
+    ref = pfref.RefMap(cw, ch, p)
+    rng = np.random.default_rng(8)
+    ref.set_war(0, 1); ref.set_war(0, 2)
+    for _ in range(50):
+        ref.blockers_incref(float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)),
+                            float(rng.uniform(2, 9)), int(rng.integers(0, 4)), 0)
+    ref.update()
+    cost, blk, liid, fac = ref.cost_base(), ref.blockers(), ref.local_islands(), ref.factions()
+    enemies = np.zeros(16, np.uint16); enemies[0] = 0b110; enemies[1] = 0b001; enemies[2] = 0b001
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost, blk, liid); nav.map_build_nav(0); nav.route_build(0)
+    om = pforacle.OracleMap(cw, ch, cost, blk, liid, factions=fac, enemies=enemies)
+    free = synth.blocked_to_image(cost, cw, ch) != 255
+    pairs = [pr for pr in cases.route_pairs(cost, cw, ch, 57, 40)][:12]
+    oks, dids, ffids, flows, loss, has = [], [], [], [], [], []
+    for src, dst in pairs:
+        ref.fc_clear()
+        ok, did = ref.request_path(src, dst, faction=0)
+        oks.append(ok); dids.append(did)
+        fid = np.zeros(cw * ch, np.uint64); hs = np.zeros(cw * ch, np.uint8)
+        fl = np.zeros((cw * ch, 64, 64), np.uint8); ls = np.zeros((cw * ch, 64, 64), np.uint8)
+        for c in range(cw * ch):
+            f, i = ref.fc_flow(did, (c // cw, c % cw)) if ok else (None, None)
+            l = ref.fc_los(did, (c // cw, c % cw)) if ok else None
+            if f is not None:
+                fl[c] = f; fid[c] = i; hs[c] |= 1
+            if l is not None:
+                ls[c] = l; hs[c] |= 2
+        ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs)
+    assert any(oks) and all((d & 0xF) == 0 for d, o in zip(dids, oks) if o)
+    nav.request_faction(0)
+    _check_route_against(nav, om, cw, ch, pairs, oks, dids, ffids, flows, loss, has)
+    nav.request_faction()
+    ref.close(); nav.close()
+
+
 def _check_route_against(nav, om, cw, ch, pairs, ok_e, did_e, ffid_e, flow_e, los_e, has_e):
     for k, (src, dst) in enumerate(pairs):
         ok, did, fr, fid, fc, lr, lc = nav.route_request_path(tuple(src), tuple(dst))
