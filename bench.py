@@ -40,6 +40,8 @@ MAP_SEED = 0x5EED0001          # 0x5EED0000 + config#
 CHUNKS = 16
 AGENTS_PER_GPU = 100_000
 GOALS_PER_GPU = 16
+WORKLOAD = "C2"
+C3_MODE = False
 HZ = 20
 ALG_BYTES_PER_AGENT = 360      # SURVEY.md 8d "Canonical figure"
 ALG_BYTES_PER_FLOW_FIELD = 24_704   # TARGET_PORTAL: cost 4096 + blockers 8192 + islands 8192+128 + dirs 4096
@@ -109,7 +111,12 @@ def build_workload(pf, world, rank):
     nflocks = GOALS_PER_GPU * world
     # radii in {1.5, 3.0}, spawn discs with spacing >= 2.2 r
     radii = np.where(np.arange(nflocks) % 2 == 0, 1.5, 3.0).astype(np.float32)
-    a = synth.make_agents(cost, CHUNKS, CHUNKS, n_total, nflocks, MAP_SEED, radius=radii, spacing=2.2, hz=HZ)
+    if C3_MODE:
+        # radius 1.0, 64 flocks. 1 M agents on 14 M wu^2 of passable ground cannot be sparser than
+        # ~0.07 agents/wu^2 (k10 ~ 22), so the spawn discs are sized to tile the map (spacing 4.05 r)
+        a = synth.make_agents(cost, CHUNKS, CHUNKS, n_total, nflocks, MAP_SEED + 2, radius=1.0, spacing=4.05, hz=HZ)
+    else:
+        a = synth.make_agents(cost, CHUNKS, CHUNKS, n_total, nflocks, MAP_SEED, radius=radii, spacing=2.2, hz=HZ)
     # field-pool destinations are rank-local: flock f of this rank's goal range -> dest f - g_lo
     g_lo, g_hi = shard_range(nflocks, rank, world)
     dest = np.full(nflocks, -1, np.int32)
@@ -318,7 +325,7 @@ def run_ours(args):
         "metric": "agent_updates_per_sec", "value": value, "unit": "agent-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 1024x1024-tile map (16x16 chunks), %d agents/GPU in %d flocks/GPU, %d flow-field goals/GPU "
+        "config": {"workload": WORKLOAD + ": 1024x1024-tile map (16x16 chunks), %d agents/GPU in %d flocks/GPU, %d flow-field goals/GPU "
                                "(every chunk connected to each goal), hz=20" % (AGENTS_PER_GPU, GOALS_PER_GPU, GOALS_PER_GPU),
                    "agents_total": total_agents, "goals_total": GOALS_PER_GPU * world, "map_seed": hex(MAP_SEED),
                    "parallelism": "agents+goals sharded x%d, 1 all-gather of 24-B records/tick" % world if world > 1 else "single GPU",
@@ -448,7 +455,7 @@ def run_reference(args):
         "impl": "reference", "metric": "agent_updates_per_sec", "value": value, "unit": "agent-updates/s",
         "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 1024x1024-tile map (16x16 chunks), %d agents/GPU in %d flocks/GPU, %d flow-field goals/GPU "
+        "config": {"workload": WORKLOAD + ": 1024x1024-tile map (16x16 chunks), %d agents/GPU in %d flocks/GPU, %d flow-field goals/GPU "
                                "(every chunk connected to each goal), hz=20" % (AGENTS_PER_GPU, GOALS_PER_GPU, GOALS_PER_GPU),
                    "note": "CPU arm: throughput of the reference's own code on a bounded sample of that workload; "
                            "it does not scale with --gpus (rank 0 only, world=%d)" % world},
@@ -469,7 +476,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+                    help="C2 (default, the headline config): 100k agents / 16 goals per GPU; C3: 1M agents of radius 1.0 in "
+                         "64 flocks / 64 goals (BASELINE.json configs[2]), extra evidence only")
     args = ap.parse_args()
+    if args.workload == "C3":
+        global AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE
+        AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE = 1_000_000, 64, "C3", True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -549,6 +549,7 @@ __device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int n
                                                  uint32_t lane, float &best, int &best_idx, v2 &best_p, int &any)
 {
     int next = 0, my = -1, vo = 0, myk = 0;
+    int vstart = 0;      // obstacle that swallowed this lane's previous candidate: tested first (any order is exact)
     v2 myp = {0.0f, 0.0f};
     while (true) {
         const bool need = my < 0;
@@ -562,8 +563,10 @@ __device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int n
         if (!__any_sync(FULL, my >= 0)) break;
         if (my >= 0) {
             bool finished = false, inside = false;
-            if (vo < nvo) inside = vo_contains(s, vo, myp);
-            if (inside) finished = true;
+            int vidx = vo + vstart;
+            if (vidx >= nvo) vidx -= nvo;
+            if (vo < nvo) inside = vo_contains(s, vidx, myp);
+            if (inside) { finished = true; vstart = vidx; }
             else if (++vo >= nvo) {
                 finished = true;
                 any = 1;
