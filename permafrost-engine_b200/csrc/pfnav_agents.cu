@@ -208,10 +208,20 @@ __global__ void k_desired_velocity(MapView m, PoolView pool, const pfnav_agent *
 // ------------------------------------------------------------------------------------------
 // K6b: cohesion_force (movement.c:1653). One thread per work item; members in ascending uid.
 // ------------------------------------------------------------------------------------------
+// member positions of every flock, contiguous in member-list order (one coalesced stream for k_cohesion)
+__global__ void k_gather_flock_pos(const pf_record *__restrict__ rec, const uint32_t *__restrict__ flock_members, int n,
+                                   float2 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const pf_record r = rec[flock_members[i]];
+    out[i] = make_float2(r.px, r.pz);
+}
+
 __global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent *__restrict__ agents,
                            const uint32_t *__restrict__ flock_start, const uint32_t *__restrict__ flock_members,
-                           const uint32_t *__restrict__ work, int nwork, float scaled_max_force,
-                           float2 *__restrict__ out)
+                           const float2 *__restrict__ member_pos, const uint32_t *__restrict__ work, int nwork,
+                           float scaled_max_force, float2 *__restrict__ out)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwork) return;
@@ -222,22 +232,24 @@ __global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent 
         const pf_record self = rec[uid];
         const uint32_t b = flock_start[fl], e = flock_start[fl + 1];
         v2 com = {0.0f, 0.0f};
-        uint32_t cnt = 0;
+        // The reference's sum runs over the flock in khash bucket order (movement.c:1660), i.e. it is not
+        // reproducible to the last bit anyway; what must hold is the 1e-4 velocity budget. The weight
+        // exp(-6 (|d| - 37.5) / 50) is therefore evaluated with the SFU (rsqrt + ex2, relative error < 1e-6) and
+        // the member itself is removed afterwards: its weight is exp(4.5) exactly as evaluated here for |d| = 0.
+        const float self_scale = __expf(4.5f);
         for (uint32_t k = b; k < e; k++) {
-            const uint32_t cu = flock_members[k];
-            if (cu == uid) continue;
-            const float2 p = *reinterpret_cast<const float2 *>(&rec[cu]);
-            const v2 diff = {p.x - self.px, p.y - self.pz};
-            // (len - 50*0.75) / 50 is evaluated in double by the reference and rounded once; the
-            // float form differs by <= 1 ulp of t, far inside the 1e-4 budget (cohesion's summation
-            // order is not reproducible anyway: it follows khash bucket order, movement.c:1660)
-            const float t = (v2_len(diff) - 37.5f) / 50.0f;
-            const float scale = expf(-6.0f * t);
+            const float2 p = member_pos[k];
+            const float dx = p.x - self.px, dz = p.y - self.pz;
+            const float len2 = dx * dx + dz * dz;
+            const float len = len2 * rsqrtf(fmaxf(len2, 1e-30f));
+            const float scale = __expf((len - 37.5f) * -0.12f);
             com.x += p.x * scale;
             com.z += p.y * scale;
-            cnt++;
         }
+        const uint32_t cnt = e - b - 1;
         if (cnt > 0) {
+            com.x -= self.px * self_scale;
+            com.z -= self.pz * self_scale;
             com = v2_scale(com, 1.0f / (float)cnt);
             ret = v2_sub(com, v2{self.px, self.pz});
             ret = v2_truncate(ret, scaled_max_force);
@@ -979,6 +991,7 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
+    cudaFree(ctx->d_member_pos);
     if (ctx->update_done) cudaEventDestroy(ctx->update_done);
     cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
     ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
@@ -1267,8 +1280,16 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
     {
     pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
+    if (ctx->cap_member_pos < ctx->n_agents) {
+        cudaFree(ctx->d_member_pos); ctx->d_member_pos = nullptr; ctx->cap_member_pos = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_member_pos, std::max<size_t>(ctx->n_agents, 1) * sizeof(float2)));
+        ctx->cap_member_pos = ctx->n_agents;
+    }
+    k_gather_flock_pos<<<((int)ctx->n_agents + 255) / 256, 256, 0, st>>>(ctx->d_records, ctx->d_flock_members, (int)ctx->n_agents,
+                                                                        ctx->d_member_pos);
     k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
-                                                   ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
+                                                   ctx->d_member_pos, ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
+    ctx->launches++;
     }
     // everything above is independent of the flow/LOS fields; the LOS chains forked by
     // pfnav_pool_request_goals have been running alongside it
