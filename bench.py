@@ -263,22 +263,28 @@ def run_ours(args):
         tl = torch.tensor([float(launches)], device="cuda"); dist.all_reduce(tl); launches = int(tl.item())
     # ---- per-phase device times, each phase alone between synchronisations (kernel time without the
     #      host-side gaps of the full step); used for the roofline line and flow_fields_per_sec ----
-    def phase_time(fn, iters=3):
-        ms = []
+    def phase_time(fn, iters=5):
+        """median over `iters` isolated runs of (CUDA-event time of fn, per-kernel-group times from the library)"""
+        ms, profs = [], []
         for _ in range(iters):
             flush.zero_(); torch.cuda.synchronize()
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_.record(stream); fn(); b_.record(stream); torch.cuda.synchronize()
             ms.append(a_.elapsed_time(b_))
-        return float(np.median(ms))
+            profs.append(nav.profile_read())
+        med = {k: (float(np.median([p_[k][0] for p_ in profs])), profs[0][k][1]) for k in profs[0]}
+        return float(np.median(ms)), med
     nav.profile_enable(True)
-    phase_time(lambda: (fields_phase(), nav.fields_join(sp))); prof_f = nav.profile_read()
-    phase_time(lambda: nav.agents_rebuild_index(sp)); prof_i = nav.profile_read()
-    phase_time(lambda: nav.agents_tick(capi.TICK_VDES_FROM_POOL, sp)); prof_t = nav.profile_read()
+    nav.profile_read()
+    _, prof_f = phase_time(lambda: (fields_phase(), nav.fields_join(sp)))
+    _, prof_i = phase_time(lambda: nav.agents_rebuild_index(sp))
+    tick_alone_ms, prof_t = phase_time(lambda: nav.agents_tick(capi.TICK_VDES_FROM_POOL, sp))
+    if os.environ.get("PF_BENCH_DEBUG"):
+        print("debug: tick alone %.3f ms, profile %s" % (tick_alone_ms, prof_t), file=sys.stderr)
     nav.profile_enable(False)
     prof = {"flow": prof_f["flow"], "los": prof_f["los"], "index": prof_i["index"], "vdes": prof_t["vdes"],
             "cohesion": prof_t["cohesion"], "velocity": prof_t["velocity"]}
-    prof_iters = 3
+    prof_iters = 1
     # miss counter sanity: every agent must have found its field in the pool
     vpref, vdes, los = nav.agents_read_debug(nwork)
     frac_no_dir = float((np.abs(vdes).sum(axis=1) == 0).mean())

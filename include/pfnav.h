@@ -414,6 +414,12 @@ int  pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream);
 /* Read the (updated) entity snapshot back: agents_out / ms_out may be NULL. */
 int  pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, pfnav_movestate *ms_out, size_t maxout);
 
+/* Test / tuning hook for pfnav_agents_tick: 0 = single-pass velocity kernel; 1 (default) = while LOS chains of
+ * pfnav_pool_request_goals are still in flight, run the part of the update that does not depend on the
+ * fields (neighbours, separation, velocity obstacles, admissible ray intersections) before joining them and
+ * only the final choice after; 2 = always split. Results are identical in every mode. */
+int  pfnav_set_two_phase(pfnav_ctx *ctx, int mode);
+
 /* flags for pfnav_agents_tick */
 #define PFNAV_TICK_VDES_FROM_POOL   (1u << 0)  /* compute vdes + has_dest_los on device (nav.c:3468, 4026) */
 

@@ -65,7 +65,7 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase",
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
 ]
@@ -98,6 +98,7 @@ def load():
     L.pfnav_fields_join.argtypes = [C.c_void_p, C.c_void_p]
     L.pfnav_set_enemy_factions.argtypes = [C.c_void_p, C.c_int, C.c_uint16]
     L.pfnav_request_faction.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_set_two_phase.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_map_upload_factions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_pool_repair.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_flow_fields_repair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -272,6 +273,9 @@ class Nav:
         a, b = C.c_int(0), C.c_int(0)
         _chk(self.L.pfnav_pool_repair(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def set_two_phase(self, mode):
+        _chk(self.L.pfnav_set_two_phase(self.h, mode))
 
     def request_faction(self, faction_id=FACTION_ID_NONE):
         _chk(self.L.pfnav_request_faction(self.h, faction_id))

@@ -591,9 +591,9 @@ __device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int n
     }
 }
 
-// clearpath_new_velocity (clearpath.c:552). Warp-cooperative; returns a warp-uniform status.
-__device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat,
-                                       uint32_t lane, v2 &out)
+// compute_all_hrvos / compute_all_vos (clearpath.c:216-247): the ray table of the velocity obstacles,
+// one neighbour per lane, order-preserving compaction. Returns the number of rays (2 per obstacle).
+__device__ int build_vos(VelSmem &s, const cp_ent ent, int ndyn, int nstat, uint32_t lane)
 {
     // ---- compute_all_hrvos / compute_all_vos: one neighbour per lane, order-preserving compaction ----
     int n_rays = 0;
@@ -648,6 +648,14 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
         n_rays += 2 * __popc(m);
     }
     __syncwarp();
+    return n_rays;
+}
+
+// clearpath_new_velocity (clearpath.c:552). Warp-cooperative; returns a warp-uniform status.
+__device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat,
+                                       uint32_t lane, v2 &out)
+{
+    const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
     const int nvo = n_rays >> 1;
 
     // ---- is the preferred velocity admissible? one velocity obstacle per lane ----
@@ -774,6 +782,145 @@ __device__ void remove_furthest(VelSmem &s, const v2 pos, int &ndyn, int &nstat,
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-phase ClearPath. Everything G_ClearPath_NewVelocity does except the final choice is independent of
+// the preferred velocity: the velocity obstacles depend on positions / velocities only, and so do the
+// pairwise ray intersections (compute_vo_xpoints, clearpath.c:321) and their inside-PCR tests. Phase A
+// (k_agent_velocity<1>, runs while the LOS chains are still in flight) therefore collects the ADMISSIBLE
+// intersection points of every agent; phase B (k_agent_velocity<2>, after the fields are joined) computes
+// the preferred velocity, tests it and its projections (compute_vdes_proj_points, :344) and picks the
+// nearest admissible point by (distance, sequence index) = compute_vnew's first minimum (:368).
+// ------------------------------------------------------------------------------------------
+struct pf_xpoint { float x, z; int k; };
+#define PF_PREP_XP_CAP 64
+#define PF_PREP_OVERFLOW 0xFFFFFFFFu
+struct pf_prep {
+    uint32_t ndyn, nstat, nx, _pad;
+    float sepx, sepz;
+    uint32_t dyn_id[PFNAV_MAX_NEIGHBOURS], stat_id[PFNAV_MAX_NEIGHBOURS];
+    pf_xpoint xp[PF_PREP_XP_CAP];
+};
+
+// like drain_candidates, but records every candidate that lies inside no velocity obstacle
+__device__ __forceinline__ void drain_collect(const VelSmem &s, int qn, int nvo, uint32_t lane, pf_xpoint *out, int &cnt)
+{
+    int next = 0, my = -1, vo = 0, myk = 0, vstart = 0;
+    v2 myp = {0.0f, 0.0f};
+    while (true) {
+        const bool need = my < 0;
+        const uint32_t mneed = __ballot_sync(FULL, need);
+        const int avail = qn - next;
+        if (need) {
+            const int rank = __popc(mneed & ((1u << lane) - 1));
+            if (rank < avail) { my = next + rank; vo = 0; myp = {s.cqx[my], s.cqz[my]}; myk = s.cqk[my]; }
+        }
+        next += min(__popc(mneed), avail);
+        if (!__any_sync(FULL, my >= 0)) break;
+        bool admissible = false;
+        if (my >= 0) {
+            int vidx = vo + vstart;
+            if (vidx >= nvo) vidx -= nvo;
+            bool inside = false;
+            if (vo < nvo) inside = vo_contains(s, vidx, myp);
+            if (inside) { my = -1; vstart = vidx; }
+            else if (++vo >= nvo) { admissible = true; my = -1; }
+        }
+        const uint32_t ma = __ballot_sync(FULL, admissible);
+        if (admissible) {
+            const int q = cnt + __popc(ma & ((1u << lane) - 1));
+            if (q < PF_PREP_XP_CAP) { out[q].x = myp.x; out[q].z = myp.z; out[q].k = myk; }
+        }
+        cnt += __popc(ma);
+    }
+}
+
+// phase A: admissible ray-pair intersections of one agent -> out[0..cnt) (cnt > cap = overflow)
+__device__ int clearpath_collect(VelSmem &s, const cp_ent ent, int ndyn, int nstat, uint32_t lane, pf_xpoint *out)
+{
+    const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
+    const int nvo = n_rays >> 1, npairs = n_rays * n_rays;
+    int cnt = 0, qn = 0;
+    int i = 0, j = (int)lane;
+    while (j >= n_rays && n_rays > 0) { j -= n_rays; i++; }
+    for (int base = 0; base < npairs; base += 32) {
+        const int k = base + (int)lane;
+        v2 p = {0.f, 0.f};
+        bool ok = false;
+        if (k < npairs && i != j) {
+            const v2 p1 = {s.rpx[i], s.rpz[i]}, p2 = {s.rpx[j], s.rpz[j]};
+            if (line_isect_s(p1, s.rsl[i], p2, s.rsl[j], p)) {
+                ok = !(quot_lt0(p.x - p1.x, s.rdx[i]) || quot_lt0(p.z - p1.z, s.rdz[i]) ||
+                       quot_lt0(p.x - p2.x, s.rdx[j]) || quot_lt0(p.z - p2.z, s.rdz[j]));
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, ok);
+        if (ok) {
+            const int q = qn + __popc(m & ((1u << lane) - 1));
+            s.cqx[q] = p.x; s.cqz[q] = p.z; s.cqk[q] = k;
+        }
+        qn += __popc(m);
+        j += 32;
+        while (j >= n_rays) { j -= n_rays; i++; }
+        if (qn > CQ_CAP - 32 || base + 32 >= npairs) {
+            __syncwarp();
+            drain_collect(s, qn, nvo, lane, out, cnt);
+            __syncwarp();
+            qn = 0;
+        }
+    }
+    return cnt;
+}
+
+// phase B: the choice among {des_v, its projections on the rays, the stored admissible intersections}
+__device__ bool clearpath_finish(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat, uint32_t lane,
+                                 const pf_xpoint *xp, int nx, v2 &out)
+{
+    const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
+    const int nvo = n_rays >> 1, npairs = n_rays * n_rays;
+    const v2 des_v_ws = v2_add(ent.pos, des_v);
+    bool in_any = false;
+    for (int i = lane; i < nvo; i += 32) in_any |= vo_contains(s, i, des_v_ws);
+    if (!__any_sync(FULL, in_any)) { out = des_v; return true; }
+    float best = __int_as_float(0x7f800000);
+    int best_idx = 0x7fffffff;
+    v2 best_p = {0.0f, 0.0f};
+    int any = 0, qn = 0;
+    for (int base = 0; base < n_rays; base += 32) {
+        const int r = base + (int)lane;
+        if (r < n_rays) {
+            const v2 d = {s.rdx[r], s.rdz[r]};
+            const float len = v2_dot(d, des_v);
+            const v2 p = v2_add(v2{s.rpx[r], s.rpz[r]}, v2_scale(d, len));
+            s.cqx[qn + (int)lane] = p.x; s.cqz[qn + (int)lane] = p.z; s.cqk[qn + (int)lane] = npairs + r;
+        }
+        qn += min(32, n_rays - base);
+        if (qn > CQ_CAP - 32 || base + 32 >= n_rays) {
+            __syncwarp();
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            __syncwarp();
+            qn = 0;
+        }
+    }
+    for (int q = lane; q < nx; q += 32) {       // the intersections phase A found admissible
+        const pf_xpoint c = xp[q];
+        const v2 curr = v2_sub(v2{c.x, c.z}, ent.pos);
+        const float len = v2_len(v2_sub(des_v, curr));
+        any = 1;
+        if (len < best || (len == best && best_idx != 0x7fffffff && c.k < best_idx)) { best = len; best_idx = c.k; best_p = curr; }
+    }
+    any = __any_sync(FULL, any);
+    if (!any) return false;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, off);
+        const int oi = __shfl_xor_sync(FULL, best_idx, off);
+        const float ox = __shfl_xor_sync(FULL, best_p.x, off), oz = __shfl_xor_sync(FULL, best_p.z, off);
+        if (ob < best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; best_p = {ox, oz}; }
+    }
+    out = (best_idx == 0x7fffffff) ? v2{0.0f, 0.0f} : best_p;
+    return true;
+}
+
 struct TickParams {
     int hz;
     float scaled_max_force;       // (float)SCALED_MAX_FORCE, as passed to vec2_truncate
@@ -783,13 +930,15 @@ struct TickParams {
 // ------------------------------------------------------------------------------------------
 // K6c: one warp per agent
 // ------------------------------------------------------------------------------------------
+// MODE 0: the whole update in one pass. MODE 1 / 2: phase A / phase B of the two-phase scheme above.
+template <int MODE>
 __global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, 4)
 k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__restrict__ agents,
                  const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
                  const uint8_t *__restrict__ los_in, const float2 *__restrict__ cohesion_in,
                  float2 *__restrict__ vel_out, float2 *__restrict__ vpref_out, int filter_garr,
-                 uint32_t *__restrict__ nb_scratch)
+                 uint32_t *__restrict__ nb_scratch, pf_prep *__restrict__ prep)
 {
     __shared__ VelSmem smem[VEL_WARPS_PER_CTA];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -801,14 +950,14 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
         const uint32_t ent_flags = a.flags & 0xFFFFFFu;
         // COMBAT_HELD (movement.c:3405)
         if (ent_flags & PFNAV_FLAG_COMBAT_HELD) {
-            if (lane == 0) { vel_out[w] = make_float2(0.f, 0.f); vpref_out[w] = make_float2(0.f, 0.f); }
+            if (MODE != 1 && lane == 0) { vel_out[w] = make_float2(0.f, 0.f); vpref_out[w] = make_float2(0.f, 0.f); }
             continue;
         }
         const v2 pos = {a.pos[0], a.pos[1]};
         const v2 velocity = {a.velocity[0], a.velocity[1]};
-        const float2 vd = vdes_in[w];
+        const float2 vd = MODE == 1 ? make_float2(0.f, 0.f) : vdes_in[w];      // phase A runs before the fields exist
         const v2 vdes = {vd.x, vd.y};
-        const bool has_los = los_in[w] != 0;
+        const bool has_los = MODE == 1 ? false : los_in[w] != 0;
         const float hzf = (float)tp.hz;
 
         v2 vpref = {0.0f, 0.0f};
@@ -817,6 +966,10 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
         } else {
             // ================= point_seek_vpref (movement.c:1870) =================
             // ---- separation_force (movement.c:1690): 30-wu query, first 128 hits in index order ----
+            v2 separation = {0.0f, 0.0f};
+            if (MODE == 2) {
+                separation = {prep[w].sepx, prep[w].sepz};
+            } else {
             int num_near = 0;
             grid_query(g, pos.x, pos.z, 30.0f, lane, [&](bool hit, uint32_t id) -> bool {
                 const uint32_t mk = __ballot_sync(FULL, hit);
@@ -849,7 +1002,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                 s.term[k] = term;
             }
             __syncwarp();
-            v2 separation = {0.0f, 0.0f};
+            separation = {0.0f, 0.0f};
             for (int k = 0; k < num_near; k++) {         // the reference's summation order
                 const float2 t = s.term[k];
                 separation.x += t.x;
@@ -860,6 +1013,9 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                 separation = v2_scale(separation, -1.0f);
                 separation = v2_truncate(separation, tp.scaled_max_force);
             }
+                if (MODE == 1 && lane == 0) { prep[w].sepx = separation.x; prep[w].sepz = separation.z; }
+            }
+            if (MODE == 1) { /* the rest of point_seek_vpref needs the desired velocity: phase B */ } else {
             // ---- arrive_force_point (movement.c:1546) ----
             const v2 target = a.flock >= 0 ? v2{flocks[a.flock].target[0], flocks[a.flock].target[1]} : pos;
             v2 desired;
@@ -906,10 +1062,23 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             }
             const v2 accel = v2_scale(steer, 1.0f / 1.0f);
             vpref = v2_truncate(v2_add(velocity, accel), a.speed / hzf);
+            }
         }
 
         // ================= find_neighbours (movement.c:2768) =================
         int ndyn = 0, nstat = 0, raw = 0;
+        if (MODE == 2) {
+            // phase A stored the neighbour lists (ids, in the reference's order); rebuild the cp_ents
+            ndyn = (int)prep[w].ndyn; nstat = (int)prep[w].nstat;
+            for (int k = lane; k < ndyn + nstat; k += 32) {
+                const bool isst = k >= ndyn;
+                const pf_record r = rec[isst ? prep[w].stat_id[k - ndyn] : prep[w].dyn_id[k]];
+                cp_ent nd;
+                nd.pos = {r.px, r.pz}; nd.radius = r.radius;
+                nd.vel = isst ? v2{0.0f, 0.0f} : v2{r.vx, r.vz};
+                if (isst) s.stat[k - ndyn] = nd; else s.dyn[k] = nd;
+            }
+        }
         auto classify = [&](bool hit, uint32_t id) -> bool {
             const uint32_t mk = __ballot_sync(FULL, hit);
             const int rrank = __popc(mk & ((1u << lane) - 1));
@@ -928,14 +1097,16 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                 }
             }
             const uint32_t md = __ballot_sync(FULL, isdyn), ms = __ballot_sync(FULL, isstat);
-            if (isdyn) { const int k = ndyn + __popc(md & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) s.dyn[k] = nd; }
-            if (isstat) { const int k = nstat + __popc(ms & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) s.stat[k] = nd; }
+            if (isdyn) { const int k = ndyn + __popc(md & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) { s.dyn[k] = nd; if (MODE == 1) prep[w].dyn_id[k] = id; } }
+            if (isstat) { const int k = nstat + __popc(ms & ((1u << lane) - 1)); if (k < PFNAV_MAX_NEIGHBOURS) { s.stat[k] = nd; if (MODE == 1) prep[w].stat_id[k] = id; } }
             ndyn = min(ndyn + __popc(md), PFNAV_MAX_NEIGHBOURS);
             nstat = min(nstat + __popc(ms), PFNAV_MAX_NEIGHBOURS);
             raw += __popc(mk);
             return raw >= 512;
         };
-        if (!filter_garr) {
+        if (MODE == 2) {
+            // nothing to gather
+        } else if (!filter_garr) {
             grid_query(g, pos.x, pos.z, 10.0f, lane, classify);
         } else {
             // garrisoned entities exist: G_Pos_EntsInCircleFrom (position.c:379) first takes the raw hits (<= 512),
@@ -961,8 +1132,27 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
 
         // ================= G_ClearPath_NewVelocity (clearpath.c:694) =================
         const cp_ent self = {{a.prev_pos[0], a.prev_pos[1]}, velocity, a.radius};
+        if (MODE == 1) {
+            const int nx = clearpath_collect(s, self, ndyn, nstat, lane, prep[w].xp);
+            if (lane == 0) {
+                prep[w].ndyn = (uint32_t)ndyn; prep[w].nstat = (uint32_t)nstat;
+                prep[w].nx = nx > PF_PREP_XP_CAP ? PF_PREP_OVERFLOW : (uint32_t)nx;
+            }
+            __syncwarp();
+            continue;
+        }
         v2 new_vel = {0.0f, 0.0f};
-        while (true) {
+        bool done = false;
+        if (MODE == 2 && prep[w].nx != PF_PREP_OVERFLOW) {
+            v2 r;
+            if (clearpath_finish(s, self, vpref, ndyn, nstat, lane, prep[w].xp, (int)prep[w].nx, r)) { new_vel = r; done = true; }
+            else {
+                // no admissible point at all: drop the furthest neighbour and retry in one pass (clearpath.c:702-713)
+                remove_furthest(s, self.pos, ndyn, nstat, lane);
+                if (!(ndyn > 0 && nstat > 0)) { new_vel = {0.0f, 0.0f}; done = true; }
+            }
+        }
+        while (!done) {
             v2 r;
             const bool found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r);
             if (found) { new_vel = r; break; }
@@ -991,7 +1181,7 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
-    cudaFree(ctx->d_member_pos);
+    cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep);
     if (ctx->update_done) cudaEventDestroy(ctx->update_done);
     cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
     ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
@@ -1291,6 +1481,32 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
                                                    ctx->d_member_pos, ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
     ctx->launches++;
     }
+    const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
+    if (ctx->any_garrisoned && ctx->nb_scratch_warps < (size_t)ctas * VEL_WARPS_PER_CTA) {
+        // per-warp raw neighbour lists for the garrisoned-filter path (find_neighbours, 512 ids each)
+        cudaFree(ctx->d_nb_scratch); ctx->d_nb_scratch = nullptr; ctx->nb_scratch_warps = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_nb_scratch, (size_t)ctas * VEL_WARPS_PER_CTA * 512 * sizeof(uint32_t)));
+        ctx->nb_scratch_warps = (size_t)ctas * VEL_WARPS_PER_CTA;
+    }
+    // Two-phase velocity update while LOS chains are still in flight on the field stream: the part of
+    // ClearPath that does not depend on the preferred velocity (neighbours, velocity obstacles, admissible
+    // ray intersections) runs now, next to them; only the choice waits for the fields.
+    bool two_phase = ctx->two_phase && (ctx->two_phase_force ||
+                                        (ctx->los_inflight && cudaEventQuery(ctx->ev_los) == cudaErrorNotReady));
+    cudaGetLastError();
+    if (two_phase && ctx->cap_prep < (size_t)nwork) {
+        cudaFree(ctx->d_prep); ctx->d_prep = nullptr; ctx->cap_prep = 0;
+        if (cudaMalloc(&ctx->d_prep, (size_t)nwork * sizeof(pf_prep)) == cudaSuccess) ctx->cap_prep = (size_t)nwork;
+        else { cudaGetLastError(); two_phase = false; }         // no room: fall back to the single pass
+    }
+    if (two_phase) {
+        pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
+        k_agent_velocity<1><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+                                                                    ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
+                                                                    ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep);
+        ctx->launches++;
+    }
     // everything above is independent of the flow/LOS fields; the LOS chains forked by
     // pfnav_pool_request_goals have been running alongside it
     PF_CUDA(pf_fields_join(ctx, st));
@@ -1308,17 +1524,16 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     }
     }
     pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
-    const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
-    if (ctx->any_garrisoned && ctx->nb_scratch_warps < (size_t)ctas * VEL_WARPS_PER_CTA) {
-        // per-warp raw neighbour lists for the garrisoned-filter path (find_neighbours, 512 ids each)
-        cudaFree(ctx->d_nb_scratch); ctx->d_nb_scratch = nullptr; ctx->nb_scratch_warps = 0;
-        PF_CUDA(cudaMalloc(&ctx->d_nb_scratch, (size_t)ctas * VEL_WARPS_PER_CTA * 512 * sizeof(uint32_t)));
-        ctx->nb_scratch_warps = (size_t)ctas * VEL_WARPS_PER_CTA;
-    }
-    k_agent_velocity<<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
-                                                             ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
-                                                             ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
-                                                             ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch);
+    if (two_phase)
+        k_agent_velocity<2><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+                                                                    ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
+                                                                    ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep);
+    else
+        k_agent_velocity<0><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+                                                                    ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
+                                                                    ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, nullptr);
     ctx->launches += 3;
     PF_CUDA(cudaGetLastError());
     prof.~pf_prof_scope(); prof.a = nullptr;
@@ -1928,5 +2143,15 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
     if (!tg.empty() || nreq) ctx->goal_batch.valid = ctx->goal_batch.valid && tg.empty();   // pool bytes changed under a resident plan
     if (out_nrequests) *out_nrequests = nreq;
     if (out_nrepairs) *out_nrepairs = (int)tg.size();
+    return PFNAV_OK;
+}
+
+// Test / tuning hook: 0 = always the single-pass velocity kernel, 1 (default) = split it around the field join
+// whenever LOS chains are still in flight, 2 = always split (exercises the two-phase path without fields).
+extern "C" int pfnav_set_two_phase(pfnav_ctx *ctx, int mode)
+{
+    PF_ARG(ctx && mode >= 0 && mode <= 2, "mode");
+    ctx->two_phase = mode != 0;
+    ctx->two_phase_force = mode == 2;
     return PFNAV_OK;
 }

@@ -110,6 +110,8 @@ struct pfnav_ctx {
     uint32_t *d_flock_members = nullptr;  // agent ids grouped by flock, ascending uid
     float2   *d_cohesion = nullptr;       // per-agent cohesion force (pre-pass)
     float2   *d_member_pos = nullptr; size_t cap_member_pos = 0;   // positions in flock-member order
+    void *d_prep = nullptr; size_t cap_prep = 0;                   // phase-A results of the two-phase velocity update
+    bool two_phase = true, two_phase_force = false;
     // spatial index (bitmap_grid.h equivalent)
     int grid_w = 0, grid_h = 0; int32_t origin_x = 0, origin_y = 0;
     uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;

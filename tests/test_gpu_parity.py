@@ -598,3 +598,26 @@ def test_faction_fields_golden(nav):
     nav2_req = treq[:1].copy(); nav2_req["faction_id"] = 20
     with pytest.raises(Exception):
         nav.flow_fields_update(nav2_req)
+
+
+@pytest.mark.parametrize("name,cw", [("agents_dense", 1), ("agents_3x3", 3), ("update_hz20", 3)])
+def test_two_phase_velocity_update_is_bit_identical(nav, name, cw):
+    """the split velocity update (phase A before the field join, phase B after) returns exactly what the single
+    pass returns -- and both match the reference -- including agents with no admissible velocity, COMBAT_HELD
+    and GARRISONED entities"""
+    g = gold(name)
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    _upload(nav, cw, cw, g["cost"])
+    out = {}
+    try:
+        for mode in (0, 2):
+            nav.set_two_phase(mode)
+            nav.agents_upload(rec, fl, 20)
+            nav.agents_set_work(g["work"])
+            nav.agents_tick(0)
+            out[mode] = (nav.agents_read_velocities(len(g["work"])), nav.agents_read_debug(len(g["work"]))[0])
+    finally:
+        nav.set_two_phase(1)
+    assert (out[0][0] == out[2][0]).all() and (out[0][1] == out[2][1]).all()
+    assert (cases.relerr(out[2][0], g["vel"]) <= VEL_RTOL).mean() >= 0.995
