@@ -287,6 +287,10 @@ int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, 
  * does not read fields (position index, cohesion) overlaps them; pfnav_agents_tick and the pool entry
  * points order themselves after it. A caller that reads pool LOS fields through raw device pointers
  * on its own stream calls this first. */
+/* Profiling aid: per-field trace of the LOS launches. enable != 0 arms it for the following launches; with
+ * out != NULL the trace of the last traced launch is returned first: out[4i..4i+3] = {taken, dependency
+ * satisfied, finished} in %globaltimer nanoseconds and 1 + heap pops (0 = zero-filled early out). */
+int  pfnav_los_trace(pfnav_ctx *ctx, int enable, unsigned long long *out, size_t cap, size_t *out_n);
 int  pfnav_fields_join(pfnav_ctx *ctx, void *stream);
 /* On-miss chain of N_DesiredPointSeekVelocity (nav.c:3484-3554) for the uploaded work list, against the pool:
  * every work agent whose own tile has no direction (field absent or FD_NONE) is collected on the device; per

@@ -841,7 +841,8 @@ __device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
 
 __global__ void __launch_bounds__(LOS_WARPS_PER_CTA * 32)
 k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
-      uint8_t *fields, const int32_t *__restrict__ out_slot, unsigned *counter, int *done)
+      uint8_t *fields, const int32_t *__restrict__ out_slot, unsigned *counter, int *done,
+      unsigned long long *trace)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -856,6 +857,8 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
         const pfnav_los_req q = reqs[i];
+        unsigned long long t_take = 0, t_ready = 0;
+        if (trace && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_take));
         if (q.prev_index >= 0) {
             if (lane == 0) {
                 volatile int *flag = done + q.prev_index;
@@ -864,6 +867,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
             __syncwarp();
             __threadfence();
         }
+        if (trace && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ready));
         // A chunk other than the destination whose shared edge with the previous chunk carries no
         // `visible` and no `wavefront_blocked` tile starts with an empty frontier and draws no line
         // (field.c:2157-2195): the field is all zero. Most chunks far from the goal end here.
@@ -881,7 +885,13 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                 for (int j = lane; j < 256; j += 32) d4[j] = make_uint4(0, 0, 0, 0);
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) *(volatile int *)(done + i) = 1;
+                if (lane == 0) {
+                    *(volatile int *)(done + i) = 1;
+                    if (trace) {
+                        unsigned long long t_done; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
+                        trace[4 * (size_t)i] = t_take; trace[4 * (size_t)i + 1] = t_ready; trace[4 * (size_t)i + 2] = t_done; trace[4 * (size_t)i + 3] = (unsigned long long)(unsigned)(q.prev_index + 1) << 32;
+                    }
+                }
                 continue;
             }
         }
@@ -929,6 +939,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
         }
         __syncwarp();
 
+        unsigned npops = 0;
         if (lane == 0) {
             uint16_t *h = s.heap;
             int size = 0;
@@ -961,6 +972,7 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                 }
             }
             while (size > 0) {
+                npops++;
                 const uint16_t cur = heap_pop(h, size);
                 const int r = (cur >> 6) & 63, c = cur & 63;
                 const uint16_t nprio = (uint16_t)((((cur >> 12) + 1) & 3) << 12);
@@ -969,23 +981,44 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                 const int rm = max(r - 1, 0), rp = min(r + 1, 63), rmm = max(r - 2, 0), rpp = min(r + 2, 63);
                 const uint64_t b_m = s.blk[rm], b_0 = s.blk[r], b_p = s.blk[rp];
                 const uint64_t o_m = s.open[rm], o_0 = s.open[r], o_p = s.open[rp];
-                uint64_t a_m = s.assigned[rm], a_0 = s.assigned[r], a_p = s.assigned[rp];
+                const uint64_t a_m = s.assigned[rm], a_0 = s.assigned[r], a_p = s.assigned[rp];
                 const uint64_t p_mm = s.pass[rmm], p_m = s.pass[rm], p_0 = s.pass[r], p_p = s.pass[rp], p_pp = s.pass[rpp];
-                const uint64_t a_m0 = a_m, a_00 = a_0, a_p0 = a_p;
                 // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0). The list
                 // (incl. the wavefront_blocked filter) is collected before any neighbour is processed
-                // (field.c:2205): a line drawn for an earlier neighbour of this pop must not hide a later one
-                const bool t0 = r > 0 && !((b_m >> c) & 1), t1 = c > 0 && !((b_0 >> (c - 1)) & 1);
-                const bool t2 = c < 63 && !((b_0 >> (c + 1)) & 1), t3 = r < 63 && !((b_p >> c) & 1);
+                // (field.c:2205): a line drawn for an earlier neighbour of this pop must not hide a later one.
+                // The four neighbours are distinct tiles, so their tests are independent of each other: they are
+                // evaluated branch-free side by side (this loop is one thread's dependent chain -- ILP is all
+                // there is); only the rare corner / blocked-line case branches.
+                const int cl = (c + 63) & 63, cg = (c + 1) & 63;          // c-1 / c+1 as shift counts
+                const bool t0 = r > 0 && !((b_m >> c) & 1), t1 = c > 0 && !((b_0 >> cl) & 1);
+                const bool t2 = c < 63 && !((b_0 >> cg) & 1), t3 = r < 63 && !((b_p >> c) & 1);
+                const bool o0 = (o_m >> c) & 1, o1 = (o_0 >> cl) & 1, o2 = (o_0 >> cg) & 1, o3 = (o_p >> c) & 1;
+                const bool v0 = t0 && o0, v1 = t1 && o1, v2 = t2 && o2, v3 = t3 && o3;     // become visible
+                const bool p0 = v0 && !((a_m >> c) & 1), p1 = v1 && !((a_0 >> cl) & 1);
+                const bool p2 = v2 && !((a_0 >> cg) & 1), p3 = v3 && !((a_p >> c) & 1);    // first visit: push
+                const uint64_t bitc = 1ull << c;
+                if (v0) s.visb[(r - 1) * 64 + c] = 1;
+                if (v1) s.visb[r * 64 + cl] = 1;
+                if (v2) s.visb[r * 64 + cg] = 1;
+                if (v3) s.visb[(r + 1) * 64 + c] = 1;
+                if (p0) s.assigned[r - 1] = a_m | bitc;
+                if (p1 || p2) s.assigned[r] = a_0 | (p1 ? 1ull << cl : 0ull) | (p2 ? 1ull << cg : 0ull);
+                if (p3) s.assigned[r + 1] = a_p | bitc;
+                const uint16_t base0 = (uint16_t)(nprio | (r << 6) | c);
+                int sz = size;
+                if (p0) h[++sz] = (uint16_t)(base0 - 64);
+                if (p1) h[++sz] = (uint16_t)(base0 - 1);
+                if (p2) h[++sz] = (uint16_t)(base0 + 1);
+                if (p3) h[++sz] = (uint16_t)(base0 + 64);
+                size = sz;
+                if ((t0 && !o0) | (t1 && !o1) | (t2 && !o2) | (t3 && !o3)) {
+                    // an impassable (or cost > 1) neighbour that is not wavefront-blocked: field_is_los_corner
+                    // (field.c:435) on the preloaded passable rows, then the blocked line
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const bool take = e == 0 ? t0 : e == 1 ? t1 : e == 2 ? t2 : t3;
-                    if (!take) continue;
-                    const int rr = e == 0 ? r - 1 : e == 3 ? r + 1 : r, cc = e == 1 ? c - 1 : e == 2 ? c + 1 : c;
-                    const uint64_t bit = 1ull << cc;
-                    const uint64_t orow = e == 0 ? o_m : e == 3 ? o_p : o_0;
-                    if (!(orow & bit)) {
-                        // field_is_los_corner (field.c:435) on the preloaded passable rows
+                    for (int e = 0; e < 4; e++) {
+                        const bool k = e == 0 ? (t0 && !o0) : e == 1 ? (t1 && !o1) : e == 2 ? (t2 && !o2) : (t3 && !o3);
+                        if (!k) continue;
+                        const int rr = e == 0 ? r - 1 : e == 3 ? r + 1 : r, cc = e == 1 ? c - 1 : e == 2 ? c + 1 : c;
                         const uint64_t up = e == 0 ? p_mm : e == 3 ? p_0 : p_m;     // row rr-1
                         const uint64_t dn = e == 0 ? p_0 : e == 3 ? p_pp : p_p;     // row rr+1
                         const uint64_t me = e == 0 ? p_m : e == 3 ? p_p : p_0;      // row rr
@@ -995,18 +1028,8 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                         if (!corner) continue;
                         los_blocked_line(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
                                          q.chunk_r, q.chunk_c, rr, cc);
-                    } else {
-                        s.visb[rr * 64 + cc] = 1;
-                        uint64_t &arow = e == 0 ? a_m : e == 3 ? a_p : a_0;
-                        if (!(arow & bit)) {
-                            arow |= bit;
-                            h[++size] = (uint16_t)(nprio | (rr << 6) | cc);
-                        }
                     }
                 }
-                if (r > 0 && a_m != a_m0) s.assigned[r - 1] = a_m;
-                if (a_0 != a_00) s.assigned[r] = a_0;
-                if (r < 63 && a_p != a_p0) s.assigned[r + 1] = a_p;
             }
         }
         __syncwarp();
@@ -1037,7 +1060,13 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
         }
         __threadfence();
         __syncwarp();
-        if (lane == 0) *(volatile int *)(done + i) = 1;
+        if (lane == 0) {
+            *(volatile int *)(done + i) = 1;
+            if (trace) {
+                unsigned long long t_done; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
+                trace[4 * (size_t)i] = t_take; trace[4 * (size_t)i + 1] = t_ready; trace[4 * (size_t)i + 2] = t_done; trace[4 * (size_t)i + 3] = ((unsigned long long)(unsigned)(q.prev_index + 1) << 32) | (npops + 1);
+            }
+        }
     }
 }
 
@@ -1146,6 +1175,7 @@ void pfnav_fields_free(pfnav_ctx *ctx)
     free_map(ctx);
     cudaFree(ctx->d_stage); ctx->d_stage = nullptr;
     cudaFree(ctx->d_los_sched); ctx->d_los_sched = nullptr; ctx->los_sched_bytes = 0;
+    cudaFree(ctx->d_los_trace); ctx->d_los_trace = nullptr; ctx->los_trace_cap = 0;
     cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
     ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
 }
@@ -1712,10 +1742,18 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
         ctx->los_sched_bytes = need * 2;
     }
     PF_CUDA(cudaMemsetAsync(ctx->d_los_sched, 0, need, st));
+    if (ctx->los_trace_on && ctx->los_trace_cap < n) {
+        PF_CUDA(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_los_trace); ctx->d_los_trace = nullptr; ctx->los_trace_cap = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_los_trace, n * 4 * sizeof(unsigned long long)));
+        ctx->los_trace_cap = n;
+    }
     pf_prof_scope prof(ctx, st, PF_PROF_LOS);
     const int grid = std::max(1, std::min((int)((n + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA), ctx->sm_count * 3));
     k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, st>>>(g, mi, d_reqs, (int)n, d_out_fields, d_out_slot,
-                                                      (unsigned *)ctx->d_los_sched, (int *)ctx->d_los_sched + 1);
+                                                      (unsigned *)ctx->d_los_sched, (int *)ctx->d_los_sched + 1,
+                                                      ctx->los_trace_on ? ctx->d_los_trace : nullptr);
+    ctx->los_trace_n = ctx->los_trace_on ? std::min(n, ctx->los_trace_cap) : 0;
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFNAV_OK;
@@ -1778,5 +1816,22 @@ extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs
         return PFNAV_ERR_CUDA;
     }
     for (size_t k = 0; k < n; k++) memcpy(out_fields + (size_t)order[k] * 4096, tmp.data() + k * 4096, 4096);
+    return PFNAV_OK;
+}
+
+// Per-field trace of the last LOS launch (debug / profiling aid): for request i, out[4i..4i+3] =
+// {taken, dependency satisfied, finished} in %globaltimer ns, and (prev_index + 1) << 32 | (1 + heap pops; 0 = zero-filled early out).
+extern "C" int pfnav_los_trace(pfnav_ctx *ctx, int enable, unsigned long long *out, size_t cap, size_t *out_n)
+{
+    PF_ARG(ctx, "ctx");
+    PF_NEED_DEVICE(ctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    if (out && out_n) {
+        PF_CUDA(cudaDeviceSynchronize());
+        const size_t n = std::min(cap, ctx->los_trace_n);
+        if (n) PF_CUDA(cudaMemcpy(out, ctx->d_los_trace, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        *out_n = n;
+    }
+    ctx->los_trace_on = enable != 0;
     return PFNAV_OK;
 }
