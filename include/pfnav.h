@@ -133,6 +133,11 @@ int  pfnav_map_upload_factions(pfnav_ctx *ctx, int layer, const uint8_t *faction
  * Layers the context does not hold are skipped. Host-side; the device sees the change at commit. */
 int  pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags);
 int  pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags);
+/* N_BlockersIncrefOBB / N_BlockersDecrefOBB (nav.c:4685-4705): building footprints. corners_xz = the bottom
+ * face of the engine's `struct obb`: corners[0], [1], [5], [4] as 4 (x, z) pairs (M_Tile_AllUnderObj,
+ * tile.c:594-599). All four corners must lie inside the map. */
+int  pfnav_blockers_incref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
+int  pfnav_blockers_decref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
 int  pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out);
 /* N_Update + N_ApplyDeferredInvalidations (nav.c:2119-2223): for every chunk whose occupancy
  * changed, recompute the local islands, refresh the portal edge states, push the chunk's blockers +

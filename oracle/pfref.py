@@ -45,6 +45,7 @@ def lib():
         L.pfref_desired_velocity.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.pfref_blockers.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
+        L.pfref_blockers_obb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint32]
         L.pfref_update.argtypes = [C.c_void_p]
         L.pfref_clearpath.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pfref_agents_set.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -203,6 +204,10 @@ class RefMap:
 
     def blockers_decref(self, x, z, radius, faction=0, flags=0):
         lib().pfref_blockers(self.h, 0, x, z, radius, faction, flags)
+
+    def blockers_obb(self, corners_xz, incref=True, faction=0, flags=0):
+        c = np.ascontiguousarray(corners_xz, np.float32).reshape(8)
+        lib().pfref_blockers_obb(self.h, int(incref), _p(c), faction, flags)
 
     def update(self):
         lib().pfref_update(self.h)

@@ -605,6 +605,19 @@ PFREF_EXPORT void pfref_blockers(void *m, int incref, float x, float z, float ra
     else       N_BlockersDecref((vec2_t){x, z}, radius, faction_id, flags, map->pos, map->nav_private);
 }
 
+/* N_BlockersIncrefOBB / DecrefOBB (nav.c:4685): corners_xz = bottom face corners[0], [1], [5], [4] */
+PFREF_EXPORT void pfref_blockers_obb(void *m, int incref, const float *corners_xz, int faction_id, uint32_t flags)
+{
+    struct map *map = m;
+    struct obb obb;
+    memset(&obb, 0, sizeof(obb));
+    const int idx[4] = {0, 1, 5, 4};
+    for(int i = 0; i < 4; i++)
+        obb.corners[idx[i]] = (vec3_t){corners_xz[2*i], 0.0f, corners_xz[2*i+1]};
+    if(incref) N_BlockersIncrefOBB(map->nav_private, faction_id, flags, map->pos, &obb);
+    else       N_BlockersDecrefOBB(map->nav_private, faction_id, flags, map->pos, &obb);
+}
+
 PFREF_EXPORT void pfref_update(void *m)
 {
     struct map *map = m;

@@ -65,7 +65,7 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase", "pfnav_los_trace",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase", "pfnav_los_trace", "pfnav_blockers_incref_obb", "pfnav_blockers_decref_obb",
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
 ]
@@ -99,6 +99,8 @@ def load():
     L.pfnav_set_enemy_factions.argtypes = [C.c_void_p, C.c_int, C.c_uint16]
     L.pfnav_request_faction.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_set_two_phase.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_blockers_incref_obb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
+    L.pfnav_blockers_decref_obb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
     L.pfnav_los_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfnav_map_upload_factions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_pool_repair.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -329,6 +331,12 @@ class Nav:
 
     def blockers_incref(self, x, z, radius, faction=0, flags=FLAG_MOVABLE):
         _chk(self.L.pfnav_blockers_incref(self.h, x, z, radius, faction, flags))
+
+    def blockers_obb(self, corners_xz, incref=True, faction=0, flags=FLAG_MOVABLE):
+        """corners_xz: (4, 2) bottom-face corners obb->corners[0], [1], [5], [4]"""
+        c = np.ascontiguousarray(corners_xz, np.float32).reshape(8)
+        f = self.L.pfnav_blockers_incref_obb if incref else self.L.pfnav_blockers_decref_obb
+        _chk(f(self.h, _p(c), faction, flags))
 
     def blockers_decref(self, x, z, radius, faction=0, flags=FLAG_MOVABLE):
         _chk(self.L.pfnav_blockers_decref(self.h, x, z, radius, faction, flags))

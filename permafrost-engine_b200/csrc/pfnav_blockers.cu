@@ -106,6 +106,80 @@ static size_t tiles_under_circle(const pfnav_ctx *ctx, v2f c, float radius, td *
     return ret;
 }
 
+// M_Tile_LineSupercoverTilesSorted (tile.c:430), for a segment that STARTS inside the map (the only
+// case pfnav_blockers_*_obb accepts): Amanatides-Woo traversal in the reference's float arithmetic.
+static size_t line_supercover(const pfnav_ctx *ctx, float ax, float az, float bx, float bz, td *out, size_t maxout)
+{
+    size_t ret = 0;
+    if (maxout == 0) return 0;
+    float dx = bx - ax, dz = bz - az;
+    const float len = (float)sqrt(dx * dx + dz * dz);
+    dx = dx / len; dz = dz / len;                                  // PFM_Vec2_Normal
+    td cur;
+    if (!desc_for_point(ctx, ax, az, &cur)) return 0;
+    const int step_c = dx <= 0.0f ? 1 : -1;
+    const int step_r = dz >= 0.0f ? 1 : -1;
+    const float t_delta_x = (float)fabs(4 / dx), t_delta_z = (float)fabs(4 / dz);       // TILE_X_DIM is an int
+    const float bnx = (ctx->map_x - (float)(cur.chunk_c * 256)) - (float)(cur.tile_c * 4);
+    const float bnz = (ctx->map_z + (float)(cur.chunk_r * 256)) + (float)(cur.tile_r * 4);
+    float t_max_x = (step_c > 0) ? (float)(fabs(ax - (bnx - 4.0f)) / fabs(dx)) : (float)(fabs(ax - bnx) / fabs(dx));
+    float t_max_z = (step_r > 0) ? (float)(fabs(az - (bnz + 4.0f)) / fabs(dz)) : (float)(fabs(az - bnz) / fabs(dz));
+    td fin;
+    const bool ends_inside = desc_for_point(ctx, bx, bz, &fin);
+    do {
+        out[ret++] = cur;
+        int dc = 0, dr = 0;
+        if (t_max_x < t_max_z) { t_max_x = t_max_x + t_delta_x; dc = step_c; }
+        else                   { t_max_z = t_max_z + t_delta_z; dr = step_r; }
+        if (ends_inside && cur.chunk_r == fin.chunk_r && cur.chunk_c == fin.chunk_c && cur.tile_r == fin.tile_r && cur.tile_c == fin.tile_c)
+            break;
+        const int ar = cur.chunk_r * 64 + cur.tile_r + dr, ac = cur.chunk_c * 64 + cur.tile_c + dc;      // M_Tile_RelativeDesc
+        if (ar < 0 || ar >= ctx->chunk_h * 64 || ac < 0 || ac >= ctx->chunk_w * 64) break;
+        cur = {ar / 64, ac / 64, ar % 64, ac % 64};
+    } while (ret < maxout);
+    return ret;
+}
+
+// M_Tile_AllUnderObj (tile.c:594): supercover of the four bottom edges (duplicates at the corners included, as
+// in the reference: the refcounts see them twice) plus every tile of the bounding tile box -- upper bounds
+// EXCLUDED, tile.c:656-659 -- whose centre lies inside the rectangle (C_PointInsideRect2D, collision.c:756).
+// c[4] = bottom corners obb->corners[0], [1], [5], [4] as (x, z).
+static size_t tiles_under_obb(const pfnav_ctx *ctx, const v2f c[4], td *out, size_t maxout)
+{
+    size_t ret = 0;
+    int min_r = ctx->chunk_h * 64 - 1, max_r = 0, min_c = ctx->chunk_w * 64 - 1, max_c = 0;
+    // the reference starts its column minimum at {chunk_w-1, chunk_w-1} (tile.c:624): reproduce it
+    int min_c_init = (ctx->chunk_w - 1) * 64 + (ctx->chunk_w - 1);
+    min_c = min_c_init;
+    for (int i = 0; i < 4; i++) {
+        const v2f a = c[i], b = c[(i + 1) & 3];
+        const size_t n = line_supercover(ctx, a.x, a.z, b.x, b.z, out + ret, maxout - ret);
+        const td *d = out + ret;
+        ret += n;
+        if (ret == maxout) return ret;
+        for (size_t j = 0; j < n; j++) {
+            const int ar = d[j].chunk_r * 64 + d[j].tile_r, ac = d[j].chunk_c * 64 + d[j].tile_c;
+            min_r = std::min(min_r, ar); max_r = std::max(max_r, ar);
+            min_c = std::min(min_c, ac); max_c = std::max(max_c, ac);
+        }
+    }
+    const v2f ab = {c[1].x - c[0].x, c[1].z - c[0].z}, ad = {c[3].x - c[0].x, c[3].z - c[0].z};
+    const float abab = ab.x * ab.x + ab.z * ab.z, adad = ad.x * ad.x + ad.z * ad.z;
+    for (int r = min_r; r < max_r; r++)
+        for (int cc = min_c; cc < max_c; cc++) {
+            const float bx = (ctx->map_x - (float)((cc / 64) * 256)) - (float)((cc % 64) * 4);
+            const float bz = (ctx->map_z + (float)((r / 64) * 256)) + (float)((r % 64) * 4);
+            const v2f ctr = {bx - 4.0f / 2.0f, bz + 4.0f / 2.0f};
+            const v2f ap = {ctr.x - c[0].x, ctr.z - c[0].z};
+            const float apab = ap.x * ab.x + ap.z * ab.z, apad = ap.x * ad.x + ap.z * ad.z;
+            if ((apab >= 0.0f && apab <= abab) && (apad >= 0.0f && apad <= adad)) {
+                out[ret++] = {r / 64, cc / 64, r % 64, cc % 64};
+                if (ret == maxout) return ret;
+            }
+        }
+    return ret;
+}
+
 // M_Tile_Contour (tile.c:759)
 static size_t tiles_contour(const pfnav_ctx *ctx, size_t ntds, const td *tds, td *out, size_t maxout)
 {
@@ -198,6 +272,35 @@ static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, int fa
     return PFNAV_OK;
 }
 
+// n_update_blockers_obb_{ground,water,air} (nav.c:1135-1211)
+static int blockers_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags, int delta)
+{
+    v2f c[4];
+    for (int i = 0; i < 4; i++) {
+        c[i] = {corners_xz[2 * i], corners_xz[2 * i + 1]};
+        td t;
+        if (!desc_for_point(ctx, c[i].x, c[i].z, &t)) {
+            pfnav_set_error("pfnav_blockers_*_obb: corner %d lies outside the map (clipped boxes are not supported)", i);
+            return PFNAV_ERR_ARG;
+        }
+    }
+    td tds[1024], o3[1024], o5[1024], o7[1024];
+    const size_t n = tiles_under_obb(ctx, c, tds, 1024);
+    const size_t n3 = tiles_contour(ctx, n, tds, o3, 1024);
+    const size_t n5 = tiles_contour(ctx, n3, o3, o5, 1024);
+    const size_t n7 = tiles_contour(ctx, n5, o5, o7, 1024);
+    const int groups[2] = {(flags & PFNAV_FLAG_AIR) ? 8 : 4, (flags & PFNAV_FLAG_AIR) ? -1 : 0};
+    for (int gi = 0; gi < 2; gi++) {
+        const int g = groups[gi];
+        if (g < 0) continue;
+        apply(ctx, g + 0, faction_id, tds, n, delta);
+        apply(ctx, g + 1, faction_id, tds, n, delta); apply(ctx, g + 1, faction_id, o3, n3, delta);
+        apply(ctx, g + 2, faction_id, tds, n, delta); apply(ctx, g + 2, faction_id, o3, n3, delta); apply(ctx, g + 2, faction_id, o5, n5, delta);
+        apply(ctx, g + 3, faction_id, tds, n, delta); apply(ctx, g + 3, faction_id, o3, n3, delta); apply(ctx, g + 3, faction_id, o5, n5, delta); apply(ctx, g + 3, faction_id, o7, n7, delta);
+    }
+    return PFNAV_OK;
+}
+
 }   // namespace
 
 void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); g_fdirty.erase(ctx); }
@@ -206,6 +309,20 @@ extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float ran
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
     return blockers_circle(ctx, x, z, range, faction_id, flags, +1);
+}
+
+// N_BlockersIncrefOBB / N_BlockersDecrefOBB (nav.c:4685-4705). corners_xz: the bottom face of the box,
+// obb->corners[0], [1], [5], [4] as x,z pairs (tile.c:599).
+extern "C" int pfnav_blockers_incref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags)
+{
+    PF_ARG(ctx && ctx->d_cost && corners_xz, "map not created / null");
+    return blockers_obb(ctx, corners_xz, faction_id, flags, +1);
+}
+
+extern "C" int pfnav_blockers_decref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags)
+{
+    PF_ARG(ctx && ctx->d_cost && corners_xz, "map not created / null");
+    return blockers_obb(ctx, corners_xz, faction_id, flags, -1);
 }
 
 extern "C" int pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)

@@ -438,6 +438,37 @@ def test_blockers_commit_and_route_vs_ref(pfref, pforacle):
 
 
 # ---------------------------------------------------------------- host logic + ABI surface
+def test_blockers_obb_vs_ref(pfref):
+    """N_BlockersIncrefOBB / DecrefOBB (nav.c:4685): rotated building footprints -> M_Tile_AllUnderObj supercover +
+    interior + contour rings on the four ground layers, duplicates and all; identical refcounts"""
+    cw = ch = 2
+    p = cases.noise_map(cw, ch, 13, 0.05)
+    ref = pfref.RefMap(cw, ch, p)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 4)
+    for l in range(4):
+        nav.map_upload_layer(l, ref.cost_base(0))
+    rng = np.random.default_rng(4)
+    boxes = []
+    for _ in range(40):
+        c = np.array([-rng.uniform(60, cw * 256 - 60), rng.uniform(60, ch * 256 - 60)])
+        hw, hh, ang = rng.uniform(3, 30), rng.uniform(3, 30), rng.uniform(0, np.pi)
+        ax, ay = np.array([np.cos(ang), np.sin(ang)]), np.array([-np.sin(ang), np.cos(ang)])
+        b = np.array([c - ax * hw - ay * hh, c + ax * hw - ay * hh, c + ax * hw + ay * hh, c - ax * hw + ay * hh], np.float32)
+        boxes.append(b)
+        ref.blockers_obb(b, True, 0, 0); nav.blockers_obb(b, True, 0, 0)
+    for l in range(4):
+        assert (ref.blockers(l) == nav.blockers(l)).all(), l
+    assert ref.blockers(0).max() >= 2          # overlaps and the corner duplicates are counted
+    for b in boxes[:25]:
+        ref.blockers_obb(b, False, 0, 0); nav.blockers_obb(b, False, 0, 0)
+    for l in range(4):
+        assert (ref.blockers(l) == nav.blockers(l)).all(), l
+    with pytest.raises(capi.PfnavError):
+        nav.blockers_obb(np.array([[10.0, 5.0], [-5.0, 5.0], [-5.0, 20.0], [10.0, 20.0]], np.float32))   # corner outside
+    ref.close(); nav.close()
+
+
 def test_map_create_drops_state_of_previous_map():
     """dirty sets / routes / per-faction counts of an earlier, larger map must not leak into the next one"""
     nav = capi.Nav(hostonly=True)
