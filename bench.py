@@ -172,6 +172,8 @@ def run_ours(args):
     nav.map_build_nav(0)
     ngoals = W["g_hi"] - W["g_lo"]
     nav.pool_create(ngoals, ngoals * CHUNKS * CHUNKS)
+    if os.environ.get("PFNAV_TWO_PHASE"):              # A/B and profiling hook: 0 single pass, 2 always split
+        nav.set_two_phase(int(os.environ["PFNAV_TWO_PHASE"]))
     goals = [tuple(int(v) for v in W["agents"]["flock_target_tile"][f]) for f in range(W["g_lo"], W["g_hi"])]
 
     # pinned host copies for the e2e leg

@@ -1491,9 +1491,18 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     // Two-phase velocity update while LOS chains are still in flight on the field stream: the part of
     // ClearPath that does not depend on the preferred velocity (neighbours, velocity obstacles, admissible
     // ray intersections) runs now, next to them; only the choice waits for the fields.
+    // Policy: splitting costs ~5-30 % extra work (phase B rebuilds the obstacles), so it pays only while the LOS
+    // chains outlast a good part of phase A. Both durations are measured on the previous tick.
+    if (ctx->vel_timed && cudaEventQuery(ctx->ev_vel1) == cudaSuccess) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_vel0, ctx->ev_vel1) == cudaSuccess) ctx->last_vel_ms = ms;
+    }
+    bool worth = true;
+    if (ctx->last_los_ms > 0.0f && ctx->last_vel_ms > 0.0f) worth = ctx->last_los_ms > 0.5f * ctx->last_vel_ms;
     bool two_phase = ctx->two_phase && (ctx->two_phase_force ||
-                                        (ctx->los_inflight && cudaEventQuery(ctx->ev_los) == cudaErrorNotReady));
+                                        (worth && ctx->los_inflight && cudaEventQuery(ctx->ev_los) == cudaErrorNotReady));
     cudaGetLastError();
+    PF_CUDA(cudaEventRecord(ctx->ev_vel0, st));
     if (two_phase && ctx->cap_prep < (size_t)nwork) {
         cudaFree(ctx->d_prep); ctx->d_prep = nullptr; ctx->cap_prep = 0;
         if (cudaMalloc(&ctx->d_prep, (size_t)nwork * sizeof(pf_prep)) == cudaSuccess) ctx->cap_prep = (size_t)nwork;
@@ -1536,6 +1545,8 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
                                                                     ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, nullptr);
     ctx->launches += 3;
     PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(ctx->ev_vel1, st));
+    ctx->vel_timed = true;
     prof.~pf_prof_scope(); prof.a = nullptr;
     PF_CUDA(cudaEventRecord(ctx->tick_done, st));
     return PFNAV_OK;

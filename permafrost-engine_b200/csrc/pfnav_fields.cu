@@ -813,27 +813,27 @@ __device__ __forceinline__ bool los_is_corner(const LosSmem &s, int r, int c)
 //  is bound by the dependent chain of one thread, not by instruction count or memory.)
 __device__ __forceinline__ bool heap_lt(uint16_t a, uint16_t b) { return (((b >> 12) - (a >> 12)) & 3) == 1; }
 
-// pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200)
+// pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200). Only two adjacent priorities are ever in the heap,
+// so "a < b" is "a holds the lower one (that of the root being popped) and b does not": the sift of the
+// former last element X runs only if X is of the higher priority, and follows the children that hold the
+// lower one, left before right -- exactly what the strict comparisons of _pq_balance select.
 __device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
 {
     const uint16_t out = h[1];
-    h[1] = h[size];
+    const uint16_t x = h[size];
     size--;
-    // sift the former last element X (parked at h[size+1]) down from the root. Both children are
-    // loaded up front so that each level costs one shared-memory round trip.
-    const uint16_t x = h[size + 1];
+    const uint32_t lowp = out >> 12;                 // the root holds the minimum priority
     int root = 1;
-    while (true) {
-        const int l = root * 2, r = l + 1;
-        if (l > size) break;
-        const uint16_t hl = h[l], hr = h[min(r, size)];
-        int target = -1;
-        uint16_t tv = x;
-        if (heap_lt(hl, tv)) { target = l; tv = hl; }
-        if (r <= size && heap_lt(hr, tv)) { target = r; tv = hr; }
-        if (target < 0) break;
-        h[root] = tv;
-        root = target;
+    if ((uint32_t)(x >> 12) != lowp) {
+        while (true) {
+            const int l = root * 2, r = l + 1;
+            if (l > size) break;
+            const uint16_t hl = h[l], hr = h[min(r, size)];
+            const bool dl = (uint32_t)(hl >> 12) == lowp, dr = r <= size && (uint32_t)(hr >> 12) == lowp;
+            if (!(dl || dr)) break;
+            h[root] = dl ? hl : hr;
+            root = dl ? l : r;
+        }
     }
     h[root] = x;
     return out;
@@ -982,7 +982,6 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                 const uint64_t b_m = s.blk[rm], b_0 = s.blk[r], b_p = s.blk[rp];
                 const uint64_t o_m = s.open[rm], o_0 = s.open[r], o_p = s.open[rp];
                 const uint64_t a_m = s.assigned[rm], a_0 = s.assigned[r], a_p = s.assigned[rp];
-                const uint64_t p_mm = s.pass[rmm], p_m = s.pass[rm], p_0 = s.pass[r], p_p = s.pass[rp], p_pp = s.pass[rpp];
                 // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0). The list
                 // (incl. the wavefront_blocked filter) is collected before any neighbour is processed
                 // (field.c:2205): a line drawn for an earlier neighbour of this pop must not hide a later one.
@@ -1013,7 +1012,8 @@ k_los(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
                 size = sz;
                 if ((t0 && !o0) | (t1 && !o1) | (t2 && !o2) | (t3 && !o3)) {
                     // an impassable (or cost > 1) neighbour that is not wavefront-blocked: field_is_los_corner
-                    // (field.c:435) on the preloaded passable rows, then the blocked line
+                    // (field.c:435) on the passable rows r-2..r+2, then the blocked line
+                    const uint64_t p_mm = s.pass[rmm], p_m = s.pass[rm], p_0 = s.pass[r], p_p = s.pass[rp], p_pp = s.pass[rpp];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const bool k = e == 0 ? (t0 && !o0) : e == 1 ? (t1 && !o1) : e == 2 ? (t2 && !o2) : (t3 && !o3);
@@ -1129,8 +1129,8 @@ extern "C" int pfnav_create(int device, pfnav_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->tick_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->field_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_los, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_fork) != cudaSuccess || cudaEventCreate(&ctx->ev_los) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_vel0) != cudaSuccess || cudaEventCreate(&ctx->ev_vel1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->tick_done, cudaEventDisableTiming) != cudaSuccess) {
         pfnav_set_error("pfnav_create: stream/event creation failed");
         delete ctx;
@@ -1195,6 +1195,8 @@ extern "C" void pfnav_destroy(pfnav_ctx *ctx)
     pfnav_agents_free(ctx);
     if (ctx->tick_done) cudaEventDestroy(ctx->tick_done);
     if (ctx->tick_stream) cudaStreamDestroy(ctx->tick_stream);
+    if (ctx->ev_vel0) cudaEventDestroy(ctx->ev_vel0);
+    if (ctx->ev_vel1) cudaEventDestroy(ctx->ev_vel1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_los) cudaEventDestroy(ctx->ev_los);
     if (ctx->field_stream) cudaStreamDestroy(ctx->field_stream);

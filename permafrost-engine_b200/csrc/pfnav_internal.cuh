@@ -144,6 +144,9 @@ struct pfnav_ctx {
     // fields (all-gather, position index, cohesion) overlap the latency-bound LOS dependency chain
     cudaStream_t field_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_los = nullptr;
+    // measured durations of the previous LOS batch and the previous velocity update steer the two-phase choice
+    cudaEvent_t ev_vel0 = nullptr, ev_vel1 = nullptr;
+    bool vel_timed = false; float last_los_ms = -1.0f, last_vel_ms = -1.0f;
     bool los_inflight = false;
 
     // ---- optional per-kernel timing (pfnav_profile_enable) ----

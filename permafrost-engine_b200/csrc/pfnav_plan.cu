@@ -265,6 +265,12 @@ extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int t
 // rebuild and the cohesion pass overlap them.
 static int los_fork(pfnav_ctx *ctx, cudaStream_t st)
 {
+    // duration of the previous batch (fork -> done), if it has finished: input of the two-phase policy
+    if (ctx->los_inflight && cudaEventQuery(ctx->ev_los) == cudaSuccess) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_fork, ctx->ev_los) == cudaSuccess) ctx->last_los_ms = ms;
+    }
+    cudaGetLastError();
     PF_CUDA(cudaEventRecord(ctx->ev_fork, st));
     PF_CUDA(cudaStreamWaitEvent(ctx->field_stream, ctx->ev_fork, 0));
     return 0;
