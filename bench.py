@@ -263,6 +263,14 @@ def run_ours(args):
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
         tl = torch.tensor([float(launches)], device="cuda"); dist.all_reduce(tl); launches = int(tl.item())
+    if os.environ.get("PF_BENCH_DEBUG"):
+        # kernel-group times INSIDE overlapped steps (library events on each group's own stream)
+        nav.profile_enable(True); nav.profile_read()
+        for _ in range(3):
+            flush.zero_(); step_resident()
+        torch.cuda.synchronize()
+        pr = nav.profile_read(); nav.profile_enable(False)
+        print("debug: in-step group times over 3 steps (ms, launches): %s" % pr, file=sys.stderr)
     # ---- per-phase device times, each phase alone between synchronisations (kernel time without the
     #      host-side gaps of the full step); used for the roofline line and flow_fields_per_sec ----
     def phase_time(fn, iters=5):

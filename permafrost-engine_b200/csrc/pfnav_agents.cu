@@ -1510,7 +1510,10 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     }
     if (two_phase) {
         pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
-        k_agent_velocity<1><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+        // phase A has the whole LOS phase to hide in: a smaller persistent grid leaves the schedulers to the
+        // latency-bound LOS threads it shares the SMs with
+        const int ctas_a = ctx->phase_a_ctas_per_sm > 0 ? std::min(ctas, ctx->sm_count * ctx->phase_a_ctas_per_sm) : ctas;
+        k_agent_velocity<1><<<ctas_a, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                                     ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
                                                                     ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
                                                                     ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep);
@@ -2161,8 +2164,9 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
 // whenever LOS chains are still in flight, 2 = always split (exercises the two-phase path without fields).
 extern "C" int pfnav_set_two_phase(pfnav_ctx *ctx, int mode)
 {
-    PF_ARG(ctx && mode >= 0 && mode <= 2, "mode");
-    ctx->two_phase = mode != 0;
-    ctx->two_phase_force = mode == 2;
+    PF_ARG(ctx && mode >= 0 && (mode & 3) <= 2, "mode");
+    ctx->two_phase = (mode & 3) != 0;
+    ctx->two_phase_force = (mode & 3) == 2;
+    ctx->phase_a_ctas_per_sm = mode >> 4;          // tuning: bits 4.. = resident CTAs per SM of phase A (0 = default)
     return PFNAV_OK;
 }

@@ -1129,6 +1129,8 @@ extern "C" int pfnav_create(int device, pfnav_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->tick_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->field_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->flow_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_flow, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_fork) != cudaSuccess || cudaEventCreate(&ctx->ev_los) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_vel0) != cudaSuccess || cudaEventCreate(&ctx->ev_vel1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->tick_done, cudaEventDisableTiming) != cudaSuccess) {
@@ -1200,6 +1202,8 @@ extern "C" void pfnav_destroy(pfnav_ctx *ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_los) cudaEventDestroy(ctx->ev_los);
     if (ctx->field_stream) cudaStreamDestroy(ctx->field_stream);
+    if (ctx->ev_flow) cudaEventDestroy(ctx->ev_flow);
+    if (ctx->flow_stream) cudaStreamDestroy(ctx->flow_stream);
     delete ctx;
 }
 
@@ -1751,7 +1755,10 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
         ctx->los_trace_cap = n;
     }
     pf_prof_scope prof(ctx, st, PF_PROF_LOS);
-    const int grid = std::max(1, std::min((int)((n + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA), ctx->sm_count * 3));
+    // 2 persistent CTAs per SM (117 KB of shared memory): a flow CTA (98 KB) still fits beside them, so the flow
+    // waves of the same batch -- and with them every later launch, the block scheduler serves grids in order --
+    // are not held up until LOS CTAs retire. The makespan is one chain's latency, not a matter of warp count.
+    const int grid = std::max(1, std::min((int)((n + LOS_WARPS_PER_CTA - 1) / LOS_WARPS_PER_CTA), ctx->sm_count * 2));
     k_los<<<grid, LOS_WARPS_PER_CTA * 32, smem, st>>>(g, mi, d_reqs, (int)n, d_out_fields, d_out_slot,
                                                       (unsigned *)ctx->d_los_sched, (int *)ctx->d_los_sched + 1,
                                                       ctx->los_trace_on ? ctx->d_los_trace : nullptr);

@@ -113,6 +113,7 @@ struct pfnav_ctx {
     float2   *d_member_pos = nullptr; size_t cap_member_pos = 0;   // positions in flock-member order
     void *d_prep = nullptr; size_t cap_prep = 0;                   // phase-A results of the two-phase velocity update
     bool two_phase = true, two_phase_force = false;
+    int phase_a_ctas_per_sm = 0;
     // spatial index (bitmap_grid.h equivalent)
     int grid_w = 0, grid_h = 0; int32_t origin_x = 0, origin_y = 0;
     uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
@@ -142,8 +143,8 @@ struct pfnav_ctx {
     cudaEvent_t tick_done = nullptr;
     // LOS chains of a goal batch run on their own stream so that the parts of the tick that do not read
     // fields (all-gather, position index, cohesion) overlap the latency-bound LOS dependency chain
-    cudaStream_t field_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_los = nullptr;
+    cudaStream_t field_stream = nullptr, flow_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_los = nullptr, ev_flow = nullptr;
     // measured durations of the previous LOS batch and the previous velocity update steer the two-phase choice
     cudaEvent_t ev_vel0 = nullptr, ev_vel1 = nullptr;
     bool vel_timed = false; float last_los_ms = -1.0f, last_vel_ms = -1.0f;
@@ -166,13 +167,16 @@ static inline cudaStream_t pf_stream(pfnav_ctx *ctx, void *stream)
 static inline cudaError_t pf_fields_join(pfnav_ctx *ctx, cudaStream_t st)
 {
     if (!ctx->los_inflight) return cudaSuccess;
+    cudaError_t e = cudaStreamWaitEvent(st, ctx->ev_flow, 0);
+    if (e != cudaSuccess) return e;
     return cudaStreamWaitEvent(st, ctx->ev_los, 0);
 }
 // host-side wait for the forked LOS work (setup-time entry points that use blocking copies)
 static inline cudaError_t pf_fields_sync(pfnav_ctx *ctx)
 {
     if (!ctx->los_inflight) return cudaSuccess;
-    cudaError_t e = cudaEventSynchronize(ctx->ev_los);
+    cudaError_t e = cudaEventSynchronize(ctx->ev_flow);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_los);
     if (e == cudaSuccess) ctx->los_inflight = false;
     return e;
 }

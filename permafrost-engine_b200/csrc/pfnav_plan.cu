@@ -258,6 +258,9 @@ extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int t
     return PFNAV_OK;
 }
 
+// The flow waves and the LOS dependency chains of a goal batch each get a context-owned stream (the flow kernels
+// need ~100 KB of shared memory per CTA and would otherwise queue the caller's stream behind the persistent LOS
+// CTAs that hold most of it).
 // The LOS dependency chains of a goal batch are latency-bound (one thread per field replays the
 // reference's heap) and read nothing the flow kernels write: they run on ctx->field_stream, forked
 // after everything already queued on the caller's stream and joined (pf_fields_join) by whichever
@@ -273,10 +276,12 @@ static int los_fork(pfnav_ctx *ctx, cudaStream_t st)
     cudaGetLastError();
     PF_CUDA(cudaEventRecord(ctx->ev_fork, st));
     PF_CUDA(cudaStreamWaitEvent(ctx->field_stream, ctx->ev_fork, 0));
+    PF_CUDA(cudaStreamWaitEvent(ctx->flow_stream, ctx->ev_fork, 0));
     return 0;
 }
 static int los_forked(pfnav_ctx *ctx)
 {
+    PF_CUDA(cudaEventRecord(ctx->ev_flow, ctx->flow_stream));
     PF_CUDA(cudaEventRecord(ctx->ev_los, ctx->field_stream));
     ctx->los_inflight = true;
     return 0;
@@ -303,17 +308,16 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
             PF_CUDA(cudaSetDevice(ctx->device));
             cudaStream_t st = pf_stream(ctx, stream);
             const uint8_t *dev = (const uint8_t *)ctx->d_plan_buf;
-            int rc = 0;
+            int rc = los_fork(ctx, st);          // the LOS chains do not read flow fields: fork before the flow waves
+            if (rc) return rc;
             for (size_t w = 0; w + 1 < gb.fwave_off.size(); w++) {
                 const int first = gb.fwave_off[w], cnt = gb.fwave_off[w + 1] - first;
                 if (cnt <= 0) continue;
                 rc = pfnav_flow_launch(ctx, (const pfnav_field_req *)dev + first, cnt, ctx->d_pool_flow,
-                                       (const int32_t *)(dev + gb.b_fr) + first, st);
+                                       (const int32_t *)(dev + gb.b_fr) + first, ctx->flow_stream);
                 if (rc) return rc;
             }
             const int32_t one_wave[2] = {0, gb.nl};
-            rc = los_fork(ctx, st);
-            if (rc) return rc;
             rc = pfnav_los_launch(ctx, (const pfnav_los_req *)(dev + gb.b_fr + gb.b_fs), gb.nl, ctx->d_pool_los,
                                   (const int32_t *)(dev + gb.b_fr + gb.b_fs + gb.b_lr), 1, one_wave, ctx->field_stream);
             if (rc) return rc;
@@ -413,15 +417,14 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     const int32_t *dfs = (const int32_t *)(dev + b_fr);
     const pfnav_los_req *dlr = (const pfnav_los_req *)(dev + b_fr + b_fs);
     const int32_t *dls = (const int32_t *)(dev + b_fr + b_fs + b_lr);
-    int rc = 0;
+    int rc = los_fork(ctx, st);
+    if (rc) return rc;
     for (int w = 0; w <= maxw; w++) {
         const int first = fwave_off[w], cnt = fwave_off[w + 1] - first;
         if (cnt <= 0) continue;
-        rc = pfnav_flow_launch(ctx, dfr + first, cnt, ctx->d_pool_flow, dfs + first, st);
+        rc = pfnav_flow_launch(ctx, dfr + first, cnt, ctx->d_pool_flow, dfs + first, ctx->flow_stream);
         if (rc) return rc;
     }
-    rc = los_fork(ctx, st);
-    if (rc) return rc;
     rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), ctx->field_stream);
     if (rc) return rc;
     rc = los_forked(ctx);
