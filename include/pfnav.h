@@ -292,6 +292,8 @@ int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, 
  * does not read fields (position index, cohesion) overlaps them; pfnav_agents_tick and the pool entry
  * points order themselves after it. A caller that reads pool LOS fields through raw device pointers
  * on its own stream calls this first. */
+/* Test / tuning hook: LOS kernel variant, 0 = bit rows, 1 (default) = one state byte per tile. Same results. */
+int  pfnav_set_los_variant(pfnav_ctx *ctx, int variant);
 /* Profiling aid: per-field trace of the LOS launches. enable != 0 arms it for the following launches; with
  * out != NULL the trace of the last traced launch is returned first: out[4i..4i+3] = {taken, dependency
  * satisfied, finished} in %globaltimer nanoseconds and 1 + heap pops (0 = zero-filled early out). */

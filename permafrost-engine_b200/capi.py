@@ -65,7 +65,7 @@ SYMBOLS = [
     "pfnav_agents_upload", "pfnav_agents_set_work", "pfnav_agents_tick",
     "pfnav_agents_read_velocities", "pfnav_agents_read_debug", "pfnav_ents_in_circle",
     "pfnav_agents_device_ptrs", "pfnav_agents_rebuild_index", "pfnav_launch_count", "pfnav_profile_enable",
-    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase", "pfnav_los_trace", "pfnav_blockers_incref_obb", "pfnav_blockers_decref_obb",
+    "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase", "pfnav_los_trace", "pfnav_set_los_variant", "pfnav_blockers_incref_obb", "pfnav_blockers_decref_obb",
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
 ]
@@ -99,6 +99,7 @@ def load():
     L.pfnav_set_enemy_factions.argtypes = [C.c_void_p, C.c_int, C.c_uint16]
     L.pfnav_request_faction.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_set_two_phase.argtypes = [C.c_void_p, C.c_int]
+    L.pfnav_set_los_variant.argtypes = [C.c_void_p, C.c_int]
     L.pfnav_blockers_incref_obb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
     L.pfnav_blockers_decref_obb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
     L.pfnav_los_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -283,6 +284,9 @@ class Nav:
         n = C.c_size_t(0)
         _chk(self.L.pfnav_los_trace(self.h, int(enable), _p(out) if read_cap else None, read_cap, C.byref(n)))
         return out[:n.value]
+
+    def set_los_variant(self, variant):
+        _chk(self.L.pfnav_set_los_variant(self.h, variant))
 
     def set_two_phase(self, mode):
         _chk(self.L.pfnav_set_two_phase(self.h, mode))

@@ -49,7 +49,16 @@ def test_flow_portal_and_merge_golden(nav, tma):
     nav.set_tma(1)
 
 
-def test_los_golden(nav):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_los_golden(nav, variant):
+    nav.set_los_variant(variant)
+    try:
+        _los_golden(nav)
+    finally:
+        nav.set_los_variant(1)
+
+
+def _los_golden(nav):
     g = gold("portal_los")
     _upload(nav, 3, 3, g["cost"])
     assert (nav.los_fields_create(g["los_reqs"].view(capi.LOS_REQ)) == g["los_exp"]).all()
