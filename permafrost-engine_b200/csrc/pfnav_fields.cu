@@ -810,7 +810,9 @@ __device__ __forceinline__ bool los_is_corner(const LosSmem &s, int r, int c)
 //  the same with the pop loop in lockstep on 32 lanes and the neighbours on 4 lanes: 3.2 ms; one state
 //  byte per tile in a padded array + bit-derived sift path: 2.45 ms; that plus a resumable lane-0 loop
 //  handing every wavefront-blocked line to the whole warp (closed-form line positions): 5.4 ms. The loop
-//  is bound by the dependent chain of one thread, not by instruction count or memory.)
+//  is bound by the dependent chain of one thread, not by memory. What did pay, later in the round,
+//  was cutting the instruction count of a pop: the byte-state kernel k_los_b below, 9.9 -> 6.2 ms for the C2 batch;
+//  a per-slot priority-bit sift on top of it bought nothing, 6.16 vs 6.23 ms.)
 __device__ __forceinline__ bool heap_lt(uint16_t a, uint16_t b) { return (((b >> 12) - (a >> 12)) & 3) == 1; }
 
 // pq_coord_pop + _pq_balance (pqueue.h:109-130, 190-200). Only two adjacent priorities are ever in the heap,
