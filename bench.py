@@ -356,7 +356,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(n_total * capi.AGENT.itemsize + len(W["flocks"]) * capi.FLOCK.itemsize + nwork * 4),
                 "d2h_bytes_per_step": int(nwork * 8)},
         "roofline": {"bound": "hbm", "kernel": {"velocity": "k_agent_velocity", "cohesion": "k_cohesion", "flow": "k_flow_unit",
-                                                  "los": "k_los", "index": "k_cell_*", "vdes": "k_desired_velocity"}[dom],
+                                                  "los": "k_los_b", "index": "k_cell_*", "vdes": "k_desired_velocity"}[dom],
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": per_launch[dom], "ms_per_launch": dom_ms,
