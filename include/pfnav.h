@@ -189,15 +189,19 @@ int  pfnav_flow_fields_update_dev(pfnav_ctx *ctx, const pfnav_field_req *d_reqs,
                                   uint8_t *d_inout_fields, void *stream);
 
 /* One N_LOSFieldCreate call (field.c:2085). 48 bytes. */
+#define PFNAV_LOS_PREV_INPLACE (-3)
 typedef struct pfnav_los_req {
     int32_t  chunk_r, chunk_c;          /* chunk the field is for */
     int32_t  layer;
     int32_t  faction_id;
     int32_t  tgt_chunk_r, tgt_chunk_c;  /* struct tile_desc target */
     int32_t  tgt_tile_r, tgt_tile_c;
-    int32_t  prev_index;                /* -1: destination chunk (prev_los == NULL); else index,
+    int32_t  prev_index;                /* -1: destination chunk (prev_los == NULL); >= 0: index,
                                          * within the same batch, of the request whose output is
-                                         * prev_los. Must be < this request's own index.        */
+                                         * prev_los (must be < this request's own index);
+                                         * PFNAV_LOS_PREV_INPLACE (host API): prev_los is a field the
+                                         * caller holds -- its 4096 bytes are passed in out_fields[i]
+                                         * and replaced by the result (N_LOSFieldCreate's `prev`).  */
     int32_t  prev_chunk_r, prev_chunk_c;/* prev_los->chunk */
     int32_t  _pad;
 } pfnav_los_req;

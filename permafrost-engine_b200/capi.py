@@ -50,6 +50,7 @@ PATCH = np.dtype([
     ("next_prot", "<f4", 4), ("_padf", "<f4", 3)])
 assert PATCH.itemsize == 128
 
+LOS_PREV_INPLACE = -3
 TICK_VDES_FROM_POOL = 1
 FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 1 << 14, 1 << 15, 1 << 18, 1 << 21
 
@@ -396,10 +397,13 @@ class Nav:
         f = self.L.pfnav_flow_fields_update_general_dev if general else self.L.pfnav_flow_fields_update_dev
         _chk(f(self.h, C.c_void_p(d_reqs_ptr), n, C.c_void_p(d_fields_ptr), C.c_void_p(stream)))
 
-    def los_fields_create(self, reqs):
+    def los_fields_create(self, reqs, prev_fields=None):
+        """prev_fields: {request index: 64x64 previous LOS field} for requests with prev_index = LOS_PREV_INPLACE"""
         reqs = np.ascontiguousarray(reqs, LOS_REQ)
         n = len(reqs)
         out = np.zeros((n, 64, 64), np.uint8)
+        for i, f in (prev_fields or {}).items():
+            out[i] = f
         _chk(self.L.pfnav_los_fields_create(self.h, _p(reqs), n, _p(out)))
         return out
 

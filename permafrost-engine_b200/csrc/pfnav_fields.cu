@@ -2056,6 +2056,7 @@ extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs
     PF_ARG(reqs && out_fields, "null buffer");
     // dependency depth = wave; requests are re-ordered wave-major on the device side
     std::vector<int> depth(n, 0), order(n), newidx(n);
+    std::vector<size_t> inplace;
     int maxd = 0;
     for (size_t i = 0; i < n; i++) {
         const pfnav_los_req &q = reqs[i];
@@ -2067,7 +2068,11 @@ extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs
                "los req: faction_id (attacking requests need pfnav_set_enemy_factions first)");
         const bool dest = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
         if (dest) { PF_ARG(q.prev_index < 0, "los req: destination chunk must not name a prev field"); }
-        else {
+        else if (q.prev_index == PFNAV_LOS_PREV_INPLACE) {
+            // N_LOSFieldCreate(..., prev) with a caller-held previous field: its bytes arrive in out_fields[i]
+            PF_ARG(abs(q.prev_chunk_r - q.chunk_r) + abs(q.prev_chunk_c - q.chunk_c) == 1, "los req: prev chunk must be adjacent");
+            inplace.push_back(i);
+        } else {
             PF_ARG(q.prev_index >= 0 && (size_t)q.prev_index < i, "los req: prev_index must name an earlier request");
             PF_ARG(abs(q.prev_chunk_r - q.chunk_r) + abs(q.prev_chunk_c - q.chunk_c) == 1, "los req: prev chunk must be adjacent");
             depth[i] = depth[q.prev_index] + 1;
@@ -2084,14 +2089,22 @@ extern "C" int pfnav_los_fields_create(pfnav_ctx *ctx, const pfnav_los_req *reqs
         sorted[k] = reqs[order[k]];
         if (sorted[k].prev_index >= 0) sorted[k].prev_index = newidx[sorted[k].prev_index];
     }
+    // caller-held previous fields ride in extra slots behind the n outputs and are named like pool slots (-2)
+    for (size_t j = 0; j < inplace.size(); j++) {
+        pfnav_los_req &q = sorted[newidx[inplace[j]]];
+        q.prev_index = -2;
+        q._pad = (int32_t)(n + j);
+    }
     PF_CUDA(cudaSetDevice(ctx->device));
     pfnav_los_req *d_reqs = nullptr;
     uint8_t *d_fields = nullptr;
     PF_CUDA(cudaMalloc(&d_reqs, n * sizeof(pfnav_los_req)));
-    if (cudaMalloc(&d_fields, n * 4096) != cudaSuccess) { cudaFree(d_reqs); pfnav_set_error("cudaMalloc fields"); return PFNAV_ERR_NOMEM; }
+    if (cudaMalloc(&d_fields, (n + inplace.size()) * 4096) != cudaSuccess) { cudaFree(d_reqs); pfnav_set_error("cudaMalloc fields"); return PFNAV_ERR_NOMEM; }
     cudaStream_t st = ctx->tick_stream;
     std::vector<uint8_t> tmp(n * 4096);
     cudaError_t e = cudaMemcpyAsync(d_reqs, sorted.data(), n * sizeof(pfnav_los_req), cudaMemcpyHostToDevice, st);
+    for (size_t j = 0; j < inplace.size() && e == cudaSuccess; j++)
+        e = cudaMemcpyAsync(d_fields + (n + j) * 4096, out_fields + inplace[j] * 4096, 4096, cudaMemcpyHostToDevice, st);
     int rc = 0;
     if (e == cudaSuccess) {
         rc = pfnav_los_fields_create_dev(ctx, d_reqs, n, d_fields, maxd + 1, wave_off.data(), st);

@@ -630,3 +630,24 @@ def test_two_phase_velocity_update_is_bit_identical(nav, name, cw):
         nav.set_two_phase(1)
     assert (out[0][0] == out[2][0]).all() and (out[0][1] == out[2][1]).all()
     assert (cases.relerr(out[2][0], g["vel"]) <= VEL_RTOL).mean() >= 0.995
+
+
+def test_los_with_caller_held_prev_field(nav):
+    """N_LOSFieldCreate(..., prev) one field at a time, the previous chunk's field held by the caller
+    (PFNAV_LOS_PREV_INPLACE), equals the chained batch -- and the golden fields"""
+    g = gold("portal_los")
+    _upload(nav, 3, 3, g["cost"])
+    reqs = g["los_reqs"].view(capi.LOS_REQ)
+    exp = g["los_exp"]
+    done = 0
+    for i in range(len(reqs)):
+        q = reqs[i:i + 1].copy()
+        if q["prev_index"][0] < 0:
+            got = nav.los_fields_create(q)[0]
+        else:
+            p = int(q["prev_index"][0])
+            q["prev_index"] = capi.LOS_PREV_INPLACE
+            got = nav.los_fields_create(q, prev_fields={0: exp[p]})[0]
+            done += 1
+        assert (got == exp[i]).all(), i
+    assert done > 0
