@@ -827,14 +827,15 @@ __device__ __forceinline__ uint16_t heap_pop(uint16_t *h, int &size)
     const uint32_t lowp = out >> 12;                 // the root holds the minimum priority
     int root = 1;
     if ((uint32_t)(x >> 12) != lowp) {
+        const uint32_t *h2 = reinterpret_cast<const uint32_t *>(h);      // children 2k, 2k+1 share one aligned word
         while (true) {
-            const int l = root * 2, r = l + 1;
+            const int l = root * 2;
             if (l > size) break;
-            const uint16_t hl = h[l], hr = h[min(r, size)];
-            const bool dl = (uint32_t)(hl >> 12) == lowp, dr = r <= size && (uint32_t)(hr >> 12) == lowp;
+            const uint32_t two = h2[root];
+            const bool dl = ((two >> 12) & 0xFu) == lowp, dr = l < size && (two >> 28) == lowp;
             if (!(dl || dr)) break;
-            h[root] = dl ? hl : hr;
-            root = dl ? l : r;
+            h[root] = (uint16_t)(dl ? two : two >> 16);
+            root = dl ? l : l + 1;
         }
     }
     h[root] = x;
