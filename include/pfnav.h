@@ -139,6 +139,8 @@ int  pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int fa
 int  pfnav_blockers_incref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
 int  pfnav_blockers_decref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
 int  pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out);
+/* nav_chunk::factions of one layer: out = u8 [chunks][15][64][64] */
+int  pfnav_blockers_get_factions(pfnav_ctx *ctx, int layer, uint8_t *out);
 /* N_Update + N_ApplyDeferredInvalidations (nav.c:2119-2223): for every chunk whose occupancy
  * changed, recompute the local islands, refresh the portal edge states, push the chunk's blockers +
  * islands to the device, and invalidate the pool: entries AT the chunk, and -- when an edge state
@@ -310,6 +312,46 @@ int  pfnav_fields_join(pfnav_ctx *ctx, void *stream);
  * FD_NONE (2) repairs the field in place: N_FlowFieldUpdateToNearestPathable when the tile is non-passable,
  * N_FlowFieldUpdateIslandToNearest otherwise. Blocking; needs pfnav_route_build. The caller re-runs the tick. */
 int  pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nrepairs);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Region fields: the dim x dim "cell arrival" fields a formation builds for every cell and
+ * every arriving group (formation.c:3152-3176 builds CELL_ARRIVAL_FIELD_RES = 96 squares per cell). The region
+ * is centred on `center`, may straddle chunks and hang over the map edge, and its directions are packed two
+ * per byte (set_flow_cell, field.c:790: even column -> high nibble); a field is dim * dim / 2 bytes, row-major.
+ * All tile coordinates are ABSOLUTE nav tiles (chunk * 64 + tile) as (r, c) int32 pairs.
+ *   PFNAV_REGION_CREATE  N_CellArrivalFieldCreate (field.c:2445) / N_GroupArrivalFieldCreate (field.c:2525):
+ *                        zero the field, seed seeds[seed_off .. seed_off + seed_n) (those inside the region) at
+ *                        cost 0, Dijkstra over passable tiles (enemy-mask rule when enemies != 0; overlay tiles
+ *                        are never entered), derive directions.
+ *   PFNAV_REGION_CELL    with CREATE: one seed (the cell's tile); the region base shifts when the tile lies one
+ *                        past the far edge (field.c:2477-2482). seed_n must be 1.
+ *   PFNAV_REGION_FIXUP   N_CellArrivalFieldUpdateToNearestPathable (field.c:2603), after CREATE when both are
+ *                        set (cell_field_fixup_task, formation.c:3171): directions off the blocked island that
+ *                        holds (start_r, start_c), a NON-passable tile inside the map-clamped region.
+ * Without PFNAV_REGION_CREATE the field is updated in place (the caller supplies it). */
+enum { PFNAV_REGION_CREATE = 1, PFNAV_REGION_FIXUP = 2, PFNAV_REGION_CELL = 4 };
+#define PFNAV_REGION_DIM_MAX 128
+typedef struct pfnav_region_req {      /* 40 bytes */
+    int32_t  layer;
+    int32_t  center_r, center_c;
+    int32_t  start_r, start_c;         /* PFNAV_REGION_FIXUP only */
+    int32_t  seed_off, seed_n;         /* pairs, into seeds_rc */
+    int32_t  overlay_off, overlay_n;   /* pairs, into overlay_rc (struct nav_cell_overlay, nav.h:695) */
+    uint16_t enemies;                  /* enemy faction bit mask, 0 = plain passability */
+    uint16_t flags;
+} pfnav_region_req;
+/* HOST buffers; synchronous. inout_fields: n * dim * dim / 2 bytes. dim even, <= PFNAV_REGION_DIM_MAX. */
+int  pfnav_region_fields(pfnav_ctx *ctx, int dim, const pfnav_region_req *reqs, size_t n, const int32_t *seeds_rc,
+                         size_t nseeds, const int32_t *overlay_rc, size_t noverlay, uint8_t *inout_fields);
+/* DEVICE buffers (requests already validated by the caller), asynchronous on `stream`. */
+int  pfnav_region_fields_dev(pfnav_ctx *ctx, int dim, const pfnav_region_req *d_reqs, size_t n,
+                             const int32_t *d_seeds_rc, const int32_t *d_overlay_rc, uint8_t *d_inout_fields,
+                             void *stream);
+/* N_GroupArrivalFieldCreate (field.c:2525) with its world-space arguments: targets_xz[ntargets][2], center_xz[2].
+ * A centre outside the map yields the zero field, targets outside the map or the region are skipped. */
+int  pfnav_group_arrival_field(pfnav_ctx *ctx, int layer, int dim, uint16_t enemies, const float *targets_xz,
+                               size_t ntargets, const float *center_xz, const int32_t *overlay_rc, size_t noverlay,
+                               uint8_t *out_field);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls

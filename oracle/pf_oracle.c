@@ -1065,3 +1065,215 @@ void pfo_flow_update_island_to_nearest(const pfo_map *m, const uint16_t *gisl, c
             if(intf[r][c] == 0.0f) inout[r * RES + c] = d;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Region ("cell arrival" / "group arrival") fields: dim x dim tiles that may straddle chunks and
+ * the map edge; the output packs two directions per byte (set_flow_cell, field.c:790: even column
+ * -> high nibble). All tile coordinates are absolute: chunk * 64 + tile.
+ * ---------------------------------------------------------------------------------------- */
+static bool abs_exists(const pfo_map *m, int ar, int ac)     /* M_Tile_RelativeDesc's bounds (tile.c:391) */
+{ return ar >= 0 && ar < m->chunk_h * RES && ac >= 0 && ac < m->chunk_w * RES; }
+static bool abs_passable(const pfo_map *m, int ar, int ac)   /* field_tile_passable (field.c:117) */
+{ return tile_passable(m, ar / RES, ac / RES, ar % RES, ac % RES); }
+static uint8_t abs_cost(const pfo_map *m, int ar, int ac)
+{ return chunk_cost(m, ar / RES, ac / RES)[(ar % RES) * RES + (ac % RES)]; }
+/* field_tile_passable_no_enemies (field.c:179) with an explicit enemy mask */
+static bool abs_passable_mask(const pfo_map *m, int ar, int ac, uint16_t enemies)
+{
+    if(enemies == 0 || !m->factions) return abs_passable(m, ar, ac);
+    const int cr = ar / RES, cc = ac / RES, r = ar % RES, c = ac % RES;
+    if(chunk_cost(m, cr, cc)[r * RES + c] == COST_IMPASSABLE) return false;
+    const uint8_t *fac = m->factions + ((size_t)cr * m->chunk_w + cc) * 15 * 4096;
+    for(int i = 0; i < 15; i++)
+        if(fac[(size_t)i * 4096 + r * RES + c] && !(enemies & (1u << i)))
+            return chunk_blk(m, cr, cc, r, c) == 0;
+    return true;
+}
+
+/* field_flow_dir (field.c:355) for a dim x dim integration field (row stride = rdim = dim) */
+static int flow_dir_n(const float *f, int n, int r, int c)
+{
+    float mc = INFINITY;
+#define F(rr, cc) f[(rr) * n + (cc)]
+    if(r > 0) mc = MINF(mc, F(r-1, c));
+    if(r < n-1) mc = MINF(mc, F(r+1, c));
+    if(c > 0) mc = MINF(mc, F(r, c-1));
+    if(c < n-1) mc = MINF(mc, F(r, c+1));
+    if(r > 0 && c > 0 && F(r-1, c) < INFINITY && F(r, c-1) < INFINITY) mc = MINF(mc, F(r-1, c-1));
+    if(r > 0 && c < n-1 && F(r-1, c) < INFINITY && F(r, c+1) < INFINITY) mc = MINF(mc, F(r-1, c+1));
+    if(r < n-1 && c > 0 && F(r+1, c) < INFINITY && F(r, c-1) < INFINITY) mc = MINF(mc, F(r+1, c-1));
+    if(r < n-1 && c < n-1 && F(r+1, c) < INFINITY && F(r, c+1) < INFINITY) mc = MINF(mc, F(r+1, c+1));
+    if(r > 0 && F(r-1, c) == mc) return FD_N;
+    else if(r < n-1 && F(r+1, c) == mc) return FD_S;
+    else if(c < n-1 && F(r, c+1) == mc) return FD_E;
+    else if(c > 0 && F(r, c-1) == mc) return FD_W;
+    else if(r > 0 && c > 0 && F(r-1, c-1) == mc) return FD_NW;
+    else if(r > 0 && c < n-1 && F(r-1, c+1) == mc) return FD_NE;
+    else if(r < n-1 && c > 0 && F(r+1, c-1) == mc) return FD_SW;
+    else if(r < n-1 && c < n-1 && F(r+1, c+1) == mc) return FD_SE;
+#undef F
+    return 0;
+}
+
+static void set_cell(int v, int r, int c, int n, uint8_t *buf)   /* set_flow_cell (field.c:790) */
+{
+    const size_t b = (size_t)r * (n / 2) + c / 2;
+    if(c % 2 == 1) buf[b] = (uint8_t)((buf[b] & 0xf0) | v);
+    else           buf[b] = (uint8_t)((buf[b] & 0x0f) | (v << 4));
+}
+
+static void overlay_mask(const int32_t *ov, int nov, int base_r, int base_c, int n, bool *mask)   /* build_overlay_mask (field.c:571) */
+{
+    memset(mask, 0, (size_t)n * n);
+    for(int i = 0; i < nov; i++) {
+        int dr = ov[2*i] - base_r, dc = ov[2*i+1] - base_c;
+        if(dr >= 0 && dr < n && dc >= 0 && dc < n) mask[dr * n + dc] = true;
+    }
+}
+
+/* N_CellArrivalFieldCreate (field.c:2445; cell_mode = 1: one target, the base is shifted when the target
+ * falls one past the far edge, :2477-2482) and the tile-space part of N_GroupArrivalFieldCreate
+ * (field.c:2525; cell_mode = 0: every seed inside the region is a zero-cost source). Dijkstra over passable
+ * tiles (field_build_integration_region, field.c:587; field_neighbours_grid_global, :253: 4-neighbourhood,
+ * edge weight = cost_base of the tile entered, overlay-blocked tiles are never entered). */
+void pfo_region_field_create(const pfo_map *m, int dim, uint16_t enemies, int cell_mode, const int32_t *seeds, int nseeds,
+                             int center_r, int center_c, const int32_t *overlay, int noverlay, uint8_t *out)
+{
+    memset(out, 0, (size_t)dim * dim / 2);
+    int base_r = center_r - dim / 2, base_c = center_c - dim / 2;
+    if(cell_mode) {
+        if(seeds[0] - base_r >= dim) base_r = seeds[0] - (dim - 1);
+        if(seeds[1] - base_c >= dim) base_c = seeds[1] - (dim - 1);
+    }
+    float *intf = malloc(sizeof(float) * dim * dim);
+    bool *mask = malloc((size_t)dim * dim);
+    for(int i = 0; i < dim * dim; i++) intf[i] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    for(int i = 0; i < (cell_mode ? 1 : nseeds); i++) {
+        int dr = seeds[2*i] - base_r, dc = seeds[2*i+1] - base_c;
+        if(dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;     /* tile_outside_region (field.c:126) */
+        pq_push(&frontier, 0.0f, seeds[2*i], seeds[2*i+1]);
+        intf[dr * dim + dc] = 0.0f;
+    }
+    const bool have_ov = overlay && noverlay > 0;
+    if(have_ov) overlay_mask(overlay, noverlay, base_r, base_c, dim, mask);
+    while(frontier.size > 0) {
+        int ar, ac; pq_pop(&frontier, &ar, &ac);
+        const int dr = ar - base_r, dc = ac - base_c;
+        for(int e = 0; e < 4; e++) {
+            static const int er[4] = {-1, 0, 0, 1}, ec[4] = {0, -1, 1, 0};
+            const int nr = ar + er[e], nc = ac + ec[e];
+            if(!abs_exists(m, nr, nc)) continue;
+            if(!abs_passable_mask(m, nr, nc, enemies)) continue;
+            const int ndr = nr - base_r, ndc = nc - base_c;
+            if(ndr < 0 || ndr >= dim || ndc < 0 || ndc >= dim) continue;
+            if(have_ov && mask[ndr * dim + ndc]) continue;
+            float total = intf[dr * dim + dc] + abs_cost(m, nr, nc);
+            if(total < intf[ndr * dim + ndc]) { intf[ndr * dim + ndc] = total; pq_push(&frontier, total, nr, nc); }
+        }
+    }
+    pq_free(&frontier);
+    for(int r = 0; r < dim; r++) for(int c = 0; c < dim; c++) {      /* field_build_flow_unaligned (field.c:804) */
+        if(intf[r * dim + c] == INFINITY) continue;
+        if(intf[r * dim + c] == 0.0f) { set_cell(FD_NONE, r, c, dim, out); continue; }
+        set_cell(flow_dir_n(intf, dim, r, c), r, c, dim, out);
+    }
+    free(intf); free(mask);
+}
+
+/* N_GroupArrivalFieldCreate (field.c:2525): world-space targets and centre */
+void pfo_group_arrival_field(const pfo_map *m, int dim, uint16_t enemies, const float *targets_xz, int ntargets,
+                             const float *center_xz, const int32_t *overlay, int noverlay, uint8_t *out)
+{
+    memset(out, 0, (size_t)dim * dim / 2);
+    tdesc ct;
+    if(!desc_for_point(m, center_xz[0], center_xz[1], &ct)) return;
+    int32_t *seeds = malloc(sizeof(int32_t) * 2 * (ntargets ? ntargets : 1));
+    int ns = 0;
+    for(int i = 0; i < ntargets; i++) {
+        tdesc t;
+        if(!desc_for_point(m, targets_xz[2*i], targets_xz[2*i+1], &t)) continue;
+        seeds[2*ns] = t.chunk_r * RES + t.tile_r; seeds[2*ns+1] = t.chunk_c * RES + t.tile_c; ns++;
+    }
+    pfo_region_field_create(m, dim, enemies, 0, seeds, ns, ct.chunk_r * RES + ct.tile_r, ct.chunk_c * RES + ct.tile_c,
+                            overlay, noverlay, out);
+    free(seeds);
+}
+
+/* N_CellArrivalFieldUpdateToNearestPathable (field.c:2603). The flood that finds the passable rim of the
+ * blocked island around `start` (field_passable_frontier, field.c:1441) runs inside the map-clamped region
+ * (clamped_region, field.c:1892: its extents are end - base, so the last row / column of a clamped edge is
+ * left out) and indexes its visited array with stride region.r (visited_idx, field.c:1431) -- when the
+ * clamped region has fewer rows than columns distinct tiles alias, so the flood order is kept literally.
+ * Then Dijkstra over non-passable or overlay-blocked tiles (field_build_integration_nonpass_region,
+ * field.c:678) from that rim; only 0 < cost < INF cells are rewritten. The unclamped base here is
+ * center - dim/2: the target shift of the create call is NOT repeated. */
+void pfo_region_field_update_to_nearest_pathable(const pfo_map *m, int dim, int start_r, int start_c, int center_r, int center_c,
+                                                 const int32_t *overlay, int noverlay, uint8_t *inout)
+{
+    const int max_r = m->chunk_h * RES, max_c = m->chunk_w * RES;
+    const int cb_r = (center_r - dim / 2 >= 0) ? center_r - dim / 2 : 0;
+    const int cb_c = (center_c - dim / 2 >= 0) ? center_c - dim / 2 : 0;
+    const int ce_r = (center_r + dim / 2 < max_r) ? center_r + dim / 2 : max_r - 1;
+    const int ce_c = (center_c + dim / 2 < max_c) ? center_c + dim / 2 : max_c - 1;
+    const int reg_r = ce_r - cb_r, reg_c = ce_c - cb_c;
+    const int nelems = (reg_r > reg_c ? reg_r : reg_c) * (reg_r > reg_c ? reg_r : reg_c);
+    const int base_r = center_r - dim / 2, base_c = center_c - dim / 2;
+
+    float *intf = malloc(sizeof(float) * dim * dim);
+    for(int i = 0; i < dim * dim; i++) intf[i] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    {
+        static const int er[4] = {0, 0, -1, 1}, ec[4] = {-1, 1, 0, 0};
+        bool *visited = calloc(nelems ? nelems : 1, 1);
+        int (*q)[2] = malloc(sizeof(int[2]) * (nelems ? nelems : 1));
+        int head = 0, tail = 0;
+        q[tail][0] = start_r; q[tail][1] = start_c; tail++;
+        visited[(start_r - cb_r) * reg_r + (start_c - cb_c)] = true;
+        while(head < tail) {
+            int r = q[head][0], c = q[head][1]; head++;
+            if(abs_passable(m, r, c)) {
+                int dr = r - base_r, dc = c - base_c;
+                if(dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+                pq_push(&frontier, 0.0f, r, c);
+                intf[dr * dim + dc] = 0.0f;
+                continue;
+            }
+            for(int e = 0; e < 4; e++) {
+                int nr = r + er[e], nc = c + ec[e];
+                if(!abs_exists(m, nr, nc)) continue;
+                int dr = nr - cb_r, dc = nc - cb_c;
+                if(dr < 0 || dr >= reg_r || dc < 0 || dc >= reg_c) continue;
+                if(visited[dr * reg_r + dc]) continue;
+                visited[dr * reg_r + dc] = true;
+                q[tail][0] = nr; q[tail][1] = nc; tail++;
+            }
+        }
+        free(visited); free(q);
+    }
+    bool *mask = malloc((size_t)dim * dim);
+    const bool have_ov = overlay && noverlay > 0;
+    if(have_ov) overlay_mask(overlay, noverlay, base_r, base_c, dim, mask);
+    while(frontier.size > 0) {
+        int ar, ac; pq_pop(&frontier, &ar, &ac);
+        const int dr = ar - base_r, dc = ac - base_c;
+        for(int e = 0; e < 4; e++) {
+            static const int er[4] = {-1, 0, 0, 1}, ec[4] = {0, -1, 1, 0};
+            const int nr = ar + er[e], nc = ac + ec[e];
+            if(!abs_exists(m, nr, nc)) continue;
+            const int ndr = nr - base_r, ndc = nc - base_c;
+            if(ndr < 0 || ndr >= dim || ndc < 0 || ndc >= dim) continue;
+            const bool ovb = have_ov && mask[ndr * dim + ndc];
+            if(abs_passable(m, nr, nc) && !ovb) continue;
+            float total = intf[dr * dim + dc] + abs_cost(m, nr, nc);
+            if(total < intf[ndr * dim + ndc]) { intf[ndr * dim + ndc] = total; pq_push(&frontier, total, nr, nc); }
+        }
+    }
+    pq_free(&frontier);
+    for(int r = 0; r < dim; r++) for(int c = 0; c < dim; c++) {
+        if(!abs_exists(m, base_r + r, base_c + c)) continue;
+        if(intf[r * dim + c] == INFINITY || intf[r * dim + c] == 0.0f) continue;
+        set_cell(flow_dir_n(intf, dim, r, c), r, c, dim, inout);
+    }
+    free(intf); free(mask);
+}

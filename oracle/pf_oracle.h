@@ -81,4 +81,13 @@ void pfo_flow_update_island_to_nearest(const pfo_map *m, const uint16_t *gisl, c
  * = {pathable, type, base_height, ramp_height}; ref_layer = the reference's enum nav_layer (0..11);
  * out = cost_base [chunks][64][64] */
 void pfo_cost_from_tiles(int chunk_w, int chunk_h, const int32_t *attrs, int ref_layer, uint8_t *out);
+/* Region fields (dim x dim tiles around `center`, two directions per byte; absolute tile coordinates
+ * = chunk * 64 + tile; seeds / overlay = (r, c) pairs): N_CellArrivalFieldCreate (field.c:2445, cell_mode 1),
+ * N_GroupArrivalFieldCreate (field.c:2525) and N_CellArrivalFieldUpdateToNearestPathable (field.c:2603) */
+void pfo_region_field_create(const pfo_map *m, int dim, uint16_t enemies, int cell_mode, const int32_t *seeds, int nseeds,
+                             int center_r, int center_c, const int32_t *overlay, int noverlay, uint8_t *out);
+void pfo_group_arrival_field(const pfo_map *m, int dim, uint16_t enemies, const float *targets_xz, int ntargets,
+                             const float *center_xz, const int32_t *overlay, int noverlay, uint8_t *out);
+void pfo_region_field_update_to_nearest_pathable(const pfo_map *m, int dim, int start_r, int start_c, int center_r, int center_c,
+                                                 const int32_t *overlay, int noverlay, uint8_t *inout);
 #endif

@@ -39,6 +39,11 @@ def lib():
         L.pfo_flow_update_nearest_pathable.argtypes = [C.POINTER(_Map)] + [C.c_int] * 4 + [C.c_void_p]
         L.pfo_flow_update_island_to_nearest.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_uint16, C.c_void_p]
         L.pfo_cost_from_tiles.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.pfo_region_field_create.argtypes = [C.POINTER(_Map), C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.pfo_group_arrival_field.argtypes = [C.POINTER(_Map), C.c_int, C.c_uint16, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_void_p]
+        L.pfo_region_field_update_to_nearest_pathable.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -90,6 +95,35 @@ class OracleMap:
         req = np.ascontiguousarray(req)
         lib().pfo_flow_update_island_to_nearest(C.byref(self.m), _p(gisl), _p(req), int(local_iid), _p(buf))
         return buf.reshape(64, 64)
+
+    # ---- region fields (absolute tile coordinates = chunk * 64 + tile) ----
+    @staticmethod
+    def _pairs(a):
+        a = np.ascontiguousarray(a if a is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        return a, len(a)
+
+    def region_field_create(self, dim, enemies, cell_mode, seeds, center, overlay=None):
+        """N_CellArrivalFieldCreate (cell_mode=1, seeds = [target]) / tile-space N_GroupArrivalFieldCreate"""
+        sd, ns = self._pairs(seeds); ov, no = self._pairs(overlay)
+        out = np.zeros((dim, dim // 2), np.uint8)
+        lib().pfo_region_field_create(C.byref(self.m), dim, int(enemies), int(cell_mode), _p(sd), ns,
+                                      int(center[0]), int(center[1]), _p(ov), no, _p(out))
+        return out
+
+    def group_arrival_field(self, dim, enemies, targets_xz, center_xz, overlay=None):
+        t = np.ascontiguousarray(targets_xz, np.float32).reshape(-1, 2); ov, no = self._pairs(overlay)
+        c = np.ascontiguousarray(center_xz, np.float32)
+        out = np.zeros((dim, dim // 2), np.uint8)
+        lib().pfo_group_arrival_field(C.byref(self.m), dim, int(enemies), _p(t), len(t), _p(c), _p(ov), no, _p(out))
+        return out
+
+    def region_field_fixup(self, dim, start, center, inout, overlay=None):
+        """N_CellArrivalFieldUpdateToNearestPathable"""
+        ov, no = self._pairs(overlay)
+        buf = np.ascontiguousarray(inout, np.uint8).copy()
+        lib().pfo_region_field_update_to_nearest_pathable(C.byref(self.m), dim, int(start[0]), int(start[1]),
+                                                          int(center[0]), int(center[1]), _p(ov), no, _p(buf))
+        return buf
 
     def los_fields_create(self, reqs):
         reqs = np.ascontiguousarray(reqs)

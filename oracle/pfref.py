@@ -32,6 +32,10 @@ def lib():
         L.pfref_flow_field_portal.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
         L.pfref_flow_nearest_pathable.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
         L.pfref_flow_island_to_nearest.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
+        L.pfref_cell_arrival_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_void_p]
+        L.pfref_group_arrival_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_void_p]
         L.pfref_set_war.argtypes = [C.c_int, C.c_int, C.c_int]
         L.pfref_los_field_faction.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -149,6 +153,22 @@ class RefMap:
         lib().pfref_flow_field_portal(self.h, layer, chunk[0], chunk[1], portal_idx, port_iid, next_iid,
                                       faction, int(init), _p(buf))
         return buf.reshape(64, 64)
+
+    def cell_arrival_field(self, dim, target, center, enemies=0, overlay=None, fixup_start=None, layer=0):
+        """N_CellArrivalFieldCreate [+ ...UpdateToNearestPathable]; absolute (r, c) tile coordinates."""
+        t = np.asarray(target, np.int32); c = np.asarray(center, np.int32)
+        ov = np.ascontiguousarray(overlay if overlay is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        st = None if fixup_start is None else np.asarray(fixup_start, np.int32)
+        out = np.zeros((dim, dim // 2), np.uint8)
+        lib().pfref_cell_arrival_field(self.h, dim, layer, int(enemies), _p(t), _p(c), _p(ov), len(ov), _p(st), _p(out))
+        return out
+
+    def group_arrival_field(self, dim, targets_xz, center_xz, enemies=0, overlay=None, layer=0):
+        t = np.ascontiguousarray(targets_xz, np.float32).reshape(-1, 2); c = np.asarray(center_xz, np.float32)
+        ov = np.ascontiguousarray(overlay if overlay is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        out = np.zeros((dim, dim // 2), np.uint8)
+        lib().pfref_group_arrival_field(self.h, dim, layer, int(enemies), _p(t), len(t), _p(c), _p(ov), len(ov), _p(out))
+        return out
 
     def set_war(self, a, b, at_war=True):
         lib().pfref_set_war(a, b, int(at_war))

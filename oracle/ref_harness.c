@@ -477,6 +477,47 @@ PFREF_EXPORT void pfref_flow_island_to_nearest(void *m, int layer, int chunk_r, 
     pfref_flow_pack(&ff, inout);
 }
 
+/* Region fields. Tile coordinates cross this boundary as absolute (r, c) = chunk * 64 + tile.
+ * N_CellArrivalFieldCreate (field.c:2445) [+ N_CellArrivalFieldUpdateToNearestPathable (field.c:2603)
+ * when start_rc != NULL, the way cell_field_fixup_task calls them, formation.c:3171-3176]. */
+static struct tile_desc pfref_td(int ar, int ac) { return (struct tile_desc){ar / 64, ac / 64, ar % 64, ac % 64}; }
+static size_t pfref_ws_size(int dim) { return (size_t)dim * dim * 64 + 4096; }
+
+PFREF_EXPORT void pfref_cell_arrival_field(void *m, int dim, int layer, int enemies, const int32_t *target_rc,
+                                           const int32_t *center_rc, const int32_t *overlay_rc, int noverlay,
+                                           const int32_t *start_rc, uint8_t *out)
+{
+    struct nav_private *priv = pfref_priv(m);
+    size_t ws = pfref_ws_size(dim);
+    void *work = malloc(ws);
+    struct tile_desc *ov = malloc(sizeof(struct tile_desc) * (noverlay ? noverlay : 1));
+    for(int i = 0; i < noverlay; i++) ov[i] = pfref_td(overlay_rc[2*i], overlay_rc[2*i+1]);
+    struct nav_cell_overlay overlay = { ov, (size_t)noverlay };
+    N_CellArrivalFieldCreate(priv, dim, dim, layer, (uint16_t)enemies, pfref_td(target_rc[0], target_rc[1]),
+        pfref_td(center_rc[0], center_rc[1]), out, work, ws, &overlay);
+    if(start_rc)
+        N_CellArrivalFieldUpdateToNearestPathable(priv, dim, dim, layer, (uint16_t)enemies,
+            pfref_td(start_rc[0], start_rc[1]), pfref_td(center_rc[0], center_rc[1]), out, work, ws, &overlay);
+    free(ov); free(work);
+}
+
+/* N_GroupArrivalFieldCreate (field.c:2525): world-space targets and centre */
+PFREF_EXPORT void pfref_group_arrival_field(void *m, int dim, int layer, int enemies, const float *targets_xz,
+                                            int ntargets, const float *center_xz, const int32_t *overlay_rc,
+                                            int noverlay, uint8_t *out)
+{
+    struct map *map = m;
+    struct nav_private *priv = pfref_priv(m);
+    size_t ws = pfref_ws_size(dim);
+    void *work = malloc(ws);
+    struct tile_desc *ov = malloc(sizeof(struct tile_desc) * (noverlay ? noverlay : 1));
+    for(int i = 0; i < noverlay; i++) ov[i] = pfref_td(overlay_rc[2*i], overlay_rc[2*i+1]);
+    struct nav_cell_overlay overlay = { ov, (size_t)noverlay };
+    N_GroupArrivalFieldCreate(priv, dim, dim, layer, (uint16_t)enemies, map->pos, (const vec2_t*)targets_xz,
+        ntargets, (vec2_t){center_xz[0], center_xz[1]}, out, work, ws, &overlay);
+    free(ov); free(work);
+}
+
 /* N_LOSFieldCreate; field.c:2085. prev may be NULL (destination chunk). */
 PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
                                   int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,

@@ -50,6 +50,13 @@ PATCH = np.dtype([
     ("next_prot", "<f4", 4), ("_padf", "<f4", 3)])
 assert PATCH.itemsize == 128
 
+REGION_REQ = np.dtype([
+    ("layer", "<i4"), ("center_r", "<i4"), ("center_c", "<i4"), ("start_r", "<i4"), ("start_c", "<i4"),
+    ("seed_off", "<i4"), ("seed_n", "<i4"), ("overlay_off", "<i4"), ("overlay_n", "<i4"),
+    ("enemies", "<u2"), ("flags", "<u2")])
+assert REGION_REQ.itemsize == 40
+REGION_CREATE, REGION_FIXUP, REGION_CELL = 1, 2, 4
+
 LOS_PREV_INPLACE = -3
 TICK_VDES_FROM_POOL = 1
 FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 1 << 14, 1 << 15, 1 << 18, 1 << 21
@@ -69,6 +76,7 @@ SYMBOLS = [
     "pfnav_profile_read", "pfnav_map_cost_from_tiles", "pfnav_map_get_layer", "pfnav_fields_join", "pfnav_flow_fields_repair", "pfnav_pool_repair", "pfnav_set_enemy_factions", "pfnav_request_faction", "pfnav_set_two_phase", "pfnav_los_trace", "pfnav_set_los_variant", "pfnav_blockers_incref_obb", "pfnav_blockers_decref_obb",
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
+    "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
 ]
 
 _lib = None
@@ -107,6 +115,12 @@ def load():
     L.pfnav_map_upload_factions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_pool_repair.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_flow_fields_repair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pfnav_region_fields.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]
+    L.pfnav_region_fields_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    L.pfnav_group_arrival_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_agents_upload_movestate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_agents_compute_updates.argtypes = [C.c_void_p, C.c_void_p]
     L.pfnav_agents_read_patches.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -123,6 +137,7 @@ def load():
     L.pfnav_blockers_incref.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
     L.pfnav_blockers_decref.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32]
     L.pfnav_blockers_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.pfnav_blockers_get_factions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.pfnav_map_commit.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.pfnav_pool_request_path.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -274,6 +289,43 @@ class Nav:
         _chk(self.L.pfnav_flow_fields_repair(self.h, _p(targets), _p(kinds), _p(args), len(targets), _p(buf)))
         return buf
 
+    def region_fields(self, dim, reqs, layer=0, inout=None):
+        """reqs: list of dicts {center, target | seeds, enemies, overlay, start, cell} in absolute tile coordinates
+        (the shape tests/cases.region_case builds) -> u8[n, dim, dim/2]. One pfnav_region_fields call."""
+        rec = np.zeros(len(reqs), REGION_REQ)
+        seeds, ovs = [], []
+        for i, q in enumerate(reqs):
+            sd = np.asarray(q["seeds"] if q.get("seeds") is not None else [q["target"]], np.int32).reshape(-1, 2)
+            ov = np.asarray(q["overlay"] if q.get("overlay") is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+            flags = 0 if q.get("no_create") else REGION_CREATE
+            if q.get("cell", q.get("seeds") is None):
+                flags |= REGION_CELL
+            if q.get("start") is not None:
+                flags |= REGION_FIXUP
+                rec["start_r"][i], rec["start_c"][i] = q["start"]
+            rec["layer"][i] = layer
+            rec["center_r"][i], rec["center_c"][i] = q["center"]
+            rec["seed_off"][i], rec["seed_n"][i] = sum(len(s) for s in seeds), len(sd)
+            rec["overlay_off"][i], rec["overlay_n"][i] = sum(len(o) for o in ovs), len(ov)
+            rec["enemies"][i] = q.get("enemies", 0); rec["flags"][i] = flags
+            seeds.append(sd); ovs.append(ov)
+        sd = np.ascontiguousarray(np.concatenate(seeds) if seeds else np.zeros((0, 2), np.int32))
+        ov = np.ascontiguousarray(np.concatenate(ovs) if ovs else np.zeros((0, 2), np.int32))
+        buf = (np.zeros((len(reqs), dim, dim // 2), np.uint8) if inout is None
+               else np.ascontiguousarray(inout, np.uint8).reshape(len(reqs), dim, dim // 2).copy())
+        _chk(self.L.pfnav_region_fields(self.h, dim, _p(rec), len(rec), _p(sd) if len(sd) else None, len(sd),
+                                        _p(ov) if len(ov) else None, len(ov), _p(buf)))
+        return buf
+
+    def group_arrival_field(self, dim, targets_xz, center_xz, enemies=0, overlay=None, layer=0):
+        """N_GroupArrivalFieldCreate (field.c:2525) with its world-space arguments"""
+        t = np.ascontiguousarray(targets_xz, np.float32).reshape(-1, 2); c = np.ascontiguousarray(center_xz, np.float32)
+        ov = np.ascontiguousarray(overlay if overlay is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        out = np.zeros((dim, dim // 2), np.uint8)
+        _chk(self.L.pfnav_group_arrival_field(self.h, layer, dim, int(enemies), _p(t) if len(t) else None, len(t), _p(c),
+                                              _p(ov) if len(ov) else None, len(ov), _p(out)))
+        return out
+
     def pool_repair(self):
         a, b = C.c_int(0), C.c_int(0)
         _chk(self.L.pfnav_pool_repair(self.h, C.byref(a), C.byref(b)))
@@ -351,6 +403,11 @@ class Nav:
         _chk(self.L.pfnav_blockers_get(self.h, layer, _p(out)))
         return out
 
+    def faction_counts(self, layer=0):
+        out = np.zeros((self.cw * self.ch, 15, 64, 64), np.uint8)
+        _chk(self.L.pfnav_blockers_get_factions(self.h, layer, _p(out)))
+        return out
+
     def map_commit(self):
         n = C.c_int(0)
         _chk(self.L.pfnav_map_commit(self.h, C.byref(n)))
@@ -396,6 +453,10 @@ class Nav:
     def flow_fields_update_dev(self, d_reqs_ptr, n, d_fields_ptr, stream=0, general=False):
         f = self.L.pfnav_flow_fields_update_general_dev if general else self.L.pfnav_flow_fields_update_dev
         _chk(f(self.h, C.c_void_p(d_reqs_ptr), n, C.c_void_p(d_fields_ptr), C.c_void_p(stream)))
+
+    def region_fields_dev(self, dim, d_reqs_ptr, n, d_seeds_ptr, d_overlay_ptr, d_fields_ptr, stream=0):
+        _chk(self.L.pfnav_region_fields_dev(self.h, dim, C.c_void_p(d_reqs_ptr), n, C.c_void_p(d_seeds_ptr),
+                                            C.c_void_p(d_overlay_ptr), C.c_void_p(d_fields_ptr), C.c_void_p(stream)))
 
     def los_fields_create(self, reqs, prev_fields=None):
         """prev_fields: {request index: 64x64 previous LOS field} for requests with prev_index = LOS_PREV_INPLACE"""

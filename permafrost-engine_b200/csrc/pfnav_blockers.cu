@@ -401,3 +401,14 @@ extern "C" int pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out)
     memcpy(out, ctx->h_blk.data() + ltiles * layer, ltiles * 2);
     return PFNAV_OK;
 }
+
+// Read back one layer's per-faction blocker counts (nav_chunk::factions, nav_data.h: [chunk][15][64][64] u8)
+// from the host mirror; all zero until a faction-tagged blocker was counted or pfnav_map_upload_factions ran.
+extern "C" int pfnav_blockers_get_factions(pfnav_ctx *ctx, int layer, uint8_t *out)
+{
+    PF_ARG(ctx && out && layer >= 0 && layer < ctx->nlayers, "args");
+    const size_t n = (size_t)ctx->chunk_w * ctx->chunk_h * 15 * 4096;
+    if ((size_t)layer < ctx->h_fac.size() && ctx->h_fac[layer].size() == n) memcpy(out, ctx->h_fac[layer].data(), n);
+    else memset(out, 0, n);
+    return PFNAV_OK;
+}

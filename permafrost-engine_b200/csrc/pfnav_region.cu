@@ -1,0 +1,439 @@
+// pfnav_region.cu -- region ("cell arrival" / "group arrival") fields, sm_100a.
+//
+// Reference: N_CellArrivalFieldCreate (navigation/field.c:2445), N_GroupArrivalFieldCreate (field.c:2525),
+// N_CellArrivalFieldUpdateToNearestPathable (field.c:2603) and their helpers field_build_integration_region
+// (:587), field_build_integration_nonpass_region (:678), field_passable_frontier (:1441), clamped_region
+// (:1892), field_build_flow_unaligned (:804), field_flow_dir (:355), set_flow_cell (:790).
+//
+// One CTA per field. The dim x dim window (dim = 96 for formations) is gathered from the row-major layer
+// images into shared memory once per pass: a cost byte and a flag byte per cell plus a 32-bit integration
+// value (6 bytes per cell, 54 KB at dim 96, four CTAs per SM). The reference's Dijkstra has non-negative
+// integer edge weights (cost_base of the tile entered, every sum < 2^24 so its float arithmetic is exact),
+// so its result is the unique shortest-distance fixed point: the kernel reaches it by in-place relaxation
+// sweeps (each thread owns a run of consecutive cells and alternates sweep direction) until no cell changes.
+//
+// The fix-up's flood (the passable rim of the blocked island around `start`) is a reachability fixed point as
+// well -- except when the map-clamped region has fewer rows than columns: the reference indexes its visited
+// array with stride region.r (visited_idx, field.c:1431), distinct tiles alias, and the outcome depends on
+// the breadth-first order. That case (regions hanging over the top / bottom map edge only) is replayed
+// literally by one thread, with the queue and visited array overlaid on the integration buffer.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "pfnav_internal.cuh"
+
+namespace {
+
+enum : uint8_t {
+    RG_EXISTS = 1,     // inside the map (M_Tile_RelativeDesc, tile.c:391)
+    RG_PASSP  = 2,     // field_tile_passable (field.c:117)
+    RG_PASSM  = 4,     // passable under the request's enemy mask (field_tile_passable_no_enemies, field.c:179)
+    RG_OVL    = 8,     // nav_cell_overlay::blocked
+    RG_ENT    = 16,    // may be entered by the current integration pass
+    RG_COMP   = 32,    // part of the blocked island flooded from `start`
+    RG_SEED   = 64,    // zero-cost source of the current integration pass
+    RG_INCL   = 128    // inside the map-clamped region of the fix-up flood
+};
+
+#define RG_INF 0xFFFFFFFFu
+#define RG_THREADS 256
+
+struct RegionGrids {
+    const uint8_t *cost; const uint16_t *blk; const uint16_t *fmask;   // [layer][H64][W64]
+    int W64, H64;
+};
+
+struct RegionSmem {
+    uint32_t *dist; uint8_t *cst; uint8_t *flg; int dim, N;
+};
+
+__device__ __forceinline__ void region_gather(const RegionGrids &g, const RegionSmem &s, int layer, int base_r, int base_c,
+                                              uint16_t enemies, const int32_t *ov, int nov)
+{
+    const size_t lbase = (size_t)layer * g.W64 * g.H64;
+    for (int i = threadIdx.x; i < s.N; i += RG_THREADS) {
+        const int r = i / s.dim, c = i - r * s.dim;
+        const int ar = base_r + r, ac = base_c + c;
+        uint8_t f = 0, cv = 0;
+        if (ar >= 0 && ar < g.H64 && ac >= 0 && ac < g.W64) {
+            const size_t off = lbase + (size_t)ar * g.W64 + ac;
+            cv = g.cost[off];
+            const uint16_t b = g.blk[off];
+            f = RG_EXISTS;
+            if (cv != 0xFF) {
+                if (b == 0) f |= RG_PASSP | RG_PASSM;
+                else if (enemies != 0 && (g.fmask[off] & ~enemies) == 0) f |= RG_PASSM;
+            }
+        }
+        s.cst[i] = cv; s.flg[i] = f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nov; k += RG_THREADS) {        // build_overlay_mask (field.c:571)
+        const int dr = ov[2 * k] - base_r, dc = ov[2 * k + 1] - base_c;
+        if (dr >= 0 && dr < s.dim && dc >= 0 && dc < s.dim) s.flg[dr * s.dim + dc] |= RG_OVL;
+    }
+    __syncthreads();
+}
+
+// relaxation to the shortest-distance fixed point over the RG_ENT cells (sources: dist == 0 on entry)
+__device__ __forceinline__ void region_relax(const RegionSmem &s)
+{
+    const int dim = s.dim, N = s.N;
+    const int per = (N + RG_THREADS - 1) / RG_THREADS;
+    const int lo = min((int)threadIdx.x * per, N), hi = min(lo + per, N);
+    bool fwd = true;
+    while (true) {
+        bool changed = false;
+        for (int k = 0; k < hi - lo; k++) {
+            const int i = fwd ? lo + k : hi - 1 - k;
+            if (!(s.flg[i] & RG_ENT)) continue;
+            const int r = i / dim, c = i - r * dim;
+            uint32_t m = RG_INF;
+            if (r > 0) m = min(m, s.dist[i - dim]);
+            if (r < dim - 1) m = min(m, s.dist[i + dim]);
+            if (c > 0) m = min(m, s.dist[i - 1]);
+            if (c < dim - 1) m = min(m, s.dist[i + 1]);
+            if (m == RG_INF) continue;
+            const uint32_t nd = m + s.cst[i];
+            if (nd < s.dist[i]) { s.dist[i] = nd; changed = true; }
+        }
+        fwd = !fwd;
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
+// field_flow_dir (field.c:355) over the integer integration values; note the last test's `c < rdim - 1`
+__device__ __forceinline__ uint32_t region_flow_dir(const uint32_t *f, int n, int r, int c)
+{
+    const int i = r * n + c;
+    const bool up = r > 0, dn = r < n - 1, lf = c > 0, rt = c < n - 1;
+    const uint32_t N_ = up ? f[i - n] : RG_INF, S_ = dn ? f[i + n] : RG_INF;
+    const uint32_t W_ = lf ? f[i - 1] : RG_INF, E_ = rt ? f[i + 1] : RG_INF;
+    uint32_t mc = min(min(N_, S_), min(W_, E_));
+    const uint32_t NW = (up && lf) ? f[i - n - 1] : RG_INF, NE = (up && rt) ? f[i - n + 1] : RG_INF;
+    const uint32_t SW = (dn && lf) ? f[i + n - 1] : RG_INF, SE = (dn && rt) ? f[i + n + 1] : RG_INF;
+    if (up && lf && N_ != RG_INF && W_ != RG_INF) mc = min(mc, NW);
+    if (up && rt && N_ != RG_INF && E_ != RG_INF) mc = min(mc, NE);
+    if (dn && lf && S_ != RG_INF && W_ != RG_INF) mc = min(mc, SW);
+    if (dn && rt && S_ != RG_INF && E_ != RG_INF) mc = min(mc, SE);
+    // enum flow_dir: FD_NONE 0, NW 1, N 2, NE 3, W 4, E 5, SW 6, S 7, SE 8
+    if (up && N_ == mc) return 2;
+    if (dn && S_ == mc) return 7;
+    if (rt && E_ == mc) return 5;
+    if (lf && W_ == mc) return 4;
+    if (up && lf && NW == mc) return 1;
+    if (up && rt && NE == mc) return 3;
+    if (dn && lf && SW == mc) return 6;
+    if (dn && rt && SE == mc) return 8;
+    return 0;
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 4) k_region_fields(RegionGrids g, int dim, const pfnav_region_req *__restrict__ reqs,
+                                                              int n, const int32_t *__restrict__ seeds,
+                                                              const int32_t *__restrict__ overlay, uint8_t *__restrict__ fields)
+{
+    extern __shared__ uint32_t rg_smem[];
+    RegionSmem s;
+    s.dim = dim; s.N = dim * dim;
+    s.dist = rg_smem; s.cst = reinterpret_cast<uint8_t *>(s.dist + s.N); s.flg = s.cst + s.N;
+    const int N = s.N, half = dim / 2, tid = threadIdx.x;
+
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        const pfnav_region_req rq = reqs[q];
+        uint8_t *out = fields + (size_t)q * (N / 2);
+        const int32_t *ov = overlay + 2 * (size_t)rq.overlay_off;
+        __syncthreads();
+
+        if (rq.flags & PFNAV_REGION_CREATE) {
+            int base_r = rq.center_r - half, base_c = rq.center_c - half;
+            const int32_t *sd = seeds + 2 * (size_t)rq.seed_off;
+            if (rq.flags & PFNAV_REGION_CELL) {              // field.c:2477-2482
+                if (sd[0] - base_r >= dim) base_r = sd[0] - (dim - 1);
+                if (sd[1] - base_c >= dim) base_c = sd[1] - (dim - 1);
+            }
+            region_gather(g, s, rq.layer, base_r, base_c, rq.enemies, ov, rq.overlay_n);
+            for (int i = tid; i < N; i += RG_THREADS) {
+                const uint8_t f = s.flg[i];
+                s.dist[i] = RG_INF;
+                if ((f & (RG_EXISTS | RG_PASSM | RG_OVL)) == (RG_EXISTS | RG_PASSM)) s.flg[i] = f | RG_ENT;
+            }
+            __syncthreads();
+            for (int k = tid; k < rq.seed_n; k += RG_THREADS) {
+                const int dr = sd[2 * k] - base_r, dc = sd[2 * k + 1] - base_c;
+                if (dr >= 0 && dr < dim && dc >= 0 && dc < dim) s.dist[dr * dim + dc] = 0;
+            }
+            __syncthreads();
+            region_relax(s);
+            // field_build_flow_unaligned (field.c:804): unreached cells keep the memset's 0 == FD_NONE
+            for (int b = tid; b < N / 2; b += RG_THREADS) {
+                const int r = b / half, c = (b - r * half) * 2;
+                uint32_t hi = 0, lo = 0;
+                const uint32_t d0 = s.dist[r * dim + c], d1 = s.dist[r * dim + c + 1];
+                if (d0 != RG_INF && d0 != 0) hi = region_flow_dir(s.dist, dim, r, c);
+                if (d1 != RG_INF && d1 != 0) lo = region_flow_dir(s.dist, dim, r, c + 1);
+                out[b] = (uint8_t)((hi << 4) | lo);
+            }
+            __syncthreads();
+        }
+
+        if (rq.flags & PFNAV_REGION_FIXUP) {
+            // the fix-up's own base: the create call's target shift is not repeated (field.c:2650-2657)
+            const int base_r = rq.center_r - half, base_c = rq.center_c - half;
+            // clamped_region (field.c:1892): extents are end - base
+            const int cb_r = base_r >= 0 ? base_r : 0, cb_c = base_c >= 0 ? base_c : 0;
+            const int ce_r = rq.center_r + half < g.H64 ? rq.center_r + half : g.H64 - 1;
+            const int ce_c = rq.center_c + half < g.W64 ? rq.center_c + half : g.W64 - 1;
+            const int reg_r = ce_r - cb_r, reg_c = ce_c - cb_c;
+            const int wr0 = cb_r - base_r, wc0 = cb_c - base_c;      // the clamped window inside the dim x dim cells
+            const int sr = rq.start_r - base_r, sc = rq.start_c - base_c;
+            const bool start_ok = sr >= wr0 && sr < wr0 + reg_r && sc >= wc0 && sc < wc0 + reg_c;
+            region_gather(g, s, rq.layer, base_r, base_c, rq.enemies, ov, rq.overlay_n);
+            for (int i = tid; i < N; i += RG_THREADS) {
+                const int r = i / dim, c = i - r * dim;
+                uint8_t f = s.flg[i];
+                if (r >= wr0 && r < wr0 + reg_r && c >= wc0 && c < wc0 + reg_c && (f & RG_EXISTS)) f |= RG_INCL;
+                s.flg[i] = f;
+            }
+            __syncthreads();
+            if (start_ok) {
+                if (reg_r >= reg_c) {
+                    // field_passable_frontier (field.c:1441) as a reachability fixed point
+                    if (tid == 0) s.flg[sr * dim + sc] |= (s.flg[sr * dim + sc] & RG_PASSP) ? RG_SEED : RG_COMP;
+                    __syncthreads();
+                    const int per = (N + RG_THREADS - 1) / RG_THREADS;
+                    const int lo = min(tid * per, N), hi = min(lo + per, N);
+                    bool fwd = true;
+                    while (true) {
+                        bool changed = false;
+                        for (int k = 0; k < hi - lo; k++) {
+                            const int i = fwd ? lo + k : hi - 1 - k;
+                            const uint8_t f = s.flg[i];
+                            if ((f & (RG_INCL | RG_PASSP | RG_COMP)) != RG_INCL) continue;
+                            const int r = i / dim, c = i - r * dim;
+                            uint8_t nb = 0;
+                            if (r > 0) nb |= s.flg[i - dim];
+                            if (r < dim - 1) nb |= s.flg[i + dim];
+                            if (c > 0) nb |= s.flg[i - 1];
+                            if (c < dim - 1) nb |= s.flg[i + 1];
+                            if (nb & RG_COMP) { s.flg[i] = f | RG_COMP; changed = true; }
+                        }
+                        fwd = !fwd;
+                        if (!__syncthreads_or(changed)) break;
+                    }
+                    for (int i = tid; i < N; i += RG_THREADS) {
+                        const uint8_t f = s.flg[i];
+                        if ((f & (RG_INCL | RG_PASSP)) != (RG_INCL | RG_PASSP)) continue;
+                        const int r = i / dim, c = i - r * dim;
+                        uint8_t nb = 0;
+                        if (r > 0) nb |= s.flg[i - dim];
+                        if (r < dim - 1) nb |= s.flg[i + dim];
+                        if (c > 0) nb |= s.flg[i - 1];
+                        if (c < dim - 1) nb |= s.flg[i + 1];
+                        if (nb & RG_COMP) s.flg[i] = f | RG_SEED;
+                    }
+                    __syncthreads();
+                } else {
+                    // rows < columns: visited_idx (field.c:1431) aliases; replay the breadth-first order literally
+                    uint8_t *visited = reinterpret_cast<uint8_t *>(s.dist);
+                    uint16_t *queue = reinterpret_cast<uint16_t *>(visited + N);
+                    for (int i = tid; i < N; i += RG_THREADS) visited[i] = 0;
+                    __syncthreads();
+                    if (tid == 0) {
+                        int head = 0, tail = 0;
+                        queue[tail++] = (uint16_t)(sr * dim + sc);
+                        visited[(sr - wr0) * reg_r + (sc - wc0)] = 1;
+                        while (head < tail) {
+                            const int i = queue[head++];
+                            const uint8_t f = s.flg[i];
+                            if (f & RG_PASSP) { s.flg[i] = f | RG_SEED; continue; }
+                            const int r = i / dim, c = i - r * dim;
+                            const int nr[4] = {r, r, r - 1, r + 1}, nc[4] = {c - 1, c + 1, c, c};   // field.c:1492-1497
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                if (nr[e] < wr0 || nr[e] >= wr0 + reg_r || nc[e] < wc0 || nc[e] >= wc0 + reg_c) continue;
+                                const int j = nr[e] * dim + nc[e];
+                                if (!(s.flg[j] & RG_EXISTS)) continue;
+                                const int v = (nr[e] - wr0) * reg_r + (nc[e] - wc0);
+                                if (visited[v]) continue;
+                                visited[v] = 1;
+                                queue[tail++] = (uint16_t)j;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                // field_build_integration_nonpass_region (field.c:678): only non-passable or overlay-blocked tiles
+                for (int i = tid; i < N; i += RG_THREADS) {
+                    const uint8_t f = s.flg[i];
+                    s.dist[i] = (f & RG_SEED) ? 0u : RG_INF;
+                    const bool ent = (f & RG_EXISTS) && !((f & RG_PASSP) && !(f & RG_OVL));
+                    s.flg[i] = ent ? (f | RG_ENT) : (f & ~RG_ENT);
+                }
+                __syncthreads();
+                region_relax(s);
+                for (int b = tid; b < N / 2; b += RG_THREADS) {
+                    const int r = b / half, c = (b - r * half) * 2;
+                    const uint32_t d0 = s.dist[r * dim + c], d1 = s.dist[r * dim + c + 1];
+                    const bool u0 = d0 != RG_INF && d0 != 0 && (s.flg[r * dim + c] & RG_EXISTS);
+                    const bool u1 = d1 != RG_INF && d1 != 0 && (s.flg[r * dim + c + 1] & RG_EXISTS);
+                    if (!(u0 || u1)) continue;
+                    uint32_t v = out[b];
+                    if (u0) v = (v & 0x0Fu) | (region_flow_dir(s.dist, dim, r, c) << 4);
+                    if (u1) v = (v & 0xF0u) | region_flow_dir(s.dist, dim, r, c + 1);
+                    out[b] = (uint8_t)v;
+                }
+            }
+        }
+    }
+}
+
+}   // namespace
+
+static int region_launch(pfnav_ctx *ctx, int dim, const pfnav_region_req *d_reqs, size_t n, const int32_t *d_seeds,
+                         const int32_t *d_overlay, uint8_t *d_fields, cudaStream_t st)
+{
+    RegionGrids g;
+    g.cost = ctx->d_cost; g.blk = ctx->d_blk; g.fmask = ctx->d_fmask; g.W64 = ctx->W64; g.H64 = ctx->H64;
+    const size_t smem = (size_t)dim * dim * 6;
+    PF_CUDA(cudaFuncSetAttribute(k_region_fields, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PFNAV_REGION_DIM_MAX * PFNAV_REGION_DIM_MAX * 6));
+    const int per_sm = std::max(1, std::min(4, (int)((size_t)(227 * 1024) / (smem + 1024))));
+    const int grid = (int)std::min<size_t>(n, (size_t)ctx->sm_count * per_sm);
+    k_region_fields<<<grid, RG_THREADS, smem, st>>>(g, dim, d_reqs, (int)n, d_seeds, d_overlay, d_fields);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_region_fields_dev(pfnav_ctx *ctx, int dim, const pfnav_region_req *d_reqs, size_t n,
+                                       const int32_t *d_seeds_rc, const int32_t *d_overlay_rc, uint8_t *d_inout_fields,
+                                       void *stream)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(dim >= 2 && dim <= PFNAV_REGION_DIM_MAX && dim % 2 == 0, "dim must be even and <= PFNAV_REGION_DIM_MAX");
+    PF_ARG(d_reqs && d_inout_fields, "null buffer");
+    PF_ARG(n < (1u << 30), "n");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    return region_launch(ctx, dim, d_reqs, n, d_seeds_rc, d_overlay_rc, d_inout_fields, pf_stream(ctx, stream));
+}
+
+// the reference asserts these (field.c:2498-2499, 1455, 1487); here they are argument errors
+static int validate_region_reqs(const pfnav_ctx *ctx, int dim, const pfnav_region_req *reqs, size_t n, const int32_t *seeds,
+                                size_t nseeds, size_t noverlay)
+{
+    const int half = dim / 2;
+    for (size_t i = 0; i < n; i++) {
+        const pfnav_region_req &q = reqs[i];
+        PF_ARG(q.layer >= 0 && q.layer < ctx->nlayers, "region request: layer");
+        PF_ARG((q.flags & (PFNAV_REGION_CREATE | PFNAV_REGION_FIXUP)) != 0, "region request: neither CREATE nor FIXUP");
+        PF_ARG(q.center_r >= 0 && q.center_r < ctx->H64 && q.center_c >= 0 && q.center_c < ctx->W64, "region request: center outside the map");
+        PF_ARG(q.overlay_n >= 0 && q.overlay_off >= 0 && (size_t)q.overlay_off + q.overlay_n <= noverlay, "region request: overlay range");
+        if (q.flags & PFNAV_REGION_CREATE) {
+            PF_ARG(q.seed_n >= 0 && q.seed_off >= 0 && (size_t)q.seed_off + q.seed_n <= nseeds, "region request: seed range");
+            for (int k = 0; k < q.seed_n; k++) {
+                const int32_t *s = seeds + 2 * ((size_t)q.seed_off + k);
+                PF_ARG(s[0] >= 0 && s[0] < ctx->H64 && s[1] >= 0 && s[1] < ctx->W64, "region request: seed tile outside the map");
+            }
+            if (q.flags & PFNAV_REGION_CELL) {
+                PF_ARG(q.seed_n == 1, "region request: PFNAV_REGION_CELL takes exactly one seed");
+                const int32_t *s = seeds + 2 * (size_t)q.seed_off;
+                PF_ARG(s[0] >= q.center_r - half && s[1] >= q.center_c - half, "region request: cell tile before the region base");
+            }
+        }
+        if (q.flags & PFNAV_REGION_FIXUP) {
+            const int cb_r = std::max(q.center_r - half, 0), cb_c = std::max(q.center_c - half, 0);
+            const int ce_r = q.center_r + half < ctx->H64 ? q.center_r + half : ctx->H64 - 1;
+            const int ce_c = q.center_c + half < ctx->W64 ? q.center_c + half : ctx->W64 - 1;
+            PF_ARG(q.start_r >= cb_r && q.start_r < ce_r && q.start_c >= cb_c && q.start_c < ce_c,
+                   "region request: fix-up start outside the clamped region");
+        }
+    }
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_region_fields(pfnav_ctx *ctx, int dim, const pfnav_region_req *reqs, size_t n, const int32_t *seeds_rc,
+                                   size_t nseeds, const int32_t *overlay_rc, size_t noverlay, uint8_t *inout_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(dim >= 2 && dim <= PFNAV_REGION_DIM_MAX && dim % 2 == 0, "dim must be even and <= PFNAV_REGION_DIM_MAX");
+    PF_ARG(reqs && inout_fields, "null buffer");
+    PF_ARG((nseeds == 0 || seeds_rc) && (noverlay == 0 || overlay_rc), "null seed / overlay list");
+    PF_ARG(n < (1u << 30), "n");
+    int rc = validate_region_reqs(ctx, dim, reqs, n, seeds_rc, nseeds, noverlay);
+    if (rc) return rc;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    const size_t fbytes = (size_t)dim * dim / 2;
+    bool need_in = false;
+    for (size_t i = 0; i < n; i++) need_in |= !(reqs[i].flags & PFNAV_REGION_CREATE);
+    const size_t b_req = n * sizeof(pfnav_region_req), b_seed = std::max<size_t>(nseeds, 1) * 8, b_ov = std::max<size_t>(noverlay, 1) * 8;
+    uint8_t *d_buf = nullptr, *d_fields = nullptr;
+    PF_CUDA(cudaMalloc(&d_buf, b_req + b_seed + b_ov));
+    if (cudaMalloc(&d_fields, n * fbytes) != cudaSuccess) { cudaFree(d_buf); pfnav_set_error("cudaMalloc region fields"); return PFNAV_ERR_NOMEM; }
+    pfnav_region_req *d_reqs = reinterpret_cast<pfnav_region_req *>(d_buf);
+    int32_t *d_seeds = reinterpret_cast<int32_t *>(d_buf + b_req), *d_ov = reinterpret_cast<int32_t *>(d_buf + b_req + b_seed);
+    cudaStream_t st = ctx->tick_stream;
+    cudaError_t e = cudaMemcpyAsync(d_reqs, reqs, b_req, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nseeds) e = cudaMemcpyAsync(d_seeds, seeds_rc, nseeds * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && noverlay) e = cudaMemcpyAsync(d_ov, overlay_rc, noverlay * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && need_in) e = cudaMemcpyAsync(d_fields, inout_fields, n * fbytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = region_launch(ctx, dim, d_reqs, n, d_seeds, d_ov, d_fields, st);
+        if (rc == 0) e = cudaMemcpyAsync(inout_fields, d_fields, n * fbytes, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf); cudaFree(d_fields);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_region_fields: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+// M_Tile_DescForPoint2D with the nav resolution (tile.c:547) -> absolute (r, c)
+static bool region_tile_for_point(const pfnav_ctx *ctx, float px, float pz, int32_t *out_rc)
+{
+    const float width = (float)(ctx->chunk_w * 256), height = (float)(ctx->chunk_h * 256);
+    if (px > ctx->map_x || px < ctx->map_x - width) return false;
+    if (pz < ctx->map_z || pz > ctx->map_z + height) return false;
+    int chunk_r = (int)(fabs(ctx->map_z - pz) / 256.0f), chunk_c = (int)(fabs(ctx->map_x - px) / 256.0f);
+    chunk_r = std::min(std::max(chunk_r, 0), ctx->chunk_h - 1);
+    chunk_c = std::min(std::max(chunk_c, 0), ctx->chunk_w - 1);
+    const float bx = ctx->map_x - (chunk_c * 256.0f), bz = ctx->map_z + (chunk_r * 256.0f);
+    const int tile_r = (int)(fabs(bz - pz) / 4), tile_c = (int)(fabs(bx - px) / 4);
+    out_rc[0] = chunk_r * 64 + std::min(std::max(tile_r, 0), 63);
+    out_rc[1] = chunk_c * 64 + std::min(std::max(tile_c, 0), 63);
+    return true;
+}
+
+extern "C" int pfnav_group_arrival_field(pfnav_ctx *ctx, int layer, int dim, uint16_t enemies, const float *targets_xz,
+                                         size_t ntargets, const float *center_xz, const int32_t *overlay_rc, size_t noverlay,
+                                         uint8_t *out_field)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(dim >= 2 && dim <= PFNAV_REGION_DIM_MAX && dim % 2 == 0, "dim must be even and <= PFNAV_REGION_DIM_MAX");
+    PF_ARG(center_xz && out_field && (ntargets == 0 || targets_xz), "null buffer");
+    PF_ARG(ntargets < (1u << 28), "ntargets");
+    int32_t c[2];
+    if (!region_tile_for_point(ctx, center_xz[0], center_xz[1], c)) {        // field.c:2552-2556
+        memset(out_field, 0, (size_t)dim * dim / 2);
+        return PFNAV_OK;
+    }
+    std::vector<int32_t> seeds;
+    seeds.reserve(ntargets * 2);
+    for (size_t i = 0; i < ntargets; i++) {
+        int32_t t[2];
+        if (region_tile_for_point(ctx, targets_xz[2 * i], targets_xz[2 * i + 1], t)) { seeds.push_back(t[0]); seeds.push_back(t[1]); }
+    }
+    pfnav_region_req q = {};
+    q.layer = layer; q.center_r = c[0]; q.center_c = c[1];
+    q.seed_off = 0; q.seed_n = (int32_t)(seeds.size() / 2);
+    q.overlay_off = 0; q.overlay_n = (int32_t)noverlay;
+    q.enemies = enemies; q.flags = PFNAV_REGION_CREATE;
+    return pfnav_region_fields(ctx, dim, &q, 1, seeds.data(), seeds.size() / 2, overlay_rc, noverlay, out_field);
+}

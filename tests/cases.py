@@ -276,3 +276,83 @@ def repair_case(ref, cw, ch, seed, per_chunk=4):
                 T.append(req); K.append(1); A.append(iid); B.append(base)
                 E.append(ref.flow_island_to_nearest((cr, cc), iid, base, **kw))
     return (np.concatenate(T), np.array(K, np.int32), np.array(A, np.int32), np.stack(B), np.stack(E))
+
+
+def region_case(seed, cw=3, ch=3, n=40, dim=96):
+    """Region-field scenario ("cell arrival" fields, field.c:2445-2711) on a map with faction blockers.
+    -> (pathable, blockers[(x, z, radius, faction)], wars, reqs) where reqs is a list of dicts
+    {center, target, enemies, overlay, start} in absolute tile coordinates (start = None: no fixup pass).
+    Covers: interior regions, regions hanging over every map edge (incl. the rows < columns clamp whose visited
+    array aliases, field.c:1431), a target one past the far edge (base shift, field.c:2477), overlay tiles,
+    enemy masks and blocked / impassable fixup starts."""
+    rng = np.random.default_rng(seed)
+    p = noise_map(cw, ch, seed, 0.10)
+    H, W = ch * 64, cw * 64
+    blockers = [(float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)), float(rng.uniform(2, 12)),
+                 int(rng.integers(0, 4))) for _ in range(80)]
+    wars = [(0, 1), (0, 2), (3, 1)]
+    half = dim // 2
+    reqs = []
+    for i in range(n):
+        kind = i % 8
+        if kind in (0, 1, 2):      # interior
+            cr_, cc_ = int(rng.integers(half, H - half)), int(rng.integers(half, W - half))
+        elif kind == 3:            # top edge (rows clamped, columns not: aliasing flood)
+            cr_, cc_ = int(rng.integers(0, half - 4)), int(rng.integers(half, W - half))
+        elif kind == 4:            # left / bottom
+            cr_, cc_ = int(rng.integers(H - half + 2, H)), int(rng.integers(0, half))
+        elif kind == 5:            # right edge
+            cr_, cc_ = int(rng.integers(half, H - half)), int(rng.integers(W - half + 1, W))
+        elif kind == 6:            # corner
+            cr_, cc_ = int(rng.integers(0, 20)), int(rng.integers(W - 20, W))
+        else:
+            cr_, cc_ = int(rng.integers(0, H)), int(rng.integers(0, W))
+        lo_r, hi_r = max(cr_ - half, 0), min(cr_ + half - 1, H - 1)
+        lo_c, hi_c = max(cr_ * 0 + cc_ - half, 0), min(cc_ + half - 1, W - 1)
+        tr, tc = int(rng.integers(lo_r, hi_r + 1)), int(rng.integers(lo_c, hi_c + 1))
+        if i % 11 == 5 and cr_ + half < H and cc_ + half < W:
+            tr, tc = cr_ + half, cc_ + half          # one past the far edge: the base shifts
+        ov = None
+        if i % 3 == 1:
+            k = int(rng.integers(1, 40))
+            ov = np.stack([rng.integers(cr_ - half - 3, cr_ + half + 3, k), rng.integers(cc_ - half - 3, cc_ + half + 3, k)], 1)
+            ov = ov[(ov[:, 0] >= 0) & (ov[:, 0] < H) & (ov[:, 1] >= 0) & (ov[:, 1] < W)].astype(np.int32)
+        enemies = [0, 0, 0b0010, 0b0110, 0b1111][i % 5]
+        reqs.append(dict(center=(cr_, cc_), target=(tr, tc), enemies=enemies, overlay=ov, start=None, want_fixup=(i % 2 == 0)))
+    return p, blockers, wars, reqs
+
+
+def region_pick_starts(reqs, cost, blk, cw, ch, seed, dim=96):
+    """choose the fixup start of every request that wants one: a non-passable tile inside the clamped region
+    (clamped_region, field.c:1892), nearest to the centre in a seeded scan order"""
+    rng = np.random.default_rng(seed)
+    H, W = ch * 64, cw * 64
+    half = dim // 2
+    img_c = cost.reshape(ch, cw, 64, 64).transpose(0, 2, 1, 3).reshape(H, W)
+    img_b = blk.reshape(ch, cw, 64, 64).transpose(0, 2, 1, 3).reshape(H, W)
+    nonp = (img_c == 255) | (img_b > 0)
+    for q in reqs:
+        if not q["want_fixup"]:
+            continue
+        cr_, cc_ = q["center"]
+        b_r = cr_ - half if cr_ - half >= 0 else 0
+        b_c = cc_ - half if cc_ - half >= 0 else 0
+        e_r = cr_ + half if cr_ + half < H else H - 1
+        e_c = cc_ + half if cc_ + half < W else W - 1
+        cand = np.argwhere(nonp[b_r:e_r, b_c:e_c])
+        if len(cand) == 0:
+            continue
+        s = cand[rng.integers(len(cand))]
+        q["start"] = (int(s[0]) + b_r, int(s[1]) + b_c)
+    return reqs
+
+
+def region_reqs_from_golden(rec, ov):
+    """inverse of make_golden.pack_region_reqs"""
+    out, o = [], 0
+    for row in rec:
+        n = int(row[7])
+        out.append(dict(center=(int(row[0]), int(row[1])), target=(int(row[2]), int(row[3])), enemies=int(row[4]),
+                        start=None if row[5] < 0 else (int(row[5]), int(row[6])), overlay=ov[o:o + n] if n else None))
+        o += n
+    return out

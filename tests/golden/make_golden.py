@@ -299,7 +299,58 @@ def gen_faction():
     ref.close()
 
 
+def pack_region_reqs(reqs):
+    """-> int32[n, 8] = center r c, target r c, enemies, start r c (-1 = none), noverlay; int32[sum, 2] overlay tiles"""
+    rec = np.full((len(reqs), 8), -1, np.int32); ovs = []
+    for i, q in enumerate(reqs):
+        ov = np.zeros((0, 2), np.int32) if q["overlay"] is None else np.asarray(q["overlay"], np.int32).reshape(-1, 2)
+        rec[i, 0:2] = q["center"]; rec[i, 2:4] = q["target"]; rec[i, 4] = q["enemies"]
+        if q["start"] is not None:
+            rec[i, 5:7] = q["start"]
+        rec[i, 7] = len(ov); ovs.append(ov)
+    return rec, np.concatenate(ovs) if ovs else np.zeros((0, 2), np.int32)
+
+
+def gen_region():
+    """Region fields: N_CellArrivalFieldCreate [+ N_CellArrivalFieldUpdateToNearestPathable]
+    (field.c:2445, 2603) at the formation size 96 and at 32, and N_GroupArrivalFieldCreate (field.c:2525)"""
+    cw = ch = 3
+    out = {}
+    for dim in (96, 32):
+        p, blockers, wars, reqs = cases.region_case(21, cw, ch, 48, dim)
+        ref = pfref.RefMap(cw, ch, p)
+        for a, b in wars:
+            ref.set_war(a, b)
+        for b in blockers:
+            ref.blockers_incref(b[0], b[1], b[2], b[3], 0)
+        ref.update()
+        cost, blk, fac = ref.cost_base(), ref.blockers(), ref.factions()
+        cases.region_pick_starts(reqs, cost, blk, cw, ch, 21, dim)
+        exp = np.stack([ref.cell_arrival_field(dim, q["target"], q["center"], q["enemies"], q["overlay"], q["start"]) for q in reqs])
+        create_only = np.stack([ref.cell_arrival_field(dim, q["target"], q["center"], q["enemies"], q["overlay"], None) for q in reqs])
+        rec, ov = pack_region_reqs(reqs)
+        rng = np.random.default_rng(dim)
+        gt, gc, ge, gx = [], [], [], []
+        for k in range(10):
+            c = np.array([-rng.uniform(-4, cw * 256 + 4), rng.uniform(-4, ch * 256 + 4)], np.float32)     # sometimes off the map
+            t = np.stack([c[0] + rng.uniform(-220, 220, 16), c[1] + rng.uniform(-220, 220, 16)], 1).astype(np.float32)
+            e = [0, 0b0110][k % 2]
+            gt.append(t); gc.append(c); ge.append(e); gx.append(ref.group_arrival_field(dim, t, c, e))
+        nfix = sum(q["start"] is not None for q in reqs)
+        print("region dim %d: %d requests, %d with fix-up (changed %d), group fields %d (zero: %d)" % (
+            dim, len(reqs), nfix, int((exp != create_only).reshape(len(reqs), -1).any(axis=1).sum()), len(gx),
+            sum(int(not x.any()) for x in gx)))
+        if dim == 96:
+            out.update(pathable=p, cost=cost, blk=blk, factions=fac, blockers=np.array(blockers, np.float32))
+        out.update({"req%d" % dim: rec, "ov%d" % dim: ov, "exp%d" % dim: exp, "create%d" % dim: create_only,
+                    "gt%d" % dim: np.stack(gt), "gc%d" % dim: np.stack(gc), "ge%d" % dim: np.array(ge, np.int32), "gx%d" % dim: np.stack(gx)})
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "region.npz"), **out)
+
+
+
 if __name__ == "__main__":
+    gen_region()
     gen_faction()
     gen_repair_pool()
     gen_repair()

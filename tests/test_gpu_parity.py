@@ -651,3 +651,89 @@ def test_los_with_caller_held_prev_field(nav):
             done += 1
         assert (got == exp[i]).all(), i
     assert done > 0
+
+
+# ------------------------------------------------------------------ region ("cell arrival") fields
+def _region_map(nav, g):
+    nav.map_create(3, 3, 1)
+    nav.map_upload_layer(0, g["cost"], g["blk"])
+    nav.map_upload_factions(0, g["factions"])
+
+
+@pytest.mark.parametrize("dim", [96, 32])
+def test_region_fields_golden(nav, dim):
+    """N_CellArrivalFieldCreate [+ N_CellArrivalFieldUpdateToNearestPathable] and N_GroupArrivalFieldCreate
+    (field.c:2445, 2603, 2525) vs the compiled reference: one batched launch, bit-exact packed directions"""
+    g = gold("region")
+    _region_map(nav, g)
+    reqs = cases.region_reqs_from_golden(g["req%d" % dim], g["ov%d" % dim])
+    got = nav.region_fields(dim, reqs)
+    bad = [i for i in range(len(reqs)) if (got[i] != g["exp%d" % dim][i]).any()]
+    assert not bad, bad
+    # create alone, then the fix-up in place on the caller's field (the reference's two separate calls)
+    create = nav.region_fields(dim, [dict(q, start=None) for q in reqs])
+    assert (create == g["create%d" % dim]).all()
+    fix = [i for i, q in enumerate(reqs) if q["start"] is not None]
+    upd = nav.region_fields(dim, [dict(reqs[i], no_create=True) for i in fix], inout=create[fix])
+    assert (upd == g["exp%d" % dim][fix]).all()
+    for k in range(len(g["gx%d" % dim])):
+        f = nav.group_arrival_field(dim, g["gt%d" % dim][k], g["gc%d" % dim][k], int(g["ge%d" % dim][k]))
+        assert (f == g["gx%d" % dim][k]).all(), k
+
+
+def test_region_fields_vs_port(nav, pforacle):
+    """a formation-sized batch (one 96 x 96 field per cell, formation.c:3152) on a 4 x 4-chunk map vs the port;
+    dims 96, 64 and 128 (PFNAV_REGION_DIM_MAX)"""
+    cw = ch = 4
+    for seed, dim, n in ((91, 96, 300), (92, 64, 64), (93, 128, 24)):
+        p, blockers, wars, reqs = cases.region_case(seed, cw, ch, n, dim)
+        cost = synth.cost_from_pathable(p, cw, ch)
+        nav.map_create(cw, ch, 1)
+        nav.map_upload_layer(0, cost); nav.map_build_nav(0)
+        enemies = np.zeros(16, np.uint16)
+        for a, b in wars:
+            enemies[a] |= 1 << b; enemies[b] |= 1 << a
+        for f in range(15):
+            nav.set_enemy_factions(f, int(enemies[f]))
+        for x, z, r, f in blockers:
+            nav.blockers_incref(float(x), float(z), float(r), int(f), 0)
+        nav.map_commit()
+        blk = nav.blockers(0)
+        fac = nav.faction_counts(0)         # nav_chunk::factions as counted by pfnav_blockers_incref (pinned by faction.npz)
+        cases.region_pick_starts(reqs, cost, blk, cw, ch, seed, dim)
+        om = pforacle.OracleMap(cw, ch, cost, blk, None, factions=fac)
+        got = nav.region_fields(dim, reqs)
+        for i, q in enumerate(reqs):
+            e = om.region_field_create(dim, q["enemies"], 1, [q["target"]], q["center"], q["overlay"])
+            if q["start"] is not None:
+                e = om.region_field_fixup(dim, q["start"], q["center"], e, q["overlay"])
+            assert (got[i] == e).all(), (seed, dim, i, q)
+        # many seeds per field (tile-space group arrival), no base shift
+        rng = np.random.default_rng(seed)
+        greqs = []
+        for q in reqs[:16]:
+            sd = np.stack([rng.integers(0, ch * 64, 20), rng.integers(0, cw * 64, 20)], 1)
+            greqs.append(dict(center=q["center"], seeds=sd, enemies=q["enemies"], overlay=q["overlay"], start=None, cell=False))
+        gg = nav.region_fields(dim, greqs)
+        for i, q in enumerate(greqs):
+            assert (gg[i] == om.region_field_create(dim, q["enemies"], 0, q["seeds"], q["center"], q["overlay"])).all(), (seed, i)
+
+
+def test_region_fields_argument_errors(nav):
+    g = gold("region")
+    _region_map(nav, g)
+    ok = dict(center=(96, 96), target=(100, 100), enemies=0, overlay=None, start=None)
+    assert nav.region_fields(96, [ok]).shape == (1, 96, 48)
+    with pytest.raises(Exception):
+        nav.region_fields(95, [ok])                                        # odd dim
+    with pytest.raises(Exception):
+        nav.region_fields(130, [ok])                                       # > PFNAV_REGION_DIM_MAX
+    with pytest.raises(Exception):
+        nav.region_fields(96, [dict(ok, center=(400, 10))])                # centre outside the map
+    with pytest.raises(Exception):
+        nav.region_fields(96, [dict(ok, target=(10, 100))])                # cell tile before the region base
+    with pytest.raises(Exception):
+        nav.region_fields(96, [dict(ok, start=(190, 190))])                # fix-up start outside the clamped region
+    with pytest.raises(Exception):
+        nav.region_fields(96, [dict(ok, seeds=[(100, 100), (101, 101)], cell=True)])
+    assert nav.region_fields(96, []).shape == (0, 96, 48)

@@ -153,6 +153,45 @@ def test_port_faction_fields_golden(pforacle):
     assert (om.los_fields_create(g["lreq"].view(capi.LOS_REQ)) == g["lexp"]).all()
 
 
+@pytest.mark.parametrize("dim", [96, 32])
+def test_port_region_fields_golden(pforacle, dim):
+    """cell arrival fields (+ fix-up) and group arrival fields vs the compiled reference's output (region.npz):
+    regions over every map edge, the aliasing flood (rows < columns), the base shift, overlays, enemy masks"""
+    g = gold("region")
+    om = pforacle.OracleMap(3, 3, g["cost"], g["blk"], None, factions=g["factions"])
+    reqs = cases.region_reqs_from_golden(g["req%d" % dim], g["ov%d" % dim])
+    for i, q in enumerate(reqs):
+        f = om.region_field_create(dim, q["enemies"], 1, [q["target"]], q["center"], q["overlay"])
+        assert (f == g["create%d" % dim][i]).all(), i
+        if q["start"] is not None:
+            f = om.region_field_fixup(dim, q["start"], q["center"], f, q["overlay"])
+        assert (f == g["exp%d" % dim][i]).all(), i
+    for k in range(len(g["gx%d" % dim])):
+        f = om.group_arrival_field(dim, int(g["ge%d" % dim][k]), g["gt%d" % dim][k], g["gc%d" % dim][k])
+        assert (f == g["gx%d" % dim][k]).all(), k
+
+
+def test_port_region_fields_vs_ref(pfref, pforacle):
+    cw = ch = 2
+    p, blockers, wars, reqs = cases.region_case(77, cw, ch, 32, 96)
+    ref = pfref.RefMap(cw, ch, p)
+    for a, b in wars:
+        ref.set_war(a, b)
+    for b in blockers:
+        ref.blockers_incref(b[0], b[1], b[2], b[3], 0)
+    ref.update()
+    cost, blk, fac = ref.cost_base(), ref.blockers(), ref.factions()
+    cases.region_pick_starts(reqs, cost, blk, cw, ch, 77, 96)
+    om = pforacle.OracleMap(cw, ch, cost, blk, None, factions=fac)
+    for q in reqs:
+        e = ref.cell_arrival_field(96, q["target"], q["center"], q["enemies"], q["overlay"], q["start"])
+        f = om.region_field_create(96, q["enemies"], 1, [q["target"]], q["center"], q["overlay"])
+        if q["start"] is not None:
+            f = om.region_field_fixup(96, q["start"], q["center"], f, q["overlay"])
+        assert (e == f).all(), q
+    ref.close()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 

@@ -85,7 +85,47 @@ def goals():
                       "prof_flow_ms": prof["flow"][0] / 5, "prof_los_ms": prof["los"][0] / 5}), flush=True)
 
 
+def region():
+    """formation-sized batches of 96 x 96 cell arrival fields (formation.c:3152) on the C2 map, device-resident"""
+    cw = ch = 16
+    p = synth.make_map(cw, ch, 0x5EED0001)
+    cost = synth.cost_from_pathable(p, cw, ch)
+    nav = capi.Nav(0)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost); nav.map_build_nav(0)
+    rng = np.random.default_rng(5)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
+    dim = 96
+    rec = np.zeros(n, capi.REGION_REQ)
+    c = rng.integers(48, cw * 64 - 48, (n, 2))
+    t = c + rng.integers(-40, 40, (n, 2))
+    rec["center_r"], rec["center_c"] = c[:, 0], c[:, 1]
+    rec["seed_off"] = np.arange(n); rec["seed_n"] = 1
+    rec["flags"] = capi.REGION_CREATE | capi.REGION_CELL
+    _stream = torch.cuda.Stream(); torch.cuda.set_stream(_stream)
+    st = _stream.cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    d_req = torch.from_numpy(rec.view(np.uint8)).cuda()
+    d_seed = torch.from_numpy(t.astype(np.int32)).cuda()
+    d_ov = torch.zeros(2, dtype=torch.int32, device="cuda")
+    out = torch.zeros((n, dim * dim // 2), dtype=torch.uint8, device="cuda")
+    def run():
+        nav.region_fields_dev(dim, d_req.data_ptr(), n, d_seed.data_ptr(), d_ov.data_ptr(), out.data_ptr(), st)
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); b.record(); torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    m = float(np.median(ms))
+    print(json.dumps({"kernel": "k_region_fields", "case": "cell arrival 96x96, create", "n": n, "ms": m, "fields_per_s": n / m * 1e3,
+                      "reached_frac": float((out != 0).float().mean().item())}), flush=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "goals":
         goals(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "region":
+        region(); sys.exit(0)
     main()
