@@ -353,6 +353,30 @@ int  pfnav_group_arrival_field(pfnav_ctx *ctx, int layer, int dim, uint16_t enem
                                size_t ntargets, const float *center_xz, const int32_t *overlay_rc, size_t noverlay,
                                uint8_t *out_field);
 
+/* Group arrival (TARGET_ZONE) fields: a flock arriving at its goal follows one shared field per chunk into the
+ * open tiles around the goal (arrival.c:859 -> N_RequestAsyncGroupArrivalField nav.c:3921 -> field task ->
+ * N_FlowFieldUpdate field.c:2050 -> field_update_zone :1810). The seeds are the first pi * radius^2 open tiles of a
+ * best-first flood from the centre (field_zone_initial_frontier, field.c:1683; computed on the host with the
+ * reference's heap order), the integration runs on the device over the chunk padded by half a chunk, and the
+ * chunk's 64 x 64 window is written one direction per byte. Call pfnav_map_commit first when blockers changed.
+ * Only maps with more than one chunk row AND column (or exactly 1 x 1) are accepted: with one of the two the
+ * reference indexes its padded buffer out of bounds. centre_r / centre_c: absolute nav tile of the zone centre. */
+int  pfnav_zone_seeds(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius,
+                      int32_t *out_rc, size_t cap, size_t *out_n);
+/* chunks_rc: n (chunk_r, chunk_c) pairs; out_fields: HOST, n * 4096 bytes. Synchronous. */
+int  pfnav_zone_fields(pfnav_ctx *ctx, int layer, int centre_r, int centre_c, int radius, const int32_t *chunks_rc,
+                       size_t n, uint8_t *out_fields);
+/* N_RequestAsyncGroupArrivalField + N_AwaitAsyncFields (nav.c:3921, 3958): the zone fields of every chunk within
+ * reach (2 * radius tiles) of the world-space centre go into pool destination `dest` as its flow fields. A centre
+ * outside the map requests nothing. Returns when the fields are in the pool. */
+int  pfnav_pool_request_zone(pfnav_ctx *ctx, int dest, int layer, const float *centre_xz, int radius, void *stream,
+                             int *out_nfields);
+/* N_DesiredGroupArrivalVelocity (nav.c:3561) for n world positions against pool destination `dest`:
+ * out_vel[n][2] = N_FlowDir of the tile's direction; out_flags[n]: bit 0 = the call returned true (position and centre on
+ * the map, chunk field present), bit 1 = *out_at_slot (FD_NONE within `radius` tiles of the centre). HOST buffers. */
+int  pfnav_group_arrival_velocity(pfnav_ctx *ctx, int dest, const float *centre_xz, int radius, const float *pos_xz,
+                                  size_t n, float *out_vel, uint8_t *out_flags);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls
  * R_GL_MoveUploadData / R_GL_MoveDispatchWork / R_GL_MoveReadNewVelocities,

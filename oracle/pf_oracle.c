@@ -1277,3 +1277,139 @@ void pfo_region_field_update_to_nearest_pathable(const pfo_map *m, int dim, int 
     }
     free(intf); free(mask);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * TARGET_ZONE chunk fields (the group arrival fields a flock follows into the open slots around its goal):
+ * N_FlowFieldUpdate -> field_update_zone (field.c:1810) over the chunk padded by half a chunk on every side.
+ * ---------------------------------------------------------------------------------------- */
+/* field_zone_initial_frontier (field.c:1683): (1) snap to the nearest open tile, best-first by squared
+ * distance from the centre, stepping through blocked tiles; (2) best-first flood of the connected open
+ * footprint from that tile (pushed at priority 0) until `budget` tiles are collected. Both use the
+ * reference's binary heap, whose tie order decides which tiles of the last distance class make the budget. */
+static int zone_initial_frontier(const pfo_map *m, int centre_r, int centre_c, int base_r, int base_c, int dim,
+                                 int32_t *out, int budget)
+{
+    static const int er[8] = {0, 0, -1, 1, -1, -1, 1, 1}, ec[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+    const int cdr = centre_r - base_r, cdc = centre_c - base_c;
+    if(cdr < 0 || cdr >= dim || cdc < 0 || cdc >= dim) return 0;
+    bool *visited = calloc((size_t)dim * dim, 1);
+    pq frontier; pq_init(&frontier);
+    visited[cdr * dim + cdc] = true;
+    pq_push(&frontier, 0.0f, centre_r, centre_c);
+    int start_r = 0, start_c = 0; bool have_start = false;
+    while(frontier.size > 0) {
+        int r, c; pq_pop(&frontier, &r, &c);
+        if(abs_passable(m, r, c)) { start_r = r; start_c = c; have_start = true; break; }
+        for(int e = 0; e < 8; e++) {
+            int nr = r + er[e], nc = c + ec[e];
+            if(!abs_exists(m, nr, nc)) continue;
+            int dr = nr - base_r, dc = nc - base_c;
+            if(dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+            if(visited[dr * dim + dc]) continue;
+            visited[dr * dim + dc] = true;
+            int ndr = nr - centre_r, ndc = nc - centre_c;
+            pq_push(&frontier, (float)(ndr * ndr + ndc * ndc), nr, nc);
+        }
+    }
+    int ret = 0;
+    if(have_start) {
+        frontier.size = 0;
+        memset(visited, 0, (size_t)dim * dim);
+        visited[(start_r - base_r) * dim + (start_c - base_c)] = true;
+        pq_push(&frontier, 0.0f, start_r, start_c);
+        while(frontier.size > 0 && ret < budget) {
+            int r, c; pq_pop(&frontier, &r, &c);
+            if(abs_passable(m, r, c)) { out[2*ret] = r; out[2*ret+1] = c; ret++; }
+            for(int e = 0; e < 8; e++) {
+                int nr = r + er[e], nc = c + ec[e];
+                if(!abs_exists(m, nr, nc)) continue;
+                int dr = nr - base_r, dc = nc - base_c;
+                if(dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+                if(visited[dr * dim + dc]) continue;
+                visited[dr * dim + dc] = true;
+                if(!abs_passable(m, nr, nc)) continue;
+                int ndr = nr - centre_r, ndc = nc - centre_c;
+                pq_push(&frontier, (float)(ndr * ndr + ndc * ndc), nr, nc);
+            }
+        }
+    }
+    pq_free(&frontier); free(visited);
+    return ret;
+}
+
+/* the zone's seed tiles alone (for the device path's parity tests): out = (r, c) pairs, returns the count */
+int pfo_zone_seeds(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, int32_t *out)
+{
+    const int dim = (m->chunk_h > 1 && m->chunk_w > 1) ? 2 * RES : RES;
+    const int base_r = chunk_r > 0 ? chunk_r * RES - RES / 2 : 0, base_c = chunk_c > 0 ? chunk_c * RES - RES / 2 : 0;
+    size_t budget = (size_t)(M_PI * radius * radius + 0.5);
+    if(budget > (size_t)(dim * dim)) budget = dim * dim;
+    return zone_initial_frontier(m, centre_r, centre_c, base_r, base_c, dim, out, (int)budget);
+}
+
+/* N_FlowFieldUpdate for TARGET_ZONE (field.c:2050 -> field_update_zone, :1810), in place on `inout` (64 x 64
+ * direction bytes): the integration runs over the padded region (plain passability, no overlay) and
+ * field_build_flow_region (field.c:762) writes the chunk's window, leaving unreached tiles as they were. Only the
+ * square cases are defined: 128 x 128 on maps with more than one chunk row AND column, 64 x 64 on a 1 x 1 map
+ * (with one of the two the reference's row stride overruns its buffer). */
+void pfo_flow_field_zone(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, uint8_t *inout)
+{
+    const int dim = (m->chunk_h > 1 && m->chunk_w > 1) ? 2 * RES : RES;
+    const int base_r = chunk_r > 0 ? chunk_r * RES - RES / 2 : 0, base_c = chunk_c > 0 ? chunk_c * RES - RES / 2 : 0;
+    const int roff = chunk_r > 0 ? RES / 2 : 0, coff = chunk_c > 0 ? RES / 2 : 0;
+    int32_t *seeds = malloc(sizeof(int32_t) * 2 * dim * dim);
+    const int ns = pfo_zone_seeds(m, chunk_r, chunk_c, centre_r, centre_c, radius, seeds);
+    float *intf = malloc(sizeof(float) * dim * dim);
+    for(int i = 0; i < dim * dim; i++) intf[i] = INFINITY;
+    pq frontier; pq_init(&frontier);
+    for(int i = 0; i < ns; i++) {
+        pq_push(&frontier, 0.0f, seeds[2*i], seeds[2*i+1]);
+        intf[(seeds[2*i] - base_r) * dim + (seeds[2*i+1] - base_c)] = 0.0f;
+    }
+    while(frontier.size > 0) {
+        int ar, ac; pq_pop(&frontier, &ar, &ac);
+        const int dr = ar - base_r, dc = ac - base_c;
+        for(int e = 0; e < 4; e++) {
+            static const int er[4] = {-1, 0, 0, 1}, ec[4] = {0, -1, 1, 0};
+            const int nr = ar + er[e], nc = ac + ec[e];
+            if(!abs_exists(m, nr, nc) || !abs_passable(m, nr, nc)) continue;
+            const int ndr = nr - base_r, ndc = nc - base_c;
+            if(ndr < 0 || ndr >= dim || ndc < 0 || ndc >= dim) continue;
+            float total = intf[dr * dim + dc] + abs_cost(m, nr, nc);
+            if(total < intf[ndr * dim + ndc]) { intf[ndr * dim + ndc] = total; pq_push(&frontier, total, nr, nc); }
+        }
+    }
+    pq_free(&frontier);
+    for(int r = 0; r < RES; r++) for(int c = 0; c < RES; c++) {
+        const int ir = r + roff, ic = c + coff;
+        if(intf[ir * dim + ic] == INFINITY) continue;
+        if(intf[ir * dim + ic] == 0.0f) { inout[r * RES + c] = FD_NONE; continue; }
+        inout[r * RES + c] = (uint8_t)flow_dir_n(intf, dim, ir, ic);
+    }
+    free(intf); free(seeds);
+}
+
+/* N_DesiredGroupArrivalVelocity (nav.c:3561) against caller-held zone fields: fields[chunk] = 64 x 64 direction
+ * bytes or NULL-equivalent (has[chunk] == 0). out_vel 2 floats, out_flags bit0 = returned true, bit1 = at_slot */
+void pfo_group_arrival_velocity(const pfo_map *m, const uint8_t *fields, const uint8_t *has, const float *centre_xz, int radius,
+                                const float *pos_xz, int n, float *out_vel, uint8_t *out_flags)
+{
+    tdesc ct;
+    const bool cok = desc_for_point(m, centre_xz[0], centre_xz[1], &ct);
+    for(int i = 0; i < n; i++) {
+        out_vel[2*i] = out_vel[2*i+1] = 0.0f; out_flags[i] = 0;
+        tdesc t;
+        if(!desc_for_point(m, pos_xz[2*i], pos_xz[2*i+1], &t) || !cok) continue;
+        const int chunk = t.chunk_r * m->chunk_w + t.chunk_c;
+        if(!has[chunk]) continue;
+        const int dir = fields[(size_t)chunk * 4096 + t.tile_r * RES + t.tile_c];
+        v2 d = flow_dir_vec(dir);
+        out_vel[2*i] = d.x; out_vel[2*i+1] = d.z;
+        out_flags[i] = 1;
+        if(dir == FD_NONE) {
+            const int dr = (t.chunk_r * RES + t.tile_r) - (ct.chunk_r * RES + ct.tile_r);
+            const int dc = (t.chunk_c * RES + t.tile_c) - (ct.chunk_c * RES + ct.tile_c);
+            if(dr * dr + dc * dc <= radius * radius) out_flags[i] |= 2;
+        }
+    }
+}

@@ -43,6 +43,11 @@ def lib():
                                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pfo_group_arrival_field.argtypes = [C.POINTER(_Map), C.c_int, C.c_uint16, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_void_p]
+        L.pfo_zone_seeds.restype = C.c_int
+        L.pfo_zone_seeds.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
+        L.pfo_flow_field_zone.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
+        L.pfo_group_arrival_velocity.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_int, C.c_void_p, C.c_void_p]
         L.pfo_region_field_update_to_nearest_pathable.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -124,6 +129,24 @@ class OracleMap:
         lib().pfo_region_field_update_to_nearest_pathable(C.byref(self.m), dim, int(start[0]), int(start[1]),
                                                           int(center[0]), int(center[1]), _p(ov), no, _p(buf))
         return buf
+
+    def zone_seeds(self, chunk, centre, radius):
+        out = np.zeros((4 * 4096, 2), np.int32)
+        n = lib().pfo_zone_seeds(C.byref(self.m), chunk[0], chunk[1], int(centre[0]), int(centre[1]), int(radius), _p(out))
+        return out[:n].copy()
+
+    def flow_field_zone(self, chunk, centre, radius, inout=None):
+        """N_FlowFieldInit + N_FlowFieldUpdate(TARGET_ZONE); centre = absolute (r, c)"""
+        buf = np.zeros((64, 64), np.uint8) if inout is None else np.ascontiguousarray(inout, np.uint8).reshape(64, 64).copy()
+        lib().pfo_flow_field_zone(C.byref(self.m), chunk[0], chunk[1], int(centre[0]), int(centre[1]), int(radius), _p(buf))
+        return buf
+
+    def group_arrival_velocity(self, fields, has, centre_xz, radius, pos_xz):
+        fields = np.ascontiguousarray(fields, np.uint8); has = np.ascontiguousarray(has, np.uint8)
+        pos = np.ascontiguousarray(pos_xz, np.float32).reshape(-1, 2); c = np.ascontiguousarray(centre_xz, np.float32)
+        vel = np.zeros((len(pos), 2), np.float32); fl = np.zeros(len(pos), np.uint8)
+        lib().pfo_group_arrival_velocity(C.byref(self.m), _p(fields), _p(has), _p(c), int(radius), _p(pos), len(pos), _p(vel), _p(fl))
+        return vel, fl
 
     def los_fields_create(self, reqs):
         reqs = np.ascontiguousarray(reqs)

@@ -36,6 +36,9 @@ def lib():
                                                C.c_int, C.c_void_p, C.c_void_p]
         L.pfref_group_arrival_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                 C.c_void_p, C.c_int, C.c_void_p]
+        L.pfref_flow_field_zone.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
+        L.pfref_group_arrival_velocity.restype = C.c_int
+        L.pfref_group_arrival_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_set_war.argtypes = [C.c_int, C.c_int, C.c_int]
         L.pfref_los_field_faction.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -169,6 +172,20 @@ class RefMap:
         out = np.zeros((dim, dim // 2), np.uint8)
         lib().pfref_group_arrival_field(self.h, dim, layer, int(enemies), _p(t), len(t), _p(c), _p(ov), len(ov), _p(out))
         return out
+
+    def flow_field_zone(self, chunk, centre, radius, layer=0):
+        """N_FlowFieldUpdate(TARGET_ZONE) for one chunk; centre = absolute (r, c)"""
+        out = np.zeros((64, 64), np.uint8)
+        lib().pfref_flow_field_zone(self.h, layer, chunk[0], chunk[1], int(centre[0]), int(centre[1]), int(radius), _p(out))
+        return out
+
+    def group_arrival_velocity(self, centre_xz, radius, pos_xz, layer=0):
+        """request + await the zone fields in reach, then N_DesiredGroupArrivalVelocity per position
+        -> (vel[n, 2], flags[n]: bit0 ok, bit1 at_slot, chunk fields built)"""
+        pos = np.ascontiguousarray(pos_xz, np.float32).reshape(-1, 2); c = np.ascontiguousarray(centre_xz, np.float32)
+        vel = np.zeros((len(pos), 2), np.float32); fl = np.zeros(len(pos), np.uint8)
+        nb = lib().pfref_group_arrival_velocity(self.h, layer, _p(c), int(radius), len(pos), _p(pos), _p(vel), _p(fl))
+        return vel, fl, nb
 
     def set_war(self, a, b, at_war=True):
         lib().pfref_set_war(a, b, int(at_war))

@@ -518,6 +518,63 @@ PFREF_EXPORT void pfref_group_arrival_field(void *m, int dim, int layer, int ene
     free(ov); free(work);
 }
 
+/* N_FlowFieldInit + N_FlowFieldUpdate with a TARGET_ZONE target (field.c:2050 -> field_update_zone, :1810);
+ * centre in absolute tile coordinates */
+PFREF_EXPORT void pfref_flow_field_zone(void *m, int layer, int chunk_r, int chunk_c, int centre_r, int centre_c,
+                                        int radius, uint8_t *out)
+{
+    struct nav_private *priv = pfref_priv(m);
+    struct flow_field ff;
+    N_FlowFieldInit((struct coord){chunk_r, chunk_c}, &ff);
+    struct field_target target = (struct field_target){ .type = TARGET_ZONE,
+        .zone = (struct zone_desc){ pfref_td(centre_r, centre_c), (uint16_t)radius } };
+    N_FlowFieldUpdate((struct coord){chunk_r, chunk_c}, priv, 0, layer, target, priv->unit_query_ctx, &ff);
+    pfref_flow_pack(&ff, out);
+}
+
+#ifndef CLAMP
+#define CLAMP(a, min, max) (MIN(MAX((a), (min)), (max)))
+#endif
+/* N_RequestAsyncGroupArrivalField (nav.c:3921) + N_AwaitAsyncFields inline: the zone fields of every chunk in
+ * reach are put into the reference's field cache; then N_DesiredGroupArrivalVelocity (nav.c:3561) per position.
+ * out_flags bit0 = returned true, bit1 = at_slot. Returns the number of chunk fields built. */
+PFREF_EXPORT int pfref_group_arrival_velocity(void *m, int layer, const float *centre_xz, int radius, int n,
+                                              const float *pos_xz, float *out_vel, uint8_t *out_flags)
+{
+    struct map *map = m;
+    struct nav_private *priv = pfref_priv(m);
+    struct map_resolution res;
+    N_GetResolution(priv, &res);
+    vec2_t centre = (vec2_t){centre_xz[0], centre_xz[1]};
+    struct tile_desc ct;
+    int built = 0;
+    if(M_Tile_DescForPoint2D(res, map->pos, centre, &ct)) {
+        struct field_target target = (struct field_target){ .type = TARGET_ZONE, .zone = (struct zone_desc){ ct, (uint16_t)radius } };
+        int reach = 2 * radius;                                   /* nav.c:3945-3951 */
+        int gr = ct.chunk_r * (int)res.tile_h + ct.tile_r, gc = ct.chunk_c * (int)res.tile_w + ct.tile_c;
+        int min_cr = CLAMP((gr - reach) / (int)res.tile_h, 0, (int)res.chunk_h - 1);
+        int max_cr = CLAMP((gr + reach) / (int)res.tile_h, 0, (int)res.chunk_h - 1);
+        int min_cc = CLAMP((gc - reach) / (int)res.tile_w, 0, (int)res.chunk_w - 1);
+        int max_cc = CLAMP((gc + reach) / (int)res.tile_w, 0, (int)res.chunk_w - 1);
+        for(int cr = min_cr; cr <= max_cr; cr++) {
+        for(int cc = min_cc; cc <= max_cc; cc++) {
+            struct flow_field ff;
+            N_FlowFieldInit((struct coord){cr, cc}, &ff);
+            N_FlowFieldUpdate((struct coord){cr, cc}, priv, 0, layer, target, priv->unit_query_ctx, &ff);
+            N_FC_PutFlowField(priv->fieldcache, N_FlowFieldID((struct coord){cr, cc}, target, layer), &ff);
+            built++;
+        }}
+    }
+    for(int i = 0; i < n; i++) {
+        vec2_t vel; bool at_slot = false;
+        bool ok = N_DesiredGroupArrivalVelocity((vec2_t){pos_xz[2*i], pos_xz[2*i+1]}, priv, layer, map->pos, centre,
+            (uint16_t)radius, &vel, &at_slot);
+        out_vel[2*i] = vel.x; out_vel[2*i+1] = vel.z;
+        out_flags[i] = (uint8_t)((ok ? 1 : 0) | (at_slot ? 2 : 0));
+    }
+    return built;
+}
+
 /* N_LOSFieldCreate; field.c:2085. prev may be NULL (destination chunk). */
 PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
                                   int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,

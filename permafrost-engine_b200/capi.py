@@ -77,6 +77,7 @@ SYMBOLS = [
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
     "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
+    "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
 ]
 
 _lib = None
@@ -119,6 +120,10 @@ def load():
                                       C.c_size_t, C.c_void_p]
     L.pfnav_region_fields_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+    L.pfnav_zone_seeds.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.pfnav_zone_fields.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pfnav_pool_request_zone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.pfnav_group_arrival_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.pfnav_group_arrival_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_agents_upload_movestate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -325,6 +330,29 @@ class Nav:
         _chk(self.L.pfnav_group_arrival_field(self.h, layer, dim, int(enemies), _p(t) if len(t) else None, len(t), _p(c),
                                               _p(ov) if len(ov) else None, len(ov), _p(out)))
         return out
+
+    def zone_seeds(self, chunk, centre, radius, layer=0):
+        out = np.zeros((4 * 4096, 2), np.int32); n = C.c_size_t(0)
+        _chk(self.L.pfnav_zone_seeds(self.h, layer, chunk[0], chunk[1], int(centre[0]), int(centre[1]), int(radius), _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def zone_fields(self, centre, radius, chunks, layer=0):
+        """N_FlowFieldInit + N_FlowFieldUpdate(TARGET_ZONE) for the listed chunks -> u8[n, 64, 64]"""
+        ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
+        out = np.zeros((len(ch), 64, 64), np.uint8)
+        _chk(self.L.pfnav_zone_fields(self.h, layer, int(centre[0]), int(centre[1]), int(radius), _p(ch), len(ch), _p(out)))
+        return out
+
+    def pool_request_zone(self, dest, centre_xz, radius, layer=0, stream=0):
+        c = np.ascontiguousarray(centre_xz, np.float32); n = C.c_int(0)
+        _chk(self.L.pfnav_pool_request_zone(self.h, dest, layer, _p(c), int(radius), C.c_void_p(stream), C.byref(n)))
+        return n.value
+
+    def group_arrival_velocity(self, dest, centre_xz, radius, pos_xz):
+        c = np.ascontiguousarray(centre_xz, np.float32); pos = np.ascontiguousarray(pos_xz, np.float32).reshape(-1, 2)
+        vel = np.zeros((len(pos), 2), np.float32); fl = np.zeros(len(pos), np.uint8)
+        _chk(self.L.pfnav_group_arrival_velocity(self.h, dest, _p(c), int(radius), _p(pos), len(pos), _p(vel), _p(fl)))
+        return vel, fl
 
     def pool_repair(self):
         a, b = C.c_int(0), C.c_int(0)

@@ -130,7 +130,8 @@ __device__ __forceinline__ uint32_t region_flow_dir(const uint32_t *f, int n, in
 
 __global__ void __launch_bounds__(RG_THREADS, 4) k_region_fields(RegionGrids g, int dim, const pfnav_region_req *__restrict__ reqs,
                                                               int n, const int32_t *__restrict__ seeds,
-                                                              const int32_t *__restrict__ overlay, uint8_t *__restrict__ fields)
+                                                              const int32_t *__restrict__ overlay, uint8_t *__restrict__ fields,
+                                                              int chunk_out)
 {
     extern __shared__ uint32_t rg_smem[];
     RegionSmem s;
@@ -140,9 +141,37 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_region_fields(RegionGrids g, 
 
     for (int q = blockIdx.x; q < n; q += gridDim.x) {
         const pfnav_region_req rq = reqs[q];
-        uint8_t *out = fields + (size_t)q * (N / 2);
+        uint8_t *out = fields + (size_t)q * (chunk_out ? 4096 : N / 2);
         const int32_t *ov = overlay + 2 * (size_t)rq.overlay_off;
         __syncthreads();
+
+        if (chunk_out) {
+            // TARGET_ZONE chunk field (field_update_zone, field.c:1810): the chunk (center_r, center_c) padded by
+            // half a chunk; field_build_flow_region (field.c:762) writes the chunk's 64 x 64 window of an
+            // initialised (all FD_NONE) field, one direction per byte
+            const int roff = (rq.center_r > 0 && dim > 64) ? 32 : 0, coff = (rq.center_c > 0 && dim > 64) ? 32 : 0;
+            const int base_r = rq.center_r * 64 - roff, base_c = rq.center_c * 64 - coff;
+            const int32_t *sd = seeds + 2 * (size_t)rq.seed_off;
+            region_gather(g, s, rq.layer, base_r, base_c, 0, ov, 0);
+            for (int i = tid; i < N; i += RG_THREADS) {
+                const uint8_t f = s.flg[i];
+                s.dist[i] = RG_INF;
+                if ((f & (RG_EXISTS | RG_PASSP)) == (RG_EXISTS | RG_PASSP)) s.flg[i] = f | RG_ENT;
+            }
+            __syncthreads();
+            for (int k = tid; k < rq.seed_n; k += RG_THREADS) {
+                const int dr = sd[2 * k] - base_r, dc = sd[2 * k + 1] - base_c;
+                if (dr >= 0 && dr < dim && dc >= 0 && dc < dim) s.dist[dr * dim + dc] = 0;
+            }
+            __syncthreads();
+            region_relax(s);
+            for (int t = tid; t < 4096; t += RG_THREADS) {
+                const int r = (t >> 6) + roff, c = (t & 63) + coff;
+                const uint32_t d = s.dist[r * dim + c];
+                out[t] = (d != RG_INF && d != 0) ? (uint8_t)region_flow_dir(s.dist, dim, r, c) : (uint8_t)0;
+            }
+            continue;
+        }
 
         if (rq.flags & PFNAV_REGION_CREATE) {
             int base_r = rq.center_r - half, base_c = rq.center_c - half;
@@ -290,7 +319,7 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_region_fields(RegionGrids g, 
 }   // namespace
 
 static int region_launch(pfnav_ctx *ctx, int dim, const pfnav_region_req *d_reqs, size_t n, const int32_t *d_seeds,
-                         const int32_t *d_overlay, uint8_t *d_fields, cudaStream_t st)
+                         const int32_t *d_overlay, uint8_t *d_fields, cudaStream_t st, int chunk_out = 0)
 {
     RegionGrids g;
     g.cost = ctx->d_cost; g.blk = ctx->d_blk; g.fmask = ctx->d_fmask; g.W64 = ctx->W64; g.H64 = ctx->H64;
@@ -299,7 +328,7 @@ static int region_launch(pfnav_ctx *ctx, int dim, const pfnav_region_req *d_reqs
                                  PFNAV_REGION_DIM_MAX * PFNAV_REGION_DIM_MAX * 6));
     const int per_sm = std::max(1, std::min(4, (int)((size_t)(227 * 1024) / (smem + 1024))));
     const int grid = (int)std::min<size_t>(n, (size_t)ctx->sm_count * per_sm);
-    k_region_fields<<<grid, RG_THREADS, smem, st>>>(g, dim, d_reqs, (int)n, d_seeds, d_overlay, d_fields);
+    k_region_fields<<<grid, RG_THREADS, smem, st>>>(g, dim, d_reqs, (int)n, d_seeds, d_overlay, d_fields, chunk_out);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFNAV_OK;
@@ -436,4 +465,359 @@ extern "C" int pfnav_group_arrival_field(pfnav_ctx *ctx, int layer, int dim, uin
     q.overlay_off = 0; q.overlay_n = (int32_t)noverlay;
     q.enemies = enemies; q.flags = PFNAV_REGION_CREATE;
     return pfnav_region_fields(ctx, dim, &q, 1, seeds.data(), seeds.size() / 2, overlay_rc, noverlay, out_field);
+}
+
+// ------------------------------------------------------------------------------------------
+// TARGET_ZONE chunk fields: the group arrival fields (N_RequestAsyncGroupArrivalField nav.c:3921 ->
+// N_FlowFieldUpdate field.c:2050 -> field_update_zone :1810) and their per-entity consumer
+// N_DesiredGroupArrivalVelocity (nav.c:3561).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// lib/public/pqueue.h:109-208 (1-indexed binary min-heap, hole-based sift; ties keep the reference's order)
+struct zone_heap {
+    struct node { float prio; int r, c; };
+    std::vector<node> a{1};
+    size_t size() const { return a.size() - 1; }
+    void clear() { a.resize(1); }
+    void push(float prio, int r, int c)
+    {
+        a.push_back({});
+        size_t curr = a.size() - 1, parent = curr / 2;
+        while (curr > 1 && a[parent].prio > prio) { a[curr] = a[parent]; curr = parent; parent /= 2; }
+        a[curr] = {prio, r, c};
+    }
+    void pop(int *r, int *c)
+    {
+        *r = a[1].r; *c = a[1].c;
+        const size_t n = a.size() - 2;      // size after the pop; a[n + 1], the last element, is the one being sifted
+        a[1] = a[n + 1];
+        size_t root = 1;
+        while (root != n + 1) {             // _pq_balance: `target` starts at the sifted element's own slot
+            size_t target = n + 1;
+            const size_t l = root * 2, rr = l + 1;
+            if (l <= n && a[l].prio < a[target].prio) target = l;
+            if (rr <= n && a[rr].prio < a[target].prio) target = rr;
+            a[root] = a[target];
+            root = target;
+        }
+        a.pop_back();
+    }
+};
+
+struct zone_map {
+    const uint8_t *cost; const uint16_t *blk; int chunk_w, chunk_h;
+    bool exists(int r, int c) const { return r >= 0 && r < chunk_h * 64 && c >= 0 && c < chunk_w * 64; }
+    bool passable(int r, int c) const       // field_tile_passable (field.c:117)
+    {
+        const size_t off = ((size_t)(r / 64) * chunk_w + c / 64) * 4096 + (r % 64) * 64 + (c % 64);
+        return cost[off] != 0xFF && blk[off] == 0;
+    }
+};
+
+// field_zone_initial_frontier (field.c:1683)
+void zone_initial_frontier(const zone_map &m, int centre_r, int centre_c, int base_r, int base_c, int dim, size_t budget,
+                           std::vector<int32_t> &out)
+{
+    static const int er[8] = {0, 0, -1, 1, -1, -1, 1, 1}, ec[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+    const int cdr = centre_r - base_r, cdc = centre_c - base_c;
+    if (cdr < 0 || cdr >= dim || cdc < 0 || cdc >= dim) return;
+    std::vector<uint8_t> visited((size_t)dim * dim, 0);
+    zone_heap frontier;
+    visited[cdr * dim + cdc] = 1;
+    frontier.push(0.0f, centre_r, centre_c);
+    int start_r = 0, start_c = 0; bool have_start = false;
+    while (frontier.size() > 0) {
+        int r, c; frontier.pop(&r, &c);
+        if (m.passable(r, c)) { start_r = r; start_c = c; have_start = true; break; }
+        for (int e = 0; e < 8; e++) {
+            const int nr = r + er[e], nc = c + ec[e];
+            if (!m.exists(nr, nc)) continue;
+            const int dr = nr - base_r, dc = nc - base_c;
+            if (dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+            if (visited[dr * dim + dc]) continue;
+            visited[dr * dim + dc] = 1;
+            const int ndr = nr - centre_r, ndc = nc - centre_c;
+            frontier.push((float)(ndr * ndr + ndc * ndc), nr, nc);
+        }
+    }
+    if (!have_start) return;
+    frontier.clear();
+    std::fill(visited.begin(), visited.end(), 0);
+    visited[(start_r - base_r) * dim + (start_c - base_c)] = 1;
+    frontier.push(0.0f, start_r, start_c);
+    size_t ret = 0;
+    while (frontier.size() > 0 && ret < budget) {
+        int r, c; frontier.pop(&r, &c);
+        if (m.passable(r, c)) { out.push_back(r); out.push_back(c); ret++; }
+        for (int e = 0; e < 8; e++) {
+            const int nr = r + er[e], nc = c + ec[e];
+            if (!m.exists(nr, nc)) continue;
+            const int dr = nr - base_r, dc = nc - base_c;
+            if (dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+            if (visited[dr * dim + dc]) continue;
+            visited[dr * dim + dc] = 1;
+            if (!m.passable(nr, nc)) continue;
+            const int ndr = nr - centre_r, ndc = nc - centre_c;
+            frontier.push((float)(ndr * ndr + ndc * ndc), nr, nc);
+        }
+    }
+}
+
+struct ZoneView {
+    const int32_t *slot; const uint8_t *flow; const uint8_t *has;     // the field pool (pfnav_pool_*)
+    int chunk_w, chunk_h; float map_x, map_z;
+};
+
+// M_Tile_DescForPoint2D (tile.c:547) -> absolute (r, c); divisions by powers of two are exact in float
+__device__ __forceinline__ bool zone_tile_for_point(const ZoneView &z, float px, float pz, int &ar, int &ac)
+{
+    const float width = (float)(z.chunk_w * 256), height = (float)(z.chunk_h * 256);
+    if (px > z.map_x || px < z.map_x - width) return false;
+    if (pz < z.map_z || pz > z.map_z + height) return false;
+    int chunk_r = (int)(fabsf(z.map_z - pz) / 256.0f), chunk_c = (int)(fabsf(z.map_x - px) / 256.0f);
+    chunk_r = min(max(chunk_r, 0), z.chunk_h - 1);
+    chunk_c = min(max(chunk_c, 0), z.chunk_w - 1);
+    const float bx = z.map_x - (float)chunk_c * 256.0f, bz = z.map_z + (float)chunk_r * 256.0f;
+    const int tile_r = (int)(fabsf(bz - pz) / 4.0f), tile_c = (int)(fabsf(bx - px) / 4.0f);
+    ar = chunk_r * 64 + min(max(tile_r, 0), 63);
+    ac = chunk_c * 64 + min(max(tile_c, 0), 63);
+    return true;
+}
+
+// N_DesiredGroupArrivalVelocity (nav.c:3561): one thread per position
+__global__ void k_group_arrival_velocity(ZoneView z, int dest, float cx, float cz, int radius, const float2 *__restrict__ pos, int n,
+                                         float2 *__restrict__ out_vel, uint8_t *__restrict__ out_flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 v = make_float2(0.0f, 0.0f);
+    uint8_t fl = 0;
+    int ar, ac, cr, cc;
+    const float2 p = pos[i];
+    if (zone_tile_for_point(z, p.x, p.y, ar, ac) && zone_tile_for_point(z, cx, cz, cr, cc)) {
+        const int chunk = (ar >> 6) * z.chunk_w + (ac >> 6);
+        const int slot = z.slot[(size_t)dest * z.chunk_w * z.chunk_h + chunk];
+        if (slot >= 0 && (z.has[slot] & 1)) {
+            const uint32_t dir = z.flow[(size_t)slot * 4096 + (ar & 63) * 64 + (ac & 63)];
+            // N_FlowDir (field.c:2429): x grows to the left
+            const float d = (float)(1.0 / 1.4142135623730951);      // 1.0f / sqrt(2.0f): a double division rounded to float
+            switch (dir) {
+            case 1: v = make_float2(d, -d); break;
+            case 2: v = make_float2(0.0f, -1.0f); break;
+            case 3: v = make_float2(-d, -d); break;
+            case 4: v = make_float2(1.0f, 0.0f); break;
+            case 5: v = make_float2(-1.0f, 0.0f); break;
+            case 6: v = make_float2(d, d); break;
+            case 7: v = make_float2(0.0f, 1.0f); break;
+            case 8: v = make_float2(-d, d); break;
+            default: break;
+            }
+            fl = 1;
+            if (dir == 0) {
+                const int dr = ar - cr, dc = ac - cc;
+                if (dr * dr + dc * dc <= radius * radius) fl |= 2;
+            }
+        }
+    }
+    out_vel[i] = v; out_flags[i] = fl;
+}
+
+}   // namespace
+
+static int zone_dim(const pfnav_ctx *ctx, int *out_dim)
+{
+    // field_update_zone sizes its square buffer with rdim as the row stride (field.c:1821-1828): only the
+    // cases where rows == columns are defined
+    if (ctx->chunk_h > 1 && ctx->chunk_w > 1) { *out_dim = 128; return PFNAV_OK; }
+    if (ctx->chunk_h == 1 && ctx->chunk_w == 1) { *out_dim = 64; return PFNAV_OK; }
+    pfnav_set_error("zone fields need a map with more than one chunk row AND column (or a 1 x 1 map): the reference's padded "
+                    "region is indexed with one stride for both");
+    return PFNAV_ERR_ARG;
+}
+
+// seeds of every requested chunk + the device launch; d_out = n x 4096 direction bytes
+static int zone_fields_launch(pfnav_ctx *ctx, int layer, int centre_r, int centre_c, int radius, const int32_t *chunks_rc, size_t n,
+                              uint8_t *d_out, cudaStream_t st)
+{
+    int dim = 0;
+    int rc = zone_dim(ctx, &dim);
+    if (rc) return rc;
+    const size_t ltiles = (size_t)ctx->chunk_w * ctx->chunk_h * 4096;
+    zone_map zm = { ctx->h_cost.data() + ltiles * layer, ctx->h_blk.data() + ltiles * layer, ctx->chunk_w, ctx->chunk_h };
+    size_t budget = (size_t)(M_PI * radius * radius + 0.5);             // field.c:1843
+    if (budget > (size_t)dim * dim) budget = (size_t)dim * dim;
+    std::vector<pfnav_region_req> reqs(n);
+    std::vector<int32_t> seeds;
+    for (size_t i = 0; i < n; i++) {
+        const int cr = chunks_rc[2 * i], cc = chunks_rc[2 * i + 1];
+        PF_ARG(cr >= 0 && cr < ctx->chunk_h && cc >= 0 && cc < ctx->chunk_w, "zone field: chunk");
+        const int base_r = (cr > 0 && dim > 64) ? cr * 64 - 32 : cr * 64, base_c = (cc > 0 && dim > 64) ? cc * 64 - 32 : cc * 64;
+        pfnav_region_req q = {};
+        q.layer = layer; q.center_r = cr; q.center_c = cc;
+        q.seed_off = (int32_t)(seeds.size() / 2);
+        zone_initial_frontier(zm, centre_r, centre_c, base_r, base_c, dim, budget, seeds);
+        q.seed_n = (int32_t)(seeds.size() / 2) - q.seed_off;
+        q.flags = PFNAV_REGION_CREATE;
+        reqs[i] = q;
+    }
+    const size_t b_req = n * sizeof(pfnav_region_req), b_seed = std::max<size_t>(seeds.size(), 2) * 4;
+    uint8_t *d_buf = nullptr;
+    PF_CUDA(cudaMalloc(&d_buf, b_req + b_seed + 8));
+    cudaError_t e = cudaMemcpyAsync(d_buf, reqs.data(), b_req, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !seeds.empty()) e = cudaMemcpyAsync(d_buf + b_req, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        rc = region_launch(ctx, dim, reinterpret_cast<const pfnav_region_req *>(d_buf), n, reinterpret_cast<const int32_t *>(d_buf + b_req),
+                           reinterpret_cast<const int32_t *>(d_buf + b_req + b_seed), d_out, st, 1);
+    // the staging buffer is read by the kernel: free it once the stream has passed it (pageable copies above are
+    // already staged by the driver when cudaMemcpyAsync returns)
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("zone fields: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_zone_fields(pfnav_ctx *ctx, int layer, int centre_r, int centre_c, int radius, const int32_t *chunks_rc,
+                                 size_t n, uint8_t *out_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(chunks_rc && out_fields, "null buffer");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(centre_r >= 0 && centre_r < ctx->H64 && centre_c >= 0 && centre_c < ctx->W64, "zone centre outside the map");
+    PF_ARG(radius >= 0 && radius <= 0xFFFF, "radius");
+    PF_ARG(n < (1u << 24), "n");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *d_out = nullptr;
+    PF_CUDA(cudaMalloc(&d_out, n * 4096));
+    int rc = zone_fields_launch(ctx, layer, centre_r, centre_c, radius, chunks_rc, n, d_out, ctx->tick_stream);
+    if (rc == 0 && cudaMemcpy(out_fields, d_out, n * 4096, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        pfnav_set_error("pfnav_zone_fields: copy back failed"); rc = PFNAV_ERR_CUDA;
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int pfnav_pool_request_zone(pfnav_ctx *ctx, int dest, int layer, const float *centre_xz, int radius, void *stream,
+                                       int *out_nfields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(ctx->d_pool_slot, "pool not created");
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(centre_xz, "centre");
+    PF_ARG(radius >= 0 && radius <= 0xFFFF, "radius");
+    if (out_nfields) *out_nfields = 0;
+    int32_t c[2];
+    if (!region_tile_for_point(ctx, centre_xz[0], centre_xz[1], c)) return PFNAV_OK;       // nav.c:3931
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
+    cudaStream_t st = pf_stream(ctx, stream);
+    // the chunks the footprint can reach (nav.c:3945-3951; C division truncates toward zero)
+    const int reach = 2 * radius;
+    auto clampi = [](int v, int lo, int hi) { return std::min(std::max(v, lo), hi); };
+    const int min_cr = clampi((c[0] - reach) / 64, 0, ctx->chunk_h - 1), max_cr = clampi((c[0] + reach) / 64, 0, ctx->chunk_h - 1);
+    const int min_cc = clampi((c[1] - reach) / 64, 0, ctx->chunk_w - 1), max_cc = clampi((c[1] + reach) / 64, 0, ctx->chunk_w - 1);
+    std::vector<int32_t> chunks;
+    for (int cr = min_cr; cr <= max_cr; cr++)
+        for (int cc = min_cc; cc <= max_cc; cc++) { chunks.push_back(cr); chunks.push_back(cc); }
+    const size_t n = chunks.size() / 2;
+    const int nchunks = ctx->chunk_w * ctx->chunk_h;
+    // pool slots first, so that a full pool fails before any work is queued
+    std::vector<int32_t> slots(n);
+    for (size_t i = 0; i < n; i++) {
+        const size_t si = (size_t)dest * nchunks + chunks[2 * i] * ctx->chunk_w + chunks[2 * i + 1];
+        int slot = ctx->h_pool_slot[si];
+        if (slot < 0) {
+            if (ctx->pool_used >= ctx->pool_max) { pfnav_set_error("pfnav_pool_request_zone: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
+            slot = ctx->pool_used++;
+            ctx->h_pool_slot[si] = slot;
+            PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + si, &ctx->h_pool_slot[si], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        }
+        slots[i] = slot;
+    }
+    uint8_t *d_tmp = nullptr;
+    PF_CUDA(cudaMalloc(&d_tmp, n * 4096));
+    int rc = zone_fields_launch(ctx, layer, c[0], c[1], radius, chunks.data(), n, d_tmp, st);
+    uint8_t *d_has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096;
+    for (size_t i = 0; i < n && rc == 0; i++) {
+        ctx->h_pool_has[slots[i]] |= 1;
+        if (cudaMemcpyAsync(ctx->d_pool_flow + (size_t)slots[i] * 4096, d_tmp + i * 4096, 4096, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_has + slots[i], &ctx->h_pool_has[slots[i]], 1, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            pfnav_set_error("pfnav_pool_request_zone: pool copy failed"); rc = PFNAV_ERR_CUDA;
+        }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(d_tmp);
+    ctx->goal_batch.valid = false;
+    if (rc == 0 && out_nfields) *out_nfields = (int)n;
+    return rc;
+}
+
+extern "C" int pfnav_group_arrival_velocity(pfnav_ctx *ctx, int dest, const float *centre_xz, int radius, const float *pos_xz,
+                                            size_t n, float *out_vel, uint8_t *out_flags)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(ctx->d_pool_slot, "pool not created");
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(centre_xz && pos_xz && out_vel && out_flags, "null buffer");
+    PF_ARG(n < (1u << 30), "n");
+    PF_ARG(radius >= 0 && radius <= 0xFFFF, "radius");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
+    uint8_t *d_buf = nullptr;
+    PF_CUDA(cudaMalloc(&d_buf, n * 17));
+    float2 *d_pos = reinterpret_cast<float2 *>(d_buf), *d_vel = d_pos + n;
+    uint8_t *d_fl = d_buf + n * 16;
+    cudaStream_t st = ctx->tick_stream;
+    ZoneView z = { ctx->d_pool_slot, ctx->d_pool_flow, ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->chunk_w, ctx->chunk_h,
+                   ctx->map_x, ctx->map_z };
+    cudaError_t e = cudaMemcpyAsync(d_pos, pos_xz, n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_group_arrival_velocity<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, dest, centre_xz[0], centre_xz[1], radius, d_pos, (int)n, d_vel, d_fl);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_vel, d_vel, n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_flags, d_fl, n, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("pfnav_group_arrival_velocity: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+// The zone's seed tiles alone (host structure code, no device needed): the first `budget` open tiles of the
+// best-first flood. out_rc = (r, c) pairs, at most cap of them; *out_n = the full count.
+extern "C" int pfnav_zone_seeds(pfnav_ctx *ctx, int layer, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius,
+                                int32_t *out_rc, size_t cap, size_t *out_n)
+{
+    PF_ARG(ctx && !ctx->h_cost.empty(), "map not created");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk");
+    PF_ARG(centre_r >= 0 && centre_r < ctx->H64 && centre_c >= 0 && centre_c < ctx->W64, "zone centre outside the map");
+    PF_ARG(radius >= 0 && radius <= 0xFFFF && out_n, "radius / out_n");
+    int dim = 0;
+    int rc = zone_dim(ctx, &dim);
+    if (rc) return rc;
+    const size_t ltiles = (size_t)ctx->chunk_w * ctx->chunk_h * 4096;
+    zone_map zm = { ctx->h_cost.data() + ltiles * layer, ctx->h_blk.data() + ltiles * layer, ctx->chunk_w, ctx->chunk_h };
+    size_t budget = (size_t)(M_PI * radius * radius + 0.5);
+    if (budget > (size_t)dim * dim) budget = (size_t)dim * dim;
+    const int base_r = (chunk_r > 0 && dim > 64) ? chunk_r * 64 - 32 : chunk_r * 64, base_c = (chunk_c > 0 && dim > 64) ? chunk_c * 64 - 32 : chunk_c * 64;
+    std::vector<int32_t> seeds;
+    zone_initial_frontier(zm, centre_r, centre_c, base_r, base_c, dim, budget, seeds);
+    *out_n = seeds.size() / 2;
+    if (out_rc) memcpy(out_rc, seeds.data(), std::min(cap * 2, seeds.size()) * sizeof(int32_t));
+    return PFNAV_OK;
 }

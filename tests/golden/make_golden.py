@@ -342,6 +342,25 @@ def gen_region():
             sum(int(not x.any()) for x in gx)))
         if dim == 96:
             out.update(pathable=p, cost=cost, blk=blk, factions=fac, blockers=np.array(blockers, np.float32))
+            # TARGET_ZONE chunk fields (field_update_zone, field.c:1810) for every chunk of the map, and the consumer
+            # N_DesiredGroupArrivalVelocity (nav.c:3561) after N_RequestAsyncGroupArrivalField's chunk selection
+            zr = np.random.default_rng(5)
+            zc = np.stack([zr.integers(0, ch * 64, 12), zr.integers(0, cw * 64, 12)], 1).astype(np.int32)
+            zrad = np.array([0, 1, 2, 3, 5, 8, 12, 17, 23, 30, 45, 70], np.int32)
+            zexp = np.stack([np.stack([ref.flow_field_zone((c // cw, c % cw), zc[k], int(zrad[k])) for c in range(cw * ch)])
+                             for k in range(len(zc))])
+            gv = []
+            for k in range(6):
+                cxz = np.array([-zr.uniform(-3, cw * 256 + 3), zr.uniform(-3, ch * 256 + 3)], np.float32)
+                rad = int(zr.integers(2, 30))
+                pos = np.stack([cxz[0] + zr.uniform(-260, 260, 400), cxz[1] + zr.uniform(-260, 260, 400)], 1).astype(np.float32)
+                v, f, nb = ref.group_arrival_velocity(cxz, rad, pos)
+                gv.append((cxz, rad, pos, v, f, nb))
+                print("zone consumer %d: %d chunk fields, %d ok, %d at slot" % (k, nb, int((f & 1).sum()), int((f >> 1).sum())))
+            print("zone fields: non-empty %d of %d" % (int(zexp.reshape(-1, 4096).any(axis=1).sum()), zexp.shape[0] * zexp.shape[1]))
+            out.update(zc=zc, zrad=zrad, zexp=zexp, gv_centre=np.stack([g[0] for g in gv]), gv_radius=np.array([g[1] for g in gv], np.int32),
+                       gv_pos=np.stack([g[2] for g in gv]), gv_vel=np.stack([g[3] for g in gv]), gv_flags=np.stack([g[4] for g in gv]),
+                       gv_nfields=np.array([g[5] for g in gv], np.int32))
         out.update({"req%d" % dim: rec, "ov%d" % dim: ov, "exp%d" % dim: exp, "create%d" % dim: create_only,
                     "gt%d" % dim: np.stack(gt), "gc%d" % dim: np.stack(gc), "ge%d" % dim: np.array(ge, np.int32), "gx%d" % dim: np.stack(gx)})
         ref.close()

@@ -737,3 +737,26 @@ def test_region_fields_argument_errors(nav):
     with pytest.raises(Exception):
         nav.region_fields(96, [dict(ok, seeds=[(100, 100), (101, 101)], cell=True)])
     assert nav.region_fields(96, []).shape == (0, 96, 48)
+
+
+def test_zone_fields_and_group_arrival_golden(nav):
+    """TARGET_ZONE chunk fields (seeds on the host in the reference's heap order, integration on the device) and
+    N_DesiredGroupArrivalVelocity out of the pool, vs the compiled reference"""
+    g = gold("region")
+    cw = ch = 3
+    _region_map(nav, g)
+    allchunks = [(c // cw, c % cw) for c in range(cw * ch)]
+    for k in range(len(g["zc"])):
+        got = nav.zone_fields(g["zc"][k], int(g["zrad"][k]), allchunks)
+        bad = [c for c in range(cw * ch) if (got[c] != g["zexp"][k, c]).any()]
+        assert not bad, (k, bad)
+    nav.pool_create(8, 64)
+    for k in range(len(g["gv_radius"])):
+        n = nav.pool_request_zone(k, g["gv_centre"][k], int(g["gv_radius"][k]))
+        assert n == int(g["gv_nfields"][k]), k
+        v, f = nav.group_arrival_velocity(k, g["gv_centre"][k], int(g["gv_radius"][k]), g["gv_pos"][k])
+        assert (f == g["gv_flags"][k]).all(), k
+        assert (v == g["gv_vel"][k]).all(), k
+    # a destination without zone fields: every call "returns false"
+    v, f = nav.group_arrival_velocity(7, g["gv_centre"][1], int(g["gv_radius"][1]), g["gv_pos"][1])
+    assert not f.any() and not v.any()

@@ -192,6 +192,57 @@ def test_port_region_fields_vs_ref(pfref, pforacle):
     ref.close()
 
 
+def _zone_chunks(centre_xz, radius, cw, ch):
+    """N_RequestAsyncGroupArrivalField's chunk selection (nav.c:3945-3951) for a map at the origin"""
+    ct_r = min(int(abs(centre_xz[1]) / 4), ch * 64 - 1); ct_c = min(int(abs(centre_xz[0]) / 4), cw * 64 - 1)
+    clamp = lambda a, lo, hi: max(lo, min(hi, a))
+    tdiv = lambda a: int(a / 64)                       # C division truncates toward zero
+    reach = 2 * radius
+    return (ct_r, ct_c), [(cr, cc) for cr in range(clamp(tdiv(ct_r - reach), 0, ch - 1), clamp(tdiv(ct_r + reach), 0, ch - 1) + 1)
+                          for cc in range(clamp(tdiv(ct_c - reach), 0, cw - 1), clamp(tdiv(ct_c + reach), 0, cw - 1) + 1)]
+
+
+def test_port_zone_fields_golden(pforacle):
+    """TARGET_ZONE chunk fields (field_update_zone, field.c:1810) and N_DesiredGroupArrivalVelocity (nav.c:3561)"""
+    g = gold("region")
+    cw = ch = 3
+    om = pforacle.OracleMap(cw, ch, g["cost"], g["blk"], None)
+    for k in range(len(g["zc"])):
+        for c in range(cw * ch):
+            assert (om.flow_field_zone((c // cw, c % cw), g["zc"][k], int(g["zrad"][k])) == g["zexp"][k, c]).all(), (k, c)
+    for k in range(len(g["gv_radius"])):
+        cxz, rad = g["gv_centre"][k], int(g["gv_radius"][k])
+        fields = np.zeros((cw * ch, 64, 64), np.uint8); has = np.zeros(cw * ch, np.uint8)
+        inside = (0 <= -cxz[0] <= cw * 256) and (0 <= cxz[1] <= ch * 256)
+        if inside:
+            ct, chunks = _zone_chunks(cxz, rad, cw, ch)
+            for cr, cc in chunks:
+                fields[cr * cw + cc] = om.flow_field_zone((cr, cc), ct, rad); has[cr * cw + cc] = 1
+        assert int(has.sum()) == int(g["gv_nfields"][k])
+        v, f = om.group_arrival_velocity(fields, has, cxz, rad, g["gv_pos"][k])
+        assert (f == g["gv_flags"][k]).all() and (v == g["gv_vel"][k]).all(), k
+
+
+def test_zone_seeds_host_vs_port(pforacle):
+    """the host-side seed flood of the CUDA path (pfnav_zone_seeds, no device needed) == the port's, order included"""
+    g = gold("region")
+    cw = ch = 3
+    om = pforacle.OracleMap(cw, ch, g["cost"], g["blk"], None)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, g["cost"], g["blk"])
+    rng = np.random.default_rng(2)
+    for k in range(40):
+        centre = (int(rng.integers(0, ch * 64)), int(rng.integers(0, cw * 64))); radius = int(rng.integers(0, 60))
+        for cr in range(ch):
+            for cc in range(cw):
+                a, b = nav.zone_seeds((cr, cc), centre, radius), om.zone_seeds((cr, cc), centre, radius)
+                assert a.shape == b.shape and (a == b).all(), (centre, radius, cr, cc)
+    nav.map_create(1, 3, 1)
+    with pytest.raises(Exception):
+        nav.zone_seeds((0, 0), (10, 10), 3)            # one chunk column: the reference's stride overruns its buffer
+    nav.close()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 
