@@ -95,6 +95,18 @@ int  pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *cost_base,
  *   pathability rule applies to `layer`. Follow with pfnav_map_build_nav(layer). */
 int  pfnav_map_cost_from_tiles(pfnav_ctx *ctx, int layer, int ref_layer, const void *const *chunk_tiles,
                                size_t tile_stride);
+/* PFMAP terrain ingestion (docs/pfmap.txt). pfnav_tile is the head of the engine's `struct tile`
+ * (map/public/tile.h:101) as pfnav_map_cost_from_tiles reads it (tile_stride = sizeof(pfnav_tile)).
+ * pfnav_pfmap_parse: al_parse_pfmap_header (asset_load.c:168) + the material / splat lines + m_al_read_pfchunk /
+ * m_al_parse_tile (map_asset_load.c:181, 103) over a memory image of the file. out_tiles = [chunk][32][32], chunks in
+ * row-major order, cap_tiles records; NULL reads the header only. Malformed input -> PFNAV_ERR_ARG. Host only.
+ * pfnav_map_load_pfmap: parse + pfnav_map_create(num_cols, num_rows, nlayers) + for every layer i the device cost
+ * pass under the reference layer ref_layers[i] + pfnav_map_build_nav(i) -- N_NewCtxForMapData (nav.c:2284). */
+typedef struct pfnav_tile { int32_t pathable, type, base_height, ramp_height; } pfnav_tile;
+int  pfnav_pfmap_parse(const char *text, size_t len, int *out_chunk_rows, int *out_chunk_cols, pfnav_tile *out_tiles,
+                       size_t cap_tiles);
+int  pfnav_map_load_pfmap(pfnav_ctx *ctx, const char *text, size_t len, int nlayers, const int32_t *ref_layers,
+                          float map_x, float map_z);
 /* Read one layer's DEVICE grids back in the packed chunk-blocked layout of N_CopyCostBasePacked /
  * N_CopyBlockersPacked (nav.c:2432, 2462). Any out pointer may be NULL. */
 int  pfnav_map_get_layer(pfnav_ctx *ctx, int layer, uint8_t *cost_base, uint16_t *blockers,

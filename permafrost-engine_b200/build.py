@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfnav.so")
-SOURCES = ["pfnav_fields.cu", "pfnav_agents.cu", "pfnav_plan.cu", "pfnav_route.cu", "pfnav_blockers.cu", "pfnav_region.cu"]
+SOURCES = ["pfnav_fields.cu", "pfnav_agents.cu", "pfnav_plan.cu", "pfnav_route.cu", "pfnav_blockers.cu", "pfnav_region.cu", "pfnav_pfmap.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     # bit-parity with the reference's x86-64 SSE float arithmetic: no FMA contraction

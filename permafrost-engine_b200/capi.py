@@ -77,7 +77,7 @@ SYMBOLS = [
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
     "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
-    "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
+    "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
 ]
 
 _lib = None
@@ -120,6 +120,8 @@ def load():
                                       C.c_size_t, C.c_void_p]
     L.pfnav_region_fields_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+    L.pfnav_pfmap_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+    L.pfnav_map_load_pfmap.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_float, C.c_float]
     L.pfnav_zone_seeds.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfnav_zone_fields.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_pool_request_zone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
@@ -223,6 +225,36 @@ def los_req(chunk, target_td, layer=0, prev_index=-1, prev_chunk=(0, 0)):
     return q
 
 
+def pfmap_parse(text):
+    """PFMAP text (bytes) -> int32[H32][W32][4] = {pathable, type, base_height, ramp_height} (global row-major)"""
+    L = load()
+    rows, cols = C.c_int(0), C.c_int(0)
+    _chk(L.pfnav_pfmap_parse(text, len(text), C.byref(rows), C.byref(cols), None, 0))
+    rec = np.zeros((rows.value * cols.value, 32, 32, 4), np.int32)
+    _chk(L.pfnav_pfmap_parse(text, len(text), C.byref(rows), C.byref(cols), _p(rec), rec.size // 4))
+    return rec.reshape(rows.value, cols.value, 32, 32, 4).transpose(0, 2, 1, 3, 4).reshape(rows.value * 32, cols.value * 32, 4).copy()
+
+
+def pfmap_write(tiles, materials=("Grass grass.png",), version="1.0", per_line=4):
+    """the inverse (m_al_write_tile, map_asset_load.c:132) for test inputs: tiles int32[H32][W32][4]"""
+    H, W = tiles.shape[0] // 32, tiles.shape[1] // 32
+    out = ["version %s" % version, "num_materials %d" % len(materials)]
+    if float(version) >= 1.1:
+        out.append("num_splats 0")
+    out += ["num_rows %d" % H, "num_cols %d" % W] + ["material " + m for m in materials]
+    for cr in range(H):
+        for cc in range(W):
+            for r in range(32):
+                row = []
+                for c in range(32):
+                    p, ty, bh, rh = [int(v) for v in tiles[cr * 32 + r, cc * 32 + c]]
+                    row.append("%01X%c%02d%02d%03d%03d%01d0%01d%01d%01d%01d%01d%01d%01d000" % (
+                        ty, "+" if bh >= 0 else "-", abs(bh), rh, 0, 0, 1 if p else 0, 1, 0, 0, 1, 1, 1, 1))
+                for k in range(0, 32, per_line):
+                    out.append(" ".join(row[k:k + per_line]))
+    return ("\n".join(out) + "\n").encode()
+
+
 class Nav:
     """One device navigation context (what `struct nav_private` is to the reference)."""
 
@@ -252,6 +284,14 @@ class Nav:
     def map_create(self, chunk_w, chunk_h, nlayers=1, map_x=0.0, map_z=0.0):
         self.cw, self.ch = chunk_w, chunk_h
         _chk(self.L.pfnav_map_create(self.h, chunk_w, chunk_h, nlayers, map_x, map_z))
+
+    def map_load_pfmap(self, text, ref_layers, map_x=0.0, map_z=0.0):
+        """parse a PFMAP image and build layer i under the reference layer ref_layers[i] (device cost pass + nav build)"""
+        rl = np.ascontiguousarray(ref_layers, np.int32)
+        rows, cols = C.c_int(0), C.c_int(0)
+        _chk(self.L.pfnav_pfmap_parse(text, len(text), C.byref(rows), C.byref(cols), None, 0))
+        _chk(self.L.pfnav_map_load_pfmap(self.h, text, len(text), len(rl), _p(rl), map_x, map_z))
+        self.cw, self.ch = cols.value, rows.value
 
     def map_upload_layer(self, layer, cost_base, blockers=None, local_islands=None):
         cost_base = np.ascontiguousarray(cost_base, np.uint8)

@@ -368,7 +368,50 @@ def gen_region():
 
 
 
+def gen_demo_map():
+    """The engine's own demo map (assets/maps/demo.pfmap, 4 x 4 chunks, every tile type, heights -3..9) through the
+    reference's nav build: per-layer cost grids, local islands, portals and a few path requests. The tile attributes
+    are read with the package's PFMAP parser (pfnav_pfmap_parse == m_al_parse_tile's fixed positions) and stored, so
+    the GPU box can rebuild the PFMAP text without the asset."""
+    text = open("/root/reference/assets/maps/demo.pfmap", "rb").read()
+    tiles = capi.pfmap_parse(text)
+    ch, cw = tiles.shape[0] // 32, tiles.shape[1] // 32
+    ref = pfref.RefMap(cw, ch, tiles=tiles)
+    out = dict(tiles=tiles.astype(np.int8))
+    for layer in (0, 1, 3, 4, 8):
+        out["cost_%d" % layer] = ref.cost_base(layer)
+    out["liid_0"] = ref.local_islands(0)
+    out["portals_0"] = ref.portals(0)
+    out["islands_0"] = ref.islands(0)
+    cost = out["cost_0"]
+    pairs = cases.route_pairs(cost, cw, ch, 9, 16)
+    n = cw * ch
+    oks, dids, ffids, flows, loss, has = [], [], [], [], [], []
+    for src, dst in pairs:
+        ref.fc_clear()
+        ok, did = ref.request_path(src, dst)
+        oks.append(ok); dids.append(did)
+        fid = np.zeros(n, np.uint64); hs = np.zeros(n, np.uint8)
+        fl = np.zeros((n, 64, 64), np.uint8); ls = np.zeros((n, 64, 64), np.uint8)
+        if ok:
+            for c in range(n):
+                f, k = ref.fc_flow(did, (c // cw, c % cw)); l = ref.fc_los(did, (c // cw, c % cw))
+                if f is not None:
+                    fl[c] = f; fid[c] = k; hs[c] |= 1
+                if l is not None:
+                    ls[c] = l; hs[c] |= 2
+        ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs)
+    out.update(pairs=np.array(pairs, np.float32), ok=np.array(oks), did=np.array(dids, np.uint32), ffid=np.array(ffids),
+               flow=np.array(flows), los=np.array(loss), has=np.array(has))
+    print("demo map: %dx%d chunks, impassable ground tiles %d, portals %d, routes ok %d of %d" % (
+        ch, cw, int((cost == 255).sum()), len(out["portals_0"]), int(sum(oks)), len(oks)))
+    np.savez_compressed(os.path.join(HERE, "demo_map.npz"), **out)
+    ref.close()
+
+
+
 if __name__ == "__main__":
+    gen_demo_map()
     gen_region()
     gen_faction()
     gen_repair_pool()

@@ -760,3 +760,30 @@ def test_zone_fields_and_group_arrival_golden(nav):
     # a destination without zone fields: every call "returns false"
     v, f = nav.group_arrival_velocity(7, g["gv_centre"][1], int(g["gv_radius"][1]), g["gv_pos"][1])
     assert not f.any() and not v.any()
+
+
+def test_demo_map_pfmap_ingestion_golden(nav):
+    """the engine's demo map as PFMAP text -> pfnav_map_load_pfmap (parse, device cost pass for five
+    reference layers, islands, portals) -> N_RequestPath into the pool; everything equals the reference's build"""
+    g = gold("demo_map")
+    text = capi.pfmap_write(g["tiles"].astype(np.int32), version="1.2")
+    layers = (0, 1, 3, 4, 8)
+    nav.map_load_pfmap(text, layers)
+    for slot, layer in enumerate(layers):
+        cost, blk, _ = nav.map_get_layer(slot)
+        assert (cost == g["cost_%d" % layer]).all(), layer
+        assert not blk.any()
+    assert (nav.local_islands(0) == g["liid_0"]).all()
+    assert (nav.portals(0)[:, :9] == g["portals_0"][:, :9]).all()
+    nav.route_build(0)
+    for i, (src, dst) in enumerate(g["pairs"]):
+        nav.pool_create(1, 16)
+        ok, did, nf, nl = nav.pool_request_path(0, tuple(src), tuple(dst))
+        assert ok == bool(g["ok"][i]) and (not ok or did == int(g["did"][i]))
+        for c in range(16):
+            f, l, ffid = nav.pool_get(0, (c // 4, c % 4))
+            assert (f is not None) == bool(g["has"][i][c] & 1) and (l is not None) == bool(g["has"][i][c] & 2), (i, c)
+            if f is not None:
+                assert ffid == int(g["ffid"][i][c]) and (f == g["flow"][i][c]).all(), (i, c)
+            if l is not None:
+                assert (l == g["los"][i][c]).all(), (i, c)

@@ -449,6 +449,41 @@ def test_route_request_path_golden(pforacle):
         nav.close()
 
 
+def test_pfmap_parse_roundtrip_and_errors():
+    """pfnav_pfmap_parse (docs/pfmap.txt; al_parse_pfmap_header asset_load.c:168, m_al_parse_tile map_asset_load.c:103):
+    host code, no device"""
+    t = cases.tile_attr_case(3, 2, 5)
+    want = np.concatenate([(t[..., :1] != 0).astype(np.int32), t[..., 1:]], -1)
+    txt = capi.pfmap_write(t)
+    assert (capi.pfmap_parse(txt) == want).all()
+    assert (capi.pfmap_parse(capi.pfmap_write(t, version="1.2", per_line=8)) == want).all()       # num_splats line, 8 tiles per line
+    assert (capi.pfmap_parse(txt.replace(b"\n", b"\r\n")) == want).all()
+    for bad in (b"", b"version 1.0\nnum_materials 0\nnum_rows 1\nnum_cols 1\n0+00", txt[:-30], txt.replace(b"0+", b"0+0", 1),
+                txt.replace(b"num_rows", b"rows", 1)):
+        with pytest.raises(capi.PfnavError):
+            capi.pfmap_parse(bad)
+    demo = "/root/reference/assets/maps/demo.pfmap"
+    if os.path.exists(demo):                       # the engine's own demo map: the tiles the golden was built from
+        assert (capi.pfmap_parse(open(demo, "rb").read()) == gold("demo_map")["tiles"]).all()
+
+
+def test_demo_map_nav_build_golden(pforacle):
+    """the engine's demo map (4 x 4 chunks, every tile type, heights -3..9) through the reference's nav build: per-layer
+    cost grids (port), local / global islands, portals and 16 path requests (host planner + port fields)"""
+    g = gold("demo_map")
+    tiles = g["tiles"].astype(np.int32)
+    for layer in (0, 1, 3, 4, 8):
+        assert (pforacle.cost_from_tiles(4, 4, tiles, layer) == g["cost_%d" % layer]).all(), layer
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(4, 4, 1); nav.map_upload_layer(0, g["cost_0"]); nav.map_build_nav(0); nav.route_build(0)
+    assert (nav.local_islands(0) == g["liid_0"]).all()
+    assert (nav.route_islands(0) == g["islands_0"]).all()
+    assert (nav.portals(0)[:, :9] == g["portals_0"][:, :9]).all()
+    om = pforacle.OracleMap(4, 4, g["cost_0"], None, g["liid_0"])
+    _check_route_against(nav, om, 4, 4, g["pairs"], g["ok"], g["did"], g["ffid"], g["flow"], g["los"], g["has"])
+    nav.close()
+
+
 def test_route_request_path_vs_ref(pfref, pforacle):
     cw = ch = 4
     p = cases.noise_map(cw, ch, 91, 0.1)
