@@ -389,6 +389,30 @@ int  pfnav_pool_request_zone(pfnav_ctx *ctx, int dest, int layer, const float *c
 int  pfnav_group_arrival_velocity(pfnav_ctx *ctx, int dest, const float *centre_xz, int radius, const float *pos_xz,
                                   size_t n, float *out_vel, uint8_t *out_flags);
 
+/* TARGET_ENTITY / TARGET_ENEMIES chunk fields (N_FlowFieldUpdate field.c:2040-2048 -> field_update_entity :1609,
+ * field_update_enemies :1540; consumers N_DesiredSurroundVelocity / N_DesiredEnemySeekVelocity nav.c:3683, 3603).
+ * Same padded-chunk integration as the zone fields; the zero-cost frontier is the set of tiles under the target
+ * entity (field_entity_initial_frontier, field.c:1317) or under every enemy near the chunk
+ * (field_enemies_initial_frontier, field.c:1209). What field.c reads about an entity through its
+ * nav_unit_query_ctx is passed in a pfnav_footprint; WHICH entities count as enemies (faction, COMBATABLE,
+ * diplomacy, not dying: field_enemy_ent field.c:963) is engine state and is decided by the caller. */
+typedef struct pfnav_footprint {       /* 48 bytes */
+    float    x, z;                     /* ent_pos_xz */
+    float    sel_radius;               /* ent_sel_radius; used unless is_building */
+    uint32_t is_building;              /* ENTITY_FLAG_BUILDING: the footprint is the bottom face of ent_curr_obb ... */
+    float    corners_xz[8];            /* ... as 4 (x, z) pairs, like pfnav_blockers_incref_obb; all inside the map */
+} pfnav_footprint;
+enum { PFNAV_TARGET_ENTITY = 0, PFNAV_TARGET_ENEMIES = 1 };
+/* Seed tiles of one chunk's field (host structure code, no device needed). ref_layer = the reference's enum
+ * nav_layer of `layer`, which fixes the number of contour rings (ENTITY: 3x3 -> 1, 5x5 -> 1, 7x7 and above -> 2;
+ * ENEMIES: 1 / 2 / 3). ENEMIES keeps only the entities whose position lies in the chunk's search rectangle
+ * (the chunk grown by half a chunk + 16 units, field.c:1229-1243) and returns each tile once, row-major. */
+int  pfnav_entity_seeds(pfnav_ctx *ctx, int ref_layer, int target_kind, const pfnav_footprint *ents, size_t nents,
+                        int chunk_r, int chunk_c, int32_t *out_rc, size_t cap, size_t *out_n);
+/* N_FlowFieldInit + N_FlowFieldUpdate for the listed chunks; out_fields: HOST, n * 4096 bytes. Synchronous. */
+int  pfnav_entity_fields(pfnav_ctx *ctx, int layer, int ref_layer, int target_kind, const pfnav_footprint *ents,
+                         size_t nents, const int32_t *chunks_rc, size_t n, uint8_t *out_fields);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Per-tick agent velocity update (seam B1: the reference's own GPU back-end calls
  * R_GL_MoveUploadData / R_GL_MoveDispatchWork / R_GL_MoveReadNewVelocities,

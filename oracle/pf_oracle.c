@@ -1347,18 +1347,19 @@ int pfo_zone_seeds(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int
     return zone_initial_frontier(m, centre_r, centre_c, base_r, base_c, dim, out, (int)budget);
 }
 
-/* N_FlowFieldUpdate for TARGET_ZONE (field.c:2050 -> field_update_zone, :1810), in place on `inout` (64 x 64
+/* The shared tail of field_update_zone / _entity / _enemies (field.c:1810, 1609, 1540): `seeds` (absolute tiles inside
+ * the padded region) at cost 0, field_build_integration_region (:587) with plain passability and no overlay, then
+ * field_build_flow_region (:762) over the chunk's window. pfo_flow_field_zone =
+ * N_FlowFieldUpdate for TARGET_ZONE (field.c:2050 -> field_update_zone, :1810), in place on `inout` (64 x 64
  * direction bytes): the integration runs over the padded region (plain passability, no overlay) and
  * field_build_flow_region (field.c:762) writes the chunk's window, leaving unreached tiles as they were. Only the
  * square cases are defined: 128 x 128 on maps with more than one chunk row AND column, 64 x 64 on a 1 x 1 map
  * (with one of the two the reference's row stride overruns its buffer). */
-void pfo_flow_field_zone(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, uint8_t *inout)
+void pfo_chunk_field_seeded(const pfo_map *m, int chunk_r, int chunk_c, const int32_t *seeds, int ns, uint8_t *inout)
 {
     const int dim = (m->chunk_h > 1 && m->chunk_w > 1) ? 2 * RES : RES;
     const int base_r = chunk_r > 0 ? chunk_r * RES - RES / 2 : 0, base_c = chunk_c > 0 ? chunk_c * RES - RES / 2 : 0;
     const int roff = chunk_r > 0 ? RES / 2 : 0, coff = chunk_c > 0 ? RES / 2 : 0;
-    int32_t *seeds = malloc(sizeof(int32_t) * 2 * dim * dim);
-    const int ns = pfo_zone_seeds(m, chunk_r, chunk_c, centre_r, centre_c, radius, seeds);
     float *intf = malloc(sizeof(float) * dim * dim);
     for(int i = 0; i < dim * dim; i++) intf[i] = INFINITY;
     pq frontier; pq_init(&frontier);
@@ -1386,7 +1387,16 @@ void pfo_flow_field_zone(const pfo_map *m, int chunk_r, int chunk_c, int centre_
         if(intf[ir * dim + ic] == 0.0f) { inout[r * RES + c] = FD_NONE; continue; }
         inout[r * RES + c] = (uint8_t)flow_dir_n(intf, dim, ir, ic);
     }
-    free(intf); free(seeds);
+    free(intf);
+}
+
+void pfo_flow_field_zone(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, uint8_t *inout)
+{
+    const int dim = (m->chunk_h > 1 && m->chunk_w > 1) ? 2 * RES : RES;
+    int32_t *seeds = malloc(sizeof(int32_t) * 2 * dim * dim);
+    const int ns = pfo_zone_seeds(m, chunk_r, chunk_c, centre_r, centre_c, radius, seeds);
+    pfo_chunk_field_seeded(m, chunk_r, chunk_c, seeds, ns, inout);
+    free(seeds);
 }
 
 /* N_DesiredGroupArrivalVelocity (nav.c:3561) against caller-held zone fields: fields[chunk] = 64 x 64 direction

@@ -94,6 +94,7 @@ void pfo_region_field_update_to_nearest_pathable(const pfo_map *m, int dim, int 
  * field_zone_initial_frontier (field.c:1683) and the per-entity consumer N_DesiredGroupArrivalVelocity (nav.c:3561).
  * centre in absolute tile coordinates; inout = 64 x 64 direction bytes of chunk (chunk_r, chunk_c). */
 int  pfo_zone_seeds(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, int32_t *out);
+void pfo_chunk_field_seeded(const pfo_map *m, int chunk_r, int chunk_c, const int32_t *seeds, int ns, uint8_t *inout);
 void pfo_flow_field_zone(const pfo_map *m, int chunk_r, int chunk_c, int centre_r, int centre_c, int radius, uint8_t *inout);
 void pfo_group_arrival_velocity(const pfo_map *m, const uint8_t *fields, const uint8_t *has, const float *centre_xz, int radius,
                                 const float *pos_xz, int n, float *out_vel, uint8_t *out_flags);

@@ -45,6 +45,7 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_void_p]
         L.pfo_zone_seeds.restype = C.c_int
         L.pfo_zone_seeds.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
+        L.pfo_chunk_field_seeded.argtypes = [C.POINTER(_Map), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pfo_flow_field_zone.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
         L.pfo_group_arrival_velocity.argtypes = [C.POINTER(_Map), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_int, C.c_void_p, C.c_void_p]
@@ -134,6 +135,13 @@ class OracleMap:
         out = np.zeros((4 * 4096, 2), np.int32)
         n = lib().pfo_zone_seeds(C.byref(self.m), chunk[0], chunk[1], int(centre[0]), int(centre[1]), int(radius), _p(out))
         return out[:n].copy()
+
+    def chunk_field_seeded(self, chunk, seeds, inout=None):
+        """padded-chunk field (zone / entity / enemies targets) from its zero-cost tiles"""
+        sd, ns = self._pairs(seeds)
+        buf = np.zeros((64, 64), np.uint8) if inout is None else np.ascontiguousarray(inout, np.uint8).reshape(64, 64).copy()
+        lib().pfo_chunk_field_seeded(C.byref(self.m), chunk[0], chunk[1], _p(sd), ns, _p(buf))
+        return buf
 
     def flow_field_zone(self, chunk, centre, radius, inout=None):
         """N_FlowFieldInit + N_FlowFieldUpdate(TARGET_ZONE); centre = absolute (r, c)"""

@@ -39,6 +39,8 @@ def lib():
         L.pfref_flow_field_zone.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
         L.pfref_group_arrival_velocity.restype = C.c_int
         L.pfref_group_arrival_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfref_agents_set_factions.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_flow_field_entity.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
         L.pfref_set_war.argtypes = [C.c_int, C.c_int, C.c_int]
         L.pfref_los_field_faction.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pfref_los_field.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -186,6 +188,22 @@ class RefMap:
         vel = np.zeros((len(pos), 2), np.float32); fl = np.zeros(len(pos), np.uint8)
         nb = lib().pfref_group_arrival_velocity(self.h, layer, _p(c), int(radius), len(pos), _p(pos), _p(vel), _p(fl))
         return vel, fl, nb
+
+    def agents_set_factions(self, factions):
+        f = np.ascontiguousarray(factions, np.int32)
+        lib().pfref_agents_set_factions(len(f), _p(f))
+
+    def flow_field_entity(self, chunk, uid, layer=0):
+        """N_FlowFieldUpdate(TARGET_ENTITY) around uploaded agent `uid` (surround fields)"""
+        out = np.zeros((64, 64), np.uint8)
+        lib().pfref_flow_field_entity(self.h, layer, chunk[0], chunk[1], 0, int(uid), _p(out))
+        return out
+
+    def flow_field_enemies(self, chunk, faction, layer=0):
+        """N_FlowFieldUpdate(TARGET_ENEMIES): towards the nearest enemy of `faction` among the uploaded agents"""
+        out = np.zeros((64, 64), np.uint8)
+        lib().pfref_flow_field_entity(self.h, layer, chunk[0], chunk[1], 1, int(faction), _p(out))
+        return out
 
     def set_war(self, a, b, at_war=True):
         lib().pfref_set_war(a, b, int(at_war))

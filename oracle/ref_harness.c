@@ -575,6 +575,89 @@ PFREF_EXPORT int pfref_group_arrival_velocity(void *m, int layer, const float *c
     return built;
 }
 
+/* TARGET_ENTITY / TARGET_ENEMIES fields through a nav_unit_query_ctx assembled from the tables pfref_agents_set
+ * fills (N_FlowFieldUpdate field.c:2040-2048). Entities are the uploaded agents (uid = index; none is a building,
+ * none is dying); factions come from pfref_agents_set_factions, the war matrix from pfref_set_war. */
+bool G_GetDiplomacyStateFrom(enum diplomacy_state (*table)[MAX_FACTIONS], int fac_id_a, int fac_id_b,
+                             enum diplomacy_state *out)                        /* game.c:2907 */
+{
+    if(fac_id_a == fac_id_b)
+        return false;
+    *out = table[fac_id_a][fac_id_b];
+    return true;
+}
+
+/* Fog of war is engine state: every entity is visible to the requester here (field_enemy_ent's last test,
+ * field.c:980). The transforms / bounding boxes only feed that test, so they are placeholders. */
+quat_t Entity_GetRotFrom(khash_t(trans) *table, uint32_t uid) { return (quat_t){0.0f, 0.0f, 0.0f, 1.0f}; }
+vec3_t Entity_GetScaleFrom(khash_t(trans) *table, uint32_t uid) { return (vec3_t){1.0f, 1.0f, 1.0f}; }
+void   Entity_ModelMatrixFrom(vec3_t pos, quat_t rot, vec3_t scale, mat4x4_t *out) { memset(out, 0, sizeof(*out)); }
+void   Entity_CurrentOBBFrom(const struct aabb *aabb, mat4x4_t model, vec3_t scale, struct obb *out) { memset(out, 0, sizeof(*out)); }
+bool   G_Fog_ObjVisibleFrom(uint32_t *state, bool enabled, uint16_t fac_mask, const struct obb *obb) { return true; }
+static khash_t(aabb) *s_pfref_aabbs;
+static int s_nagents;        /* defined with the agent tables below */
+
+static struct nav_unit_query_ctx s_pfref_qctx;
+static enum diplomacy_state      s_pfref_diptable[MAX_FACTIONS][MAX_FACTIONS];
+static khash_t(id)              *s_pfref_dying;
+
+static struct nav_unit_query_ctx *pfref_query_ctx(void)
+{
+    struct move_gamestate *gs = &s_move_work.gamestate;
+    if(!s_pfref_dying) s_pfref_dying = kh_init(id);
+    for(int a = 0; a < MAX_FACTIONS; a++)
+        for(int b = 0; b < MAX_FACTIONS; b++)
+            s_pfref_diptable[a][b] = s_pfref_war[a][b] ? DIPLOMACY_STATE_WAR : DIPLOMACY_STATE_PEACE;
+    memset(&s_pfref_qctx, 0, sizeof(s_pfref_qctx));
+    s_pfref_qctx.flags = gs->flags;
+    s_pfref_qctx.positions = gs->positions;
+    s_pfref_qctx.postree = gs->postree;
+    s_pfref_qctx.faction_ids = gs->faction_ids;
+    s_pfref_qctx.sel_radiuses = gs->sel_radiuses;
+    if(s_pfref_aabbs) kh_destroy(aabb, s_pfref_aabbs);
+    s_pfref_aabbs = kh_init(aabb);
+    for(size_t i = 0; i < s_nagents; i++) {
+        int ret;
+        khiter_t k = kh_put(aabb, s_pfref_aabbs, (uint32_t)i, &ret);
+        memset(&kh_value(s_pfref_aabbs, k), 0, sizeof(struct aabb));
+    }
+    s_pfref_qctx.aabbs = s_pfref_aabbs;
+    s_pfref_qctx.dying_set = s_pfref_dying;
+    s_pfref_qctx.diptable = (void*)s_pfref_diptable;
+    return &s_pfref_qctx;
+}
+
+PFREF_EXPORT void pfref_agents_set_factions(int n, const int32_t *factions)
+{
+    struct move_gamestate *gs = &s_move_work.gamestate;
+    for(int i = 0; i < n; i++) {
+        khiter_t k = kh_get(id, gs->faction_ids, (uint32_t)i);
+        if(k != kh_end(gs->faction_ids)) kh_value(gs->faction_ids, k) = factions[i];
+    }
+}
+
+/* kind 0: TARGET_ENTITY, arg = the target entity's uid; kind 1: TARGET_ENEMIES, arg = the requesting faction */
+PFREF_EXPORT void pfref_flow_field_entity(void *m, int layer, int chunk_r, int chunk_c, int kind, int arg, uint8_t *out)
+{
+    struct map *map = m;
+    struct nav_private *priv = pfref_priv(m);
+    struct flow_field ff;
+    N_FlowFieldInit((struct coord){chunk_r, chunk_c}, &ff);
+    struct field_target target;
+    memset(&target, 0, sizeof(target));
+    if(kind == 0) {
+        target.type = TARGET_ENTITY;
+        target.ent = (struct entity_desc){ (uint32_t)arg, map->pos };
+    }else{
+        target.type = TARGET_ENEMIES;
+        target.enemies.faction_id = arg;
+        target.enemies.map_pos = map->pos;
+        target.enemies.chunk = (struct coord){chunk_r, chunk_c};
+    }
+    N_FlowFieldUpdate((struct coord){chunk_r, chunk_c}, priv, arg, layer, target, pfref_query_ctx(), &ff);
+    pfref_flow_pack(&ff, out);
+}
+
 /* N_LOSFieldCreate; field.c:2085. prev may be NULL (destination chunk). */
 PFREF_EXPORT void pfref_los_field(void *m, int layer, int chunk_r, int chunk_c,
                                   int tgt_chunk_r, int tgt_chunk_c, int tgt_tile_r, int tgt_tile_c,

@@ -57,6 +57,10 @@ REGION_REQ = np.dtype([
 assert REGION_REQ.itemsize == 40
 REGION_CREATE, REGION_FIXUP, REGION_CELL = 1, 2, 4
 
+FOOTPRINT = np.dtype([("x", "<f4"), ("z", "<f4"), ("sel_radius", "<f4"), ("is_building", "<u4"), ("corners_xz", "<f4", 8)])
+assert FOOTPRINT.itemsize == 48
+TARGET_ENTITY, TARGET_ENEMIES = 0, 1
+
 LOS_PREV_INPLACE = -3
 TICK_VDES_FROM_POOL = 1
 FLAG_MOVABLE, FLAG_WATER, FLAG_AIR, FLAG_GARRISONED, FLAG_COMBAT_HELD = 1 << 3, 1 << 14, 1 << 15, 1 << 18, 1 << 21
@@ -77,7 +81,7 @@ SYMBOLS = [
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
     "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
-    "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
+    "pfnav_entity_seeds", "pfnav_entity_fields", "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
 ]
 
 _lib = None
@@ -122,6 +126,9 @@ def load():
                                           C.c_void_p]
     L.pfnav_pfmap_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
     L.pfnav_map_load_pfmap.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_float, C.c_float]
+    L.pfnav_entity_seeds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]
+    L.pfnav_entity_fields.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_zone_seeds.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.pfnav_zone_fields.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]
     L.pfnav_pool_request_zone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
@@ -369,6 +376,30 @@ class Nav:
         out = np.zeros((dim, dim // 2), np.uint8)
         _chk(self.L.pfnav_group_arrival_field(self.h, layer, dim, int(enemies), _p(t) if len(t) else None, len(t), _p(c),
                                               _p(ov) if len(ov) else None, len(ov), _p(out)))
+        return out
+
+    @staticmethod
+    def footprints(pos_xz, sel_radius):
+        """circle footprints (non-building entities) for entity_seeds / entity_fields"""
+        pos = np.asarray(pos_xz, np.float32).reshape(-1, 2)
+        fp = np.zeros(len(pos), FOOTPRINT)
+        fp["x"], fp["z"] = pos[:, 0], pos[:, 1]
+        fp["sel_radius"] = np.broadcast_to(np.asarray(sel_radius, np.float32), (len(pos),))
+        return fp
+
+    def entity_seeds(self, kind, ents, chunk, ref_layer=0):
+        ents = np.ascontiguousarray(ents, FOOTPRINT)
+        out = np.zeros((4 * 4096, 2), np.int32); n = C.c_size_t(0)
+        _chk(self.L.pfnav_entity_seeds(self.h, ref_layer, kind, _p(ents) if len(ents) else None, len(ents), chunk[0], chunk[1],
+                                       _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def entity_fields(self, kind, ents, chunks, layer=0, ref_layer=0):
+        """N_FlowFieldInit + N_FlowFieldUpdate(TARGET_ENTITY | TARGET_ENEMIES) for the listed chunks -> u8[n, 64, 64]"""
+        ents = np.ascontiguousarray(ents, FOOTPRINT)
+        ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
+        out = np.zeros((len(ch), 64, 64), np.uint8)
+        _chk(self.L.pfnav_entity_fields(self.h, layer, ref_layer, kind, _p(ents) if len(ents) else None, len(ents), _p(ch), len(ch), _p(out)))
         return out
 
     def zone_seeds(self, chunk, centre, radius, layer=0):

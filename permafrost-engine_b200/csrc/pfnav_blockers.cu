@@ -303,6 +303,30 @@ static int blockers_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id,
 
 }   // namespace
 
+// The tiles an entity occupies as a field target (field_entity_initial_frontier field.c:1334-1355,
+// field_enemies_initial_frontier :1262-1283): circle (selection radius) or building OBB footprint, then `rings`
+// contour rings, each taken around everything collected so far, all inside one 512-entry array.
+// out_rc: up to 512 (r, c) pairs. Returns the count, or -1 when an OBB corner lies outside the map.
+int pfnav_footprint_tiles(const pfnav_ctx *ctx, const pfnav_footprint *e, int rings, int32_t *out_rc)
+{
+    td tds[512];
+    size_t n;
+    if (e->is_building) {
+        v2f c[4];
+        for (int i = 0; i < 4; i++) {
+            c[i] = {e->corners_xz[2 * i], e->corners_xz[2 * i + 1]};
+            td t;
+            if (!desc_for_point(ctx, c[i].x, c[i].z, &t)) return -1;
+        }
+        n = tiles_under_obb(ctx, c, tds, 512);
+    } else {
+        n = tiles_under_circle(ctx, {e->x, e->z}, e->sel_radius, tds, 512);
+    }
+    for (int k = 0; k < rings; k++) n += tiles_contour(ctx, n, tds, tds + n, 512 - n);
+    for (size_t i = 0; i < n; i++) { out_rc[2 * i] = tds[i].chunk_r * 64 + tds[i].tile_r; out_rc[2 * i + 1] = tds[i].chunk_c * 64 + tds[i].tile_c; }
+    return (int)n;
+}
+
 void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); g_fdirty.erase(ctx); }
 
 extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)

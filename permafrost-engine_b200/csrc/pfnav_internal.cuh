@@ -232,3 +232,6 @@ void pfnav_agents_free(pfnav_ctx *ctx);
 
 // ---- device helpers shared by kernels ----
 __device__ __forceinline__ uint32_t pf_lane() { return threadIdx.x & 31; }
+
+// entity footprint -> tiles (pfnav_blockers.cu), for the TARGET_ENTITY / TARGET_ENEMIES frontiers
+int pfnav_footprint_tiles(const pfnav_ctx *ctx, const pfnav_footprint *e, int rings, int32_t *out_rc);

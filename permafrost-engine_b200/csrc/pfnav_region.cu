@@ -636,7 +636,47 @@ static int zone_dim(const pfnav_ctx *ctx, int *out_dim)
     return PFNAV_ERR_ARG;
 }
 
-// seeds of every requested chunk + the device launch; d_out = n x 4096 direction bytes
+// Padded-chunk fields from per-chunk seed lists (seed_off[i] .. seed_off[i + 1] pairs of chunk i); d_out = n x 4096
+// direction bytes. Shared by the zone, entity and enemies targets (field_update_zone / _entity / _enemies).
+static int chunk_fields_launch(pfnav_ctx *ctx, int layer, int dim, const int32_t *chunks_rc, size_t n, const std::vector<int32_t> &seeds,
+                               const std::vector<size_t> &seed_off, uint8_t *d_out, cudaStream_t st)
+{
+    std::vector<pfnav_region_req> reqs(n);
+    for (size_t i = 0; i < n; i++) {
+        pfnav_region_req q = {};
+        q.layer = layer; q.center_r = chunks_rc[2 * i]; q.center_c = chunks_rc[2 * i + 1];
+        q.seed_off = (int32_t)seed_off[i]; q.seed_n = (int32_t)(seed_off[i + 1] - seed_off[i]);
+        q.flags = PFNAV_REGION_CREATE;
+        reqs[i] = q;
+    }
+    const size_t b_req = n * sizeof(pfnav_region_req), b_seed = std::max<size_t>(seeds.size(), 2) * 4;
+    uint8_t *d_buf = nullptr;
+    PF_CUDA(cudaMalloc(&d_buf, b_req + b_seed + 8));
+    int rc = PFNAV_OK;
+    cudaError_t e = cudaMemcpyAsync(d_buf, reqs.data(), b_req, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !seeds.empty()) e = cudaMemcpyAsync(d_buf + b_req, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        rc = region_launch(ctx, dim, reinterpret_cast<const pfnav_region_req *>(d_buf), n, reinterpret_cast<const int32_t *>(d_buf + b_req),
+                           reinterpret_cast<const int32_t *>(d_buf + b_req + b_seed), d_out, st, 1);
+    // the staging buffer is read by the kernel: free it once the stream has passed it
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        pfnav_set_error("chunk fields: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return PFNAV_ERR_CUDA;
+    }
+    return PFNAV_OK;
+}
+
+// the padded region of chunk (cr, cc): field.c:1566-1571
+static inline void chunk_region_base(int dim, int cr, int cc, int *base_r, int *base_c)
+{
+    *base_r = (cr > 0 && dim > 64) ? cr * 64 - 32 : cr * 64;
+    *base_c = (cc > 0 && dim > 64) ? cc * 64 - 32 : cc * 64;
+}
+
+// zone seeds of every requested chunk + the device launch
 static int zone_fields_launch(pfnav_ctx *ctx, int layer, int centre_r, int centre_c, int radius, const int32_t *chunks_rc, size_t n,
                               uint8_t *d_out, cudaStream_t st)
 {
@@ -647,38 +687,17 @@ static int zone_fields_launch(pfnav_ctx *ctx, int layer, int centre_r, int centr
     zone_map zm = { ctx->h_cost.data() + ltiles * layer, ctx->h_blk.data() + ltiles * layer, ctx->chunk_w, ctx->chunk_h };
     size_t budget = (size_t)(M_PI * radius * radius + 0.5);             // field.c:1843
     if (budget > (size_t)dim * dim) budget = (size_t)dim * dim;
-    std::vector<pfnav_region_req> reqs(n);
     std::vector<int32_t> seeds;
+    std::vector<size_t> off(n + 1, 0);
     for (size_t i = 0; i < n; i++) {
         const int cr = chunks_rc[2 * i], cc = chunks_rc[2 * i + 1];
         PF_ARG(cr >= 0 && cr < ctx->chunk_h && cc >= 0 && cc < ctx->chunk_w, "zone field: chunk");
-        const int base_r = (cr > 0 && dim > 64) ? cr * 64 - 32 : cr * 64, base_c = (cc > 0 && dim > 64) ? cc * 64 - 32 : cc * 64;
-        pfnav_region_req q = {};
-        q.layer = layer; q.center_r = cr; q.center_c = cc;
-        q.seed_off = (int32_t)(seeds.size() / 2);
+        int base_r, base_c;
+        chunk_region_base(dim, cr, cc, &base_r, &base_c);
         zone_initial_frontier(zm, centre_r, centre_c, base_r, base_c, dim, budget, seeds);
-        q.seed_n = (int32_t)(seeds.size() / 2) - q.seed_off;
-        q.flags = PFNAV_REGION_CREATE;
-        reqs[i] = q;
+        off[i + 1] = seeds.size() / 2;
     }
-    const size_t b_req = n * sizeof(pfnav_region_req), b_seed = std::max<size_t>(seeds.size(), 2) * 4;
-    uint8_t *d_buf = nullptr;
-    PF_CUDA(cudaMalloc(&d_buf, b_req + b_seed + 8));
-    cudaError_t e = cudaMemcpyAsync(d_buf, reqs.data(), b_req, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && !seeds.empty()) e = cudaMemcpyAsync(d_buf + b_req, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-        rc = region_launch(ctx, dim, reinterpret_cast<const pfnav_region_req *>(d_buf), n, reinterpret_cast<const int32_t *>(d_buf + b_req),
-                           reinterpret_cast<const int32_t *>(d_buf + b_req + b_seed), d_out, st, 1);
-    // the staging buffer is read by the kernel: free it once the stream has passed it (pageable copies above are
-    // already staged by the driver when cudaMemcpyAsync returns)
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(d_buf);
-    if (rc) return rc;
-    if (e != cudaSuccess || e2 != cudaSuccess) {
-        pfnav_set_error("zone fields: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
-        return PFNAV_ERR_CUDA;
-    }
-    return PFNAV_OK;
+    return chunk_fields_launch(ctx, layer, dim, chunks_rc, n, seeds, off, d_out, st);
 }
 
 extern "C" int pfnav_zone_fields(pfnav_ctx *ctx, int layer, int centre_r, int centre_c, int radius, const int32_t *chunks_rc,
@@ -820,4 +839,118 @@ extern "C" int pfnav_zone_seeds(pfnav_ctx *ctx, int layer, int chunk_r, int chun
     *out_n = seeds.size() / 2;
     if (out_rc) memcpy(out_rc, seeds.data(), std::min(cap * 2, seeds.size()) * sizeof(int32_t));
     return PFNAV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// TARGET_ENTITY / TARGET_ENEMIES chunk fields (field_update_entity field.c:1609, field_update_enemies :1540)
+// ------------------------------------------------------------------------------------------
+// BG_SCALE_F (lib/public/bitmap_grid.h:196): the position index compares scaled integers, bounds inclusive (:543)
+static inline int32_t bg_scale_f(float x) { return (int32_t)lrintf(x * 256.0f); }
+
+static int entity_seeds(const pfnav_ctx *ctx, int ref_layer, int kind, const pfnav_footprint *ents, size_t nents, int dim,
+                        int chunk_r, int chunk_c, std::vector<int32_t> &out)
+{
+    int base_r, base_c;
+    chunk_region_base(dim, chunk_r, chunk_c, &base_r, &base_c);
+    int32_t tiles[512 * 2];
+    if (kind == PFNAV_TARGET_ENTITY) {
+        // field_entity_initial_frontier (field.c:1317): note `layer == GROUND_3X3` for the first ring
+        const int rings = (ref_layer == 1) + (ref_layer >= 2) + (ref_layer >= 3);
+        const int n = pfnav_footprint_tiles(ctx, &ents[0], rings, tiles);
+        if (n < 0) { pfnav_set_error("entity field: a building corner lies outside the map"); return PFNAV_ERR_ARG; }
+        for (int i = 0; i < n; i++) {
+            const int dr = tiles[2 * i] - base_r, dc = tiles[2 * i + 1] - base_c;
+            if (dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+            out.push_back(tiles[2 * i]); out.push_back(tiles[2 * i + 1]);
+        }
+        return PFNAV_OK;
+    }
+    // field_enemies_initial_frontier (field.c:1209)
+    const int rings = (ref_layer >= 1) + (ref_layer >= 2) + (ref_layer >= 3);
+    // field_chunk_bounds (field.c:863) and the search rectangle (:1229-1243), in the reference's float arithmetic
+    const int x_offset = -(chunk_c * 256), z_offset = chunk_r * 256;
+    const float x_max = ctx->map_x + (float)x_offset, x_min = x_max - 256.0f;
+    const float z_min = ctx->map_z + (float)z_offset, z_max = z_min + 256.0f;
+    const float xlen = x_max - x_min, zlen = z_max - z_min;
+    const int32_t imnx = bg_scale_f(x_min - xlen / 2.0f - 16.0f), imxx = bg_scale_f(x_max + xlen / 2.0f + 16.0f);
+    const int32_t imnz = bg_scale_f(z_min - zlen / 2.0f - 16.0f), imxz = bg_scale_f(z_max + zlen / 2.0f + 16.0f);
+    std::vector<uint8_t> has((size_t)dim * dim, 0);
+    for (size_t k = 0; k < nents; k++) {
+        const int32_t ix = bg_scale_f(ents[k].x), iz = bg_scale_f(ents[k].z);
+        if (ix < imnx || ix > imxx || iz < imnz || iz > imxz) continue;
+        const int n = pfnav_footprint_tiles(ctx, &ents[k], rings, tiles);
+        if (n < 0) { pfnav_set_error("enemies field: a building corner lies outside the map"); return PFNAV_ERR_ARG; }
+        for (int i = 0; i < n; i++) {
+            const int dr = tiles[2 * i] - base_r, dc = tiles[2 * i + 1] - base_c;
+            if (dr < 0 || dr >= dim || dc < 0 || dc >= dim) continue;
+            has[(size_t)dr * dim + dc] = 1;
+        }
+    }
+    for (int r = 0; r < dim; r++)
+        for (int c = 0; c < dim; c++)
+            if (has[(size_t)r * dim + c]) { out.push_back(base_r + r); out.push_back(base_c + c); }
+    return PFNAV_OK;
+}
+
+static int entity_args_ok(const pfnav_ctx *ctx, int ref_layer, int kind, const pfnav_footprint *ents, size_t nents)
+{
+    PF_ARG(ref_layer >= 0 && ref_layer < PFNAV_NAV_LAYER_MAX, "ref_layer");
+    PF_ARG(kind == PFNAV_TARGET_ENTITY || kind == PFNAV_TARGET_ENEMIES, "target_kind");
+    PF_ARG(nents == 0 || ents, "ents");
+    PF_ARG(kind != PFNAV_TARGET_ENTITY || nents == 1, "TARGET_ENTITY takes exactly one entity");
+    PF_ARG(nents < (1u << 24), "nents");
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_entity_seeds(pfnav_ctx *ctx, int ref_layer, int target_kind, const pfnav_footprint *ents, size_t nents,
+                                  int chunk_r, int chunk_c, int32_t *out_rc, size_t cap, size_t *out_n)
+{
+    PF_ARG(ctx && !ctx->h_cost.empty(), "map not created");
+    PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w && out_n, "chunk / out_n");
+    int rc = entity_args_ok(ctx, ref_layer, target_kind, ents, nents);
+    if (rc) return rc;
+    int dim = 0;
+    rc = zone_dim(ctx, &dim);
+    if (rc) return rc;
+    std::vector<int32_t> seeds;
+    rc = entity_seeds(ctx, ref_layer, target_kind, ents, nents, dim, chunk_r, chunk_c, seeds);
+    if (rc) return rc;
+    *out_n = seeds.size() / 2;
+    if (out_rc) memcpy(out_rc, seeds.data(), std::min(cap * 2, seeds.size()) * sizeof(int32_t));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_entity_fields(pfnav_ctx *ctx, int layer, int ref_layer, int target_kind, const pfnav_footprint *ents,
+                                   size_t nents, const int32_t *chunks_rc, size_t n, uint8_t *out_fields)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    PF_NEED_DEVICE(ctx);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(chunks_rc && out_fields, "null buffer");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    PF_ARG(n < (1u << 24), "n");
+    int rc = entity_args_ok(ctx, ref_layer, target_kind, ents, nents);
+    if (rc) return rc;
+    int dim = 0;
+    rc = zone_dim(ctx, &dim);
+    if (rc) return rc;
+    std::vector<int32_t> seeds;
+    std::vector<size_t> off(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        const int cr = chunks_rc[2 * i], cc = chunks_rc[2 * i + 1];
+        PF_ARG(cr >= 0 && cr < ctx->chunk_h && cc >= 0 && cc < ctx->chunk_w, "entity field: chunk");
+        rc = entity_seeds(ctx, ref_layer, target_kind, ents, nents, dim, cr, cc, seeds);
+        if (rc) return rc;
+        off[i + 1] = seeds.size() / 2;
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *d_out = nullptr;
+    PF_CUDA(cudaMalloc(&d_out, n * 4096));
+    rc = chunk_fields_launch(ctx, layer, dim, chunks_rc, n, seeds, off, d_out, ctx->tick_stream);
+    if (rc == 0 && cudaMemcpy(out_fields, d_out, n * 4096, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        pfnav_set_error("pfnav_entity_fields: copy back failed"); rc = PFNAV_ERR_CUDA;
+    }
+    cudaFree(d_out);
+    return rc;
 }

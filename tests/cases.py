@@ -356,3 +356,21 @@ def region_reqs_from_golden(rec, ov):
                         start=None if row[5] < 0 else (int(row[5]), int(row[6])), overlay=ov[o:o + n] if n else None))
         o += n
     return out
+
+
+def target_case(seed, cw=3, ch=3, n=120):
+    """entities for the TARGET_ENTITY / TARGET_ENEMIES fields: positions, selection radii, factions, flags
+    (all MOVABLE, ~85 % COMBATABLE) -> dict"""
+    rng = np.random.default_rng(seed)
+    pos = np.stack([-rng.uniform(4, cw * 256 - 4, n), rng.uniform(4, ch * 256 - 4, n)], 1).astype(np.float32)
+    radius = rng.uniform(0.5, 9.0, n).astype(np.float32)
+    factions = rng.integers(0, 4, n).astype(np.int32)
+    flags = np.full(n, (1 << 3) | (1 << 4), np.uint32)
+    flags[rng.random(n) < 0.15] &= ~np.uint32(1 << 4)
+    return dict(pos=pos, radius=radius, factions=factions, flags=flags)
+
+
+def enemies_of(faction, wars, factions, flags):
+    """field_enemy_ent (field.c:963) with fog disabled: other faction, COMBATABLE, at war"""
+    foes = [b if a == faction else a for a, b in wars if faction in (a, b)]
+    return np.isin(factions, foes) & ((flags & (1 << 4)) != 0)

@@ -410,7 +410,39 @@ def gen_demo_map():
 
 
 
+def gen_targets():
+    """TARGET_ENTITY / TARGET_ENEMIES chunk fields (field_update_entity field.c:1609, field_update_enemies :1540) on
+    reference layers 0 (1x1) and 2 (5x5: contour rings), through a nav_unit_query_ctx over 120 entities"""
+    cw = ch = 3
+    p, blockers, wars, _ = cases.region_case(7, cw, ch, 4, 96)
+    ref = pfref.RefMap(cw, ch, p)
+    for a, b in wars:
+        ref.set_war(a, b)
+    for b in blockers[:30]:
+        ref.blockers_incref(b[0], b[1], b[2], b[3], 0)
+    ref.update()
+    t = cases.target_case(4, cw, ch)
+    n = len(t["radius"])
+    z = np.zeros((n, 2), np.float32)
+    ref.agents_set(t["pos"], t["pos"], z, t["radius"], np.ones(n, np.float32), np.zeros(n, np.int32), t["flags"],
+                   np.full(n, -1, np.int32), np.zeros((0, 2), np.float32), np.zeros(0, np.uint32))
+    ref.agents_set_factions(t["factions"])
+    uids = np.arange(0, n, 15)
+    out = dict(pathable=p, blockers=np.array(blockers[:30], np.float32), wars=np.array(wars, np.int32), uids=uids, **t)
+    for L in (0, 2):
+        out["cost_%d" % L] = ref.cost_base(L); out["blk_%d" % L] = ref.blockers(L)
+        out["ent_%d" % L] = np.stack([np.stack([ref.flow_field_entity((c // cw, c % cw), int(u), layer=L) for c in range(cw * ch)]) for u in uids])
+        out["foe_%d" % L] = np.stack([np.stack([ref.flow_field_enemies((c // cw, c % cw), f, layer=L) for c in range(cw * ch)]) for f in range(4)])
+        print("targets layer %d: entity fields non-empty %d of %d, enemies %d of %d" % (
+            L, int(out["ent_%d" % L].reshape(-1, 4096).any(axis=1).sum()), len(uids) * cw * ch,
+            int(out["foe_%d" % L].reshape(-1, 4096).any(axis=1).sum()), 4 * cw * ch))
+    np.savez_compressed(os.path.join(HERE, "targets.npz"), **out)
+    ref.close()
+
+
+
 if __name__ == "__main__":
+    gen_targets()
     gen_demo_map()
     gen_region()
     gen_faction()

@@ -787,3 +787,24 @@ def test_demo_map_pfmap_ingestion_golden(nav):
                 assert ffid == int(g["ffid"][i][c]) and (f == g["flow"][i][c]).all(), (i, c)
             if l is not None:
                 assert (l == g["los"][i][c]).all(), (i, c)
+
+
+def test_entity_and_enemies_fields_golden(nav):
+    """N_FlowFieldUpdate with TARGET_ENTITY / TARGET_ENEMIES (field.c:2040-2048) on reference layers 0 and 2: every
+    chunk of the map in one launch per target, vs the compiled reference"""
+    g = gold("targets")
+    cw = ch = 3
+    wars = [tuple(w) for w in g["wars"]]
+    allchunks = [(c // cw, c % cw) for c in range(cw * ch)]
+    nav.map_create(cw, ch, 2)
+    for slot, L in enumerate((0, 2)):
+        nav.map_upload_layer(slot, g["cost_%d" % L], g["blk_%d" % L])
+    fp = nav.footprints(g["pos"], g["radius"])
+    for slot, L in enumerate((0, 2)):
+        for k, u in enumerate(g["uids"]):
+            got = nav.entity_fields(capi.TARGET_ENTITY, fp[u:u + 1], allchunks, layer=slot, ref_layer=L)
+            assert (got == g["ent_%d" % L][k]).all(), (L, u)
+        for f in range(4):
+            sel = cases.enemies_of(f, wars, g["factions"], g["flags"])
+            got = nav.entity_fields(capi.TARGET_ENEMIES, fp[sel], allchunks, layer=slot, ref_layer=L)
+            assert (got == g["foe_%d" % L][f]).all(), (L, f)

@@ -243,6 +243,32 @@ def test_zone_seeds_host_vs_port(pforacle):
     nav.close()
 
 
+def test_entity_and_enemies_fields_golden(pforacle):
+    """TARGET_ENTITY / TARGET_ENEMIES: the host seed code of the CUDA path (pfnav_entity_seeds: footprint tiles,
+    contour rings per reference layer, the enemies' search rectangle) + the port's padded-chunk integration
+    == the compiled reference's N_FlowFieldUpdate through a nav_unit_query_ctx"""
+    g = gold("targets")
+    cw = ch = 3
+    wars = [tuple(w) for w in g["wars"]]
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, g["cost_0"], g["blk_0"])
+    fp = nav.footprints(g["pos"], g["radius"])
+    for L in (0, 2):
+        om = pforacle.OracleMap(cw, ch, g["cost_%d" % L], g["blk_%d" % L], None)
+        for k, u in enumerate(g["uids"]):
+            for c in range(cw * ch):
+                sd = nav.entity_seeds(capi.TARGET_ENTITY, fp[u:u + 1], (c // cw, c % cw), ref_layer=L)
+                assert (om.chunk_field_seeded((c // cw, c % cw), sd) == g["ent_%d" % L][k, c]).all(), (L, u, c)
+        for f in range(4):
+            sel = cases.enemies_of(f, wars, g["factions"], g["flags"])
+            for c in range(cw * ch):
+                sd = nav.entity_seeds(capi.TARGET_ENEMIES, fp[sel], (c // cw, c % cw), ref_layer=L)
+                assert (om.chunk_field_seeded((c // cw, c % cw), sd) == g["foe_%d" % L][f, c]).all(), (L, f, c)
+    with pytest.raises(capi.PfnavError):
+        nav.entity_seeds(capi.TARGET_ENTITY, fp[:2], (0, 0))              # one target entity only
+    nav.close()
+
+
 TILE_CASES = ((2, 2), (3, 2))
 
 
