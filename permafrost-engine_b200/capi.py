@@ -232,6 +232,31 @@ def los_req(chunk, target_td, layer=0, prev_index=-1, prev_chunk=(0, 0)):
     return q
 
 
+def pack_region_reqs(reqs, layer=0):
+    """list of dicts {center, target | seeds, enemies, overlay, start, cell, no_create} -> (REGION_REQ[n], seeds int32[k, 2],
+    overlay int32[m, 2]) as pfnav_region_fields takes them"""
+    rec = np.zeros(len(reqs), REGION_REQ)
+    seeds, ovs = [], []
+    for i, q in enumerate(reqs):
+        sd = np.asarray(q["seeds"] if q.get("seeds") is not None else [q["target"]], np.int32).reshape(-1, 2)
+        ov = np.asarray(q["overlay"] if q.get("overlay") is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
+        flags = 0 if q.get("no_create") else REGION_CREATE
+        if q.get("cell", q.get("seeds") is None):
+            flags |= REGION_CELL
+        if q.get("start") is not None:
+            flags |= REGION_FIXUP
+            rec["start_r"][i], rec["start_c"][i] = q["start"]
+        rec["layer"][i] = layer
+        rec["center_r"][i], rec["center_c"][i] = q["center"]
+        rec["seed_off"][i], rec["seed_n"][i] = sum(len(s) for s in seeds), len(sd)
+        rec["overlay_off"][i], rec["overlay_n"][i] = sum(len(o) for o in ovs), len(ov)
+        rec["enemies"][i] = q.get("enemies", 0); rec["flags"][i] = flags
+        seeds.append(sd); ovs.append(ov)
+    sd = np.ascontiguousarray(np.concatenate(seeds) if seeds else np.zeros((0, 2), np.int32))
+    ov = np.ascontiguousarray(np.concatenate(ovs) if ovs else np.zeros((0, 2), np.int32))
+    return rec, sd, ov
+
+
 def pfmap_parse(text):
     """PFMAP text (bytes) -> int32[H32][W32][4] = {pathable, type, base_height, ramp_height} (global row-major)"""
     L = load()
@@ -344,25 +369,7 @@ class Nav:
     def region_fields(self, dim, reqs, layer=0, inout=None):
         """reqs: list of dicts {center, target | seeds, enemies, overlay, start, cell} in absolute tile coordinates
         (the shape tests/cases.region_case builds) -> u8[n, dim, dim/2]. One pfnav_region_fields call."""
-        rec = np.zeros(len(reqs), REGION_REQ)
-        seeds, ovs = [], []
-        for i, q in enumerate(reqs):
-            sd = np.asarray(q["seeds"] if q.get("seeds") is not None else [q["target"]], np.int32).reshape(-1, 2)
-            ov = np.asarray(q["overlay"] if q.get("overlay") is not None else np.zeros((0, 2)), np.int32).reshape(-1, 2)
-            flags = 0 if q.get("no_create") else REGION_CREATE
-            if q.get("cell", q.get("seeds") is None):
-                flags |= REGION_CELL
-            if q.get("start") is not None:
-                flags |= REGION_FIXUP
-                rec["start_r"][i], rec["start_c"][i] = q["start"]
-            rec["layer"][i] = layer
-            rec["center_r"][i], rec["center_c"][i] = q["center"]
-            rec["seed_off"][i], rec["seed_n"][i] = sum(len(s) for s in seeds), len(sd)
-            rec["overlay_off"][i], rec["overlay_n"][i] = sum(len(o) for o in ovs), len(ov)
-            rec["enemies"][i] = q.get("enemies", 0); rec["flags"][i] = flags
-            seeds.append(sd); ovs.append(ov)
-        sd = np.ascontiguousarray(np.concatenate(seeds) if seeds else np.zeros((0, 2), np.int32))
-        ov = np.ascontiguousarray(np.concatenate(ovs) if ovs else np.zeros((0, 2), np.int32))
+        rec, sd, ov = pack_region_reqs(reqs, layer)
         buf = (np.zeros((len(reqs), dim, dim // 2), np.uint8) if inout is None
                else np.ascontiguousarray(inout, np.uint8).reshape(len(reqs), dim, dim // 2).copy())
         _chk(self.L.pfnav_region_fields(self.h, dim, _p(rec), len(rec), _p(sd) if len(sd) else None, len(sd),
