@@ -61,23 +61,31 @@ __device__ __forceinline__ void region_gather(const RegionGrids &g, const Region
 __device__ __forceinline__ void region_relax(const RegionSmem &s)
 {
     const int dim = s.dim, N = s.N;
-    const int per = (N + RG_THREADS - 1) / RG_THREADS;
+    // a thread owns `per` consecutive cells; per is made odd so that the lanes of a warp, which walk their runs in
+    // lock step, hit 32 different shared-memory banks (an even run length of 36 or 64 words is a 4- / 32-way conflict)
+    const int per = ((N + RG_THREADS - 1) / RG_THREADS) | 1;
     const int lo = min((int)threadIdx.x * per, N), hi = min(lo + per, N);
+    // (row, column) of the run's first and last cell; the sweeps step them instead of dividing per cell
+    const int r_lo = lo / dim, c_lo = lo - r_lo * dim;
+    const int last = hi > lo ? hi - 1 : lo, r_hi = last / dim, c_hi = last - r_hi * dim;
     bool fwd = true;
     while (true) {
         bool changed = false;
+        int i = fwd ? lo : hi - 1, r = fwd ? r_lo : r_hi, c = fwd ? c_lo : c_hi;
         for (int k = 0; k < hi - lo; k++) {
-            const int i = fwd ? lo + k : hi - 1 - k;
-            if (!(s.flg[i] & RG_ENT)) continue;
-            const int r = i / dim, c = i - r * dim;
-            uint32_t m = RG_INF;
-            if (r > 0) m = min(m, s.dist[i - dim]);
-            if (r < dim - 1) m = min(m, s.dist[i + dim]);
-            if (c > 0) m = min(m, s.dist[i - 1]);
-            if (c < dim - 1) m = min(m, s.dist[i + 1]);
-            if (m == RG_INF) continue;
-            const uint32_t nd = m + s.cst[i];
-            if (nd < s.dist[i]) { s.dist[i] = nd; changed = true; }
+            if (s.flg[i] & RG_ENT) {
+                uint32_t m = RG_INF;
+                if (r > 0) m = min(m, s.dist[i - dim]);
+                if (r < dim - 1) m = min(m, s.dist[i + dim]);
+                if (c > 0) m = min(m, s.dist[i - 1]);
+                if (c < dim - 1) m = min(m, s.dist[i + 1]);
+                if (m != RG_INF) {
+                    const uint32_t nd = m + s.cst[i];
+                    if (nd < s.dist[i]) { s.dist[i] = nd; changed = true; }
+                }
+            }
+            if (fwd) { i++; if (++c == dim) { c = 0; r++; } }
+            else     { i--; if (--c < 0) { c = dim - 1; r--; } }
         }
         fwd = !fwd;
         if (!__syncthreads_or(changed)) break;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_region_fields(RegionGrids g, 
                     // field_passable_frontier (field.c:1441) as a reachability fixed point
                     if (tid == 0) s.flg[sr * dim + sc] |= (s.flg[sr * dim + sc] & RG_PASSP) ? RG_SEED : RG_COMP;
                     __syncthreads();
-                    const int per = (N + RG_THREADS - 1) / RG_THREADS;
+                    const int per = ((N + RG_THREADS - 1) / RG_THREADS) | 1;
                     const int lo = min(tid * per, N), hi = min(lo + per, N);
                     bool fwd = true;
                     while (true) {
