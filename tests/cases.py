@@ -374,3 +374,20 @@ def enemies_of(faction, wars, factions, flags):
     """field_enemy_ent (field.c:963) with fog disabled: other faction, COMBATABLE, at war"""
     foes = [b if a == faction else a for a, b in wars if faction in (a, b)]
     return np.isin(factions, foes) & ((flags & (1 << 4)) != 0)
+
+
+def stress_layout(army=256, spacing=12.0):
+    """the unit layout of the reference's own stress test (scripts/test_stress.py:73-121): two armies of `army` units in
+    4 rows on the 4 x 4-chunk plain map centred at the origin, red (selection radius 3.25) attacking (-100, 0), blue
+    (3.00) attacking (+100, 0). -> pos[2 * army, 2], radius, flock_of, targets[2, 2]"""
+    import math
+    nrows = 4; ncols = math.ceil(army / nrows)
+    red, blue = [], []
+    for r in range(int(-nrows // 2), int(nrows // 2 + nrows % 2)):
+        for c in range(int(-ncols // 2), int(ncols // 2 + ncols % 2)):
+            red.append((-(r * spacing) + 35.0, c * spacing))
+            blue.append(((r * spacing) - 35.0, c * spacing))
+    pos = np.array(red + blue, np.float32)
+    radius = np.concatenate([np.full(len(red), 3.25, np.float32), np.full(len(blue), 3.0, np.float32)])
+    flock_of = np.concatenate([np.zeros(len(red), np.int32), np.ones(len(blue), np.int32)])
+    return pos, radius, flock_of, np.array([[-100.0, 0.0], [100.0, 0.0]], np.float32)

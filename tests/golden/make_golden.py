@@ -441,7 +441,80 @@ def gen_targets():
 
 
 
+def gen_stress():
+    """The reference's own stress scenario (scripts/test_stress.py): assets/maps/plain.pfmap centred at the origin
+    (M_CenterAtOrigin, map.c:420: pos = (+512, 0, -512)), 2 x 256 units marching at each other. One movement tick:
+    both path requests (flow + LOS fields of the field cache), vdes / LOS per unit, the velocity pass. Units start with
+    half their speed towards the goal (+ seeded jitter) so that the obstacle avoidance has moving neighbours."""
+    text = open("/root/reference/assets/maps/plain.pfmap", "rb").read()
+    tiles = capi.pfmap_parse(text)
+    ch, cw = tiles.shape[0] // 32, tiles.shape[1] // 32
+    mx, mz = cw * 256 / 2.0, -(ch * 256 / 2.0)
+    ref = pfref.RefMap(cw, ch, tiles=tiles, map_x=mx, map_z=mz)
+    pos, radius, flock_of, targets = cases.stress_layout()
+    n = len(pos)
+    rng = np.random.default_rng(12)
+    d = targets[flock_of] - pos
+    vel = (d / np.maximum(np.sqrt((d * d).sum(1, keepdims=True)), 1e-6) * (0.5 * 20.0 / 20)).astype(np.float32)
+    vel = (vel + (rng.random((n, 2)).astype(np.float32) - 0.5) * np.float32(0.05)).astype(np.float32)
+    a = dict(pos=pos, prev_pos=(pos - vel).astype(np.float32), vel=vel, radius=radius, max_speed=np.full(n, 20.0, np.float32),
+             speed=np.full(n, 20.0, np.float32), state=np.zeros(n, np.int32), flags=np.full(n, 1 << 3, np.uint32),
+             flock_of=flock_of, flock_target=targets)
+    nc = cw * ch
+    dest_ids, oks, ffids, flows, loss, has, srcs = [], [], [], [], [], [], []
+    for f in range(2):
+        src = pos[np.argmax(flock_of == f)]
+        ref.fc_clear()
+        ok, did = ref.request_path((float(src[0]), float(src[1])), (float(targets[f][0]), float(targets[f][1])))
+        assert ok
+        fid = np.zeros(nc, np.uint64); hs = np.zeros(nc, np.uint8)
+        fl = np.zeros((nc, 64, 64), np.uint8); ls = np.zeros((nc, 64, 64), np.uint8)
+        for c in range(nc):
+            ff, k = ref.fc_flow(did, (c // cw, c % cw)); lf = ref.fc_los(did, (c // cw, c % cw))
+            if ff is not None:
+                fl[c] = ff; fid[c] = k; hs[c] |= 1
+            if lf is not None:
+                ls[c] = lf; hs[c] |= 2
+        dest_ids.append(did); oks.append(ok); ffids.append(fid); flows.append(fl); loss.append(ls); has.append(hs); srcs.append(src)
+    ref.fc_clear()
+    for f in range(2):
+        ref.request_path((float(srcs[f][0]), float(srcs[f][1])), (float(targets[f][0]), float(targets[f][1])))
+    ref.agents_set(a["pos"], a["prev_pos"], a["vel"], a["radius"], a["max_speed"], a["state"], a["flags"],
+                   a["flock_of"], a["flock_target"], np.array(dest_ids, np.uint32), hz=20)
+    work = np.arange(n, dtype=np.uint32)
+    vdes = np.zeros((n, 2), np.float32); los = np.zeros(n, np.uint8)
+    for _pass in range(2):
+        for f in range(2):
+            sel = np.nonzero(flock_of == f)[0]
+            v, l = ref.desired_velocity(dest_ids[f], pos[sel], a["prev_pos"][sel], targets[f])
+            vdes[sel] = v; los[sel] = l
+    # the settled field cache (what the second pass read)
+    pool_chunks, pool_flow, pool_los = [], [], []
+    for f in range(2):
+        for c in range(nc):
+            ff, _ = ref.fc_flow(dest_ids[f], (c // cw, c % cw)); lf = ref.fc_los(dest_ids[f], (c // cw, c % cw))
+            if ff is None and lf is None:
+                continue
+            pool_chunks.append((f, c // cw, c % cw, ff is not None, lf is not None))
+            pool_flow.append(ff if ff is not None else np.zeros((64, 64), np.uint8))
+            pool_los.append(lf if lf is not None else np.zeros((64, 64), np.uint8))
+    ref.work_set(work, vdes, los, a["speed"][work])
+    vel_out, _ = ref.velocity_work(1)
+    vpref = ref.vpref()
+    print("stress: %d units, map origin (%.0f, %.0f), units with LOS %d, zero vdes %d, zero new velocity %d, pool fields %d" % (
+        n, mx, mz, int(los.sum()), int((np.abs(vdes).sum(1) == 0).sum()), int((np.abs(vel_out).sum(1) == 0).sum()), len(pool_chunks)))
+    np.savez_compressed(os.path.join(HERE, "stress.npz"), tiles=tiles.astype(np.int8), cost=ref.cost_base(), liid=ref.local_islands(),
+                        islands=ref.islands(), map_origin=np.array([mx, mz], np.float32),
+                        **{"a_" + k: v for k, v in a.items()}, work=work, vdes=vdes, los=los, vel=vel_out, vpref=vpref,
+                        pairs=np.array([[srcs[f], targets[f]] for f in range(2)], np.float32), ok=np.array(oks), did=np.array(dest_ids, np.uint32),
+                        ffid=np.array(ffids), flow=np.array(flows), los_f=np.array(loss), has=np.array(has),
+                        pool_chunks=np.array(pool_chunks, np.int32), pool_flow=np.array(pool_flow, np.uint8), pool_los=np.array(pool_los, np.uint8))
+    ref.close()
+
+
+
 if __name__ == "__main__":
+    gen_stress()
     gen_targets()
     gen_demo_map()
     gen_region()

@@ -808,3 +808,36 @@ def test_entity_and_enemies_fields_golden(nav):
             sel = cases.enemies_of(f, wars, g["factions"], g["flags"])
             got = nav.entity_fields(capi.TARGET_ENEMIES, fp[sel], allchunks, layer=slot, ref_layer=L)
             assert (got == g["foe_%d" % L][f]).all(), (L, f)
+
+
+def test_stress_scenario_golden(nav):
+    """the reference's stress test layout on its plain map centred at the origin (map position (+512, -512)): PFMAP
+    ingestion, both path requests into the pool, one tick with vdes / LOS from the pool, vs the compiled reference"""
+    g = gold("stress")
+    mx, mz = [float(v) for v in g["map_origin"]]
+    nav.map_load_pfmap(capi.pfmap_write(g["tiles"].astype(np.int32)), (0,), mx, mz)
+    cost, _, liid = nav.map_get_layer(0)
+    assert (cost == g["cost"]).all() and (liid == g["liid"]).all()
+    nav.route_build(0)
+    nav.pool_create(2, 32)
+    for f, (src, dst) in enumerate(g["pairs"]):
+        ok, did, nf, nl = nav.pool_request_path(f, tuple(src), tuple(dst))
+        assert ok and did == int(g["did"][f])
+        for c in range(16):
+            fl_, lo_, ffid = nav.pool_get(f, (c // 4, c % 4))
+            assert (fl_ is not None) == bool(g["has"][f][c] & 1) and (lo_ is not None) == bool(g["has"][f][c] & 2), (f, c)
+            if fl_ is not None:
+                assert ffid == int(g["ffid"][f][c]) and (fl_ == g["flow"][f][c]).all(), (f, c)
+            if lo_ is not None:
+                assert (lo_ == g["los_f"][f][c]).all(), (f, c)
+    a = {k[2:]: g[k] for k in g.files if k.startswith("a_")}
+    rec, fl = capi.pack_agents(a)
+    nav.agents_upload(rec, fl, 20)
+    nav.agents_set_work(g["work"])
+    nav.agents_tick(capi.TICK_VDES_FROM_POOL)
+    vel = nav.agents_read_velocities(len(g["work"]))
+    vpref, vdes, los = nav.agents_read_debug(len(g["work"]))
+    assert (los == g["los"]).all()
+    assert (vdes == g["vdes"]).all()
+    assert (cases.relerr(vpref, g["vpref"]) <= VEL_RTOL).all()
+    assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995

@@ -510,6 +510,32 @@ def test_demo_map_nav_build_golden(pforacle):
     nav.close()
 
 
+def test_stress_scenario_golden(pforacle):
+    """the reference's own stress test (scripts/test_stress.py) on its plain map CENTRED AT THE ORIGIN (map position
+    (+512, -512), M_CenterAtOrigin map.c:420): both path requests (planner + port fields), vdes / LOS per unit out of the
+    settled field cache, and the velocity pass of 512 units"""
+    g = gold("stress")
+    mx, mz = [float(v) for v in g["map_origin"]]
+    assert (pforacle.cost_from_tiles(4, 4, g["tiles"].astype(np.int32), 0) == g["cost"]).all()
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(4, 4, 1, mx, mz); nav.map_upload_layer(0, g["cost"]); nav.map_build_nav(0); nav.route_build(0)
+    assert (nav.local_islands(0) == g["liid"]).all() and (nav.route_islands(0) == g["islands"]).all()
+    om = pforacle.OracleMap(4, 4, g["cost"], None, g["liid"], map_x=mx, map_z=mz)
+    _check_route_against(nav, om, 4, 4, g["pairs"], g["ok"], g["did"], g["ffid"], g["flow"], g["los_f"], g["has"])
+    nav.close()
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    slot = np.full(2 * 16, -1, np.int32)
+    for k, (f, cr, cc, hf, hl) in enumerate(g["pool_chunks"]):
+        slot[f * 16 + cr * 4 + cc] = k
+    vdes, los = om.desired_velocity(rec, fl, g["work"], slot, g["pool_flow"], g["pool_los"])
+    assert (los == g["los"]).all() and (vdes == g["vdes"]).all()
+    w = pforacle.OracleWorld(om, rec, fl, 20)
+    vel, vpref = w.velocity_work(g["work"])
+    assert cases.relerr(vpref, g["vpref"]).max() <= 1e-4 and cases.relerr(vel, g["vel"]).max() <= 1e-4
+    w.close()
+
+
 def test_route_request_path_vs_ref(pfref, pforacle):
     cw = ch = 4
     p = cases.noise_map(cw, ch, 91, 0.1)
