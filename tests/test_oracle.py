@@ -646,6 +646,39 @@ def test_blockers_obb_vs_ref(pfref):
     ref.close(); nav.close()
 
 
+def test_map_origin_blockers_and_fields_vs_ref(pfref, pforacle):
+    """a map that is not at the origin (the engine centres its maps, map.c:420) and is not square: circle + OBB
+    blockers on the four ground layers, islands, faction counts, world-space group arrival fields"""
+    cw, ch, mx, mz = 4, 3, 512.0, -384.0
+    p = cases.noise_map(cw, cw, 17, 0.1)[:ch * 32]
+    ref = pfref.RefMap(cw, ch, p, map_x=mx, map_z=mz)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 4, mx, mz)
+    for L in range(4):
+        nav.map_upload_layer(L, ref.cost_base(L)); nav.map_build_nav(L)
+    rng = np.random.default_rng(5)
+    for _ in range(80):
+        x, z, r, f = mx - rng.uniform(6, cw * 256 - 6), mz + rng.uniform(6, ch * 256 - 6), rng.uniform(1, 14), int(rng.integers(0, 4))
+        ref.blockers_incref(float(x), float(z), float(r), f, 0); nav.blockers_incref(float(x), float(z), float(r), f, 0)
+    for _ in range(12):
+        c = np.array([mx - rng.uniform(40, cw * 256 - 40), mz + rng.uniform(40, ch * 256 - 40)])
+        ang, hx, hz = rng.uniform(0, np.pi), rng.uniform(4, 30), rng.uniform(4, 30)
+        ax, az = np.array([np.cos(ang), np.sin(ang)]), np.array([-np.sin(ang), np.cos(ang)])
+        corners = np.array([c - ax * hx - az * hz, c + ax * hx - az * hz, c + ax * hx + az * hz, c - ax * hx + az * hz], np.float32)
+        ref.blockers_obb(corners, True, 1, 0); nav.blockers_obb(corners, True, 1, 0)
+    ref.update(); nav.map_commit()
+    for L in range(4):
+        assert (nav.blockers(L) == ref.blockers(L)).all(), L
+        assert (nav.local_islands(L) == ref.local_islands(L)).all(), L
+        assert (nav.faction_counts(L) == ref.factions(L)).all(), L
+    om = pforacle.OracleMap(cw, ch, ref.cost_base(0), ref.blockers(0), None, map_x=mx, map_z=mz)
+    for _ in range(12):
+        c = (mx - rng.uniform(-5, cw * 256 + 5), mz + rng.uniform(-5, ch * 256 + 5))
+        t = np.stack([c[0] + rng.uniform(-200, 200, 10), c[1] + rng.uniform(-200, 200, 10)], 1)
+        assert (ref.group_arrival_field(96, t, c) == om.group_arrival_field(96, 0, t, c)).all()
+    ref.close(); nav.close()
+
+
 def test_map_create_drops_state_of_previous_map():
     """dirty sets / routes / per-faction counts of an earlier, larger map must not leak into the next one"""
     nav = capi.Nav(hostonly=True)
