@@ -1171,8 +1171,6 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-static uint8_t *g_dummy = nullptr;
-
 void pfnav_agents_free(pfnav_ctx *ctx)
 {
     cudaFree(ctx->d_agents); cudaFree(ctx->d_records); cudaFree(ctx->d_flocks);

@@ -616,7 +616,6 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
     if (dst_port < 0) return PFNAV_OK;
     std::vector<Router::hop> path;
     float cost;
-    int dst_port_chunk = dchunk;
     bool exists = R.portal_graph_path(src, dst, dchunk, dst_port, path, &cost);
     if (!exists) {
         const tdesc orig = dst;
@@ -631,7 +630,6 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
         if (src.chunk_r == dst.chunk_r && src.chunk_c == dst.chunk_c) *out_ok = 1;
         return PFNAV_OK;
     }
-    (void)dst_port_chunk;
     int prev_los_chunk = dst.chunk_r * cw + dst.chunk_c;
     const uint16_t dst_liid_now = R.closest_pathable_liid(dchunk, {dst.tile_r, dst.tile_c});
     // walk the portal path backwards (nav.c:1941-2042)

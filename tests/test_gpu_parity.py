@@ -830,14 +830,37 @@ def test_stress_scenario_golden(nav):
                 assert ffid == int(g["ffid"][f][c]) and (fl_ == g["flow"][f][c]).all(), (f, c)
             if lo_ is not None:
                 assert (lo_ == g["los_f"][f][c]).all(), (f, c)
+    # the tick reads the SETTLED field cache of the reference (its per-unit on-miss requests have added the chunks the
+    # two requests above never touched): first put exactly those fields, then let the on-miss chain rebuild them
     a = {k[2:]: g[k] for k in g.files if k.startswith("a_")}
     rec, fl = capi.pack_agents(a)
+    n = len(g["work"])
+
+    def tick_and_check(tag):
+        nav.agents_tick(capi.TICK_VDES_FROM_POOL)
+        vel = nav.agents_read_velocities(n)
+        vpref, vdes, los = nav.agents_read_debug(n)
+        assert (los == g["los"]).all(), tag
+        assert (vdes == g["vdes"]).all(), tag
+        assert (cases.relerr(vpref, g["vpref"]) <= VEL_RTOL).all(), tag
+        assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995, tag
+
+    nav.pool_create(2, 32)
+    for k, (f, cr, cc, hf, hl) in enumerate(g["pool_chunks"]):
+        nav.pool_put(int(f), (int(cr), int(cc)), g["pool_flow"][k] if hf else None, g["pool_los"][k] if hl else None)
     nav.agents_upload(rec, fl, 20)
     nav.agents_set_work(g["work"])
-    nav.agents_tick(capi.TICK_VDES_FROM_POOL)
-    vel = nav.agents_read_velocities(len(g["work"]))
-    vpref, vdes, los = nav.agents_read_debug(len(g["work"]))
-    assert (los == g["los"]).all()
-    assert (vdes == g["vdes"]).all()
-    assert (cases.relerr(vpref, g["vpref"]) <= VEL_RTOL).all()
-    assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995
+    tick_and_check("settled cache put")
+    nav.pool_create(2, 32)
+    for f, (src, dst) in enumerate(g["pairs"]):
+        assert nav.pool_request_path(f, tuple(src), tuple(dst))[0]
+    for _ in range(6):
+        nav.agents_tick(capi.TICK_VDES_FROM_POOL)
+        nreq, nrep = nav.pool_repair()
+        if nreq + nrep == 0:
+            break
+    for k, (f, cr, cc, hf, hl) in enumerate(g["pool_chunks"]):
+        fl_, lo_, _ = nav.pool_get(int(f), (int(cr), int(cc)))
+        assert (fl_ is not None) == bool(hf) and (lo_ is not None) == bool(hl), (f, cr, cc)
+        assert (not hf or (fl_ == g["pool_flow"][k]).all()) and (not hl or (lo_ == g["pool_los"][k]).all()), (f, cr, cc)
+    tick_and_check("on-miss chain")
