@@ -91,3 +91,28 @@ def test_chunk_window_kernel_source_on_cpu_threads(emu, pforacle):
         got = _run(emu, cost, blk, fmask, 128, rec, np.concatenate(sds).astype(np.int32), np.zeros((0, 2), np.int32),
                    np.full((cw * ch, 64, 64), 0xEE, np.uint8), 1)
         assert (got == g["zexp"][k]).all(), k
+
+
+@pytest.mark.parametrize("seed,dim,n", [(92, 64, 40), (93, 128, 16), (94, 96, 60)])
+def test_region_kernel_source_vs_port(emu, pforacle, seed, dim, n):
+    """further window sizes (incl. PFNAV_REGION_DIM_MAX) and a 4 x 4-chunk map: kernel source on CPU threads vs the port"""
+    cw = ch = 4
+    p, blockers, wars, reqs = cases.region_case(seed, cw, ch, n, dim)
+    cost_c = synth.cost_from_pathable(p, cw, ch)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost_c); nav.map_build_nav(0)
+    for x, z, r, f in blockers:
+        nav.blockers_incref(float(x), float(z), float(r), int(f), 0)
+    nav.map_commit()
+    blk_c, fac = nav.blockers(0), nav.faction_counts(0)
+    nav.close()
+    cases.region_pick_starts(reqs, cost_c, blk_c, cw, ch, seed, dim)
+    om = pforacle.OracleMap(cw, ch, cost_c, blk_c, None, factions=fac)
+    rec, sd, ov = capi.pack_region_reqs(reqs)
+    got = _run(emu, _image(cost_c, cw, ch), _image(blk_c, cw, ch), _fmask(fac, cw, ch), dim, rec, sd, ov,
+               np.zeros((len(reqs), dim, dim // 2), np.uint8), 0)
+    for i, q in enumerate(reqs):
+        e = om.region_field_create(dim, q["enemies"], 1, [q["target"]], q["center"], q["overlay"])
+        if q["start"] is not None:
+            e = om.region_field_fixup(dim, q["start"], q["center"], e, q["overlay"])
+        assert (got[i] == e).all(), (seed, dim, i, q)
