@@ -64,7 +64,7 @@ def gen_agents(name, cw, n, nflocks, seed, dens, spacing):
                    a["flock_of"], a["flock_target"], np.array(dest_ids, np.uint32), hz=20)
     work = np.nonzero((a["state"] != 2) & (a["state"] != 4))[0].astype(np.uint32)
     vdes = np.zeros((len(work), 2), np.float32); los = np.zeros(len(work), np.uint8)
-    for _pass in range(2):       # pass 0 settles the reference's field cache (see tools/gpu_check.py)
+    for _pass in range(2):       # pass 0 settles the reference's field cache (see tests/tools/gpu_check.py)
         for f in range(nflocks):
             sel = np.nonzero(a["flock_of"][work] == f)[0]
             if len(sel) == 0:

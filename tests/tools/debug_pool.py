@@ -2,7 +2,7 @@
 """GPU debug: batched pfnav_pool_request_goals vs the oracle port executing the same plan."""
 import importlib, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import bench, pforacle
 pf = importlib.import_module("permafrost-engine_b200"); capi, synth = pf.capi, pf.synth

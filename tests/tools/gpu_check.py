@@ -3,7 +3,7 @@
 Prints mismatch statistics; exits non-zero on any integer mismatch."""
 import importlib, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 pf = importlib.import_module("permafrost-engine_b200")
 import pfref
