@@ -95,6 +95,9 @@ class RefMap:
             self.h = lib().pfref_map_new(chunk_w, chunk_h, _p(pathable), map_x, map_z)
         if not self.h:
             raise RuntimeError("pfref_map_new failed")
+        for a in range(15):                     # the harness's war matrix is process-global: every map starts at peace
+            for b in range(a + 1, 15):
+                lib().pfref_set_war(a, b, 0)
 
     def close(self):
         if self.h:
