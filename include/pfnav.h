@@ -516,6 +516,12 @@ typedef struct pfnav_patch {            /* struct movestate_patch (movement.c:24
     float    _padf[3];
 } pfnav_patch;                          /* 128 bytes */
 
+/* Inspection / test entry: the two map searches of arrived() (movement.c:2170) for a flock target on `layer`, as
+ * pfnav_agents_compute_updates precomputes them per (flock, layer): N_ClosestPathable (nav.c:4126) and the tile
+ * centres N_IsMaximallyClose compares with (nav.c:4707). out_mc_xz: up to cap (x, z) pairs. Host code; needs
+ * pfnav_route_build(layer). */
+int  pfnav_route_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, int32_t *out_nearest_ok,
+                                float *out_nearest_xz, float *out_mc_xz, size_t cap, int32_t *out_mc_n);
 /* HOST array of n_agents records, uid == index. */
 int  pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movestate *ms, size_t n);
 /* After pfnav_agents_tick on the same stream: entity_compute_update for every work item, reading the

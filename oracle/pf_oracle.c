@@ -1423,3 +1423,225 @@ void pfo_group_arrival_velocity(const pfo_map *m, const uint8_t *fields, const u
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * State update: entity_compute_update (game/movement.c:2303-2650) for the point-seek states, no formation and
+ * no arrival group. The quaternion helpers keep the reference's mix of float and double arithmetic (pf_math.c).
+ * The map of the world holds ONE layer: it stands for the layer Entity_NavLayerWithRadius picks (entity.c:554).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float x, y, z, w; } pquat;
+#define PFO_PI_D 3.14159265358979323846
+#define PFO_HIST 14
+
+/* first column of PFM_Mat4x4_RotFromQuat (pf_math.c:324) applied to (1,0,0,1), as PFM_Quat_PitchDiff uses it (:677) */
+static void quat_front(pquat q, float *dx, float *dz)
+{
+    *dx = (float)(1 - 2 * ((double)q.y * (double)q.y) - 2 * ((double)q.z * (double)q.z));
+    *dz = 2 * q.x * q.z + 2 * q.w * q.y;
+}
+static float quat_pitch_diff(pquat a, pquat b)            /* PFM_Quat_PitchDiff (pf_math.c:677-704) */
+{
+    float ax, az, bx, bz;
+    quat_front(a, &ax, &az); quat_front(b, &bx, &bz);
+    const float dot = ax * bx + az * bz, det = ax * bz - az * bx;
+    return (float)atan2((double)det, (double)dot);
+}
+static pquat dir_quat_from_velocity(v2 v)                  /* movement.c:1411 */
+{
+    const float angle_rad = (float)(atan2((double)v.z, (double)v.x) - PFO_PI_D / 2.0f);
+    pquat q = {0.0f, (float)(1.0f * sin((double)(angle_rad / 2.0f))), 0.0f, (float)cos((double)(angle_rad / 2.0f))};
+    return q;
+}
+/* turn_toward (movement.c:2249): PFM_Mat4x4_MakeRotY -> PFM_Quat_FromRotMat -> PFM_Quat_MultQuat -> PFM_Quat_Normal */
+static pquat turn_toward(pquat cur, pquat target, float max_deg)
+{
+    float angle_deg = (float)((double)quat_pitch_diff(cur, target) * (180.0f / PFO_PI_D));
+    if(180.0f - fabs((double)angle_deg) < 1.0f) angle_deg = 180.0f;
+    const double mn = ((double)max_deg < fabs((double)angle_deg)) ? (double)max_deg : fabs((double)angle_deg);
+    const int sg = (angle_deg > 0) - (angle_deg < 0);
+    const float turn_deg = (float)(mn * -sg);
+    const float radians = (float)((double)turn_deg * (PFO_PI_D / 180.0f));
+    const float c = (float)cos((double)radians), sn = (float)sin((double)radians);
+    const float m00 = c, m02 = -sn, m20 = sn, m22 = c, m11 = 1.0f;
+    pquat rot;
+    const float tr = m00 + m11 + m22;
+    if(tr > 0) {
+        const float S = (float)(sqrt((double)tr + 1.0) * 2);
+        rot.w = (float)(0.25 * (double)S); rot.x = (0.0f - 0.0f) / S; rot.y = (m02 - m20) / S; rot.z = (0.0f - 0.0f) / S;
+    }else if((m00 > m11) && (m00 > m22)) {
+        const float S = (float)(sqrt(1.0 + (double)m00 - (double)m11 - (double)m22) * 2);
+        rot.w = (0.0f - 0.0f) / S; rot.x = (float)(0.25 * (double)S); rot.y = (0.0f + 0.0f) / S; rot.z = (m02 + m20) / S;
+    }else if(m11 > m22) {
+        const float S = (float)(sqrt(1.0 + (double)m11 - (double)m00 - (double)m22) * 2);
+        rot.w = (m02 - m20) / S; rot.x = (0.0f + 0.0f) / S; rot.y = (float)(0.25 * (double)S); rot.z = (0.0f + 0.0f) / S;
+    }else{
+        const float S = (float)(sqrt(1.0 + (double)m22 - (double)m00 - (double)m11) * 2);
+        rot.w = (0.0f - 0.0f) / S; rot.x = (m02 + m20) / S; rot.y = (0.0f + 0.0f) / S; rot.z = (float)(0.25 * (double)S);
+    }
+    pquat f;                                                /* PFM_Quat_MultQuat(&rot, &cur) (pf_math.c:639) */
+    f.x = ( rot.x * cur.w) + (rot.y * cur.z) - (rot.z * cur.y) + (rot.w * cur.x);
+    f.y = (-rot.x * cur.z) + (rot.y * cur.w) + (rot.z * cur.x) + (rot.w * cur.y);
+    f.z = ( rot.x * cur.y) - (rot.y * cur.x) + (rot.z * cur.w) + (rot.w * cur.z);
+    f.w = (-rot.x * cur.x) - (rot.y * cur.y) - (rot.z * cur.z) + (rot.w * cur.w);
+    const float len = (float)sqrt((double)(f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w));
+    f.x = f.x / len; f.y = f.y / len; f.z = f.z / len; f.w = f.w / len;
+    return f;
+}
+
+enum { ST_MOVING = 0, ST_ARRIVED = 2, ST_SEEK_ENEMIES = 3, ST_WAITING = 4, ST_SURROUND = 5, ST_ENTER_RANGE = 6 };
+enum { UP_STATE = 1 << 0, UP_VELOCITY = 1 << 1, UP_POSITION = 1 << 2, UP_ROTATION = 1 << 3, UP_NEXT_POS = 1 << 4,
+       UP_PREV_POS = 1 << 5, UP_STEP = 1 << 6, UP_LEFT = 1 << 7, UP_NEXT_ROT = 1 << 8, UP_PREV_ROT = 1 << 9,
+       UP_TURNING_IN_PLACE = 1 << 14 };
+#define FL_WATER (1u << 14)
+#define FL_AIR (1u << 15)
+#define FL_GARRISONED (1u << 18)
+#define FL_COMBAT_HELD (1u << 21)
+
+void pfo_entity_updates(const pfo_world *w, const pfo_movestate *mss, const pfo_arrival *arr, const uint32_t *work, size_t nwork,
+                        const float *new_vel_xz, const float *vdes_xz, pfo_patch *out)
+{
+    const pfo_map *m = &w->map;
+    const float EPS = 1.0f / 1024;
+    const int H64 = m->chunk_h * RES, W64 = m->chunk_w * RES;
+    const float turn_rate = (float)((double)(15.0f / (float)w->hz) * 20.0);     /* SCALED_MAX_TURN_RATE (movement.c:434) */
+    for(size_t wi = 0; wi < nwork; wi++) {
+        const uint32_t uid = work[wi];
+        const pfo_agent *a = &w->agents[uid];
+        const pfo_movestate *ms = &mss[uid];
+        pfo_patch p;
+        memset(&p, 0, sizeof(p));
+        p.next_state = -1;
+        const pquat ms_rot = {ms->next_rot[0], ms->next_rot[1], ms->next_rot[2], ms->next_rot[3]};
+        v2 new_vel = {new_vel_xz[2 * wi], new_vel_xz[2 * wi + 1]};
+        const v2 vdes = {vdes_xz[2 * wi], vdes_xz[2 * wi + 1]};
+        const v2 ms_vel = {a->velocity[0], a->velocity[1]};
+        const v2 curr_xz = {a->pos[0], a->pos[1]};
+        const uint32_t state = a->state;
+
+        if(ms->left > 0) {                                   /* flush an unfinished interpolation (movement.c:2311) */
+            p.flags |= UP_POSITION | UP_ROTATION | UP_LEFT;
+            memcpy(p.next_pos, ms->next_pos, sizeof(p.next_pos));
+            p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+            p.next_left = 0;
+        }
+        bool turn_to_move = false;                           /* heading gate (movement.c:2323-2335) */
+        pquat travel_dir = ms_rot;
+        const bool gated = state == ST_MOVING || state == ST_SEEK_ENEMIES || state == ST_SURROUND || state == ST_ENTER_RANGE;
+        if(v2_len(new_vel) > EPS && gated) {
+            travel_dir = dir_quat_from_velocity(v2_len(vdes) > EPS ? vdes : new_vel);
+            const float heading_err = (float)fabs((double)quat_pitch_diff(ms_rot, travel_dir) * (180.0f / PFO_PI_D));
+            const float tolerance = (v2_len(ms_vel) > EPS) ? 90.0f : 10.0f;
+            if(heading_err > tolerance) { turn_to_move = true; new_vel = (v2){0.0f, 0.0f}; }
+        }
+        v2 new_pos_xz = v2_add(curr_xz, new_vel);
+        const bool still = state == ST_ARRIVED || state == ST_WAITING;
+        if(a->flags & FL_GARRISONED) {
+            if(!still) { p.flags |= UP_STATE; p.next_state = ST_ARRIVED; p.next_block = 0; }
+            out[wi] = p;
+            continue;
+        }
+        bool dummy, on_blocked, np_path, np_blocked;
+        probe(m, curr_xz.x, curr_xz.z, &dummy, &on_blocked);
+        probe(m, new_pos_xz.x, new_pos_xz.z, &np_path, &np_blocked);
+        if(v2_len(new_vel) > 0 && np_path && (on_blocked || !np_blocked)) {
+            /* unit_height (movement.c:2198) with M_HeightAtPoint == 0 (terrain height is render state) */
+            const float y = (a->flags & FL_WATER) ? 0.0f : (a->flags & FL_AIR) ? 20.0f : 0.0f;
+            p.flags |= UP_PREV_POS | UP_NEXT_POS | UP_STEP | UP_LEFT;
+            memcpy(p.next_ppos, ms->next_pos, sizeof(p.next_ppos));
+            p.next_npos[0] = new_pos_xz.x; p.next_npos[1] = y; p.next_npos[2] = new_pos_xz.z;
+            p.next_step = 1.0f / (20 / w->hz);
+            p.next_left = (float)((20 / w->hz) - 1);
+            p.flags |= UP_POSITION;
+            if((20 / w->hz) - 1 == 0) {
+                p.next_pos[0] = new_pos_xz.x; p.next_pos[1] = y; p.next_pos[2] = new_pos_xz.z;
+            }else{                                           /* interpolate_positions (movement.c:2221) */
+                float ix, iy, iz;
+                if(fabs(1.0 - (double)ms->step) < EPS) { ix = p.next_npos[0]; iy = p.next_npos[1]; iz = p.next_npos[2]; }
+                else {
+                    ix = p.next_ppos[0] + (p.next_npos[0] - p.next_ppos[0]) * ms->step;
+                    iy = p.next_ppos[1] + (p.next_npos[1] - p.next_ppos[1]) * ms->step;
+                    iz = p.next_ppos[2] + (p.next_npos[2] - p.next_ppos[2]) * ms->step;
+                }
+                new_pos_xz = (v2){ix, iz};
+                p.next_pos[0] = ix; p.next_pos[1] = iy; p.next_pos[2] = iz;
+            }
+            p.flags |= UP_VELOCITY;
+            p.next_velocity[0] = new_vel.x; p.next_velocity[1] = new_vel.z;
+            p.flags |= UP_PREV_ROT | UP_NEXT_ROT | UP_ROTATION;
+            p.next_prot[0] = ms_rot.x; p.next_prot[1] = ms_rot.y; p.next_prot[2] = ms_rot.z; p.next_prot[3] = ms_rot.w;
+            v2 wma = {0.0f, 0.0f};                           /* orient_to_velocity_history (:2291) over vel_wma (:2067) */
+            float denom = 0.0f;
+            for(int i = 0; i < PFO_HIST; i++) {
+                const int k = (ms->vel_hist_idx + i) % PFO_HIST;
+                const float wgt = (float)(PFO_HIST - i);
+                wma.x = wma.x + ms->vel_hist[k][0] * wgt;
+                wma.z = wma.z + ms->vel_hist[k][1] * wgt;
+                denom += wgt;
+            }
+            if(denom > EPS) { const float inv = 1.0f / denom; wma.x = wma.x * inv; wma.z = wma.z * inv; }
+            pquat nrot = ms_rot;
+            if(v2_len(wma) > EPS) nrot = turn_toward(ms_rot, dir_quat_from_velocity(wma), turn_rate);
+            p.next_nrot[0] = nrot.x; p.next_nrot[1] = nrot.y; p.next_nrot[2] = nrot.z; p.next_nrot[3] = nrot.w;
+            p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+        }else{
+            p.flags |= UP_VELOCITY;
+            p.next_velocity[0] = 0.0f; p.next_velocity[1] = 0.0f;
+            const bool held = (a->flags & FL_COMBAT_HELD) != 0;
+            if(held || turn_to_move) {
+                p.flags |= UP_PREV_ROT | UP_NEXT_ROT | UP_ROTATION | UP_TURNING_IN_PLACE;
+                const pquat cf = {ms->combat_facing[0], ms->combat_facing[1], ms->combat_facing[2], ms->combat_facing[3]};
+                const pquat nrot = turn_toward(ms_rot, held ? cf : travel_dir, turn_rate);
+                p.next_prot[0] = ms_rot.x; p.next_prot[1] = ms_rot.y; p.next_prot[2] = ms_rot.z; p.next_prot[3] = ms_rot.w;
+                p.next_nrot[0] = nrot.x; p.next_nrot[1] = nrot.y; p.next_nrot[2] = nrot.z; p.next_nrot[3] = nrot.w;
+                p.next_rot[0] = ms_rot.x; p.next_rot[1] = ms_rot.y; p.next_rot[2] = ms_rot.z; p.next_rot[3] = ms_rot.w;
+            }
+        }
+        bool cur_path, cur_blk;                              /* stuck on non-pathable terrain: keep the state (:2417) */
+        probe(m, new_pos_xz.x, new_pos_xz.z, &cur_path, &cur_blk);
+        if(!cur_path || a->flock < 0 || state != ST_MOVING) { out[wi] = p; continue; }
+
+        /* STATE_MOVING (movement.c:2421-2495) */
+        const pfo_flock *fl = &w->flocks[a->flock];
+        const pfo_arrival *ac = &arr[a->flock];
+        bool arrived = false;
+        {   /* arrived() (movement.c:2170) */
+            const v2 tgt = {fl->target[0], fl->target[1]};
+            const float thresh = a->radius * 1.5f;
+            if(v2_len(v2_sub(tgt, new_pos_xz)) < thresh) arrived = true;
+            if(!arrived) {                                   /* N_IsAdjacentToImpassable (nav.c:4745) && N_IsMaximallyClose (:4707) */
+                tdesc td; bool adj = false;
+                if(desc_for_point(m, new_pos_xz.x, new_pos_xz.z, &td)) {
+                    const int ar = td.chunk_r * RES + td.tile_r, acol = td.chunk_c * RES + td.tile_c;
+                    static const int dr[4] = {-1, 0, 0, 1}, dc[4] = {0, -1, 1, 0};
+                    for(int e = 0; e < 4 && !adj; e++) {
+                        const int nr = ar + dr[e], nc = acol + dc[e];
+                        if(nr < 0 || nr >= H64 || nc < 0 || nc >= W64) continue;
+                        adj = !abs_passable(m, nr, nc);
+                    }
+                }
+                if(adj)
+                    for(int i = 0; i < ac->mc_n && !arrived; i++) {
+                        const v2 d = {ac->mc[2 * i] - new_pos_xz.x, ac->mc[2 * i + 1] - new_pos_xz.z};
+                        if(v2_len(d) <= thresh) arrived = true;
+                    }
+            }
+            if(!arrived && ac->nearest_ok) {                 /* N_ClosestPathable (nav.c:4126) */
+                const v2 d = {ac->nearest[0] - new_pos_xz.x, ac->nearest[1] - new_pos_xz.z};
+                if(v2_len(d) < thresh) arrived = true;
+            }
+        }
+        if(!arrived) {
+            /* adjacent_flock_members (movement.c:953): a flock member within r + r' + ADJACENCY_SEP_DIST that has ARRIVED */
+            for(size_t o = 0; o < w->n && !arrived; o++) {
+                if(o == uid) continue;
+                const pfo_agent *b = &w->agents[o];
+                if(b->state != ST_ARRIVED || b->flock != a->flock) continue;
+                const v2 d = {curr_xz.x - b->pos[0], curr_xz.z - b->pos[1]};
+                if(v2_len(d) <= a->radius + b->radius + 5.0f) arrived = true;
+            }
+        }
+        if(arrived) { p.flags |= UP_STATE; p.next_state = ST_ARRIVED; p.next_block = 1; }
+        else if(v2_len(vdes) < EPS) { p.flags |= UP_STATE; p.next_state = ST_WAITING; p.next_block = 1; }
+        out[wi] = p;
+    }
+}

@@ -90,6 +90,21 @@ void pfo_group_arrival_field(const pfo_map *m, int dim, uint16_t enemies, const 
                              const float *center_xz, const int32_t *overlay, int noverlay, uint8_t *out);
 void pfo_region_field_update_to_nearest_pathable(const pfo_map *m, int dim, int start_r, int start_c, int center_r, int center_c,
                                                  const int32_t *overlay, int noverlay, uint8_t *inout);
+/* State update: entity_compute_update (movement.c:2303-2650) for the point-seek states. Records are layout-identical to
+ * pfnav_movestate / pfnav_patch. arr[flock]: the two map searches of arrived() (movement.c:2170) for the flock's target:
+ * N_ClosestPathable (nav.c:4126) and the tile centres N_IsMaximallyClose compares with (nav.c:4707, n_closest_island_tiles
+ * :1226), mc = 2 floats per tile. out: one patch per work item. */
+typedef struct pfo_movestate {
+    float next_pos[3], step, next_rot[4], combat_facing[4], vel_hist[14][2];
+    int32_t left, vel_hist_idx, _pad[2];
+} pfo_movestate;
+typedef struct pfo_patch {
+    uint32_t flags; int32_t next_state, next_block, _pad;
+    float next_velocity[2], next_pos[3], next_rot[4], next_ppos[3], next_npos[3], next_step, next_left, next_nrot[4], next_prot[4], _padf[3];
+} pfo_patch;
+typedef struct pfo_arrival { int32_t nearest_ok; float nearest[2]; int32_t mc_n; const float *mc; } pfo_arrival;
+void pfo_entity_updates(const pfo_world *w, const pfo_movestate *mss, const pfo_arrival *arr, const uint32_t *work, size_t nwork,
+                        const float *new_vel_xz, const float *vdes_xz, pfo_patch *out);
 /* TARGET_ZONE chunk fields: N_FlowFieldUpdate -> field_update_zone (field.c:2050, 1810), its seed flood
  * field_zone_initial_frontier (field.c:1683) and the per-entity consumer N_DesiredGroupArrivalVelocity (nav.c:3561).
  * centre in absolute tile coordinates; inout = 64 x 64 direction bytes of chunk (chunk_r, chunk_c). */

@@ -43,6 +43,7 @@ def lib():
                                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pfo_group_arrival_field.argtypes = [C.POINTER(_Map), C.c_int, C.c_uint16, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_void_p]
+        L.pfo_entity_updates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfo_zone_seeds.restype = C.c_int
         L.pfo_zone_seeds.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
         L.pfo_chunk_field_seeded.argtypes = [C.POINTER(_Map), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -171,6 +172,10 @@ class OracleMap:
         return vdes, lo
 
 
+class _Arrival(C.Structure):
+    _fields_ = [("nearest_ok", C.c_int32), ("nearest", C.c_float * 2), ("mc_n", C.c_int32), ("mc", C.c_void_p)]
+
+
 class OracleWorld:
     def __init__(self, omap, agents, flocks, hz=20):
         self.omap = omap
@@ -188,6 +193,21 @@ class OracleWorld:
         out = np.zeros(maxout, np.uint32)
         n = lib().pfo_ents_in_circle(self.h, x, z, r, _p(out), maxout)
         return out[:n].copy()
+
+    def entity_updates(self, movestate, arrival, work, new_vel, vdes, patch_dtype):
+        """entity_compute_update per work item. movestate: 176-B records (uid order); arrival: per flock
+        (nearest_ok, nearest[2], mc[n, 2]); -> record array of patch_dtype (128 B)"""
+        ms = np.ascontiguousarray(movestate); work = np.ascontiguousarray(work, np.uint32)
+        nv = np.ascontiguousarray(new_vel, np.float32); vd = np.ascontiguousarray(vdes, np.float32)
+        keep = [np.ascontiguousarray(a[2], np.float32).reshape(-1, 2) for a in arrival]
+        arr = (_Arrival * len(arrival))()
+        for i, a in enumerate(arrival):
+            arr[i].nearest_ok = int(a[0]); arr[i].nearest[0], arr[i].nearest[1] = float(a[1][0]), float(a[1][1])
+            arr[i].mc_n = len(keep[i]); arr[i].mc = keep[i].ctypes.data
+        out = np.zeros(len(work), patch_dtype)
+        assert out.dtype.itemsize == 128 and ms.dtype.itemsize == 176
+        lib().pfo_entity_updates(self.h, _p(ms), C.byref(arr), _p(work), len(work), _p(nv), _p(vd), _p(out))
+        return out
 
     def velocity_work(self, work):
         work = np.ascontiguousarray(work, np.uint32)

@@ -81,7 +81,7 @@ SYMBOLS = [
     "pfnav_map_upload_factions", "pfnav_agents_upload_movestate", "pfnav_agents_compute_updates",
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
     "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
-    "pfnav_entity_seeds", "pfnav_entity_fields", "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
+    "pfnav_route_arrival_consts", "pfnav_entity_seeds", "pfnav_entity_fields", "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
 ]
 
 _lib = None
@@ -126,6 +126,8 @@ def load():
                                           C.c_void_p]
     L.pfnav_pfmap_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
     L.pfnav_map_load_pfmap.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_float, C.c_float]
+    L.pfnav_route_arrival_consts.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.POINTER(C.c_int32)]
     L.pfnav_entity_seeds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t)]
     L.pfnav_entity_fields.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -408,6 +410,13 @@ class Nav:
         out = np.zeros((len(ch), 64, 64), np.uint8)
         _chk(self.L.pfnav_entity_fields(self.h, layer, ref_layer, kind, _p(ents) if len(ents) else None, len(ents), _p(ch), len(ch), _p(out)))
         return out
+
+    def route_arrival_consts(self, target_xz, layer=0):
+        """-> (nearest_ok, nearest[2], mc[n, 2]): the constants of arrived() for one flock target"""
+        ok, n = C.c_int32(0), C.c_int32(0)
+        nearest = np.zeros(2, np.float32); mc = np.zeros((256, 2), np.float32)
+        _chk(self.L.pfnav_route_arrival_consts(self.h, layer, float(target_xz[0]), float(target_xz[1]), C.byref(ok), _p(nearest), _p(mc), 256, C.byref(n)))
+        return ok.value, nearest, mc[:n.value].copy()
 
     def zone_seeds(self, chunk, centre, radius, layer=0):
         out = np.zeros((4 * 4096, 2), np.int32); n = C.c_size_t(0)

@@ -1021,3 +1021,19 @@ extern "C" int pfnav_request_faction(pfnav_ctx *ctx, int faction_id)
     ctx->req_faction = faction_id;
     return PFNAV_OK;
 }
+
+// Inspection / test entry: the per-(target, layer) constants of arrived() (movement.c:2170) that
+// pfnav_agents_compute_updates uploads: N_ClosestPathable's answer and the tile centres N_IsMaximallyClose
+// compares with. out_mc: up to cap (x, z) pairs. Host structure code; needs pfnav_route_build(layer).
+extern "C" int pfnav_route_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, int32_t *out_nearest_ok,
+                                          float *out_nearest_xz, float *out_mc_xz, size_t cap, int32_t *out_mc_n)
+{
+    PF_ARG(ctx && out_nearest_ok && out_nearest_xz && out_mc_n, "null argument");
+    pf_arrival_consts c;
+    int rc = pfnav_arrival_consts(ctx, layer, tx, tz, &c);
+    if (rc) return rc;
+    *out_nearest_ok = c.nearest_ok; out_nearest_xz[0] = c.nearest[0]; out_nearest_xz[1] = c.nearest[1];
+    *out_mc_n = c.mc_n;
+    for (int i = 0; i < c.mc_n && (size_t)i < cap && out_mc_xz; i++) { out_mc_xz[2 * i] = c.mc[i][0]; out_mc_xz[2 * i + 1] = c.mc[i][1]; }
+    return PFNAV_OK;
+}

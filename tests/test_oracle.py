@@ -340,6 +340,28 @@ def test_port_velocity_with_garrisoned_and_los_golden(pforacle, name):
     w.close()
 
 
+@pytest.mark.parametrize("name", ["update_hz20", "update_hz10"])
+def test_port_entity_update_golden(pforacle, name):
+    """a-8 in the restatement: entity_compute_update (movement.c:2303) patches from the reference's velocities; flags,
+    states and all 25 floats identical. The two map searches of arrived() come from the host code of the CUDA path
+    (pfnav_route_arrival_consts), which this pins as well."""
+    g = gold(name)
+    a = _agents_from_gold(g)
+    rec, fl = capi.pack_agents(a)
+    nav = capi.Nav(hostonly=True)
+    nav.map_create(3, 3, 1); nav.map_upload_layer(0, g["cost"]); nav.map_build_nav(0); nav.route_build(0)
+    arrival = [nav.route_arrival_consts(t) for t in a["flock_target"]]
+    nav.close()
+    w = pforacle.OracleWorld(pforacle.OracleMap(3, 3, g["cost"]), rec, fl, int(g["hz"]))
+    p = w.entity_updates(g["ms"].view(capi.MOVESTATE), arrival, g["work"], g["vel"], g["vdes"], capi.PATCH)
+    oi, of = g["patch_i"], g["patch_f"]
+    assert (p["flags"] == oi[:, 0].astype(np.uint32)).all() and (p["next_state"] == oi[:, 1]).all() and (p["next_block"] == oi[:, 2]).all()
+    got = np.concatenate([p["next_velocity"], p["next_pos"], p["next_rot"], p["next_ppos"], p["next_npos"],
+                          p["next_step"][:, None], p["next_left"][:, None], p["next_nrot"], p["next_prot"]], axis=1)
+    assert (got == of[:, :25]).all()
+    w.close()
+
+
 def test_port_desired_velocity_golden(pforacle):
     g = gold("agents_3x3")
     a = _agents_from_gold(g)
