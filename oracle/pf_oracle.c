@@ -1645,3 +1645,45 @@ void pfo_entity_updates(const pfo_world *w, const pfo_movestate *mss, const pfo_
         out[wi] = p;
     }
 }
+
+/* The movestate part of entity_apply_update (movement.c:2693-2757) for one patch: velocity + velocity history
+ * (update_vel_hist :2025, seed_vel_hist_facing :2046 / facing_dir :2040), interpolation fields, next rotation. State
+ * transitions clear the velocity (entity_finish_moving, movement.c:685). agents / mss are updated in place. */
+void pfo_entity_apply(pfo_agent *agents, pfo_movestate *mss, const uint32_t *work, size_t nwork, const pfo_patch *patches)
+{
+    const float EPS = 1.0f / 1024;
+    for(size_t wi = 0; wi < nwork; wi++) {
+        pfo_agent *a = &agents[work[wi]];
+        pfo_movestate *ms = &mss[work[wi]];
+        const pfo_patch *p = &patches[wi];
+        if(a->flags & FL_GARRISONED) continue;                                   /* movement.c:2697 */
+        if(p->flags & UP_STATE) {
+            a->state = (uint32_t)p->next_state;
+            if(p->next_state == ST_ARRIVED || p->next_state == ST_WAITING) { a->velocity[0] = 0.0f; a->velocity[1] = 0.0f; }
+        }
+        if(p->flags & UP_VELOCITY) {
+            a->velocity[0] = p->next_velocity[0]; a->velocity[1] = p->next_velocity[1];
+            if(p->flags & UP_TURNING_IN_PLACE) {
+                memset(ms->vel_hist, 0, sizeof(ms->vel_hist));
+            }else{
+                bool empty = true;
+                for(int i = 0; i < PFO_HIST; i++)
+                    if(sqrtf(ms->vel_hist[i][0] * ms->vel_hist[i][0] + ms->vel_hist[i][1] * ms->vel_hist[i][1]) > EPS) empty = false;
+                const float vl = sqrtf(a->velocity[0] * a->velocity[0] + a->velocity[1] * a->velocity[1]);
+                if(empty && vl > EPS) {
+                    const float theta = (float)(2.0 * atan2((double)ms->next_rot[1], (double)ms->next_rot[3]));
+                    const float dx = (float)(-sin((double)theta)), dz = (float)cos((double)theta);
+                    for(int i = 0; i < PFO_HIST; i++) { ms->vel_hist[i][0] = dx * vl; ms->vel_hist[i][1] = dz * vl; }
+                }
+                ms->vel_hist[ms->vel_hist_idx][0] = a->velocity[0]; ms->vel_hist[ms->vel_hist_idx][1] = a->velocity[1];
+                ms->vel_hist_idx = (ms->vel_hist_idx + 1) % PFO_HIST;
+            }
+        }
+        if(p->flags & UP_POSITION) { a->pos[0] = p->next_pos[0]; a->pos[1] = p->next_pos[2]; }
+        if(p->flags & UP_PREV_POS) { a->prev_pos[0] = p->next_ppos[0]; a->prev_pos[1] = p->next_ppos[2]; }
+        if(p->flags & UP_NEXT_POS) memcpy(ms->next_pos, p->next_npos, sizeof(ms->next_pos));
+        if(p->flags & UP_STEP) ms->step = p->next_step;
+        if(p->flags & UP_LEFT) ms->left = (int)p->next_left;
+        if(p->flags & UP_NEXT_ROT) memcpy(ms->next_rot, p->next_nrot, sizeof(ms->next_rot));
+    }
+}

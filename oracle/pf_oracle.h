@@ -105,6 +105,8 @@ typedef struct pfo_patch {
 typedef struct pfo_arrival { int32_t nearest_ok; float nearest[2]; int32_t mc_n; const float *mc; } pfo_arrival;
 void pfo_entity_updates(const pfo_world *w, const pfo_movestate *mss, const pfo_arrival *arr, const uint32_t *work, size_t nwork,
                         const float *new_vel_xz, const float *vdes_xz, pfo_patch *out);
+/* the movestate part of entity_apply_update (movement.c:2693-2757), in place on agents / movestate records */
+void pfo_entity_apply(pfo_agent *agents, pfo_movestate *mss, const uint32_t *work, size_t nwork, const pfo_patch *patches);
 /* TARGET_ZONE chunk fields: N_FlowFieldUpdate -> field_update_zone (field.c:2050, 1810), its seed flood
  * field_zone_initial_frontier (field.c:1683) and the per-entity consumer N_DesiredGroupArrivalVelocity (nav.c:3561).
  * centre in absolute tile coordinates; inout = 64 x 64 direction bytes of chunk (chunk_r, chunk_c). */

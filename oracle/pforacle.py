@@ -44,6 +44,7 @@ def lib():
         L.pfo_group_arrival_field.argtypes = [C.POINTER(_Map), C.c_int, C.c_uint16, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_void_p]
         L.pfo_entity_updates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pfo_entity_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.pfo_zone_seeds.restype = C.c_int
         L.pfo_zone_seeds.argtypes = [C.POINTER(_Map)] + [C.c_int] * 5 + [C.c_void_p]
         L.pfo_chunk_field_seeded.argtypes = [C.POINTER(_Map), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -170,6 +171,14 @@ class OracleMap:
         lib().pfo_desired_velocity(C.byref(self.m), _p(agents), _p(flocks), _p(work), len(work), _p(slot),
                                    _p(flow), _p(los), _p(vdes), _p(lo))
         return vdes, lo
+
+
+def entity_apply(agents, movestate, work, patches):
+    """entity_apply_update's movestate part -> (agents, movestate) copies after the patches"""
+    a = np.ascontiguousarray(agents).copy(); ms = np.ascontiguousarray(movestate).copy()
+    work = np.ascontiguousarray(work, np.uint32); p = np.ascontiguousarray(patches)
+    lib().pfo_entity_apply(_p(a), _p(ms), _p(work), len(work), _p(p))
+    return a, ms
 
 
 class _Arrival(C.Structure):

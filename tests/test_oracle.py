@@ -360,6 +360,9 @@ def test_port_entity_update_golden(pforacle, name):
                           p["next_step"][:, None], p["next_left"][:, None], p["next_nrot"], p["next_prot"]], axis=1)
     assert (got == of[:, :25]).all()
     w.close()
+    # entity_apply_update's movestate part: velocity history after the patches
+    a2, ms2 = pforacle.entity_apply(rec, g["ms"].view(capi.MOVESTATE), g["work"], p)
+    assert (ms2["vel_hist"][g["work"]] == g["hist"]).all() and (ms2["vel_hist_idx"][g["work"]] == g["hidx"]).all()
 
 
 def test_port_desired_velocity_golden(pforacle):
