@@ -18,6 +18,8 @@
 // neighbour order), because the chosen portal path depends on them.
 #include "pfnav_internal.cuh"
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <deque>
 #include <float.h>
 #include <math.h>
@@ -200,7 +202,8 @@ extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
     pfnav_route_layer &RL = RV[layer];
     const int cw = ctx->chunk_w, chh = ctx->chunk_h, chunks = cw * chh;
     RL.chunks.assign(chunks, {});
-    for (int ch = 0; ch < chunks; ch++) {
+    // every chunk's portal edges and travel index depend on that chunk alone: spread the chunks over the host cores
+    auto build_chunk = [&](int ch) {
         const auto &ports = ctx->portals[layer][ch];
         const uint8_t *cost = L_cost(ctx, layer, ch);
         auto &RC = RL.chunks[ch];
@@ -236,6 +239,15 @@ extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
                 }
             }
         }
+    };
+    {
+        const int nthreads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 32, chunks}));
+        std::atomic<int> next{0};
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; t++)
+            pool.emplace_back([&]() { for (int ch = next.fetch_add(1); ch < chunks; ch = next.fetch_add(1)) build_chunk(ch); });
+        for (int ch = next.fetch_add(1); ch < chunks; ch = next.fetch_add(1)) build_chunk(ch);
+        for (auto &t : pool) t.join();
     }
     // n_update_island_field (nav.c:1731): global islands ignoring blockers, ids from 0
     RL.islands.assign((size_t)chunks * 4096, 0xffff);
