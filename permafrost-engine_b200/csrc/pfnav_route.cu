@@ -408,18 +408,20 @@ struct Router {
         for (int r1 = p.r0; r1 <= p.r1; r1++)
             for (int c1 = p.c0; c1 <= p.c1; c1++) {
                 if (l[r1 * 64 + c1] != cur.liid) continue;
-                for (int r2 = conn.r0; r2 <= conn.r1; r2++)
-                    for (int c2 = conn.c0; c2 <= conn.c1; c2++) {
-                        if (nconn == 256) goto done_conn;
-                        const int dr = (conn.chunk_r * 64 + r2) - (p.chunk_r * 64 + r1);
-                        const int dc = (conn.chunk_c * 64 + c2) - (p.chunk_c * 64 + c1);
-                        if (abs(dr) + abs(dc) == 1) {
-                            const uint16_t nl = cl[r2 * 64 + c2];
-                            bool contains = false;
-                            for (int i = 0; i < nconn; i++) if (conn_liids[i] == nl) { contains = true; break; }
-                            if (!contains && nl != 0xffff) conn_liids[nconn++] = nl;
-                        }
-                    }
+                // the reference scans every tile of the connected portal for Manhattan distance 1 (a_star.c:151);
+                // only the four neighbours of (r1, c1) can qualify: visit those inside the portal's rectangle in the
+                // same (row, column) order
+                const int ar = p.chunk_r * 64 + r1, ac = p.chunk_c * 64 + c1;
+                const int cand[4][2] = {{ar - 1, ac}, {ar, ac - 1}, {ar, ac + 1}, {ar + 1, ac}};
+                for (int k = 0; k < 4; k++) {
+                    const int r2 = cand[k][0] - conn.chunk_r * 64, c2 = cand[k][1] - conn.chunk_c * 64;
+                    if (r2 < conn.r0 || r2 > conn.r1 || c2 < conn.c0 || c2 > conn.c1) continue;
+                    if (nconn == 256) goto done_conn;
+                    const uint16_t nl = cl[r2 * 64 + c2];
+                    bool contains = false;
+                    for (int i = 0; i < nconn; i++) if (conn_liids[i] == nl) { contains = true; break; }
+                    if (!contains && nl != 0xffff) conn_liids[nconn++] = nl;
+                }
             }
     done_conn:
         for (int i = 0; i < nconn; i++) {
