@@ -48,6 +48,17 @@ ALG_BYTES_PER_FLOW_FIELD = 24_704   # TARGET_PORTAL: cost 4096 + blockers 8192 +
 ALG_BYTES_PER_LOS_FIELD = 16_512
 
 
+def set_workload(name):
+    """select the synthetic configuration the module-level sizes describe"""
+    global AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE, CHUNKS
+    if name == "C2":
+        AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE, CHUNKS = 100_000, 16, "C2", False, 16
+    elif name == "C3":
+        AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE, CHUNKS = 1_000_000, 64, "C3", True, 16
+    else:
+        raise ValueError(name)
+
+
 def shard_range(n, rank, world):
     """contiguous, balanced [lo, hi) of n items for `rank` (movement.c:3751-3762 equal-range split)"""
     base, rem = divmod(n, world)
@@ -496,9 +507,7 @@ def main():
                     help="C2 (default, the headline config): 100k agents / 16 goals per GPU; C3: 1M agents of radius 1.0 in "
                          "64 flocks / 64 goals (BASELINE.json configs[2]), extra evidence only")
     args = ap.parse_args()
-    if args.workload == "C3":
-        global AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE
-        AGENTS_PER_GPU, GOALS_PER_GPU, WORKLOAD, C3_MODE = 1_000_000, 64, "C3", True
+    set_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -461,6 +461,46 @@ typedef struct pfnav_flock {
 int  pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n,
                          const pfnav_flock *flocks, size_t nflocks, int hz);
 
+/* ---------------------------------------------------------------------------------------- */
+/* Multi-GPU. Entities are partitioned by contiguous index range -- the reference's own fork-join
+ * split of the work array (movement.c:3751-3762) -- one range per GPU; each GPU updates its own range and needs the
+ * 24-byte neighbour record {pos, vel, radius, state | flags} of every other entity: ONE all-gather of those records
+ * per tick, nothing else. The map is replicated; a rank's field pool holds the destinations of its own flocks.
+ *
+ *   one process per GPU (NCCL over NVLink / NVSwitch; libnccl.so.2 is resolved with dlopen at run time):
+ *       rank 0: pfnav_mgpu_unique_id(id) -> the host program hands the 128 bytes to every rank
+ *       all   : pfnav_mgpu_init(ctx, rank, world, id)
+ *       upload: pfnav_agents_upload_shard(ctx, own records, lo, hi, n_total, ...)   [lo, hi) = pfnav_mgpu_shard_range
+ *       tick  : pfnav_mgpu_gather(ctx, stream); pfnav_agents_tick(...); [compute / apply updates]; repeat
+ *   one process driving several contexts from one thread (how the engine itself would use 8 GPUs):
+ *       pfnav_group_create(ctxs, n, &g); per context pfnav_agents_upload_shard; pfnav_group_gather(g); ticks ...
+ *
+ * uids stay global (index into the whole population); work lists, movestate uploads, velocity / patch / state
+ * read-backs of a context cover its OWN range only. */
+typedef struct pfnav_group pfnav_group;
+#define PFNAV_MGPU_ID_BYTES 128
+int  pfnav_mgpu_shard_range(size_t n_total, int rank, int world, size_t *lo, size_t *hi);
+int  pfnav_mgpu_unique_id(void *out_id /* PFNAV_MGPU_ID_BYTES */);
+int  pfnav_mgpu_init(pfnav_ctx *ctx, int rank, int world, const void *id);
+int  pfnav_mgpu_finalize(pfnav_ctx *ctx);
+/* The per-tick collective: all-gather of the neighbour records (plus the flock id column after an upload that may
+ * have changed membership), then the spatial index over the whole population (G_Pos_CopyBitmapGrid, position.c:359)
+ * on this rank. Asynchronous on `stream` (blocks only when member lists are rebuilt). */
+int  pfnav_mgpu_gather(pfnav_ctx *ctx, void *stream);
+int  pfnav_group_create(pfnav_ctx **ctxs, int world, pfnav_group **out);
+int  pfnav_group_gather(pfnav_group *g);       /* on every member's own context stream */
+void pfnav_group_destroy(pfnav_group *g);
+/* move_copy_gamestate (movement.c:3607) for this context's own range [lo, hi) of a population of n_total entities;
+ * shard[i] is entity lo + i, `flock` fields index the GLOBAL flock table. The snapshot is complete after the next
+ * pfnav_mgpu_gather / pfnav_group_gather. On a context outside any multi-GPU job lo = 0, hi = n_total is the whole
+ * population (== pfnav_agents_upload).
+ * PFNAV_UPLOAD_SAME_FLOCKS: only positions, velocities, states and speeds changed since the previous upload of the
+ * same range -- flock membership, selection radii, layers, the GARRISONED flag and the flock table are as before --
+ * so the per-entity host pass and the member-list rebuild are skipped (the engine pushes deltas). */
+#define PFNAV_UPLOAD_SAME_FLOCKS (1u << 0)
+int  pfnav_agents_upload_shard(pfnav_ctx *ctx, const pfnav_agent *shard, size_t lo, size_t hi, size_t n_total,
+                               const pfnav_flock *flocks, size_t nflocks, int hz, uint32_t flags);
+
 /* Work list (move_push_work, movement.c:3741): the uids that take a velocity update this tick.
  * NULL = every agent whose state is not ARRIVED/WAITING (ent_still, movement.c:652). */
 int  pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_t nwork);

@@ -68,6 +68,10 @@ def lib():
         L.pfref_compute_updates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_apply_velocity_patch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_vpref.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_desired_from_cache.argtypes = [C.c_void_p, C.c_void_p]
+        L.pfref_update_and_apply.restype = C.c_int
+        L.pfref_update_and_apply.argtypes = [C.c_void_p]
+        L.pfref_state_get.argtypes = [C.c_int] + [C.c_void_p] * 5
         L.pfref_fields_mt.restype = C.c_double
         L.pfref_fields_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return _lib
@@ -326,6 +330,22 @@ class RefMap:
         idx = np.zeros(self._nwork, np.int32)
         lib().pfref_apply_velocity_patch(self._nwork, _p(nv), _p(fl), _p(hist), _p(idx))
         return hist, idx
+
+    def desired_from_cache(self):
+        """compute_los_state + compute_desired_velocity (movement.c:4129, 4163) on the work list -> (vdes, los)"""
+        vdes = np.zeros((self._nwork, 2), np.float32); los = np.zeros(self._nwork, np.uint8)
+        lib().pfref_desired_from_cache(_p(vdes), _p(los))
+        return vdes, los
+
+    def update_and_apply(self):
+        """entity_compute_update + entity_apply_update for the work list, then publish the next snapshot"""
+        return lib().pfref_update_and_apply(self.h)
+
+    def state_get(self, n):
+        pos = np.zeros((n, 2), np.float32); prev = np.zeros((n, 2), np.float32); vel = np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.int32); blk = np.zeros(n, np.int32)
+        lib().pfref_state_get(n, _p(pos), _p(prev), _p(vel), _p(st), _p(blk))
+        return dict(pos=pos, prev_pos=prev, vel=vel, state=st, blocking=blk)
 
     def vpref(self):
         out = np.zeros((self._nwork, 2), dtype=np.float32)

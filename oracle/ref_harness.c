@@ -19,7 +19,11 @@
 #include <sched.h>
 #include <unistd.h>
 #include <pthread.h>
+/* position.c (compiled as is) owns the real G_Pos_Set, which writes the engine's live position index; the harness
+ * keeps the live positions in a plain array instead, so movement.c's calls are routed there */
+#define G_Pos_Set pfref_live_pos_set
 #include "game/movement.c"
+#undef G_Pos_Set
 
 #include "navigation/nav_private.h"
 #include "navigation/field.h"
@@ -831,6 +835,8 @@ PFREF_EXPORT void pfref_clearpath(const float *self5, const float *vpref2,
  * ---------------------------------------------------------------------------------------- */
 
 static int        s_nagents = 0;
+static vec3_t    *s_live_pos = NULL;     /* what G_Pos_Set writes on the main thread */
+static quat_t    *s_live_rot = NULL;
 static bg_ent_t   s_pfref_tree;
 static bool       s_tree_valid = false;
 
@@ -925,7 +931,38 @@ PFREF_EXPORT void pfref_agents_set(void *m, int n, const float *pos_xz, const fl
     bg_ent_cleanup(&s_pfref_tree);
     gs->postree = &s_pfref_tree;
     s_nagents = n;
+    free(s_live_pos); free(s_live_rot);
+    s_live_pos = malloc(sizeof(vec3_t) * (n ? n : 1));
+    s_live_rot = malloc(sizeof(quat_t) * (n ? n : 1));
+    for(int i = 0; i < n; i++) {
+        s_live_pos[i] = (vec3_t){pos_xz[2*i], 0.0f, pos_xz[2*i+1]};
+        s_live_rot[i] = (quat_t){0.0f, 0.0f, 0.0f, 1.0f};
+    }
+    static bool s_args_inited = false;
+    if(!s_args_inited) { stalloc_init(&s_eventargs); s_args_inited = true; }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-tick driving of the reference (tests of the device-resident tick loop): the engine services
+ * entity_apply_update (movement.c:2693) and entity_finish_moving / entity_block (movement.c:685, 580) call, backed by
+ * plain arrays. The "live" position table is what G_Pos_Set writes on the main thread; pfref_publish() is the
+ * next tick's move_copy_gamestate (movement.c:3607) + N_Update.
+ * ---------------------------------------------------------------------------------------- */
+bool G_EntityExists(uint32_t uid) { return (int)uid < s_nagents; }
+bool G_EntityIsZombie(uint32_t uid) { (void)uid; return false; }
+bool G_EntityIsGarrisoned(uint32_t uid) { return !!(G_FlagsGetFrom(s_move_work.gamestate.flags, uid) & ENTITY_FLAG_GARRISONED); }
+uint32_t G_FlagsGet(uint32_t uid) { return G_FlagsGetFrom(s_move_work.gamestate.flags, uid); }
+bool pfref_live_pos_set(uint32_t uid, vec3_t pos) { s_live_pos[uid] = pos; return true; }
+void Entity_SetRot(uint32_t uid, quat_t rot) { s_live_rot[uid] = rot; }
+void E_Entity_Notify(enum eventtype e, uint32_t uid, void *arg, enum event_source src) { (void)e; (void)uid; (void)arg; (void)src; }
+void E_Global_Notify(enum eventtype e, void *arg, enum event_source src) { (void)e; (void)arg; (void)src; }
+void G_Combat_SetStance(uint32_t uid, enum combat_stance stance) { (void)uid; (void)stance; }
+void M_NavBlockersIncref(vec2_t xz_pos, float range, int faction_id, uint32_t flags, const struct map *map)
+{ N_BlockersIncref(xz_pos, range, faction_id, flags, map->pos, map->nav_private); }      /* map.c:1043 */
+void M_NavBlockersDecref(vec2_t xz_pos, float range, int faction_id, uint32_t flags, const struct map *map)
+{ N_BlockersDecref(xz_pos, range, faction_id, flags, map->pos, map->nav_private); }
+void M_NavInvalidateZoneFieldsAt(const struct map *map, vec2_t xz_pos, enum nav_layer layer)
+{ N_InvalidateZoneFieldsAt(map->nav_private, map->pos, xz_pos, layer); }
 
 /* Query order probe: G_Pos_EntsInCircleFrom (position.c:379) */
 PFREF_EXPORT int pfref_ents_in_circle(float x, float z, float range, uint32_t *out, int maxout)
@@ -1052,6 +1089,72 @@ PFREF_EXPORT void pfref_apply_velocity_patch(int nwork, const float *next_veloci
             out_hist[(i*VEL_HIST_LEN + k)*2 + 1] = ms->vel_hist[k].z;
         }
         out_idx[i] = ms->vel_hist_idx;
+    }
+}
+
+/* A2 of the navigation tick on the current work list, with the reference's own functions: compute_los_state
+ * (movement.c:4129) and compute_desired_velocity (:4163), i.e. N_HasDestLOS + N_DesiredPointSeekVelocity incl. the
+ * on-miss chain (inline n_request_path + field repairs). out_vdes / out_los may be NULL. */
+PFREF_EXPORT void pfref_desired_from_cache(float *out_vdes, uint8_t *out_los)
+{
+    compute_los_state();
+    compute_desired_velocity();
+    for(size_t i = 0; i < s_move_work.nwork; i++) {
+        if(out_vdes) { out_vdes[2*i] = s_move_work.in[i].ent_des_v.x; out_vdes[2*i+1] = s_move_work.in[i].ent_des_v.z; }
+        if(out_los) out_los[i] = s_move_work.in[i].has_dest_los;
+    }
+}
+
+/* entity_compute_update + entity_apply_update (movement.c:2303, 2693) for every work item with the velocities the
+ * velocity pass left in the work outputs: the real functions, engine services above. Then the next tick's
+ * snapshot: positions table + position index rebuilt from the live table, N_Update for blockers taken by
+ * entity_block. Returns the number of entities whose state changed. */
+PFREF_EXPORT int pfref_update_and_apply(void *m)
+{
+    int nwork = (int)s_move_work.nwork, changed = 0;
+    struct movestate_patch *patches = calloc(nwork ? nwork : 1, sizeof(struct movestate_patch));
+    for(int i = 0; i < nwork; i++) {
+        const struct move_work_in *in = &s_move_work.in[i];
+        entity_compute_update(s_move_work.hz, in->ent_uid, s_move_work.out[i].ent_vel, in->ent_des_v, in, &patches[i]);
+    }
+    for(int i = 0; i < nwork; i++) {
+        uint32_t uid = s_move_work.in[i].ent_uid;
+        enum move_state before = movestate_get(uid)->state;
+        entity_apply_update(uid, &patches[i]);
+        changed += (movestate_get(uid)->state != before);
+    }
+    free(patches);
+    stalloc_clear(&s_eventargs);
+    /* publish: move_copy_gamestate + G_Pos_CopyBitmapGrid */
+    struct move_gamestate *gs = &s_move_work.gamestate;
+    bg_ent_destroy(&s_pfref_tree);
+    struct map *map = m;
+    vec3_t center = M_GetCenterPos(map);
+    float hw = (map->width  * TILES_PER_CHUNK_WIDTH  * X_COORDS_PER_TILE) / 2.0f;
+    float hh = (map->height * TILES_PER_CHUNK_HEIGHT * Z_COORDS_PER_TILE) / 2.0f;
+    bg_ent_init(&s_pfref_tree, center.x - hw, center.x + hw, center.z - hh, center.z + hh, pfref_uids_equal);
+    bg_ent_reserve(&s_pfref_tree, s_nagents);
+    for(int i = 0; i < s_nagents; i++) {
+        khiter_t k = kh_get(pos, gs->positions, (uint32_t)i);
+        kh_value(gs->positions, k) = s_live_pos[i];
+        bg_ent_insert(&s_pfref_tree, s_live_pos[i].x, s_live_pos[i].z, (uint32_t)i);
+    }
+    bg_ent_cleanup(&s_pfref_tree);
+    gs->postree = &s_pfref_tree;
+    N_Update(map->nav_private);
+    N_ApplyDeferredInvalidations();
+    return changed;
+}
+
+/* entity state after the ticks so far, by uid: pos, prev_pos, velocity (2 floats each), state, blocking */
+PFREF_EXPORT void pfref_state_get(int n, float *pos, float *prev_pos, float *vel, int32_t *state, int32_t *blocking)
+{
+    for(int i = 0; i < n; i++) {
+        const struct movestate *ms = movestate_get(i);
+        pos[2*i] = s_live_pos[i].x; pos[2*i+1] = s_live_pos[i].z;
+        prev_pos[2*i] = ms->prev_pos.x; prev_pos[2*i+1] = ms->prev_pos.z;
+        vel[2*i] = ms->velocity.x; vel[2*i+1] = ms->velocity.z;
+        state[i] = ms->state; blocking[i] = ms->blocking;
     }
 }
 

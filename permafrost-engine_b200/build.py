@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfnav.so")
-SOURCES = ["pfnav_fields.cu", "pfnav_agents.cu", "pfnav_plan.cu", "pfnav_route.cu", "pfnav_blockers.cu", "pfnav_region.cu", "pfnav_pfmap.cu"]
+SOURCES = ["pfnav_fields.cu", "pfnav_agents.cu", "pfnav_plan.cu", "pfnav_route.cu", "pfnav_blockers.cu", "pfnav_region.cu", "pfnav_pfmap.cu", "pfnav_mgpu.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     # bit-parity with the reference's x86-64 SSE float arithmetic: no FMA contraction
@@ -29,16 +29,24 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
+                os.path.getmtime(os.path.join(CSRC, src)), *[os.path.getmtime(h) for h in HEADERS]):
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose:
             sys.stderr.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
-        objs.append(obj)
+        return obj
+
+    HEADERS = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+              [os.path.join(HERE, "..", "include", "pfnav.h")]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:      # one nvcc per translation unit
+        objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -82,6 +82,8 @@ SYMBOLS = [
     "pfnav_agents_read_patches", "pfnav_agents_apply_updates", "pfnav_agents_read_state",
     "pfnav_region_fields", "pfnav_region_fields_dev", "pfnav_group_arrival_field", "pfnav_blockers_get_factions",
     "pfnav_route_arrival_consts", "pfnav_entity_seeds", "pfnav_entity_fields", "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
+    "pfnav_mgpu_shard_range", "pfnav_mgpu_unique_id", "pfnav_mgpu_init", "pfnav_mgpu_finalize", "pfnav_mgpu_gather",
+    "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
 ]
 
 _lib = None
@@ -178,6 +180,17 @@ def load():
                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_agents_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     L.pfnav_agents_set_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_upload_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                            C.c_int, C.c_uint32]
+    L.pfnav_mgpu_shard_range.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.pfnav_mgpu_unique_id.argtypes = [C.c_void_p]
+    L.pfnav_mgpu_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.pfnav_mgpu_finalize.argtypes = [C.c_void_p]
+    L.pfnav_mgpu_gather.argtypes = [C.c_void_p, C.c_void_p]
+    L.pfnav_group_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.pfnav_group_gather.argtypes = [C.c_void_p]
+    L.pfnav_group_destroy.argtypes = [C.c_void_p]
+    L.pfnav_group_destroy.restype = None
     L.pfnav_agents_tick.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.pfnav_agents_read_velocities.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_agents_read_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -635,6 +648,24 @@ class Nav:
         self.nagents = len(agents)
         _chk(self.L.pfnav_agents_upload(self.h, _p(agents), len(agents), _p(flocks), len(flocks), hz))
 
+    def agents_upload_shard(self, shard, lo, hi, n_total, flocks, hz=20, flags=0):
+        """this context's own entity range [lo, hi) of a population of n_total (multi-GPU); shard[i] = entity lo + i"""
+        shard = np.ascontiguousarray(shard, AGENT)
+        flocks = np.ascontiguousarray(flocks, FLOCK)
+        assert len(shard) == hi - lo
+        self.nagents = n_total
+        _chk(self.L.pfnav_agents_upload_shard(self.h, _p(shard), lo, hi, n_total, _p(flocks), len(flocks), hz, flags))
+
+    def mgpu_init(self, rank, world, nccl_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        _chk(self.L.pfnav_mgpu_init(self.h, rank, world, buf))
+
+    def mgpu_gather(self, stream=0):
+        _chk(self.L.pfnav_mgpu_gather(self.h, C.c_void_p(stream)))
+
+    def mgpu_finalize(self):
+        _chk(self.L.pfnav_mgpu_finalize(self.h))
+
     def agents_set_work(self, uids=None):
         if uids is None:
             _chk(self.L.pfnav_agents_set_work(self.h, None, 0))
@@ -706,6 +737,39 @@ class Nav:
 
     def launch_count(self):
         return int(self.L.pfnav_launch_count(self.h))
+
+
+UPLOAD_SAME_FLOCKS = 1
+
+
+def mgpu_shard_range(n_total, rank, world):
+    lo, hi = C.c_size_t(0), C.c_size_t(0)
+    _chk(load().pfnav_mgpu_shard_range(n_total, rank, world, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def mgpu_unique_id():
+    buf = (C.c_char * 128)()
+    _chk(load().pfnav_mgpu_unique_id(buf))
+    return bytes(buf.raw)
+
+
+class Group:
+    """in-process multi-GPU group: several Nav contexts of this process, rank i = navs[i]"""
+
+    def __init__(self, navs):
+        self.navs = list(navs)
+        arr = (C.c_void_p * len(navs))(*[n.h for n in navs])
+        self.g = C.c_void_p(0)
+        _chk(load().pfnav_group_create(arr, len(navs), C.byref(self.g)))
+
+    def gather(self):
+        _chk(load().pfnav_group_gather(self.g))
+
+    def close(self):
+        if self.g:
+            load().pfnav_group_destroy(self.g)
+            self.g = None
 
 
 def pack_agents(a):

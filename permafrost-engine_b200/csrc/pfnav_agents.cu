@@ -64,6 +64,8 @@ struct PoolView {
     const uint8_t *los;      // [max][4096] ; first byte of a never-written LOS slot region is valid 0s
     const uint8_t *has;      // [max] bit0 flow present, bit1 LOS present
     int ndests;
+    uint32_t *touch;         // [max] last tick that read the slot (LRU stamp), may be NULL
+    uint32_t tick_no;
 };
 struct GridView {
     const uint32_t *cell_start, *cell_count;
@@ -155,7 +157,10 @@ __global__ void k_desired_velocity(MapView m, PoolView pool, const pfnav_agent *
         // ---- N_HasDestLOS sampled at prev_pos (movement.c:4137) ----
         if (desc_for_point(m, a.prev_pos[0], a.prev_pos[1], t)) {
             const int s = slots[t.chunk_r * m.chunk_w + t.chunk_c];
-            if (s >= 0 && (pool.has[s] & 2)) los = pool.los[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 1;
+            if (s >= 0 && (pool.has[s] & 2)) {
+                los = pool.los[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 1;
+                if (pool.touch && pool.touch[s] != pool.tick_no) pool.touch[s] = pool.tick_no;
+            }
         }
         // ---- N_DesiredPointSeekVelocity at pos ----
         if (desc_for_point(m, a.pos[0], a.pos[1], t)) {
@@ -165,6 +170,7 @@ __global__ void k_desired_velocity(MapView m, PoolView pool, const pfnav_agent *
             } else {
                 const uint8_t *base_ff = pool.flow + (size_t)s * 4096;
                 const int base_dir = base_ff[t.tile_r * 64 + t.tile_c] & 0xF;
+                if (pool.touch && pool.touch[s] != pool.tick_no) pool.touch[s] = pool.tick_no;
                 // n_interpolated_flow_dir (nav.c:3407)
                 const float bx = (m.map_x - (float)(t.chunk_c * 256)) - (float)(t.tile_c * 4);
                 const float bz = (m.map_z + (float)(t.chunk_r * 256)) + (float)(t.tile_r * 4);
@@ -266,18 +272,6 @@ __device__ __forceinline__ int cell_of(int32_t i, int32_t origin, int n)
 {
     int c = (i - origin) >> 12;
     return min(max(c, 0), n - 1);
-}
-
-__global__ void k_make_records(const pfnav_agent *__restrict__ agents, pf_record *__restrict__ rec, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const pfnav_agent a = agents[i];
-    pf_record r;
-    r.px = a.pos[0]; r.pz = a.pos[1]; r.vx = a.velocity[0]; r.vz = a.velocity[1];
-    r.radius = a.radius;
-    r.state_flags = (a.state << 24) | (a.flags & 0xFFFFFFu);
-    rec[i] = r;
 }
 
 __global__ void k_cell_count(const pf_record *__restrict__ rec, int n, GridView g, uint32_t *__restrict__ count)
@@ -1179,7 +1173,8 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
-    cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep);
+    cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep); cudaFree(ctx->d_flock_of); cudaFree(ctx->d_facts);
+    ctx->d_flock_of = nullptr; ctx->d_facts = nullptr;
     if (ctx->update_done) cudaEventDestroy(ctx->update_done);
     cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
     ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
@@ -1197,8 +1192,10 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     PF_NEED_DEVICE(ctx);
     PF_ARG(ndests > 0 && max_fields > 0, "ndests/max_fields");
     PF_CUDA(cudaSetDevice(ctx->device));
-    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
-    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
+    PF_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los); cudaFree(ctx->d_pool_touch);
+    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr; ctx->d_pool_touch = nullptr;
+    ctx->los_inflight = false;
     const size_t nslots = (size_t)ndests * ctx->chunk_w * ctx->chunk_h;
     PF_CUDA(cudaMalloc(&ctx->d_pool_slot, nslots * sizeof(int32_t)));
     PF_CUDA(cudaMalloc(&ctx->d_pool_flow, (size_t)max_fields * 4096));
@@ -1206,6 +1203,9 @@ extern "C" int pfnav_pool_create(pfnav_ctx *ctx, int ndests, int max_fields)
     PF_CUDA(cudaMalloc(&ctx->d_pool_los, (size_t)max_fields * 4096 + max_fields));
     PF_CUDA(cudaMemset(ctx->d_pool_slot, 0xFF, nslots * sizeof(int32_t)));
     PF_CUDA(cudaMemset(ctx->d_pool_los + (size_t)max_fields * 4096, 0, max_fields));
+    PF_CUDA(cudaMalloc(&ctx->d_pool_touch, (size_t)max_fields * 4));
+    PF_CUDA(cudaMemset(ctx->d_pool_touch, 0, (size_t)max_fields * 4));
+    ctx->h_slot_touch.assign(max_fields, 0); ctx->h_slot_owner.assign(max_fields, -1); ctx->pool_free.clear();
     ctx->h_pool_slot.assign(nslots, -1);
     ctx->h_pool_has.assign(max_fields, 0);
     ctx->h_pool_req.assign(max_fields, pfnav_field_req{});
@@ -1225,6 +1225,10 @@ extern "C" int pfnav_pool_clear(pfnav_ctx *ctx)
     std::fill(ctx->h_pool_slot.begin(), ctx->h_pool_slot.end(), -1);
     std::fill(ctx->h_pool_has.begin(), ctx->h_pool_has.end(), 0);
     std::fill(ctx->h_pool_ffid.begin(), ctx->h_pool_ffid.end(), 0);
+    PF_CUDA(cudaMemset(ctx->d_pool_touch, 0, (size_t)ctx->pool_max * 4));
+    std::fill(ctx->h_slot_touch.begin(), ctx->h_slot_touch.end(), 0);
+    std::fill(ctx->h_slot_owner.begin(), ctx->h_slot_owner.end(), -1);
+    ctx->pool_free.clear();
     ctx->goal_batch.valid = false;
     ctx->pool_used = 0;
     return PFNAV_OK;
@@ -1239,13 +1243,18 @@ extern "C" int pfnav_pool_put(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
     PF_CUDA(cudaSetDevice(ctx->device));
     PF_CUDA(pf_fields_sync(ctx));
     const size_t si = (size_t)dest * ctx->chunk_w * ctx->chunk_h + chunk_r * ctx->chunk_w + chunk_c;
-    int slot = ctx->h_pool_slot[si];
+    int32_t slot = ctx->h_pool_slot[si];
     uint8_t *d_has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096;
     if (slot < 0) {
-        if (ctx->pool_used >= ctx->pool_max) { pfnav_set_error("pfnav_pool_put: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
-        slot = ctx->pool_used++;
-        ctx->h_pool_slot[si] = slot;
-        PF_CUDA(cudaMemcpy(ctx->d_pool_slot + si, &slot, sizeof(int32_t), cudaMemcpyHostToDevice));
+        bool evicted = false;
+        int rc = pf_pool_reserve(ctx, &si, 1, &slot, &evicted);
+        if (rc) return rc;
+        if (evicted) {
+            PF_CUDA(cudaMemcpy(ctx->d_pool_slot, ctx->h_pool_slot.data(), ctx->h_pool_slot.size() * 4, cudaMemcpyHostToDevice));
+            PF_CUDA(cudaMemcpy(d_has, ctx->h_pool_has.data(), ctx->pool_max, cudaMemcpyHostToDevice));
+        } else {
+            PF_CUDA(cudaMemcpy(ctx->d_pool_slot + si, &slot, sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
     }
     uint8_t has = ctx->h_pool_has[slot];
     if (flow_field) { PF_CUDA(cudaMemcpy(ctx->d_pool_flow + (size_t)slot * 4096, flow_field, 4096, cudaMemcpyHostToDevice)); has |= 1; }
@@ -1299,17 +1308,81 @@ static int build_index(pfnav_ctx *ctx, cudaStream_t st)
     return 0;
 }
 
-extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n, const pfnav_flock *flocks,
-                                   size_t nflocks, int hz)
+// records of the uploaded range + the flock id column (neighbour kernels read other agents' flock through it)
+__global__ void k_make_records(const pfnav_agent *__restrict__ agents, pf_record *__restrict__ rec, int32_t *__restrict__ flock_of,
+                               int lo, int hi)
+{
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const pfnav_agent a = agents[i];
+    pf_record r;
+    r.px = a.pos[0]; r.pz = a.pos[1]; r.vx = a.velocity[0]; r.vz = a.velocity[1];
+    r.radius = a.radius;
+    r.state_flags = (a.state << 24) | (a.flags & 0xFFFFFFu);
+    rec[i] = r;
+    flock_of[i] = a.flock;
+}
+
+// population-wide facts the tick needs from records it did not upload itself (other ranks' shards): the largest
+// selection radius (adjacency pre-selection of k_entity_update) and whether any entity is garrisoned
+__global__ void k_population_facts(const pf_record *__restrict__ rec, int n, uint32_t *__restrict__ out)
+{
+    uint32_t mx = 0, garr = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const pf_record r = rec[i];
+        mx = max(mx, __float_as_uint(fmaxf(r.radius, 0.0f)));          // non-negative floats order like their bit patterns
+        garr |= (r.state_flags & PFNAV_FLAG_GARRISONED) ? 1u : 0u;
+    }
+    for (int off = 16; off > 0; off >>= 1) { mx = max(mx, __shfl_xor_sync(FULL, mx, off)); garr |= __shfl_xor_sync(FULL, garr, off); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); if (garr) atomicOr(&out[1], 1u); }
+}
+
+int pfnav_mgpu_allgather(pfnav_ctx *ctx, void *d_buf, size_t elem_bytes, cudaStream_t st);      // pfnav_mgpu.cu
+
+// flock member lists (ascending uid: the iteration order our cohesion sum is defined over) from the flock id column
+static int rebuild_flock_members(pfnav_ctx *ctx, cudaStream_t st)
+{
+    const size_t n = ctx->n_agents, nflocks = ctx->n_flocks;
+    std::vector<int32_t> fo(n ? n : 1);
+    PF_CUDA(cudaMemcpyAsync(fo.data(), ctx->d_flock_of, n * 4, cudaMemcpyDeviceToHost, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> fstart(nflocks + 1, 0), members(n ? n : 1);
+    for (size_t i = 0; i < n; i++) {
+        PF_ARG(fo[i] < (int)nflocks, "agent flock index out of range");
+        if (fo[i] >= 0) fstart[fo[i] + 1]++;
+    }
+    for (size_t f = 0; f < nflocks; f++) fstart[f + 1] += fstart[f];
+    {
+        std::vector<uint32_t> cur(fstart.begin(), fstart.end() - 1);
+        for (size_t i = 0; i < n; i++)
+            if (fo[i] >= 0) members[cur[fo[i]]++] = (uint32_t)i;
+    }
+    PF_CUDA(cudaMemcpyAsync(ctx->d_flock_start, fstart.data(), (nflocks + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n) PF_CUDA(cudaMemcpyAsync(ctx->d_flock_members, members.data(), n * 4, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaStreamSynchronize(st));      // host vectors go out of scope
+    return 0;
+}
+
+// move_copy_gamestate (movement.c:3607) for the index range [lo, hi) of a population of n_total entities
+// (uid == index into the whole population). Single GPU: lo = 0, hi = n_total. Multi-GPU: every rank uploads its own
+// range (pfnav_mgpu_shard_range) and the 24-byte neighbour records + flock ids of the other ranges arrive through
+// the all-gather.
+static int agents_upload_impl(pfnav_ctx *ctx, const pfnav_agent *agents, size_t lo, size_t hi, size_t n,
+                              const pfnav_flock *flocks, size_t nflocks, int hz, uint32_t flags)
 {
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_NEED_DEVICE(ctx);
-    PF_ARG(n == 0 || agents, "agents");
+    PF_ARG(lo <= hi && hi <= n, "shard range");
+    PF_ARG(hi == lo || agents, "agents");
     PF_ARG(nflocks == 0 || flocks, "flocks");
     PF_ARG(hz == 20 || hz == 10 || hz == 5 || hz == 1, "hz must be 20, 10, 5 or 1 (movement.c:2210)");
     PF_ARG(n < (1u << 31), "n");
+    const bool sharded = ctx->mgpu != nullptr;
+    PF_ARG(sharded || (lo == 0 && hi == n), "a partial upload needs pfnav_mgpu_init / pfnav_group_create first");
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->tick_stream;
+    const bool same = (flags & PFNAV_UPLOAD_SAME_FLOCKS) && ctx->n_agents == n && ctx->n_flocks == nflocks &&
+                      ctx->shard_lo == lo && ctx->shard_hi == hi && ctx->hz == hz;
     ctx->hz = hz;
     int rc;
     if (n > ctx->cap_agents) {
@@ -1317,6 +1390,7 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
         if ((rc = ensure(ctx->d_agents, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_records, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_flock_members, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_flock_of, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_ix, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_iy, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_id, cap, n))) return rc;
@@ -1328,40 +1402,30 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
         if ((rc = ensure(ctx->d_flock_start, cap, nflocks + 2))) return rc;
         ctx->cap_flocks = nflocks + 1;
     }
-    ctx->n_agents = n; ctx->n_flocks = nflocks;
-    // flock member lists, ascending uid (the iteration order our cohesion sum is defined over)
-    std::vector<uint32_t> fstart(nflocks + 1, 0), members(n ? n : 1);
-    ctx->flock_layer_used.assign(nflocks * PFNAV_NAV_LAYER_MAX, 0);
-    ctx->max_radius = 0.0f; ctx->has_unsupported_state = false; ctx->any_garrisoned = false;
-    for (size_t i = 0; i < n; i++) {
-        PF_ARG(agents[i].flock < (int)nflocks, "agent flock index out of range");
-        {   // Entity_NavLayerWithRadius (entity.c:554): the layer this agent's tile probes read
+    if (!ctx->d_facts) PF_CUDA(cudaMalloc(&ctx->d_facts, 8));
+    ctx->n_agents = n; ctx->n_flocks = nflocks; ctx->shard_lo = lo; ctx->shard_hi = hi;
+    if (!same) {
+        // what the host needs to know about the entities it will run work items for (its own range)
+        ctx->flock_layer_used.assign(nflocks * PFNAV_NAV_LAYER_MAX, 0);
+        ctx->has_unsupported_state = false;
+        for (size_t i = 0; i < hi - lo; i++) {
+            PF_ARG(agents[i].flock < (int)nflocks, "agent flock index out of range");
+            // Entity_NavLayerWithRadius (entity.c:554): the layer this agent's tile probes read
             const uint32_t f = agents[i].flags; const float r = agents[i].radius;
             const int base = (f & PFNAV_FLAG_WATER) ? 4 : (f & PFNAV_FLAG_AIR) ? 8 : 0;
             const int layer = base + (r >= 15.0f ? 3 : r >= 10.0f ? 2 : r >= 5.0f ? 1 : 0);
             PF_ARG(layer < ctx->nlayers, "agent needs a navigation layer that was not created (radius/flags)");
             if (agents[i].flock >= 0) ctx->flock_layer_used[(size_t)agents[i].flock * PFNAV_NAV_LAYER_MAX + layer] = 1;
-            ctx->max_radius = std::max(ctx->max_radius, r);
-            if (f & PFNAV_FLAG_GARRISONED) ctx->any_garrisoned = true;
             const uint32_t stt = agents[i].state;
             if (stt == PFNAV_STATE_MOVING_IN_FORMATION || stt == PFNAV_STATE_SURROUND_ENTITY ||
                 stt == PFNAV_STATE_ENTER_ENTITY_RANGE || stt == PFNAV_STATE_TURNING || stt == PFNAV_STATE_ARRIVING_TO_CELL)
                 ctx->has_unsupported_state = true;
         }
-        if (agents[i].flock >= 0) fstart[agents[i].flock + 1]++;
+        ctx->h_flocks.assign(flocks, flocks + nflocks);
+        ctx->arrival_valid = false;
     }
-    ctx->h_flocks.assign(flocks, flocks + nflocks);
-    ctx->arrival_valid = false;
-    for (size_t f = 0; f < nflocks; f++) fstart[f + 1] += fstart[f];
-    {
-        std::vector<uint32_t> cur(fstart.begin(), fstart.end() - 1);
-        for (size_t i = 0; i < n; i++)
-            if (agents[i].flock >= 0) members[cur[agents[i].flock]++] = (uint32_t)i;
-    }
-    PF_CUDA(cudaMemcpyAsync(ctx->d_agents, agents, n * sizeof(pfnav_agent), cudaMemcpyHostToDevice, st));
-    if (nflocks) PF_CUDA(cudaMemcpyAsync(ctx->d_flocks, flocks, nflocks * sizeof(pfnav_flock), cudaMemcpyHostToDevice, st));
-    PF_CUDA(cudaMemcpyAsync(ctx->d_flock_start, fstart.data(), (nflocks + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (n) PF_CUDA(cudaMemcpyAsync(ctx->d_flock_members, members.data(), n * 4, cudaMemcpyHostToDevice, st));
+    if (hi > lo) PF_CUDA(cudaMemcpyAsync(ctx->d_agents + lo, agents, (hi - lo) * sizeof(pfnav_agent), cudaMemcpyHostToDevice, st));
+    if (nflocks && !same) PF_CUDA(cudaMemcpyAsync(ctx->d_flocks, flocks, nflocks * sizeof(pfnav_flock), cudaMemcpyHostToDevice, st));
     // spatial index geometry: G_Pos_Init (position.c:264) + bg_init (bitmap_grid.h:959)
     {
         const float W = (float)(ctx->chunk_w * 256), H = (float)(ctx->chunk_h * 256);
@@ -1382,15 +1446,54 @@ extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, si
             ctx->cap_cells = ncells + 1;
         }
     }
-    if (n) {
-        k_make_records<<<((int)n + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_records, (int)n);
+    if (hi > lo) {
+        k_make_records<<<((int)(hi - lo) + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_records, ctx->d_flock_of, (int)lo, (int)hi);
         ctx->launches++;
     }
-    if ((rc = build_index(ctx, st))) return rc;
     // default work list: none until pfnav_agents_set_work
     ctx->n_work = 0;
-    PF_CUDA(cudaStreamSynchronize(st));      // host vectors above go out of scope
+    if (sharded) {
+        // the other ranges' records (and, when membership may have changed, flock ids) come from the peers;
+        // pfnav_mgpu_gather / pfnav_group_gather follows and finishes the snapshot (index, facts, member lists)
+        ctx->members_stale = !same;
+        PF_CUDA(cudaStreamSynchronize(st));
+        return PFNAV_OK;
+    }
+    return pfnav_agents_finish_snapshot(ctx, st, !same);
+}
+
+// Everything that needs the WHOLE population's records: member lists, population facts, spatial index.
+int pfnav_agents_finish_snapshot(pfnav_ctx *ctx, cudaStream_t st, bool members)
+{
+    int rc;
+    const int n = (int)ctx->n_agents;
+    if (members && (rc = rebuild_flock_members(ctx, st))) return rc;
+    if (members) {
+        PF_CUDA(cudaMemsetAsync(ctx->d_facts, 0, 8, st));
+        if (n) { k_population_facts<<<std::min((n + 255) / 256, 1024), 256, 0, st>>>(ctx->d_records, n, ctx->d_facts); ctx->launches++; }
+        uint32_t facts[2] = {0, 0};
+        PF_CUDA(cudaMemcpyAsync(facts, ctx->d_facts, 8, cudaMemcpyDeviceToHost, st));
+        PF_CUDA(cudaStreamSynchronize(st));
+        memcpy(&ctx->max_radius, &facts[0], 4);
+        ctx->any_garrisoned = facts[1] != 0;
+    }
+    if ((rc = build_index(ctx, st))) return rc;
+    PF_CUDA(cudaStreamSynchronize(st));
     return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_upload(pfnav_ctx *ctx, const pfnav_agent *agents, size_t n, const pfnav_flock *flocks,
+                                   size_t nflocks, int hz)
+{
+    PF_ARG(ctx && !ctx->mgpu, "multi-GPU contexts upload their own range: pfnav_agents_upload_shard");
+    return agents_upload_impl(ctx, agents, 0, n, n, flocks, nflocks, hz, 0);
+}
+
+extern "C" int pfnav_agents_upload_shard(pfnav_ctx *ctx, const pfnav_agent *shard, size_t lo, size_t hi, size_t n_total,
+                                         const pfnav_flock *flocks, size_t nflocks, int hz, uint32_t flags)
+{
+    PF_ARG(ctx, "ctx");
+    return agents_upload_impl(ctx, shard, lo, hi, n_total, flocks, nflocks, hz, flags);
 }
 
 extern "C" int pfnav_agents_rebuild_index(pfnav_ctx *ctx, void *stream)
@@ -1416,14 +1519,17 @@ extern "C" int pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_
     std::vector<uint32_t> all;
     if (!uids) {
         // every agent that is not still (ent_still, movement.c:652) -- needs the host copy of state
-        std::vector<pfnav_agent> h(ctx->n_agents);
-        PF_CUDA(cudaMemcpy(h.data(), ctx->d_agents, ctx->n_agents * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < ctx->n_agents; i++)
-            if (h[i].state != PFNAV_STATE_ARRIVED && h[i].state != PFNAV_STATE_WAITING) all.push_back((uint32_t)i);
+        const size_t lo = ctx->shard_lo, cnt = ctx->shard_hi - ctx->shard_lo;
+        std::vector<pfnav_agent> h(cnt);
+        PF_CUDA(cudaDeviceSynchronize());
+        if (cnt) PF_CUDA(cudaMemcpy(h.data(), ctx->d_agents + lo, cnt * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; i++)
+            if (h[i].state != PFNAV_STATE_ARRIVED && h[i].state != PFNAV_STATE_WAITING) all.push_back((uint32_t)(lo + i));
         uids = all.data();
         nwork = all.size();
     }
-    for (size_t i = 0; i < nwork; i++) PF_ARG(uids[i] < ctx->n_agents, "work uid out of range");
+    for (size_t i = 0; i < nwork; i++)
+        PF_ARG(uids[i] >= ctx->shard_lo && uids[i] < ctx->shard_hi, "work uid outside this context's own entity range");
     if (nwork > ctx->cap_work) {
         size_t cap = 0; int rc;
         if ((rc = ensure(ctx->d_work, cap, nwork))) return rc; cap = 0;
@@ -1457,6 +1563,7 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = pf_stream(ctx, stream);
     const int nwork = (int)ctx->n_work;
+    ctx->tick_no++;
     MapView m;
     m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
     m.chunk_w = ctx->chunk_w; m.chunk_h = ctx->chunk_h; m.map_x = ctx->map_x; m.map_z = ctx->map_z;
@@ -1527,6 +1634,7 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         PoolView pv;
         pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
         pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
+        pv.touch = ctx->d_pool_touch; pv.tick_no = ctx->tick_no;
         k_desired_velocity<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
                                                                ctx->d_vdes_out, ctx->d_los_out, ctx->d_work_count);
     } else {
@@ -1691,7 +1799,8 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
                 const pf_record *__restrict__ rec, const pfnav_movestate *__restrict__ mss,
                 const pfnav_flock *__restrict__ flocks, const pf_arrival_dev *__restrict__ arr,
                 const float2 *__restrict__ mc_tiles, int nlayers, const uint32_t *__restrict__ work, int nwork,
-                const float2 *__restrict__ vel_in, const float2 *__restrict__ vdes_in, pfnav_patch *__restrict__ out)
+                const float2 *__restrict__ vel_in, const float2 *__restrict__ vdes_in, pfnav_patch *__restrict__ out,
+                const int32_t *__restrict__ flock_of)
 {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwork) return;
@@ -1851,7 +1960,7 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
                     if (o == uid) continue;
                     const pf_record r = rec[o];
                     if ((r.state_flags >> 24) != PFNAV_STATE_ARRIVED) continue;
-                    if (agents[o].flock != a.flock) continue;
+                    if (flock_of[o] != a.flock) continue;
                     const v2 d = {curr_xz.x - r.px, curr_xz.z - r.pz};
                     if (v2_len(d) <= a.radius + r.radius + 5.0f) { arrived = true; break; }
                 }
@@ -1921,14 +2030,14 @@ __global__ void k_entity_apply(pfnav_agent *__restrict__ agents, pfnav_movestate
 extern "C" int pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movestate *ms, size_t n)
 {
     PF_ARG(ctx && ctx->d_agents && ms, "agents not uploaded / ms == NULL");
-    PF_ARG(n == ctx->n_agents, "one movestate record per uploaded agent");
+    PF_ARG(n == ctx->shard_hi - ctx->shard_lo, "one movestate record per uploaded agent (of this context's own range)");
     PF_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    if (n > ctx->cap_movestate) {
-        if ((rc = ensure(ctx->d_movestate, ctx->cap_movestate, n))) return rc;
-        ctx->cap_movestate = n;
+    if (ctx->n_agents > ctx->cap_movestate) {
+        if ((rc = ensure(ctx->d_movestate, ctx->cap_movestate, ctx->n_agents))) return rc;
+        ctx->cap_movestate = ctx->n_agents;
     }
-    PF_CUDA(cudaMemcpy(ctx->d_movestate, ms, n * sizeof(pfnav_movestate), cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(ctx->d_movestate + ctx->shard_lo, ms, n * sizeof(pfnav_movestate), cudaMemcpyHostToDevice));
     ctx->movestate_set = true;
     return PFNAV_OK;
 }
@@ -1990,7 +2099,7 @@ extern "C" int pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream)
     const size_t b0 = ctx->n_flocks * (size_t)ctx->nlayers * sizeof(pf_arrival_dev);
     k_entity_update<<<(nwork + 127) / 128, 128, 0, st>>>(m, grid_of(ctx), up, ctx->d_agents, ctx->d_records, ctx->d_movestate,
         ctx->d_flocks, (const pf_arrival_dev *)ctx->d_arrival, (const float2 *)((const uint8_t *)ctx->d_arrival + b0),
-        ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches);
+        ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches, ctx->d_flock_of);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaEventRecord(ctx->update_done, st));
@@ -2027,11 +2136,11 @@ extern "C" int pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, 
     PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
     PF_CUDA(cudaSetDevice(ctx->device));
     PF_CUDA(cudaDeviceSynchronize());
-    const size_t n = std::min(maxout, ctx->n_agents);
-    if (agents_out) PF_CUDA(cudaMemcpy(agents_out, ctx->d_agents, n * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
+    const size_t n = std::min(maxout, ctx->shard_hi - ctx->shard_lo);       // this context's own entity range
+    if (agents_out && n) PF_CUDA(cudaMemcpy(agents_out, ctx->d_agents + ctx->shard_lo, n * sizeof(pfnav_agent), cudaMemcpyDeviceToHost));
     if (ms_out) {
         PF_ARG(ctx->movestate_set, "no movestate uploaded");
-        PF_CUDA(cudaMemcpy(ms_out, ctx->d_movestate, n * sizeof(pfnav_movestate), cudaMemcpyDeviceToHost));
+        if (n) PF_CUDA(cudaMemcpy(ms_out, ctx->d_movestate + ctx->shard_lo, n * sizeof(pfnav_movestate), cudaMemcpyDeviceToHost));
     }
     return PFNAV_OK;
 }
@@ -2091,6 +2200,7 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
     PoolView pv;
     pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
     pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
+    pv.touch = nullptr; pv.tick_no = 0;
     k_collect_misses<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_liid, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
                                                          d_miss, d_cnt, (uint32_t)nwork);
     ctx->launches++;

@@ -217,8 +217,7 @@ static size_t tiles_contour(const pfnav_ctx *ctx, size_t ntds, const td *tds, td
     return ret;
 }
 
-static std::unordered_map<const pfnav_ctx *, std::set<std::pair<int, int>>> g_dirty;     // (layer, chunk)
-static std::unordered_map<const pfnav_ctx *, std::set<std::pair<int, int>>> g_fdirty;    // faction mask changed
+// dirty (layer, chunk) sets live in the context: pfnav_ctx::dirty (occupancy changed), ::fdirty (faction mask changed)
 
 // n_update_blockers (nav.c:1017) on the host mirror; layers the context does not hold are skipped
 static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size_t n, int delta)
@@ -238,7 +237,7 @@ static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size
         uint16_t &v = ctx->h_blk[lbase + (size_t)chunk * 4096 + t];
         const int prev = v;
         v = (uint16_t)(prev + delta);
-        if (!!v != !!prev) g_dirty[ctx].insert({layer, chunk});
+        if (!!v != !!prev) ctx->dirty.insert({layer, chunk});
         if (fac) {
             uint8_t &fv = ctx->h_fac[layer][((size_t)chunk * 15 + faction_id) * 4096 + t];
             const int fprev = fv;
@@ -246,7 +245,7 @@ static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size
             if (!!fv != !!fprev) {
                 uint16_t &m = ctx->h_fmask[lbase + (size_t)chunk * 4096 + t];
                 m = fv ? (uint16_t)(m | (1u << faction_id)) : (uint16_t)(m & ~(1u << faction_id));
-                g_fdirty[ctx].insert({layer, chunk});
+                ctx->fdirty.insert({layer, chunk});
             }
         }
     }
@@ -327,7 +326,7 @@ int pfnav_footprint_tiles(const pfnav_ctx *ctx, const pfnav_footprint *e, int ri
     return (int)n;
 }
 
-void pfnav_blockers_forget(const pfnav_ctx *ctx) { g_dirty.erase(ctx); g_fdirty.erase(ctx); }
+void pfnav_blockers_forget(pfnav_ctx *ctx) { ctx->dirty.clear(); ctx->fdirty.clear(); }
 
 extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
 {
@@ -365,21 +364,20 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
     if (ctx->device >= 0) {
         PF_CUDA(cudaSetDevice(ctx->device));
         PF_CUDA(pf_fields_sync(ctx));     // forked LOS chains still read the map that is about to change
+        // ticks / field launches on the context stream or on caller streams (all non-blocking, so not ordered against
+        // the synchronous copies below) may still read the grids
+        PF_CUDA(cudaDeviceSynchronize());
     }
     {   // faction masks follow the refcounts at once (they only matter to attacking requests)
-        auto fit = g_fdirty.find(ctx);
-        if (fit != g_fdirty.end()) {
-            for (const auto &lc : fit->second) { int rc = pfnav_fmask_push_chunk(ctx, lc.first, lc.second); if (rc) return rc; }
-            if (!fit->second.empty()) ctx->map_epoch++;
-            fit->second.clear();
-        }
+        for (const auto &lc : ctx->fdirty) { int rc = pfnav_fmask_push_chunk(ctx, lc.first, lc.second); if (rc) return rc; }
+        if (!ctx->fdirty.empty()) ctx->map_epoch++;
+        ctx->fdirty.clear();
     }
-    auto it = g_dirty.find(ctx);
     int nd = 0;
-    if (it != g_dirty.end()) {
+    if (!ctx->dirty.empty()) {
         const int chunks = ctx->chunk_w * ctx->chunk_h;
         bool pool_touched = false;
-        for (const auto &lc : it->second) {
+        for (const auto &lc : ctx->dirty) {
             const int layer = lc.first, chunk = lc.second;
             int rc = pfnav_map_refresh_chunk(ctx, layer, chunk / ctx->chunk_w, chunk % ctx->chunk_w);
             if (rc) return rc;
@@ -405,7 +403,7 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
                 }
             }
         }
-        it->second.clear();
+        ctx->dirty.clear();
         if (pool_touched && ctx->device >= 0) {
             PF_CUDA(cudaSetDevice(ctx->device));
             PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,

@@ -1454,12 +1454,14 @@ void pfnav_fields_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_stage); ctx->d_stage = nullptr;
     cudaFree(ctx->d_los_sched); ctx->d_los_sched = nullptr; ctx->los_sched_bytes = 0;
     cudaFree(ctx->d_los_trace); ctx->d_los_trace = nullptr; ctx->los_trace_cap = 0;
-    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los);
-    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr;
+    cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los); cudaFree(ctx->d_pool_touch);
+    ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr; ctx->d_pool_touch = nullptr;
+    if (ctx->ev_los_sched) { cudaEventDestroy(ctx->ev_los_sched); ctx->ev_los_sched = nullptr; }
 }
 
-void pfnav_route_forget(const pfnav_ctx *ctx);
-void pfnav_blockers_forget(const pfnav_ctx *ctx);
+void pfnav_route_forget(pfnav_ctx *ctx);
+void pfnav_route_invalidate_layer(pfnav_ctx *ctx, int layer);
+void pfnav_blockers_forget(pfnav_ctx *ctx);
 
 extern "C" void pfnav_destroy(pfnav_ctx *ctx)
 {
@@ -1535,6 +1537,17 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     pfnav_route_forget(ctx);
     pfnav_blockers_forget(ctx);
     ctx->h_fac.clear(); ctx->h_fmask.clear();
+    // the field pool is sized ndests x (chunks of the OLD map): it does not carry over either
+    if (ctx->device >= 0 && ctx->d_pool_slot) {
+        PF_CUDA(cudaSetDevice(ctx->device));
+        PF_CUDA(cudaDeviceSynchronize());
+        cudaFree(ctx->d_pool_slot); cudaFree(ctx->d_pool_flow); cudaFree(ctx->d_pool_los); cudaFree(ctx->d_pool_touch);
+        ctx->d_pool_slot = nullptr; ctx->d_pool_flow = nullptr; ctx->d_pool_los = nullptr; ctx->d_pool_touch = nullptr;
+    }
+    ctx->pool_ndests = 0; ctx->pool_max = 0; ctx->pool_used = 0;
+    ctx->h_pool_slot.clear(); ctx->h_pool_has.clear(); ctx->h_pool_req.clear(); ctx->h_pool_ffid.clear();
+    ctx->h_slot_owner.clear(); ctx->h_slot_touch.clear(); ctx->pool_free.clear();
+    ctx->goal_batch.valid = false;
     ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
     ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;
     ctx->map_x = map_x; ctx->map_z = map_z;
@@ -1587,6 +1600,9 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(cost_base, "cost_base");
     ctx->map_epoch++;
+    // new costs: the portal edges / travel index / global islands built from the old ones are void. (The structural
+    // build re-uploads the layer from the mirrors themselves: same costs, tables stay.)
+    if (cost_base != ctx->h_cost.data() + (size_t)ctx->W64 * ctx->H64 * layer) pfnav_route_invalidate_layer(ctx, layer);
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     if (ctx->device < 0) {
         memmove(ctx->h_cost.data() + ltiles * layer, cost_base, ltiles);
@@ -1596,6 +1612,7 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
         return PFNAV_OK;
     }
     PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaDeviceSynchronize());     // the kernels below run on the default stream: nothing may still read the old grids
     int rc = ensure_stage(ctx, ltiles * 2);
     if (rc) return rc;
     const int nblk = std::min<size_t>((ltiles + 255) / 256, 148 * 8);
@@ -1774,6 +1791,7 @@ extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, in
     if (local_islands) memmove(ctx->h_liid.data() + hoff, local_islands, 8192);
     if (ctx->device < 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaDeviceSynchronize());     // synchronous copies below are not ordered against the (non-blocking) work streams
     if (cost_base)
         PF_CUDA(cudaMemcpy2D(ctx->d_cost + off, ctx->W64, cost_base, 64, 64, 64, cudaMemcpyHostToDevice));
     if (blockers)
@@ -2014,10 +2032,14 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
     const size_t smem = LOS_WARPS_PER_CTA * (ctx->los_variant == 1 ? sizeof(LosSmemB) : sizeof(LosSmem));
     (void)n_waves; (void)h_wave_offsets;        // requests are dependency-sorted; the kernel schedules them itself
     cudaStream_t st = pf_stream(ctx, stream);
-    // scheduler state: [counter][done flags]
+    // scheduler state: [counter][done flags]. ONE buffer per context: the warps of a launch spin on its flags, so a
+    // later launch (on any stream) must not reset or free it while an earlier one is still running -- every launch
+    // is ordered after the previous one through ev_los_sched, and growing the buffer waits for the whole device.
+    if (!ctx->ev_los_sched) PF_CUDA(cudaEventCreateWithFlags(&ctx->ev_los_sched, cudaEventDisableTiming));
+    else PF_CUDA(cudaStreamWaitEvent(st, ctx->ev_los_sched, 0));
     const size_t need = (n + 1) * sizeof(int);
     if (ctx->los_sched_bytes < need) {
-        PF_CUDA(cudaStreamSynchronize(st));
+        PF_CUDA(cudaDeviceSynchronize());
         cudaFree(ctx->d_los_sched);
         ctx->d_los_sched = nullptr; ctx->los_sched_bytes = 0;
         PF_CUDA(cudaMalloc(&ctx->d_los_sched, need * 2));
@@ -2046,6 +2068,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
     ctx->los_trace_n = ctx->los_trace_on ? std::min(n, ctx->los_trace_cap) : 0;
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(ctx->ev_los_sched, st));
     return PFNAV_OK;
 }
 

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/pfnav.h"
 
@@ -78,11 +80,15 @@ struct pfnav_ctx {
     unsigned long long *d_los_trace = nullptr; size_t los_trace_cap = 0, los_trace_n = 0; bool los_trace_on = false;
     int los_variant = 1;
     void *d_los_sched = nullptr; size_t los_sched_bytes = 0;   // LOS scheduler: work counter + per-request done flags
+    cudaEvent_t ev_los_sched = nullptr;                        // recorded after every LOS launch: the next one waits for it
     // host mirrors (chunk-blocked, [layer][chunk][64][64]) for the host-side planner
     std::vector<uint8_t>  h_cost;
     std::vector<uint16_t> h_blk, h_liid;
     struct portal_t { int16_t chunk_r, chunk_c, r0, c0, r1, c1; int32_t conn_chunk, conn_idx; };
     std::vector<std::vector<std::vector<portal_t>>> portals;   // [layer][chunk][idx]
+    // host-side derived state, owned by the context (no process-global tables: contexts on different threads are independent)
+    void *route_state = nullptr;                               // pfnav_route.cu: std::vector<pfnav_route_layer>
+    std::set<std::pair<int, int>> dirty, fdirty;               // pfnav_blockers.cu: (layer, chunk) occupancy / faction mask changed
 
     // ---- field pool ----
     int pool_ndests = 0, pool_max = 0, pool_used = 0;
@@ -101,6 +107,14 @@ struct pfnav_ctx {
     } goal_batch;
     uint8_t *d_pool_flow = nullptr;   // [max][4096]
     uint8_t *d_pool_los = nullptr;    // [max][4096]
+    // LRU eviction (fieldcache.c:59-71 keeps CONFIG_*_CACHE_SZ entries per LRU cache): every slot remembers the last
+    // tick that read it (device side, written by the desired-velocity kernels) or requested it (host side)
+    uint32_t *d_pool_touch = nullptr;             // [max] last tick number a work item read the slot
+    std::vector<uint32_t> h_slot_touch;           // [max] last tick number a request named the slot
+    std::vector<int64_t>  h_slot_owner;           // [max] dest * chunks + chunk, or -1 (free)
+    std::vector<int32_t>  pool_free;              // evicted slots, reused before pool_used grows
+    uint32_t tick_no = 1;                         // advanced by pfnav_agents_tick
+    uint64_t pool_evictions = 0;
 
     // ---- agents ----
     size_t n_agents = 0, cap_agents = 0, n_flocks = 0, cap_flocks = 0;
@@ -110,6 +124,12 @@ struct pfnav_ctx {
     pfnav_flock *d_flocks = nullptr;
     uint32_t *d_flock_start = nullptr;    // [nflocks+1] offsets into d_flock_members
     uint32_t *d_flock_members = nullptr;  // agent ids grouped by flock, ascending uid
+    int32_t  *d_flock_of = nullptr;       // [n_agents] flock id column (all-gathered with the records)
+    uint32_t *d_facts = nullptr;          // {max radius bits, any garrisoned}
+    // multi-GPU: this context owns the entity index range [shard_lo, shard_hi) of the population (pfnav_mgpu.cu)
+    size_t shard_lo = 0, shard_hi = 0;
+    void *mgpu = nullptr;                 // pf_mgpu: NCCL communicator or in-process group membership
+    bool members_stale = false;           // flock member lists must be rebuilt at the next gather
     float2   *d_cohesion = nullptr;       // per-agent cohesion force (pre-pass)
     float2   *d_member_pos = nullptr; size_t cap_member_pos = 0;   // positions in flock-member order
     void *d_prep = nullptr; size_t cap_prep = 0;                   // phase-A results of the two-phase velocity update
@@ -198,6 +218,9 @@ int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const
 
 int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk);
 
+// pool slots with LRU eviction (pfnav_plan.cu)
+int pf_pool_reserve(pfnav_ctx *ctx, const size_t *keys, size_t n, int32_t *slots_out, bool *out_evicted);
+
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
        PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };
 
@@ -229,6 +252,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
 
 // ---- pfnav_agents.cu ----
 void pfnav_agents_free(pfnav_ctx *ctx);
+int pfnav_agents_finish_snapshot(pfnav_ctx *ctx, cudaStream_t st, bool members);
 
 // ---- device helpers shared by kernels ----
 __device__ __forceinline__ uint32_t pf_lane() { return threadIdx.x & 31; }

@@ -258,6 +258,72 @@ extern "C" int pfnav_plan_goal(pfnav_ctx *ctx, int layer, int tgt_chunk_r, int t
     return PFNAV_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Pool slots with LRU eviction. The reference keeps its fields in LRU caches of fixed capacity
+// (fieldcache.c:59-71; CONFIG_FLOW_CACHE_SZ / CONFIG_LOS_CACHE_SZ, config.h:64-65): a request that finds the
+// cache full evicts the least recently used entry, and an agent that later misses it re-requests its path
+// (nav.c:3484-3506 == pfnav_pool_repair). Here one slot holds the flow AND the LOS field of a (dest, chunk);
+// "recently used" = the last tick whose desired-velocity pass read the slot (device side) or whose request
+// named it (host side); ties go to the lower slot index.
+// pf_pool_reserve: slots for the (dest, chunk) keys a request batch is about to write -- all or nothing: on
+// PFNAV_ERR_NOMEM nothing was changed. keys may repeat. *out_evicted: slot-table entries of OTHER keys changed
+// (the caller re-uploads the whole table and the `has` bytes).
+// ------------------------------------------------------------------------------------------
+int pf_pool_reserve(pfnav_ctx *ctx, const size_t *keys, size_t n, int32_t *slots_out, bool *out_evicted)
+{
+    if (out_evicted) *out_evicted = false;
+    std::vector<size_t> fresh;
+    for (size_t i = 0; i < n; i++)
+        if (ctx->h_pool_slot[keys[i]] < 0) fresh.push_back(keys[i]);
+    std::sort(fresh.begin(), fresh.end());
+    fresh.erase(std::unique(fresh.begin(), fresh.end()), fresh.end());
+    const size_t avail = ctx->pool_free.size() + (size_t)(ctx->pool_max - ctx->pool_used);
+    if (fresh.size() > avail) {
+        const size_t k = fresh.size() - avail;
+        std::vector<uint32_t> stamp(ctx->h_slot_touch);
+        if (ctx->device >= 0 && ctx->d_pool_touch) {
+            PF_CUDA(cudaSetDevice(ctx->device));
+            PF_CUDA(cudaDeviceSynchronize());         // ticks on any stream may still be stamping slots (eviction is rare)
+            std::vector<uint32_t> dev(ctx->pool_max);
+            PF_CUDA(cudaMemcpy(dev.data(), ctx->d_pool_touch, (size_t)ctx->pool_max * 4, cudaMemcpyDeviceToHost));
+            for (int s = 0; s < ctx->pool_max; s++) stamp[s] = std::max(stamp[s], dev[s]);
+        }
+        std::vector<uint8_t> pinned(ctx->pool_max, 0);
+        for (size_t i = 0; i < n; i++) { const int s = ctx->h_pool_slot[keys[i]]; if (s >= 0) pinned[s] = 1; }
+        std::vector<int32_t> cand;
+        for (int s = 0; s < ctx->pool_used; s++)
+            if (ctx->h_slot_owner[s] >= 0 && !pinned[s]) cand.push_back(s);
+        if (cand.size() < k) {
+            pfnav_set_error("field pool full: %zu new (dest, chunk) fields requested, %zu slots free, %zu evictable of %d",
+                            fresh.size(), avail, cand.size(), ctx->pool_max);
+            return PFNAV_ERR_NOMEM;
+        }
+        std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return stamp[a] != stamp[b] ? stamp[a] < stamp[b] : a < b; });
+        for (size_t i = 0; i < k; i++) {
+            const int32_t s = cand[i];
+            const size_t owner = (size_t)ctx->h_slot_owner[s];
+            ctx->h_pool_slot[owner] = -1; ctx->h_pool_ffid[owner] = 0;
+            ctx->h_pool_has[s] = 0; ctx->h_slot_owner[s] = -1;
+            ctx->pool_free.push_back(s);
+            ctx->pool_evictions++;
+        }
+        if (out_evicted) *out_evicted = true;
+        ctx->goal_batch.valid = false;
+    }
+    for (size_t key : fresh) {
+        int32_t s;
+        if (!ctx->pool_free.empty()) { s = ctx->pool_free.back(); ctx->pool_free.pop_back(); }
+        else s = ctx->pool_used++;
+        ctx->h_pool_slot[key] = s; ctx->h_slot_owner[s] = (int64_t)key; ctx->h_pool_has[s] = 0;
+    }
+    for (size_t i = 0; i < n; i++) {
+        const int32_t s = ctx->h_pool_slot[keys[i]];
+        ctx->h_slot_touch[s] = ctx->tick_no;
+        if (slots_out) slots_out[i] = s;
+    }
+    return PFNAV_OK;
+}
+
 // The flow waves and the LOS dependency chains of a goal batch each get a context-owned stream (the flow kernels
 // need ~100 KB of shared memory per CTA and would otherwise queue the caller's stream behind the persistent LOS
 // CTAs that hold most of it).
@@ -334,17 +400,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     std::vector<pfnav_field_req> fr(cap), all_fr;
     std::vector<pfnav_los_req> lr(cap), all_lr;
     std::vector<int32_t> fc(cap), fw(cap), lc(cap), all_fs, all_fw, all_ls, all_ld;
-    auto slot_for = [&](int dest, int chunk, uint8_t bits) -> int {
-        const size_t si = (size_t)dest * chunks + chunk;
-        int slot = ctx->h_pool_slot[si];
-        if (slot < 0) {
-            if (ctx->pool_used >= ctx->pool_max) return -1;
-            slot = ctx->pool_used++;
-            ctx->h_pool_slot[si] = slot;
-        }
-        ctx->h_pool_has[slot] |= bits;
-        return slot;
-    };
+    std::vector<size_t> fkeys, lkeys;
     for (int g = 0; g < ngoals; g++) {
         PF_ARG(dests[g] >= 0 && dests[g] < ctx->pool_ndests, "dest");
         int nf = 0, nl = 0;
@@ -352,22 +408,30 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
                                  fr.data(), fc.data(), fw.data(), cap, &nf, lr.data(), lc.data(), cap, &nl);
         if (rc) return rc;
         for (int i = 0; i < nf; i++) {
-            const int s = slot_for(dests[g], fc[i], 1);
-            if (s < 0) { pfnav_set_error("pfnav_pool_request_goals: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
-            all_fr.push_back(fr[i]); all_fs.push_back(s); all_fw.push_back(fw[i]);
-            ctx->h_pool_req[s] = fr[i];
+            all_fr.push_back(fr[i]); all_fw.push_back(fw[i]);
+            fkeys.push_back((size_t)dests[g] * chunks + fc[i]);
         }
         const int lbase = (int)all_lr.size();
         std::vector<int> depth(nl, 0);
         for (int i = 0; i < nl; i++) {
-            const int s = slot_for(dests[g], lc[i], 2);
-            if (s < 0) { pfnav_set_error("pfnav_pool_request_goals: pool full (%d fields)", ctx->pool_max); return PFNAV_ERR_NOMEM; }
             pfnav_los_req q = lr[i];
             if (q.prev_index >= 0) { depth[i] = depth[q.prev_index] + 1; q.prev_index += lbase; }
-            all_lr.push_back(q); all_ls.push_back(s); all_ld.push_back(depth[i]);
+            all_lr.push_back(q); all_ld.push_back(depth[i]);
+            lkeys.push_back((size_t)dests[g] * chunks + lc[i]);
         }
     }
     const int nf = (int)all_fr.size(), nl = (int)all_lr.size();
+    {   // slots for everything the batch writes, all or nothing (nothing is published before this succeeds)
+        std::vector<size_t> keys(fkeys);
+        keys.insert(keys.end(), lkeys.begin(), lkeys.end());
+        std::vector<int32_t> slots(keys.size());
+        int rc = pf_pool_reserve(ctx, keys.data(), keys.size(), slots.data(), nullptr);
+        if (rc) return rc;
+        all_fs.assign(slots.begin(), slots.begin() + nf);
+        all_ls.assign(slots.begin() + nf, slots.end());
+        for (int i = 0; i < nf; i++) { ctx->h_pool_has[all_fs[i]] |= 1; ctx->h_pool_req[all_fs[i]] = all_fr[i]; }
+        for (int i = 0; i < nl; i++) ctx->h_pool_has[all_ls[i]] |= 2;
+    }
     // stable order by wave / depth
     int maxw = 0, maxd = 0;
     for (int i = 0; i < nf; i++) maxw = std::max(maxw, all_fw[i]);

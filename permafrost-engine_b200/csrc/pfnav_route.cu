@@ -143,9 +143,25 @@ struct pfnav_route_layer {
     std::vector<pfnav_route_chunk> chunks;
     std::vector<uint16_t> islands;                                // global islands, chunk-blocked
 };
-static std::unordered_map<const pfnav_ctx *, std::vector<pfnav_route_layer>> g_routes;
+// The routing structures live in the context (pfnav_ctx::route_state): two contexts driven from two threads
+// (one per GPU in one process) share nothing.
+typedef std::vector<pfnav_route_layer> route_vec;
+static inline route_vec *routes_of(const pfnav_ctx *ctx) { return (route_vec *)ctx->route_state; }
+// the built layer, or nullptr
+static inline pfnav_route_layer *route_layer(const pfnav_ctx *ctx, int layer)
+{
+    route_vec *rv = routes_of(ctx);
+    if (!rv || layer < 0 || layer >= (int)rv->size() || !(*rv)[layer].built) return nullptr;
+    return &(*rv)[layer];
+}
 
-void pfnav_route_forget(const pfnav_ctx *ctx) { g_routes.erase(ctx); }
+void pfnav_route_forget(pfnav_ctx *ctx) { delete routes_of(ctx); ctx->route_state = nullptr; }
+// the portal lists of `layer` were rebuilt: its edge / travel tables no longer describe them
+void pfnav_route_invalidate_layer(pfnav_ctx *ctx, int layer)
+{
+    route_vec *rv = routes_of(ctx);
+    if (rv && layer >= 0 && layer < (int)rv->size()) (*rv)[layer] = pfnav_route_layer();
+}
 
 static inline const uint8_t *L_cost(const pfnav_ctx *ctx, int layer, int chunk)
 { return ctx->h_cost.data() + ((size_t)layer * ctx->chunk_w * ctx->chunk_h + chunk) * 4096; }
@@ -180,9 +196,9 @@ static void update_edge_states(pfnav_ctx *ctx, pfnav_route_layer &RL, int layer,
 // or -1 when the routing structure of the layer has not been built.
 int pfnav_route_refresh_edges(pfnav_ctx *ctx, int layer, int chunk)
 {
-    auto it = g_routes.find(ctx);
-    if (it == g_routes.end() || layer >= (int)it->second.size() || !it->second[layer].built) return -1;
-    auto &RL = it->second[layer];
+    pfnav_route_layer *prl = route_layer(ctx, layer);
+    if (!prl) return -1;
+    auto &RL = *prl;
     std::vector<int> before;
     for (auto &ev : RL.chunks[chunk].edges) for (auto &e : ev) before.push_back(e.es);
     update_edge_states(ctx, RL, layer, chunk);
@@ -197,7 +213,8 @@ extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG((size_t)layer < ctx->portals.size() && !ctx->portals[layer].empty(), "pfnav_map_build_nav not called for this layer");
-    auto &RV = g_routes[ctx];
+    if (!ctx->route_state) ctx->route_state = new route_vec();
+    auto &RV = *routes_of(ctx);
     if ((int)RV.size() < ctx->nlayers) RV.resize(ctx->nlayers);
     pfnav_route_layer &RL = RV[layer];
     const int cw = ctx->chunk_w, chh = ctx->chunk_h, chunks = cw * chh;
@@ -287,18 +304,18 @@ extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
 extern "C" int pfnav_route_islands_get(pfnav_ctx *ctx, int layer, uint16_t *out)
 {
     PF_ARG(ctx && out, "args");
-    auto it = g_routes.find(ctx);
-    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
-    memcpy(out, it->second[layer].islands.data(), it->second[layer].islands.size() * 2);
+    const pfnav_route_layer *prl = route_layer(ctx, layer);
+    PF_ARG(prl, "pfnav_route_build not called");
+    memcpy(out, prl->islands.data(), prl->islands.size() * 2);
     return PFNAV_OK;
 }
 
 extern "C" int pfnav_route_edges_get(pfnav_ctx *ctx, int layer, int chunk, int portal, uint32_t *out, int maxout, int *out_n)
 {
     PF_ARG(ctx && out && out_n, "args");
-    auto it = g_routes.find(ctx);
-    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
-    const auto &RL = it->second[layer];
+    const pfnav_route_layer *prl = route_layer(ctx, layer);
+    PF_ARG(prl, "pfnav_route_build not called");
+    const auto &RL = *prl;
     PF_ARG(chunk >= 0 && chunk < (int)RL.chunks.size() && portal >= 0 && portal < (int)RL.chunks[chunk].edges.size(), "chunk/portal");
     int n = 0;
     for (const auto &e : RL.chunks[chunk].edges[portal]) {
@@ -562,9 +579,9 @@ extern "C" int pfnav_route_request_path(pfnav_ctx *ctx, int layer, float src_x, 
                                         uint32_t *out_dest_id, int *out_ok)
 {
     PF_ARG(ctx && n_flow && n_los && out_ok && out_dest_id, "args");
-    auto it = g_routes.find(ctx);
-    PF_ARG(it != g_routes.end() && layer >= 0 && layer < (int)it->second.size() && it->second[layer].built, "pfnav_route_build not called");
-    pfnav_route_layer &RL = it->second[layer];
+    pfnav_route_layer *prl = route_layer(ctx, layer);
+    PF_ARG(prl, "pfnav_route_build not called");
+    pfnav_route_layer &RL = *prl;
     const int cw = ctx->chunk_w, chunks = cw * ctx->chunk_h;
     Router R{ctx, RL, layer, cw, ctx->chunk_h};
     *n_flow = 0; *n_los = 0; *out_ok = 0;
@@ -723,32 +740,30 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
     if (out_n_los) *out_n_los = nl;
     if (nf == 0 && nl == 0) return PFNAV_OK;
     ctx->goal_batch.valid = false;          // the staging buffer is about to be reused
-    auto slot_for = [&](int chunk, uint8_t bits) -> int {
-        const size_t si = (size_t)dest * chunks + chunk;
-        int slot = ctx->h_pool_slot[si];
-        if (slot < 0) {
-            if (ctx->pool_used >= ctx->pool_max) return -1;
-            slot = ctx->pool_used++;
-            ctx->h_pool_slot[si] = slot;
-        }
-        ctx->h_pool_has[slot] |= bits;
-        return slot;
-    };
     // flow waves: a request that updates a chunk already written in this batch runs one wave later
     std::vector<int32_t> fslot(nf), fwave(nf), lslot(nl), ldepth(nl, 0);
     std::vector<int> seen(chunks, 0);
     int maxw = 0, maxd = 0;
+    bool evicted = false;
+    {   // slots for everything this request writes (and the previous-chunk LOS fields it reads), all or nothing
+        std::vector<size_t> keys;
+        for (int i = 0; i < nf; i++) keys.push_back((size_t)dest * chunks + fc[i]);
+        for (int i = 0; i < nl; i++) keys.push_back((size_t)dest * chunks + lc[i]);
+        for (int i = 0; i < nl; i++)
+            if (lr[i].prev_index == -2) keys.push_back((size_t)dest * chunks + lr[i].prev_chunk_r * ctx->chunk_w + lr[i].prev_chunk_c);
+        std::vector<int32_t> slots(keys.size());
+        rc = pf_pool_reserve(ctx, keys.data(), keys.size(), slots.data(), &evicted);
+        if (rc) return rc;
+        for (int i = 0; i < nf; i++) { fslot[i] = slots[i]; ctx->h_pool_has[fslot[i]] |= 1; }
+        for (int i = 0; i < nl; i++) { lslot[i] = slots[nf + i]; ctx->h_pool_has[lslot[i]] |= 2; }
+    }
     for (int i = 0; i < nf; i++) {
-        fslot[i] = slot_for(fc[i], 1);
-        if (fslot[i] < 0) { pfnav_set_error("pfnav_pool_request_path: pool full"); return PFNAV_ERR_NOMEM; }
         fwave[i] = seen[fc[i]]++;
         maxw = std::max(maxw, fwave[i]);
         ctx->h_pool_ffid[(size_t)dest * chunks + fc[i]] = fid[i];
         ctx->h_pool_req[fslot[i]] = fr[i];
     }
     for (int i = 0; i < nl; i++) {
-        lslot[i] = slot_for(lc[i], 2);
-        if (lslot[i] < 0) { pfnav_set_error("pfnav_pool_request_path: pool full"); return PFNAV_ERR_NOMEM; }
         if (lr[i].prev_index >= 0) ldepth[i] = ldepth[lr[i].prev_index] + 1;
         else if (lr[i].prev_index == -2) {
             const int pchunk = lr[i].prev_chunk_r * ctx->chunk_w + lr[i].prev_chunk_c;
@@ -790,8 +805,11 @@ extern "C" int pfnav_pool_request_path(pfnav_ctx *ctx, int dest, int layer, floa
     }
     uint8_t *dev = (uint8_t *)ctx->d_plan_buf;
     PF_CUDA(cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, st));
-    PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + (size_t)dest * chunks, ctx->h_pool_slot.data() + (size_t)dest * chunks,
-                            (size_t)chunks * 4, cudaMemcpyHostToDevice, st));
+    if (evicted)      // entries of other destinations lost their slots
+        PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot, ctx->h_pool_slot.data(), ctx->h_pool_slot.size() * 4, cudaMemcpyHostToDevice, st));
+    else
+        PF_CUDA(cudaMemcpyAsync(ctx->d_pool_slot + (size_t)dest * chunks, ctx->h_pool_slot.data() + (size_t)dest * chunks,
+                                (size_t)chunks * 4, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
                             cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaStreamSynchronize(st));
@@ -839,12 +857,12 @@ extern "C" int pfnav_pool_get(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c
 int pfnav_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, pf_arrival_consts *out)
 {
     out->nearest_ok = 0; out->nearest[0] = out->nearest[1] = 0.0f; out->mc_n = 0;
-    auto it = g_routes.find(ctx);
-    if (it == g_routes.end() || layer < 0 || layer >= (int)it->second.size() || !it->second[layer].built) {
+    const pfnav_route_layer *prl = route_layer(ctx, layer);
+    if (!prl) {
         pfnav_set_error("pfnav_agents_compute_updates: pfnav_route_build(layer %d) is needed (global islands, nav.c:1731)", layer);
         return PFNAV_ERR_ARG;
     }
-    const pfnav_route_layer &RL = it->second[layer];
+    const pfnav_route_layer &RL = *prl;
     tdesc t;
     if (!desc_for_point(ctx, tx, tz, &t)) return PFNAV_OK;       // target outside the map: the reference asserts
     const int cw = ctx->chunk_w, chh = ctx->chunk_h, W = cw * 64, H = chh * 64;
@@ -953,10 +971,9 @@ int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int a
         return PFNAV_OK;
     }
     // ---- kind 1 ----
-    auto it = g_routes.find(ctx);
-    PF_ARG(it != g_routes.end() && layer < (int)it->second.size() && it->second[layer].built,
-           "pfnav_route_build(layer) is needed (global islands, nav.c:1731)");
-    const uint16_t *gisl = it->second[layer].islands.data() + (size_t)chunk * 4096;
+    const pfnav_route_layer *prl = route_layer(ctx, layer);
+    PF_ARG(prl, "pfnav_route_build(layer) is needed (global islands, nav.c:1731)");
+    const uint16_t *gisl = prl->islands.data() + (size_t)chunk * 4096;
     const uint16_t local_iid = (uint16_t)arg;
     std::vector<int> init;
     if ((q.target_type & 0xFF) == PFNAV_TARGET_TILE) {

@@ -98,7 +98,7 @@ def test_empty_and_error_paths(nav):
     with pytest.raises(capi.PfnavError):
         nav.flow_fields_update(bad)
     att = capi.tile_req((0, 0), (3, 3)); att["faction_id"] = 2
-    with pytest.raises(capi.PfnavError):           # attacking (faction-aware) fields: not implemented, must say so
+    with pytest.raises(capi.PfnavError):           # attacking (faction-aware) request before pfnav_set_enemy_factions: refused
         nav.flow_fields_update(att)
 
 
@@ -190,10 +190,10 @@ def test_agents_golden(nav, name, cw):
     vpref, vdes, los = nav.agents_read_debug(len(g["work"]))
     assert (vdes == g["vdes"]).all() and (los == g["los"]).all()
     e_vp, e_v = cases.relerr(vpref, g["vpref"]), cases.relerr(vel, g["vel"])
-    # every agent within tolerance except the documented discontinuity budget (epsilon-threshold
-    # branches of ClearPath, SURVEY.md 7 "Hard parts"): at most 0.5 % of agents
-    assert (e_vp <= VEL_RTOL).mean() >= 0.999, e_vp.max()
-    assert (e_v <= VEL_RTOL).mean() >= 0.995, e_v.max()
+    # EVERY agent within north_star's 1e-4 relative (measured on B200: <= 2e-6 for vpref, <= 3e-7 for the velocity;
+    # no agent of any committed population lands on the other side of an epsilon-threshold branch of ClearPath)
+    assert e_vp.max() <= VEL_RTOL, (e_vp.max(), np.nonzero(e_vp > VEL_RTOL)[0][:10])
+    assert e_v.max() <= VEL_RTOL, (e_v.max(), np.nonzero(e_v > VEL_RTOL)[0][:10])
 
 
 def test_agents_vdes_from_pool_golden(nav):
@@ -212,7 +212,7 @@ def test_agents_vdes_from_pool_golden(nav):
     vpref, vdes, los = nav.agents_read_debug(len(g["work"]))
     assert (los == g["los"]).all()
     assert (vdes == g["vdes"]).all()
-    assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995
+    assert cases.relerr(vel, g["vel"]).max() <= VEL_RTOL
 
 
 def test_agents_vs_port_dense_crowd(nav, pforacle):
@@ -233,8 +233,8 @@ def test_agents_vs_port_dense_crowd(nav, pforacle):
     nav.agents_tick(0)
     vel = nav.agents_read_velocities(len(work))
     vpref, _, _ = nav.agents_read_debug(len(work))
-    assert (cases.relerr(vpref, evpref) <= VEL_RTOL).mean() >= 0.999
-    assert (cases.relerr(vel, evel) <= VEL_RTOL).mean() >= 0.995
+    assert cases.relerr(vpref, evpref).max() <= VEL_RTOL
+    assert cases.relerr(vel, evel).max() <= VEL_RTOL
     # hz variants and a COMBAT_HELD agent
     rec2 = rec.copy(); rec2["flags"][work[0]] |= capi.FLAG_COMBAT_HELD
     w2 = pforacle.OracleWorld(om, rec2, fl, 10)
@@ -244,7 +244,7 @@ def test_agents_vs_port_dense_crowd(nav, pforacle):
     nav.agents_tick(0)
     vel2 = nav.agents_read_velocities(200)
     assert (vel2[0] == 0).all()
-    assert (cases.relerr(vel2, evel2) <= VEL_RTOL).mean() >= 0.995
+    assert cases.relerr(vel2, evel2).max() <= VEL_RTOL
     w.close(); w2.close()
 
 
@@ -503,15 +503,14 @@ def test_entity_update_golden(nav, name):
     nav.agents_set_work(work)
     nav.agents_tick(0)
     vel = nav.agents_read_velocities(len(work))
-    assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995
+    assert cases.relerr(vel, g["vel"]).max() <= VEL_RTOL
     nav.agents_compute_updates()
     p = nav.agents_read_patches(len(work))
     oi, of = g["patch_i"], g["patch_f"]
-    # discrete outcome: identical wherever the input velocity itself was within tolerance
-    good = cases.relerr(vel, g["vel"]) <= VEL_RTOL
+    # discrete outcome (flags, next state, blocking): identical for EVERY work item
     same = (p["flags"] == oi[:, 0].astype(np.uint32)) & (p["next_state"] == oi[:, 1]) & (p["next_block"] == oi[:, 2])
-    assert same[good].mean() >= 0.998, (same[good].mean(), np.nonzero(~same & good)[0][:10])
-    sel = same & good
+    assert same.all(), np.nonzero(~same)[0][:10]
+    sel = same
     got = np.concatenate([p["next_velocity"], p["next_pos"], p["next_rot"], p["next_ppos"], p["next_npos"],
                           p["next_step"][:, None], p["next_left"][:, None], p["next_nrot"], p["next_prot"]], axis=1)
     exp = of[:, :25]
@@ -629,7 +628,7 @@ def test_two_phase_velocity_update_is_bit_identical(nav, name, cw):
     finally:
         nav.set_two_phase(1)
     assert (out[0][0] == out[2][0]).all() and (out[0][1] == out[2][1]).all()
-    assert (cases.relerr(out[2][0], g["vel"]) <= VEL_RTOL).mean() >= 0.995
+    assert cases.relerr(out[2][0], g["vel"]).max() <= VEL_RTOL
 
 
 def test_los_with_caller_held_prev_field(nav):
@@ -843,7 +842,7 @@ def test_stress_scenario_golden(nav):
         assert (los == g["los"]).all(), tag
         assert (vdes == g["vdes"]).all(), tag
         assert (cases.relerr(vpref, g["vpref"]) <= VEL_RTOL).all(), tag
-        assert (cases.relerr(vel, g["vel"]) <= VEL_RTOL).mean() >= 0.995, tag
+        assert cases.relerr(vel, g["vel"]).max() <= VEL_RTOL, tag
 
     nav.pool_create(2, 32)
     for k, (f, cr, cc, hf, hl) in enumerate(g["pool_chunks"]):
