@@ -78,6 +78,10 @@ void pfnav_destroy(pfnav_ctx *ctx);
 int  pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nlayers,
                       float map_x, float map_z);
 
+/* map->pos: the world (x, z) of the map's top-left corner, when it is only known after the grids (a caller that
+ * mirrors an existing nav context learns it with the first world-space call). Grids are unaffected. */
+int  pfnav_map_set_pos(pfnav_ctx *ctx, float map_x, float map_z);
+
 /* Upload one layer from HOST chunk-blocked arrays ([chunk_r][chunk_c][64][64]).
  * blockers / local_islands may be NULL (treated as all 0 / left unchanged).
  * Same packed layout as N_CopyCostBasePacked / N_CopyBlockersPacked (nav.c:2432, 2462). */
@@ -150,6 +154,9 @@ int  pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float range, int fa
  * tile.c:594-599). All four corners must lie inside the map. */
 int  pfnav_blockers_incref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
 int  pfnav_blockers_decref_obb(pfnav_ctx *ctx, const float *corners_xz, int faction_id, uint32_t flags);
+/* a tick's worth of the two calls above, applied in order (delta = +1 incref, -1 decref) */
+typedef struct pfnav_blocker_op { float x, z, range; int32_t faction_id; uint32_t flags; int32_t delta; } pfnav_blocker_op;
+int  pfnav_blockers_batch(pfnav_ctx *ctx, const pfnav_blocker_op *ops, size_t n);
 int  pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out);
 /* nav_chunk::factions of one layer: out = u8 [chunks][15][64][64] */
 int  pfnav_blockers_get_factions(pfnav_ctx *ctx, int layer, uint8_t *out);
@@ -306,6 +313,12 @@ int  pfnav_pool_request_goal(pfnav_ctx *ctx, int dest, int layer, int tgt_chunk_
  * dests[ngoals]; targets: 4 ints per goal {chunk_r, chunk_c, tile_r, tile_c}. */
 int  pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
                               const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los);
+/* PFNAV_REQUEST_MISSING_ONLY: (dest, chunk) fields the pool still holds are kept -- the field cache's hit path
+ * (fieldcache.c:138-141) -- and only the missing ones (never built, invalidated by pfnav_map_commit, or evicted)
+ * are planned and built; a rebuilt LOS field reads a kept parent chunk's field out of the pool. */
+#define PFNAV_REQUEST_MISSING_ONLY (1u << 0)
+int  pfnav_pool_request_goals_ex(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer, const int32_t *targets,
+                                 uint32_t flags, void *stream, int *out_n_flow, int *out_n_los);
 /* pfnav_pool_request_goals runs the LOS dependency chains on a context-owned stream so that work which
  * does not read fields (position index, cohesion) overlaps them; pfnav_agents_tick and the pool entry
  * points order themselves after it. A caller that reads pool LOS fields through raw device pointers

@@ -84,6 +84,7 @@ SYMBOLS = [
     "pfnav_route_arrival_consts", "pfnav_entity_seeds", "pfnav_entity_fields", "pfnav_pfmap_parse", "pfnav_map_load_pfmap", "pfnav_zone_seeds", "pfnav_zone_fields", "pfnav_pool_request_zone", "pfnav_group_arrival_velocity",
     "pfnav_mgpu_shard_range", "pfnav_mgpu_unique_id", "pfnav_mgpu_init", "pfnav_mgpu_finalize", "pfnav_mgpu_gather",
     "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
+    "pfnav_pool_request_goals_ex", "pfnav_blockers_batch", "pfnav_map_set_pos",
 ]
 
 _lib = None
@@ -180,6 +181,9 @@ def load():
                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_agents_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     L.pfnav_agents_set_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_pool_request_goals_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pfnav_blockers_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.pfnav_agents_upload_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.c_int, C.c_uint32]
     L.pfnav_mgpu_shard_range.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -633,13 +637,18 @@ class Nav:
         _chk(self.L.pfnav_pool_get(self.h, dest, chunk[0], chunk[1], _p(f), _p(l), C.byref(has), C.byref(ffid)))
         return (f if has.value & 1 else None), (l if has.value & 2 else None), ffid.value
 
-    def pool_request_goals(self, dests, targets, layer=0, stream=0):
+    def pool_request_goals(self, dests, targets, layer=0, stream=0, flags=0):
         dests = np.ascontiguousarray(dests, np.int32)
         targets = np.ascontiguousarray(targets, np.int32).reshape(-1, 4)
         nf, nl = C.c_int(0), C.c_int(0)
-        _chk(self.L.pfnav_pool_request_goals(self.h, len(dests), _p(dests), layer, _p(targets), C.c_void_p(stream),
-                                             C.byref(nf), C.byref(nl)))
+        _chk(self.L.pfnav_pool_request_goals_ex(self.h, len(dests), _p(dests), layer, _p(targets), flags, C.c_void_p(stream),
+                                                C.byref(nf), C.byref(nl)))
         return nf.value, nl.value
+
+    def blockers_batch(self, ops):
+        """ops: BLOCKER_OP records {x, z, range, faction_id, flags, delta}"""
+        ops = np.ascontiguousarray(ops, BLOCKER_OP)
+        _chk(self.L.pfnav_blockers_batch(self.h, _p(ops), len(ops)))
 
     # ---- agents ----
     def agents_upload(self, agents, flocks, hz=20):
@@ -732,7 +741,7 @@ class Nav:
         """-> dict name -> (total_ms, launches_groups)"""
         ms = np.zeros(8, np.float32); cnt = np.zeros(8, np.uint32)
         _chk(self.L.pfnav_profile_read(self.h, _p(ms), _p(cnt)))
-        names = ["flow", "los", "index", "vdes", "cohesion", "velocity"]
+        names = ["flow", "los", "index", "vdes", "cohesion", "velocity", "update", "apply"]
         return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(names)}
 
     def launch_count(self):
@@ -740,6 +749,9 @@ class Nav:
 
 
 UPLOAD_SAME_FLOCKS = 1
+REQUEST_MISSING_ONLY = 1
+BLOCKER_OP = np.dtype([("x", np.float32), ("z", np.float32), ("range", np.float32), ("faction_id", np.int32),
+                       ("flags", np.uint32), ("delta", np.int32)])
 
 
 def mgpu_shard_range(n_total, rank, world):

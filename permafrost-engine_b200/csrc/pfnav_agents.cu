@@ -1450,8 +1450,8 @@ static int agents_upload_impl(pfnav_ctx *ctx, const pfnav_agent *agents, size_t 
         k_make_records<<<((int)(hi - lo) + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_records, ctx->d_flock_of, (int)lo, (int)hi);
         ctx->launches++;
     }
-    // default work list: none until pfnav_agents_set_work
-    ctx->n_work = 0;
+    // default work list: none until pfnav_agents_set_work (a same-structure re-upload keeps the current one)
+    if (!same) ctx->n_work = 0;
     if (sharded) {
         // the other ranges' records (and, when membership may have changed, flock ids) come from the peers;
         // pfnav_mgpu_gather / pfnav_group_gather follows and finishes the snapshot (index, facts, member lists)
@@ -2097,6 +2097,7 @@ extern "C" int pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream)
     up.adj_query_r = ctx->max_radius + 5.0f + 0.0625f;
     const int nwork = (int)ctx->n_work;
     const size_t b0 = ctx->n_flocks * (size_t)ctx->nlayers * sizeof(pf_arrival_dev);
+    pf_prof_scope prof(ctx, st, PF_PROF_UPDATE);
     k_entity_update<<<(nwork + 127) / 128, 128, 0, st>>>(m, grid_of(ctx), up, ctx->d_agents, ctx->d_records, ctx->d_movestate,
         ctx->d_flocks, (const pf_arrival_dev *)ctx->d_arrival, (const float2 *)((const uint8_t *)ctx->d_arrival + b0),
         ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches, ctx->d_flock_of);
@@ -2123,6 +2124,7 @@ extern "C" int pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream)
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = pf_stream(ctx, stream);
     const int nwork = (int)ctx->n_work;
+    pf_prof_scope prof(ctx, st, PF_PROF_APPLY);
     k_entity_apply<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_agents, ctx->d_movestate, ctx->d_records, ctx->d_work, nwork,
                                                        ctx->d_patches);
     ctx->launches++;
@@ -2150,10 +2152,13 @@ extern "C" int pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, 
 // ------------------------------------------------------------------------------------------
 struct pf_miss { uint32_t wi, uid; int32_t dest, chunk, tile, liid; float px, pz; };
 
-// work agents whose own tile has no flow direction in the pool (field absent, or dir_idx == FD_NONE)
+// work agents that would take one of the on-miss branches of the navigation tick:
+//   kind 0  compute_los_state -> N_HasDestLOS (nav.c:4026): no LOS field for (dest, chunk of prev_pos)
+//   kind 1  compute_desired_velocity -> N_DesiredPointSeekVelocity (nav.c:3468): no flow field for (dest, chunk of
+//           pos), or the agent's own tile has no direction (dir_idx == FD_NONE)
 __global__ void k_collect_misses(MapView m, PoolView pool, const uint16_t *__restrict__ liid_img,
                                  const pfnav_agent *__restrict__ agents, const pfnav_flock *__restrict__ flocks,
-                                 const uint32_t *__restrict__ work, int nwork, pf_miss *__restrict__ out,
+                                 const uint32_t *__restrict__ work, int nwork, int kind, pf_miss *__restrict__ out,
                                  uint32_t *__restrict__ count, uint32_t cap)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2163,22 +2168,35 @@ __global__ void k_collect_misses(MapView m, PoolView pool, const uint16_t *__res
     if (a.flock < 0) return;
     const pfnav_flock fl = flocks[a.flock];
     if (fl.dest < 0 || fl.dest >= pool.ndests) return;
+    const float px = kind == 0 ? a.prev_pos[0] : a.pos[0], pz = kind == 0 ? a.prev_pos[1] : a.pos[1];
     tile_desc t;
-    if (!desc_for_point(m, a.pos[0], a.pos[1], t)) return;
+    if (!desc_for_point(m, px, pz, t)) return;
     const int chunks = m.chunk_w * m.chunk_h, chunk = t.chunk_r * m.chunk_w + t.chunk_c;
     const int s = pool.slot[(size_t)fl.dest * chunks + chunk];
-    bool miss = (s < 0) || !(pool.has[s] & 1);
-    if (!miss) miss = (pool.flow[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 0xF) == 0;
+    bool miss;
+    if (kind == 0) miss = (s < 0) || !(pool.has[s] & 2);
+    else {
+        miss = (s < 0) || !(pool.has[s] & 1);
+        if (!miss) miss = (pool.flow[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 0xF) == 0;
+    }
     if (!miss) return;
     const uint32_t k = atomicAdd(count, 1u);
     if (k >= cap) return;
     pf_miss r;
     r.wi = (uint32_t)w; r.uid = uid; r.dest = fl.dest; r.chunk = chunk; r.tile = t.tile_r * 64 + t.tile_c;
     r.liid = liid_img[((size_t)fl.layer * m.H64 + t.chunk_r * 64 + t.tile_r) * m.W64 + t.chunk_c * 64 + t.tile_c];
-    r.px = a.pos[0]; r.pz = a.pos[1];
+    r.px = px; r.pz = pz;
     out[k] = r;
 }
 
+// The on-miss branches of one navigation tick against the device pool, in the reference's order: first every
+// work item's LOS state (compute_los_state, movement.c:4129: a (dest, chunk) without LOS field requests the path
+// from the entity's previous position), then every work item's desired velocity (compute_desired_velocity, :4163:
+// request from the entity's position, then the in-place field repair if its tile still has no direction). The
+// reference walks the entities serially and every request changes what the next entity finds; here the candidates
+// are collected on the device, reduced to one representative per (dest, chunk[, local island | blocked tile]) in work
+// order, and each representative is RE-CHECKED against the pool as the requests before it left it -- an entity the
+// reference would have found served by an earlier entity's request does not request again.
 extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nrepairs)
 {
     PF_ARG(ctx && ctx->d_agents && ctx->d_pool_slot, "agents / pool missing");
@@ -2190,81 +2208,100 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
     cudaStream_t st = ctx->tick_stream;
     PF_CUDA(cudaDeviceSynchronize());
     const int nwork = (int)ctx->n_work;
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
     pf_miss *d_miss = nullptr; uint32_t *d_cnt = nullptr;
     PF_CUDA(cudaMalloc(&d_miss, (size_t)nwork * sizeof(pf_miss)));
     if (cudaMalloc(&d_cnt, 4) != cudaSuccess) { cudaFree(d_miss); pfnav_set_error("cudaMalloc"); return PFNAV_ERR_NOMEM; }
-    cudaMemsetAsync(d_cnt, 0, 4, st);
     MapView m;
     m.cost = ctx->d_cost; m.blk = ctx->d_blk; m.W64 = ctx->W64; m.H64 = ctx->H64;
     m.chunk_w = ctx->chunk_w; m.chunk_h = ctx->chunk_h; m.map_x = ctx->map_x; m.map_z = ctx->map_z;
-    PoolView pv;
-    pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
-    pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
-    pv.touch = nullptr; pv.tick_no = 0;
-    k_collect_misses<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_liid, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
-                                                         d_miss, d_cnt, (uint32_t)nwork);
-    ctx->launches++;
-    uint32_t cnt = 0;
-    cudaError_t e = cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    std::vector<pf_miss> miss(std::min<uint32_t>(cnt, (uint32_t)nwork));
-    if (e == cudaSuccess && !miss.empty())
-        e = cudaMemcpy(miss.data(), d_miss, miss.size() * sizeof(pf_miss), cudaMemcpyDeviceToHost);
-    cudaFree(d_miss); cudaFree(d_cnt);
-    if (e != cudaSuccess) { pfnav_set_error("pfnav_pool_repair: %s", cudaGetErrorString(e)); return PFNAV_ERR_CUDA; }
-    if (miss.empty()) return PFNAV_OK;
-    // the reference walks the entities in work order; one representative per (dest, chunk, island | tile)
-    std::sort(miss.begin(), miss.end(), [](const pf_miss &a, const pf_miss &b) { return a.wi < b.wi; });
-    std::vector<pf_miss> reps;
-    {
+    std::vector<int> flock_of_dest(ctx->pool_ndests, -1);
+    for (size_t f = 0; f < ctx->h_flocks.size(); f++)
+        if (ctx->h_flocks[f].dest >= 0 && ctx->h_flocks[f].dest < ctx->pool_ndests) flock_of_dest[ctx->h_flocks[f].dest] = (int)f;
+    int nreq = 0, nrep = 0, rc = 0;
+    auto collect = [&](int kind, std::vector<pf_miss> &reps) -> int {
+        PoolView pv;
+        pv.slot = ctx->d_pool_slot; pv.flow = ctx->d_pool_flow; pv.los = ctx->d_pool_los;
+        pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
+        pv.touch = nullptr; pv.tick_no = 0;
+        PF_CUDA(cudaMemsetAsync(d_cnt, 0, 4, st));
+        k_collect_misses<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_liid, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
+                                                             kind, d_miss, d_cnt, (uint32_t)nwork);
+        ctx->launches++;
+        uint32_t cnt = 0;
+        PF_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        PF_CUDA(cudaStreamSynchronize(st));
+        std::vector<pf_miss> miss(std::min<uint32_t>(cnt, (uint32_t)nwork));
+        if (!miss.empty()) PF_CUDA(cudaMemcpy(miss.data(), d_miss, miss.size() * sizeof(pf_miss), cudaMemcpyDeviceToHost));
+        std::sort(miss.begin(), miss.end(), [](const pf_miss &a, const pf_miss &b) { return a.wi < b.wi; });
         std::vector<uint64_t> seen;
+        reps.clear();
         for (const pf_miss &r : miss) {
-            const uint64_t key = ((uint64_t)r.dest << 40) | ((uint64_t)r.chunk << 20) |
-                                 (r.liid == 0xFFFF ? (0x10000u | (uint32_t)r.tile) : (uint32_t)r.liid);
+            uint64_t key = ((uint64_t)r.dest << 40) | ((uint64_t)r.chunk << 20);
+            if (kind == 1) key |= (r.liid == 0xFFFF ? (0x10000u | (uint32_t)r.tile) : (uint32_t)r.liid);
             if (std::find(seen.begin(), seen.end(), key) != seen.end()) continue;
             seen.push_back(key);
             reps.push_back(r);
         }
-    }
-    const int chunks = ctx->chunk_w * ctx->chunk_h;
-    // (1) n_request_path from the entity's own position (nav.c:3486, 3499)
-    int nreq = 0;
-    std::vector<int> flock_of_dest(ctx->pool_ndests, -1);
-    for (size_t f = 0; f < ctx->h_flocks.size(); f++)
-        if (ctx->h_flocks[f].dest >= 0 && ctx->h_flocks[f].dest < ctx->pool_ndests) flock_of_dest[ctx->h_flocks[f].dest] = (int)f;
-    std::vector<uint8_t> path_ok(reps.size(), 0);
-    for (size_t k = 0; k < reps.size(); k++) {
-        const pf_miss &r = reps[k];
+        return 0;
+    };
+    auto request_from = [&](const pf_miss &r, int *ok) -> int {
         const int f = flock_of_dest[r.dest];
-        if (f < 0) continue;
+        *ok = 0;
+        if (f < 0) return 0;
         const pfnav_flock &fl = ctx->h_flocks[f];
-        int ok = 0, nf = 0, nl = 0; uint32_t did = 0;
-        int rc = pfnav_pool_request_path(ctx, r.dest, fl.layer, r.px, r.pz, fl.target[0], fl.target[1], nullptr, &did, &ok, &nf, &nl);
-        if (rc) return rc;
-        path_ok[k] = ok ? 1 : 0;        // no path from here: the reference returns a zero vector and repairs nothing (nav.c:3501)
+        int nf = 0, nl = 0; uint32_t did = 0;
+        int rc2 = pfnav_pool_request_path(ctx, r.dest, fl.layer, r.px, r.pz, fl.target[0], fl.target[1], nullptr, &did, ok, &nf, &nl);
+        if (rc2) return rc2;
         if (nf + nl > 0) nreq++;
+        return 0;
+    };
+    std::vector<pf_miss> reps;
+    // ---- LOS state (N_HasDestLOS, nav.c:4038-4045) ----
+    if (!(rc = collect(0, reps))) {
+        for (const pf_miss &r : reps) {
+            const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
+            if (slot >= 0 && (ctx->h_pool_has[slot] & 2)) continue;          // an earlier entity's request built it
+            int ok;
+            if ((rc = request_from(r, &ok))) break;
+        }
     }
-    PF_CUDA(cudaDeviceSynchronize());
-    // (2) still FD_NONE -> repair the field in place (nav.c:3520-3546)
-    std::vector<pfnav_field_req> tg; std::vector<int32_t> kinds, args, slots;
-    for (size_t k = 0; k < reps.size(); k++) {
-        const pf_miss &r = reps[k];
-        if (!path_ok[k]) continue;
-        const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
-        if (slot < 0 || !(ctx->h_pool_has[slot] & 1)) continue;          // no path: the reference returns a zero vector
-        uint8_t dir = 0;
-        PF_CUDA(cudaMemcpy(&dir, ctx->d_pool_flow + (size_t)slot * 4096 + r.tile, 1, cudaMemcpyDeviceToHost));
-        if ((dir & 0xF) != 0) continue;                                   // case 1: the path query fixed it
-        tg.push_back(ctx->h_pool_req[slot]);
-        slots.push_back(slot);
-        if (r.liid == 0xFFFF) { kinds.push_back(PFNAV_REPAIR_NEAREST_PATHABLE); args.push_back(((r.tile >> 6) << 8) | (r.tile & 63)); }
-        else                  { kinds.push_back(PFNAV_REPAIR_ISLAND_TO_NEAREST); args.push_back(r.liid); }
+    // ---- desired velocity (N_DesiredPointSeekVelocity, nav.c:3483-3554) ----
+    if (!rc && !(rc = collect(1, reps))) {
+        for (const pf_miss &r : reps) {
+            auto dir_now = [&](int *dir) -> int {          // the tile's direction as the pool holds it right now, -1 = no field
+                const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
+                *dir = -1;
+                if (slot < 0 || !(ctx->h_pool_has[slot] & 1)) return 0;
+                uint8_t d = 0;
+                PF_CUDA(cudaDeviceSynchronize());
+                PF_CUDA(cudaMemcpy(&d, ctx->d_pool_flow + (size_t)slot * 4096 + r.tile, 1, cudaMemcpyDeviceToHost));
+                *dir = d & 0xF;
+                return 0;
+            };
+            int dir;
+            if ((rc = dir_now(&dir))) break;
+            if (dir > 0) continue;                                        // served by an earlier entity's request / repair
+            int ok;
+            if ((rc = request_from(r, &ok))) break;
+            if (!ok) continue;                                            // no path from here: zero vector, nothing repaired (nav.c:3501)
+            if ((rc = dir_now(&dir))) break;
+            if (dir != 0) continue;                                       // case 1: the path query fixed it (or no field: no path)
+            const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
+            const pfnav_field_req tg = ctx->h_pool_req[slot];
+            int32_t kind, arg;
+            if (r.liid == 0xFFFF) { kind = PFNAV_REPAIR_NEAREST_PATHABLE; arg = ((r.tile >> 6) << 8) | (r.tile & 63); }
+            else                  { kind = PFNAV_REPAIR_ISLAND_TO_NEAREST; arg = r.liid; }
+            const int32_t sl = slot;
+            if ((rc = pfnav_flow_repair_pool(ctx, &tg, &kind, &arg, &sl, 1))) break;
+            nrep++;
+        }
     }
-    int rc = pfnav_flow_repair_pool(ctx, tg.data(), kinds.data(), args.data(), slots.data(), tg.size());
+    cudaFree(d_miss); cudaFree(d_cnt);
     if (rc) return rc;
-    if (!tg.empty() || nreq) ctx->goal_batch.valid = ctx->goal_batch.valid && tg.empty();   // pool bytes changed under a resident plan
+    if (nrep) ctx->goal_batch.valid = false;      // pool bytes changed under a resident plan
     if (out_nrequests) *out_nrequests = nreq;
-    if (out_nrepairs) *out_nrepairs = (int)tg.size();
+    if (out_nrepairs) *out_nrepairs = nrep;
     return PFNAV_OK;
 }
 

@@ -354,6 +354,18 @@ extern "C" int pfnav_blockers_decref(pfnav_ctx *ctx, float x, float z, float ran
     return blockers_circle(ctx, x, z, range, faction_id, flags, -1);
 }
 
+// A tick's worth of N_BlockersIncref / N_BlockersDecref calls (nav.c:4663-4683) in one call, applied in order.
+extern "C" int pfnav_blockers_batch(pfnav_ctx *ctx, const pfnav_blocker_op *ops, size_t n)
+{
+    PF_ARG(ctx && ctx->d_cost && (n == 0 || ops), "map not created / null");
+    for (size_t i = 0; i < n; i++) {
+        PF_ARG(ops[i].delta == 1 || ops[i].delta == -1, "blocker op: delta must be +1 or -1");
+        int rc = blockers_circle(ctx, ops[i].x, ops[i].z, ops[i].range, ops[i].faction_id, ops[i].flags, ops[i].delta);
+        if (rc) return rc;
+    }
+    return PFNAV_OK;
+}
+
 // N_Update + N_ApplyDeferredInvalidations: recompute the local islands of every dirty chunk, refresh the
 // portal edge states there, push the chunk (blockers + islands) to the device, and invalidate pool
 // entries: everything AT a dirty chunk; and, when an edge state flipped, every field of every

@@ -1580,6 +1580,13 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     return PFNAV_OK;
 }
 
+extern "C" int pfnav_map_set_pos(pfnav_ctx *ctx, float map_x, float map_z)
+{
+    PF_ARG(ctx && ctx->d_cost, "map not created");
+    if (ctx->map_x != map_x || ctx->map_z != map_z) { ctx->map_x = map_x; ctx->map_z = map_z; ctx->map_epoch++; ctx->arrival_valid = false; }
+    return PFNAV_OK;
+}
+
 static int refresh_unit_flags(pfnav_ctx *ctx, int layer)
 {
     const int chunks = ctx->chunk_w * ctx->chunk_h;

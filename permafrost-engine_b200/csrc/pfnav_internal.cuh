@@ -222,7 +222,7 @@ int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk);
 int pf_pool_reserve(pfnav_ctx *ctx, const size_t *keys, size_t n, int32_t *slots_out, bool *out_evicted);
 
 enum { PF_PROF_FLOW = 0, PF_PROF_LOS = 1, PF_PROF_INDEX = 2, PF_PROF_VDES = 3, PF_PROF_COHESION = 4,
-       PF_PROF_VELOCITY = 5, PF_PROF_SLOTS = 8 };
+       PF_PROF_VELOCITY = 5, PF_PROF_UPDATE = 6, PF_PROF_APPLY = 7, PF_PROF_SLOTS = 8 };
 
 // RAII helper: brackets the launches of one kernel group with events when profiling is on
 struct pf_prof_scope {

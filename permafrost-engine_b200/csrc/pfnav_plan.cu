@@ -12,8 +12,10 @@
 // field for that request. The cost-faithful search is listed under "next" in DESIGN.md.
 #include "pfnav_internal.cuh"
 #include <algorithm>
+#include <atomic>
 #include <deque>
 #include <string.h>
+#include <thread>
 
 static inline size_t chunk_off(const pfnav_ctx *ctx, int layer, int cr, int cc)
 {
@@ -360,6 +362,13 @@ static int los_forked(pfnav_ctx *ctx)
 extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
                                         const int32_t *targets, void *stream, int *out_n_flow, int *out_n_los)
 {
+    return pfnav_pool_request_goals_ex(ctx, ngoals, dests, layer, targets, 0, stream, out_n_flow, out_n_los);
+}
+
+extern "C" int pfnav_pool_request_goals_ex(pfnav_ctx *ctx, int ngoals, const int32_t *dests, int layer,
+                                           const int32_t *targets, uint32_t flags, void *stream, int *out_n_flow, int *out_n_los)
+{
+    const bool missing_only = (flags & PFNAV_REQUEST_MISSING_ONLY) != 0;
     PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
     PF_NEED_DEVICE(ctx);
     PF_ARG(ngoals >= 0 && (ngoals == 0 || (dests && targets)), "goals");
@@ -369,7 +378,7 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     const int chunks = ctx->chunk_w * ctx->chunk_h;
     {   // fast path: the same batch on an unchanged map and pool -> the plan is still resident on the device
         auto &gb = ctx->goal_batch;
-        if (gb.valid && gb.epoch == ctx->map_epoch && gb.layer == layer && (int)gb.dests.size() == ngoals &&
+        if (!missing_only && gb.valid && gb.epoch == ctx->map_epoch && gb.layer == layer && (int)gb.dests.size() == ngoals &&
             memcmp(gb.dests.data(), dests, (size_t)ngoals * 4) == 0 && memcmp(gb.targets.data(), targets, (size_t)ngoals * 16) == 0) {
             PF_CUDA(cudaSetDevice(ctx->device));
             cudaStream_t st = pf_stream(ctx, stream);
@@ -397,29 +406,68 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
     }
     PF_CUDA(pf_fields_sync(ctx));       // the plan buffer below may still be read by a forked LOS kernel
     const int cap = chunks * 8 + 8;
-    std::vector<pfnav_field_req> fr(cap), all_fr;
-    std::vector<pfnav_los_req> lr(cap), all_lr;
-    std::vector<int32_t> fc(cap), fw(cap), lc(cap), all_fs, all_fw, all_ls, all_ld;
+    std::vector<pfnav_field_req> all_fr;
+    std::vector<pfnav_los_req> all_lr;
+    std::vector<int32_t> all_fs, all_fw, all_ls, all_ld;
     std::vector<size_t> fkeys, lkeys;
+    for (int g = 0; g < ngoals; g++) PF_ARG(dests[g] >= 0 && dests[g] < ctx->pool_ndests, "dest");
+    // the goals are planned independently of each other (read-only walks over the host mirrors): one host thread each
+    struct goal_plan { std::vector<pfnav_field_req> fr; std::vector<pfnav_los_req> lr; std::vector<int32_t> fc, fw, lc; int nf = 0, nl = 0, rc = 0; std::string err; };
+    std::vector<goal_plan> plans(ngoals);
+    {
+        auto plan_one = [&](int g) {
+            goal_plan &P = plans[g];
+            P.fr.resize(cap); P.lr.resize(cap); P.fc.resize(cap); P.fw.resize(cap); P.lc.resize(cap);
+            P.rc = pfnav_plan_goal(ctx, layer, targets[4 * g], targets[4 * g + 1], targets[4 * g + 2], targets[4 * g + 3],
+                                   P.fr.data(), P.fc.data(), P.fw.data(), cap, &P.nf, P.lr.data(), P.lc.data(), cap, &P.nl);
+            if (P.rc) P.err = pfnav_last_error();          // the error text is thread-local
+        };
+        const int nthreads = std::max(1, std::min({ngoals, (int)std::thread::hardware_concurrency(), 32}));
+        if (nthreads == 1) { for (int g = 0; g < ngoals; g++) plan_one(g); }
+        else {
+            std::atomic<int> next{0};
+            std::vector<std::thread> pool;
+            auto worker = [&]() { for (int g = next.fetch_add(1); g < ngoals; g = next.fetch_add(1)) plan_one(g); };
+            for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+            worker();
+            for (auto &t : pool) t.join();
+        }
+    }
     for (int g = 0; g < ngoals; g++) {
-        PF_ARG(dests[g] >= 0 && dests[g] < ctx->pool_ndests, "dest");
-        int nf = 0, nl = 0;
-        int rc = pfnav_plan_goal(ctx, layer, targets[4 * g], targets[4 * g + 1], targets[4 * g + 2], targets[4 * g + 3],
-                                 fr.data(), fc.data(), fw.data(), cap, &nf, lr.data(), lc.data(), cap, &nl);
-        if (rc) return rc;
+        goal_plan &P = plans[g];
+        if (P.rc) { pfnav_set_error("%s", P.err.c_str()); return P.rc; }
+        const int nf = P.nf, nl = P.nl;
+        const pfnav_field_req *fr = P.fr.data(); const pfnav_los_req *lr = P.lr.data();
+        const int32_t *fc = P.fc.data(), *fw = P.fw.data(), *lc = P.lc.data();
+        // PFNAV_REQUEST_MISSING_ONLY: fields the pool still holds for this destination are kept, like a field-cache hit
+        // (fieldcache.c:138-141); a rebuilt LOS field whose parent chunk is kept reads the parent out of its pool slot
+        auto held = [&](int chunk, uint8_t bit) {
+            if (!missing_only) return false;
+            const int sl = ctx->h_pool_slot[(size_t)dests[g] * chunks + chunk];
+            return sl >= 0 && (ctx->h_pool_has[sl] & bit);
+        };
         for (int i = 0; i < nf; i++) {
+            if (held(fc[i], 1)) continue;
             all_fr.push_back(fr[i]); all_fw.push_back(fw[i]);
             fkeys.push_back((size_t)dests[g] * chunks + fc[i]);
         }
-        const int lbase = (int)all_lr.size();
-        std::vector<int> depth(nl, 0);
+        std::vector<int> depth(nl, 0), newpos(nl, -1);
         for (int i = 0; i < nl; i++) {
+            if (held(lc[i], 2)) continue;
             pfnav_los_req q = lr[i];
-            if (q.prev_index >= 0) { depth[i] = depth[q.prev_index] + 1; q.prev_index += lbase; }
+            if (q.prev_index >= 0) {
+                if (newpos[q.prev_index] >= 0) { depth[i] = depth[q.prev_index] + 1; q.prev_index = newpos[q.prev_index]; }
+                else {
+                    q.prev_index = -2;      // parent kept: its absolute pool slot rides in _pad
+                    q._pad = ctx->h_pool_slot[(size_t)dests[g] * chunks + q.prev_chunk_r * ctx->chunk_w + q.prev_chunk_c];
+                }
+            }
+            newpos[i] = (int)all_lr.size();
             all_lr.push_back(q); all_ld.push_back(depth[i]);
             lkeys.push_back((size_t)dests[g] * chunks + lc[i]);
         }
     }
+    if (all_fr.empty() && all_lr.empty()) return PFNAV_OK;
     const int nf = (int)all_fr.size(), nl = (int)all_lr.size();
     {   // slots for everything the batch writes, all or nothing (nothing is published before this succeeds)
         std::vector<size_t> keys(fkeys);
@@ -489,13 +537,13 @@ extern "C" int pfnav_pool_request_goals(pfnav_ctx *ctx, int ngoals, const int32_
         rc = pfnav_flow_launch(ctx, dfr + first, cnt, ctx->d_pool_flow, dfs + first, ctx->flow_stream);
         if (rc) return rc;
     }
-    rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), ctx->field_stream);
+    if (nl) rc = pfnav_los_launch(ctx, dlr, nl, ctx->d_pool_los, dls, maxd + 1, lwave_off.data(), ctx->field_stream);
     if (rc) return rc;
     rc = los_forked(ctx);
     if (rc) return rc;
     {
         auto &gb = ctx->goal_batch;
-        gb.valid = true; gb.epoch = ctx->map_epoch; gb.layer = layer;
+        gb.valid = !missing_only; gb.epoch = ctx->map_epoch; gb.layer = layer;
         gb.dests.assign(dests, dests + ngoals); gb.targets.assign(targets, targets + 4 * (size_t)ngoals);
         gb.nf = nf; gb.nl = nl; gb.fwave_off = fwave_off; gb.b_fr = b_fr; gb.b_fs = b_fs; gb.b_lr = b_lr; gb.b_ls = b_ls;
     }

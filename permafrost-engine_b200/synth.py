@@ -116,10 +116,13 @@ def random_passable_tiles(cost_blocked, n, rng):
 
 
 def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, max_speed=20.0,
-                spacing=2.6, hz=20, map_x=0.0, map_z=0.0, goal_min_dist=150.0):
+                spacing=2.6, hz=20, map_x=0.0, map_z=0.0, goal_min_dist=150.0, cells=None):
     """Agent population: `nflocks` discs of agents on passable ground, hex-packed at `spacing` x radius,
     each flock with a seeded goal tile at least `goal_min_dist` wu away (so group arrival stays
-    inactive, arrival.c:57).  Returns dict of numpy arrays."""
+    inactive, arrival.c:57).  Returns dict of numpy arrays.
+    cells = (per_side, first): flock f is confined to cell `first + f` of a per_side x per_side grid over the map and
+    spawns around that cell's centre, so flocks never overlap and the local density does not depend on how many
+    flocks exist (weak-scaling populations)."""
     rng = Xoshiro(seed)
     g = rng.numpy()
     img = blocked_to_image(cost_blocked, chunk_w, chunk_h)
@@ -138,6 +141,19 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
         step = spacing * float(radii[f])
         # spawn centre
         cr, cc = passable[g.integers(0, len(passable))]
+        bx0 = bz0 = -np.inf; bx1 = bz1 = np.inf
+        if cells is not None:
+            per_side, first = cells
+            cell = first + f
+            assert cell < per_side * per_side, "more flocks than grid cells"
+            cell_w, cell_h = W64 * NAV_TILE / per_side, H64 * NAV_TILE / per_side
+            gr_, gc_ = cell // per_side, cell % per_side
+            bx1 = map_x - gc_ * cell_w; bx0 = bx1 - cell_w          # x decreases with the column
+            bz0 = map_z + gr_ * cell_h; bz1 = bz0 + cell_h
+            # nearest passable tile to the cell centre
+            ctr_r = (gr_ + 0.5) * cell_h / NAV_TILE; ctr_c = (gc_ + 0.5) * cell_w / NAV_TILE
+            k_ = np.argmin((passable[:, 0] - ctr_r) ** 2 + (passable[:, 1] - ctr_c) ** 2)
+            cr, cc = passable[k_]
         cx = map_x - (cc + 0.5) * NAV_TILE
         cz = map_z + (cr + 0.5) * NAV_TILE
         need = per[f]
@@ -154,11 +170,14 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
             order = np.argsort(d2, axis=None, kind="stable")
             xs = xs.ravel()[order]; zs = zs.ravel()[order]
             inside = (xs < map_x - 1) & (xs > map_x - W64 * NAV_TILE + 1) & (zs > map_z + 1) & (zs < map_z + H64 * NAV_TILE - 1)
+            inside &= (xs > bx0 + 1) & (xs < bx1 - 1) & (zs > bz0 + 1) & (zs < bz1 - 1)
             xs = xs[inside]; zs = zs[inside]
             tr, tc = tile_for_xz(xs, zs, chunk_w, chunk_h, map_x, map_z)
             ok = img[tr, tc] != 0xFF
             xs = xs[ok]; zs = zs[ok]
             got = len(xs)
+            if got < need and R * step > 4 * max(W64, H64) * NAV_TILE:
+                raise ValueError("flock %d: %d agents at spacing %.2f do not fit its area" % (f, need, step))
             R *= 2
         pos[k:k + need, 0] = xs[:need]
         pos[k:k + need, 1] = zs[:need]
