@@ -460,7 +460,9 @@ typedef struct pfnav_agent {
     uint32_t flags;         /* PFNAV_FLAG_*                                */
     int32_t  flock;         /* index into flocks, -1 = none                */
     uint32_t has_dest_los;  /* in: ignored when computed from the pool     */
-    uint32_t _pad;
+    uint32_t aux_dest1;     /* 1 + field-pool destination of this entity's TARGET_ENEMIES fields (STATE_SEEK_ENEMIES,
+                             * M_NavDesiredEnemySeekVelocity) or TARGET_ENTITY fields (STATE_SURROUND_ENTITY,
+                             * M_NavDesiredSurroundVelocity), built with pfnav_pool_request_entity_fields; 0 = none */
 } pfnav_agent;
 
 typedef struct pfnav_flock {
@@ -520,9 +522,8 @@ int  pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_t nwork);
 
 /* ---------------------------------------------------------------------------------------- */
 /* State update: entity_compute_update (game/movement.c:2303-2650) on the device, one
- * `struct movestate_patch` (movement.c:245-262) per work item, for the point-seek states the velocity
- * pass covers (STATE_MOVING / STATE_SEEK_ENEMIES; formation, surround, enter-range and turning states
- * belong to engine subsystems outside this path and are rejected). The engine applies the patches on
+ * `struct movestate_patch` (movement.c:245-262) per work item, for every movement state (the formation inputs
+ * and the state beyond point seeking arrive through pfnav_formation_in / pfnav_movestate_ext). The engine applies the patches on
  * its main thread (entity_apply_update, movement.c:2693: blockers, events, G_Pos_Set);
  * pfnav_agents_apply_updates is the device-side equivalent for the movestate fields so that
  * consecutive ticks can run without a host round trip. */
@@ -538,6 +539,44 @@ typedef struct pfnav_movestate {        /* the part of struct movestate (movemen
     int32_t _pad[2];
 } pfnav_movestate;                      /* 176 bytes */
 
+/* The formation inputs of one work item: struct formation_state + cell_pos + cell_arrival_vdes of struct move_work_in
+ * (movement.c:215-225, 264-276). formation.c computes them on the main thread (G_Formation_*); the velocity pass and
+ * the state update read them (STATE_MOVING_IN_FORMATION / STATE_ARRIVING_TO_CELL). 64 bytes. */
+#define PFNAV_FORM_HAS_FORMATION    (1u << 0)   /* fstate.fid != NULL_FID */
+#define PFNAV_FORM_ASSIGNMENT_READY (1u << 1)
+#define PFNAV_FORM_ASSIGNED_TO_CELL (1u << 2)
+#define PFNAV_FORM_IN_RANGE_OF_CELL (1u << 3)
+#define PFNAV_FORM_ARRIVED_AT_CELL  (1u << 4)
+typedef struct pfnav_formation_in {
+    float    cell_pos[2];            /* in->cell_pos                                   */
+    float    cell_arrival_vdes[2];   /* in->cell_arrival_vdes: the desired velocity of STATE_ARRIVING_TO_CELL */
+    float    cohesion[2];            /* fstate.normal_cohesion_force                   */
+    float    align[2];               /* fstate.normal_align_force                      */
+    float    drag[2];                /* fstate.normal_drag_force                       */
+    float    target_orientation[4];  /* fstate.target_orientation                      */
+    uint32_t flags;                  /* PFNAV_FORM_*                                   */
+    uint32_t _pad;
+} pfnav_formation_in;
+/* HOST array, one record per entity of this context's own range (uid order). Optional: without it every entity is
+ * outside any formation (fid == NULL_FID). */
+int  pfnav_agents_upload_formation(pfnav_ctx *ctx, const pfnav_formation_in *f, size_t n);
+
+/* The rest of struct movestate (movement.c:146-215) that the states beyond point seeking read. 64 bytes. */
+#define PFNAV_NULL_UID 0xffffffffu
+typedef struct pfnav_movestate_ext {
+    int32_t  wait_prev;              /* ms->wait_prev (enum pfnav_move_state)          */
+    int32_t  wait_ticks_left;
+    uint32_t surround_target_uid;    /* PFNAV_NULL_UID = none; also the target of STATE_ENTER_ENTITY_RANGE */
+    uint32_t using_surround_field;
+    float    target_range;           /* STATE_ENTER_ENTITY_RANGE                       */
+    float    target_prev_pos[2];
+    float    _padf;
+    float    target_dir[4];          /* STATE_TURNING: ms->target_dir                  */
+    float    rot[4];                 /* Entity_GetRot(uid), what Entity_SetRot last set */
+} pfnav_movestate_ext;
+/* HOST array, own range, uid order. Optional: zero / NULL_UID defaults. */
+int  pfnav_agents_upload_movestate_ext(pfnav_ctx *ctx, const pfnav_movestate_ext *ms, size_t n);
+
 /* enum movestate_flags (movement.c:226-242), same bit values */
 #define PFNAV_UPDATE_SET_STATE        (1u << 0)
 #define PFNAV_UPDATE_SET_VELOCITY     (1u << 1)
@@ -549,13 +588,24 @@ typedef struct pfnav_movestate {        /* the part of struct movestate (movemen
 #define PFNAV_UPDATE_SET_LEFT         (1u << 7)
 #define PFNAV_UPDATE_SET_NEXT_ROT     (1u << 8)
 #define PFNAV_UPDATE_SET_PREV_ROT     (1u << 9)
+#define PFNAV_UPDATE_SET_DEST         (1u << 10)
+#define PFNAV_UPDATE_SET_TARGET_PREV  (1u << 11)
+#define PFNAV_UPDATE_SET_MOVING       (1u << 12)
+#define PFNAV_UPDATE_SET_TARGET_DIR   (1u << 13)
 #define PFNAV_UPDATE_TURNING_IN_PLACE (1u << 14)
+/* engine_todo: what the device pass leaves to the engine for this work item */
+#define PFNAV_TODO_SURROUND_QUERY     (1u << 0)  /* STATE_SURROUND_ENTITY with a live target: the branch decisions of
+                                                  * movement.c:2513-2567 need the target's geometry (M_NavObjAdjacentFrom,
+                                                  * M_NavClosestReachableAdjacentPosFrom: OBBs, entity tables) -- the movement
+                                                  * part of the patch is complete, the state decision is the engine's */
+#define PFNAV_TODO_USE_SURROUND_FIELD  (1u << 1) /* ent_update_using_surround_field (movement.c:2672): ms->using_surround_field */
+#define PFNAV_TODO_DROP_SURROUND_FIELD (1u << 2) /* ... switches on / off (low / high water marks of the distance to the target) */
 
 typedef struct pfnav_patch {            /* struct movestate_patch (movement.c:245-262); unselected fields are 0 */
     uint32_t flags;
-    int32_t  next_state;                /* -1 unless SET_STATE                            */
+    int32_t  next_state;                /* -1 unless SET_STATE / SET_MOVING               */
     int32_t  next_block;
-    int32_t  _pad;
+    int32_t  next_attack;
     float    next_velocity[2];
     float    next_pos[3];               /* y: 0 (AIR_UNIT_HEIGHT for air units); terrain height
                                          * (M_HeightAtPoint) is render state, added by the engine  */
@@ -566,8 +616,13 @@ typedef struct pfnav_patch {            /* struct movestate_patch (movement.c:24
     float    next_left;
     float    next_nrot[4];
     float    next_prot[4];
-    float    _padf[3];
-} pfnav_patch;                          /* 128 bytes */
+    int32_t  wait_ticks_left;           /* ms->wait_ticks_left after the call (entity_compute_update counts it down in place) */
+    uint32_t engine_todo;               /* PFNAV_TODO_*                                    */
+    float    _padf;
+    float    next_dest[2];              /* UPDATE_SET_DEST: the engine re-issues the move order (G_Move_SetDest) */
+    float    next_target_prev[2];
+    float    next_target_dir[4];
+} pfnav_patch;                          /* 160 bytes */
 
 /* Inspection / test entry: the two map searches of arrived() (movement.c:2170) for a flock target on `layer`, as
  * pfnav_agents_compute_updates precomputes them per (flock, layer): N_ClosestPathable (nav.c:4126) and the tile
@@ -579,7 +634,9 @@ int  pfnav_route_arrival_consts(pfnav_ctx *ctx, int layer, float tx, float tz, i
 int  pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movestate *ms, size_t n);
 /* After pfnav_agents_tick on the same stream: entity_compute_update for every work item, reading the
  * tick's new velocities and desired velocities. Needs pfnav_route_build for every layer the agents
- * use (global islands feed arrived(), movement.c:2170). */
+ * use (global islands feed arrived(), movement.c:2170). Every movement state is accepted: MOVING / MOVING_IN_FORMATION
+ * (formation inputs), SEEK_ENEMIES, ENTER_ENTITY_RANGE, TURNING, WAITING, ARRIVING_TO_CELL are decided on the device;
+ * SURROUND_ENTITY with a live target is flagged PFNAV_TODO_SURROUND_QUERY (see there). */
 int  pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream);
 /* Work-item order. Blocks until the update pass has finished. */
 int  pfnav_agents_read_patches(pfnav_ctx *ctx, pfnav_patch *out, size_t maxout);
@@ -589,6 +646,15 @@ int  pfnav_agents_read_patches(pfnav_ctx *ctx, pfnav_patch *out, size_t maxout);
 int  pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream);
 /* Read the (updated) entity snapshot back: agents_out / ms_out may be NULL. */
 int  pfnav_agents_read_state(pfnav_ctx *ctx, pfnav_agent *agents_out, pfnav_movestate *ms_out, size_t maxout);
+
+/* N_FlowFieldUpdate with TARGET_ENEMIES / TARGET_ENTITY straight into the pool (what N_RequestAsyncEnemySeekField /
+ * N_RequestAsyncSurroundField + N_AwaitAsyncFields leave in the field cache, nav.c:3769-3960): the fields of the listed
+ * chunks become the flow fields of pool destination `dest`; entities name it through pfnav_agent::aux_dest1. The
+ * footprints are remembered for the in-place repairs of N_DesiredEnemySeekVelocity / N_DesiredSurroundVelocity
+ * (nav.c:3647-3675, 3729-3757), which pfnav_pool_repair runs for entities standing on a tile without direction. */
+int  pfnav_pool_request_entity_fields(pfnav_ctx *ctx, int dest, int layer, int ref_layer, int target_kind,
+                                      const pfnav_footprint *ents, size_t nents, const int32_t *chunks_rc, size_t n,
+                                      void *stream);
 
 /* Test / tuning hook for pfnav_agents_tick: 0 = single-pass velocity kernel; 1 (default) = while LOS chains of
  * pfnav_pool_request_goals are still in flight, run the part of the update that does not depend on the

@@ -185,6 +185,13 @@ class _Arrival(C.Structure):
     _fields_ = [("nearest_ok", C.c_int32), ("nearest", C.c_float * 2), ("mc_n", C.c_int32), ("mc", C.c_void_p)]
 
 
+PATCH128 = np.dtype([
+    ("flags", "<u4"), ("next_state", "<i4"), ("next_block", "<i4"), ("_pad", "<i4"),
+    ("next_velocity", "<f4", 2), ("next_pos", "<f4", 3), ("next_rot", "<f4", 4), ("next_ppos", "<f4", 3),
+    ("next_npos", "<f4", 3), ("next_step", "<f4"), ("next_left", "<f4"), ("next_nrot", "<f4", 4),
+    ("next_prot", "<f4", 4), ("_padf", "<f4", 3)])
+
+
 class OracleWorld:
     def __init__(self, omap, agents, flocks, hz=20):
         self.omap = omap
@@ -213,7 +220,7 @@ class OracleWorld:
         for i, a in enumerate(arrival):
             arr[i].nearest_ok = int(a[0]); arr[i].nearest[0], arr[i].nearest[1] = float(a[1][0]), float(a[1][1])
             arr[i].mc_n = len(keep[i]); arr[i].mc = keep[i].ctypes.data
-        out = np.zeros(len(work), patch_dtype)
+        out = np.zeros(len(work), PATCH128)        # the port's pfo_patch (the point-seek subset of struct movestate_patch)
         assert out.dtype.itemsize == 128 and ms.dtype.itemsize == 176
         lib().pfo_entity_updates(self.h, _p(ms), C.byref(arr), _p(work), len(work), _p(nv), _p(vd), _p(out))
         return out

@@ -68,6 +68,9 @@ def lib():
         L.pfref_compute_updates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_apply_velocity_patch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_vpref.argtypes = [C.c_int, C.c_void_p]
+        L.pfref_work_set_formation.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.pfref_movestate_ext_set.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.pfref_compute_updates_ext.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pfref_desired_from_cache.argtypes = [C.c_void_p, C.c_void_p]
         L.pfref_update_and_apply.restype = C.c_int
         L.pfref_update_and_apply.argtypes = [C.c_void_p]
@@ -330,6 +333,22 @@ class RefMap:
         idx = np.zeros(self._nwork, np.int32)
         lib().pfref_apply_velocity_patch(self._nwork, _p(nv), _p(fl), _p(hist), _p(idx))
         return hist, idx
+
+    def work_set_formation(self, form14, flags):
+        """formation inputs per work item (pfref_work_set_formation)"""
+        f = np.ascontiguousarray(form14, np.float32).reshape(self._nwork, 14); fl = np.ascontiguousarray(flags, np.uint32)
+        lib().pfref_work_set_formation(self._nwork, _p(f), _p(fl))
+
+    def movestate_ext_set(self, ints4, floats11):
+        i = np.ascontiguousarray(ints4, np.int32); f = np.ascontiguousarray(floats11, np.float32)
+        lib().pfref_movestate_ext_set(len(i), _p(i), _p(f))
+
+    def compute_updates_ext(self, new_vel):
+        """-> (ints[n,4], floats[n,28], extra[n,9] = next_dest[2], next_target_prev[2], next_target_dir[4], next_attack)"""
+        new_vel = np.ascontiguousarray(new_vel, dtype=np.float32)
+        oi = np.zeros((self._nwork, 4), np.int32); of = np.zeros((self._nwork, 28), np.float32); ox = np.zeros((self._nwork, 9), np.float32)
+        lib().pfref_compute_updates_ext(self._nwork, _p(new_vel), _p(oi), _p(of), _p(ox))
+        return oi, of, ox
 
     def desired_from_cache(self):
         """compute_los_state + compute_desired_velocity (movement.c:4129, 4163) on the work list -> (vdes, los)"""

@@ -954,6 +954,7 @@ bool G_EntityIsGarrisoned(uint32_t uid) { return !!(G_FlagsGetFrom(s_move_work.g
 uint32_t G_FlagsGet(uint32_t uid) { return G_FlagsGetFrom(s_move_work.gamestate.flags, uid); }
 bool pfref_live_pos_set(uint32_t uid, vec3_t pos) { s_live_pos[uid] = pos; return true; }
 void Entity_SetRot(uint32_t uid, quat_t rot) { s_live_rot[uid] = rot; }
+quat_t Entity_GetRot(uint32_t uid) { return s_live_rot[uid]; }
 void E_Entity_Notify(enum eventtype e, uint32_t uid, void *arg, enum event_source src) { (void)e; (void)uid; (void)arg; (void)src; }
 void E_Global_Notify(enum eventtype e, void *arg, enum event_source src) { (void)e; (void)arg; (void)src; }
 void G_Combat_SetStance(uint32_t uid, enum combat_stance stance) { (void)uid; (void)stance; }
@@ -1002,6 +1003,83 @@ PFREF_EXPORT void pfref_work_set(int nwork, const uint32_t *uids, const float *v
         in->stat_neighbs = malloc(sizeof(vec_cp_ent_t));
         vec_cp_ent_init(in->dyn_neighbs);  vec_cp_ent_resize(in->dyn_neighbs, MAX_NEIGHBOURS);
         vec_cp_ent_init(in->stat_neighbs); vec_cp_ent_resize(in->stat_neighbs, MAX_NEIGHBOURS);
+    }
+}
+
+/* Formation inputs of the work items (struct formation_state + cell_pos + cell_arrival_vdes of struct move_work_in,
+ * movement.c:215-225, 264-276): what formation.c's G_Formation_* getters hand to move_push_work (movement.c:4361-4400).
+ * form: 14 floats per item {cell_pos[2], cell_arrival_vdes[2], cohesion[2], align[2], drag[2], target_orientation[4]};
+ * flags: bit0 has formation, bit1 assignment_ready, bit2 assigned_to_cell, bit3 in_range_of_cell, bit4 arrived_at_cell.
+ * For STATE_ARRIVING_TO_CELL the desired velocity of the item is cell_arrival_vdes (ent_desired_velocity, movement.c:1507). */
+PFREF_EXPORT void pfref_work_set_formation(int nwork, const float *form, const uint32_t *flags)
+{
+    for(int i = 0; i < nwork; i++) {
+        struct move_work_in *in = &s_move_work.in[i];
+        const float *f = form + 14 * i;
+        in->cell_pos = (vec2_t){f[0], f[1]};
+        in->cell_arrival_vdes = (vec2_t){f[2], f[3]};
+        in->fstate.fid = (flags[i] & 1) ? 1 : NULL_FID;
+        in->fstate.assignment_ready = !!(flags[i] & 2);
+        in->fstate.assigned_to_cell = !!(flags[i] & 4);
+        in->fstate.in_range_of_cell = !!(flags[i] & 8);
+        in->fstate.arrived_at_cell = !!(flags[i] & 16);
+        in->fstate.normal_cohesion_force = (vec2_t){f[4], f[5]};
+        in->fstate.normal_align_force = (vec2_t){f[6], f[7]};
+        in->fstate.normal_drag_force = (vec2_t){f[8], f[9]};
+        in->fstate.target_orientation = (quat_t){f[10], f[11], f[12], f[13]};
+        if(movestate_get(in->ent_uid)->state == STATE_ARRIVING_TO_CELL)
+            in->ent_des_v = in->cell_arrival_vdes;
+    }
+}
+
+/* The rest of struct movestate (movement.c:146-215) for the states beyond point seeking, by uid: ints[4] =
+ * {wait_prev, wait_ticks_left, surround_target_uid, using_surround_field}, floats[11] = {target_range,
+ * target_prev_pos[2], target_dir[4], rot[4]} (rot = what Entity_GetRot returns). */
+PFREF_EXPORT void pfref_movestate_ext_set(int n, const int32_t *ints, const float *floats)
+{
+    for(int i = 0; i < n; i++) {
+        struct movestate *ms = movestate_get(i);
+        ms->wait_prev = ints[4*i]; ms->wait_ticks_left = ints[4*i+1];
+        ms->surround_target_uid = (uint32_t)ints[4*i+2]; ms->using_surround_field = !!ints[4*i+3];
+        const float *f = floats + 11 * i;
+        ms->target_range = f[0];
+        ms->target_prev_pos = (vec2_t){f[1], f[2]};
+        ms->target_dir = (quat_t){f[3], f[4], f[5], f[6]};
+        s_live_rot[i] = (quat_t){f[7], f[8], f[9], f[10]};
+    }
+}
+
+/* patch fields beyond the first 25 floats: next_dest[2], next_target_prev[2], next_target_dir[4], next_attack */
+PFREF_EXPORT void pfref_compute_updates_ext(int nwork, const float *new_vel, int32_t *out_i, float *out_f, float *out_x)
+{
+    for(int i = 0; i < nwork; i++) {
+        const struct move_work_in *in = &s_move_work.in[i];
+        struct movestate_patch p;
+        memset(&p, 0, sizeof(p));
+        entity_compute_update(s_move_work.hz, in->ent_uid, (vec2_t){new_vel[2*i], new_vel[2*i+1]}, in->ent_des_v, in, &p);
+        float *ox = out_x + 9*i;
+        memset(ox, 0, 9 * sizeof(float));
+        if(p.flags & UPDATE_SET_DEST) { ox[0] = p.next_dest.x; ox[1] = p.next_dest.z; ox[8] = p.next_attack; }
+        if(p.flags & UPDATE_SET_TARGET_PREV) { ox[2] = p.next_target_prev.x; ox[3] = p.next_target_prev.z; }
+        if(p.flags & UPDATE_SET_TARGET_DIR) { ox[4] = p.next_target_dir.x; ox[5] = p.next_target_dir.y; ox[6] = p.next_target_dir.z; ox[7] = p.next_target_dir.w; }
+        /* the first 25 floats + ints exactly as pfref_compute_updates lays them out */
+        const struct movestate *ms = movestate_get(in->ent_uid);
+        int32_t *oi = out_i + 4*i;
+        float *of = out_f + 28*i;
+        memset(of, 0, 28 * sizeof(float));
+        oi[0] = p.flags;
+        oi[1] = (p.flags & (UPDATE_SET_STATE | UPDATE_SET_MOVING)) ? (int32_t)p.next_state : -1;
+        oi[2] = (p.flags & UPDATE_SET_STATE) ? (int32_t)p.next_block : 0;
+        oi[3] = ms->wait_ticks_left;
+        if(p.flags & UPDATE_SET_VELOCITY) { of[0] = p.next_velocity.x; of[1] = p.next_velocity.z; }
+        if(p.flags & UPDATE_SET_POSITION) { of[2] = p.next_pos.x; of[3] = p.next_pos.y; of[4] = p.next_pos.z; }
+        if(p.flags & UPDATE_SET_ROTATION) { of[5] = p.next_rot.x; of[6] = p.next_rot.y; of[7] = p.next_rot.z; of[8] = p.next_rot.w; }
+        if(p.flags & UPDATE_SET_PREV_POS) { of[9] = p.next_ppos.x; of[10] = p.next_ppos.y; of[11] = p.next_ppos.z; }
+        if(p.flags & UPDATE_SET_NEXT_POS) { of[12] = p.next_npos.x; of[13] = p.next_npos.y; of[14] = p.next_npos.z; }
+        if(p.flags & UPDATE_SET_STEP) of[15] = p.next_step;
+        if(p.flags & UPDATE_SET_LEFT) of[16] = p.next_left;
+        if(p.flags & UPDATE_SET_NEXT_ROT) { of[17] = p.next_nrot.x; of[18] = p.next_nrot.y; of[19] = p.next_nrot.z; of[20] = p.next_nrot.w; }
+        if(p.flags & UPDATE_SET_PREV_ROT) { of[21] = p.next_prot.x; of[22] = p.next_prot.y; of[23] = p.next_prot.z; of[24] = p.next_prot.w; }
     }
 }
 

@@ -32,7 +32,7 @@ assert LOS_REQ.itemsize == 48
 AGENT = np.dtype([
     ("pos", "<f4", 2), ("prev_pos", "<f4", 2), ("velocity", "<f4", 2), ("vdes", "<f4", 2),
     ("radius", "<f4"), ("max_speed", "<f4"), ("speed", "<f4"), ("state", "<u4"), ("flags", "<u4"),
-    ("flock", "<i4"), ("has_dest_los", "<u4"), ("_pad", "<u4")])
+    ("flock", "<i4"), ("has_dest_los", "<u4"), ("aux_dest1", "<u4")])
 assert AGENT.itemsize == 64
 
 FLOCK = np.dtype([("target", "<f4", 2), ("dest", "<i4"), ("layer", "<i4")])
@@ -44,11 +44,24 @@ MOVESTATE = np.dtype([
 assert MOVESTATE.itemsize == 176
 
 PATCH = np.dtype([
-    ("flags", "<u4"), ("next_state", "<i4"), ("next_block", "<i4"), ("_pad", "<i4"),
+    ("flags", "<u4"), ("next_state", "<i4"), ("next_block", "<i4"), ("next_attack", "<i4"),
     ("next_velocity", "<f4", 2), ("next_pos", "<f4", 3), ("next_rot", "<f4", 4), ("next_ppos", "<f4", 3),
     ("next_npos", "<f4", 3), ("next_step", "<f4"), ("next_left", "<f4"), ("next_nrot", "<f4", 4),
-    ("next_prot", "<f4", 4), ("_padf", "<f4", 3)])
-assert PATCH.itemsize == 128
+    ("next_prot", "<f4", 4), ("wait_ticks_left", "<i4"), ("engine_todo", "<u4"), ("_padf", "<f4"),
+    ("next_dest", "<f4", 2), ("next_target_prev", "<f4", 2), ("next_target_dir", "<f4", 4)])
+assert PATCH.itemsize == 160
+
+FORMATION_IN = np.dtype([
+    ("cell_pos", "<f4", 2), ("cell_arrival_vdes", "<f4", 2), ("cohesion", "<f4", 2), ("align", "<f4", 2), ("drag", "<f4", 2),
+    ("target_orientation", "<f4", 4), ("flags", "<u4"), ("_pad", "<u4")])
+assert FORMATION_IN.itemsize == 64
+FORM_HAS_FORMATION, FORM_ASSIGNMENT_READY, FORM_ASSIGNED_TO_CELL, FORM_IN_RANGE_OF_CELL, FORM_ARRIVED_AT_CELL = 1, 2, 4, 8, 16
+MOVESTATE_EXT = np.dtype([
+    ("wait_prev", "<i4"), ("wait_ticks_left", "<i4"), ("surround_target_uid", "<u4"), ("using_surround_field", "<u4"),
+    ("target_range", "<f4"), ("target_prev_pos", "<f4", 2), ("_padf", "<f4"), ("target_dir", "<f4", 4), ("rot", "<f4", 4)])
+assert MOVESTATE_EXT.itemsize == 64
+NULL_UID = 0xFFFFFFFF
+TODO_SURROUND_QUERY, TODO_USE_SURROUND_FIELD, TODO_DROP_SURROUND_FIELD = 1, 2, 4
 
 REGION_REQ = np.dtype([
     ("layer", "<i4"), ("center_r", "<i4"), ("center_c", "<i4"), ("start_r", "<i4"), ("start_c", "<i4"),
@@ -85,6 +98,7 @@ SYMBOLS = [
     "pfnav_mgpu_shard_range", "pfnav_mgpu_unique_id", "pfnav_mgpu_init", "pfnav_mgpu_finalize", "pfnav_mgpu_gather",
     "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
     "pfnav_pool_request_goals_ex", "pfnav_blockers_batch", "pfnav_map_set_pos",
+    "pfnav_agents_upload_formation", "pfnav_agents_upload_movestate_ext", "pfnav_pool_request_entity_fields",
 ]
 
 _lib = None
@@ -184,6 +198,11 @@ def load():
     L.pfnav_pool_request_goals_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pfnav_blockers_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_upload_formation.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_agents_upload_movestate_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pfnav_pool_request_entity_fields.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                                   C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pfnav_map_set_pos.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.pfnav_agents_upload_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.c_int, C.c_uint32]
     L.pfnav_mgpu_shard_range.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -695,6 +714,20 @@ class Nav:
     def agents_upload_movestate(self, ms):
         ms = np.ascontiguousarray(ms, MOVESTATE)
         _chk(self.L.pfnav_agents_upload_movestate(self.h, _p(ms), len(ms)))
+
+    def agents_upload_formation(self, f):
+        f = np.ascontiguousarray(f, FORMATION_IN)
+        _chk(self.L.pfnav_agents_upload_formation(self.h, _p(f), len(f)))
+
+    def agents_upload_movestate_ext(self, ms):
+        ms = np.ascontiguousarray(ms, MOVESTATE_EXT)
+        _chk(self.L.pfnav_agents_upload_movestate_ext(self.h, _p(ms), len(ms)))
+
+    def pool_request_entity_fields(self, dest, kind, footprints, chunks, layer=0, ref_layer=0, stream=0):
+        fp = np.ascontiguousarray(footprints, FOOTPRINT)
+        ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
+        _chk(self.L.pfnav_pool_request_entity_fields(self.h, dest, layer, ref_layer, kind, _p(fp), len(fp), _p(ch), len(ch),
+                                                     C.c_void_p(stream)))
 
     def agents_compute_updates(self, stream=0):
         _chk(self.L.pfnav_agents_compute_updates(self.h, C.c_void_p(stream)))

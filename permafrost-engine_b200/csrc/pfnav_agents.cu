@@ -139,29 +139,74 @@ __device__ __forceinline__ v2 flow_dir_vec(int dir)
 // ------------------------------------------------------------------------------------------
 // K6a: desired velocity + LOS from the device field pool
 // ------------------------------------------------------------------------------------------
+// ent_desired_velocity (movement.c:1466) decides per movement state where the desired velocity comes from:
+//   TURNING                      zero
+//   SEEK_ENEMIES                 N_DesiredEnemySeekVelocity (nav.c:3603): direction of the own tile in the TARGET_ENEMIES
+//                                field of its chunk -- pool destination aux_dest1 - 1 -- NOT interpolated
+//   SURROUND_ENTITY              N_DesiredSurroundVelocity (nav.c:3687) out of the TARGET_ENTITY field the same way while
+//                                ms->using_surround_field (and the target exists); the point-seek field otherwise
+//   ARRIVING_TO_CELL             the caller's cell_arrival_vdes (formation.c owns the cell fields)
+//   everything else              N_DesiredPointSeekVelocity (nav.c:3468)
+// and compute_los_state (movement.c:4129): N_HasDestLOS at prev_pos for entities in a flock, except surround-field users.
 __global__ void k_desired_velocity(MapView m, PoolView pool, const pfnav_agent *__restrict__ agents,
                                    const pfnav_flock *__restrict__ flocks, const uint32_t *__restrict__ work,
                                    int nwork, float2 *__restrict__ vdes_out, uint8_t *__restrict__ los_out,
-                                   uint32_t *__restrict__ miss_count)
+                                   uint32_t *__restrict__ miss_count, const pfnav_movestate_ext *__restrict__ ext,
+                                   const pfnav_formation_in *__restrict__ form)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwork) return;
-    const pfnav_agent a = agents[work[w]];
+    const uint32_t uid = work[w];
+    const pfnav_agent a = agents[uid];
     v2 vdes = {0.0f, 0.0f};
     uint8_t los = 0;
-    const int dest = (a.flock >= 0) ? flocks[a.flock].dest : -1;
-    if (dest >= 0 && dest < pool.ndests) {
-        const int chunks = m.chunk_w * m.chunk_h;
-        const int32_t *slots = pool.slot + (size_t)dest * chunks;
+    int dest = (a.flock >= 0) ? flocks[a.flock].dest : -1;
+    bool field_dir_only = false, want_los = a.flock >= 0, want_vdes = true;
+    if (a.state == PFNAV_STATE_TURNING) want_vdes = false;
+    else if (a.state == PFNAV_STATE_ARRIVING_TO_CELL) {
+        want_vdes = false;
+        if (form) vdes = {form[uid].cell_arrival_vdes[0], form[uid].cell_arrival_vdes[1]};
+    } else if (a.state == PFNAV_STATE_SEEK_ENEMIES) {
+        dest = (int)a.aux_dest1 - 1; field_dir_only = true; want_los = false;
+    } else if (a.state == PFNAV_STATE_SURROUND_ENTITY && ext && ext[uid].surround_target_uid != 0xffffffffu &&
+               ext[uid].using_surround_field) {
+        dest = (int)a.aux_dest1 - 1; field_dir_only = true; want_los = false;
+    }
+    if (field_dir_only) {
         tile_desc t;
-        // ---- N_HasDestLOS sampled at prev_pos (movement.c:4137) ----
+        if (dest >= 0 && dest < pool.ndests && desc_for_point(m, a.pos[0], a.pos[1], t)) {
+            const int s = pool.slot[(size_t)dest * m.chunk_w * m.chunk_h + t.chunk_r * m.chunk_w + t.chunk_c];
+            if (s < 0 || !(pool.has[s] & 1)) atomicAdd(miss_count, 1u);
+            else {
+                vdes = flow_dir_vec(pool.flow[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 0xF);
+                if (pool.touch && pool.touch[s] != pool.tick_no) pool.touch[s] = pool.tick_no;
+            }
+        }
+        vdes_out[w] = make_float2(vdes.x, vdes.z);
+        los_out[w] = 0;
+        return;
+    }
+    const int pdest = (a.flock >= 0) ? flocks[a.flock].dest : -1;
+    if (want_los && pdest >= 0 && pdest < pool.ndests) {
+        tile_desc t;
         if (desc_for_point(m, a.prev_pos[0], a.prev_pos[1], t)) {
-            const int s = slots[t.chunk_r * m.chunk_w + t.chunk_c];
+            const int s = pool.slot[(size_t)pdest * m.chunk_w * m.chunk_h + t.chunk_r * m.chunk_w + t.chunk_c];
             if (s >= 0 && (pool.has[s] & 2)) {
                 los = pool.los[(size_t)s * 4096 + t.tile_r * 64 + t.tile_c] & 1;
                 if (pool.touch && pool.touch[s] != pool.tick_no) pool.touch[s] = pool.tick_no;
             }
         }
+    }
+    if (!want_vdes) {
+        vdes_out[w] = make_float2(vdes.x, vdes.z);
+        los_out[w] = los;
+        return;
+    }
+    if (dest >= 0 && dest < pool.ndests) {
+        const int chunks = m.chunk_w * m.chunk_h;
+        const int32_t *slots = pool.slot + (size_t)dest * chunks;
+        tile_desc t;
+        // (N_HasDestLOS, sampled at prev_pos, was evaluated above: movement.c:4137)
         // ---- N_DesiredPointSeekVelocity at pos ----
         if (desc_for_point(m, a.pos[0], a.pos[1], t)) {
             const int s = slots[t.chunk_r * m.chunk_w + t.chunk_c];
@@ -490,6 +535,16 @@ struct VelSmem {
     float2 term[128];
     float cqx[CQ_CAP], cqz[CQ_CAP];      // candidate points awaiting the inside-PCR test
     int cqk[CQ_CAP];                      // their sequence index in the reference's push order
+    // ---- one-pass emulation of the drop-furthest retry loop (clearpath_retry) ----
+    uint8_t vo_src[64];                   // obstacle -> neighbour slot it was built from (dyn: 0..31, stat: 32..63)
+    uint8_t nb_rank[64];                  // neighbour slot -> removal time 1.. (255: still there when the loop ends)
+    uint8_t vo_rank[64];                  // obstacle -> removal time of its neighbour
+    uint8_t vo_ord[64];                   // obstacles by decreasing removal time
+    uint8_t cur[64];                      // working lists: dyn slots at [0, nd), stat slots at [32, 32 + ns)
+    uint8_t nalive[64];                   // obstacles alive after t removals
+    uint8_t pos_t[64][64];                // pos_t[t][obstacle] = its index among the alive obstacles after t removals (255 gone)
+    float   ndist[64];                    // neighbour slot -> distance from the entity
+    uint8_t cqd[CQ_CAP];                  // death time of the queued candidates
 };
 
 // One velocity obstacle of inside_pcr (clearpath.c:252-287): is `test` strictly inside VO `i`?
@@ -617,6 +672,7 @@ __device__ int build_vos(VelSmem &s, const cp_ent ent, int ndyn, int nstat, uint
         const uint32_t m = __ballot_sync(FULL, keep);
         if (keep) {
             const int k = 2 * __popc(m & ((1u << lane) - 1));
+            s.vo_src[k >> 1] = (uint8_t)lane;
             s.rpx[k] = apex.x; s.rpz[k] = apex.z; s.rdx[k] = left.x; s.rdz[k] = left.z; s.rsl[k] = line_slope(left);
             s.rpx[k + 1] = apex.x; s.rpz[k + 1] = apex.z; s.rdx[k + 1] = right.x; s.rdz[k + 1] = right.z; s.rsl[k + 1] = line_slope(right);
         }
@@ -636,6 +692,7 @@ __device__ int build_vos(VelSmem &s, const cp_ent ent, int ndyn, int nstat, uint
         const uint32_t m = __ballot_sync(FULL, keep);
         if (keep) {
             const int k = n_rays + 2 * __popc(m & ((1u << lane) - 1));
+            s.vo_src[k >> 1] = (uint8_t)(32 + lane);
             s.rpx[k] = apex.x; s.rpz[k] = apex.z; s.rdx[k] = left.x; s.rdz[k] = left.z; s.rsl[k] = line_slope(left);
             s.rpx[k + 1] = apex.x; s.rpz[k + 1] = apex.z; s.rdx[k + 1] = right.x; s.rdz[k + 1] = right.z; s.rsl[k + 1] = line_slope(right);
         }
@@ -647,9 +704,10 @@ __device__ int build_vos(VelSmem &s, const cp_ent ent, int ndyn, int nstat, uint
 
 // clearpath_new_velocity (clearpath.c:552). Warp-cooperative; returns a warp-uniform status.
 __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat,
-                                       uint32_t lane, v2 &out)
+                                       uint32_t lane, v2 &out, int &n_rays_out)
 {
     const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
+    n_rays_out = n_rays;
     const int nvo = n_rays >> 1;
 
     // ---- is the preferred velocity admissible? one velocity obstacle per lane ----
@@ -746,6 +804,244 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
     }
     out = (best_idx == 0x7fffffff) ? v2{0.0f, 0.0f} : best_p;
     return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// G_ClearPath_NewVelocity's retry loop (clearpath.c:702-713) in ONE pass. After a solve that finds no admissible
+// velocity the reference drops the furthest neighbour (remove_furthest :390) and solves again from scratch, while both
+// neighbour lists are non-empty. Which neighbour goes at which step depends on the distances and the list order only,
+// never on the velocities, so the whole removal schedule is known up front: neighbour n leaves at time rank(n). The
+// obstacle of a neighbour and the candidate points generated by its two rays do not depend on the other neighbours,
+// hence for every candidate point c of the FIRST solve
+//     adm(c)   = max rank of the obstacles that contain c   (it becomes admissible once they are all gone)
+//     death(c) = min rank of the obstacles whose rays generate c
+// and the solve after t removals succeeds iff the preferred velocity (adm <= t) or some candidate (adm <= t < death) is
+// admissible. The first such t is T = min(adm); by minimality every candidate usable at T has adm == T exactly, and
+// compute_vnew (:368) picks the one nearest to the preferred velocity, first in ITS list order on ties -- the order of
+// the ray table after T swap-with-last deletions, which pos_t[] reproduces. Obstacles are tested in decreasing rank, so
+// the first hit is the maximum and most points end at the nearest (widest) obstacles after one or two tests.
+// Cost: one solve instead of up to 63.
+// ------------------------------------------------------------------------------------------
+// removal schedule; returns the number of removals after which the loop ends (no solve happens at that time)
+__device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int nvo, uint32_t lane)
+{
+    for (int k = lane; k < 64; k += 32) {
+        const bool valid = k < 32 ? k < ndyn : (k - 32) < nstat;
+        float d = -__int_as_float(0x7f800000);
+        if (valid) { const cp_ent e = k < 32 ? s.dyn[k] : s.stat[k - 32]; d = v2_len(v2_sub(pos, e.pos)); }
+        s.ndist[k] = d; s.nb_rank[k] = 255; s.cur[k] = (uint8_t)k;
+    }
+    __syncwarp();
+    uint64_t hasvo = 0;             // neighbour slots that carry an obstacle (same_position neighbours do not, clearpath.c:123)
+    for (int v = 0; v < nvo; v++) hasvo |= 1ull << s.vo_src[v];
+    int nd = ndyn, ns = nstat, t = 0, t_end = 0;
+    auto record = [&](int tt) {     // pos_t[tt][*]: list order = dyn part then stat part, obstacles only
+        for (int v = lane; v < 64; v += 32) s.pos_t[tt][v] = 255;
+        __syncwarp();
+        int before = 0;
+        for (int q0 = 0; q0 < nd + ns; q0 += 32) {
+            const int q = q0 + (int)lane;
+            int slot = -1;
+            if (q < nd + ns) slot = q < nd ? s.cur[q] : s.cur[32 + q - nd];
+            const bool hv = slot >= 0 && ((hasvo >> slot) & 1);
+            const uint32_t mk = __ballot_sync(FULL, hv);
+            if (hv) {
+                int v = 0;              // inverse of vo_src (<= 64 entries, rare path)
+                while (s.vo_src[v] != slot) v++;
+                s.pos_t[tt][v] = (uint8_t)(before + __popc(mk & ((1u << lane) - 1)));
+            }
+            before += __popc(mk);
+        }
+        if (lane == 0) s.nalive[tt] = (uint8_t)before;
+        __syncwarp();
+    };
+    record(0);
+    while (true) {
+        float bd = -__int_as_float(0x7f800000);
+        int bp = 0x7fffffff;
+        for (int q = lane; q < nd + ns; q += 32) {
+            const int slot = q < nd ? s.cur[q] : s.cur[32 + q - nd];
+            const float d = s.ndist[slot];
+            if (d > bd) { bd = d; bp = q; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(FULL, bd, off);
+            const int op = __shfl_xor_sync(FULL, bp, off);
+            if (od > bd || (od == bd && op < bp)) { bd = od; bp = op; }
+        }
+        if (bp == 0x7fffffff) { t_end = t + 1; break; }      // nothing left to remove: the loop condition fails next
+        t++;
+        if (lane == 0) {
+            int slot;
+            if (bp < nd) { slot = s.cur[bp]; s.cur[bp] = s.cur[nd - 1]; }
+            else { const int j = bp - nd; slot = s.cur[32 + j]; s.cur[32 + j] = s.cur[32 + ns - 1]; }
+            s.nb_rank[slot] = (uint8_t)t;
+        }
+        if (bp < nd) nd--; else ns--;
+        __syncwarp();
+        if (!(nd > 0 && ns > 0)) { t_end = t; break; }
+        record(t);
+    }
+    for (int v = lane; v < nvo; v += 32) s.vo_rank[v] = s.nb_rank[s.vo_src[v]];
+    __syncwarp();
+    for (int v = lane; v < nvo; v += 32) {                   // order by decreasing rank, index ascending among equals
+        const int r = s.vo_rank[v];
+        int p = 0;
+        for (int u = 0; u < nvo; u++) { const int ru = s.vo_rank[u]; p += (ru > r) || (ru == r && u < v); }
+        s.vo_ord[p] = (uint8_t)v;
+    }
+    __syncwarp();
+    return t_end;
+}
+
+// position of a candidate in the reference's candidate list of the solve after T removals (xpoints in (i, j) order
+// over the ray table of that time, then the projection points); id: ray_i * 128 + ray_j, or 0x8000 | ray for projections
+__device__ __forceinline__ int retry_seq(const VelSmem &s, int id, int T)
+{
+    const int nr = 2 * s.nalive[T];
+    if (id & 0x8000) { const int r = id & 0x7f; return nr * nr + 2 * s.pos_t[T][r >> 1] + (r & 1); }
+    const int i = id >> 7, j = id & 0x7f;
+    return (2 * s.pos_t[T][i >> 1] + (i & 1)) * nr + 2 * s.pos_t[T][j >> 1] + (j & 1);
+}
+
+struct retry_best { int T; float dist; int id; v2 p; };
+
+__device__ __forceinline__ bool retry_better(const VelSmem &s, int T, float dist, int id, const retry_best &b)
+{
+    if (T != b.T) return T < b.T;
+    if (dist != b.dist) return dist < b.dist;
+    if (b.id < 0) return true;
+    return retry_seq(s, id, T) < retry_seq(s, b.id, T);
+}
+
+// like drain_candidates, for the retry emulation: cqk holds the candidate id, cqd its death time
+__device__ __forceinline__ void drain_ranked(const VelSmem &s, int qn, int nvo, const v2 ent_pos, const v2 des_v,
+                                             uint32_t lane, retry_best &best)
+{
+    int next = 0, my = -1, k = 0, myid = 0, mydeath = 0;
+    v2 myp = {0.0f, 0.0f};
+    while (true) {
+        const bool need = my < 0;
+        const uint32_t mneed = __ballot_sync(FULL, need);
+        const int avail = qn - next;
+        if (need) {
+            const int rank = __popc(mneed & ((1u << lane) - 1));
+            if (rank < avail) { my = next + rank; k = 0; myp = {s.cqx[my], s.cqz[my]}; myid = s.cqk[my]; mydeath = s.cqd[my]; }
+        }
+        next += min(__popc(mneed), avail);
+        if (!__any_sync(FULL, my >= 0)) break;
+        if (my >= 0) {
+            bool finished = false;
+            int adm = -1;
+            if (k < nvo) {
+                const int v = s.vo_ord[k];
+                const int r = s.vo_rank[v];
+                // obstacles come in decreasing rank, so the first hit is the maximum rank among the containing ones
+                if (vo_contains(s, v, myp)) { adm = r; finished = true; }
+                else if (++k >= nvo) { adm = 0; finished = true; }
+            } else { adm = 0; finished = true; }
+            if (finished) {
+                if (adm < mydeath && adm <= best.T) {
+                    const v2 curr = v2_sub(myp, ent_pos);
+                    const float len = v2_len(v2_sub(des_v, curr));
+                    if (retry_better(s, adm, len, myid, best)) { best.T = adm; best.dist = len; best.id = myid; best.p = curr; }
+                }
+                my = -1;
+            }
+        }
+    }
+}
+
+// everything G_ClearPath_NewVelocity does after its first solve found nothing. The ray table of that solve is still in
+// shared memory (build_vos). Returns the velocity of the first successful later solve, or zero when the loop ends first.
+__device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat, int n_rays, uint32_t lane)
+{
+    const int nvo = n_rays >> 1;
+    // with one of the two lists empty the loop condition fails right after the first removal (the common case in a crowd
+    // where everybody moves): no second solve, the answer is zero
+    if (ndyn == 0 || nstat == 0) return v2{0.0f, 0.0f};
+    const int t_end = retry_schedule(s, ent.pos, ndyn, nstat, nvo, lane);
+    if (t_end <= 1) return v2{0.0f, 0.0f};                   // the loop ends right after the first removal
+    // the preferred velocity: admissible once every obstacle that contains it is gone
+    const v2 des_v_ws = v2_add(ent.pos, des_v);
+    int adm_des = 0;
+    for (int v = lane; v < nvo; v += 32)
+        if (vo_contains(s, v, des_v_ws)) adm_des = max(adm_des, (int)s.vo_rank[v]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) adm_des = max(adm_des, __shfl_xor_sync(FULL, adm_des, off));
+    retry_best best; best.T = min(adm_des, t_end - 1); best.dist = __int_as_float(0x7f800000); best.id = -1; best.p = {0.0f, 0.0f};
+    const int npairs = n_rays * n_rays;
+    int qn = 0;
+    auto flush = [&](bool last) {
+        if (qn > CQ_CAP - 32 || (last && qn > 0)) {
+            __syncwarp();
+            drain_ranked(s, qn, nvo, ent.pos, des_v, lane, best);
+            __syncwarp();
+            qn = 0;
+            int t = best.T;                                   // the warp-wide best time bounds what is still worth testing
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t = min(t, __shfl_xor_sync(FULL, t, off));
+            if (t < best.T) { best.T = t; best.dist = __int_as_float(0x7f800000); best.id = -1; }
+        }
+    };
+    for (int base = 0; base < n_rays; base += 32) {            // projection points (compute_vdes_proj_points, :344)
+        const int r = base + (int)lane;
+        if (r < n_rays) {
+            const v2 d = {s.rdx[r], s.rdz[r]};
+            const float len = v2_dot(d, des_v);
+            const v2 p = v2_add(v2{s.rpx[r], s.rpz[r]}, v2_scale(d, len));
+            s.cqx[qn + (int)lane] = p.x; s.cqz[qn + (int)lane] = p.z; s.cqk[qn + (int)lane] = 0x8000 | r;
+            s.cqd[qn + (int)lane] = s.vo_rank[r >> 1];
+        }
+        qn += min(32, n_rays - base);
+        flush(base + 32 >= n_rays);
+    }
+    int i = 0, j = (int)lane;
+    while (j >= n_rays && n_rays > 0) { j -= n_rays; i++; }
+    for (int base = 0; base < npairs; base += 32) {            // ray-pair intersections (compute_vo_xpoints, :321)
+        const int k = base + (int)lane;
+        v2 p = {0.f, 0.f};
+        bool ok = false;
+        int death = 0;
+        if (k < npairs && i != j) {
+            death = min((int)s.vo_rank[i >> 1], (int)s.vo_rank[j >> 1]);
+            if (death > 0) {           // a pair that dies at time <= 0 cannot exist (ranks start at 1); kept for symmetry
+                const v2 p1 = {s.rpx[i], s.rpz[i]}, p2 = {s.rpx[j], s.rpz[j]};
+                if (line_isect_s(p1, s.rsl[i], p2, s.rsl[j], p))
+                    ok = !(quot_lt0(p.x - p1.x, s.rdx[i]) || quot_lt0(p.z - p1.z, s.rdz[i]) ||
+                           quot_lt0(p.x - p2.x, s.rdx[j]) || quot_lt0(p.z - p2.z, s.rdz[j]));
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, ok);
+        if (ok) {
+            const int q = qn + __popc(m & ((1u << lane) - 1));
+            s.cqx[q] = p.x; s.cqz[q] = p.z; s.cqk[q] = (i << 7) | j; s.cqd[q] = (uint8_t)death;
+        }
+        qn += __popc(m);
+        j += 32;
+        while (j >= n_rays) { j -= n_rays; i++; }
+        flush(base + 32 >= npairs);
+    }
+    // warp-wide choice: smallest time, then distance, then list position at that time
+    int T = best.T;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) T = min(T, __shfl_xor_sync(FULL, T, off));
+    if (best.T != T) { best.dist = __int_as_float(0x7f800000); best.id = -1; }
+    if (adm_des <= T && adm_des <= t_end - 1) return des_v;     // inside_pcr(des_v) is tested before any candidate (:602)
+    float d = best.dist;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d = fminf(d, __shfl_xor_sync(FULL, d, off));
+    const bool mine = best.id >= 0 && best.dist == d;
+    if (!__any_sync(FULL, mine)) return v2{0.0f, 0.0f};          // no solve before the loop ends finds a point
+    int seq = mine ? retry_seq(s, best.id, T) : 0x7fffffff;
+    int smin = seq;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) smin = min(smin, __shfl_xor_sync(FULL, smin, off));
+    const int src = __ffs(__ballot_sync(FULL, mine && seq == smin)) - 1;
+    v2 out;
+    out.x = __shfl_sync(FULL, best.p.x, src); out.z = __shfl_sync(FULL, best.p.z, src);
+    return out;
 }
 
 // remove_furthest (clearpath.c:390): first strict maximum over dyn then stat; swap-with-last delete
@@ -867,9 +1163,10 @@ __device__ int clearpath_collect(VelSmem &s, const cp_ent ent, int ndyn, int nst
 
 // phase B: the choice among {des_v, its projections on the rays, the stored admissible intersections}
 __device__ bool clearpath_finish(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat, uint32_t lane,
-                                 const pf_xpoint *xp, int nx, v2 &out)
+                                 const pf_xpoint *xp, int nx, v2 &out, int &n_rays_out)
 {
     const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
+    n_rays_out = n_rays;
     const int nvo = n_rays >> 1, npairs = n_rays * n_rays;
     const v2 des_v_ws = v2_add(ent.pos, des_v);
     bool in_any = false;
@@ -932,11 +1229,12 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
                  const uint8_t *__restrict__ los_in, const float2 *__restrict__ cohesion_in,
                  float2 *__restrict__ vel_out, float2 *__restrict__ vpref_out, int filter_garr,
-                 uint32_t *__restrict__ nb_scratch, pf_prep *__restrict__ prep)
+                 uint32_t *__restrict__ nb_scratch, pf_prep *__restrict__ prep,
+                 const pfnav_formation_in *__restrict__ form)
 {
-    __shared__ VelSmem smem[VEL_WARPS_PER_CTA];
+    extern __shared__ __align__(16) uint8_t vel_smem_raw[];      // VEL_WARPS_PER_CTA x VelSmem (> 48 KB: opt-in, pfnav_agents_init)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    VelSmem &s = smem[warp];
+    VelSmem &s = reinterpret_cast<VelSmem *>(vel_smem_raw)[warp];
     const int total_warps = gridDim.x * VEL_WARPS_PER_CTA;
     for (int w = blockIdx.x * VEL_WARPS_PER_CTA + warp; w < nwork; w += total_warps) {
         const uint32_t uid = work[w];
@@ -1010,6 +1308,28 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                 if (MODE == 1 && lane == 0) { prep[w].sepx = separation.x; prep[w].sepz = separation.z; }
             }
             if (MODE == 1) { /* the rest of point_seek_vpref needs the desired velocity: phase B */ } else {
+            // the state picks the steering variant (move_velocity_work, movement.c:3414-3448)
+            const uint32_t st_ = a.state;
+            pfnav_formation_in fin;
+            const bool has_form = form != nullptr && (st_ == PFNAV_STATE_ARRIVING_TO_CELL || st_ == PFNAV_STATE_MOVING_IN_FORMATION);
+            if (has_form) fin = form[uid];
+            const bool cell_mode = st_ == PFNAV_STATE_ARRIVING_TO_CELL, form_mode = st_ == PFNAV_STATE_MOVING_IN_FORMATION;
+            const bool enemy_mode = st_ == PFNAV_STATE_SEEK_ENEMIES;
+            const bool ready = has_form && (fin.flags & PFNAV_FORM_ASSIGNMENT_READY);
+            v2 arrive;
+            if (cell_mode) {
+                // ---- arrive_force_cell (movement.c:1571): NOT relative to the current velocity, not truncated ----
+                const v2 cell = has_form ? v2{fin.cell_pos[0], fin.cell_pos[1]} : pos;
+                v2 desired = v2_sub(cell, pos);
+                const float distance = v2_len(desired);
+                if (distance < 10.0f) desired = v2_scale(desired, distance / 10.0f);
+                else desired = v2_scale(vdes, a.max_speed / hzf);
+                arrive = desired;
+            } else if (enemy_mode) {
+                // ---- arrive_force_enemies (movement.c:1593) ----
+                const v2 desired = v2_scale(vdes, a.max_speed / hzf);
+                arrive = v2_truncate(v2_sub(desired, velocity), tp.scaled_max_force);
+            } else {
             // ---- arrive_force_point (movement.c:1546) ----
             const v2 target = a.flock >= 0 ? v2{flocks[a.flock].target[0], flocks[a.flock].target[1]} : pos;
             v2 desired;
@@ -1022,10 +1342,12 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             } else {
                 desired = v2_scale(vdes, a.max_speed / hzf);
             }
-            v2 arrive = v2_truncate(v2_sub(desired, velocity), tp.scaled_max_force);
-            // ---- cohesion (pre-pass) ----
+            arrive = v2_truncate(v2_sub(desired, velocity), tp.scaled_max_force);
+            }
+            // ---- cohesion: the flock-wide pre-pass, or the formation's own forces (fstate, movement.c:215-225) ----
             const float2 ch = cohesion_in[w];
-            const v2 cohesion = {ch.x, ch.y};
+            const v2 cohesion = (cell_mode || form_mode) ? (has_form ? v2{fin.cohesion[0], fin.cohesion[1]} : v2{0.0f, 0.0f}) : v2{ch.x, ch.y};
+            const v2 alignment = has_form ? v2{fin.align[0], fin.align[1]} : v2{0.0f, 0.0f};
 
             const int layer = nav_layer_for(ent_flags, a.radius);
             bool on_blocked, dummy, lp, lb, rp, rb, tpth, tb, bp, bb;
@@ -1036,17 +1358,23 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             probe_tile(m, layer, pos.x, pos.z - 4.0f, bp, bb);      // bot
 
             v2 steer = {0.0f, 0.0f};
-            for (int prio = 0; prio < 3; prio++) {
+            for (int prio = 0; prio < (enemy_mode ? 1 : 3); prio++) {
                 if (prio == 0) {
-                    // point_seek_total_force (movement.c:1745)
+                    // point_seek_total_force / formation_point_seek_total_force / cell_seek_total_force /
+                    // enemy_seek_total_force (movement.c:1745, 1960, 1769, 1801)
                     const v2 A = v2_scale(arrive, 0.5f), C = v2_scale(cohesion, 0.15f), S = v2_scale(separation, 0.6f);
+                    const v2 AL = v2_scale(alignment, 0.15f);
                     v2 ret = {0.0f, 0.0f};
                     ret = v2_add(ret, A);
                     ret = v2_add(ret, S);
-                    ret = v2_add(ret, C);
+                    if (cell_mode) {
+                        const v2 cell = has_form ? v2{fin.cell_pos[0], fin.cell_pos[1]} : pos;
+                        if (v2_len(v2_sub(cell, pos)) > 30.0f) { ret = v2_add(ret, C); ret = v2_add(ret, AL); }     // CELL_ARRIVAL_RADIUS
+                    } else if (!enemy_mode) ret = v2_add(ret, C);
                     steer = v2_truncate(ret, tp.scaled_max_force);
                 } else if (prio == 1) steer = separation;
                 else steer = arrive;
+                if (enemy_mode) break;              // enemy_seek_vpref (movement.c:1946): no nullify pass, no fall-backs
                 // nullify_impass_components (movement.c:1831)
                 if (steer.x > 0 && (!lp || (!on_blocked && lb))) steer.x = 0.0f;
                 if (steer.x < 0 && (!rp || (!on_blocked && rb))) steer.x = 0.0f;
@@ -1056,6 +1384,11 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             }
             const v2 accel = v2_scale(steer, 1.0f / 1.0f);
             vpref = v2_truncate(v2_add(velocity, accel), a.speed / hzf);
+            if ((cell_mode || form_mode) && has_form) {
+                // formation drag caps the speed at 75 % (movement.c:1940, 2017); unassigned members stand still (:3426, :3438)
+                if (v2_len(v2{fin.drag[0], fin.drag[1]}) > EPS_F) vpref = v2_truncate(vpref, (float)(((double)a.speed * 0.75) / (double)hzf));
+                if (!ready) vpref = {0.0f, 0.0f};
+            } else if (cell_mode || form_mode) vpref = {0.0f, 0.0f};
             }
         }
 
@@ -1136,22 +1469,17 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             continue;
         }
         v2 new_vel = {0.0f, 0.0f};
-        bool done = false;
-        if (MODE == 2 && prep[w].nx != PF_PREP_OVERFLOW) {
+        {
+            // first solve; when it finds no admissible velocity the drop-furthest retry loop (clearpath.c:702-713) is
+            // resolved in one pass over the same ray table (clearpath_retry)
             v2 r;
-            if (clearpath_finish(s, self, vpref, ndyn, nstat, lane, prep[w].xp, (int)prep[w].nx, r)) { new_vel = r; done = true; }
-            else {
-                // no admissible point at all: drop the furthest neighbour and retry in one pass (clearpath.c:702-713)
-                remove_furthest(s, self.pos, ndyn, nstat, lane);
-                if (!(ndyn > 0 && nstat > 0)) { new_vel = {0.0f, 0.0f}; done = true; }
-            }
-        }
-        while (!done) {
-            v2 r;
-            const bool found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r);
-            if (found) { new_vel = r; break; }
-            remove_furthest(s, self.pos, ndyn, nstat, lane);
-            if (!(ndyn > 0 && nstat > 0)) { new_vel = {0.0f, 0.0f}; break; }
+            int n_rays = 0;
+            bool found;
+            if (MODE == 2 && prep[w].nx != PF_PREP_OVERFLOW)
+                found = clearpath_finish(s, self, vpref, ndyn, nstat, lane, prep[w].xp, (int)prep[w].nx, r, n_rays);
+            else
+                found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r, n_rays);
+            new_vel = found ? r : clearpath_retry(s, self, vpref, ndyn, nstat, n_rays, lane);
         }
         new_vel = v2_truncate(new_vel, a.max_speed / hzf);      // movement.c:3464
         if (lane == 0) {
@@ -1165,6 +1493,16 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
+#define VEL_SMEM_BYTES ((int)(VEL_WARPS_PER_CTA * sizeof(VelSmem)))
+int pfnav_agents_init(pfnav_ctx *ctx)
+{
+    (void)ctx;
+    PF_CUDA(cudaFuncSetAttribute(k_agent_velocity<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, VEL_SMEM_BYTES));
+    PF_CUDA(cudaFuncSetAttribute(k_agent_velocity<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VEL_SMEM_BYTES));
+    PF_CUDA(cudaFuncSetAttribute(k_agent_velocity<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VEL_SMEM_BYTES));
+    return 0;
+}
+
 void pfnav_agents_free(pfnav_ctx *ctx)
 {
     cudaFree(ctx->d_agents); cudaFree(ctx->d_records); cudaFree(ctx->d_flocks);
@@ -1174,7 +1512,9 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
     cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep); cudaFree(ctx->d_flock_of); cudaFree(ctx->d_facts);
-    ctx->d_flock_of = nullptr; ctx->d_facts = nullptr;
+    cudaFree(ctx->d_formation); cudaFree(ctx->d_ms_ext); cudaFree(ctx->d_enter); cudaFree(ctx->d_ttiles);
+    ctx->d_flock_of = nullptr; ctx->d_facts = nullptr; ctx->d_formation = nullptr; ctx->d_ms_ext = nullptr;
+    ctx->d_enter = nullptr; ctx->d_ttiles = nullptr; ctx->cap_formation = ctx->cap_ms_ext = ctx->cap_enter = ctx->cap_ttiles = 0;
     if (ctx->update_done) cudaEventDestroy(ctx->update_done);
     cudaFree(ctx->d_los_out); cudaFree(ctx->d_work_count); cudaFree(ctx->d_scan_tmp);
     ctx->d_agents = nullptr; ctx->d_records = nullptr; ctx->d_flocks = nullptr; ctx->d_flock_start = nullptr;
@@ -1423,6 +1763,9 @@ static int agents_upload_impl(pfnav_ctx *ctx, const pfnav_agent *agents, size_t 
         }
         ctx->h_flocks.assign(flocks, flocks + nflocks);
         ctx->arrival_valid = false;
+        // optional per-entity inputs of the previous population do not carry over
+        cudaFree(ctx->d_formation); ctx->d_formation = nullptr; ctx->cap_formation = 0;
+        cudaFree(ctx->d_ms_ext); ctx->d_ms_ext = nullptr; ctx->cap_ms_ext = 0;
     }
     if (hi > lo) PF_CUDA(cudaMemcpyAsync(ctx->d_agents + lo, agents, (hi - lo) * sizeof(pfnav_agent), cudaMemcpyHostToDevice, st));
     if (nflocks && !same) PF_CUDA(cudaMemcpyAsync(ctx->d_flocks, flocks, nflocks * sizeof(pfnav_flock), cudaMemcpyHostToDevice, st));
@@ -1618,10 +1961,10 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         // phase A has the whole LOS phase to hide in: a smaller persistent grid leaves the schedulers to the
         // latency-bound LOS threads it shares the SMs with
         const int ctas_a = ctx->phase_a_ctas_per_sm > 0 ? std::min(ctas, ctx->sm_count * ctx->phase_a_ctas_per_sm) : ctas;
-        k_agent_velocity<1><<<ctas_a, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+        k_agent_velocity<1><<<ctas_a, VEL_WARPS_PER_CTA * 32, VEL_SMEM_BYTES, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                                     ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
                                                                     ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
-                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep);
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep, ctx->d_formation);
         ctx->launches++;
     }
     // everything above is independent of the flow/LOS fields; the LOS chains forked by
@@ -1636,22 +1979,23 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         pv.has = ctx->d_pool_los + (size_t)ctx->pool_max * 4096; pv.ndests = ctx->pool_ndests;
         pv.touch = ctx->d_pool_touch; pv.tick_no = ctx->tick_no;
         k_desired_velocity<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
-                                                               ctx->d_vdes_out, ctx->d_los_out, ctx->d_work_count);
+                                                               ctx->d_vdes_out, ctx->d_los_out, ctx->d_work_count,
+                                                               ctx->d_ms_ext, ctx->d_formation);
     } else {
         k_copy_vdes<<<(nwork + 255) / 256, 256, 0, st>>>(ctx->d_agents, ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out);
     }
     }
     pf_prof_scope prof(ctx, st, PF_PROF_VELOCITY);
     if (two_phase)
-        k_agent_velocity<2><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+        k_agent_velocity<2><<<ctas, VEL_WARPS_PER_CTA * 32, VEL_SMEM_BYTES, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                                     ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
                                                                     ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
-                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep);
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, (pf_prep *)ctx->d_prep, ctx->d_formation);
     else
-        k_agent_velocity<0><<<ctas, VEL_WARPS_PER_CTA * 32, 0, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
+        k_agent_velocity<0><<<ctas, VEL_WARPS_PER_CTA * 32, VEL_SMEM_BYTES, st>>>(m, grid_of(ctx), tp, ctx->d_agents, ctx->d_records, ctx->d_flocks,
                                                                     ctx->d_work, nwork, ctx->d_vdes_out, ctx->d_los_out,
                                                                     ctx->d_cohesion, ctx->d_vel_out, ctx->d_vpref_out,
-                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, nullptr);
+                                                                    ctx->any_garrisoned ? 1 : 0, ctx->d_nb_scratch, nullptr, ctx->d_formation);
     ctx->launches += 3;
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaEventRecord(ctx->ev_vel1, st));
@@ -1800,7 +2144,9 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
                 const pfnav_flock *__restrict__ flocks, const pf_arrival_dev *__restrict__ arr,
                 const float2 *__restrict__ mc_tiles, int nlayers, const uint32_t *__restrict__ work, int nwork,
                 const float2 *__restrict__ vel_in, const float2 *__restrict__ vdes_in, pfnav_patch *__restrict__ out,
-                const int32_t *__restrict__ flock_of)
+                const int32_t *__restrict__ flock_of, const pfnav_movestate_ext *__restrict__ exts,
+                const pfnav_formation_in *__restrict__ forms, const pf_arrival_dev *__restrict__ tarr,
+                const float2 *__restrict__ t_tiles)
 {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwork) return;
@@ -1811,6 +2157,7 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
     pfnav_patch p;
     memset(&p, 0, sizeof(p));
     p.next_state = -1;
+    p.wait_ticks_left = exts ? exts[uid].wait_ticks_left : 0;
     const quat ms_rot = {ms.next_rot[0], ms.next_rot[1], ms.next_rot[2], ms.next_rot[3]};
     v2 new_vel = {vel_in[wi].x, vel_in[wi].y};
     const v2 vdes = {vdes_in[wi].x, vdes_in[wi].y};
@@ -1908,18 +2255,108 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
     // stuck on non-pathable terrain: keep the state (movement.c:2417)
     bool cur_path, cur_blk;
     probe_tile(m, layer, new_pos_xz.x, new_pos_xz.z, cur_path, cur_blk);
-    if (!cur_path || a.flock < 0 || state != PFNAV_STATE_MOVING) { out[wi] = p; return; }
+    if (!cur_path) { out[wi] = p; return; }
+    pfnav_movestate_ext ex;
+    if (exts) ex = exts[uid];
+    else { memset(&ex, 0, sizeof(ex)); ex.surround_target_uid = PFNAV_NULL_UID; ex.rot[3] = 1.0f; }
+    p.wait_ticks_left = ex.wait_ticks_left;
+    uint32_t fflags = 0;
+    pfnav_formation_in fin;
+    if (forms) { fin = forms[uid]; fflags = fin.flags; }
+    const bool has_fid = fflags & PFNAV_FORM_HAS_FORMATION;
 
-    // ---- STATE_MOVING (movement.c:2421-2495), no formation, no arrival group ----
-    const pfnav_flock fl = flocks[a.flock];
-    const pf_arrival_dev ac = arr[(size_t)a.flock * nlayers + layer];
-    bool arrived = false;
-    {   // arrived() (movement.c:2170)
-        const v2 tgt = {fl.target[0], fl.target[1]};
-        const float thresh = a.radius * 1.5f;
-        if (v2_len(v2_sub(tgt, new_pos_xz)) < thresh) arrived = true;
+    switch (state) {
+    case PFNAV_STATE_MOVING:
+    case PFNAV_STATE_MOVING_IN_FORMATION: {
+        // movement.c:2424-2500 (no arrival group: G_ArrivalGroup_ForLayer is the f-1 consumer, inactive here)
+        if (has_fid && !(fflags & PFNAV_FORM_ASSIGNMENT_READY)) break;
+        if (has_fid && (fflags & PFNAV_FORM_ASSIGNED_TO_CELL) && (fflags & PFNAV_FORM_IN_RANGE_OF_CELL)) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVING_TO_CELL;
+            break;
+        }
+        if (a.flock < 0) break;
+        const pfnav_flock fl = flocks[a.flock];
+        const pf_arrival_dev ac = arr[(size_t)a.flock * nlayers + layer];
+        bool arrived = false;
+        {   // arrived() (movement.c:2170)
+            const v2 tgt = {fl.target[0], fl.target[1]};
+            const float thresh = a.radius * 1.5f;
+            if (v2_len(v2_sub(tgt, new_pos_xz)) < thresh) arrived = true;
+            if (!arrived) {
+                // N_IsAdjacentToImpassable (nav.c:4745) && N_IsMaximallyClose (nav.c:4707)
+                tile_desc td;
+                bool adj = false;
+                if (desc_for_point(m, new_pos_xz.x, new_pos_xz.z, td)) {
+                    const int ar = td.chunk_r * 64 + td.tile_r, acol = td.chunk_c * 64 + td.tile_c;
+                    const int dr[4] = {-1, 0, 0, 1}, dc[4] = {0, -1, 1, 0};
+                    for (int e = 0; e < 4 && !adj; e++) {
+                        const int nr = ar + dr[e], nc = acol + dc[e];
+                        if (nr < 0 || nr >= m.H64 || nc < 0 || nc >= m.W64) continue;
+                        adj = tile_blocked_abs(m, layer, nr, nc);
+                    }
+                }
+                if (adj) {
+                    for (int i = 0; i < ac.mc_n && !arrived; i++) {
+                        const float2 tc = mc_tiles[ac.mc_off + i];
+                        const v2 d = {tc.x - new_pos_xz.x, tc.y - new_pos_xz.z};
+                        if (v2_len(d) <= thresh) arrived = true;
+                    }
+                }
+            }
+            if (!arrived && ac.nearest_ok) {
+                const v2 d = {ac.nearest[0] - new_pos_xz.x, ac.nearest[1] - new_pos_xz.z};
+                if (v2_len(d) < thresh) arrived = true;
+            }
+        }
         if (!arrived) {
-            // N_IsAdjacentToImpassable (nav.c:4745) && N_IsMaximallyClose (nav.c:4707)
+            // adjacent_flock_members (movement.c:953): any flock member within r + r' + ADJACENCY_SEP_DIST that has
+            // ARRIVED. The spatial index pre-selects (radius r + max radius + 5 plus slack); the test itself is
+            // the reference's float comparison, so the outcome does not depend on the pre-selection.
+            const int32_t icx = bg_scale(curr_xz.x), icy = bg_scale(curr_xz.z), ir = bg_scale(a.radius + up.adj_query_r);
+            const int cx_lo = max((icx - ir - g.origin_x) >> 12, 0), cx_hi = min((icx + ir - g.origin_x) >> 12, g.grid_w - 1);
+            const int cy_lo = max((icy - ir - g.origin_y) >> 12, 0), cy_hi = min((icy + ir - g.origin_y) >> 12, g.grid_h - 1);
+            for (int cy = cy_lo; cy <= cy_hi && !arrived; cy++)
+                for (int cx = cx_lo; cx <= cx_hi && !arrived; cx++) {
+                    const int c = cy * g.grid_w + cx;
+                    const uint32_t b = g.cell_start[c], cnt = g.cell_count[c];
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const uint32_t o = g.id[b + k];
+                        if (o == uid) continue;
+                        const pf_record r = rec[o];
+                        if ((r.state_flags >> 24) != PFNAV_STATE_ARRIVED) continue;
+                        if (flock_of[o] != a.flock) continue;
+                        const v2 d = {curr_xz.x - r.px, curr_xz.z - r.pz};
+                        if (v2_len(d) <= a.radius + r.radius + 5.0f) { arrived = true; break; }
+                    }
+                }
+        }
+        if (arrived) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
+        } else if (v2_len(vdes) < EPS) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_WAITING; p.next_block = 1;
+        }
+        break;
+    }
+    case PFNAV_STATE_SEEK_ENEMIES:
+        break;                              // stays a soft obstacle and retries next tick (movement.c:2501)
+    case PFNAV_STATE_SURROUND_ENTITY:
+        if (ex.surround_target_uid == PFNAV_NULL_UID) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
+        } else p.engine_todo |= PFNAV_TODO_SURROUND_QUERY;
+        break;
+    case PFNAV_STATE_ENTER_ENTITY_RANGE: {
+        // movement.c:2569-2603
+        if (ex.surround_target_uid == PFNAV_NULL_UID) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
+            break;
+        }
+        const pf_record tr = rec[ex.surround_target_uid];
+        const v2 xz_target = {tr.px, tr.pz};
+        const v2 delta = v2_sub(new_pos_xz, xz_target);
+        bool stop = v2_len(delta) <= ex.target_range;
+        if (!stop && tarr) {
+            // M_NavIsAdjacentToImpassable(new_pos) && M_NavIsMaximallyClose(new_pos, target, 0): the tile list of the
+            // target is precomputed per work item on the host (pfnav_arrival_consts with the target's position)
             tile_desc td;
             bool adj = false;
             if (desc_for_point(m, new_pos_xz.x, new_pos_xz.z, td)) {
@@ -1932,44 +2369,68 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
                 }
             }
             if (adj) {
-                for (int i = 0; i < ac.mc_n && !arrived; i++) {
-                    const float2 tc = mc_tiles[ac.mc_off + i];
+                const pf_arrival_dev ta = tarr[wi];
+                for (int i = 0; i < ta.mc_n && !stop; i++) {
+                    const float2 tc = t_tiles[ta.mc_off + i];
                     const v2 d = {tc.x - new_pos_xz.x, tc.y - new_pos_xz.z};
-                    if (v2_len(d) <= thresh) arrived = true;
+                    if (v2_len(d) <= 0.0f) stop = true;          // tolerance 0.0f (movement.c:2584)
                 }
             }
         }
-        if (!arrived && ac.nearest_ok) {
-            const v2 d = {ac.nearest[0] - new_pos_xz.x, ac.nearest[1] - new_pos_xz.z};
-            if (v2_len(d) < thresh) arrived = true;
+        if (stop) { p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_WAITING; p.next_block = 1; break; }
+        const v2 tdelta = v2_sub(xz_target, v2{ex.target_prev_pos[0], ex.target_prev_pos[1]});
+        if (v2_len(tdelta) > 5.0f) {
+            p.flags |= PFNAV_UPDATE_SET_DEST | PFNAV_UPDATE_SET_TARGET_PREV;
+            p.next_dest[0] = xz_target.x; p.next_dest[1] = xz_target.z; p.next_attack = 0;
+            p.next_target_prev[0] = xz_target.x; p.next_target_prev[1] = xz_target.z;
         }
+        break;
     }
-    if (!arrived) {
-        // adjacent_flock_members (movement.c:953): any flock member within r + r' + ADJACENCY_SEP_DIST that has
-        // ARRIVED. The spatial index pre-selects (radius r + max radius + 5 plus slack); the test itself is
-        // the reference's float comparison, so the outcome does not depend on the pre-selection.
-        const int32_t icx = bg_scale(curr_xz.x), icy = bg_scale(curr_xz.z), ir = bg_scale(a.radius + up.adj_query_r);
-        const int cx_lo = max((icx - ir - g.origin_x) >> 12, 0), cx_hi = min((icx + ir - g.origin_x) >> 12, g.grid_w - 1);
-        const int cy_lo = max((icy - ir - g.origin_y) >> 12, 0), cy_hi = min((icy + ir - g.origin_y) >> 12, g.grid_h - 1);
-        for (int cy = cy_lo; cy <= cy_hi && !arrived; cy++)
-            for (int cx = cx_lo; cx <= cx_hi && !arrived; cx++) {
-                const int c = cy * g.grid_w + cx;
-                const uint32_t b = g.cell_start[c], cnt = g.cell_count[c];
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const uint32_t o = g.id[b + k];
-                    if (o == uid) continue;
-                    const pf_record r = rec[o];
-                    if ((r.state_flags >> 24) != PFNAV_STATE_ARRIVED) continue;
-                    if (flock_of[o] != a.flock) continue;
-                    const v2 d = {curr_xz.x - r.px, curr_xz.z - r.pz};
-                    if (v2_len(d) <= a.radius + r.radius + 5.0f) { arrived = true; break; }
-                }
-            }
+    case PFNAV_STATE_TURNING: {
+        // movement.c:2605-2627
+        const quat ent_rot = {ex.rot[0], ex.rot[1], ex.rot[2], ex.rot[3]};
+        const quat tdir = {ex.target_dir[0], ex.target_dir[1], ex.target_dir[2], ex.target_dir[3]};
+        const float degrees = (float)((double)quat_pitch_diff(ent_rot, tdir) * (180.0f / PF_PI_D));
+        if (fabs((double)degrees) <= 5.0f) {
+            p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
+            break;
+        }
+        const quat fin_rot = turn_toward(ent_rot, tdir, turn_rate);
+        p.flags |= PFNAV_UPDATE_SET_ROTATION | PFNAV_UPDATE_SET_PREV_ROT;
+        p.next_rot[0] = fin_rot.x; p.next_rot[1] = fin_rot.y; p.next_rot[2] = fin_rot.z; p.next_rot[3] = fin_rot.w;
+        p.next_prot[0] = fin_rot.x; p.next_prot[1] = fin_rot.y; p.next_prot[2] = fin_rot.z; p.next_prot[3] = fin_rot.w;
+        break;
     }
-    if (arrived) {
-        p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_ARRIVED; p.next_block = 1;
-    } else if (v2_len(vdes) < EPS) {
-        p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_WAITING; p.next_block = 1;
+    case PFNAV_STATE_WAITING:
+        // movement.c:2630-2645: the countdown lives in the movestate itself
+        p.wait_ticks_left = ex.wait_ticks_left - 1;
+        if (p.wait_ticks_left == 0) { p.flags |= PFNAV_UPDATE_SET_MOVING; p.next_state = ex.wait_prev; }
+        break;
+    case PFNAV_STATE_ARRIVED:
+        break;
+    case PFNAV_STATE_ARRIVING_TO_CELL:
+        // movement.c:2648-2670
+        if (!has_fid) { p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_MOVING; break; }
+        if (!(fflags & PFNAV_FORM_ASSIGNMENT_READY)) break;
+        if (!(fflags & PFNAV_FORM_IN_RANGE_OF_CELL)) { p.flags |= PFNAV_UPDATE_SET_STATE; p.next_state = PFNAV_STATE_MOVING_IN_FORMATION; break; }
+        if (fflags & PFNAV_FORM_ARRIVED_AT_CELL) {
+            p.flags |= PFNAV_UPDATE_SET_STATE | PFNAV_UPDATE_SET_TARGET_DIR; p.next_state = PFNAV_STATE_TURNING;
+            for (int i = 0; i < 4; i++) p.next_target_dir[i] = fin.target_orientation[i];
+        }
+        break;
+    default:
+        break;
+    }
+    {   // ent_update_using_surround_field (movement.c:2672-2691) runs at the end of the apply on the tick's snapshot
+        // positions; it is evaluated here, where the snapshot is still intact, and carried in the patch
+        const uint32_t after = (p.flags & (PFNAV_UPDATE_SET_STATE | PFNAV_UPDATE_SET_MOVING)) ? (uint32_t)p.next_state : state;
+        if (after == PFNAV_STATE_SURROUND_ENTITY && ex.surround_target_uid != PFNAV_NULL_UID) {
+            const pf_record tr = rec[ex.surround_target_uid];
+            const float dx = (float)fabs((double)(tr.px - curr_xz.x)), dz = (float)fabs((double)(tr.pz - curr_xz.z));
+            const float low = (float)(256.0 / 3.0f), high = (float)(256.0 / 2.0f);       // CHUNK_WIDTH / 3, / 2 (movement.c:440-443)
+            if (!ex.using_surround_field) { if (dx < low && dz < low) p.engine_todo |= PFNAV_TODO_USE_SURROUND_FIELD; }
+            else if (dx >= high || dz >= high) p.engine_todo |= PFNAV_TODO_DROP_SURROUND_FIELD;
+        }
     }
     out[wi] = p;
 }
@@ -1977,7 +2438,7 @@ k_entity_update(MapView m, GridView g, UpdateParams up, const pfnav_agent *__res
 // entity_apply_update (movement.c:2693-2757), movestate fields only
 __global__ void k_entity_apply(pfnav_agent *__restrict__ agents, pfnav_movestate *__restrict__ mss,
                                pf_record *__restrict__ rec, const uint32_t *__restrict__ work, int nwork,
-                               const pfnav_patch *__restrict__ patches)
+                               const pfnav_patch *__restrict__ patches, pfnav_movestate_ext *__restrict__ exts)
 {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwork) return;
@@ -1987,11 +2448,15 @@ __global__ void k_entity_apply(pfnav_agent *__restrict__ agents, pfnav_movestate
     pfnav_movestate ms = mss[uid];
     const float EPS = 1.0f / 1024;
     if (a.flags & PFNAV_FLAG_GARRISONED) return;
+    pfnav_movestate_ext ex;
+    if (exts) { ex = exts[uid]; ex.wait_ticks_left = p.wait_ticks_left; }      // the countdown of STATE_WAITING (movement.c:2633)
     if (p.flags & PFNAV_UPDATE_SET_STATE) {
-        a.state = (uint32_t)p.next_state;
         if (p.next_state == PFNAV_STATE_ARRIVED || p.next_state == PFNAV_STATE_WAITING) {
-            a.velocity[0] = 0.0f; a.velocity[1] = 0.0f;      // entity_finish_moving (movement.c:685)
+            // entity_finish_moving (movement.c:685): blockers / events / combat stance stay with the engine
+            if (exts && p.next_state == PFNAV_STATE_WAITING) { ex.wait_prev = (int32_t)a.state; ex.wait_ticks_left = 60; }     // WAIT_TICKS
+            a.velocity[0] = 0.0f; a.velocity[1] = 0.0f;
         }
+        a.state = (uint32_t)p.next_state;
     }
     if (p.flags & PFNAV_UPDATE_SET_VELOCITY) {
         a.velocity[0] = p.next_velocity[0]; a.velocity[1] = p.next_velocity[1];
@@ -2018,6 +2483,23 @@ __global__ void k_entity_apply(pfnav_agent *__restrict__ agents, pfnav_movestate
     if (p.flags & PFNAV_UPDATE_SET_STEP) ms.step = p.next_step;
     if (p.flags & PFNAV_UPDATE_SET_LEFT) ms.left = (int)p.next_left;
     if (p.flags & PFNAV_UPDATE_SET_NEXT_ROT) { ms.next_rot[0] = p.next_nrot[0]; ms.next_rot[1] = p.next_nrot[1]; ms.next_rot[2] = p.next_nrot[2]; ms.next_rot[3] = p.next_nrot[3]; }
+    if (exts) {
+        if (p.flags & PFNAV_UPDATE_SET_ROTATION) { ex.rot[0] = p.next_rot[0]; ex.rot[1] = p.next_rot[1]; ex.rot[2] = p.next_rot[2]; ex.rot[3] = p.next_rot[3]; }   // Entity_SetRot
+        if (p.flags & PFNAV_UPDATE_SET_TARGET_PREV) { ex.target_prev_pos[0] = p.next_target_prev[0]; ex.target_prev_pos[1] = p.next_target_prev[1]; }
+        if (p.flags & PFNAV_UPDATE_SET_TARGET_DIR) { ex.target_dir[0] = p.next_target_dir[0]; ex.target_dir[1] = p.next_target_dir[1]; ex.target_dir[2] = p.next_target_dir[2]; ex.target_dir[3] = p.next_target_dir[3]; }
+    }
+    if (p.flags & PFNAV_UPDATE_SET_MOVING) {
+        // movement.c:2750-2755: entity_unblock is the engine's; move_notify_motion_start wipes the velocity history
+        if (!(a.flags & PFNAV_FLAG_COMBAT_HELD))
+            for (int i = 0; i < PFNAV_VEL_HIST_LEN; i++) { ms.vel_hist[i][0] = 0.0f; ms.vel_hist[i][1] = 0.0f; }
+        a.state = (uint32_t)p.next_state;
+    }
+    if (exts && a.state == PFNAV_STATE_SURROUND_ENTITY) {
+        // ent_update_using_surround_field (movement.c:2672), decided by the update pass on the tick's snapshot positions
+        if (p.engine_todo & PFNAV_TODO_USE_SURROUND_FIELD) ex.using_surround_field = 1;
+        if (p.engine_todo & PFNAV_TODO_DROP_SURROUND_FIELD) ex.using_surround_field = 0;
+    }
+    if (exts) exts[uid] = ex;
     agents[uid] = a;
     mss[uid] = ms;
     pf_record r;
@@ -2040,6 +2522,51 @@ extern "C" int pfnav_agents_upload_movestate(pfnav_ctx *ctx, const pfnav_movesta
     PF_CUDA(cudaMemcpy(ctx->d_movestate + ctx->shard_lo, ms, n * sizeof(pfnav_movestate), cudaMemcpyHostToDevice));
     ctx->movestate_set = true;
     return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_upload_formation(pfnav_ctx *ctx, const pfnav_formation_in *f, size_t n)
+{
+    PF_ARG(ctx && ctx->d_agents && f, "agents not uploaded / null");
+    PF_ARG(n == ctx->shard_hi - ctx->shard_lo, "one record per uploaded agent (of this context's own range)");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n_agents > ctx->cap_formation) {
+        cudaFree(ctx->d_formation); ctx->d_formation = nullptr; ctx->cap_formation = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_formation, ctx->n_agents * sizeof(pfnav_formation_in)));
+        PF_CUDA(cudaMemset(ctx->d_formation, 0, ctx->n_agents * sizeof(pfnav_formation_in)));
+        ctx->cap_formation = ctx->n_agents;
+    }
+    PF_CUDA(cudaMemcpy(ctx->d_formation + ctx->shard_lo, f, n * sizeof(pfnav_formation_in), cudaMemcpyHostToDevice));
+    return PFNAV_OK;
+}
+
+extern "C" int pfnav_agents_upload_movestate_ext(pfnav_ctx *ctx, const pfnav_movestate_ext *ms, size_t n)
+{
+    PF_ARG(ctx && ctx->d_agents && ms, "agents not uploaded / null");
+    PF_ARG(n == ctx->shard_hi - ctx->shard_lo, "one record per uploaded agent (of this context's own range)");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n_agents > ctx->cap_ms_ext) {
+        cudaFree(ctx->d_ms_ext); ctx->d_ms_ext = nullptr; ctx->cap_ms_ext = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_ms_ext, ctx->n_agents * sizeof(pfnav_movestate_ext)));
+        ctx->cap_ms_ext = ctx->n_agents;
+    }
+    PF_CUDA(cudaMemcpy(ctx->d_ms_ext + ctx->shard_lo, ms, n * sizeof(pfnav_movestate_ext), cudaMemcpyHostToDevice));
+    return PFNAV_OK;
+}
+
+// work items in STATE_ENTER_ENTITY_RANGE and where their target stands (for the N_IsMaximallyClose clause, movement.c:2583)
+struct pf_enter_item { uint32_t wi; int32_t layer; float tx, tz; };
+__global__ void k_collect_enter_range(const pfnav_agent *__restrict__ agents, const pfnav_movestate_ext *__restrict__ exts,
+                                      const pf_record *__restrict__ rec, const uint32_t *__restrict__ work, int nwork,
+                                      pf_enter_item *__restrict__ out, uint32_t *__restrict__ count)
+{
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwork) return;
+    const uint32_t uid = work[wi];
+    const pfnav_agent a = agents[uid];
+    if (a.state != PFNAV_STATE_ENTER_ENTITY_RANGE || exts[uid].surround_target_uid == PFNAV_NULL_UID) return;
+    const pf_record tr = rec[exts[uid].surround_target_uid];
+    const uint32_t k = atomicAdd(count, 1u);
+    out[k] = {(uint32_t)wi, nav_layer_for(a.flags, a.radius), tr.px, tr.pz};
 }
 
 static int refresh_arrival_consts(pfnav_ctx *ctx, cudaStream_t st)
@@ -2077,7 +2604,6 @@ extern "C" int pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream)
 {
     PF_ARG(ctx && ctx->d_agents, "agents not uploaded");
     PF_ARG(ctx->movestate_set, "pfnav_agents_upload_movestate not called");
-    PF_ARG(!ctx->has_unsupported_state, "formation / surround / enter-range / turning states are outside this path");
     if (ctx->n_work == 0) return PFNAV_OK;
     PF_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = pf_stream(ctx, stream);
@@ -2097,10 +2623,51 @@ extern "C" int pfnav_agents_compute_updates(pfnav_ctx *ctx, void *stream)
     up.adj_query_r = ctx->max_radius + 5.0f + 0.0625f;
     const int nwork = (int)ctx->n_work;
     const size_t b0 = ctx->n_flocks * (size_t)ctx->nlayers * sizeof(pf_arrival_dev);
+    // STATE_ENTER_ENTITY_RANGE: the tiles N_IsMaximallyClose (nav.c:4707) compares with depend on where the TARGET entity
+    // stands; they are computed on the host per work item in that state (a handful of units at a time)
+    const pf_arrival_dev *d_tarr = nullptr; const float2 *d_ttiles = nullptr;
+    if (ctx->d_ms_ext) {
+        if ((size_t)nwork > ctx->cap_enter) {
+            cudaFree(ctx->d_enter); ctx->d_enter = nullptr; ctx->cap_enter = 0;
+            PF_CUDA(cudaMalloc(&ctx->d_enter, (size_t)nwork * (sizeof(pf_enter_item) + sizeof(pf_arrival_dev)) + 16));
+            ctx->cap_enter = (size_t)nwork;
+        }
+        uint32_t *d_cnt = (uint32_t *)ctx->d_enter;
+        pf_enter_item *d_items = (pf_enter_item *)((uint8_t *)ctx->d_enter + 16);
+        pf_arrival_dev *d_t = (pf_arrival_dev *)(d_items + nwork);
+        PF_CUDA(cudaMemsetAsync(d_cnt, 0, 4, st));
+        k_collect_enter_range<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_agents, ctx->d_ms_ext, ctx->d_records, ctx->d_work, nwork, d_items, d_cnt);
+        ctx->launches++;
+        uint32_t cnt = 0;
+        PF_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        PF_CUDA(cudaStreamSynchronize(st));
+        if (cnt) {
+            std::vector<pf_enter_item> items(cnt);
+            PF_CUDA(cudaMemcpy(items.data(), d_items, cnt * sizeof(pf_enter_item), cudaMemcpyDeviceToHost));
+            std::vector<pf_arrival_dev> tarr(nwork);
+            memset(tarr.data(), 0, tarr.size() * sizeof(pf_arrival_dev));
+            std::vector<float2> tiles;
+            pf_arrival_consts c;
+            for (const pf_enter_item &it : items) {
+                if ((rc = pfnav_arrival_consts(ctx, it.layer, it.tx, it.tz, &c))) return rc;
+                tarr[it.wi].mc_n = c.mc_n; tarr[it.wi].mc_off = (int32_t)tiles.size();
+                for (int i = 0; i < c.mc_n; i++) tiles.push_back(make_float2(c.mc[i][0], c.mc[i][1]));
+            }
+            if (tiles.size() * sizeof(float2) > ctx->cap_ttiles) {
+                cudaFree(ctx->d_ttiles); ctx->d_ttiles = nullptr; ctx->cap_ttiles = 0;
+                PF_CUDA(cudaMalloc(&ctx->d_ttiles, tiles.size() * sizeof(float2) * 2));
+                ctx->cap_ttiles = tiles.size() * sizeof(float2) * 2;
+            }
+            PF_CUDA(cudaMemcpy(d_t, tarr.data(), tarr.size() * sizeof(pf_arrival_dev), cudaMemcpyHostToDevice));
+            if (!tiles.empty()) PF_CUDA(cudaMemcpy(ctx->d_ttiles, tiles.data(), tiles.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            d_tarr = d_t; d_ttiles = (const float2 *)ctx->d_ttiles;
+        }
+    }
     pf_prof_scope prof(ctx, st, PF_PROF_UPDATE);
     k_entity_update<<<(nwork + 127) / 128, 128, 0, st>>>(m, grid_of(ctx), up, ctx->d_agents, ctx->d_records, ctx->d_movestate,
         ctx->d_flocks, (const pf_arrival_dev *)ctx->d_arrival, (const float2 *)((const uint8_t *)ctx->d_arrival + b0),
-        ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches, ctx->d_flock_of);
+        ctx->nlayers, ctx->d_work, nwork, ctx->d_vel_out, ctx->d_vdes_out, ctx->d_patches, ctx->d_flock_of,
+        ctx->d_ms_ext, ctx->d_formation, d_tarr, d_ttiles);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaEventRecord(ctx->update_done, st));
@@ -2126,7 +2693,7 @@ extern "C" int pfnav_agents_apply_updates(pfnav_ctx *ctx, void *stream)
     const int nwork = (int)ctx->n_work;
     pf_prof_scope prof(ctx, st, PF_PROF_APPLY);
     k_entity_apply<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_agents, ctx->d_movestate, ctx->d_records, ctx->d_work, nwork,
-                                                       ctx->d_patches);
+                                                       ctx->d_patches, ctx->d_ms_ext);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaEventRecord(ctx->update_done, st));
@@ -2159,12 +2726,37 @@ struct pf_miss { uint32_t wi, uid; int32_t dest, chunk, tile, liid; float px, pz
 __global__ void k_collect_misses(MapView m, PoolView pool, const uint16_t *__restrict__ liid_img,
                                  const pfnav_agent *__restrict__ agents, const pfnav_flock *__restrict__ flocks,
                                  const uint32_t *__restrict__ work, int nwork, int kind, pf_miss *__restrict__ out,
-                                 uint32_t *__restrict__ count, uint32_t cap)
+                                 uint32_t *__restrict__ count, uint32_t cap, const pfnav_movestate_ext *__restrict__ exts, int nlayers_)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwork) return;
     const uint32_t uid = work[w];
     const pfnav_agent a = agents[uid];
+    if (kind == 2) {
+        // kind 2: N_DesiredEnemySeekVelocity / N_DesiredSurroundVelocity (nav.c:3603, 3687): the entity's TARGET_ENEMIES /
+        // TARGET_ENTITY field exists but its own tile has no direction
+        const bool seek = a.state == PFNAV_STATE_SEEK_ENEMIES;
+        const bool surr = a.state == PFNAV_STATE_SURROUND_ENTITY && exts && exts[uid].surround_target_uid != PFNAV_NULL_UID &&
+                          exts[uid].using_surround_field;
+        const int dest = (int)a.aux_dest1 - 1;
+        if (!(seek || surr) || dest < 0 || dest >= pool.ndests) return;
+        tile_desc t;
+        if (!desc_for_point(m, a.pos[0], a.pos[1], t)) return;
+        const int chunks = m.chunk_w * m.chunk_h, chunk = t.chunk_r * m.chunk_w + t.chunk_c;
+        const int sl = pool.slot[(size_t)dest * chunks + chunk];
+        if (sl < 0 || !(pool.has[sl] & 1)) return;                      // building it needs the engine's entity list
+        const int layer = nav_layer_for(a.flags, a.radius);
+        const uint16_t li = layer < nlayers_ ? liid_img[((size_t)layer * m.H64 + t.chunk_r * 64 + t.tile_r) * m.W64 + t.chunk_c * 64 + t.tile_c] : 0xFFFF;
+        // the surround variant repairs a blocked tile whether or not it already has a direction (nav.c:3729)
+        if ((pool.flow[(size_t)sl * 4096 + t.tile_r * 64 + t.tile_c] & 0xF) != 0 && !(surr && li == 0xFFFF)) return;
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k >= cap) return;
+        pf_miss r;
+        r.wi = (uint32_t)w; r.uid = uid; r.dest = dest; r.chunk = chunk; r.tile = t.tile_r * 64 + t.tile_c; r.liid = li;
+        r.px = a.pos[0]; r.pz = a.pos[1];
+        out[k] = r;
+        return;
+    }
     if (a.flock < 0) return;
     const pfnav_flock fl = flocks[a.flock];
     if (fl.dest < 0 || fl.dest >= pool.ndests) return;
@@ -2226,7 +2818,7 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
         pv.touch = nullptr; pv.tick_no = 0;
         PF_CUDA(cudaMemsetAsync(d_cnt, 0, 4, st));
         k_collect_misses<<<(nwork + 127) / 128, 128, 0, st>>>(m, pv, ctx->d_liid, ctx->d_agents, ctx->d_flocks, ctx->d_work, nwork,
-                                                             kind, d_miss, d_cnt, (uint32_t)nwork);
+                                                             kind, d_miss, d_cnt, (uint32_t)nwork, ctx->d_ms_ext, ctx->nlayers);
         ctx->launches++;
         uint32_t cnt = 0;
         PF_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
@@ -2238,7 +2830,7 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
         reps.clear();
         for (const pf_miss &r : miss) {
             uint64_t key = ((uint64_t)r.dest << 40) | ((uint64_t)r.chunk << 20);
-            if (kind == 1) key |= (r.liid == 0xFFFF ? (0x10000u | (uint32_t)r.tile) : (uint32_t)r.liid);
+            if (kind >= 1) key |= (r.liid == 0xFFFF ? (0x10000u | (uint32_t)r.tile) : (uint32_t)r.liid);
             if (std::find(seen.begin(), seen.end(), key) != seen.end()) continue;
             seen.push_back(key);
             reps.push_back(r);
@@ -2292,6 +2884,32 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
             int32_t kind, arg;
             if (r.liid == 0xFFFF) { kind = PFNAV_REPAIR_NEAREST_PATHABLE; arg = ((r.tile >> 6) << 8) | (r.tile & 63); }
             else                  { kind = PFNAV_REPAIR_ISLAND_TO_NEAREST; arg = r.liid; }
+            const int32_t sl = slot;
+            if ((rc = pfnav_flow_repair_pool(ctx, &tg, &kind, &arg, &sl, 1))) break;
+            nrep++;
+        }
+    }
+    // ---- enemy-seek / surround fields: in-place repairs only (nav.c:3647-3675, 3729-3757) ----
+    if (!rc && !(rc = collect(2, reps))) {
+        for (const pf_miss &r : reps) {
+            const int slot = ctx->h_pool_slot[(size_t)r.dest * chunks + r.chunk];
+            if (slot < 0 || !(ctx->h_pool_has[slot] & 1)) continue;
+            uint8_t d = 0;
+            if (cudaDeviceSynchronize() != cudaSuccess ||
+                cudaMemcpy(&d, ctx->d_pool_flow + (size_t)slot * 4096 + r.tile, 1, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                pfnav_set_error("pfnav_pool_repair: read-back failed"); rc = PFNAV_ERR_CUDA; break;
+            }
+            const pfnav_field_req tg = ctx->h_pool_req[slot];
+            if ((tg.target_type & 0xFF) < 2) continue;
+            const bool surround = (tg.target_type & 0xFF) == 2 + PFNAV_TARGET_ENTITY;
+            int32_t kind, arg;
+            if (r.liid == 0xFFFF) {
+                if ((d & 0xF) != 0 && !surround) continue;
+                kind = PFNAV_REPAIR_NEAREST_PATHABLE; arg = ((r.tile >> 6) << 8) | (r.tile & 63);
+            } else {
+                if ((d & 0xF) != 0) continue;
+                kind = PFNAV_REPAIR_ISLAND_TO_NEAREST; arg = r.liid;
+            }
             const int32_t sl = slot;
             if ((rc = pfnav_flow_repair_pool(ctx, &tg, &kind, &arg, &sl, 1))) break;
             nrep++;

@@ -767,6 +767,14 @@ __device__ void los_blocked_line(LosSmem &s, const LosMapInfo mi, int tgt_cr, in
     const float len = sqrtf(sx_ * sx_ + sz_ * sz_);   // PFM_Vec2_Len: float sum, correctly rounded sqrt
     sx_ = sx_ / len;
     sz_ = sz_ / len;
+    if (!(len > 0.0f)) {
+        // The line starts ON the target tile (a blocked / impassable destination seen as a corner by its neighbour):
+        // the slope is 0/0 = NaN, (int)(NaN * 1000) is INT_MIN on x86-64 (cvttss2si), abs() and the negation leave it
+        // there, err = dx + dy wraps to 0 (the engine is built with -fwrapv) and every step takes the `e2 >= dy` branch
+        // only: with sx = -1 (NaN > 0 is false) the reference marks the row from the tile to column 0.
+        or_row(&s.blk[r], (c == 63) ? ~0ull : ((2ull << c) - 1));
+        return;
+    }
     int dx = abs((int)(sx_ * 1000));
     int dy = -abs((int)(sz_ * 1000));
     const int sx = sx_ > 0.0f ? 1 : -1;
@@ -1104,6 +1112,12 @@ __device__ void los_blocked_line_b(LosSmemB &s, const LosMapInfo mi, int tgt_cr,
     const float len = sqrtf(sx_ * sx_ + sz_ * sz_);
     sx_ = sx_ / len;
     sz_ = sz_ / len;
+    if (!(len > 0.0f)) {
+        // line from the target tile to itself: NaN slope, INT_MIN deltas, wrapped error term -- the reference walks the
+        // row towards column 0 (see los_blocked_line)
+        for (int idx0 = (r + 1) * LB_W + (c + 1); !(s.st[idx0] & LB_BORDER); idx0--) s.st[idx0] |= LB_BLK;
+        return;
+    }
     const int dx = abs((int)(sx_ * 1000));
     const int dy = -abs((int)(sz_ * 1000));
     const int sx = sx_ > 0.0f ? 1 : -1;
@@ -1414,6 +1428,7 @@ extern "C" int pfnav_create(int device, pfnav_ctx **out)
         return PFNAV_ERR_CUDA;
     }
     int rc = pfnav_fields_init(ctx);
+    if (!rc) rc = pfnav_agents_init(ctx);
     if (rc) { delete ctx; return rc; }
     *out = ctx;
     return PFNAV_OK;
@@ -1546,7 +1561,7 @@ extern "C" int pfnav_map_create(pfnav_ctx *ctx, int chunk_w, int chunk_h, int nl
     }
     ctx->pool_ndests = 0; ctx->pool_max = 0; ctx->pool_used = 0;
     ctx->h_pool_slot.clear(); ctx->h_pool_has.clear(); ctx->h_pool_req.clear(); ctx->h_pool_ffid.clear();
-    ctx->h_slot_owner.clear(); ctx->h_slot_touch.clear(); ctx->pool_free.clear();
+    ctx->h_slot_owner.clear(); ctx->h_slot_touch.clear(); ctx->pool_free.clear(); ctx->aux.clear();
     ctx->goal_batch.valid = false;
     ctx->chunk_w = chunk_w; ctx->chunk_h = chunk_h; ctx->nlayers = nlayers;
     ctx->W64 = chunk_w * 64; ctx->H64 = chunk_h * 64;

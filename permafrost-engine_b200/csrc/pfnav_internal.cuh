@@ -115,6 +115,9 @@ struct pfnav_ctx {
     std::vector<int32_t>  pool_free;              // evicted slots, reused before pool_used grows
     uint32_t tick_no = 1;                         // advanced by pfnav_agents_tick
     uint64_t pool_evictions = 0;
+    // TARGET_ENEMIES / TARGET_ENTITY destinations (pfnav_pool_request_entity_fields): what their repairs start from
+    struct aux_target { int kind = -1, layer = 0, ref_layer = 0; std::vector<pfnav_footprint> ents; };
+    std::vector<aux_target> aux;
 
     // ---- agents ----
     size_t n_agents = 0, cap_agents = 0, n_flocks = 0, cap_flocks = 0;
@@ -125,6 +128,9 @@ struct pfnav_ctx {
     uint32_t *d_flock_start = nullptr;    // [nflocks+1] offsets into d_flock_members
     uint32_t *d_flock_members = nullptr;  // agent ids grouped by flock, ascending uid
     int32_t  *d_flock_of = nullptr;       // [n_agents] flock id column (all-gathered with the records)
+    pfnav_formation_in  *d_formation = nullptr; size_t cap_formation = 0;   // optional formation inputs, uid order
+    pfnav_movestate_ext *d_ms_ext = nullptr;    size_t cap_ms_ext = 0;      // optional: the movestate beyond point seeking
+    void *d_enter = nullptr; size_t cap_enter = 0; void *d_ttiles = nullptr; size_t cap_ttiles = 0;   // ENTER_ENTITY_RANGE scratch
     uint32_t *d_facts = nullptr;          // {max radius bits, any garrisoned}
     // multi-GPU: this context owns the entity index range [shard_lo, shard_hi) of the population (pfnav_mgpu.cu)
     size_t shard_lo = 0, shard_hi = 0;
@@ -218,6 +224,8 @@ int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const
 
 int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk);
 
+int pfnav_aux_chunk_seeds(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, std::vector<int> &out);     // pfnav_region.cu
+
 // pool slots with LRU eviction (pfnav_plan.cu)
 int pf_pool_reserve(pfnav_ctx *ctx, const size_t *keys, size_t n, int32_t *slots_out, bool *out_evicted);
 
@@ -252,6 +260,7 @@ int pfnav_los_launch(pfnav_ctx *ctx, const pfnav_los_req *d_reqs, size_t n, uint
 
 // ---- pfnav_agents.cu ----
 void pfnav_agents_free(pfnav_ctx *ctx);
+int pfnav_agents_init(pfnav_ctx *ctx);
 int pfnav_agents_finish_snapshot(pfnav_ctx *ctx, cudaStream_t st, bool members);
 
 // ---- device helpers shared by kernels ----

@@ -663,3 +663,82 @@ extern "C" int pfnav_entity_fields(pfnav_ctx *ctx, int layer, int ref_layer, int
     cudaFree(d_out);
     return rc;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// TARGET_ENEMIES / TARGET_ENTITY fields as pool destinations: what N_RequestAsyncEnemySeekField /
+// N_RequestAsyncSurroundField + N_AwaitAsyncFields leave in the field cache for the chunks the seekers stand on
+// (nav.c:3769-3960), consumed by N_DesiredEnemySeekVelocity / N_DesiredSurroundVelocity (k_desired_velocity).
+// ------------------------------------------------------------------------------------------
+extern "C" int pfnav_pool_request_entity_fields(pfnav_ctx *ctx, int dest, int layer, int ref_layer, int target_kind,
+                                                const pfnav_footprint *ents, size_t nents, const int32_t *chunks_rc, size_t n,
+                                                void *stream)
+{
+    PF_ARG(ctx && ctx->d_pool_slot, "pool not created");
+    PF_NEED_DEVICE(ctx);
+    PF_ARG(dest >= 0 && dest < ctx->pool_ndests, "dest");
+    PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    int rc = entity_args_ok(ctx, ref_layer, target_kind, ents, nents);
+    if (rc) return rc;
+    // the footprints stay with the destination: the in-place repairs of its fields start from them (field.c:2334-2360)
+    if (ctx->aux.size() < (size_t)ctx->pool_ndests) ctx->aux.resize(ctx->pool_ndests);
+    pfnav_ctx::aux_target &A = ctx->aux[dest];
+    A.kind = target_kind; A.layer = layer; A.ref_layer = ref_layer; A.ents.assign(ents, ents + nents);
+    if (n == 0) return PFNAV_OK;
+    PF_ARG(chunks_rc, "chunks");
+    int dim = 0;
+    if ((rc = zone_dim(ctx, &dim))) return rc;
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    std::vector<int32_t> seeds;
+    std::vector<size_t> off(n + 1, 0), keys(n);
+    for (size_t i = 0; i < n; i++) {
+        const int cr = chunks_rc[2 * i], cc = chunks_rc[2 * i + 1];
+        PF_ARG(cr >= 0 && cr < ctx->chunk_h && cc >= 0 && cc < ctx->chunk_w, "entity field: chunk");
+        if ((rc = entity_seeds(ctx, ref_layer, target_kind, ents, nents, dim, cr, cc, seeds))) return rc;
+        off[i + 1] = seeds.size() / 2;
+        keys[i] = (size_t)dest * chunks + cr * ctx->chunk_w + cc;
+    }
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));
+    std::vector<int32_t> slots(n);
+    bool evicted = false;
+    if ((rc = pf_pool_reserve(ctx, keys.data(), n, slots.data(), &evicted))) return rc;
+    cudaStream_t st = pf_stream(ctx, stream);
+    uint8_t *d_out = nullptr;
+    PF_CUDA(cudaMalloc(&d_out, n * 4096));
+    rc = chunk_fields_launch(ctx, layer, dim, chunks_rc, n, seeds, off, d_out, st);
+    for (size_t i = 0; i < n && rc == 0; i++) {
+        if (cudaMemcpyAsync(ctx->d_pool_flow + (size_t)slots[i] * 4096, d_out + i * 4096, 4096, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            pfnav_set_error("pfnav_pool_request_entity_fields: copy into the pool failed"); rc = PFNAV_ERR_CUDA;
+        }
+        ctx->h_pool_has[slots[i]] |= 1;
+        pfnav_field_req q;
+        memset(&q, 0, sizeof(q));
+        q.chunk_r = chunks_rc[2 * i]; q.chunk_c = chunks_rc[2 * i + 1]; q.layer = layer; q.faction_id = PFNAV_FACTION_ID_NONE;
+        q.target_type = 2 + target_kind;          // beyond the chunk-local kinds: the frontier comes from ctx->aux[dest]
+        q._pad = dest;
+        ctx->h_pool_req[slots[i]] = q;
+    }
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(ctx->d_pool_slot, ctx->h_pool_slot.data(), ctx->h_pool_slot.size() * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { pfnav_set_error("pfnav_pool_request_entity_fields: %s", cudaGetErrorString(e)); rc = PFNAV_ERR_CUDA; }
+    }
+    cudaFree(d_out);
+    ctx->goal_batch.valid = false;
+    return rc;
+}
+
+// the chunk-local frontier of a TARGET_ENEMIES / TARGET_ENTITY pool destination (field_enemies_initial_frontier /
+// field_entity_initial_frontier with the chunk itself as the region, field.c:2334-2360): tile indices r * 64 + c
+int pfnav_aux_chunk_seeds(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, std::vector<int> &out)
+{
+    PF_ARG(dest >= 0 && (size_t)dest < ctx->aux.size() && ctx->aux[dest].kind >= 0, "no entity fields were requested for this destination");
+    const pfnav_ctx::aux_target &A = ctx->aux[dest];
+    std::vector<int32_t> seeds;
+    int rc = entity_seeds(ctx, A.ref_layer, A.kind, A.ents.data(), A.ents.size(), 64, chunk_r, chunk_c, seeds);
+    if (rc) return rc;
+    for (size_t i = 0; i + 1 < seeds.size(); i += 2) out.push_back((seeds[i] - chunk_r * 64) * 64 + (seeds[i + 1] - chunk_c * 64));
+    return PFNAV_OK;
+}

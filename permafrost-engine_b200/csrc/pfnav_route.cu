@@ -976,7 +976,11 @@ int pfnav_repair_seeds(pfnav_ctx *ctx, const pfnav_field_req &q, int kind, int a
     const uint16_t *gisl = prl->islands.data() + (size_t)chunk * 4096;
     const uint16_t local_iid = (uint16_t)arg;
     std::vector<int> init;
-    if ((q.target_type & 0xFF) == PFNAV_TARGET_TILE) {
+    if ((q.target_type & 0xFF) >= 2) {
+        // TARGET_ENEMIES / TARGET_ENTITY field of pool destination q._pad: the entities' own tiles inside the chunk
+        int rc = pfnav_aux_chunk_seeds(ctx, q._pad, q.chunk_r, q.chunk_c, init);
+        if (rc) return rc;
+    } else if ((q.target_type & 0xFF) == PFNAV_TARGET_TILE) {
         // field_tile_initial_frontier (field.c:1096); when the tile is blocked the reference retries with
         // ignoreblock (field.c:2367) -- either way the frontier is the tile itself
         init.push_back(q.tile_r * 64 + q.tile_c);

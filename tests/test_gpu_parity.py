@@ -863,3 +863,37 @@ def test_stress_scenario_golden(nav):
         assert (fl_ is not None) == bool(hf) and (lo_ is not None) == bool(hl), (f, cr, cc)
         assert (not hf or (fl_ == g["pool_flow"][k]).all()) and (not hl or (lo_ == g["pool_los"][k]).all()), (f, cr, cc)
     tick_and_check("on-miss chain")
+
+
+def test_los_blocked_destination_tile(nav, pforacle):
+    """the destination tile itself is blocked: its neighbour sees it as a corner and casts the `wavefront blocked` line
+    from the tile to ITSELF -- a 0/0 slope whose x86 float->int conversions (INT_MIN) and wrapped error term make the
+    reference mark the whole row towards column 0 (field.c:463-517). Found by the link-swap test; the port reproduces it."""
+    cw = ch = 3
+    p = cases.noise_map(cw, ch, 8181, 0.08)
+    cost = synth.cost_from_pathable(p, cw, ch)
+    nav.map_create(cw, ch, 1); nav.map_upload_layer(0, cost); nav.map_build_nav(0)
+    rng = np.random.default_rng(8181)
+    for _ in range(40):
+        x, z, r = float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)), float(rng.uniform(2, 9))
+        nav.blockers_incref(x, z, r, 0, 0)
+    nav.map_commit()
+    blk, liid = nav.blockers(0), nav.local_islands(0)
+    om = pforacle.OracleMap(cw, ch, cost, blk, liid)
+    reqs = []
+    for chunk in range(cw * ch):
+        for r_, c_ in np.argwhere((cost[chunk] != 255) & (blk[chunk] > 0))[::23][:6]:       # blocked, passable by cost
+            td = (chunk // cw, chunk % cw, int(r_), int(c_))
+            reqs.append(capi.los_req((td[0], td[1]), td))
+    assert len(reqs) >= 12
+    reqs = np.concatenate(reqs)
+    for variant in (1, 0):
+        nav.set_los_variant(variant)
+        try:
+            got = nav.los_fields_create(reqs)
+        finally:
+            nav.set_los_variant(1)
+        exp = om.los_fields_create(reqs)
+        bad = np.nonzero((got != exp).reshape(len(reqs), -1).any(axis=1))[0]
+        assert len(bad) == 0, (variant, bad[:10])
+    assert ((exp >> 1) & 1).sum() > 100

@@ -766,3 +766,29 @@ def test_product_does_not_touch_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     src = open(os.path.join(dp, f)).read()
                     assert "pforacle" not in src and "pfref" not in src and "oracle/" not in src, f
+
+
+def test_port_los_blocked_destination_tile_vs_ref(pforacle, pfref):
+    """pins the port on the reference's behaviour for a blocked destination tile (the NaN-slope line, field.c:463-517)"""
+    cw = ch = 3
+    p = cases.noise_map(cw, ch, 8181, 0.08)
+    ref = pfref.RefMap(cw, ch, p)
+    try:
+        rng = np.random.default_rng(8181)
+        for _ in range(40):
+            x, z, r = float(-rng.uniform(10, cw * 256 - 10)), float(rng.uniform(10, ch * 256 - 10)), float(rng.uniform(2, 9))
+            ref.blockers_incref(x, z, r)
+        ref.update()
+        cost, blk, liid = ref.cost_base(), ref.blockers(), ref.local_islands()
+        om = pforacle.OracleMap(cw, ch, cost, blk, liid)
+        n = 0
+        for chunk in range(cw * ch):
+            for r_, c_ in np.argwhere((cost[chunk] != 255) & (blk[chunk] > 0))[::23][:6]:
+                td = (chunk // cw, chunk % cw, int(r_), int(c_))
+                exp = ref.los((td[0], td[1]), td)
+                got = om.los_fields_create(capi.los_req((td[0], td[1]), td))[0]
+                assert (got == exp).all(), td
+                n += 1
+        assert n >= 12
+    finally:
+        ref.close()
