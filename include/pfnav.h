@@ -662,6 +662,11 @@ int  pfnav_pool_request_entity_fields(pfnav_ctx *ctx, int dest, int layer, int r
  * only the final choice after; 2 = always split. Results are identical in every mode. */
 int  pfnav_set_two_phase(pfnav_ctx *ctx, int mode);
 
+/* Test / tuning hook: cohesion pass (cohesion_force, movement.c:1653). 0 (default) = flocks of >= 20 000 members are summed
+ * through the position index with an exp(-0.12 d) cut-off at 230 wu and a per-entity fall-back to the full member list
+ * wherever the cut-off could matter beyond float rounding; 1 = always windowed; 2 = always the full member list. */
+int  pfnav_set_cohesion_mode(pfnav_ctx *ctx, int mode);
+
 /* flags for pfnav_agents_tick */
 #define PFNAV_TICK_VDES_FROM_POOL   (1u << 0)  /* compute vdes + has_dest_los on device (nav.c:3468, 4026) */
 

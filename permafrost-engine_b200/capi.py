@@ -99,6 +99,7 @@ SYMBOLS = [
     "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
     "pfnav_pool_request_goals_ex", "pfnav_blockers_batch", "pfnav_map_set_pos",
     "pfnav_agents_upload_formation", "pfnav_agents_upload_movestate_ext", "pfnav_pool_request_entity_fields",
+    "pfnav_set_cohesion_mode",
 ]
 
 _lib = None
@@ -728,6 +729,9 @@ class Nav:
         ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
         _chk(self.L.pfnav_pool_request_entity_fields(self.h, dest, layer, ref_layer, kind, _p(fp), len(fp), _p(ch), len(ch),
                                                      C.c_void_p(stream)))
+
+    def set_cohesion_mode(self, mode):
+        _chk(self.L.pfnav_set_cohesion_mode(self.h, mode))
 
     def agents_compute_updates(self, stream=0):
         _chk(self.L.pfnav_agents_compute_updates(self.h, C.c_void_p(stream)))

@@ -269,15 +269,37 @@ __global__ void k_gather_flock_pos(const pf_record *__restrict__ rec, const uint
     out[i] = make_float2(r.px, r.pz);
 }
 
-__global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent *__restrict__ agents,
-                           const uint32_t *__restrict__ flock_start, const uint32_t *__restrict__ flock_members,
-                           const float2 *__restrict__ member_pos, const uint32_t *__restrict__ work, int nwork,
-                           float scaled_max_force, float2 *__restrict__ out)
+// scaled integer coordinates + cell of the position index (bitmap_grid.h: 16-wu cells)
+__device__ __forceinline__ int32_t bg_scale(float x) { return __float2int_rn(x * 256.0f); }   // BG_SCALE_F
+__device__ __forceinline__ int cell_of(int32_t i, int32_t origin, int n)
+{
+    int c = (i - origin) >> 12;
+    return min(max(c, 0), n - 1);
+}
+
+// cohesion weight exp(-6 (|d| - 37.5) / 50) = 2^(|d| * (-0.12 log2 e) + 4.5 log2 e) on the SFU (rsqrt + ex2, flush-to-zero
+// forms: no denormal fix-up code; a flushed weight is < 1e-38 of a neighbour's)
+__device__ __forceinline__ float coh_weight(float dx, float dz)
+{
+    const float len2 = fmaxf(fmaf(dx, dx, dz * dz), 1e-30f);
+    float r, w;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(len2));
+    const float len = len2 * r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fmaf(len, -0.12f * 1.4426950408889634f, 4.5f * 1.4426950408889634f)));
+    return w;
+}
+
+// the whole member list of the flock (the definition; used for small flocks and as the fall-back of the windowed pass)
+__global__ void k_cohesion(const pf_record *__restrict__ rec, const int32_t *__restrict__ flock_of,
+                           const uint32_t *__restrict__ flock_start, const float2 *__restrict__ member_pos,
+                           const uint32_t *__restrict__ uids, const uint32_t *__restrict__ nuids_dev, int nuids_host,
+                           float scaled_max_force, float2 *__restrict__ out_by_uid)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwork) return;
-    const uint32_t uid = work[w];
-    const int fl = agents[uid].flock;
+    const int nu = nuids_dev ? (int)*nuids_dev : nuids_host;
+    if (w >= nu) return;
+    const uint32_t uid = uids[w];
+    const int fl = flock_of[uid];
     v2 ret = {0.0f, 0.0f};
     if (fl >= 0) {
         const pf_record self = rec[uid];
@@ -287,15 +309,13 @@ __global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent 
         // reproducible to the last bit anyway; what must hold is the 1e-4 velocity budget. The weight
         // exp(-6 (|d| - 37.5) / 50) is therefore evaluated with the SFU (rsqrt + ex2, relative error < 1e-6) and
         // the member itself is removed afterwards: its weight is exp(4.5) exactly as evaluated here for |d| = 0.
-        const float self_scale = __expf(4.5f);
+        const float self_scale = coh_weight(0.0f, 0.0f);
+#pragma unroll 4
         for (uint32_t k = b; k < e; k++) {
             const float2 p = member_pos[k];
-            const float dx = p.x - self.px, dz = p.y - self.pz;
-            const float len2 = dx * dx + dz * dz;
-            const float len = len2 * rsqrtf(fmaxf(len2, 1e-30f));
-            const float scale = __expf((len - 37.5f) * -0.12f);
-            com.x += p.x * scale;
-            com.z += p.y * scale;
+            const float scale = coh_weight(p.x - self.px, p.y - self.pz);
+            com.x = fmaf(p.x, scale, com.x);
+            com.z = fmaf(p.y, scale, com.z);
         }
         const uint32_t cnt = e - b - 1;
         if (cnt > 0) {
@@ -306,18 +326,106 @@ __global__ void k_cohesion(const pf_record *__restrict__ rec, const pfnav_agent 
             ret = v2_truncate(ret, scaled_max_force);
         }
     }
-    out[w] = make_float2(ret.x, ret.z);
+    out_by_uid[uid] = make_float2(ret.x, ret.z);
+}
+
+// cohesion_force (movement.c:1653) for big flocks. The weight of a member falls off as exp(-0.12 d): beyond COH_R = 230 wu
+// a member weighs < 1.1e-12 of one standing next to the entity, so the sum over the members within COH_R equals the full
+// sum to float precision WHENEVER the entity has company nearby. The pass walks the position index instead of the member
+// list: 128 consecutive entries of the index (spatial neighbours: the index is cell-major) share one window of cell rows,
+// the window's entries stream through shared memory in tiles, every thread accumulates its own entity's sum. An entity
+// whose window holds too little weight to make the cut-off harmless (sum < N * exp(4.5 - 0.12 * 230) * 1e7, i.e. the
+// dropped members could matter at the 1e-7 level) is handed to the full-list kernel instead, so the result never
+// depends on the cut-off by more than float rounding. Index coordinates are the 1/256-wu integers of the position index.
+#define COH_R 230.0f
+#define COH_THREADS 128
+__global__ void __launch_bounds__(COH_THREADS)
+k_cohesion_window(GridView g, const pf_record *__restrict__ rec, const int32_t *__restrict__ sfl,
+                  const uint32_t *__restrict__ flock_start, int n, uint32_t lo, uint32_t hi, float scaled_max_force,
+                  float2 *__restrict__ out_by_uid, uint32_t *__restrict__ fallback, uint32_t *__restrict__ nfallback)
+{
+    __shared__ float4 tile[COH_THREADS];       // {x, z, flock id bits, -}
+    __shared__ int bb[4];
+    const int tid = threadIdx.x;
+    const float thresh_unit = __expf(4.5f - 0.12f * COH_R) * 1e7f;
+    for (int base = blockIdx.x * COH_THREADS; base < n; base += gridDim.x * COH_THREADS) {
+        const int k = base + tid;
+        uint32_t uid = 0; int fl = -1; bool active = false;
+        float sx = 0.0f, sz = 0.0f, six_f = 0.0f, siy_f = 0.0f, self_w = 0.0f;
+        int mycx = 0, mycy = 0;
+        if (k < n) {
+            uid = g.id[k]; fl = sfl[k];
+            active = uid >= lo && uid < hi && fl >= 0;
+            mycx = cell_of(g.ix[k], g.origin_x, g.grid_w); mycy = cell_of(g.iy[k], g.origin_y, g.grid_h);
+            six_f = (float)g.ix[k] * (1.0f / 256.0f); siy_f = (float)g.iy[k] * (1.0f / 256.0f);
+        }
+        if (!__syncthreads_or(active)) continue;
+        if (tid == 0) { bb[0] = 0x7fffffff; bb[1] = -1; bb[2] = 0x7fffffff; bb[3] = -1; }
+        __syncthreads();
+        if (active) {
+            const pf_record self = rec[uid];
+            sx = self.px; sz = self.pz;
+            self_w = coh_weight(six_f - sx, siy_f - sz);       // what the loop below adds for the entity's own entry
+            atomicMin(&bb[0], mycx); atomicMax(&bb[1], mycx); atomicMin(&bb[2], mycy); atomicMax(&bb[3], mycy);
+        }
+        __syncthreads();
+        const int cy0 = bb[2], cy1 = bb[3];
+        float ax = 0.0f, az = 0.0f, wsum = 0.0f;
+        const int RC = (int)(COH_R / 16.0f) + 1;
+        // One window per grid row of the block's entities: 128 consecutive index entries lie in one row, or wrap from the
+        // end of one into the start of the next (then one window around both would span the whole map width).
+        for (int cyv = cy0; cyv <= cy1; cyv++) {
+            const bool mine = active && mycy == cyv;
+            __syncthreads();
+            if (tid == 0) { bb[0] = 0x7fffffff; bb[1] = -1; }
+            __syncthreads();
+            if (mine) { atomicMin(&bb[0], mycx); atomicMax(&bb[1], mycx); }
+            __syncthreads();
+            const int cx0 = bb[0], cx1 = bb[1];
+            if (cx1 < 0) continue;                                  // nobody in this row (uniform: read from shared memory)
+            for (int ry = max(cyv - RC, 0); ry <= min(cyv + RC, g.grid_h - 1); ry++) {
+                const int gap = max(abs(ry - cyv) - 1, 0);
+                const float dy = (float)gap * 16.0f;
+                if (dy > COH_R) continue;
+                const int nx = (int)(sqrtf(COH_R * COH_R - dy * dy) / 16.0f) + 1;
+                const int x0 = max(cx0 - nx, 0), x1 = min(cx1 + nx, g.grid_w - 1);
+                const uint32_t s0 = g.cell_start[ry * g.grid_w + x0], s1 = g.cell_start[ry * g.grid_w + x1 + 1];
+                for (uint32_t t0 = s0; t0 < s1; t0 += COH_THREADS) {
+                    const uint32_t e = t0 + tid;
+                    if (e < s1)
+                        tile[tid] = make_float4((float)g.ix[e] * (1.0f / 256.0f), (float)g.iy[e] * (1.0f / 256.0f), __int_as_float(sfl[e]), 0.0f);
+                    __syncthreads();
+                    const int nt = (int)min((uint32_t)COH_THREADS, s1 - t0);
+                    if (mine) {
+#pragma unroll 4
+                        for (int j = 0; j < nt; j++) {
+                            const float4 m = tile[j];
+                            const float scale = __float_as_int(m.z) == fl ? coh_weight(m.x - sx, m.y - sz) : 0.0f;
+                            ax = fmaf(m.x, scale, ax); az = fmaf(m.y, scale, az); wsum += scale;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (active) {
+            const uint32_t N = flock_start[fl + 1] - flock_start[fl];
+            if (N <= 1) out_by_uid[uid] = make_float2(0.0f, 0.0f);
+            else if (wsum - self_w >= (float)N * thresh_unit) {
+                // the entity's own index entry was summed too: take it out again (weight exp(4.5) at distance 0)
+                v2 com = {ax - six_f * self_w, az - siy_f * self_w};
+                com = v2_scale(com, 1.0f / (float)(N - 1));
+                v2 ret = v2_sub(com, v2{sx, sz});
+                ret = v2_truncate(ret, scaled_max_force);
+                out_by_uid[uid] = make_float2(ret.x, ret.z);
+            } else fallback[atomicAdd(nfallback, 1u)] = uid;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // K5: spatial index build (bitmap_grid.h: 16-wu cells, scaled int32 coordinates)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int32_t bg_scale(float x) { return __float2int_rn(x * 256.0f); }   // BG_SCALE_F
-__device__ __forceinline__ int cell_of(int32_t i, int32_t origin, int n)
-{
-    int c = (i - origin) >> 12;
-    return min(max(c, 0), n - 1);
-}
 
 __global__ void k_cell_count(const pf_record *__restrict__ rec, int n, GridView g, uint32_t *__restrict__ count)
 {
@@ -366,7 +474,7 @@ __global__ void k_cell_scatter(const pf_record *__restrict__ rec, int n, GridVie
 // 1477), then materialise the scaled coordinates next to them.
 __global__ void k_cell_sort(const pf_record *__restrict__ rec, GridView g, const uint32_t *__restrict__ start,
                             uint32_t *__restrict__ sid, int32_t *__restrict__ six, int32_t *__restrict__ siy,
-                            int ncells)
+                            int ncells, const int32_t *__restrict__ flock_of, int32_t *__restrict__ sfl)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
@@ -381,6 +489,7 @@ __global__ void k_cell_sort(const pf_record *__restrict__ rec, GridView g, const
         const pf_record r = rec[sid[i]];
         six[i] = bg_scale(r.px);
         siy[i] = bg_scale(r.pz);
+        sfl[i] = flock_of[sid[i]];
     }
 }
 
@@ -523,6 +632,9 @@ __device__ __forceinline__ void vo_edges(const cp_ent ent, const cp_ent nb, v2 &
 }
 
 #define VEL_WARPS_PER_CTA 4
+#ifndef VEL_MIN_CTAS
+#define VEL_MIN_CTAS 6          // 24 warps / SM: <= 80 registers (4 B of spill in the single-pass variant), 6 x 32 KB of shared memory
+#endif
 #define CQ_CAP 160
 struct VelSmem {
     cp_ent dyn[PFNAV_MAX_NEIGHBOURS];
@@ -541,8 +653,6 @@ struct VelSmem {
     uint8_t vo_rank[64];                  // obstacle -> removal time of its neighbour
     uint8_t vo_ord[64];                   // obstacles by decreasing removal time
     uint8_t cur[64];                      // working lists: dyn slots at [0, nd), stat slots at [32, 32 + ns)
-    uint8_t nalive[64];                   // obstacles alive after t removals
-    uint8_t pos_t[64][64];                // pos_t[t][obstacle] = its index among the alive obstacles after t removals (255 gone)
     float   ndist[64];                    // neighbour slot -> distance from the entity
     uint8_t cqd[CQ_CAP];                  // death time of the queued candidates
 };
@@ -818,7 +928,8 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
 // and the solve after t removals succeeds iff the preferred velocity (adm <= t) or some candidate (adm <= t < death) is
 // admissible. The first such t is T = min(adm); by minimality every candidate usable at T has adm == T exactly, and
 // compute_vnew (:368) picks the one nearest to the preferred velocity, first in ITS list order on ties -- the order of
-// the ray table after T swap-with-last deletions, which pos_t[] reproduces. Obstacles are tested in decreasing rank, so
+// the ray table after T swap-with-last deletions; a tie between two different points is therefore flagged and that (rare)
+// entity replays the loop literally. Obstacles are tested in decreasing rank, so
 // the first hit is the maximum and most points end at the nearest (widest) obstacles after one or two tests.
 // Cost: one solve instead of up to 63.
 // ------------------------------------------------------------------------------------------
@@ -832,30 +943,7 @@ __device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int
         s.ndist[k] = d; s.nb_rank[k] = 255; s.cur[k] = (uint8_t)k;
     }
     __syncwarp();
-    uint64_t hasvo = 0;             // neighbour slots that carry an obstacle (same_position neighbours do not, clearpath.c:123)
-    for (int v = 0; v < nvo; v++) hasvo |= 1ull << s.vo_src[v];
     int nd = ndyn, ns = nstat, t = 0, t_end = 0;
-    auto record = [&](int tt) {     // pos_t[tt][*]: list order = dyn part then stat part, obstacles only
-        for (int v = lane; v < 64; v += 32) s.pos_t[tt][v] = 255;
-        __syncwarp();
-        int before = 0;
-        for (int q0 = 0; q0 < nd + ns; q0 += 32) {
-            const int q = q0 + (int)lane;
-            int slot = -1;
-            if (q < nd + ns) slot = q < nd ? s.cur[q] : s.cur[32 + q - nd];
-            const bool hv = slot >= 0 && ((hasvo >> slot) & 1);
-            const uint32_t mk = __ballot_sync(FULL, hv);
-            if (hv) {
-                int v = 0;              // inverse of vo_src (<= 64 entries, rare path)
-                while (s.vo_src[v] != slot) v++;
-                s.pos_t[tt][v] = (uint8_t)(before + __popc(mk & ((1u << lane) - 1)));
-            }
-            before += __popc(mk);
-        }
-        if (lane == 0) s.nalive[tt] = (uint8_t)before;
-        __syncwarp();
-    };
-    record(0);
     while (true) {
         float bd = -__int_as_float(0x7f800000);
         int bp = 0x7fffffff;
@@ -881,7 +969,6 @@ __device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int
         if (bp < nd) nd--; else ns--;
         __syncwarp();
         if (!(nd > 0 && ns > 0)) { t_end = t; break; }
-        record(t);
     }
     for (int v = lane; v < nvo; v += 32) s.vo_rank[v] = s.nb_rank[s.vo_src[v]];
     __syncwarp();
@@ -895,24 +982,19 @@ __device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int
     return t_end;
 }
 
-// position of a candidate in the reference's candidate list of the solve after T removals (xpoints in (i, j) order
-// over the ray table of that time, then the projection points); id: ray_i * 128 + ray_j, or 0x8000 | ray for projections
-__device__ __forceinline__ int retry_seq(const VelSmem &s, int id, int T)
-{
-    const int nr = 2 * s.nalive[T];
-    if (id & 0x8000) { const int r = id & 0x7f; return nr * nr + 2 * s.pos_t[T][r >> 1] + (r & 1); }
-    const int i = id >> 7, j = id & 0x7f;
-    return (2 * s.pos_t[T][i >> 1] + (i & 1)) * nr + 2 * s.pos_t[T][j >> 1] + (j & 1);
-}
+struct retry_best { int T; float dist; int id; v2 p; int tie; };
 
-struct retry_best { int T; float dist; int id; v2 p; };
-
-__device__ __forceinline__ bool retry_better(const VelSmem &s, int T, float dist, int id, const retry_best &b)
+// (time, distance) order. Two DIFFERENT points at exactly the same time and distance would be ordered by their position in
+// the candidate list of the solve after T removals (compute_vnew keeps the first, clearpath.c:368) -- that list order
+// depends on the swap-with-last deletions done so far; instead of reproducing it the tie is flagged and the caller
+// replays the reference's loop literally (it practically never happens: identical points, e.g. xpoint(i, j) and
+// xpoint(j, i), are no tie -- either one gives the same velocity).
+__device__ __forceinline__ bool retry_better(int T, float dist, const v2 p, retry_best &b)
 {
     if (T != b.T) return T < b.T;
     if (dist != b.dist) return dist < b.dist;
-    if (b.id < 0) return true;
-    return retry_seq(s, id, T) < retry_seq(s, b.id, T);
+    if (b.id >= 0 && (p.x != b.p.x || p.z != b.p.z)) b.tie = 1;
+    return false;
 }
 
 // like drain_candidates, for the retry emulation: cqk holds the candidate id, cqd its death time
@@ -945,7 +1027,7 @@ __device__ __forceinline__ void drain_ranked(const VelSmem &s, int qn, int nvo, 
                 if (adm < mydeath && adm <= best.T) {
                     const v2 curr = v2_sub(myp, ent_pos);
                     const float len = v2_len(v2_sub(des_v, curr));
-                    if (retry_better(s, adm, len, myid, best)) { best.T = adm; best.dist = len; best.id = myid; best.p = curr; }
+                    if (retry_better(adm, len, curr, best)) { best.T = adm; best.dist = len; best.id = myid; best.p = curr; best.tie = 0; }
                 }
                 my = -1;
             }
@@ -954,9 +1036,11 @@ __device__ __forceinline__ void drain_ranked(const VelSmem &s, int qn, int nvo, 
 }
 
 // everything G_ClearPath_NewVelocity does after its first solve found nothing. The ray table of that solve is still in
-// shared memory (build_vos). Returns the velocity of the first successful later solve, or zero when the loop ends first.
-__device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat, int n_rays, uint32_t lane)
+// shared memory (build_vos). Returns the velocity of the first successful later solve, or zero when the loop ends first;
+// `exact` is cleared when an order-dependent tie was met (the caller then replays the loop literally).
+__device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int ndyn, int nstat, int n_rays, uint32_t lane, bool &exact)
 {
+    exact = true;
     const int nvo = n_rays >> 1;
     // with one of the two lists empty the loop condition fails right after the first removal (the common case in a crowd
     // where everybody moves): no second solve, the answer is zero
@@ -970,7 +1054,7 @@ __device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int 
         if (vo_contains(s, v, des_v_ws)) adm_des = max(adm_des, (int)s.vo_rank[v]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) adm_des = max(adm_des, __shfl_xor_sync(FULL, adm_des, off));
-    retry_best best; best.T = min(adm_des, t_end - 1); best.dist = __int_as_float(0x7f800000); best.id = -1; best.p = {0.0f, 0.0f};
+    retry_best best; best.T = min(adm_des, t_end - 1); best.dist = __int_as_float(0x7f800000); best.id = -1; best.p = {0.0f, 0.0f}; best.tie = 0;
     const int npairs = n_rays * n_rays;
     int qn = 0;
     auto flush = [&](bool last) {
@@ -982,7 +1066,7 @@ __device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int 
             int t = best.T;                                   // the warp-wide best time bounds what is still worth testing
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) t = min(t, __shfl_xor_sync(FULL, t, off));
-            if (t < best.T) { best.T = t; best.dist = __int_as_float(0x7f800000); best.id = -1; }
+            if (t < best.T) { best.T = t; best.dist = __int_as_float(0x7f800000); best.id = -1; best.tie = 0; }
         }
     };
     for (int base = 0; base < n_rays; base += 32) {            // projection points (compute_vdes_proj_points, :344)
@@ -1027,20 +1111,20 @@ __device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int 
     int T = best.T;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) T = min(T, __shfl_xor_sync(FULL, T, off));
-    if (best.T != T) { best.dist = __int_as_float(0x7f800000); best.id = -1; }
+    if (best.T != T) { best.dist = __int_as_float(0x7f800000); best.id = -1; best.tie = 0; }
     if (adm_des <= T && adm_des <= t_end - 1) return des_v;     // inside_pcr(des_v) is tested before any candidate (:602)
     float d = best.dist;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) d = fminf(d, __shfl_xor_sync(FULL, d, off));
     const bool mine = best.id >= 0 && best.dist == d;
-    if (!__any_sync(FULL, mine)) return v2{0.0f, 0.0f};          // no solve before the loop ends finds a point
-    int seq = mine ? retry_seq(s, best.id, T) : 0x7fffffff;
-    int smin = seq;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) smin = min(smin, __shfl_xor_sync(FULL, smin, off));
-    const int src = __ffs(__ballot_sync(FULL, mine && seq == smin)) - 1;
+    const uint32_t mm = __ballot_sync(FULL, mine);
+    if (!mm) return v2{0.0f, 0.0f};                              // no solve before the loop ends finds a point
+    const int src = __ffs(mm) - 1;
     v2 out;
     out.x = __shfl_sync(FULL, best.p.x, src); out.z = __shfl_sync(FULL, best.p.z, src);
+    // ties between different points, inside a lane or across lanes: list order would decide
+    const bool differs = mine && (best.tie || best.p.x != out.x || best.p.z != out.z);
+    if (__any_sync(FULL, differs)) exact = false;
     return out;
 }
 
@@ -1223,7 +1307,7 @@ struct TickParams {
 // ------------------------------------------------------------------------------------------
 // MODE 0: the whole update in one pass. MODE 1 / 2: phase A / phase B of the two-phase scheme above.
 template <int MODE>
-__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, VEL_MIN_CTAS)
 k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__restrict__ agents,
                  const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
@@ -1345,7 +1429,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             arrive = v2_truncate(v2_sub(desired, velocity), tp.scaled_max_force);
             }
             // ---- cohesion: the flock-wide pre-pass, or the formation's own forces (fstate, movement.c:215-225) ----
-            const float2 ch = cohesion_in[w];
+            const float2 ch = cohesion_in[uid];
             const v2 cohesion = (cell_mode || form_mode) ? (has_form ? v2{fin.cohesion[0], fin.cohesion[1]} : v2{0.0f, 0.0f}) : v2{ch.x, ch.y};
             const v2 alignment = has_form ? v2{fin.align[0], fin.align[1]} : v2{0.0f, 0.0f};
 
@@ -1479,7 +1563,21 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
                 found = clearpath_finish(s, self, vpref, ndyn, nstat, lane, prep[w].xp, (int)prep[w].nx, r, n_rays);
             else
                 found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r, n_rays);
-            new_vel = found ? r : clearpath_retry(s, self, vpref, ndyn, nstat, n_rays, lane);
+            if (found) new_vel = r;
+            else {
+                bool exact;
+                new_vel = clearpath_retry(s, self, vpref, ndyn, nstat, n_rays, lane, exact);
+                if (!exact) {
+                    // replay the reference's loop literally (clearpath.c:702-713)
+                    new_vel = {0.0f, 0.0f};
+                    while (true) {
+                        remove_furthest(s, self.pos, ndyn, nstat, lane);
+                        if (!(ndyn > 0 && nstat > 0)) break;
+                        int nr2;
+                        if (clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r, nr2)) { new_vel = r; break; }
+                    }
+                }
+            }
         }
         new_vel = v2_truncate(new_vel, a.max_speed / hzf);      // movement.c:3464
         if (lane == 0) {
@@ -1508,7 +1606,8 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_agents); cudaFree(ctx->d_records); cudaFree(ctx->d_flocks);
     cudaFree(ctx->d_flock_start); cudaFree(ctx->d_flock_members); cudaFree(ctx->d_cohesion);
     cudaFree(ctx->d_cell_count); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_cell_fill);
-    cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id);
+    cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id); cudaFree(ctx->d_sorted_flock);
+    cudaFree(ctx->d_coh_fallback); ctx->d_sorted_flock = nullptr; ctx->d_coh_fallback = nullptr; ctx->cap_coh = 0;
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
     cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep); cudaFree(ctx->d_flock_of); cudaFree(ctx->d_facts);
@@ -1639,7 +1738,7 @@ static int build_index(pfnav_ctx *ctx, cudaStream_t st)
         k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_records, n, g, ctx->d_cell_start, ctx->d_cell_fill,
                                                        ctx->d_sorted_id);
         k_cell_sort<<<(ncells + 127) / 128, 128, 0, st>>>(ctx->d_records, g, ctx->d_cell_start, ctx->d_sorted_id,
-                                                         ctx->d_sorted_ix, ctx->d_sorted_iy, ncells);
+                                                         ctx->d_sorted_ix, ctx->d_sorted_iy, ncells, ctx->d_flock_of, ctx->d_sorted_flock);
         ctx->launches += 4;
     } else {
         PF_CUDA(cudaMemsetAsync(ctx->d_cell_start, 0, (size_t)(ncells + 1) * 4, st));
@@ -1700,6 +1799,7 @@ static int rebuild_flock_members(pfnav_ctx *ctx, cudaStream_t st)
     PF_CUDA(cudaMemcpyAsync(ctx->d_flock_start, fstart.data(), (nflocks + 1) * 4, cudaMemcpyHostToDevice, st));
     if (n) PF_CUDA(cudaMemcpyAsync(ctx->d_flock_members, members.data(), n * 4, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaStreamSynchronize(st));      // host vectors go out of scope
+    ctx->h_flock_start = fstart;
     return 0;
 }
 
@@ -1733,6 +1833,7 @@ static int agents_upload_impl(pfnav_ctx *ctx, const pfnav_agent *agents, size_t 
         if ((rc = ensure(ctx->d_flock_of, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_ix, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_iy, cap, n))) return rc; cap = 0;
+        if ((rc = ensure(ctx->d_sorted_flock, cap, n))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_sorted_id, cap, n))) return rc;
         ctx->cap_agents = n;
     }
@@ -1879,7 +1980,6 @@ extern "C" int pfnav_agents_set_work(pfnav_ctx *ctx, const uint32_t *uids, size_
         if ((rc = ensure(ctx->d_vel_out, cap, nwork))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_vpref_out, cap, nwork))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_vdes_out, cap, nwork))) return rc; cap = 0;
-        if ((rc = ensure(ctx->d_cohesion, cap, nwork))) return rc; cap = 0;
         if ((rc = ensure(ctx->d_los_out, cap, nwork))) return rc;
         ctx->cap_work = nwork;
     }
@@ -1923,11 +2023,36 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         PF_CUDA(cudaMalloc(&ctx->d_member_pos, std::max<size_t>(ctx->n_agents, 1) * sizeof(float2)));
         ctx->cap_member_pos = ctx->n_agents;
     }
+    if (ctx->cap_coh < ctx->n_agents) {
+        cudaFree(ctx->d_cohesion); cudaFree(ctx->d_coh_fallback); ctx->d_cohesion = nullptr; ctx->d_coh_fallback = nullptr; ctx->cap_coh = 0;
+        PF_CUDA(cudaMalloc(&ctx->d_cohesion, std::max<size_t>(ctx->n_agents, 1) * sizeof(float2)));
+        PF_CUDA(cudaMalloc(&ctx->d_coh_fallback, (std::max<size_t>(ctx->n_agents, 1) + 4) * sizeof(uint32_t)));
+        ctx->cap_coh = ctx->n_agents;
+    }
     k_gather_flock_pos<<<((int)ctx->n_agents + 255) / 256, 256, 0, st>>>(ctx->d_records, ctx->d_flock_members, (int)ctx->n_agents,
                                                                         ctx->d_member_pos);
-    k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_agents, ctx->d_flock_start, ctx->d_flock_members,
-                                                   ctx->d_member_pos, ctx->d_work, nwork, tp.scaled_max_force, ctx->d_cohesion);
-    ctx->launches++;
+    // big flocks: windowed pass over the position index + full-list fall-back for entities without company; small
+    // populations: the full member list directly (the window would cover the whole flock anyway)
+    size_t biggest = 0;
+    for (size_t f = 0; f + 1 < ctx->h_flock_start.size(); f++) biggest = std::max<size_t>(biggest, ctx->h_flock_start[f + 1] - ctx->h_flock_start[f]);
+    const bool windowed = ctx->cohesion_mode == 1 || (ctx->cohesion_mode == 0 && biggest >= 20000);
+    if (windowed) {
+        uint32_t *d_nfb = ctx->d_coh_fallback + ctx->n_agents;
+        PF_CUDA(cudaMemsetAsync(d_nfb, 0, 4, st));
+        const int nblk = ((int)ctx->n_agents + COH_THREADS - 1) / COH_THREADS;     // one 128-entry run each: the hardware scheduler balances them
+        k_cohesion_window<<<nblk, COH_THREADS, 0, st>>>(grid_of(ctx), ctx->d_records, ctx->d_sorted_flock, ctx->d_flock_start,
+                                                        (int)ctx->n_agents, (uint32_t)ctx->shard_lo, (uint32_t)ctx->shard_hi,
+                                                        tp.scaled_max_force, ctx->d_cohesion, ctx->d_coh_fallback, d_nfb);
+        // fall-back entities: the grid is sized for the worst case, the kernel reads the count on the device
+        const int nown = (int)(ctx->shard_hi - ctx->shard_lo);
+        k_cohesion<<<(nown + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_flock_of, ctx->d_flock_start, ctx->d_member_pos,
+                                                      ctx->d_coh_fallback, d_nfb, 0, tp.scaled_max_force, ctx->d_cohesion);
+        ctx->launches += 2;
+    } else {
+        k_cohesion<<<(nwork + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_flock_of, ctx->d_flock_start, ctx->d_member_pos,
+                                                       ctx->d_work, nullptr, nwork, tp.scaled_max_force, ctx->d_cohesion);
+        ctx->launches++;
+    }
     }
     const int ctas = std::min((nwork + VEL_WARPS_PER_CTA - 1) / VEL_WARPS_PER_CTA, ctx->sm_count * 8 * 4);
     if (ctx->any_garrisoned && ctx->nb_scratch_warps < (size_t)ctas * VEL_WARPS_PER_CTA) {
@@ -2925,6 +3050,15 @@ extern "C" int pfnav_pool_repair(pfnav_ctx *ctx, int *out_nrequests, int *out_nr
 
 // Test / tuning hook: 0 = always the single-pass velocity kernel, 1 (default) = split it around the field join
 // whenever LOS chains are still in flight, 2 = always split (exercises the two-phase path without fields).
+// Test / tuning hook: cohesion pass, 0 = automatic (windowed for flocks of >= 20 000), 1 = always windowed, 2 = always the
+// full member list. Results agree to float rounding (the windowed pass falls back per entity where they would not).
+extern "C" int pfnav_set_cohesion_mode(pfnav_ctx *ctx, int mode)
+{
+    PF_ARG(ctx && mode >= 0 && mode <= 2, "mode");
+    ctx->cohesion_mode = mode;
+    return PFNAV_OK;
+}
+
 extern "C" int pfnav_set_two_phase(pfnav_ctx *ctx, int mode)
 {
     PF_ARG(ctx && mode >= 0 && (mode & 3) <= 2, "mode");

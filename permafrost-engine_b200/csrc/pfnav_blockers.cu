@@ -25,41 +25,70 @@ namespace {
 
 struct td { int chunk_r, chunk_c, tile_r, tile_c; };
 struct v2f { float x, z; };
+struct geom { float map_x, map_z; int chunk_w, chunk_h; };
 #define EPS_COLL (1.0f / 1024.0f)          // collision.c:64
+#define HD __host__ __device__ __forceinline__
 
-static bool point_inside_rect(v2f p, v2f a, v2f b, v2f d)
+// The reference's float / double expressions, one rounding per operation: the device compiler must not contract
+// a*b+c into an FMA (the host compiler does not: x86-64 baseline has none), so every operation is spelled out.
+#ifdef __CUDA_ARCH__
+HD float  f_add(float a, float b) { return __fadd_rn(a, b); }
+HD float  f_sub(float a, float b) { return __fsub_rn(a, b); }
+HD float  f_mul(float a, float b) { return __fmul_rn(a, b); }
+HD float  f_div(float a, float b) { return __fdiv_rn(a, b); }
+HD double d_add(double a, double b) { return __dadd_rn(a, b); }
+HD double d_sub(double a, double b) { return __dsub_rn(a, b); }
+HD double d_mul(double a, double b) { return __dmul_rn(a, b); }
+HD double d_div(double a, double b) { return __ddiv_rn(a, b); }
+HD double d_sqrt(double a) { return __dsqrt_rn(a); }
+#else
+HD float  f_add(float a, float b) { return a + b; }
+HD float  f_sub(float a, float b) { return a - b; }
+HD float  f_mul(float a, float b) { return a * b; }
+HD float  f_div(float a, float b) { return a / b; }
+HD double d_add(double a, double b) { return a + b; }
+HD double d_sub(double a, double b) { return a - b; }
+HD double d_mul(double a, double b) { return a * b; }
+HD double d_div(double a, double b) { return a / b; }
+HD double d_sqrt(double a) { return sqrt(a); }
+#endif
+HD double d_sq(float a) { return d_mul((double)a, (double)a); }     // pow(a, 2)
+HD float  f_dot(v2f a, v2f b) { return f_add(f_mul(a.x, b.x), f_mul(a.z, b.z)); }
+
+HD bool point_inside_rect(v2f p, v2f a, v2f b, v2f d)
 {
-    const v2f ap = {p.x - a.x, p.z - a.z}, ab = {b.x - a.x, b.z - a.z}, ad = {d.x - a.x, d.z - a.z};
-    const float ap_ab = ap.x * ab.x + ap.z * ab.z, ap_ad = ap.x * ad.x + ap.z * ad.z;
-    return (ap_ab >= 0.0f && ap_ab <= ab.x * ab.x + ab.z * ab.z) && (ap_ad >= 0.0f && ap_ad <= ad.x * ad.x + ad.z * ad.z);
+    const v2f ap = {f_sub(p.x, a.x), f_sub(p.z, a.z)}, ab = {f_sub(b.x, a.x), f_sub(b.z, a.z)}, ad = {f_sub(d.x, a.x), f_sub(d.z, a.z)};
+    const float ap_ab = f_dot(ap, ab), ap_ad = f_dot(ap, ad);
+    return (ap_ab >= 0.0f && ap_ab <= f_dot(ab, ab)) && (ap_ad >= 0.0f && ap_ad <= f_dot(ad, ad));
 }
 
-static bool line_circle(float ax, float az, float bx, float bz, v2f c, float radius)
+HD bool line_circle(float ax, float az, float bx, float bz, v2f c, float radius)
 {
-    const float dx = bx - ax, dz = bz - az;
-    const float A = pow(dx, 2) + pow(dz, 2);
-    const float B = 2 * (dx * (ax - c.x) + dz * (az - c.z));
-    const float C = pow(ax - c.x, 2) + pow(az - c.z, 2) - pow(radius, 2);
-    const float det = pow(B, 2) - (4 * A * C);
+    const float dx = f_sub(bx, ax), dz = f_sub(bz, az);
+    const float A = (float)d_add(d_sq(dx), d_sq(dz));
+    const float B = f_mul(2.0f, f_add(f_mul(dx, f_sub(ax, c.x)), f_mul(dz, f_sub(az, c.z))));
+    const float C = (float)d_sub(d_add(d_sq(f_sub(ax, c.x)), d_sq(f_sub(az, c.z))), d_sq(radius));
+    const float det = (float)d_sub(d_sq(B), (double)f_mul(f_mul(4.0f, A), C));
     float t;
     if (det < 0.0f || A < EPS_COLL) return false;
-    else if (det == 0.0f) t = -B / (2 * A);
+    else if (det == 0.0f) t = f_div(-B, f_mul(2.0f, A));
     else {
-        const float t1 = (-B + sqrt(det)) / (2 * A), t2 = (-B - sqrt(det)) / (2 * A);
-        t = std::min(t1, t2);
+        const double root = d_sqrt((double)det), two_a = (double)f_mul(2.0f, A);
+        const float t1 = (float)d_div(d_add((double)(-B), root), two_a), t2 = (float)d_div(d_sub((double)(-B), root), two_a);
+        t = t1 < t2 ? t1 : t2;
     }
     if (t < 0.0f || t > 1.0f) return false;
     return true;
 }
 
 // C_CircleRectIntersection (collision.c:997); rect = {x, z, width, height}, x decreasing with the column
-static bool circle_rect(v2f center, float radius, float rx, float rz, float w, float h)
+HD bool circle_rect(v2f center, float radius, float rx, float rz, float w, float h)
 {
-    const v2f corners[4] = {{rx - w, rz}, {rx, rz}, {rx, rz + h}, {rx - w, rz + h}};
+    const v2f corners[4] = {{f_sub(rx, w), rz}, {rx, rz}, {rx, f_add(rz, h)}, {f_sub(rx, w), f_add(rz, h)}};
     if (point_inside_rect(center, corners[0], corners[1], corners[3])) return true;
     for (int i = 0; i < 4; i++) {
-        const float ddx = corners[i].x - center.x, ddz = corners[i].z - center.z;
-        if ((float)sqrt(ddx * ddx + ddz * ddz) <= radius) return true;
+        const float ddx = f_sub(corners[i].x, center.x), ddz = f_sub(corners[i].z, center.z);
+        if ((float)d_sqrt((double)f_add(f_mul(ddx, ddx), f_mul(ddz, ddz))) <= radius) return true;
     }
     for (int i = 0; i < 4; i++) {
         const v2f a = corners[i], b = corners[(i + 1) & 3];
@@ -68,39 +97,49 @@ static bool circle_rect(v2f center, float radius, float rx, float rz, float w, f
     return false;
 }
 
+HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 // M_Tile_DescForPoint2D with the nav resolution (tile.c:547)
-static bool desc_for_point(const pfnav_ctx *ctx, float px, float pz, td *out)
+HD bool desc_for_point(const geom &g, float px, float pz, td *out)
 {
-    const float width = (float)(ctx->chunk_w * 256), height = (float)(ctx->chunk_h * 256);
-    if (px > ctx->map_x || px < ctx->map_x - width) return false;
-    if (pz < ctx->map_z || pz > ctx->map_z + height) return false;
-    int chunk_r = (int)(fabs(ctx->map_z - pz) / 256.0f), chunk_c = (int)(fabs(ctx->map_x - px) / 256.0f);
-    chunk_r = std::min(std::max(chunk_r, 0), ctx->chunk_h - 1);
-    chunk_c = std::min(std::max(chunk_c, 0), ctx->chunk_w - 1);
-    const float bx = ctx->map_x - (chunk_c * 256.0f), bz = ctx->map_z + (chunk_r * 256.0f);
-    int tile_r = (int)(fabs(bz - pz) / 4), tile_c = (int)(fabs(bx - px) / 4);
+    const float width = (float)(g.chunk_w * 256), height = (float)(g.chunk_h * 256);
+    if (px > g.map_x || px < f_sub(g.map_x, width)) return false;
+    if (pz < g.map_z || pz > f_add(g.map_z, height)) return false;
+    int chunk_r = (int)(fabsf(f_sub(g.map_z, pz)) / 256.0f), chunk_c = (int)(fabsf(f_sub(g.map_x, px)) / 256.0f);
+    chunk_r = clampi(chunk_r, 0, g.chunk_h - 1);
+    chunk_c = clampi(chunk_c, 0, g.chunk_w - 1);
+    const float bx = f_sub(g.map_x, chunk_c * 256.0f), bz = f_add(g.map_z, chunk_r * 256.0f);
+    const int tile_r = (int)(fabsf(f_sub(bz, pz)) / 4.0f), tile_c = (int)(fabsf(f_sub(bx, px)) / 4.0f);
     out->chunk_r = chunk_r; out->chunk_c = chunk_c;
-    out->tile_r = std::min(std::max(tile_r, 0), 63); out->tile_c = std::min(std::max(tile_c, 0), 63);
+    out->tile_r = clampi(tile_r, 0, 63); out->tile_c = clampi(tile_c, 0, 63);
     return true;
 }
+
+// M_Tile_Bounds (tile.c:356) of the nav tile (ar, ac) + the circle test of M_Tile_AllUnderCircle (tile.c:687)
+HD bool tile_under_circle(const geom &g, int ar, int ac, v2f c, float radius)
+{
+    const float bx = f_sub(f_sub(g.map_x, (float)((ac / 64) * 256)), (float)((ac % 64) * 4));
+    const float bz = f_add(f_add(g.map_z, (float)((ar / 64) * 256)), (float)((ar % 64) * 4));
+    return circle_rect(c, radius, bx, bz, 4.0f, 4.0f);
+}
+
+static geom geom_of(const pfnav_ctx *ctx) { return geom{ctx->map_x, ctx->map_z, ctx->chunk_w, ctx->chunk_h}; }
+static bool desc_for_point(const pfnav_ctx *ctx, float px, float pz, td *out) { return desc_for_point(geom_of(ctx), px, pz, out); }
 
 // M_Tile_AllUnderCircle (tile.c:687)
 static size_t tiles_under_circle(const pfnav_ctx *ctx, v2f c, float radius, td *out, size_t maxout)
 {
+    const geom g = geom_of(ctx);
     td tile;
-    if (!desc_for_point(ctx, c.x, c.z, &tile)) return 0;
+    if (!desc_for_point(g, c.x, c.z, &tile)) return 0;
     const int ntiles = (int)ceil(radius / 4);
     size_t ret = 0;
     for (int dr = -ntiles; dr <= ntiles; dr++)
         for (int dc = -ntiles; dc <= ntiles; dc++) {
             const int ar = tile.chunk_r * 64 + tile.tile_r + dr, ac = tile.chunk_c * 64 + tile.tile_c + dc;
             if (ar < 0 || ar >= ctx->chunk_h * 64 || ac < 0 || ac >= ctx->chunk_w * 64) continue;
-            const td cur = {ar / 64, ac / 64, ar % 64, ac % 64};
-            // M_Tile_Bounds (tile.c:356)
-            const float bx = (ctx->map_x - (float)(cur.chunk_c * 256)) - (float)(cur.tile_c * 4);
-            const float bz = (ctx->map_z + (float)(cur.chunk_r * 256)) + (float)(cur.tile_r * 4);
-            if (!circle_rect(c, radius, bx, bz, 4.0f, 4.0f)) continue;
-            out[ret++] = cur;
+            if (!tile_under_circle(g, ar, ac, c, radius)) continue;
+            out[ret++] = {ar / 64, ac / 64, ar % 64, ac % 64};
             if (ret == maxout) return ret;
         }
     return ret;
@@ -219,10 +258,358 @@ static size_t tiles_contour(const pfnav_ctx *ctx, size_t ntds, const td *tds, td
 
 // dirty (layer, chunk) sets live in the context: pfnav_ctx::dirty (occupancy changed), ::fdirty (faction mask changed)
 
-// n_update_blockers (nav.c:1017) on the host mirror; layers the context does not hold are skipped
+// ------------------------------------------------------------------------------------------
+// Device side. On a context with a device the refcounts live in HBM: blocker operations are queued by the
+// entry points and applied by pfnav_map_commit (or the first read-back) in three launches --
+//   k_blockers_circles  one warp per circle: the tiles under it and its three contour rings as 31 x 31 bit rows,
+//                       counted into d_blk (u16) / d_fac (u8 per faction) with word-wide compare-and-swap;
+//   k_blockers_tiles    the same counting for tile lists rasterised on the host (building footprints, circles
+//                       wider than the bit window);
+//   k_chunks_finish     one CTA per touched (layer, chunk): faction masks from the counts, and -- when the set of
+//                       passable tiles changed -- the local islands (union-find in shared memory, islands numbered
+//                       by their first tile in row-major order exactly like the reference's flood fill nav.c:1213);
+// then the touched chunks come back in one copy to refresh the host mirrors the route planner reads.
+// "Dirty" here means the chunk's passable set changed between two commits; the reference marks a chunk on every
+// 0 <-> non-zero transition of a single count (nav.c:1038), which also fires for an obstacle that leaves and
+// re-enters a tile inside one tick. Both recompute identical islands / fields; ours skips the no-op rebuilds.
+// ------------------------------------------------------------------------------------------
+struct tile_op { int32_t layer, ar, ac, faction, delta; };
+#define CIRCLE_MAX_NT 12                    // (2 * nt + 1) + 6 ring columns <= 31 bits
+
+struct blk_state {
+    std::vector<pfnav_blocker_op> circles;
+    std::vector<tile_op> tiles;
+    uint8_t *d_fac = nullptr;               // [layer][15][H64][W64] u8, allocated with the first faction-tagged op
+    uint8_t *d_touched = nullptr, *d_ftouched = nullptr, *d_res = nullptr;      // [nlayers * chunks]
+    int nslots = 0;
+    void *d_ops = nullptr; size_t ops_bytes = 0;
+    void *d_out = nullptr; size_t out_bytes = 0;
+    uint64_t applied_ops = 0;
+};
+static blk_state *state_of(pfnav_ctx *ctx, bool create)
+{
+    if (!ctx->blk_state && create) ctx->blk_state = new blk_state();
+    return (blk_state *)ctx->blk_state;
+}
+
+struct apply_args {
+    geom g; int nlayers, W64, H64;
+    uint16_t *blk; uint8_t *fac; uint8_t *touched, *ftouched;
+};
+
+__device__ __forceinline__ void atomic_add_u16(uint16_t *p, int d)
+{
+    unsigned *w = (unsigned *)((uintptr_t)p & ~(uintptr_t)3);
+    const int sh = ((uintptr_t)p & 2) ? 16 : 0;
+    unsigned old = *w, assumed;
+    do {
+        assumed = old;
+        const unsigned v = (((assumed >> sh) & 0xFFFFu) + (unsigned)d) & 0xFFFFu;
+        old = atomicCAS(w, assumed, (assumed & ~(0xFFFFu << sh)) | (v << sh));
+    } while (old != assumed);
+}
+__device__ __forceinline__ void atomic_add_u8(uint8_t *p, int d)
+{
+    unsigned *w = (unsigned *)((uintptr_t)p & ~(uintptr_t)3);
+    const int sh = (int)((uintptr_t)p & 3) * 8;
+    unsigned old = *w, assumed;
+    do {
+        assumed = old;
+        const unsigned v = (((assumed >> sh) & 0xFFu) + (unsigned)d) & 0xFFu;
+        old = atomicCAS(w, assumed, (assumed & ~(0xFFu << sh)) | (v << sh));
+    } while (old != assumed);
+}
+
+// n_update_blockers (nav.c:1017) for one tile: `times` applications of `delta` at once
+__device__ __forceinline__ void apply_tile(const apply_args &a, int layer, int ar, int ac, int faction, int d)
+{
+    const size_t ltiles = (size_t)a.W64 * a.H64, t = (size_t)ar * a.W64 + ac;
+    atomic_add_u16(a.blk + ltiles * layer + t, d);
+    const int slot = layer * (a.g.chunk_w * a.g.chunk_h) + (ar >> 6) * a.g.chunk_w + (ac >> 6);
+    a.touched[slot] = 1;
+    if (faction >= 0 && faction < 15) {
+        atomic_add_u8(a.fac + ltiles * 15 * layer + ltiles * faction + t, d);
+        a.ftouched[slot] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_blockers_circles(const pfnav_blocker_op *__restrict__ ops, int nops, apply_args a)
+{
+    __shared__ unsigned rows[4][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int op = blockIdx.x * 4 + w;
+    if (op >= nops) return;
+    const pfnav_blocker_op o = ops[op];
+    const v2f c = {o.x, o.z};
+    td ct;
+    if (!desc_for_point(a.g, o.x, o.z, &ct)) return;           // M_Tile_AllUnderCircle returns 0 tiles (tile.c:693)
+    const int nt = (int)ceil(o.range / 4);
+    const int side = 2 * nt + 1, win = side + 6;
+    const int r0 = ct.chunk_r * 64 + ct.tile_r - nt - 3, c0 = ct.chunk_c * 64 + ct.tile_c - nt - 3;
+    rows[w][lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < side * side; i += 32) {
+        const int dr = i / side, dc = i - dr * side;
+        const int ar = r0 + 3 + dr, ac = c0 + 3 + dc;
+        if (ar < 0 || ar >= a.H64 || ac < 0 || ac >= a.W64) continue;
+        if (tile_under_circle(a.g, ar, ac, c, o.range)) atomicOr(&rows[w][dr + 3], 1u << (dc + 3));
+    }
+    __syncwarp();
+    // bit rows: lane = window row, bit = window column
+    const int lo = max(0, -c0), hi = min(win, a.W64 - c0);
+    const unsigned colmask = hi > lo ? (((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+    const int myr = r0 + lane;
+    const unsigned inmap = (lane < win && myr >= 0 && myr < a.H64) ? colmask : 0u;
+    const unsigned s = rows[w][lane];
+    // M_Tile_Contour (tile.c:759): the in-map tiles 8-adjacent to the set and not in it
+    auto contour = [&](unsigned m) {
+        const unsigned h = m | (m << 1) | (m >> 1);
+        unsigned up = __shfl_up_sync(0xFFFFFFFFu, h, 1), dn = __shfl_down_sync(0xFFFFFFFFu, h, 1);
+        if (lane == 0) up = 0;
+        if (lane == 31) dn = 0;
+        return (h | up | dn) & ~m & inmap;
+    };
+    const unsigned o3 = contour(s), o5 = contour(o3), o7 = contour(o5);
+    const bool air = (o.flags & PFNAV_FLAG_AIR) != 0;
+    for (int layer = 0; layer < a.nlayers; layer++) {
+        const int grp = layer >> 2, k = layer & 3;
+        if (air ? grp != 2 : grp > 1) continue;                // nav.c:1051-1127: ground + water, or air
+        unsigned u = s | (k >= 1 ? o3 : 0u) | (k >= 2 ? o5 : 0u) | (k >= 3 ? o7 : 0u);
+        while (u) {
+            const int b = __ffs(u) - 1;
+            u &= u - 1;
+            const int times = (int)((s >> b) & 1u) + (k >= 1 ? (int)((o3 >> b) & 1u) : 0) + (k >= 2 ? (int)((o5 >> b) & 1u) : 0) +
+                              (k >= 3 ? (int)((o7 >> b) & 1u) : 0);
+            apply_tile(a, layer, myr, c0 + b, o.faction_id, o.delta * times);
+        }
+    }
+}
+
+__global__ void k_blockers_tiles(const tile_op *__restrict__ ops, int nops, apply_args a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nops) return;
+    const tile_op o = ops[i];
+    apply_tile(a, o.layer, o.ar, o.ac, o.faction, o.delta);
+}
+
+__device__ __forceinline__ int uf_find(volatile int *L, int x)
+{
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+__device__ __forceinline__ void uf_unite(int *L, int a, int b)
+{
+    while (true) {
+        a = uf_find(L, a); b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }          // link the larger root under the smaller one
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct finish_args {
+    int nlayers, chunk_w, chunk_h, W64, H64;
+    const uint8_t *cost; const uint16_t *blk; uint16_t *liid; const uint8_t *fac; uint16_t *fmask;
+    uint8_t *touched, *ftouched, *res;
+};
+
+__global__ void __launch_bounds__(256) k_chunks_finish(finish_args a)
+{
+    __shared__ int L[4096];
+    __shared__ uint16_t ids[4096];
+    __shared__ int warp_tot[8];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    const bool t = a.touched[slot] != 0, ft = a.ftouched[slot] != 0;
+    if (!t && !ft) { if (tid == 0) a.res[slot] = 0; return; }
+    const int chunks = a.chunk_w * a.chunk_h, layer = slot / chunks, chunk = slot - layer * chunks;
+    const int cr = chunk / a.chunk_w, cc = chunk - cr * a.chunk_w;
+    const size_t ltiles = (size_t)a.W64 * a.H64;
+    const size_t base = (size_t)cr * 64 * a.W64 + cc * 64;
+    int changed = 0, fchanged = 0;
+    for (int i = tid; i < 4096; i += 256) {
+        const size_t off = base + (size_t)(i >> 6) * a.W64 + (i & 63);
+        const bool pass = a.cost[ltiles * layer + off] != 0xFF && a.blk[ltiles * layer + off] == 0;
+        changed |= (int)(pass != (a.liid[ltiles * layer + off] != 0xFFFF));
+        L[i] = pass ? i : -1;
+        if (ft && a.fac) {
+            unsigned m = 0;
+            for (int f = 0; f < 15; f++) m |= (unsigned)(a.fac[ltiles * 15 * layer + ltiles * f + off] != 0) << f;
+            if (a.fmask[ltiles * layer + off] != (uint16_t)m) { a.fmask[ltiles * layer + off] = (uint16_t)m; fchanged = 1; }
+        }
+    }
+    changed = __syncthreads_or(changed);
+    fchanged = __syncthreads_or(fchanged);
+    if (changed) {
+        // n_update_local_islands (nav.c:1213): 4-connected components of the passable tiles
+        for (int i = tid; i < 4096; i += 256) {
+            if (L[i] < 0) continue;
+            if ((i & 63) && L[i - 1] >= 0) uf_unite(L, i, i - 1);
+            if (i >= 64 && L[i - 64] >= 0) uf_unite(L, i, i - 64);
+        }
+        __syncthreads();
+        for (int i = tid; i < 4096; i += 256) if (L[i] >= 0) { const int r = uf_find(L, i); L[i] = r; }
+        __syncthreads();
+        // island ids count the roots (= the first tile of each island in scan order) from 1
+        int cnt = 0;
+        for (int j = 0; j < 16; j++) cnt += (int)(L[tid * 16 + j] == tid * 16 + j);
+        int incl = cnt;
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((tid & 31) >= d) incl += v; }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        int before = incl - cnt;
+        for (int wv = 0; wv < (tid >> 5); wv++) before += warp_tot[wv];
+        for (int j = 0; j < 16; j++) if (L[tid * 16 + j] == tid * 16 + j) ids[tid * 16 + j] = (uint16_t)(++before);
+        __syncthreads();
+        for (int i = tid; i < 4096; i += 256) {
+            const size_t off = base + (size_t)(i >> 6) * a.W64 + (i & 63);
+            a.liid[ltiles * layer + off] = L[i] >= 0 ? ids[L[i]] : (uint16_t)0xFFFF;
+        }
+    }
+    if (tid == 0) {
+        a.res[slot] = (uint8_t)((t ? 1 : 0) | (changed ? 2 : 0) | (fchanged ? 4 : 0));
+        a.touched[slot] = 0; a.ftouched[slot] = 0;
+    }
+}
+
+// the touched chunks, chunk-blocked, for the host mirrors: out[e] = {blk[4096], liid[4096]}
+__global__ void __launch_bounds__(256) k_chunks_gather(const int32_t *__restrict__ slots, int chunk_w, int chunk_h, int W64, int H64,
+                                                       const uint16_t *__restrict__ blk, const uint16_t *__restrict__ liid,
+                                                       uint16_t *__restrict__ out)
+{
+    const int slot = slots[blockIdx.x], chunks = chunk_w * chunk_h, layer = slot / chunks, chunk = slot - layer * chunks;
+    const int cr = chunk / chunk_w, cc = chunk - cr * chunk_w;
+    const size_t off0 = (size_t)W64 * H64 * layer + (size_t)cr * 64 * W64 + cc * 64;
+    uint16_t *o = out + (size_t)blockIdx.x * 8192;
+    for (int i = threadIdx.x; i < 4096; i += 256) {
+        const size_t off = off0 + (size_t)(i >> 6) * W64 + (i & 63);
+        o[i] = blk[off]; o[4096 + i] = liid[off];
+    }
+}
+
+static int ensure_buf(void **p, size_t *cap, size_t bytes)
+{
+    if (*cap >= bytes) return 0;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    PF_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return 0;
+}
+
+// d_fac of one layer from the host counts ([chunk][15][4096] -> [15][H64][W64])
+static int fac_push_layer(pfnav_ctx *ctx, blk_state *st, int layer)
+{
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    uint8_t *dst = st->d_fac + ltiles * 15 * layer;
+    if ((size_t)layer >= ctx->h_fac.size() || ctx->h_fac[layer].size() != ltiles * 15) {
+        PF_CUDA(cudaMemset(dst, 0, ltiles * 15));
+        return 0;
+    }
+    std::vector<uint8_t> img(ltiles * 15);
+    const uint8_t *src = ctx->h_fac[layer].data();
+    const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h;
+    for (size_t ch = 0; ch < chunks; ch++) {
+        const size_t cr = ch / ctx->chunk_w, cc = ch % ctx->chunk_w;
+        for (int f = 0; f < 15; f++)
+            for (int r = 0; r < 64; r++)
+                memcpy(img.data() + ltiles * f + (cr * 64 + r) * ctx->W64 + cc * 64, src + (ch * 15 + f) * 4096 + r * 64, 64);
+    }
+    PF_CUDA(cudaMemcpy(dst, img.data(), ltiles * 15, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Apply the queued operations on the device and bring the touched chunks' mirrors up to date; fills ctx->dirty
+// (passable set changed) and ctx->fdirty (a faction mask changed) for pfnav_map_commit.
+static int device_flush(pfnav_ctx *ctx)
+{
+    blk_state *st = state_of(ctx, false);
+    if (!st || ctx->device < 0 || (st->circles.empty() && st->tiles.empty())) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(pf_fields_sync(ctx));         // forked LOS chains still read the map that is about to change
+    // ticks / field launches on the context stream or on caller streams (all non-blocking, so not ordered against
+    // the default stream used below) may still read the grids
+    PF_CUDA(cudaDeviceSynchronize());
+    const int chunks = ctx->chunk_w * ctx->chunk_h, nslots = chunks * ctx->nlayers;
+    const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+    if (st->nslots != nslots) {
+        cudaFree(st->d_touched); st->d_touched = nullptr;
+        PF_CUDA(cudaMalloc(&st->d_touched, (size_t)nslots * 3));
+        PF_CUDA(cudaMemset(st->d_touched, 0, (size_t)nslots * 3));
+        st->d_ftouched = st->d_touched + nslots; st->d_res = st->d_touched + 2 * (size_t)nslots;
+        st->nslots = nslots;
+    }
+    bool need_fac = false;
+    for (const auto &o : st->circles) need_fac |= (o.faction_id >= 0 && o.faction_id < 15);
+    for (const auto &o : st->tiles) need_fac |= (o.faction >= 0 && o.faction < 15);
+    if (need_fac && !st->d_fac) {
+        PF_CUDA(cudaMalloc(&st->d_fac, ltiles * 15 * ctx->nlayers));
+        for (int l = 0; l < ctx->nlayers; l++) { int rc = fac_push_layer(ctx, st, l); if (rc) return rc; }
+    }
+    apply_args a;
+    a.g = geom_of(ctx); a.nlayers = ctx->nlayers; a.W64 = ctx->W64; a.H64 = ctx->H64;
+    a.blk = ctx->d_blk; a.fac = st->d_fac; a.touched = st->d_touched; a.ftouched = st->d_ftouched;
+    const size_t nc = st->circles.size(), ntl = st->tiles.size();
+    if (ensure_buf(&st->d_ops, &st->ops_bytes, std::max(nc * sizeof(pfnav_blocker_op), std::max(ntl * sizeof(tile_op), (size_t)nslots * 4))))
+        return PFNAV_ERR_CUDA;
+    if (nc) {
+        PF_CUDA(cudaMemcpy(st->d_ops, st->circles.data(), nc * sizeof(pfnav_blocker_op), cudaMemcpyHostToDevice));
+        k_blockers_circles<<<(unsigned)((nc + 3) / 4), 128>>>((const pfnav_blocker_op *)st->d_ops, (int)nc, a);
+        ctx->launches++;
+    }
+    if (ntl) {
+        PF_CUDA(cudaMemcpy(st->d_ops, st->tiles.data(), ntl * sizeof(tile_op), cudaMemcpyHostToDevice));   // after the circles kernel (same stream)
+        k_blockers_tiles<<<(unsigned)((ntl + 255) / 256), 256>>>((const tile_op *)st->d_ops, (int)ntl, a);
+        ctx->launches++;
+    }
+    st->applied_ops += nc + ntl;
+    st->circles.clear(); st->tiles.clear();
+    finish_args f;
+    f.nlayers = ctx->nlayers; f.chunk_w = ctx->chunk_w; f.chunk_h = ctx->chunk_h; f.W64 = ctx->W64; f.H64 = ctx->H64;
+    f.cost = ctx->d_cost; f.blk = ctx->d_blk; f.liid = ctx->d_liid; f.fac = st->d_fac; f.fmask = ctx->d_fmask;
+    f.touched = st->d_touched; f.ftouched = st->d_ftouched; f.res = st->d_res;
+    k_chunks_finish<<<nslots, 256>>>(f);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    std::vector<uint8_t> res(nslots);
+    PF_CUDA(cudaMemcpy(res.data(), st->d_res, nslots, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> slots;
+    for (int s = 0; s < nslots; s++) {
+        if (res[s] & 1) slots.push_back(s);
+        if (res[s] & 2) ctx->dirty.insert({s / chunks, s % chunks});
+        if (res[s] & 4) ctx->fdirty.insert({s / chunks, s % chunks});
+    }
+    if (!slots.empty()) {
+        if (ensure_buf(&st->d_out, &st->out_bytes, slots.size() * 8192 * sizeof(uint16_t))) return PFNAV_ERR_CUDA;
+        PF_CUDA(cudaMemcpy(st->d_ops, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+        k_chunks_gather<<<(unsigned)slots.size(), 256>>>((const int32_t *)st->d_ops, ctx->chunk_w, ctx->chunk_h, ctx->W64, ctx->H64,
+                                                         ctx->d_blk, ctx->d_liid, (uint16_t *)st->d_out);
+        ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        std::vector<uint16_t> out(slots.size() * 8192);
+        PF_CUDA(cudaMemcpy(out.data(), st->d_out, out.size() * 2, cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < slots.size(); e++) {
+            const size_t hoff = (size_t)slots[e] * 4096;        // [layer][chunk][4096] == slot * 4096
+            memcpy(ctx->h_blk.data() + hoff, out.data() + e * 8192, 8192);
+            if (res[slots[e]] & 2) memcpy(ctx->h_liid.data() + hoff, out.data() + e * 8192 + 4096, 8192);
+        }
+    }
+    return PFNAV_OK;
+}
+
+// n_update_blockers (nav.c:1017); layers the context does not hold are skipped. With a device the tiles are queued
+// for k_blockers_tiles; a host-only context counts them into its mirrors at once.
 static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size_t n, int delta)
 {
     if (layer >= ctx->nlayers) return;
+    if (ctx->device >= 0) {
+        blk_state *st = state_of(ctx, true);
+        for (size_t i = 0; i < n; i++)
+            st->tiles.push_back({layer, tds[i].chunk_r * 64 + tds[i].tile_r, tds[i].chunk_c * 64 + tds[i].tile_c, faction_id, delta});
+        return;
+    }
     const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h, ltiles = chunks * 4096;
     const size_t lbase = (size_t)layer * ltiles;
     const bool fac = faction_id >= 0 && faction_id < 15;
@@ -253,6 +640,10 @@ static void apply(pfnav_ctx *ctx, int layer, int faction_id, const td *tds, size
 
 static int blockers_circle(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags, int delta)
 {
+    if (ctx->device >= 0 && range >= 0.0f && (int)ceil(range / 4) <= CIRCLE_MAX_NT) {      // rasterised by k_blockers_circles
+        state_of(ctx, true)->circles.push_back({x, z, range, faction_id, flags, delta});
+        return PFNAV_OK;
+    }
     td tds[1024], o3[1024], o5[1024], o7[1024];
     const size_t n = tiles_under_circle(ctx, {x, z}, range, tds, 1024);
     const size_t n3 = tiles_contour(ctx, n, tds, o3, 1024);
@@ -326,7 +717,32 @@ int pfnav_footprint_tiles(const pfnav_ctx *ctx, const pfnav_footprint *e, int ri
     return (int)n;
 }
 
-void pfnav_blockers_forget(pfnav_ctx *ctx) { ctx->dirty.clear(); ctx->fdirty.clear(); }
+// the map is going away (pfnav_map_create / pfnav_destroy): queued operations and the device-side counts with it
+void pfnav_blockers_forget(pfnav_ctx *ctx)
+{
+    ctx->dirty.clear(); ctx->fdirty.clear();
+    blk_state *st = state_of(ctx, false);
+    if (!st) return;
+    if (ctx->device >= 0) {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        cudaFree(st->d_fac); cudaFree(st->d_touched); cudaFree(st->d_ops); cudaFree(st->d_out);
+    }
+    delete st;
+    ctx->blk_state = nullptr;
+}
+
+// Apply what is queued (no-op on a host-only context): called before anything that reads or overwrites the counts.
+int pfnav_blockers_flush(pfnav_ctx *ctx) { return device_flush(ctx); }
+
+// pfnav_map_upload_factions replaced the host counts of one layer: the device copy follows
+int pfnav_blockers_factions_uploaded(pfnav_ctx *ctx, int layer)
+{
+    blk_state *st = state_of(ctx, false);
+    if (!st || !st->d_fac || ctx->device < 0) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    return fac_push_layer(ctx, st, layer) ? PFNAV_ERR_CUDA : PFNAV_OK;
+}
 
 extern "C" int pfnav_blockers_incref(pfnav_ctx *ctx, float x, float z, float range, int faction_id, uint32_t flags)
 {
@@ -375,13 +791,11 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
     PF_ARG(ctx && ctx->d_cost, "map not created");
     if (ctx->device >= 0) {
         PF_CUDA(cudaSetDevice(ctx->device));
-        PF_CUDA(pf_fields_sync(ctx));     // forked LOS chains still read the map that is about to change
-        // ticks / field launches on the context stream or on caller streams (all non-blocking, so not ordered against
-        // the synchronous copies below) may still read the grids
-        PF_CUDA(cudaDeviceSynchronize());
-    }
-    {   // faction masks follow the refcounts at once (they only matter to attacking requests)
-        for (const auto &lc : ctx->fdirty) { int rc = pfnav_fmask_push_chunk(ctx, lc.first, lc.second); if (rc) return rc; }
+        int rc = device_flush(ctx);       // counts, faction masks and local islands of the touched chunks, on the device
+        if (rc) return rc;
+        if (!ctx->fdirty.empty()) ctx->map_epoch++;     // faction masks only matter to attacking requests
+        ctx->fdirty.clear();
+    } else {
         if (!ctx->fdirty.empty()) ctx->map_epoch++;
         ctx->fdirty.clear();
     }
@@ -391,8 +805,10 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
         bool pool_touched = false;
         for (const auto &lc : ctx->dirty) {
             const int layer = lc.first, chunk = lc.second;
-            int rc = pfnav_map_refresh_chunk(ctx, layer, chunk / ctx->chunk_w, chunk % ctx->chunk_w);
-            if (rc) return rc;
+            if (ctx->device < 0) {      // host-only context: islands on the host mirror (the device path did them in k_chunks_finish)
+                int rc = pfnav_map_refresh_chunk(ctx, layer, chunk / ctx->chunk_w, chunk % ctx->chunk_w);
+                if (rc) return rc;
+            }
             const int flipped = pfnav_route_refresh_edges(ctx, layer, chunk);
             nd++;
             if (!ctx->h_pool_slot.empty()) {
@@ -416,8 +832,10 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
             }
         }
         ctx->dirty.clear();
+        ctx->map_epoch++;
         if (pool_touched && ctx->device >= 0) {
             PF_CUDA(cudaSetDevice(ctx->device));
+            PF_CUDA(cudaDeviceSynchronize());     // a tick on a non-blocking stream may still read the flags
             PF_CUDA(cudaMemcpy(ctx->d_pool_los + (size_t)ctx->pool_max * 4096, ctx->h_pool_has.data(), ctx->pool_max,
                                cudaMemcpyHostToDevice));
         }
@@ -431,6 +849,7 @@ extern "C" int pfnav_map_commit(pfnav_ctx *ctx, int *out_ndirty)
 extern "C" int pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out)
 {
     PF_ARG(ctx && out && layer >= 0 && layer < ctx->nlayers, "args");
+    { int rc = device_flush(ctx); if (rc) return rc; }
     const size_t ltiles = (size_t)ctx->chunk_w * ctx->chunk_h * 4096;
     memcpy(out, ctx->h_blk.data() + ltiles * layer, ltiles * 2);
     return PFNAV_OK;
@@ -441,7 +860,23 @@ extern "C" int pfnav_blockers_get(pfnav_ctx *ctx, int layer, uint16_t *out)
 extern "C" int pfnav_blockers_get_factions(pfnav_ctx *ctx, int layer, uint8_t *out)
 {
     PF_ARG(ctx && out && layer >= 0 && layer < ctx->nlayers, "args");
+    { int rc = device_flush(ctx); if (rc) return rc; }
     const size_t n = (size_t)ctx->chunk_w * ctx->chunk_h * 15 * 4096;
+    if (blk_state *st = state_of(ctx, false); st && st->d_fac && ctx->device >= 0) {
+        // the device holds the counts: [15][H64][W64] -> [chunk][15][4096]
+        PF_CUDA(cudaSetDevice(ctx->device));
+        const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
+        std::vector<uint8_t> img(ltiles * 15);
+        PF_CUDA(cudaMemcpy(img.data(), st->d_fac + ltiles * 15 * layer, ltiles * 15, cudaMemcpyDeviceToHost));
+        const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h;
+        for (size_t ch = 0; ch < chunks; ch++) {
+            const size_t cr = ch / ctx->chunk_w, cc = ch % ctx->chunk_w;
+            for (int f = 0; f < 15; f++)
+                for (int r = 0; r < 64; r++)
+                    memcpy(out + (ch * 15 + f) * 4096 + r * 64, img.data() + ltiles * f + (cr * 64 + r) * ctx->W64 + cc * 64, 64);
+        }
+        return PFNAV_OK;
+    }
     if ((size_t)layer < ctx->h_fac.size() && ctx->h_fac[layer].size() == n) memcpy(out, ctx->h_fac[layer].data(), n);
     else memset(out, 0, n);
     return PFNAV_OK;

@@ -1621,6 +1621,7 @@ extern "C" int pfnav_map_upload_layer(pfnav_ctx *ctx, int layer, const uint8_t *
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(cost_base, "cost_base");
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }     // queued refcount operations come first
     ctx->map_epoch++;
     // new costs: the portal edges / travel index / global islands built from the old ones are void. (The structural
     // build re-uploads the layer from the mirrors themselves: same costs, tables stay.)
@@ -1670,6 +1671,7 @@ extern "C" int pfnav_map_cost_from_tiles(pfnav_ctx *ctx, int layer, int ref_laye
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(ref_layer >= 0 && ref_layer < PFNAV_NAV_LAYER_MAX, "ref_layer");
     PF_ARG(chunk_tiles && tile_stride >= 16, "chunk_tiles / tile_stride");
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }     // queued refcount operations come first
     PF_CUDA(cudaSetDevice(ctx->device));
     const int W32 = ctx->chunk_w * 32, H32 = ctx->chunk_h * 32;
     const size_t ntiles = (size_t)W32 * H32, ltiles = (size_t)ctx->W64 * ctx->H64;
@@ -1720,6 +1722,7 @@ extern "C" int pfnav_map_get_layer(pfnav_ctx *ctx, int layer, uint8_t *cost_base
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_NEED_DEVICE(ctx);
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }
     PF_CUDA(cudaSetDevice(ctx->device));
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     std::vector<uint16_t> img(ltiles);
@@ -1751,6 +1754,7 @@ extern "C" int pfnav_map_upload_factions(pfnav_ctx *ctx, int layer, const uint8_
 {
     PF_ARG(ctx && ctx->d_cost && factions, "map not created / null");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }     // queued refcount operations come first
     const size_t chunks = (size_t)ctx->chunk_w * ctx->chunk_h, ltiles = chunks * 4096;
     if (ctx->h_fac.size() < (size_t)ctx->nlayers) ctx->h_fac.resize(ctx->nlayers);
     if (ctx->h_fmask.size() < ltiles * ctx->nlayers) ctx->h_fmask.assign(ltiles * ctx->nlayers, 0);
@@ -1773,7 +1777,7 @@ extern "C" int pfnav_map_upload_factions(pfnav_ctx *ctx, int layer, const uint8_
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaDeviceSynchronize());
-    return PFNAV_OK;
+    return pfnav_blockers_factions_uploaded(ctx, layer);
 }
 
 // Push the faction masks of one chunk after blocker refcount changes (called by pfnav_map_commit).
@@ -1804,6 +1808,7 @@ extern "C" int pfnav_map_update_chunk(pfnav_ctx *ctx, int layer, int chunk_r, in
     PF_ARG(ctx && ctx->d_cost, "map not created");
     PF_ARG(layer >= 0 && layer < ctx->nlayers, "layer");
     PF_ARG(chunk_r >= 0 && chunk_r < ctx->chunk_h && chunk_c >= 0 && chunk_c < ctx->chunk_w, "chunk coords");
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }     // queued refcount operations come first
     ctx->map_epoch++;
     const size_t ltiles = (size_t)ctx->W64 * ctx->H64;
     const size_t off = ltiles * layer + (size_t)chunk_r * 64 * ctx->W64 + chunk_c * 64;

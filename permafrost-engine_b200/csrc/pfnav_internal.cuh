@@ -89,6 +89,7 @@ struct pfnav_ctx {
     // host-side derived state, owned by the context (no process-global tables: contexts on different threads are independent)
     void *route_state = nullptr;                               // pfnav_route.cu: std::vector<pfnav_route_layer>
     std::set<std::pair<int, int>> dirty, fdirty;               // pfnav_blockers.cu: (layer, chunk) occupancy / faction mask changed
+    void *blk_state = nullptr;                                 // pfnav_blockers.cu: queued blocker ops + device-side refcount state
 
     // ---- field pool ----
     int pool_ndests = 0, pool_max = 0, pool_used = 0;
@@ -147,6 +148,10 @@ struct pfnav_ctx {
     size_t cap_cells = 0;
     int32_t  *d_sorted_ix = nullptr, *d_sorted_iy = nullptr;
     uint32_t *d_sorted_id = nullptr;
+    int32_t  *d_sorted_flock = nullptr;                  // flock id of every index entry (windowed cohesion)
+    uint32_t *d_coh_fallback = nullptr; size_t cap_coh = 0;
+    std::vector<uint32_t> h_flock_start;
+    int cohesion_mode = 0;
     void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
     // work list + outputs
     size_t n_work = 0, cap_work = 0;
@@ -223,6 +228,8 @@ int pfnav_flow_repair_pool(pfnav_ctx *ctx, const pfnav_field_req *targets, const
                            const int32_t *slots, size_t n);
 
 int pfnav_fmask_push_chunk(pfnav_ctx *ctx, int layer, int chunk);
+int pfnav_blockers_flush(pfnav_ctx *ctx);                        // pfnav_blockers.cu: apply the queued blocker operations now
+int pfnav_blockers_factions_uploaded(pfnav_ctx *ctx, int layer); // pfnav_blockers.cu: host faction counts of a layer were replaced
 
 int pfnav_aux_chunk_seeds(pfnav_ctx *ctx, int dest, int chunk_r, int chunk_c, std::vector<int> &out);     // pfnav_region.cu
 

@@ -86,6 +86,45 @@ def test_bench_population_sample_vs_reference(pf, nav, c2map, bench, workload):
             assert len(got) == len(exp) and (got == exp).all(), (workload, int(i), r)
 
 
+def test_windowed_cohesion_equals_member_list(pf, nav, bench):
+    """cohesion_force through the position index with the exp(-0.12 d) cut-off (+ per-entity fall-back) against the plain
+    sum over the flock's member list, on the bench's C2 population and on a C4-style flock of 60 000: preferred velocities
+    agree to float rounding, far inside the 1e-4 budget"""
+    for workload, nsel in (("C2", 20_000), ("C4", 20_000)):
+        bench.set_workload(workload)
+        try:
+            W = bench.build_workload(pf, 1, 0) if workload == "C2" else None
+            if W is None:
+                # one C4 cell: 60 000 agents of radius 1.0 in one flock on an 8 x 8-chunk map
+                p = synth.make_map(8, 8, 0x5EED0004)
+                cost = synth.cost_from_pathable(p, 8, 8)
+                a = synth.make_agents(cost, 8, 8, 60_000, 1, 0x5EED0004, radius=1.0, spacing=3.9)
+                W = dict(cost=cost, agents=a, n_total=60_000, chunks=8)
+            else:
+                W["chunks"] = bench.CHUNKS
+        finally:
+            bench.set_workload("C2")
+        a, n, cw = W["agents"], W["n_total"], W["chunks"]
+        d = a["flock_target"][a["flock_of"]] - a["pos"]
+        aa = dict(a); aa["vdes"] = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-6)).astype(np.float32)
+        rec, fl = capi.pack_agents(aa)
+        nav.map_create(cw, cw, 1); nav.map_upload_layer(0, W["cost"])
+        nav.agents_upload(rec, fl, 20)
+        work = np.sort(np.random.default_rng(3).choice(n, nsel, replace=False)).astype(np.uint32)
+        nav.agents_set_work(work)
+        out = {}
+        try:
+            for mode in (2, 1):
+                nav.set_cohesion_mode(mode)
+                nav.agents_tick(0)
+                out[mode] = (nav.agents_read_debug(nsel)[0], nav.agents_read_velocities(nsel))
+        finally:
+            nav.set_cohesion_mode(0)
+        e_vp = cases.relerr(out[1][0], out[2][0]); e_v = cases.relerr(out[1][1], out[2][1])
+        assert e_vp.max() <= 2e-5, (workload, e_vp.max())
+        assert e_v.max() <= VEL_RTOL, (workload, e_v.max())
+
+
 def test_c2_desired_velocity_from_pool_vs_reference(pf, nav, c2map, bench):
     """A2 at full size: N_RequestPath for four flocks of the C2 population on the 1024 x 1024 map (routes of up to ~20
     hops), then N_HasDestLOS + N_DesiredPointSeekVelocity for 2 000 of their agents incl. the on-miss chain
@@ -221,10 +260,26 @@ def test_c5_churn_vs_reference(pf, nav, c2map, bench):
         ref.update()
 
 
-def _run_trajectory(nav, ref, a, ms, cw, cost, hz, nticks, with_blockers):
+def _vel_ok(vel, evel, pos):
+    """north_star's 1e-4 relative -- or ONE float spacing of the entity's position, the reference's own noise floor:
+    G_ClearPath_NewVelocity works in absolute map coordinates and returns `chosen point - position` (clearpath.c:694-715),
+    so its result is quantised at ulp(|pos|) (3e-5 wu at |pos| = 256..512) whatever the velocity's own magnitude; a
+    1e-7 relative difference in a preferred velocity (cohesion summation order) can move the chosen point by that one
+    step. Returns (all within bounds, number of entities that needed the floor)."""
+    d = np.abs(vel - evel).max(axis=1)
+    rel_ok = d <= VEL_RTOL * np.maximum(np.abs(evel).max(axis=1), 1e-3)
+    floor_ok = d <= np.spacing(np.abs(pos).max(axis=1).astype(np.float32))
+    return bool((rel_ok | floor_ok).all()), int((~rel_ok & floor_ok).sum())
+
+
+def _run_trajectory(nav, ref, a, ms, cw, cost, hz, nticks, with_blockers, follow=False):
     """tick -> entity_compute_update -> entity_apply_update -> next snapshot, `nticks` times, on both sides; the engine's
     share of the apply (entity_block: N_BlockersIncref for patches with next_block, then N_Update) is done by the test
-    on our side. Returns the per-tick maxima of the position / velocity deviation."""
+    on our side. The device state is uploaded once and never touched again. follow=True: before every tick after the
+    first the REFERENCE is re-seeded with the device's state (positions, velocities, movestates), so that every tick is
+    compared on identical inputs; free-running, the two sides are two chaotic trajectories that separate by one
+    position ulp per tick from the first ClearPath rounding step on (tests/tools/diag_traj.py prints both).
+    Returns the per-tick maxima of the position / velocity deviation."""
     n = len(a["radius"])
     dest_ids = np.array([ref.dest_id((float(t[0]), float(t[1]))) for t in a["flock_target"]], np.uint32)
     ref.agents_set(a["pos"], a["prev_pos"], a["vel"], a["radius"], a["max_speed"], a["state"], a["flags"],
@@ -246,11 +301,17 @@ def _run_trajectory(nav, ref, a, ms, cw, cost, hz, nticks, with_blockers):
     work = np.nonzero((state != 2) & (state != 4))[0].astype(np.uint32)
     ref.work_set(work, np.zeros((len(work), 2), np.float32), np.zeros(len(work), np.uint8), a["speed"][work])
     ref.desired_from_cache()
+    nfloor = 0
     for tick in range(nticks):
         work = np.nonzero((state != 2) & (state != 4))[0].astype(np.uint32)
         if len(work) == 0:
             break
         # reference
+        if follow and tick:
+            ref.agents_set(got["pos"], got["prev_pos"], got["velocity"], a["radius"], a["max_speed"], got["state"], a["flags"],
+                           a["flock_of"], a["flock_target"], dest_ids, hz=hz)
+            ref.movestate_set(gms["next_pos"][:, [0, 2]], gms["next_rot"], gms["step"], gms["left"], gms["vel_hist"],
+                              gms["vel_hist_idx"], np.zeros(n, np.int32), np.zeros(n, np.int32), gms["combat_facing"])
         ref.work_set(work, np.zeros((len(work), 2), np.float32), np.zeros(len(work), np.uint8), a["speed"][work])
         evdes, elos = ref.desired_from_cache()
         evel, _ = ref.velocity_work(os.cpu_count())
@@ -271,17 +332,19 @@ def _run_trajectory(nav, ref, a, ms, cw, cost, hz, nticks, with_blockers):
             assert (vdes == evdes).all(), (tick, np.nonzero((vdes != evdes).any(axis=1))[0][:10])
         else:       # positions carry the <= 1e-6 relative deviation of the previous ticks' velocities into the blend weights
             assert np.abs(vdes - evdes).max() <= VEL_RTOL, (tick, np.abs(vdes - evdes).max(), np.nonzero(np.abs(vdes - evdes).max(axis=1) > VEL_RTOL)[0][:10])
-        assert cases.relerr(vel, evel).max() <= VEL_RTOL, (tick, cases.relerr(vel, evel).max())
+        ok, nf = _vel_ok(vel, evel, snapshot[work])
+        assert ok, (tick, cases.relerr(vel, evel).max())
+        nfloor += nf
         nav.agents_compute_updates()
         patches = nav.agents_read_patches(len(work))
         nav.agents_apply_updates()
         nav.agents_rebuild_index()
-        got, _ = nav.agents_read_state(n)
+        got, gms = nav.agents_read_state(n)
         assert (got["state"] == est["state"]).all(), (tick, np.nonzero(got["state"] != est["state"])[0][:10])
         e_pos = np.abs(got["pos"] - est["pos"]).max(); e_prev = np.abs(got["prev_pos"] - est["prev_pos"]).max()
         e_vel = cases.relerr(got["velocity"], est["vel"]).max()
         # positions are world coordinates of magnitude <= 1e3: 1e-4 relative of the per-tick displacement (<= 1 wu)
-        assert e_pos <= 1e-4 and e_prev <= 1e-4 and e_vel <= VEL_RTOL, (tick, e_pos, e_prev, e_vel)
+        assert e_pos <= 1e-4 and e_prev <= 1e-4 and _vel_ok(got["velocity"], est["vel"], snapshot)[0], (tick, e_pos, e_prev, e_vel)
         out.append((len(work), float(e_pos), float(e_vel)))
         if with_blockers:
             # the engine side of entity_apply_update: entity_finish_moving -> entity_block (movement.c:685, 580)
@@ -296,6 +359,8 @@ def _run_trajectory(nav, ref, a, ms, cw, cost, hz, nticks, with_blockers):
             assert (nav.local_islands(0) == ref.local_islands()).all(), tick
         state = est["state"]
         snapshot = got["pos"].copy()
+    # the position-ulp floor is a rare event (a rounding step of ClearPath's absolute-coordinate result), not a blanket
+    assert nfloor <= max(2, nticks // 2), nfloor
     return out
 
 
@@ -318,7 +383,7 @@ def test_device_resident_trajectory_vs_reference(pf, nav, pfref, hz):
     ms["vel_hist"] = np.repeat(a["vel"][:, None, :], 14, axis=1)
     ref = pfref.RefMap(cw, cw, p)
     try:
-        out = _run_trajectory(nav, ref, a, ms, cw, cost, hz, 8, with_blockers=True)
+        out = _run_trajectory(nav, ref, a, ms, cw, cost, hz, 8, with_blockers=True, follow=True)
         assert len(out) == 8 and out[-1][0] > 1000, out
     finally:
         ref.close()
