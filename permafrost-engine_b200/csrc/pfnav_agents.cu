@@ -339,10 +339,26 @@ __global__ void k_cohesion(const pf_record *__restrict__ rec, const int32_t *__r
 // depends on the cut-off by more than float rounding. Index coordinates are the 1/256-wu integers of the position index.
 #define COH_R 230.0f
 #define COH_THREADS 128
+__device__ __forceinline__ void coh_finish(float ax, float az, float wsum, float self_w, float six_f, float siy_f, float sx, float sz,
+                                           uint32_t N, float thresh_unit, float scaled_max_force, uint32_t uid,
+                                           float2 *__restrict__ out_by_uid, uint32_t *__restrict__ fallback,
+                                           uint32_t *__restrict__ nfallback)
+{
+    if (N <= 1) out_by_uid[uid] = make_float2(0.0f, 0.0f);
+    else if (wsum - self_w >= (float)N * thresh_unit) {
+        // the entity's own index entry was summed too: take it out again (weight exp(4.5) at distance 0)
+        v2 com = {ax - six_f * self_w, az - siy_f * self_w};
+        com = v2_scale(com, 1.0f / (float)(N - 1));
+        v2 ret = v2_sub(com, v2{sx, sz});
+        ret = v2_truncate(ret, scaled_max_force);
+        out_by_uid[uid] = make_float2(ret.x, ret.z);
+    } else fallback[atomicAdd(nfallback, 1u)] = uid;
+}
 __global__ void __launch_bounds__(COH_THREADS)
 k_cohesion_window(GridView g, const pf_record *__restrict__ rec, const int32_t *__restrict__ sfl,
                   const uint32_t *__restrict__ flock_start, int n, uint32_t lo, uint32_t hi, float scaled_max_force,
-                  float2 *__restrict__ out_by_uid, uint32_t *__restrict__ fallback, uint32_t *__restrict__ nfallback)
+                  float2 *__restrict__ out_by_uid, uint32_t *__restrict__ fallback, uint32_t *__restrict__ nfallback,
+                  float4 *__restrict__ part, int nsplit)
 {
     __shared__ float4 tile[COH_THREADS];       // {x, z, flock id bits, -}
     __shared__ int bb[4];
@@ -383,7 +399,7 @@ k_cohesion_window(GridView g, const pf_record *__restrict__ rec, const int32_t *
             __syncthreads();
             const int cx0 = bb[0], cx1 = bb[1];
             if (cx1 < 0) continue;                                  // nobody in this row (uniform: read from shared memory)
-            for (int ry = max(cyv - RC, 0); ry <= min(cyv + RC, g.grid_h - 1); ry++) {
+            for (int ry = max(cyv - RC, 0) + (int)blockIdx.y; ry <= min(cyv + RC, g.grid_h - 1); ry += nsplit) {
                 const int gap = max(abs(ry - cyv) - 1, 0);
                 const float dy = (float)gap * 16.0f;
                 if (dy > COH_R) continue;
@@ -408,19 +424,34 @@ k_cohesion_window(GridView g, const pf_record *__restrict__ rec, const int32_t *
                 }
             }
         }
-        if (active) {
-            const uint32_t N = flock_start[fl + 1] - flock_start[fl];
-            if (N <= 1) out_by_uid[uid] = make_float2(0.0f, 0.0f);
-            else if (wsum - self_w >= (float)N * thresh_unit) {
-                // the entity's own index entry was summed too: take it out again (weight exp(4.5) at distance 0)
-                v2 com = {ax - six_f * self_w, az - siy_f * self_w};
-                com = v2_scale(com, 1.0f / (float)(N - 1));
-                v2 ret = v2_sub(com, v2{sx, sz});
-                ret = v2_truncate(ret, scaled_max_force);
-                out_by_uid[uid] = make_float2(ret.x, ret.z);
-            } else fallback[atomicAdd(nfallback, 1u)] = uid;
+        if (nsplit > 1) {                    // a small population split over blockIdx.y: k_cohesion_finish adds the parts up
+            if (k < n) part[(size_t)blockIdx.y * n + k] = make_float4(ax, az, wsum, 0.0f);
+        } else if (active) {
+            coh_finish(ax, az, wsum, self_w, six_f, siy_f, sx, sz, flock_start[fl + 1] - flock_start[fl], thresh_unit,
+                       scaled_max_force, uid, out_by_uid, fallback, nfallback);
         }
     }
+}
+
+// the window rows of one 128-entry run were split over `nsplit` blocks (populations too small to fill the chip with one
+// block per run): add the partial sums in split order and finish as the fused path does
+__global__ void k_cohesion_finish(GridView g, const pf_record *__restrict__ rec, const int32_t *__restrict__ sfl,
+                                  const uint32_t *__restrict__ flock_start, int n, uint32_t lo, uint32_t hi, float scaled_max_force,
+                                  float2 *__restrict__ out_by_uid, uint32_t *__restrict__ fallback, uint32_t *__restrict__ nfallback,
+                                  const float4 *__restrict__ part, int nsplit)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t uid = g.id[k];
+    const int fl = sfl[k];
+    if (!(uid >= lo && uid < hi && fl >= 0)) return;
+    float ax = 0.0f, az = 0.0f, wsum = 0.0f;
+    for (int sp = 0; sp < nsplit; sp++) { const float4 p = part[(size_t)sp * n + k]; ax += p.x; az += p.y; wsum += p.z; }
+    const pf_record self = rec[uid];
+    const float six_f = (float)g.ix[k] * (1.0f / 256.0f), siy_f = (float)g.iy[k] * (1.0f / 256.0f);
+    const float self_w = coh_weight(six_f - self.px, siy_f - self.pz);
+    coh_finish(ax, az, wsum, self_w, six_f, siy_f, self.px, self.pz, flock_start[fl + 1] - flock_start[fl],
+               __expf(4.5f - 0.12f * COH_R) * 1e7f, scaled_max_force, uid, out_by_uid, fallback, nfallback);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -716,36 +747,43 @@ __device__ __forceinline__ bool vo_contains(const VelSmem &s, int i, v2 test)
 // per iteration; a lane whose candidate is decided immediately takes the next one, so all lanes stay
 // busy whatever the early-exit pattern of inside_pcr is. Keeps the per-lane first-minimum of
 // compute_vnew (clearpath.c:368) on (distance, sequence index).
+// The candidate a lane has in flight survives between two drains of the same solve (DrainLane): a drain that is not the
+// last one of its solve returns as soon as the queue is empty and leaves the long-running candidates (the ones that pass
+// obstacle after obstacle) in their lanes, where the next batch of candidates fills the idle lanes around them; only the
+// final drain (`flush`) waits for the stragglers.
+struct DrainLane { int busy = 0, vo = 0, myk = 0, vstart = 0; v2 myp = {0.0f, 0.0f}; };
+// vstart: obstacle that swallowed this lane's previous candidate: tested first (any order is exact)
+
 __device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int nvo, const v2 ent_pos, const v2 des_v,
-                                                 uint32_t lane, float &best, int &best_idx, v2 &best_p, int &any)
+                                                 uint32_t lane, float &best, int &best_idx, v2 &best_p, int &any,
+                                                 DrainLane &dl, bool flush)
 {
-    int next = 0, my = -1, vo = 0, myk = 0;
-    int vstart = 0;      // obstacle that swallowed this lane's previous candidate: tested first (any order is exact)
-    v2 myp = {0.0f, 0.0f};
+    int next = 0;
     while (true) {
-        const bool need = my < 0;
+        const bool need = !dl.busy;
         const uint32_t mneed = __ballot_sync(FULL, need);
         const int avail = qn - next;
-        if (need) {
+        if (need && avail > 0) {
             const int rank = __popc(mneed & ((1u << lane) - 1));
-            if (rank < avail) { my = next + rank; vo = 0; myp = {s.cqx[my], s.cqz[my]}; myk = s.cqk[my]; }
+            if (rank < avail) { const int my = next + rank; dl.busy = 1; dl.vo = 0; dl.myp = {s.cqx[my], s.cqz[my]}; dl.myk = s.cqk[my]; }
         }
         next += min(__popc(mneed), avail);
-        if (!__any_sync(FULL, my >= 0)) break;
-        if (my >= 0) {
+        if (!flush && next >= qn) break;
+        if (!__any_sync(FULL, dl.busy)) break;
+        if (dl.busy) {
             bool finished = false, inside = false;
-            int vidx = vo + vstart;
+            int vidx = dl.vo + dl.vstart;
             if (vidx >= nvo) vidx -= nvo;
-            if (vo < nvo) inside = vo_contains(s, vidx, myp);
-            if (inside) { finished = true; vstart = vidx; }
-            else if (++vo >= nvo) {
+            if (dl.vo < nvo) inside = vo_contains(s, vidx, dl.myp);
+            if (inside) { finished = true; dl.vstart = vidx; }
+            else if (++dl.vo >= nvo) {
                 finished = true;
                 any = 1;
-                const v2 curr = v2_sub(myp, ent_pos);
+                const v2 curr = v2_sub(dl.myp, ent_pos);
                 const float len = v2_len(v2_sub(des_v, curr));
-                if (len < best || (len == best && best_idx != 0x7fffffff && myk < best_idx)) { best = len; best_idx = myk; best_p = curr; }
+                if (len < best || (len == best && best_idx != 0x7fffffff && dl.myk < best_idx)) { best = len; best_idx = dl.myk; best_p = curr; }
             }
-            if (finished) my = -1;
+            if (finished) dl.busy = 0;
         }
     }
 }
@@ -836,6 +874,7 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
     int best_idx = 0x7fffffff;
     v2 best_p = {0.0f, 0.0f};
     int any = 0, qn = 0;
+    DrainLane dl;
     const int npairs = n_rays * n_rays;
     // Exact pruning: compute_vnew (clearpath.c:368) keeps the admissible candidate nearest to des_v (first
     // one on ties), so a candidate that is certainly farther than an admissible candidate already found
@@ -855,7 +894,7 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
         qn += min(32, n_rays - base);
         if (qn > CQ_CAP - 32 || base + 32 >= n_rays) {
             __syncwarp();
-            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any, dl, true);     // the bound below needs them all
             __syncwarp();
             qn = 0;
         }
@@ -896,7 +935,7 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
         while (j >= n_rays) { j -= n_rays; i++; }
         if (qn > CQ_CAP - 32 || base + 32 >= npairs) {
             __syncwarp();
-            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any, dl, base + 32 >= npairs);
             __syncwarp();
             qn = 0;
             refresh_bound();
@@ -1176,33 +1215,34 @@ struct pf_prep {
 };
 
 // like drain_candidates, but records every candidate that lies inside no velocity obstacle
-__device__ __forceinline__ void drain_collect(const VelSmem &s, int qn, int nvo, uint32_t lane, pf_xpoint *out, int &cnt)
+__device__ __forceinline__ void drain_collect(const VelSmem &s, int qn, int nvo, uint32_t lane, pf_xpoint *out, int &cnt,
+                                              DrainLane &dl, bool flush)
 {
-    int next = 0, my = -1, vo = 0, myk = 0, vstart = 0;
-    v2 myp = {0.0f, 0.0f};
+    int next = 0;
     while (true) {
-        const bool need = my < 0;
+        const bool need = !dl.busy;
         const uint32_t mneed = __ballot_sync(FULL, need);
         const int avail = qn - next;
-        if (need) {
+        if (need && avail > 0) {
             const int rank = __popc(mneed & ((1u << lane) - 1));
-            if (rank < avail) { my = next + rank; vo = 0; myp = {s.cqx[my], s.cqz[my]}; myk = s.cqk[my]; }
+            if (rank < avail) { const int my = next + rank; dl.busy = 1; dl.vo = 0; dl.myp = {s.cqx[my], s.cqz[my]}; dl.myk = s.cqk[my]; }
         }
         next += min(__popc(mneed), avail);
-        if (!__any_sync(FULL, my >= 0)) break;
+        if (!flush && next >= qn) break;
+        if (!__any_sync(FULL, dl.busy)) break;
         bool admissible = false;
-        if (my >= 0) {
-            int vidx = vo + vstart;
+        if (dl.busy) {
+            int vidx = dl.vo + dl.vstart;
             if (vidx >= nvo) vidx -= nvo;
             bool inside = false;
-            if (vo < nvo) inside = vo_contains(s, vidx, myp);
-            if (inside) { my = -1; vstart = vidx; }
-            else if (++vo >= nvo) { admissible = true; my = -1; }
+            if (dl.vo < nvo) inside = vo_contains(s, vidx, dl.myp);
+            if (inside) { dl.busy = 0; dl.vstart = vidx; }
+            else if (++dl.vo >= nvo) { admissible = true; dl.busy = 0; }
         }
         const uint32_t ma = __ballot_sync(FULL, admissible);
         if (admissible) {
             const int q = cnt + __popc(ma & ((1u << lane) - 1));
-            if (q < PF_PREP_XP_CAP) { out[q].x = myp.x; out[q].z = myp.z; out[q].k = myk; }
+            if (q < PF_PREP_XP_CAP) { out[q].x = dl.myp.x; out[q].z = dl.myp.z; out[q].k = dl.myk; }
         }
         cnt += __popc(ma);
     }
@@ -1214,6 +1254,7 @@ __device__ int clearpath_collect(VelSmem &s, const cp_ent ent, int ndyn, int nst
     const int n_rays = build_vos(s, ent, ndyn, nstat, lane);
     const int nvo = n_rays >> 1, npairs = n_rays * n_rays;
     int cnt = 0, qn = 0;
+    DrainLane dl;
     int i = 0, j = (int)lane;
     while (j >= n_rays && n_rays > 0) { j -= n_rays; i++; }
     for (int base = 0; base < npairs; base += 32) {
@@ -1237,7 +1278,7 @@ __device__ int clearpath_collect(VelSmem &s, const cp_ent ent, int ndyn, int nst
         while (j >= n_rays) { j -= n_rays; i++; }
         if (qn > CQ_CAP - 32 || base + 32 >= npairs) {
             __syncwarp();
-            drain_collect(s, qn, nvo, lane, out, cnt);
+            drain_collect(s, qn, nvo, lane, out, cnt, dl, base + 32 >= npairs);
             __syncwarp();
             qn = 0;
         }
@@ -1271,7 +1312,8 @@ __device__ bool clearpath_finish(VelSmem &s, const cp_ent ent, const v2 des_v, i
         qn += min(32, n_rays - base);
         if (qn > CQ_CAP - 32 || base + 32 >= n_rays) {
             __syncwarp();
-            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any);
+            DrainLane dl;
+            drain_candidates(s, qn, nvo, ent.pos, des_v, lane, best, best_idx, best_p, any, dl, true);
             __syncwarp();
             qn = 0;
         }
@@ -1608,6 +1650,7 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_cell_count); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_cell_fill);
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id); cudaFree(ctx->d_sorted_flock);
     cudaFree(ctx->d_coh_fallback); ctx->d_sorted_flock = nullptr; ctx->d_coh_fallback = nullptr; ctx->cap_coh = 0;
+    cudaFree(ctx->d_coh_part); ctx->d_coh_part = nullptr; ctx->cap_coh_part = 0;
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
     cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep); cudaFree(ctx->d_flock_of); cudaFree(ctx->d_facts);
@@ -2040,9 +2083,23 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         uint32_t *d_nfb = ctx->d_coh_fallback + ctx->n_agents;
         PF_CUDA(cudaMemsetAsync(d_nfb, 0, 4, st));
         const int nblk = ((int)ctx->n_agents + COH_THREADS - 1) / COH_THREADS;     // one 128-entry run each: the hardware scheduler balances them
-        k_cohesion_window<<<nblk, COH_THREADS, 0, st>>>(grid_of(ctx), ctx->d_records, ctx->d_sorted_flock, ctx->d_flock_start,
+        // fewer runs than ~8 blocks per SM: split every run's window rows over blockIdx.y
+        const int nsplit = std::max(1, std::min(8, (ctx->sm_count * 8 + nblk - 1) / nblk));
+        if (nsplit > 1 && ctx->cap_coh_part < (size_t)nsplit * ctx->n_agents) {
+            cudaFree(ctx->d_coh_part); ctx->d_coh_part = nullptr; ctx->cap_coh_part = 0;
+            PF_CUDA(cudaMalloc(&ctx->d_coh_part, (size_t)8 * ctx->n_agents * sizeof(float4)));
+            ctx->cap_coh_part = (size_t)8 * ctx->n_agents;
+        }
+        k_cohesion_window<<<dim3(nblk, nsplit), COH_THREADS, 0, st>>>(grid_of(ctx), ctx->d_records, ctx->d_sorted_flock, ctx->d_flock_start,
                                                         (int)ctx->n_agents, (uint32_t)ctx->shard_lo, (uint32_t)ctx->shard_hi,
-                                                        tp.scaled_max_force, ctx->d_cohesion, ctx->d_coh_fallback, d_nfb);
+                                                        tp.scaled_max_force, ctx->d_cohesion, ctx->d_coh_fallback, d_nfb,
+                                                        (float4 *)ctx->d_coh_part, nsplit);
+        if (nsplit > 1) {
+            k_cohesion_finish<<<((int)ctx->n_agents + 127) / 128, 128, 0, st>>>(grid_of(ctx), ctx->d_records, ctx->d_sorted_flock,
+                ctx->d_flock_start, (int)ctx->n_agents, (uint32_t)ctx->shard_lo, (uint32_t)ctx->shard_hi, tp.scaled_max_force,
+                ctx->d_cohesion, ctx->d_coh_fallback, d_nfb, (const float4 *)ctx->d_coh_part, nsplit);
+            ctx->launches++;
+        }
         // fall-back entities: the grid is sized for the worst case, the kernel reads the count on the device
         const int nown = (int)(ctx->shard_hi - ctx->shard_lo);
         k_cohesion<<<(nown + 127) / 128, 128, 0, st>>>(ctx->d_records, ctx->d_flock_of, ctx->d_flock_start, ctx->d_member_pos,
