@@ -544,6 +544,7 @@ __device__ __forceinline__ void grid_query(const GridView &g, float x, float z, 
     const int ax_lo = wide ? 0 : cx_lo, ax_hi = wide ? g.grid_w - 1 : cx_hi;
     const int ay_lo = wide ? 0 : cy_lo, ay_hi = wide ? g.grid_h - 1 : cy_hi;
     const int cstep = wide ? (1 << 30) : 8;                    // one "coarse block" spans everything when wide
+    const bool small = !wide && ir >= 0 && ir <= 12000;         // <= 46 wu
     const int cyc_lo = wide ? 0 : ay_lo >> 3, cyc_hi = wide ? 0 : ay_hi >> 3;
     const int cxc_lo = wide ? 0 : ax_lo >> 3, cxc_hi = wide ? 0 : ax_hi >> 3;
     for (int cyc = cyc_lo; cyc <= cyc_hi; cyc++) {
@@ -551,20 +552,24 @@ __device__ __forceinline__ void grid_query(const GridView &g, float x, float z, 
             const int fy0 = wide ? ay_lo : max(cyc * cstep, ay_lo), fy1 = wide ? ay_hi + 1 : min(cyc * cstep + cstep, ay_hi + 1);
             const int fx0 = wide ? ax_lo : max(cxc * cstep, ax_lo), fx1 = wide ? ax_hi + 1 : min(cxc * cstep + cstep, ax_hi + 1);
             for (int fy = fy0; fy < fy1; fy++) {
-                for (int fx = fx0; fx < fx1; fx++) {
-                    const int c = fy * g.grid_w + fx;
-                    const uint32_t b = g.cell_start[c], cnt = g.cell_count[c];
-                    for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
-                        const uint32_t k = k0 + lane;
-                        bool hit = false;
-                        uint32_t id = 0;
-                        if (k < cnt) {
-                            const long long dx = (long long)g.ix[b + k] - icx, dy = (long long)g.iy[b + k] - icy;
+                // the cells fx0..fx1-1 of one fine row are adjacent in the cell-major index: one contiguous run of entries,
+                // visited in ascending cell x, in-cell order -- the reference's order
+                const uint32_t b = g.cell_start[fy * g.grid_w + fx0], e = g.cell_start[fy * g.grid_w + fx1];
+                for (uint32_t k0 = b; k0 < e; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    bool hit = false;
+                    uint32_t id = 0;
+                    if (k < e) {
+                        if (small) {        // |d| <= range + one cell on either side: the squares fit 32 bits
+                            const int32_t dx = g.ix[k] - icx, dy = g.iy[k] - icy;
+                            hit = abs(dx) <= ir && abs(dy) <= ir && dx * dx + dy * dy <= (int32_t)ir2;
+                        } else {
+                            const long long dx = (long long)g.ix[k] - icx, dy = (long long)g.iy[k] - icy;
                             hit = dx * dx + dy * dy <= ir2;
-                            id = g.id[b + k];
                         }
-                        if (emit(hit, id)) return;
+                        id = g.id[k];
                     }
+                    if (emit(hit, id)) return;
                 }
             }
         }
@@ -1391,6 +1396,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             int num_near = 0;
             grid_query(g, pos.x, pos.z, 30.0f, lane, [&](bool hit, uint32_t id) -> bool {
                 const uint32_t mk = __ballot_sync(FULL, hit);
+                if (!mk) return false;
                 const int rank = __popc(mk & ((1u << lane) - 1));
                 if (hit && num_near + rank < 128) s.near_id[num_near + rank] = id;
                 num_near += __popc(mk);
@@ -1534,6 +1540,7 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
         }
         auto classify = [&](bool hit, uint32_t id) -> bool {
             const uint32_t mk = __ballot_sync(FULL, hit);
+            if (!mk) return false;
             const int rrank = __popc(mk & ((1u << lane) - 1));
             bool isdyn = false, isstat = false;
             cp_ent nd;
