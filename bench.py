@@ -403,7 +403,9 @@ def run_ours(args):
             gather_phase()
         nav.pool_request_goals(goal_dests, goal_targets, 0, sp)
         step_moving()
+        nav.clearpath_stats()                                       # reset
         ms_m, _, _ = timed(step_moving, args.steps)
+        cps = nav.clearpath_stats()
         nav.profile_enable(True); nav.profile_read()
         for _ in range(3):
             step_moving()
@@ -414,6 +416,7 @@ def run_ours(args):
         moving = {"value": nwork * world * args.steps / (ms_m / 1e3), "ms_per_step": ms_m / args.steps,
                   "mean_displacement_wu": moved, "still_moving": float(((st["state"] != 2) & (st["state"] != 4)).mean()),
                   "phase_ms_per_step": {k: v[0] / 3 for k, v in pm.items() if v[1]},
+                  "clearpath_per_step": {k: v / args.steps for k, v in cps.items()},
                   "note": "tick + entity_compute_update + entity_apply_update + gather/index per step, positions advance on the device"}
     if rank == 0:
         sampler.stop_evt.set(); sampler.join(2)

@@ -666,6 +666,10 @@ int  pfnav_set_two_phase(pfnav_ctx *ctx, int mode);
  * through the position index with an exp(-0.12 d) cut-off at 230 wu and a per-entity fall-back to the full member list
  * wherever the cut-off could matter beyond float rounding; 1 = always windowed; 2 = always the full member list. */
 int  pfnav_set_cohesion_mode(pfnav_ctx *ctx, int mode);
+/* test / tuning hook: counters of G_ClearPath_NewVelocity's retry loop (clearpath.c:702-713) since the last reset:
+ * out4 = {first solves without an admissible velocity, of those with both neighbour lists non-empty, entities that
+ * replayed the loop literally (order-dependent tie), solves inside those replays} */
+int  pfnav_agents_clearpath_stats(pfnav_ctx *ctx, uint64_t *out4, int reset);
 
 /* flags for pfnav_agents_tick */
 #define PFNAV_TICK_VDES_FROM_POOL   (1u << 0)  /* compute vdes + has_dest_los on device (nav.c:3468, 4026) */

@@ -99,7 +99,7 @@ SYMBOLS = [
     "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
     "pfnav_pool_request_goals_ex", "pfnav_blockers_batch", "pfnav_map_set_pos",
     "pfnav_agents_upload_formation", "pfnav_agents_upload_movestate_ext", "pfnav_pool_request_entity_fields",
-    "pfnav_set_cohesion_mode",
+    "pfnav_set_cohesion_mode", "pfnav_agents_clearpath_stats",
 ]
 
 _lib = None
@@ -729,6 +729,11 @@ class Nav:
         ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
         _chk(self.L.pfnav_pool_request_entity_fields(self.h, dest, layer, ref_layer, kind, _p(fp), len(fp), _p(ch), len(ch),
                                                      C.c_void_p(stream)))
+
+    def clearpath_stats(self, reset=True):
+        out = np.zeros(4, np.uint64)
+        _chk(self.L.pfnav_agents_clearpath_stats(self.h, _p(out), 1 if reset else 0))
+        return dict(zip(("no_admissible", "loop_possible", "literal_replays", "replay_solves"), (int(v) for v in out)))
 
     def set_cohesion_mode(self, mode):
         _chk(self.L.pfnav_set_cohesion_mode(self.h, mode))

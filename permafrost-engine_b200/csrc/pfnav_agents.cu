@@ -488,6 +488,60 @@ __global__ void k_cell_scan(const uint32_t *__restrict__ count, uint32_t *__rest
     if (tid == 1023) start[ncells] = part[1023];
 }
 
+// the same scan for big grids, three launches: 4096 cells per block (4 per thread) -> block sums, their scan, apply
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t *warp_tot, uint32_t &total)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += o; }
+        warp_tot[lane] = wi - w;                       // exclusive
+        if (lane == 31) warp_tot[32] = wi;             // block total
+    }
+    __syncthreads();
+    total = warp_tot[32];
+    return warp_tot[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(1024) k_cell_scan_sum(const uint32_t *__restrict__ count, uint32_t *__restrict__ part, int ncells)
+{
+    __shared__ uint32_t wt[33];
+    const int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4;
+    uint32_t v = 0;
+    for (int j = 0; j < 4; j++) if (i0 + j < ncells) v += count[i0 + j];
+    uint32_t total;
+    block_excl_scan_1024(v, wt, total);
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_cell_scan_parts(uint32_t *__restrict__ part, int nb, uint32_t *__restrict__ start, int ncells)
+{
+    __shared__ uint32_t wt[33];
+    const uint32_t v = (int)threadIdx.x < nb ? part[threadIdx.x] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan_1024(v, wt, total);
+    if ((int)threadIdx.x < nb) part[threadIdx.x] = ex;
+    if (threadIdx.x == 0) start[ncells] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_cell_scan_apply(const uint32_t *__restrict__ count, const uint32_t *__restrict__ part,
+                                                          uint32_t *__restrict__ start, int ncells)
+{
+    __shared__ uint32_t wt[33];
+    const int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4;
+    uint32_t c[4], v = 0;
+    for (int j = 0; j < 4; j++) { c[j] = i0 + j < ncells ? count[i0 + j] : 0u; v += c[j]; }
+    uint32_t total;
+    uint32_t run = part[blockIdx.x] + block_excl_scan_1024(v, wt, total);
+    for (int j = 0; j < 4; j++) if (i0 + j < ncells) { start[i0 + j] = run; run += c[j]; }
+}
+
 __global__ void k_cell_scatter(const pf_record *__restrict__ rec, int n, GridView g,
                                const uint32_t *__restrict__ start, uint32_t *__restrict__ fill,
                                uint32_t *__restrict__ sid)
@@ -668,6 +722,9 @@ __device__ __forceinline__ void vo_edges(const cp_ent ent, const cp_ent nb, v2 &
 }
 
 #define VEL_WARPS_PER_CTA 4
+#ifndef VEL_MIN_CTAS_SINGLE
+#define VEL_MIN_CTAS_SINGLE 6
+#endif
 #ifndef VEL_MIN_CTAS
 #define VEL_MIN_CTAS 6          // 24 warps / SM: <= 80 registers (4 B of spill in the single-pass variant), 6 x 32 KB of shared memory
 #endif
@@ -977,6 +1034,20 @@ __device__ bool clearpath_new_velocity(VelSmem &s, const cp_ent ent, const v2 de
 // the first hit is the maximum and most points end at the nearest (widest) obstacles after one or two tests.
 // Cost: one solve instead of up to 63.
 // ------------------------------------------------------------------------------------------
+// obstacle ranks from the neighbour ranks, and the obstacles ordered by decreasing rank (index ascending among equals)
+__device__ __forceinline__ void retry_rank_vos(VelSmem &s, int nvo, uint32_t lane)
+{
+    for (int v = lane; v < nvo; v += 32) s.vo_rank[v] = s.nb_rank[s.vo_src[v]];
+    __syncwarp();
+    for (int v = lane; v < nvo; v += 32) {
+        const int r = s.vo_rank[v];
+        int p = 0;
+        for (int u = 0; u < nvo; u++) { const int ru = s.vo_rank[u]; p += (ru > r) || (ru == r && u < v); }
+        s.vo_ord[p] = (uint8_t)v;
+    }
+    __syncwarp();
+}
+
 // removal schedule; returns the number of removals after which the loop ends (no solve happens at that time)
 __device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int nvo, uint32_t lane)
 {
@@ -1014,15 +1085,46 @@ __device__ int retry_schedule(VelSmem &s, const v2 pos, int ndyn, int nstat, int
         __syncwarp();
         if (!(nd > 0 && ns > 0)) { t_end = t; break; }
     }
-    for (int v = lane; v < nvo; v += 32) s.vo_rank[v] = s.nb_rank[s.vo_src[v]];
-    __syncwarp();
-    for (int v = lane; v < nvo; v += 32) {                   // order by decreasing rank, index ascending among equals
-        const int r = s.vo_rank[v];
-        int p = 0;
-        for (int u = 0; u < nvo; u++) { const int ru = s.vo_rank[u]; p += (ru > r) || (ru == r && u < v); }
-        s.vo_ord[p] = (uint8_t)v;
+    retry_rank_vos(s, nvo, lane);
+    return t_end;
+}
+
+// The same schedule without the serial loop, for the common case that no two neighbours are exactly equally far away:
+// the loop then removes them in descending distance whatever the list order, neighbour n leaves at time
+// 1 + #{m : d(m) > d(n)}, and the loop ends when the last member of either list has left. Equal distances (lattice
+// crowds) fall back to the literal schedule above, whose tie-break follows the swap-with-last list order.
+__device__ int retry_schedule_fast(VelSmem &s, const v2 pos, int ndyn, int nstat, int nvo, uint32_t lane)
+{
+    for (int k = lane; k < 64; k += 32) {
+        const bool valid = k < 32 ? k < ndyn : (k - 32) < nstat;
+        float d = -__int_as_float(0x7f800000);
+        if (valid) { const cp_ent e = k < 32 ? s.dyn[k] : s.stat[k - 32]; d = v2_len(v2_sub(pos, e.pos)); }
+        s.ndist[k] = d;
     }
     __syncwarp();
+    bool tie = false;
+    int rk[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = (int)lane + 32 * h;
+        const bool valid = h == 0 ? (int)lane < ndyn : (int)lane < nstat;
+        if (valid) {
+            const float d = s.ndist[k];
+            int r = 1;
+            for (int j = 0; j < ndyn; j++) { const float dj = s.ndist[j]; r += dj > d; tie |= (dj == d && j != k); }
+            for (int j = 0; j < nstat; j++) { const float dj = s.ndist[32 + j]; r += dj > d; tie |= (dj == d && 32 + j != k); }
+            rk[h] = r;
+        }
+    }
+    if (__any_sync(FULL, tie)) return retry_schedule(s, pos, ndyn, nstat, nvo, lane);
+    int md = rk[0], ms = rk[1];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { md = max(md, __shfl_xor_sync(FULL, md, off)); ms = max(ms, __shfl_xor_sync(FULL, ms, off)); }
+    const int t_end = min(md, ms);
+    s.nb_rank[lane] = (uint8_t)(((int)lane < ndyn && rk[0] <= t_end) ? rk[0] : 255);
+    s.nb_rank[32 + lane] = (uint8_t)(((int)lane < nstat && rk[1] <= t_end) ? rk[1] : 255);
+    __syncwarp();
+    retry_rank_vos(s, nvo, lane);
     return t_end;
 }
 
@@ -1039,6 +1141,29 @@ __device__ __forceinline__ bool retry_better(int T, float dist, const v2 p, retr
     if (dist != b.dist) return dist < b.dist;
     if (b.id >= 0 && (p.x != b.p.x || p.z != b.p.z)) b.tie = 1;
     return false;
+}
+
+// the outcome of the retry loop from the per-lane bests: smallest time, then distance, then list position at that time
+__device__ __forceinline__ v2 retry_finish(retry_best &best, int adm_des, int t_end, const v2 des_v, uint32_t lane, bool &exact)
+{
+    int T = best.T;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) T = min(T, __shfl_xor_sync(FULL, T, off));
+    if (best.T != T) { best.dist = __int_as_float(0x7f800000); best.id = -1; best.tie = 0; }
+    if (adm_des <= T && adm_des <= t_end - 1) return des_v;     // inside_pcr(des_v) is tested before any candidate (:602)
+    float d = best.dist;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d = fminf(d, __shfl_xor_sync(FULL, d, off));
+    const bool mine = best.id >= 0 && best.dist == d;
+    const uint32_t mm = __ballot_sync(FULL, mine);
+    if (!mm) return v2{0.0f, 0.0f};                              // no solve before the loop ends finds a point
+    const int src = __ffs(mm) - 1;
+    v2 out;
+    out.x = __shfl_sync(FULL, best.p.x, src); out.z = __shfl_sync(FULL, best.p.z, src);
+    // ties between different points, inside a lane or across lanes: list order would decide
+    const bool differs = mine && (best.tie || best.p.x != out.x || best.p.z != out.z);
+    if (__any_sync(FULL, differs)) exact = false;
+    return out;
 }
 
 // like drain_candidates, for the retry emulation: cqk holds the candidate id, cqd its death time
@@ -1089,7 +1214,7 @@ __device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int 
     // with one of the two lists empty the loop condition fails right after the first removal (the common case in a crowd
     // where everybody moves): no second solve, the answer is zero
     if (ndyn == 0 || nstat == 0) return v2{0.0f, 0.0f};
-    const int t_end = retry_schedule(s, ent.pos, ndyn, nstat, nvo, lane);
+    const int t_end = retry_schedule_fast(s, ent.pos, ndyn, nstat, nvo, lane);
     if (t_end <= 1) return v2{0.0f, 0.0f};                   // the loop ends right after the first removal
     // the preferred velocity: admissible once every obstacle that contains it is gone
     const v2 des_v_ws = v2_add(ent.pos, des_v);
@@ -1151,25 +1276,7 @@ __device__ v2 clearpath_retry(VelSmem &s, const cp_ent ent, const v2 des_v, int 
         while (j >= n_rays) { j -= n_rays; i++; }
         flush(base + 32 >= npairs);
     }
-    // warp-wide choice: smallest time, then distance, then list position at that time
-    int T = best.T;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) T = min(T, __shfl_xor_sync(FULL, T, off));
-    if (best.T != T) { best.dist = __int_as_float(0x7f800000); best.id = -1; best.tie = 0; }
-    if (adm_des <= T && adm_des <= t_end - 1) return des_v;     // inside_pcr(des_v) is tested before any candidate (:602)
-    float d = best.dist;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d = fminf(d, __shfl_xor_sync(FULL, d, off));
-    const bool mine = best.id >= 0 && best.dist == d;
-    const uint32_t mm = __ballot_sync(FULL, mine);
-    if (!mm) return v2{0.0f, 0.0f};                              // no solve before the loop ends finds a point
-    const int src = __ffs(mm) - 1;
-    v2 out;
-    out.x = __shfl_sync(FULL, best.p.x, src); out.z = __shfl_sync(FULL, best.p.z, src);
-    // ties between different points, inside a lane or across lanes: list order would decide
-    const bool differs = mine && (best.tie || best.p.x != out.x || best.p.z != out.z);
-    if (__any_sync(FULL, differs)) exact = false;
-    return out;
+    return retry_finish(best, adm_des, t_end, des_v, lane, exact);
 }
 
 // remove_furthest (clearpath.c:390): first strict maximum over dyn then stat; swap-with-last delete
@@ -1347,6 +1454,7 @@ struct TickParams {
     int hz;
     float scaled_max_force;       // (float)SCALED_MAX_FORCE, as passed to vec2_truncate
     double scaled_max_force_d;    // SCALED_MAX_FORCE as the double it is in comparisons (movement.c:1895)
+    unsigned long long *stats;    // ClearPath event counters (pfnav_agents_clearpath_stats), never read by the kernels
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1354,7 +1462,7 @@ struct TickParams {
 // ------------------------------------------------------------------------------------------
 // MODE 0: the whole update in one pass. MODE 1 / 2: phase A / phase B of the two-phase scheme above.
 template <int MODE>
-__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, VEL_MIN_CTAS)
+__global__ void __launch_bounds__(VEL_WARPS_PER_CTA * 32, MODE == 0 ? VEL_MIN_CTAS_SINGLE : VEL_MIN_CTAS)
 k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__restrict__ agents,
                  const pf_record *__restrict__ rec, const pfnav_flock *__restrict__ flocks,
                  const uint32_t *__restrict__ work, int nwork, const float2 *__restrict__ vdes_in,
@@ -1607,24 +1715,27 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
             // resolved in one pass over the same ray table (clearpath_retry)
             v2 r;
             int n_rays = 0;
-            bool found;
+            bool found, exact = true;
             if (MODE == 2 && prep[w].nx != PF_PREP_OVERFLOW)
                 found = clearpath_finish(s, self, vpref, ndyn, nstat, lane, prep[w].xp, (int)prep[w].nx, r, n_rays);
             else
                 found = clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r, n_rays);
             if (found) new_vel = r;
             else {
-                bool exact;
+                if (lane == 0) { atomicAdd(tp.stats + 0, 1ull); if (ndyn > 0 && nstat > 0) atomicAdd(tp.stats + 1, 1ull); }
                 new_vel = clearpath_retry(s, self, vpref, ndyn, nstat, n_rays, lane, exact);
                 if (!exact) {
                     // replay the reference's loop literally (clearpath.c:702-713)
                     new_vel = {0.0f, 0.0f};
+                    unsigned long long solves = 0;
                     while (true) {
                         remove_furthest(s, self.pos, ndyn, nstat, lane);
                         if (!(ndyn > 0 && nstat > 0)) break;
                         int nr2;
+                        solves++;
                         if (clearpath_new_velocity(s, self, vpref, ndyn, nstat, lane, r, nr2)) { new_vel = r; break; }
                     }
+                    if (lane == 0) { atomicAdd(tp.stats + 2, 1ull); atomicAdd(tp.stats + 3, solves); }
                 }
             }
         }
@@ -1658,6 +1769,8 @@ void pfnav_agents_free(pfnav_ctx *ctx)
     cudaFree(ctx->d_sorted_ix); cudaFree(ctx->d_sorted_iy); cudaFree(ctx->d_sorted_id); cudaFree(ctx->d_sorted_flock);
     cudaFree(ctx->d_coh_fallback); ctx->d_sorted_flock = nullptr; ctx->d_coh_fallback = nullptr; ctx->cap_coh = 0;
     cudaFree(ctx->d_coh_part); ctx->d_coh_part = nullptr; ctx->cap_coh_part = 0;
+    cudaFree(ctx->d_cp_stats); ctx->d_cp_stats = nullptr;
+    cudaFree(ctx->d_scan_part); ctx->d_scan_part = nullptr;
     cudaFree(ctx->d_work); cudaFree(ctx->d_vel_out); cudaFree(ctx->d_vpref_out); cudaFree(ctx->d_vdes_out);
     cudaFree(ctx->d_movestate); cudaFree(ctx->d_patches); cudaFree(ctx->d_arrival); cudaFree(ctx->d_nb_scratch);
     cudaFree(ctx->d_member_pos); cudaFree(ctx->d_prep); cudaFree(ctx->d_flock_of); cudaFree(ctx->d_facts);
@@ -1784,7 +1897,15 @@ static int build_index(pfnav_ctx *ctx, cudaStream_t st)
     if (n > 0) {
         const GridView g = grid_of(ctx);
         k_cell_count<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_records, n, g, ctx->d_cell_count);
-        k_cell_scan<<<1, 1024, 0, st>>>(ctx->d_cell_count, ctx->d_cell_start, ncells);
+        const int nsb = (ncells + 4095) / 4096;
+        if (nsb > 1 && nsb <= 1024) {
+            if (!ctx->d_scan_part) PF_CUDA(cudaMalloc(&ctx->d_scan_part, 1024 * sizeof(uint32_t)));
+            k_cell_scan_sum<<<nsb, 1024, 0, st>>>(ctx->d_cell_count, (uint32_t *)ctx->d_scan_part, ncells);
+            k_cell_scan_parts<<<1, 1024, 0, st>>>((uint32_t *)ctx->d_scan_part, nsb, ctx->d_cell_start, ncells);
+            k_cell_scan_apply<<<nsb, 1024, 0, st>>>(ctx->d_cell_count, (const uint32_t *)ctx->d_scan_part, ctx->d_cell_start, ncells);
+            ctx->launches += 2;
+        } else
+            k_cell_scan<<<1, 1024, 0, st>>>(ctx->d_cell_count, ctx->d_cell_start, ncells);
         k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_records, n, g, ctx->d_cell_start, ctx->d_cell_fill,
                                                        ctx->d_sorted_id);
         k_cell_sort<<<(ncells + 127) / 128, 128, 0, st>>>(ctx->d_records, g, ctx->d_cell_start, ctx->d_sorted_id,
@@ -2065,6 +2186,11 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     tp.hz = ctx->hz;
     tp.scaled_max_force_d = (double)(0.75f / (float)ctx->hz) * 20.0;
     tp.scaled_max_force = (float)tp.scaled_max_force_d;
+    if (!ctx->d_cp_stats) {
+        PF_CUDA(cudaMalloc(&ctx->d_cp_stats, 8 * sizeof(unsigned long long)));
+        PF_CUDA(cudaMemsetAsync(ctx->d_cp_stats, 0, 8 * sizeof(unsigned long long), st));
+    }
+    tp.stats = (unsigned long long *)ctx->d_cp_stats;
     PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
     {
     pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
@@ -2094,6 +2220,8 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
         const int nsplit = std::max(1, std::min(8, (ctx->sm_count * 8 + nblk - 1) / nblk));
         if (nsplit > 1 && ctx->cap_coh_part < (size_t)nsplit * ctx->n_agents) {
             cudaFree(ctx->d_coh_part); ctx->d_coh_part = nullptr; ctx->cap_coh_part = 0;
+    cudaFree(ctx->d_cp_stats); ctx->d_cp_stats = nullptr;
+    cudaFree(ctx->d_scan_part); ctx->d_scan_part = nullptr;
             PF_CUDA(cudaMalloc(&ctx->d_coh_part, (size_t)8 * ctx->n_agents * sizeof(float4)));
             ctx->cap_coh_part = (size_t)8 * ctx->n_agents;
         }
@@ -3120,6 +3248,22 @@ extern "C" int pfnav_set_cohesion_mode(pfnav_ctx *ctx, int mode)
 {
     PF_ARG(ctx && mode >= 0 && mode <= 2, "mode");
     ctx->cohesion_mode = mode;
+    return PFNAV_OK;
+}
+
+// Test / tuning hook: how often G_ClearPath_NewVelocity's retry loop (clearpath.c:702-713) was entered since the last reset.
+// out[0] = first solves without an admissible velocity, out[1] = of those with both neighbour lists non-empty (the loop
+// can run), out[2] = entities that replayed the loop literally (order-dependent tie), out[3] = solves inside those replays.
+extern "C" int pfnav_agents_clearpath_stats(pfnav_ctx *ctx, uint64_t *out4, int reset)
+{
+    PF_ARG(ctx && out4, "args");
+    PF_NEED_DEVICE(ctx);
+    memset(out4, 0, 4 * sizeof(uint64_t));
+    if (!ctx->d_cp_stats) return PFNAV_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    PF_CUDA(cudaDeviceSynchronize());
+    PF_CUDA(cudaMemcpy(out4, ctx->d_cp_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) PF_CUDA(cudaMemset(ctx->d_cp_stats, 0, 8 * sizeof(unsigned long long)));
     return PFNAV_OK;
 }
 

@@ -150,6 +150,8 @@ struct pfnav_ctx {
     uint32_t *d_sorted_id = nullptr;
     int32_t  *d_sorted_flock = nullptr;                  // flock id of every index entry (windowed cohesion)
     uint32_t *d_coh_fallback = nullptr; size_t cap_coh = 0;
+    void *d_scan_part = nullptr;                              // block sums of the cell-count scan
+    void *d_cp_stats = nullptr;                               // ClearPath event counters (pfnav_agents_clearpath_stats)
     void *d_coh_part = nullptr; size_t cap_coh_part = 0;      // windowed cohesion: partial sums of split runs, float4 [nsplit][n]
     std::vector<uint32_t> h_flock_start;
     int cohesion_mode = 0;
