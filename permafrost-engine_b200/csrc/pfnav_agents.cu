@@ -1455,6 +1455,7 @@ struct TickParams {
     float scaled_max_force;       // (float)SCALED_MAX_FORCE, as passed to vec2_truncate
     double scaled_max_force_d;    // SCALED_MAX_FORCE as the double it is in comparisons (movement.c:1895)
     unsigned long long *stats;    // ClearPath event counters (pfnav_agents_clearpath_stats), never read by the kernels
+    unsigned int *queue;          // next work item of the velocity kernels, one counter per MODE; zeroed every tick
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1474,8 +1475,13 @@ k_agent_velocity(MapView m, GridView g, TickParams tp, const pfnav_agent *__rest
     extern __shared__ __align__(16) uint8_t vel_smem_raw[];      // VEL_WARPS_PER_CTA x VelSmem (> 48 KB: opt-in, pfnav_agents_init)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     VelSmem &s = reinterpret_cast<VelSmem *>(vel_smem_raw)[warp];
-    const int total_warps = gridDim.x * VEL_WARPS_PER_CTA;
-    for (int w = blockIdx.x * VEL_WARPS_PER_CTA + warp; w < nwork; w += total_warps) {
+    // work items are taken from a queue, not strided: an entity whose ClearPath solve runs long (no admissible velocity, a
+    // sixth of a moving crowd) would otherwise hold its CTA's three other warps idle at the end of their own strides
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = (int)atomicAdd(tp.queue + MODE, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= nwork) break;
         const uint32_t uid = work[w];
         const pfnav_agent a = agents[uid];
         const uint32_t ent_flags = a.flags & 0xFFFFFFu;
@@ -2187,10 +2193,12 @@ extern "C" int pfnav_agents_tick(pfnav_ctx *ctx, uint32_t flags, void *stream)
     tp.scaled_max_force_d = (double)(0.75f / (float)ctx->hz) * 20.0;
     tp.scaled_max_force = (float)tp.scaled_max_force_d;
     if (!ctx->d_cp_stats) {
-        PF_CUDA(cudaMalloc(&ctx->d_cp_stats, 8 * sizeof(unsigned long long)));
-        PF_CUDA(cudaMemsetAsync(ctx->d_cp_stats, 0, 8 * sizeof(unsigned long long), st));
+        PF_CUDA(cudaMalloc(&ctx->d_cp_stats, 16 * sizeof(unsigned long long)));
+        PF_CUDA(cudaMemsetAsync(ctx->d_cp_stats, 0, 16 * sizeof(unsigned long long), st));
     }
     tp.stats = (unsigned long long *)ctx->d_cp_stats;
+    tp.queue = (unsigned int *)(tp.stats + 8);
+    PF_CUDA(cudaMemsetAsync(tp.queue, 0, 4 * sizeof(unsigned int), st));
     PF_CUDA(cudaMemsetAsync(ctx->d_work_count, 0, 4, st));
     {
     pf_prof_scope prof(ctx, st, PF_PROF_COHESION);
