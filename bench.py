@@ -674,6 +674,8 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the box sets NCCL_DEBUG) goes to a file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pfnav_bench_nccl.%h.%p.log")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
