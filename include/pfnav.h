@@ -665,6 +665,13 @@ int  pfnav_set_two_phase(pfnav_ctx *ctx, int mode);
 /* Test / tuning hook: cohesion pass (cohesion_force, movement.c:1653). 0 (default) = flocks of >= 20 000 members are summed
  * through the position index with an exp(-0.12 d) cut-off at 230 wu and a per-entity fall-back to the full member list
  * wherever the cut-off could matter beyond float rounding; 1 = always windowed; 2 = always the full member list. */
+/* AStar_PortalGraphPath (a_star.c:429) for a batch of n searches, one device thread per search. req: 8 ints
+ * per search {start chunk index, start tile r, c, end chunk index, end tile r, c, finish chunk index, finish portal index};
+ * out: (4 + 3 * max_hops) ints per search {status, nhops, cost (float bits), 0, then (chunk index, portal index, local
+ * island) per hop from start to finish}; status 1 = path found, 0 = none, -1 = the search outgrew its device scratch or
+ * max_hops. on_device == 0 runs the host planner's own routine instead (what pfnav_route_request_path uses), for
+ * comparison. Needs pfnav_route_build(layer); blocker changes must be committed. */
+int  pfnav_route_graph_paths(pfnav_ctx *ctx, int layer, const int32_t *req, int n, int32_t *out, int max_hops, int on_device);
 int  pfnav_set_cohesion_mode(pfnav_ctx *ctx, int mode);
 /* test / tuning hook: counters of G_ClearPath_NewVelocity's retry loop (clearpath.c:702-713) since the last reset:
  * out4 = {first solves without an admissible velocity, of those with both neighbour lists non-empty, entities that

@@ -99,7 +99,7 @@ SYMBOLS = [
     "pfnav_group_create", "pfnav_group_gather", "pfnav_group_destroy", "pfnav_agents_upload_shard",
     "pfnav_pool_request_goals_ex", "pfnav_blockers_batch", "pfnav_map_set_pos",
     "pfnav_agents_upload_formation", "pfnav_agents_upload_movestate_ext", "pfnav_pool_request_entity_fields",
-    "pfnav_set_cohesion_mode", "pfnav_agents_clearpath_stats",
+    "pfnav_set_cohesion_mode", "pfnav_agents_clearpath_stats", "pfnav_route_graph_paths",
 ]
 
 _lib = None
@@ -729,6 +729,16 @@ class Nav:
         ch = np.ascontiguousarray(chunks, np.int32).reshape(-1, 2)
         _chk(self.L.pfnav_pool_request_entity_fields(self.h, dest, layer, ref_layer, kind, _p(fp), len(fp), _p(ch), len(ch),
                                                      C.c_void_p(stream)))
+
+    def route_graph_paths(self, req, max_hops=256, on_device=True, layer=0):
+        """AStar_PortalGraphPath batch; req int32[n, 8]; -> status[n], cost[n], list of hop arrays [nhops, 3]"""
+        req = np.ascontiguousarray(req, np.int32).reshape(-1, 8)
+        n = len(req)
+        out = np.zeros((n, 4 + 3 * max_hops), np.int32)
+        _chk(self.L.pfnav_route_graph_paths(self.h, layer, _p(req), n, _p(out), max_hops, 1 if on_device else 0))
+        cost = out[:, 2].copy().view(np.float32)
+        hops = [out[i, 4:4 + 3 * max(out[i, 1], 0)].reshape(-1, 3).copy() if out[i, 0] == 1 else np.zeros((0, 3), np.int32) for i in range(n)]
+        return out[:, 0].copy(), cost, hops
 
     def clearpath_stats(self, reset=True):
         out = np.zeros(4, np.uint64)

@@ -155,7 +155,8 @@ static inline pfnav_route_layer *route_layer(const pfnav_ctx *ctx, int layer)
     return &(*rv)[layer];
 }
 
-void pfnav_route_forget(pfnav_ctx *ctx) { delete routes_of(ctx); ctx->route_state = nullptr; }
+void pfnav_route_dev_forget(pfnav_ctx *ctx);
+void pfnav_route_forget(pfnav_ctx *ctx) { pfnav_route_dev_forget(ctx); delete routes_of(ctx); ctx->route_state = nullptr; }
 // the portal lists of `layer` were rebuilt: its edge / travel tables no longer describe them
 void pfnav_route_invalidate_layer(pfnav_ctx *ctx, int layer)
 {
@@ -1070,5 +1071,363 @@ extern "C" int pfnav_route_arrival_consts(pfnav_ctx *ctx, int layer, float tx, f
     *out_nearest_ok = c.nearest_ok; out_nearest_xz[0] = c.nearest[0]; out_nearest_xz[1] = c.nearest[1];
     *out_mc_n = c.mc_n;
     for (int i = 0; i < c.mc_n && (size_t)i < cap && out_mc_xz; i++) { out_mc_xz[2 * i] = c.mc[i][0]; out_mc_xz[2 * i + 1] = c.mc[i][1]; }
+    return PFNAV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-side AStar_PortalGraphPath (a_star.c:429): a batch of portal-graph searches, one thread per
+// search. The search itself is the reference's, statement for statement -- N_ClosestPathableLocalIsland (nav.c:5131)
+// for both ends, N_PortalReachableFromTile (:4852) + the travel-cost index for the start portals,
+// neighbours_portal_graph (a_star.c:212), portal_node_penalty (:298), and the 1-indexed binary heap of pqueue.h:109-208
+// whose tie order decides between equal-cost paths -- over device copies of the portal table, the intra-chunk edges with
+// their states, the travel-cost index and the local-island image. Per-search scratch (heap, cost / predecessor table,
+// flood queue) lives in HBM: 0.6 MB per search in flight, a few hundred searches per launch.
+// Not wired into pfnav_pool_request_path yet: the rest of n_request_path (fallback branches, field emission) is host code.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct dev_portal { int16_t r0, c0, r1, c1, chunk_r, chunk_c; int32_t conn_chunk, conn_idx, edge_off, edge_cnt; };
+struct dev_edge { int32_t nb, es; float cost; };
+struct dev_route {
+    const dev_portal *ports;      // [chunks][64]
+    const int32_t *nports;        // [chunks]
+    const int32_t *port_base;     // [chunks]: first row of the chunk's portals in `travel`
+    const dev_edge *edges;
+    const uint16_t *travel;       // [port_base[chunk] + i][4096]
+    const uint16_t *liid;         // image of the layer [H64][W64]
+    int cw, chh, W64;
+    float penalty;
+};
+#define GP_HT 8192                // cost / predecessor table slots (open addressing)
+#define GP_PQ 16384               // heap capacity
+struct gp_scratch {
+    uint64_t hkey[GP_HT]; uint64_t hfrom[GP_HT]; float hcost[GP_HT];
+    float pprio[GP_PQ]; uint64_t pdata[GP_PQ];
+    uint16_t queue[4096]; uint8_t visited[4096];
+};
+struct route_dev_state {
+    dev_portal *d_ports = nullptr; int32_t *d_nports = nullptr, *d_port_base = nullptr; dev_edge *d_edges = nullptr;
+    uint16_t *d_travel = nullptr; size_t travel_rows = 0, nedges = 0;
+    gp_scratch *d_scratch = nullptr; int scratch_n = 0;
+    void *d_req = nullptr, *d_out = nullptr; size_t req_bytes = 0, out_bytes = 0;
+    int layer = -1; uint64_t epoch = ~0ull; const void *built_for = nullptr;
+};
+
+__device__ __forceinline__ uint16_t gp_li(const dev_route &R, int chunk, int r, int c)
+{
+    return R.liid[(size_t)((chunk / R.cw) * 64 + r) * R.W64 + (chunk % R.cw) * 64 + c];
+}
+__device__ __forceinline__ uint64_t gp_key(int chunk, int pi, uint16_t liid) { return ((uint64_t)liid << 32) | ((uint64_t)chunk << 8) | (uint64_t)pi; }
+
+// N_ClosestPathableLocalIsland (nav.c:5131)
+__device__ uint16_t gp_closest_liid(const dev_route &R, gp_scratch &S, int chunk, int tr, int tc)
+{
+    const uint16_t own = gp_li(R, chunk, tr, tc);
+    if (own != 0xffff) return own;
+    for (int i = 0; i < 4096; i++) S.visited[i] = 0;
+    int head = 0, tail = 0;
+    S.queue[tail++] = (uint16_t)(tr * 64 + tc);
+    S.visited[tr * 64 + tc] = 1;
+    while (head < tail) {
+        const int cur = S.queue[head++], r = cur >> 6, c = cur & 63;
+        const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+        for (int e = 0; e < 4; e++) {
+            const int nr = r + dr[e], nc = c + dc[e];
+            if (nr < 0 || nr >= 64 || nc < 0 || nc >= 64) continue;
+            if (S.visited[nr * 64 + nc]) continue;
+            const uint16_t l = gp_li(R, chunk, nr, nc);
+            if (l != 0xffff) return l;
+            S.visited[nr * 64 + nc] = 1;
+            S.queue[tail++] = (uint16_t)(nr * 64 + nc);
+        }
+    }
+    return 0xffff;
+}
+
+// N_PortalReachableFromTile (nav.c:4852)
+__device__ bool gp_portal_reachable(const dev_route &R, int chunk, const dev_portal &p, int tr, int tc)
+{
+    for (int r = p.r0; r <= p.r1; r++)
+        for (int c = p.c0; c <= p.c1; c++) {
+            const uint16_t l = gp_li(R, chunk, r, c);
+            if (l == 0xffff) continue;
+            for (int r1 = tr - 1; r1 <= tr + 1; r1++)
+                for (int c1 = tc - 1; c1 <= tc + 1; c1++) {
+                    if (r1 < 0 || r1 >= 64 || c1 < 0 || c1 >= 64) continue;
+                    if (l == gp_li(R, chunk, r1, c1)) return true;
+                }
+        }
+    return false;
+}
+
+__device__ __forceinline__ int gp_find(const gp_scratch &S, uint64_t key)       // slot of key, or of the first free slot
+{
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 51) & (GP_HT - 1);
+    while (S.hkey[h] != 0 && S.hkey[h] != key) h = (h + 1) & (GP_HT - 1);
+    return (int)h;
+}
+// pq push / pop: pqueue.h:165-208 (strict comparisons, hole sift)
+__device__ __forceinline__ bool gp_push(gp_scratch &S, int &size, float prio, uint64_t d)
+{
+    if (size + 2 >= GP_PQ) return false;
+    int curr = size + 1, parent = curr / 2;
+    while (curr > 1 && S.pprio[parent] > prio) { S.pprio[curr] = S.pprio[parent]; S.pdata[curr] = S.pdata[parent]; curr = parent; parent /= 2; }
+    S.pprio[curr] = prio; S.pdata[curr] = d;
+    size++;
+    return true;
+}
+__device__ __forceinline__ uint64_t gp_pop(gp_scratch &S, int &size)
+{
+    const uint64_t out = S.pdata[1];
+    const float xp = S.pprio[size]; const uint64_t xd = S.pdata[size];
+    size--;
+    int root = 1;
+    while (true) {
+        const int l = root * 2, r = l + 1;
+        int target = 0; float tp = xp;
+        if (l <= size && S.pprio[l] < tp) { target = l; tp = S.pprio[l]; }
+        if (r <= size && S.pprio[r] < tp) { target = r; tp = S.pprio[r]; }
+        if (!target) break;
+        S.pprio[root] = S.pprio[target]; S.pdata[root] = S.pdata[target];
+        root = target;
+    }
+    S.pprio[root] = xp; S.pdata[root] = xd;
+    return out;
+}
+
+// req: {start chunk, start tile_r, start tile_c, end chunk, end tile_r, end tile_c, finish chunk, finish portal}
+// out (per search, 4 + 3 * max_hops ints): {status (1 found, 0 none, -1 scratch overflow), nhops, cost bits, 0, hops (chunk, portal, liid)...}
+__global__ void k_portal_graph_path(dev_route R, const int32_t *__restrict__ req, int n, gp_scratch *scratch, int32_t *out, int max_hops)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gp_scratch &S = scratch[i];
+    const int32_t *q = req + (size_t)i * 8;
+    int32_t *o = out + (size_t)i * (4 + 3 * max_hops);
+    o[0] = 0; o[1] = 0; o[2] = 0; o[3] = 0;
+    const int bchunk = q[0], echunk = q[3], fin_chunk = q[6], fin_pi = q[7];
+    const uint16_t start_liid = gp_closest_liid(R, S, bchunk, q[1], q[2]);
+    if (start_liid == 0xffff) return;
+    const uint16_t end_liid = gp_closest_liid(R, S, echunk, q[4], q[5]);
+    if (end_liid == 0xffff) return;
+    for (int k = 0; k < GP_HT; k++) S.hkey[k] = 0;
+    int size = 0, nkeys = 0;
+    bool overflow = false;
+    for (int p = 0; p < R.nports[bchunk]; p++) {
+        const dev_portal &P = R.ports[bchunk * 64 + p];
+        if (!gp_portal_reachable(R, bchunk, P, q[1], q[2])) continue;
+        const uint16_t t = R.travel[(size_t)(R.port_base[bchunk] + p) * 4096 + q[1] * 64 + q[2]];
+        if (t == 0xffff) continue;
+        const float cost = (float)t / 8;
+        const uint64_t key = gp_key(bchunk, p, start_liid);
+        const int s = gp_find(S, key);
+        if (S.hkey[s] == 0) { S.hkey[s] = key; S.hfrom[s] = 0; nkeys++; }
+        S.hcost[s] = cost;
+        overflow |= !gp_push(S, size, cost, key);
+    }
+    const uint64_t last = gp_key(fin_chunk, fin_pi, end_liid);
+    while (size > 0 && !overflow) {
+        const uint64_t cur = gp_pop(S, size);
+        if (cur == last) break;
+        const int cchunk = (int)((cur >> 8) & 0xffffff), cpi = (int)(cur & 0xff);
+        const uint16_t cli = (uint16_t)(cur >> 32);
+        const float base = S.hcost[gp_find(S, cur)];
+        auto relax = [&](uint64_t nk, float step) {
+            const float new_cost = base + step + R.penalty;
+            const int s = gp_find(S, nk);
+            if (S.hkey[s] == 0) {
+                if (nkeys + 1 >= GP_HT * 3 / 4) { overflow = true; return; }
+                S.hkey[s] = nk; nkeys++;
+            } else if (!(new_cost < S.hcost[s])) return;
+            S.hcost[s] = new_cost; S.hfrom[s] = cur;
+            overflow |= !gp_push(S, size, new_cost, nk);
+        };
+        // neighbours_portal_graph (a_star.c:212): the chunk's own portals over active edges whose portal touches the island ...
+        const dev_portal &P = R.ports[cchunk * 64 + cpi];
+        int nout = 0;
+        for (int e = 0; e < P.edge_cnt && nout < 256; e++) {
+            const dev_edge E = R.edges[P.edge_off + e];
+            if (E.es == 1) continue;
+            const dev_portal &NP = R.ports[cchunk * 64 + E.nb];
+            bool reach = false;
+            for (int r = NP.r0; r <= NP.r1 && !reach; r++)
+                for (int c = NP.c0; c <= NP.c1; c++)
+                    if (gp_li(R, cchunk, r, c) == cli) { reach = true; break; }
+            if (!reach) continue;
+            relax(gp_key(cchunk, E.nb, cli), E.cost);
+            nout++;
+        }
+        // ... then the islands of the connected chunk that touch this one across the portal (portal_connected_liids, :151)
+        const dev_portal &C = R.ports[P.conn_chunk * 64 + P.conn_idx];
+        uint16_t conn_liids[256];
+        int nconn = 0;
+        bool full = false;
+        for (int r1 = P.r0; r1 <= P.r1 && !full; r1++)
+            for (int c1 = P.c0; c1 <= P.c1 && !full; c1++) {
+                if (gp_li(R, cchunk, r1, c1) != cli) continue;
+                const int ar = P.chunk_r * 64 + r1, ac = P.chunk_c * 64 + c1;
+                const int cand[4][2] = {{ar - 1, ac}, {ar, ac - 1}, {ar, ac + 1}, {ar + 1, ac}};
+                for (int k = 0; k < 4; k++) {
+                    const int r2 = cand[k][0] - C.chunk_r * 64, c2 = cand[k][1] - C.chunk_c * 64;
+                    if (r2 < C.r0 || r2 > C.r1 || c2 < C.c0 || c2 > C.c1) continue;
+                    if (nconn == 256) { full = true; break; }
+                    const uint16_t nl = gp_li(R, P.conn_chunk, r2, c2);
+                    bool contains = false;
+                    for (int j = 0; j < nconn; j++) if (conn_liids[j] == nl) { contains = true; break; }
+                    if (!contains && nl != 0xffff) conn_liids[nconn++] = nl;
+                }
+            }
+        for (int j = 0; j < nconn && nout < 256; j++, nout++) relax(gp_key(P.conn_chunk, P.conn_idx, conn_liids[j]), 1.0f);
+    }
+    if (overflow) { o[0] = -1; return; }
+    const int ls = gp_find(S, last);
+    if (S.hkey[ls] == 0 || S.hfrom[ls] == 0) return;       // came_from holds no entry for the finish node
+    int nh = 0;
+    for (uint64_t cur = last; cur != 0; cur = S.hfrom[gp_find(S, cur)]) nh++;
+    o[1] = nh; o[2] = __float_as_int(S.hcost[ls]);
+    if (nh > max_hops) { o[0] = -1; return; }
+    int k = nh;
+    for (uint64_t cur = last; cur != 0; cur = S.hfrom[gp_find(S, cur)]) {
+        k--;
+        o[4 + 3 * k] = (int)((cur >> 8) & 0xffffff); o[4 + 3 * k + 1] = (int)(cur & 0xff); o[4 + 3 * k + 2] = (int)(cur >> 32);
+    }
+    o[0] = 1;
+}
+
+static route_dev_state *route_dev(pfnav_ctx *ctx)
+{
+    if (!ctx->route_dev_state) ctx->route_dev_state = new route_dev_state();
+    return (route_dev_state *)ctx->route_dev_state;
+}
+
+}   // namespace
+
+void pfnav_route_dev_forget(pfnav_ctx *ctx)
+{
+    route_dev_state *D = (route_dev_state *)ctx->route_dev_state;
+    if (!D) return;
+    if (ctx->device >= 0) {
+        cudaSetDevice(ctx->device);
+        cudaFree(D->d_ports); cudaFree(D->d_nports); cudaFree(D->d_port_base); cudaFree(D->d_edges); cudaFree(D->d_travel);
+        cudaFree(D->d_scratch); cudaFree(D->d_req); cudaFree(D->d_out);
+    }
+    delete D;
+    ctx->route_dev_state = nullptr;
+}
+
+// device copies of the routing tables of one layer; the travel-cost index follows the costs (re-sent when the layer was
+// rebuilt), the portal table + edge states follow every commit (map_epoch)
+static int route_dev_sync(pfnav_ctx *ctx, int layer, pfnav_route_layer &RL, route_dev_state *D)
+{
+    const int chunks = ctx->chunk_w * ctx->chunk_h;
+    if (D->layer == layer && D->epoch == ctx->map_epoch && D->built_for == (const void *)RL.chunks.data()) return 0;
+    std::vector<dev_portal> ports((size_t)chunks * 64);
+    std::vector<int32_t> nports(chunks), base(chunks);
+    std::vector<dev_edge> edges;
+    size_t rows = 0;
+    for (int ch = 0; ch < chunks; ch++) {
+        const auto &pp = ctx->portals[layer][ch];
+        nports[ch] = (int32_t)pp.size(); base[ch] = (int32_t)rows; rows += pp.size();
+        for (size_t i = 0; i < pp.size(); i++) {
+            dev_portal d;
+            d.r0 = pp[i].r0; d.c0 = pp[i].c0; d.r1 = pp[i].r1; d.c1 = pp[i].c1; d.chunk_r = pp[i].chunk_r; d.chunk_c = pp[i].chunk_c;
+            d.conn_chunk = pp[i].conn_chunk; d.conn_idx = pp[i].conn_idx;
+            d.edge_off = (int32_t)edges.size(); d.edge_cnt = (int32_t)RL.chunks[ch].edges[i].size();
+            for (const auto &e : RL.chunks[ch].edges[i]) edges.push_back({e.nb, e.es, e.cost});
+            ports[(size_t)ch * 64 + i] = d;
+        }
+    }
+    const bool retravel = D->layer != layer || D->built_for != (const void *)RL.chunks.data() || D->travel_rows != rows;
+    if (!D->d_ports) {
+        PF_CUDA(cudaMalloc(&D->d_ports, ports.size() * sizeof(dev_portal)));
+        PF_CUDA(cudaMalloc(&D->d_nports, (size_t)chunks * 4));
+        PF_CUDA(cudaMalloc(&D->d_port_base, (size_t)chunks * 4));
+    }
+    if (D->nedges < edges.size()) {
+        cudaFree(D->d_edges); D->d_edges = nullptr;
+        PF_CUDA(cudaMalloc(&D->d_edges, std::max<size_t>(edges.size(), 1) * sizeof(dev_edge)));
+        D->nedges = edges.size();
+    }
+    PF_CUDA(cudaMemcpy(D->d_ports, ports.data(), ports.size() * sizeof(dev_portal), cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(D->d_nports, nports.data(), (size_t)chunks * 4, cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(D->d_port_base, base.data(), (size_t)chunks * 4, cudaMemcpyHostToDevice));
+    if (!edges.empty()) PF_CUDA(cudaMemcpy(D->d_edges, edges.data(), edges.size() * sizeof(dev_edge), cudaMemcpyHostToDevice));
+    if (retravel) {
+        cudaFree(D->d_travel); D->d_travel = nullptr;
+        PF_CUDA(cudaMalloc(&D->d_travel, std::max<size_t>(rows, 1) * 4096 * 2));
+        for (int ch = 0; ch < chunks; ch++)
+            if (nports[ch])
+                PF_CUDA(cudaMemcpy(D->d_travel + (size_t)base[ch] * 4096, RL.chunks[ch].travel.data(), (size_t)nports[ch] * 4096 * 2,
+                                   cudaMemcpyHostToDevice));
+        D->travel_rows = rows;
+    }
+    D->layer = layer; D->epoch = ctx->map_epoch; D->built_for = (const void *)RL.chunks.data();
+    return 0;
+}
+
+// AStar_PortalGraphPath for n searches. req: 8 ints per search {start chunk index, start tile r, c, end chunk index, end tile
+// r, c, finish chunk index, finish portal index}; out: (4 + 3 * max_hops) ints per search {status, nhops, cost (float
+// bits), 0, then (chunk, portal, local island) per hop, start to finish}; status 1 = path, 0 = none, -1 = the search
+// outgrew its scratch (heap 16 k entries / 6 k nodes) or max_hops. on_device != 0: the kernel; 0: the host planner's own
+// routine (what pfnav_route_request_path runs), for comparison.
+extern "C" int pfnav_route_graph_paths(pfnav_ctx *ctx, int layer, const int32_t *req, int n, int32_t *out, int max_hops, int on_device)
+{
+    PF_ARG(ctx && req && out && n >= 0 && max_hops > 0, "args");
+    pfnav_route_layer *prl = route_layer(ctx, layer);
+    PF_ARG(prl, "pfnav_route_build not called");
+    const int cw = ctx->chunk_w, chunks = cw * ctx->chunk_h;
+    for (int i = 0; i < n; i++) {
+        const int32_t *q = req + (size_t)i * 8;
+        PF_ARG(q[0] >= 0 && q[0] < chunks && q[3] >= 0 && q[3] < chunks && q[6] >= 0 && q[6] < chunks, "chunk index");
+        PF_ARG(q[1] >= 0 && q[1] < 64 && q[2] >= 0 && q[2] < 64 && q[4] >= 0 && q[4] < 64 && q[5] >= 0 && q[5] < 64, "tile");
+        PF_ARG(q[7] >= 0 && q[7] < (int)ctx->portals[layer][q[6]].size(), "finish portal");
+    }
+    const size_t ostride = 4 + 3 * (size_t)max_hops;
+    if (!on_device) {
+        Router R{ctx, *prl, layer, cw, ctx->chunk_h};
+        for (int ch = 0; ch < chunks; ch++) update_edge_states(ctx, *prl, layer, ch);
+        for (int i = 0; i < n; i++) {
+            const int32_t *q = req + (size_t)i * 8;
+            int32_t *o = out + (size_t)i * ostride;
+            memset(o, 0, ostride * 4);
+            std::vector<Router::hop> path;
+            float cost = 0.0f;
+            const tdesc s = {q[0] / cw, q[0] % cw, q[1], q[2]}, e = {q[3] / cw, q[3] % cw, q[4], q[5]};
+            if (!R.portal_graph_path(s, e, q[6], q[7], path, &cost)) continue;
+            o[1] = (int32_t)path.size(); memcpy(&o[2], &cost, 4);
+            if ((int)path.size() > max_hops) { o[0] = -1; continue; }
+            for (size_t k = 0; k < path.size(); k++) { o[4 + 3 * k] = path[k].chunk; o[4 + 3 * k + 1] = path[k].pi; o[4 + 3 * k + 2] = path[k].liid; }
+            o[0] = 1;
+        }
+        return PFNAV_OK;
+    }
+    PF_NEED_DEVICE(ctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    { int rc = pfnav_blockers_flush(ctx); if (rc) return rc; }
+    for (int ch = 0; ch < chunks; ch++) update_edge_states(ctx, *prl, layer, ch);      // n_update_all_edge_states (nav.c:1787)
+    route_dev_state *D = route_dev(ctx);
+    D->epoch = ~0ull;                                                                  // edge states were just refreshed
+    if (route_dev_sync(ctx, layer, *prl, D)) return PFNAV_ERR_CUDA;
+    const int batch = 512;
+    if (D->scratch_n < std::min(n, batch)) {
+        cudaFree(D->d_scratch); D->d_scratch = nullptr;
+        PF_CUDA(cudaMalloc(&D->d_scratch, (size_t)std::min(std::max(n, 1), batch) * sizeof(gp_scratch)));
+        D->scratch_n = std::min(std::max(n, 1), batch);
+    }
+    if (D->req_bytes < (size_t)batch * 32) { cudaFree(D->d_req); PF_CUDA(cudaMalloc(&D->d_req, (size_t)batch * 32)); D->req_bytes = (size_t)batch * 32; }
+    if (D->out_bytes < (size_t)batch * ostride * 4) { cudaFree(D->d_out); PF_CUDA(cudaMalloc(&D->d_out, (size_t)batch * ostride * 4)); D->out_bytes = (size_t)batch * ostride * 4; }
+    dev_route R;
+    R.ports = D->d_ports; R.nports = D->d_nports; R.port_base = D->d_port_base; R.edges = D->d_edges; R.travel = D->d_travel;
+    R.liid = ctx->d_liid + (size_t)ctx->W64 * ctx->H64 * layer; R.cw = cw; R.chh = ctx->chunk_h; R.W64 = ctx->W64;
+    R.penalty = (float)sqrt(pow(64, 2.0f) + pow(64, 2.0f));                          // portal_node_penalty (a_star.c:298)
+    PF_CUDA(cudaDeviceSynchronize());
+    for (int b0 = 0; b0 < n; b0 += batch) {
+        const int nb = std::min(batch, n - b0);
+        PF_CUDA(cudaMemcpy(D->d_req, req + (size_t)b0 * 8, (size_t)nb * 32, cudaMemcpyHostToDevice));
+        k_portal_graph_path<<<(nb + 31) / 32, 32>>>(R, (const int32_t *)D->d_req, nb, D->d_scratch, (int32_t *)D->d_out, max_hops);
+        ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(out + (size_t)b0 * ostride, D->d_out, (size_t)nb * ostride * 4, cudaMemcpyDeviceToHost));
+    }
     return PFNAV_OK;
 }
