@@ -1408,7 +1408,7 @@ extern "C" int pfnav_route_graph_paths(pfnav_ctx *ctx, int layer, const int32_t 
     route_dev_state *D = route_dev(ctx);
     D->epoch = ~0ull;                                                                  // edge states were just refreshed
     if (route_dev_sync(ctx, layer, *prl, D)) return PFNAV_ERR_CUDA;
-    const int batch = 512;
+    const int batch = 4096;                                                            // 364 KB of scratch per search in flight
     if (D->scratch_n < std::min(n, batch)) {
         cudaFree(D->d_scratch); D->d_scratch = nullptr;
         PF_CUDA(cudaMalloc(&D->d_scratch, (size_t)std::min(std::max(n, 1), batch) * sizeof(gp_scratch)));
