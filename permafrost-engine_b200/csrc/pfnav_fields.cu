@@ -1135,6 +1135,29 @@ __device__ void los_blocked_line_b(LosSmemB &s, const LosMapInfo mi, int tgt_cr,
     }
 }
 
+// Heap of the byte-state kernel: entries = prio2 << 13 | padded index ((r + 1) * 66 + c + 1 < 8192), so that a pop needs
+// no unpacking and no address arithmetic before its four state loads. heap_remove_root is heap_pop without the read of
+// the root: the caller reads h[1] first and issues the neighbour loads BEFORE the sift, whose dependent chain then hides them.
+__device__ __forceinline__ void heap_remove_root13(uint16_t *h, int &size, uint32_t lowp)
+{
+    const uint16_t x = h[size];
+    size--;
+    int root = 1;
+    if ((uint32_t)(x >> 13) != lowp) {
+        const uint32_t *h2 = reinterpret_cast<const uint32_t *>(h);      // children 2k, 2k+1 share one aligned word
+        while (true) {
+            const int l = root * 2;
+            if (l > size) break;
+            const uint32_t two = h2[root];
+            const bool dl = ((two >> 13) & 0x7u) == lowp, dr = l < size && (two >> 29) == lowp;
+            if (!(dl || dr)) break;
+            h[root] = (uint16_t)(dl ? two : two >> 16);
+            root = dl ? l : l + 1;
+        }
+    }
+    h[root] = x;
+}
+
 __global__ void __launch_bounds__(LOS_WARPS_PER_CTA * 32)
 k_los_b(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int n,
       uint8_t *fields, const int32_t *__restrict__ out_slot, unsigned *counter, int *done,
@@ -1242,7 +1265,7 @@ k_los_b(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int 
             int size = 0;
             const bool dest_chunk = (q.chunk_r == q.tgt_chunk_r && q.chunk_c == q.tgt_chunk_c);
             if (dest_chunk) {
-                h[++size] = (uint16_t)((q.tgt_tile_r << 6) | q.tgt_tile_c);
+                h[++size] = (uint16_t)((q.tgt_tile_r + 1) * LB_W + q.tgt_tile_c + 1);
                 s.st[(q.tgt_tile_r + 1) * LB_W + q.tgt_tile_c + 1] |= LB_ASG;
             } else {
                 // carry the shared edge over from the previous chunk's field (field.c:2122-2196)
@@ -1262,20 +1285,22 @@ k_los_b(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int 
                         los_blocked_line_b(s, mi, q.tgt_chunk_r, q.tgt_chunk_c, q.tgt_tile_r, q.tgt_tile_c,
                                            q.chunk_r, q.chunk_c, r, c);
                     if (pv & 1) {
-                        h[++size] = (uint16_t)((r << 6) | c);     // priority 0: an append, all seeds are equal
+                        h[++size] = (uint16_t)idx;                // priority 0: an append, all seeds are equal
                         s.st[idx] |= LB_ASG;
                     }
                 }
             }
             while (size > 0) {
                 npops++;
-                const uint16_t cur = heap_pop(h, size);
-                const int r = (cur >> 6) & 63, c = cur & 63;
-                const uint16_t nprio = (uint16_t)((((cur >> 12) + 1) & 3) << 12);
-                uint8_t *ctr = s.st + (r + 1) * LB_W + (c + 1);
+                const uint32_t cur = h[1];
+                const uint32_t pidx = cur & 0x1FFFu;
+                const uint16_t nprio = (uint16_t)((((cur >> 13) + 1) & 3) << 13);
+                uint8_t *ctr = s.st + pidx;
                 // neighbour order of field_neighbours_grid_los: (-1,0) (0,-1) (0,+1) (+1,0); the four states are read
-                // before anything of this pop is written (the list is collected first, field.c:2205)
+                // before anything of this pop is written (the list is collected first, field.c:2205) -- and before the
+                // sift, which touches only the heap array
                 const uint32_t s0 = ctr[-LB_W], s1 = ctr[-1], s2 = ctr[1], s3 = ctr[LB_W];
+                heap_remove_root13(h, size, cur >> 13);
                 const uint32_t TM = LB_BLK | LB_BORDER | LB_OPEN;
                 const bool v0 = (s0 & TM) == LB_OPEN, v1 = (s1 & TM) == LB_OPEN, v2 = (s2 & TM) == LB_OPEN, v3 = (s3 & TM) == LB_OPEN;
                 const bool p0 = v0 && !(s0 & LB_ASG), p1 = v1 && !(s1 & LB_ASG), p2 = v2 && !(s2 & LB_ASG), p3 = v3 && !(s3 & LB_ASG);
@@ -1283,16 +1308,17 @@ k_los_b(FlowGrids g, LosMapInfo mi, const pfnav_los_req *__restrict__ reqs, int 
                 if (v1) ctr[-1] = (uint8_t)(s1 | LB_VIS | LB_ASG);
                 if (v2) ctr[1] = (uint8_t)(s2 | LB_VIS | LB_ASG);
                 if (v3) ctr[LB_W] = (uint8_t)(s3 | LB_VIS | LB_ASG);
-                const uint16_t base0 = (uint16_t)(nprio | (r << 6) | c);
+                const uint16_t base0 = (uint16_t)(nprio | pidx);
                 int sz = size;
-                if (p0) h[++sz] = (uint16_t)(base0 - 64);
+                if (p0) h[++sz] = (uint16_t)(base0 - LB_W);
                 if (p1) h[++sz] = (uint16_t)(base0 - 1);
                 if (p2) h[++sz] = (uint16_t)(base0 + 1);
-                if (p3) h[++sz] = (uint16_t)(base0 + 64);
+                if (p3) h[++sz] = (uint16_t)(base0 + LB_W);
                 size = sz;
                 if (!((s0 & TM) && (s1 & TM) && (s2 & TM) && (s3 & TM))) {
                     // an impassable (or cost > 1) neighbour that is inside the chunk and not wavefront-blocked:
                     // field_is_los_corner (field.c:435), then the blocked line
+                    const int r = (int)(pidx / LB_W) - 1, c = (int)(pidx % LB_W) - 1;
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const uint32_t se = e == 0 ? s0 : e == 1 ? s1 : e == 2 ? s2 : s3;
