@@ -95,3 +95,75 @@ def test_reference_nav_on_gpu_fields(both):
     finally:
         for m in maps:
             m.close()
+
+
+# ------------------------------------------------------------------------------------------
+# Seam B1: the reference's own GPU back-end hooks (render.h:619-691), compiled on libpfnav.so
+# ------------------------------------------------------------------------------------------
+B1_ENT = np.dtype([("dest", "<f4", 2), ("vdes", "<f4", 2), ("cell_pos", "<f4", 2), ("coh", "<f4", 2), ("align", "<f4", 2),
+                   ("drag", "<f4", 2), ("pos", "<f4", 2), ("velocity", "<f4", 2), ("movestate", "<u4"), ("flock_id", "<u4"),
+                   ("flags", "<u4"), ("speed", "<f4"), ("max_speed", "<f4"), ("radius", "<f4"), ("layer", "<u4"),
+                   ("has_dest_los", "<u4"), ("ready", "<u4"), ("pad0", "<u4")])             # struct gpu_ent_desc, movement.c:350
+B1_FLOCK = np.dtype([("ents", "<u4", 1024), ("nmembers", "<u4"), ("target", "<f4", 2)])      # struct gpu_flock_desc, :341
+B1_RES = np.dtype([("chunk_w", "<i4"), ("chunk_h", "<i4"), ("tile_w", "<i4"), ("tile_h", "<i4"), ("field_w", "<f4"),
+                   ("field_h", "<f4")])                                                     # struct map_resolution, tile.h:127
+
+
+def test_b1_movement_backend_equals_direct_tick(pf):
+    """shim/gl_movement_pfnav.c: R_GL_MoveUploadData / UpdateUniforms / DispatchWork / ReadNewVelocities called as
+    move_submit_gpu_velocity_work calls them (movement.c:3943), with buffers laid out as move_upload_input packs them
+    (:3790-3915), against pfnav_agents_tick on the same population (prev_pos = pos: the seam carries no prev_pos)."""
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libpfnav_b1.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libpfnav_b1.so not built (make -C oracle shimb1)")
+    L = C.CDLL(path)
+    cw = 3
+    p, cost, a = cases.agent_case(cw, 2000, 3, 515, 0.04, 2.4)
+    n = len(a["radius"])
+    a["prev_pos"] = a["pos"].copy()
+    d = a["flock_target"][a["flock_of"]] - a["pos"]
+    a["vdes"] = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-6)).astype(np.float32)
+    rng = np.random.default_rng(5)
+    a["has_los"] = (rng.random(n) < 0.3).astype(np.uint32)
+    work = np.nonzero((a["state"] != 2) & (a["state"] != 4))[0].astype(np.uint32)
+    # blockers under the arrived entities, as the engine would hold them
+    blk = np.zeros((cw * cw, 64, 64), np.uint16)
+    # ---- direct ----
+    nav = capi.Nav(0)
+    nav.map_create(cw, cw, 1); nav.map_upload_layer(0, cost, blk)
+    rec, fl = capi.pack_agents(a)
+    fl["dest"] = -1
+    for hz in (20, 10):
+        nav.agents_upload(rec, fl, hz); nav.agents_set_work(work); nav.agents_tick(0)
+        want = nav.agents_read_velocities(len(work))
+        # ---- through the seam ----
+        ents = np.zeros(n, B1_ENT)
+        ents["dest"] = a["flock_target"][a["flock_of"]]; ents["vdes"] = a["vdes"]; ents["pos"] = a["pos"]; ents["velocity"] = a["vel"]
+        ents["movestate"] = a["state"]; ents["flock_id"] = a["flock_of"] + 1; ents["flags"] = a["flags"]
+        ents["speed"] = a["speed"]; ents["max_speed"] = a["max_speed"]; ents["radius"] = a["radius"]; ents["has_dest_los"] = a["has_los"]
+        flocks = np.zeros(len(a["flock_target"]), B1_FLOCK)
+        flocks["target"] = a["flock_target"]
+        for f in range(len(flocks)):          # member lists cut at 1024 like the engine's buffer (the shim ignores them)
+            m = np.nonzero(a["flock_of"] == f)[0][:1024]
+            flocks["ents"][f, :len(m)] = m + 1; flocks["nmembers"][f] = len(m)
+        gpuids = (work + 1).astype(np.uint32)
+        res = np.zeros(1, B1_RES); res["chunk_w"] = cw; res["chunk_h"] = cw; res["tile_w"] = 32; res["tile_h"] = 32
+        map_pos = np.zeros(2, np.float32)
+        sz = lambda v: C.byref(C.c_size_t(int(v)))
+        ptr = lambda arr: arr.ctypes.data_as(C.c_void_p)
+        costb = np.ascontiguousarray(cost, np.uint8)
+        L.R_GL_MoveUploadData(ptr(gpuids), sz(len(gpuids)), ptr(ents), sz(ents.nbytes), ptr(flocks), sz(flocks.nbytes),
+                              ptr(costb), sz(costb.nbytes), ptr(blk), sz(blk.nbytes))
+        L.R_GL_MoveUpdateUniforms(ptr(res), ptr(map_pos), C.byref(C.c_int(hz)), C.byref(C.c_int(len(work))))
+        L.R_GL_MoveDispatchWork(sz(n))
+        done = C.c_int(0)
+        L.R_GL_MovePollCompletion(C.byref(done))
+        assert done.value == 1
+        got = np.zeros((len(work), 2), np.float32)
+        L.R_GL_MoveReadNewVelocities(ptr(got), sz(len(work)), sz(len(work)))
+        L.R_GL_MoveInvalidateData()
+        assert (got == want).all(), (hz, np.abs(got - want).max())
+        assert np.abs(want).max() > 0.1
+    L.R_GL_MoveClearState()
+    nav.close()
