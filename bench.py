@@ -229,6 +229,8 @@ def run_ours(args):
         nav.map_commit()
     ngoals = W["g_hi"] - W["g_lo"]
     nav.pool_create(ngoals, ngoals * CHUNKS * CHUNKS)
+    if os.environ.get("PFNAV_COHESION_MODE"):          # A/B hook: 1 always the windowed cohesion pass, 2 always the member list
+        nav.set_cohesion_mode(int(os.environ["PFNAV_COHESION_MODE"]))
     if os.environ.get("PFNAV_TWO_PHASE"):              # A/B and profiling hook: 0 single pass, 2 always split
         nav.set_two_phase(int(os.environ["PFNAV_TWO_PHASE"]))
     goals = [tuple(int(v) for v in W["agents"]["flock_target_tile"][f]) for f in range(W["g_lo"], W["g_hi"])]

@@ -158,8 +158,7 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
         cz = map_z + (cr + 0.5) * NAV_TILE
         need = per[f]
         got = 0
-        ring = 0
-        pts = []
+        shrinks = 0
         # hex spiral lattice around the centre, keeping only points on passable tiles inside the map
         R = int(np.ceil(np.sqrt(need / 0.55))) + 4
         while got < need:
@@ -176,8 +175,16 @@ def make_agents(cost_blocked, chunk_w, chunk_h, n, nflocks, seed, radius=1.0, ma
             ok = img[tr, tc] != 0xFF
             xs = xs[ok]; zs = zs[ok]
             got = len(xs)
-            if got < need and R * step > 4 * max(W64, H64) * NAV_TILE:
-                raise ValueError("flock %d: %d agents at spacing %.2f do not fit its area" % (f, need, step))
+            if got < need and R * step > (1.5 * max(bx1 - bx0, bz1 - bz0) if cells is not None else 4 * max(W64, H64) * NAV_TILE):
+                # the whole area was searched. A flock confined to a grid cell whose passable part is too small for the
+                # nominal spacing packs a little tighter (3 % per try) instead of failing: the weak-scaling populations
+                # fill ~94 % of the passable map at N = 8, some cells hold more obstacles than others
+                if cells is None or shrinks >= 40:
+                    raise ValueError("flock %d: %d agents at spacing %.2f do not fit its area" % (f, need, step))
+                shrinks += 1
+                step *= 0.97
+                R = int(np.ceil(np.sqrt(need / 0.55))) + 4
+                continue
             R *= 2
         pos[k:k + need, 0] = xs[:need]
         pos[k:k + need, 1] = zs[:need]
