@@ -60,3 +60,29 @@ def test_shard_range_covers_everything():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             assert max(e[1] - e[0] for e in edges) - min(e[1] - e[0] for e in edges) <= 1
+
+
+def test_bench_population_builds_for_8_ranks():
+    """bench.py's weak-scaling populations at the driver's largest GPU count (config C4 at N = 8 = BASELINE configs[3]: 4 M
+    agents, 64 flocks, one per cell of an 8 x 8 grid over the 2048^2 map -- ~94 % of the passable area): every flock must fit
+    its cell (cells with more obstacles pack a few per cent tighter), and the N = 2 population must be a prefix of it."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    pf = importlib.import_module("permafrost-engine_b200")
+    bench.set_workload("C4")
+    try:
+        w8 = bench.build_workload(pf, 8, 7)
+        a = w8["agents"]
+        assert len(a["pos"]) == 4_000_000 and w8["nflocks"] == 64 and w8["hi"] - w8["lo"] == 500_000
+        assert (np.bincount(a["flock_of"], minlength=64) == 62500).all()
+        for f in range(64):                                  # hex packing at (nearly) the nominal spacing, no overlaps
+            p = a["pos"][a["flock_of"] == f][:400]
+            d = np.linalg.norm(p[1:] - p[0], axis=1).min()
+            assert 3.3 <= d <= 3.91, (f, d)
+        w2 = bench.build_workload(pf, 2, 0)
+        assert np.array_equal(w2["agents"]["pos"], a["pos"][:len(w2["agents"]["pos"])])
+    finally:
+        bench.set_workload("C2")
