@@ -748,7 +748,6 @@ struct VelSmem {
     uint8_t cur[64];                      // working lists: dyn slots at [0, nd), stat slots at [32, 32 + ns)
     float   ndist[64];                    // neighbour slot -> distance from the entity
     uint8_t cqd[CQ_CAP];                  // death time of the queued candidates
-    uint8_t hit[32], hitv[32];            // drain_group_step: "some helper found the candidate inside" / inside which obstacle
 };
 
 // One velocity obstacle of inside_pcr (clearpath.c:252-287): is `test` strictly inside VO `i`?
@@ -810,42 +809,6 @@ __device__ __forceinline__ bool vo_contains(const VelSmem &s, int i, v2 test)
 // per iteration; a lane whose candidate is decided immediately takes the next one, so all lanes stay
 // busy whatever the early-exit pattern of inside_pcr is. Keeps the per-lane first-minimum of
 // compute_vnew (clearpath.c:368) on (distance, sequence index).
-// One drain iteration of the final (flush) phase, when nothing is left to hand out and at least as many lanes are idle as
-// busy: the idle lanes help. Every busy lane's candidate is tested against g consecutive obstacles at once, by the lane
-// itself (offset 0) and g - 1 helpers (offsets 1 .. g - 1); "inside any obstacle" does not depend on the order or the
-// grouping of the tests. Returns, for a busy lane, whether one of the g tests hit (hit_vidx: which obstacle).
-__device__ __forceinline__ bool drain_group_step(VelSmem &s, int nvo, uint32_t lane, uint32_t mbusy, int g, int busy, int vo,
-                                                 int vstart, v2 myp, int &hit_vidx)
-{
-    const uint32_t lt = (1u << lane) - 1u;
-    const int nbusy = __popc(mbusy);
-    int partner = (int)lane, t = 0;
-    bool take = busy != 0;
-    if (!busy) {
-        const int ri = __popc(~mbusy & lt);
-        const int pr = ri / (g - 1);
-        t = 1 + ri % (g - 1);
-        take = pr < nbusy;
-        partner = take ? __fns(mbusy, 0, pr + 1) : (int)lane;
-    }
-    const float px = __shfl_sync(FULL, myp.x, partner), pz = __shfl_sync(FULL, myp.z, partner);
-    const int pvo = __shfl_sync(FULL, vo, partner), pvs = __shfl_sync(FULL, vstart, partner);
-    if (busy) s.hit[lane] = 0;
-    __syncwarp();
-    if (take) {
-        const int k = pvo + t;
-        if (k < nvo) {
-            int vidx = k + pvs;
-            if (vidx >= nvo) vidx -= nvo;
-            if (vo_contains(s, vidx, v2{px, pz})) { s.hit[partner] = 1; s.hitv[partner] = (uint8_t)vidx; }
-        }
-    }
-    __syncwarp();
-    bool hit = false;
-    if (busy && s.hit[lane]) { hit = true; hit_vidx = s.hitv[lane]; }
-    return hit;
-}
-
 // The candidate a lane has in flight survives between two drains of the same solve (DrainLane): a drain that is not the
 // last one of its solve returns as soon as the queue is empty and leaves the long-running candidates (the ones that pass
 // obstacle after obstacle) in their lanes, where the next batch of candidates fills the idle lanes around them; only the
@@ -853,7 +816,7 @@ __device__ __forceinline__ bool drain_group_step(VelSmem &s, int nvo, uint32_t l
 struct DrainLane { int busy = 0, vo = 0, myk = 0, vstart = 0; v2 myp = {0.0f, 0.0f}; };
 // vstart: obstacle that swallowed this lane's previous candidate: tested first (any order is exact)
 
-__device__ __forceinline__ void drain_candidates(VelSmem &s, int qn, int nvo, const v2 ent_pos, const v2 des_v,
+__device__ __forceinline__ void drain_candidates(const VelSmem &s, int qn, int nvo, const v2 ent_pos, const v2 des_v,
                                                  uint32_t lane, float &best, int &best_idx, v2 &best_p, int &any,
                                                  DrainLane &dl, bool flush)
 {
@@ -868,24 +831,7 @@ __device__ __forceinline__ void drain_candidates(VelSmem &s, int qn, int nvo, co
         }
         next += min(__popc(mneed), avail);
         if (!flush && next >= qn) break;
-        const uint32_t mbusy = __ballot_sync(FULL, dl.busy);
-        if (!mbusy) break;
-        const int g = next >= qn ? 1 + (32 - __popc(mbusy)) / __popc(mbusy) : 1;
-        if (g > 1) {                                             // stragglers only: the idle lanes share their obstacle tests
-            int hv = 0;
-            const bool hit = drain_group_step(s, nvo, lane, mbusy, g, dl.busy, dl.vo, dl.vstart, dl.myp, hv);
-            if (dl.busy) {
-                if (hit) { dl.busy = 0; dl.vstart = hv; }
-                else if ((dl.vo += g) >= nvo) {
-                    dl.busy = 0;
-                    any = 1;
-                    const v2 curr = v2_sub(dl.myp, ent_pos);
-                    const float len = v2_len(v2_sub(des_v, curr));
-                    if (len < best || (len == best && best_idx != 0x7fffffff && dl.myk < best_idx)) { best = len; best_idx = dl.myk; best_p = curr; }
-                }
-            }
-            continue;
-        }
+        if (!__any_sync(FULL, dl.busy)) break;
         if (dl.busy) {
             bool finished = false, inside = false;
             int vidx = dl.vo + dl.vstart;
@@ -1381,7 +1327,7 @@ struct pf_prep {
 };
 
 // like drain_candidates, but records every candidate that lies inside no velocity obstacle
-__device__ __forceinline__ void drain_collect(VelSmem &s, int qn, int nvo, uint32_t lane, pf_xpoint *out, int &cnt,
+__device__ __forceinline__ void drain_collect(const VelSmem &s, int qn, int nvo, uint32_t lane, pf_xpoint *out, int &cnt,
                                               DrainLane &dl, bool flush)
 {
     int next = 0;
@@ -1395,18 +1341,9 @@ __device__ __forceinline__ void drain_collect(VelSmem &s, int qn, int nvo, uint3
         }
         next += min(__popc(mneed), avail);
         if (!flush && next >= qn) break;
-        const uint32_t mbusy = __ballot_sync(FULL, dl.busy);
-        if (!mbusy) break;
-        const int g = next >= qn ? 1 + (32 - __popc(mbusy)) / __popc(mbusy) : 1;
+        if (!__any_sync(FULL, dl.busy)) break;
         bool admissible = false;
-        if (g > 1) {                                             // stragglers only: the idle lanes share their obstacle tests
-            int hv = 0;
-            const bool hit = drain_group_step(s, nvo, lane, mbusy, g, dl.busy, dl.vo, dl.vstart, dl.myp, hv);
-            if (dl.busy) {
-                if (hit) { dl.busy = 0; dl.vstart = hv; }
-                else if ((dl.vo += g) >= nvo) { admissible = true; dl.busy = 0; }
-            }
-        } else if (dl.busy) {
+        if (dl.busy) {
             int vidx = dl.vo + dl.vstart;
             if (vidx >= nvo) vidx -= nvo;
             bool inside = false;
