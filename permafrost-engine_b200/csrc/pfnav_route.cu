@@ -140,6 +140,7 @@ struct pfnav_route_chunk {
 };
 struct pfnav_route_layer {
     bool built = false;
+    uint64_t generation = 0;                                      // bumped by every pfnav_route_build: device copies follow it
     std::vector<pfnav_route_chunk> chunks;
     std::vector<uint16_t> islands;                                // global islands, chunk-blocked
 };
@@ -297,6 +298,7 @@ extern "C" int pfnav_route_build(pfnav_ctx *ctx, int layer)
                 }
     }
     for (int ch = 0; ch < chunks; ch++) update_edge_states(ctx, RL, layer, ch);
+    { static std::atomic<uint64_t> next_generation{1}; RL.generation = next_generation++; }
     RL.built = true;
     return PFNAV_OK;
 }
@@ -1110,7 +1112,7 @@ struct route_dev_state {
     uint16_t *d_travel = nullptr; size_t travel_rows = 0, nedges = 0;
     gp_scratch *d_scratch = nullptr; int scratch_n = 0;
     void *d_req = nullptr, *d_out = nullptr; size_t req_bytes = 0, out_bytes = 0;
-    int layer = -1; uint64_t epoch = ~0ull; const void *built_for = nullptr;
+    int layer = -1; uint64_t epoch = ~0ull, generation = 0;
 };
 
 __device__ __forceinline__ uint16_t gp_li(const dev_route &R, int chunk, int r, int c)
@@ -1320,7 +1322,7 @@ void pfnav_route_dev_forget(pfnav_ctx *ctx)
 static int route_dev_sync(pfnav_ctx *ctx, int layer, pfnav_route_layer &RL, route_dev_state *D)
 {
     const int chunks = ctx->chunk_w * ctx->chunk_h;
-    if (D->layer == layer && D->epoch == ctx->map_epoch && D->built_for == (const void *)RL.chunks.data()) return 0;
+    if (D->layer == layer && D->epoch == ctx->map_epoch && D->generation == RL.generation) return 0;
     std::vector<dev_portal> ports((size_t)chunks * 64);
     std::vector<int32_t> nports(chunks), base(chunks);
     std::vector<dev_edge> edges;
@@ -1337,7 +1339,7 @@ static int route_dev_sync(pfnav_ctx *ctx, int layer, pfnav_route_layer &RL, rout
             ports[(size_t)ch * 64 + i] = d;
         }
     }
-    const bool retravel = D->layer != layer || D->built_for != (const void *)RL.chunks.data() || D->travel_rows != rows;
+    const bool retravel = D->layer != layer || D->generation != RL.generation || D->travel_rows != rows;
     if (!D->d_ports) {
         PF_CUDA(cudaMalloc(&D->d_ports, ports.size() * sizeof(dev_portal)));
         PF_CUDA(cudaMalloc(&D->d_nports, (size_t)chunks * 4));
@@ -1361,7 +1363,7 @@ static int route_dev_sync(pfnav_ctx *ctx, int layer, pfnav_route_layer &RL, rout
                                    cudaMemcpyHostToDevice));
         D->travel_rows = rows;
     }
-    D->layer = layer; D->epoch = ctx->map_epoch; D->built_for = (const void *)RL.chunks.data();
+    D->layer = layer; D->epoch = ctx->map_epoch; D->generation = RL.generation;
     return 0;
 }
 
