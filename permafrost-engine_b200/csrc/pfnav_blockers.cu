@@ -396,11 +396,7 @@ __global__ void k_blockers_tiles(const tile_op *__restrict__ ops, int nops, appl
 __device__ __forceinline__ int uf_find(volatile int *L, int x)
 {
     int p = L[x];
-    while (p != x) {            // path halving: links only ever move to an ancestor, so concurrent writers cannot break a chain
-        const int gp = L[p];
-        L[x] = gp;
-        x = gp; p = L[x];
-    }
+    while (p != x) { x = p; p = L[x]; }
     return x;
 }
 __device__ __forceinline__ void uf_unite(int *L, int a, int b)
@@ -449,25 +445,10 @@ __global__ void __launch_bounds__(256) k_chunks_finish(finish_args a)
     fchanged = __syncthreads_or(fchanged);
     if (changed) {
         // n_update_local_islands (nav.c:1213): 4-connected components of the passable tiles
-        // horizontal runs first: every thread labels its 16 consecutive tiles of a row with the start of their run ...
-        {
-            const int i0 = tid * 16;
-            int run = -1;
-            for (int j = 0; j < 16; j++) {
-                const int i = i0 + j;
-                if (L[i] < 0) { run = -1; continue; }
-                if (run < 0) run = i;
-                L[i] = run;
-            }
-        }
-        __syncthreads();
-        // ... runs that continue across a 16-tile boundary of the same row are joined, and a run is tied to the row above
-        // once per stretch of shared columns (where the stretch begins); everything else is implied
         for (int i = tid; i < 4096; i += 256) {
             if (L[i] < 0) continue;
-            const int c = i & 63;
-            if (c && !(c & 15) && L[i - 1] >= 0) uf_unite(L, i, i - 1);
-            if (i >= 64 && L[i - 64] >= 0 && (c == 0 || L[i - 1] < 0 || L[i - 65] < 0)) uf_unite(L, i, i - 64);
+            if ((i & 63) && L[i - 1] >= 0) uf_unite(L, i, i - 1);
+            if (i >= 64 && L[i - 64] >= 0) uf_unite(L, i, i - 64);
         }
         __syncthreads();
         for (int i = tid; i < 4096; i += 256) if (L[i] >= 0) { const int r = uf_find(L, i); L[i] = r; }
